@@ -1,0 +1,202 @@
+"""ctypes binding of libfyrox_b200.so (include/fyrox_b200.h) and libfyrox_scenegen.so.
+
+The libraries are built in-tree by ``fyrox_b200.build.build_all()`` (``__graft_entry__.build``).  There
+is no fallback: if the CUDA library is missing, importing the compute API raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_DIR = os.path.join(_HERE, "lib")
+LIB_PATH = os.path.join(LIB_DIR, "libfyrox_b200.so")
+SCENEGEN_PATH = os.path.join(LIB_DIR, "libfyrox_scenegen.so")
+
+FYX_NONE = 0xFFFFFFFF
+FYX_MAX_FRUSTA = 8
+FYX_MAX_BONES = 255
+
+# status codes
+FYX_OK = 0
+FYX_ERR_INVALID_ARGUMENT = -1
+FYX_ERR_CUDA = -2
+FYX_ERR_OUT_OF_MEMORY = -3
+FYX_ERR_NOT_AFFINE = -4
+FYX_ERR_TOPOLOGY = -5
+FYX_ERR_STATE = -6
+FYX_ERR_NCCL = -7
+FYX_ERR_UNSUPPORTED = -8
+
+# node flags
+NODE_VISIBILITY = 1 << 0
+NODE_ENABLED = 1 << 1
+NODE_FRUSTUM_CULLING = 1 << 2
+NODE_CAST_SHADOWS = 1 << 3
+NODE_ALIVE = 1 << 4
+NODE_RENDERABLE = 1 << 5
+NODE_GLOBAL_VISIBILITY = 1 << 8
+NODE_GLOBAL_ENABLED = 1 << 9
+NODE_REACHABLE = 1 << 10
+NODE_DEFAULT = NODE_VISIBILITY | NODE_ENABLED | NODE_FRUSTUM_CULLING | NODE_CAST_SHADOWS | NODE_ALIVE
+
+UPDATE_INCREMENTAL = 0
+UPDATE_ALL = 1
+PASS_SHADOW = 1
+
+u32p = C.POINTER(C.c_uint32)
+f32p = C.POINTER(C.c_float)
+
+
+class fyx_config(C.Structure):
+    _fields_ = [("struct_size", C.c_uint32), ("device", C.c_int32), ("stream", C.c_void_p), ("flags", C.c_uint32)]
+
+
+class fyx_frustum(C.Structure):
+    _fields_ = [("planes", (C.c_float * 4) * 6), ("corners", (C.c_float * 3) * 8)]
+
+
+class fyx_vertex_layout(C.Structure):
+    _fields_ = [
+        ("stride", C.c_uint32),
+        ("position_offset", C.c_uint32),
+        ("normal_offset", C.c_uint32),
+        ("bone_weights_offset", C.c_uint32),
+        ("bone_indices_offset", C.c_uint32),
+    ]
+
+
+class fyx_timings(C.Structure):
+    _fields_ = [(n, C.c_float) for n in ("upload_ms", "update_ms", "cull_ms", "palette_ms", "skin_ms", "readback_ms", "total_ms")]
+
+
+class fyx_frame_desc(C.Structure):
+    _fields_ = [
+        ("struct_size", C.c_uint32),
+        ("update_flags", C.c_uint32),
+        ("n_changed", C.c_uint32),
+        ("changed_idx", C.c_void_p),
+        ("changed_m16", C.c_void_p),
+        ("n_frusta", C.c_uint32),
+        ("frusta", C.POINTER(fyx_frustum)),
+        ("cam_mask", C.c_void_p),
+        ("pass_flags", C.c_void_p),
+        ("do_palettes", C.c_uint32),
+        ("do_skin", C.c_uint32),
+        ("readback_visible", C.c_uint32),
+    ]
+
+
+# every symbol include/fyrox_b200.h declares: name -> (restype, argtypes)
+ctx_p = C.c_void_p
+SYMBOLS = {
+    "fyx_abi_version": (C.c_uint32, []),
+    "fyx_create": (C.c_int32, [C.POINTER(fyx_config), C.POINTER(ctx_p)]),
+    "fyx_destroy": (None, [ctx_p]),
+    "fyx_last_error": (C.c_char_p, [ctx_p]),
+    "fyx_sync": (C.c_int32, [ctx_p]),
+    "fyx_host_alloc": (C.c_void_p, [C.c_size_t]),
+    "fyx_host_free": (None, [C.c_void_p]),
+    "fyx_frustum_from_view_projection_matrix": (C.c_int32, [f32p, C.POINTER(fyx_frustum)]),
+    "fyx_frustum_default": (None, [C.POINTER(fyx_frustum)]),
+    "fyx_mat4_mul": (None, [f32p, f32p, f32p]),
+    "fyx_set_topology": (C.c_int32, [ctx_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "fyx_set_local_matrices": (C.c_int32, [ctx_p, C.c_uint32, C.c_void_p, C.c_void_p]),
+    "fyx_set_flags": (C.c_int32, [ctx_p, C.c_uint32, C.c_void_p, C.c_void_p]),
+    "fyx_set_render_masks": (C.c_int32, [ctx_p, C.c_uint32, C.c_void_p, C.c_void_p]),
+    "fyx_set_local_aabbs": (C.c_int32, [ctx_p, C.c_uint32, C.c_void_p, C.c_void_p]),
+    "fyx_add_skinned_surface": (
+        C.c_int32,
+        [ctx_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.POINTER(fyx_vertex_layout), u32p],
+    ),
+    "fyx_commit_surfaces": (C.c_int32, [ctx_p]),
+    "fyx_update_transforms": (C.c_int32, [ctx_p, C.c_uint32]),
+    "fyx_cull": (C.c_int32, [ctx_p, C.c_uint32, C.POINTER(fyx_frustum), C.c_void_p, C.c_void_p]),
+    "fyx_update_and_cull": (C.c_int32, [ctx_p, C.c_uint32, C.c_uint32, C.POINTER(fyx_frustum), C.c_void_p, C.c_void_p]),
+    "fyx_get_visible": (C.c_int32, [ctx_p, C.c_uint32, C.POINTER(u32p), u32p]),
+    "fyx_get_visible_device": (C.c_int32, [ctx_p, C.c_uint32, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]),
+    "fyx_build_palettes": (C.c_int32, [ctx_p]),
+    "fyx_skin": (C.c_int32, [ctx_p]),
+    "fyx_render_prep": (C.c_int32, [ctx_p, C.POINTER(fyx_frame_desc)]),
+    "fyx_get_global_matrices": (C.c_int32, [ctx_p, C.c_uint32, C.c_void_p, C.c_void_p]),
+    "fyx_get_world_aabbs": (C.c_int32, [ctx_p, C.c_uint32, C.c_void_p, C.c_void_p]),
+    "fyx_get_global_flags": (C.c_int32, [ctx_p, C.c_uint32, C.c_void_p, C.c_void_p]),
+    "fyx_get_palette": (C.c_int32, [ctx_p, C.c_uint32, C.c_void_p]),
+    "fyx_get_skinned": (C.c_int32, [ctx_p, C.c_uint32, C.c_void_p, C.c_void_p]),
+    "fyx_get_skinned_device": (C.c_int32, [ctx_p, C.c_uint32, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]),
+    "fyx_get_timings": (C.c_int32, [ctx_p, C.POINTER(fyx_timings)]),
+    "fyx_kernel_launch_count": (C.c_uint64, [ctx_p]),
+    "fyx_comm_get_unique_id": (C.c_int32, [C.c_void_p]),
+    "fyx_comm_init": (C.c_int32, [ctx_p, C.c_int32, C.c_int32, C.c_void_p]),
+    "fyx_allgather_visible": (C.c_int32, [ctx_p]),
+    "fyx_get_visible_gathered": (C.c_int32, [ctx_p, C.c_uint32, C.POINTER(u32p), u32p]),
+    "fyx_get_visible_gathered_device": (C.c_int32, [ctx_p, C.c_uint32, C.POINTER(C.c_void_p), u32p]),
+}
+
+_lib = None
+_sg = None
+
+
+def load() -> C.CDLL:
+    """Load libfyrox_b200.so; raises (no fallback) if it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(there is no CPU fallback for the render-prep path)"
+            )
+        lib = C.CDLL(LIB_PATH, mode=C.RTLD_GLOBAL)
+        for name, (res, args) in SYMBOLS.items():
+            fn = getattr(lib, name)  # AttributeError if the library does not export a declared symbol
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+    return _lib
+
+
+class sg_config(C.Structure):
+    _fields_ = [
+        ("seed", C.c_uint64),
+        ("n_nodes", C.c_uint32),
+        ("n_units", C.c_uint32),
+        ("bones_per_unit", C.c_uint32),
+        ("verts_per_unit", C.c_uint32),
+        ("rank", C.c_int32),
+        ("nranks", C.c_int32),
+    ]
+
+
+SG_SYMBOLS = {
+    "sg_create": (C.c_void_p, [C.POINTER(sg_config)]),
+    "sg_free": (None, [C.c_void_p]),
+    "sg_capacity": (C.c_uint32, [C.c_void_p]),
+    "sg_n_renderable": (C.c_uint32, [C.c_void_p]),
+    "sg_parent": (u32p, [C.c_void_p]),
+    "sg_flags": (u32p, [C.c_void_p]),
+    "sg_render_mask": (u32p, [C.c_void_p]),
+    "sg_local_m16": (f32p, [C.c_void_p]),
+    "sg_local_aabb": (f32p, [C.c_void_p]),
+    "sg_global_index": (u32p, [C.c_void_p]),
+    "sg_n_units": (C.c_uint32, [C.c_void_p]),
+    "sg_unit_mesh_node": (C.c_uint32, [C.c_void_p, C.c_uint32]),
+    "sg_unit_bone_nodes": (u32p, [C.c_void_p, C.c_uint32]),
+    "sg_unit_inv_bind": (f32p, [C.c_void_p, C.c_uint32]),
+    "sg_unit_vertices": (None, [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]),
+    "sg_units_vertices": (None, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p]),
+    "sg_animate": (C.c_uint32, [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]),
+}
+
+
+def load_scenegen() -> C.CDLL:
+    global _sg
+    if _sg is None:
+        if not os.path.exists(SCENEGEN_PATH):
+            raise RuntimeError(f"{SCENEGEN_PATH} is missing: run __graft_entry__.build()")
+        lib = C.CDLL(SCENEGEN_PATH)
+        for name, (res, args) in SG_SYMBOLS.items():
+            fn = getattr(lib, name)
+            fn.restype = res
+            fn.argtypes = args
+        _sg = lib
+    return _sg

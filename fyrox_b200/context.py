@@ -1,0 +1,357 @@
+"""Thin numpy-facing wrapper over the C ABI (one method per ``fyx_*`` entry point).
+
+All compute happens in libfyrox_b200.so's sm_100a kernels; this file only marshals arguments.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence
+
+import numpy as np
+
+from . import _lib as L
+
+
+class FyxError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"fyx error {code}: {msg}")
+        self.code = code
+
+
+def _u32(a) -> Optional[np.ndarray]:
+    if a is None:
+        return None
+    return np.ascontiguousarray(a, dtype=np.uint32)
+
+
+def _f32(a) -> Optional[np.ndarray]:
+    if a is None:
+        return None
+    return np.ascontiguousarray(a, dtype=np.float32)
+
+
+def _ptr(a: Optional[np.ndarray]):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+ANIMATED_VERTEX_LAYOUT = L.fyx_vertex_layout(68, 0, 20, 48, 64)  # scene/mesh/vertex.rs:140-210
+
+
+def frustum_from_view_projection_matrix(vp) -> Optional[L.fyx_frustum]:
+    """Frustum::from_view_projection_matrix (fyrox-math/src/frustum.rs:54-82); None where the reference returns None."""
+    lib = L.load()
+    m = _f32(np.asarray(vp, dtype=np.float32).reshape(-1))
+    assert m.size == 16
+    f = L.fyx_frustum()
+    rc = lib.fyx_frustum_from_view_projection_matrix(m.ctypes.data_as(L.f32p), C.byref(f))
+    return f if rc == 0 else None
+
+
+def frustum_default() -> L.fyx_frustum:
+    f = L.fyx_frustum()
+    L.load().fyx_frustum_default(C.byref(f))
+    return f
+
+
+def mat4_mul(a, b) -> np.ndarray:
+    """Matrix4 * Matrix4 in nalgebra's order, on 16-float column-major arrays."""
+    a = _f32(np.asarray(a).reshape(-1))
+    b = _f32(np.asarray(b).reshape(-1))
+    out = np.empty(16, dtype=np.float32)
+    L.load().fyx_mat4_mul(a.ctypes.data_as(L.f32p), b.ctypes.data_as(L.f32p), out.ctypes.data_as(L.f32p))
+    return out
+
+
+def frustum_to_numpy(f: L.fyx_frustum):
+    planes = np.array([[f.planes[p][k] for k in range(4)] for p in range(6)], dtype=np.float32)
+    corners = np.array([[f.corners[i][k] for k in range(3)] for i in range(8)], dtype=np.float32)
+    return planes, corners
+
+
+def frustum_from_numpy(planes, corners) -> L.fyx_frustum:
+    f = L.fyx_frustum()
+    for p in range(6):
+        for k in range(4):
+            f.planes[p][k] = float(planes[p][k])
+    for i in range(8):
+        for k in range(3):
+            f.corners[i][k] = float(corners[i][k])
+    return f
+
+
+class PinnedBuffer:
+    """Page-locked host memory from fyx_host_alloc, viewed as a numpy array."""
+
+    def __init__(self, shape, dtype):
+        self._lib = L.load()
+        self.dtype = np.dtype(dtype)
+        self.shape = tuple(int(s) for s in (shape if isinstance(shape, (tuple, list)) else (shape,)))
+        nbytes = int(np.prod(self.shape)) * self.dtype.itemsize
+        self.ptr = self._lib.fyx_host_alloc(max(nbytes, 1))
+        if not self.ptr:
+            raise MemoryError("fyx_host_alloc failed")
+        buf = (C.c_char * max(nbytes, 1)).from_address(self.ptr)
+        self.array = np.frombuffer(buf, dtype=self.dtype, count=int(np.prod(self.shape))).reshape(self.shape)
+
+    def free(self):
+        if self.ptr:
+            self.array = None
+            self._lib.fyx_host_free(self.ptr)
+            self.ptr = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class Context:
+    """One fyx_ctx (one GPU)."""
+
+    def __init__(self, device: int = -1, stream: Optional[int] = None):
+        self._lib = L.load()
+        cfg = L.fyx_config(C.sizeof(L.fyx_config), device, stream, 0)
+        h = L.ctx_p()
+        rc = self._lib.fyx_create(C.byref(cfg), C.byref(h))
+        if rc != 0:
+            raise FyxError(rc, (self._lib.fyx_last_error(None) or b"").decode())
+        self._h = h
+        self.n_nodes = 0
+        self._surfaces = []  # (n_bones, n_verts)
+
+    # -- plumbing --
+    def _chk(self, rc: int):
+        if rc != 0:
+            raise FyxError(rc, (self._lib.fyx_last_error(self._h) or b"").decode())
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.fyx_destroy(self._h)
+            self._h = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def handle(self):
+        return self._h
+
+    def sync(self):
+        self._chk(self._lib.fyx_sync(self._h))
+
+    # -- scene description --
+    def set_topology(self, parent, flags=None, render_mask=None, local_aabb=None, root: int = 0, global_index=None):
+        parent = _u32(parent)
+        n = parent.size
+        flags, render_mask, global_index = _u32(flags), _u32(render_mask), _u32(global_index)
+        local_aabb = _f32(local_aabb)
+        for a, k in ((flags, 1), (render_mask, 1), (global_index, 1), (local_aabb, 6)):
+            assert a is None or a.size == n * k
+        self._chk(self._lib.fyx_set_topology(self._h, n, root, _ptr(parent), _ptr(flags), _ptr(render_mask), _ptr(local_aabb), _ptr(global_index)))
+        self.n_nodes = n
+
+    def set_local_matrices(self, m16, idx=None):
+        m16 = _f32(m16)
+        idx = _u32(idx)
+        count = m16.size // 16
+        assert idx is None or idx.size == count
+        self._chk(self._lib.fyx_set_local_matrices(self._h, count, _ptr(idx), _ptr(m16)))
+
+    def set_flags(self, flags, idx=None):
+        flags, idx = _u32(flags), _u32(idx)
+        self._chk(self._lib.fyx_set_flags(self._h, flags.size, _ptr(idx), _ptr(flags)))
+
+    def set_render_masks(self, masks, idx=None):
+        masks, idx = _u32(masks), _u32(idx)
+        self._chk(self._lib.fyx_set_render_masks(self._h, masks.size, _ptr(idx), _ptr(masks)))
+
+    def set_local_aabbs(self, aabbs, idx=None):
+        aabbs, idx = _f32(aabbs), _u32(idx)
+        self._chk(self._lib.fyx_set_local_aabbs(self._h, aabbs.size // 6, _ptr(idx), _ptr(aabbs)))
+
+    def add_skinned_surface(self, mesh_node: int, bone_nodes, inv_bind_m16, verts=None, layout: L.fyx_vertex_layout = None, n_verts: int = None) -> int:
+        bone_nodes = _u32(bone_nodes)
+        inv_bind = _f32(inv_bind_m16)
+        assert inv_bind.size == bone_nodes.size * 16
+        if verts is None:
+            n_verts, vptr, lay = 0, None, None
+        else:
+            lay = layout or ANIMATED_VERTEX_LAYOUT
+            if isinstance(verts, np.ndarray):
+                verts = np.ascontiguousarray(verts)
+                if n_verts is None:
+                    n_verts = verts.nbytes // lay.stride
+                vptr = verts.ctypes.data_as(C.c_void_p)
+            else:  # raw address
+                vptr = C.c_void_p(int(verts))
+                assert n_verts is not None
+        sid = C.c_uint32()
+        self._chk(
+            self._lib.fyx_add_skinned_surface(
+                self._h, mesh_node, bone_nodes.size, _ptr(bone_nodes), _ptr(inv_bind), n_verts, vptr, C.byref(lay) if lay is not None else None, C.byref(sid)
+            )
+        )
+        self._surfaces.append((int(bone_nodes.size), int(n_verts)))
+        return sid.value
+
+    def commit_surfaces(self):
+        self._chk(self._lib.fyx_commit_surfaces(self._h))
+
+    # -- per frame --
+    def update_transforms(self, flags: int = L.UPDATE_INCREMENTAL):
+        self._chk(self._lib.fyx_update_transforms(self._h, flags))
+
+    @staticmethod
+    def _frusta(frusta: Sequence[L.fyx_frustum]):
+        arr = (L.fyx_frustum * max(len(frusta), 1))()
+        for i, f in enumerate(frusta):
+            arr[i] = f
+        return arr
+
+    def cull(self, frusta, cam_mask=None, pass_flags=None):
+        arr = self._frusta(frusta)
+        cm, pf = _u32(cam_mask), _u32(pass_flags)
+        self._chk(self._lib.fyx_cull(self._h, len(frusta), arr, _ptr(cm), _ptr(pf)))
+
+    def update_and_cull(self, frusta, update_flags: int = L.UPDATE_INCREMENTAL, cam_mask=None, pass_flags=None):
+        arr = self._frusta(frusta)
+        cm, pf = _u32(cam_mask), _u32(pass_flags)
+        self._chk(self._lib.fyx_update_and_cull(self._h, update_flags, len(frusta), arr, _ptr(cm), _ptr(pf)))
+
+    def get_visible(self, frustum: int = 0) -> np.ndarray:
+        p = L.u32p()
+        n = C.c_uint32()
+        self._chk(self._lib.fyx_get_visible(self._h, frustum, C.byref(p), C.byref(n)))
+        if n.value == 0:
+            return np.empty(0, dtype=np.uint32)
+        return np.ctypeslib.as_array(p, shape=(n.value,)).copy()
+
+    def get_visible_device(self, frustum: int = 0):
+        d_idx, d_cnt = C.c_void_p(), C.c_void_p()
+        self._chk(self._lib.fyx_get_visible_device(self._h, frustum, C.byref(d_idx), C.byref(d_cnt)))
+        return d_idx.value, d_cnt.value
+
+    def build_palettes(self):
+        self._chk(self._lib.fyx_build_palettes(self._h))
+
+    def skin(self):
+        self._chk(self._lib.fyx_skin(self._h))
+
+    def render_prep(self, *, update_flags=L.UPDATE_INCREMENTAL, changed_m16=None, changed_idx=None, n_changed=None, frusta=(), cam_mask=None,
+                    pass_flags=None, do_palettes=True, do_skin=True, readback_visible=True):
+        """One frame (fyx_render_prep). changed_m16 / changed_idx may be numpy arrays or raw (pinned) addresses."""
+        d = L.fyx_frame_desc()
+        d.struct_size = C.sizeof(L.fyx_frame_desc)
+        d.update_flags = update_flags
+        keep = []
+        if changed_m16 is not None:
+            if isinstance(changed_m16, np.ndarray):
+                m = _f32(changed_m16)
+                keep.append(m)
+                d.changed_m16 = m.ctypes.data
+                d.n_changed = m.size // 16 if n_changed is None else n_changed
+            else:
+                d.changed_m16 = int(changed_m16)
+                d.n_changed = int(n_changed)
+            if changed_idx is not None:
+                if isinstance(changed_idx, np.ndarray):
+                    ix = _u32(changed_idx)
+                    keep.append(ix)
+                    d.changed_idx = ix.ctypes.data
+                else:
+                    d.changed_idx = int(changed_idx)
+        arr = self._frusta(frusta)
+        d.n_frusta = len(frusta)
+        d.frusta = C.cast(arr, C.POINTER(L.fyx_frustum))
+        cm, pf = _u32(cam_mask), _u32(pass_flags)
+        keep += [cm, pf, arr]
+        d.cam_mask = None if cm is None else cm.ctypes.data
+        d.pass_flags = None if pf is None else pf.ctypes.data
+        d.do_palettes = 1 if do_palettes else 0
+        d.do_skin = 1 if do_skin else 0
+        d.readback_visible = 1 if readback_visible else 0
+        self._chk(self._lib.fyx_render_prep(self._h, C.byref(d)))
+
+    # -- read-back --
+    def _gather(self, fn, idx, count, width, dtype):
+        idx = _u32(idx)
+        n = self.n_nodes if idx is None and count is None else (idx.size if idx is not None else count)
+        out = np.empty((n, width) if width > 1 else (n,), dtype=dtype)
+        self._chk(fn(self._h, n, _ptr(idx), out.ctypes.data_as(C.c_void_p)))
+        return out
+
+    def get_global_matrices(self, idx=None, count=None) -> np.ndarray:
+        return self._gather(self._lib.fyx_get_global_matrices, idx, count, 16, np.float32)
+
+    def get_world_aabbs(self, idx=None, count=None) -> np.ndarray:
+        return self._gather(self._lib.fyx_get_world_aabbs, idx, count, 6, np.float32)
+
+    def get_global_flags(self, idx=None, count=None) -> np.ndarray:
+        return self._gather(self._lib.fyx_get_global_flags, idx, count, 1, np.uint32)
+
+    def get_palette(self, surface_id: int) -> np.ndarray:
+        nb = self._surfaces[surface_id][0]
+        out = np.empty((nb, 16), dtype=np.float32)
+        self._chk(self._lib.fyx_get_palette(self._h, surface_id, out.ctypes.data_as(C.c_void_p)))
+        return out
+
+    def get_skinned(self, surface_id: int, normals: bool = True):
+        nv = self._surfaces[surface_id][1]
+        pos = np.empty((nv, 3), dtype=np.float32)
+        nrm = np.empty((nv, 3), dtype=np.float32) if normals else None
+        self._chk(self._lib.fyx_get_skinned(self._h, surface_id, pos.ctypes.data_as(C.c_void_p), None if nrm is None else nrm.ctypes.data_as(C.c_void_p)))
+        return pos, nrm
+
+    def get_skinned_device(self, surface_id: int):
+        p, n = C.c_void_p(), C.c_void_p()
+        self._chk(self._lib.fyx_get_skinned_device(self._h, surface_id, C.byref(p), C.byref(n)))
+        return p.value, n.value
+
+    def timings(self) -> dict:
+        t = L.fyx_timings()
+        self._chk(self._lib.fyx_get_timings(self._h, C.byref(t)))
+        return {n: getattr(t, n) for n, _ in L.fyx_timings._fields_}
+
+    def kernel_launch_count(self) -> int:
+        return int(self._lib.fyx_kernel_launch_count(self._h))
+
+    # -- multi-GPU --
+    @staticmethod
+    def comm_unique_id() -> bytes:
+        buf = C.create_string_buffer(128)
+        lib = L.load()
+        rc = lib.fyx_comm_get_unique_id(buf)
+        if rc != 0:
+            raise FyxError(rc, (lib.fyx_last_error(None) or b"").decode())
+        return buf.raw
+
+    def comm_init(self, nranks: int, rank: int, uid: bytes):
+        assert len(uid) == 128
+        self._chk(self._lib.fyx_comm_init(self._h, nranks, rank, C.create_string_buffer(uid, 128)))
+
+    def allgather_visible(self):
+        self._chk(self._lib.fyx_allgather_visible(self._h))
+
+    def get_visible_gathered(self, frustum: int = 0) -> np.ndarray:
+        p = L.u32p()
+        n = C.c_uint32()
+        self._chk(self._lib.fyx_get_visible_gathered(self._h, frustum, C.byref(p), C.byref(n)))
+        if n.value == 0:
+            return np.empty(0, dtype=np.uint32)
+        return np.ctypeslib.as_array(p, shape=(n.value,)).copy()
+
+    def get_visible_gathered_device(self, frustum: int = 0):
+        p = C.c_void_p()
+        n = C.c_uint32()
+        self._chk(self._lib.fyx_get_visible_gathered_device(self._h, frustum, C.byref(p), C.byref(n)))
+        return p.value, n.value

@@ -1,0 +1,1212 @@
+// fyx_api.cu — the C ABI of libfyrox_b200 (include/fyrox_b200.h): context, host-side bookkeeping
+// (slot ordering by hierarchy depth, staging, surface tables) and stream-ordered kernel launches.
+// No CPU fallback exists: every compute entry point launches the sm_100a kernels of fyx_kernels.cu.
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "fyx_internal.h"
+
+using namespace fyx;
+
+// --------------------------------------------------------------------------------------------
+// small utilities
+// --------------------------------------------------------------------------------------------
+namespace {
+
+thread_local std::string g_create_error;
+
+struct DevBuf {
+    void *p = nullptr;
+    size_t bytes = 0;
+    template <class T> T *as() const { return static_cast<T *>(p); }
+};
+
+struct Surface {
+    uint32_t mesh_node;
+    uint32_t n_bones;
+    uint32_t bone_off;  // first palette entry
+    uint32_t n_verts;
+    uint64_t vert_off;  // first vertex (multiple of 4)
+    std::vector<uint32_t> bones; // node indices
+};
+
+enum { EV_START = 0, EV_UPLOAD, EV_UPDATE, EV_CULL, EV_PALETTE, EV_SKIN, EV_READBACK, EV_COUNT };
+
+} // namespace
+
+struct fyx_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    std::string err;
+    uint64_t launches = 0;
+
+    // topology
+    uint32_t n_nodes = 0, n_slots = 0, root = FYX_NONE, n_renderable = 0;
+    std::vector<uint32_t> slot_of_node, node_of_slot, level_off;
+    NodeArrays a{};
+    DevBuf b_parent, b_flags, b_mask, b_gidx, b_L[3], b_G[3], b_la[3], b_wa[3], b_slot_of_node;
+    bool have_topology = false, updated_once = false;
+
+    // error word written by kernels
+    uint32_t *d_err = nullptr;
+    uint32_t *h_err = nullptr; // pinned
+
+    // staging (host pinned + device)
+    void *h_stage = nullptr;
+    size_t h_stage_bytes = 0;
+    DevBuf d_stage;
+
+    // cull outputs
+    CullParams cp{};
+    uint32_t *d_counts = nullptr;
+    uint32_t *h_counts = nullptr; // pinned, FYX_MAX_FRUSTA
+    DevBuf b_vis[FYX_MAX_FRUSTA];
+    uint32_t *h_vis[FYX_MAX_FRUSTA] = {};
+    size_t h_vis_cap[FYX_MAX_FRUSTA] = {};
+    uint32_t last_nf = 0;
+    bool counts_on_host = false, lists_on_host = false;
+
+    // skinning
+    std::vector<Surface> surfaces;
+    bool tables_dirty = false;
+    uint64_t n_verts_total = 0; // padded
+    uint64_t vert_cap = 0;
+    uint32_t n_entries = 0, entry_cap = 0;
+    DevBuf b_vpos, b_vnrm, b_vw, b_vidx, b_opos, b_onrm, b_ib[3], b_palette, b_bone_slot, b_tiles;
+    DevBuf b_fold_node, b_fold_begin, b_fold_bone;
+    uint32_t n_tiles = 0;
+    FoldArrays fold{};
+    SkinArrays sk{};
+    std::vector<uint8_t> skinned_node; // per node: has a skinned surface
+
+    // timing
+    cudaEvent_t ev[EV_COUNT] = {};
+    fyx_timings timings{};
+
+    // multi-GPU (fyx_comm.cu)
+    void *comm = nullptr;
+    int nranks = 1, rank = 0;
+    DevBuf b_counts_packed, b_counts_all, b_gath_pad[FYX_MAX_FRUSTA], b_gath[FYX_MAX_FRUSTA];
+    uint32_t *h_counts_all = nullptr; // pinned nranks*FYX_MAX_FRUSTA
+    uint32_t gath_count[FYX_MAX_FRUSTA] = {};
+    uint32_t *h_gath[FYX_MAX_FRUSTA] = {};
+    size_t h_gath_cap[FYX_MAX_FRUSTA] = {};
+};
+
+namespace {
+
+int32_t fail(fyx_ctx *c, int32_t code, const char *fmt, ...)
+{
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (c) c->err = buf;
+    else g_create_error = buf;
+    return code;
+}
+
+#define CU(call)                                                                                         \
+    do {                                                                                                 \
+        cudaError_t e__ = (call);                                                                        \
+        if (e__ != cudaSuccess)                                                                          \
+            return fail(c, e__ == cudaErrorMemoryAllocation ? FYX_ERR_OUT_OF_MEMORY : FYX_ERR_CUDA,      \
+                        "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__);    \
+    } while (0)
+
+int32_t dev_ensure(fyx_ctx *c, DevBuf &b, size_t bytes, bool keep = false)
+{
+    if (bytes <= b.bytes) return FYX_OK;
+    size_t nb = keep ? std::max(bytes, b.bytes + b.bytes / 2) : bytes;
+    nb = (nb + 255) & ~size_t(255);
+    void *np = nullptr;
+    CU(cudaMalloc(&np, nb));
+    if (keep && b.p && b.bytes) CU(cudaMemcpyAsync(np, b.p, b.bytes, cudaMemcpyDeviceToDevice, c->stream));
+    if (b.p) {
+        CU(cudaStreamSynchronize(c->stream));
+        cudaFree(b.p);
+    }
+    b.p = np;
+    b.bytes = nb;
+    return FYX_OK;
+}
+
+void dev_free(DevBuf &b)
+{
+    if (b.p) cudaFree(b.p);
+    b.p = nullptr;
+    b.bytes = 0;
+}
+
+int32_t host_stage_ensure(fyx_ctx *c, size_t bytes)
+{
+    if (bytes <= c->h_stage_bytes) return FYX_OK;
+    if (c->h_stage) {
+        CU(cudaStreamSynchronize(c->stream));
+        cudaFreeHost(c->h_stage);
+        c->h_stage = nullptr;
+        c->h_stage_bytes = 0;
+    }
+    size_t nb = (bytes + bytes / 4 + 4095) & ~size_t(4095);
+    CU(cudaHostAlloc(&c->h_stage, nb, cudaHostAllocDefault));
+    c->h_stage_bytes = nb;
+    return FYX_OK;
+}
+
+bool is_pinned(const void *p)
+{
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return at.type == cudaMemoryTypeHost;
+}
+
+// Host → device staging of one or two arrays.  `direct` lets pinned caller memory be DMA'd without
+// the bounce copy (only legal when the caller's buffer stays untouched until the next sync, i.e.
+// inside fyx_render_prep).  Returns device pointers inside d_stage.
+int32_t stage_to_device(fyx_ctx *c, const void *a0, size_t n0, const void *a1, size_t n1, bool direct, void **d0, void **d1)
+{
+    const size_t o1 = (n0 + 255) & ~size_t(255);
+    const size_t total = o1 + ((n1 + 255) & ~size_t(255));
+    int32_t rc = dev_ensure(c, c->d_stage, total);
+    if (rc) return rc;
+    char *dbase = c->d_stage.as<char>();
+    const void *src[2] = {a0, a1};
+    const size_t len[2] = {n0, n1};
+    const size_t off[2] = {0, o1};
+    bool need_bounce = false;
+    for (int i = 0; i < 2; ++i)
+        if (src[i] && len[i] && !(direct && is_pinned(src[i]))) need_bounce = true;
+    if (need_bounce) {
+        rc = host_stage_ensure(c, total);
+        if (rc) return rc;
+        // the previous use of the bounce buffer must have drained
+        CU(cudaStreamSynchronize(c->stream));
+    }
+    for (int i = 0; i < 2; ++i) {
+        if (!src[i] || !len[i]) continue;
+        const void *from = src[i];
+        if (!(direct && is_pinned(src[i]))) {
+            memcpy(static_cast<char *>(c->h_stage) + off[i], src[i], len[i]);
+            from = static_cast<char *>(c->h_stage) + off[i];
+        }
+        CU(cudaMemcpyAsync(dbase + off[i], from, len[i], cudaMemcpyHostToDevice, c->stream));
+    }
+    *d0 = (a0 && n0) ? dbase : nullptr;
+    if (d1) *d1 = (a1 && n1) ? dbase + o1 : nullptr;
+    return FYX_OK;
+}
+
+int32_t check_device_errors(fyx_ctx *c)
+{
+    // called right after a stream synchronisation; h_err was copied before it
+    const uint32_t e = *c->h_err;
+    if (!e) return FYX_OK;
+    *c->h_err = 0;
+    cudaMemsetAsync(c->d_err, 0, sizeof(uint32_t), c->stream);
+    if (e & E_NOT_AFFINE)
+        return fail(c, FYX_ERR_NOT_AFFINE, "a matrix with a bottom row other than (0,0,0,1) or a non-finite entry was skipped");
+    if (e & E_BAD_BONE_INDEX) return fail(c, FYX_ERR_INVALID_ARGUMENT, "a vertex references a bone index >= n_bones");
+    if (e & E_NONFINITE_VERTEX) return fail(c, FYX_ERR_INVALID_ARGUMENT, "a vertex position is not finite");
+    return FYX_OK;
+}
+
+int32_t sync_and_check(fyx_ctx *c)
+{
+    CU(cudaMemcpyAsync(c->h_err, c->d_err, sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    CU(cudaGetLastError());
+    return check_device_errors(c);
+}
+
+void rebuild_node_arrays(fyx_ctx *c)
+{
+    NodeArrays &a = c->a;
+    a.cap = c->n_slots;
+    a.parent = c->b_parent.as<uint32_t>();
+    a.flags = c->b_flags.as<uint32_t>();
+    a.mask = c->b_mask.as<uint32_t>();
+    a.gidx = c->b_gidx.as<uint32_t>();
+    for (int i = 0; i < 3; ++i) {
+        a.L[i] = c->b_L[i].as<float4>();
+        a.G[i] = c->b_G[i].as<float4>();
+        a.la[i] = c->b_la[i].as<float2>();
+        a.wa[i] = c->b_wa[i].as<float2>();
+    }
+}
+
+// Frustum → kernel parameter form
+void to_dev_frustum(const fyx_frustum &f, uint32_t cam_mask, uint32_t pass_flags, FrustumDev &d)
+{
+    for (int p = 0; p < 6; ++p) d.plane[p] = make_float4(f.planes[p][0], f.planes[p][1], f.planes[p][2], f.planes[p][3]);
+    bool finite = true;
+    for (int k = 0; k < 3; ++k) {
+        d.cmin[k] = f.corners[0][k];
+        d.cmax[k] = f.corners[0][k];
+    }
+    for (int i = 0; i < 8; ++i) {
+        d.cx[i] = f.corners[i][0];
+        d.cy[i] = f.corners[i][1];
+        d.cz[i] = f.corners[i][2];
+        for (int k = 0; k < 3; ++k) {
+            const float v = f.corners[i][k];
+            if (!std::isfinite(v)) finite = false;
+            if (v < d.cmin[k]) d.cmin[k] = v;
+            if (v > d.cmax[k]) d.cmax[k] = v;
+        }
+    }
+    if (!finite) // disable the conservative early-out; the exact test decides
+        for (int k = 0; k < 3; ++k) {
+            d.cmin[k] = -INFINITY;
+            d.cmax[k] = INFINITY;
+        }
+    d.cam_mask = cam_mask;
+    d.pass_flags = pass_flags;
+}
+
+int32_t prepare_cull(fyx_ctx *c, uint32_t nf, const fyx_frustum *fr, const uint32_t *cam_mask, const uint32_t *pass_flags)
+{
+    if (nf > FYX_MAX_FRUSTA) return fail(c, FYX_ERR_INVALID_ARGUMENT, "n_frusta %u > FYX_MAX_FRUSTA", nf);
+    if (nf && !fr) return fail(c, FYX_ERR_INVALID_ARGUMENT, "frusta is NULL");
+    c->cp.nf = (int)nf;
+    c->cp.counts = c->d_counts;
+    for (uint32_t f = 0; f < nf; ++f) {
+        to_dev_frustum(fr[f], cam_mask ? cam_mask[f] : 0xFFFFFFFFu, pass_flags ? pass_flags[f] : 0u, c->cp.f[f]);
+        // worst case every renderable node is visible
+        int32_t rc = dev_ensure(c, c->b_vis[f], sizeof(uint32_t) * std::max<size_t>(c->n_renderable, 1));
+        if (rc) return rc;
+        c->cp.out[f] = c->b_vis[f].as<uint32_t>();
+    }
+    CU(cudaMemsetAsync(c->d_counts, 0, sizeof(uint32_t) * kCountStride * FYX_MAX_FRUSTA, c->stream));
+    c->last_nf = nf;
+    c->counts_on_host = c->lists_on_host = false;
+    return FYX_OK;
+}
+
+int32_t run_update(fyx_ctx *c, uint32_t update_flags, const CullParams *cull)
+{
+    const bool all = (update_flags & FYX_UPDATE_ALL) || !c->updated_once;
+    const size_t nl = c->level_off.size() ? c->level_off.size() - 1 : 0;
+    for (size_t l = 0; l < nl; ++l) {
+        launch_update_level(c->stream, c->a, c->level_off[l], c->level_off[l + 1], all, cull);
+        c->launches += (c->level_off[l + 1] > c->level_off[l]);
+    }
+    if (c->fold.n) {
+        launch_fold_bones(c->stream, c->a, c->fold, cull);
+        c->launches++;
+    }
+    c->updated_once = true;
+    CU(cudaGetLastError());
+    return FYX_OK;
+}
+
+int32_t commit_surfaces(fyx_ctx *c);
+
+int32_t readback_visible(fyx_ctx *c)
+{
+    const uint32_t nf = c->last_nf;
+    if (!nf) return FYX_OK;
+    if (!c->counts_on_host) {
+        CU(cudaMemcpy2DAsync(c->h_counts, sizeof(uint32_t), c->d_counts, sizeof(uint32_t) * kCountStride, sizeof(uint32_t), nf,
+                             cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+        c->counts_on_host = true;
+    }
+    if (!c->lists_on_host) {
+        for (uint32_t f = 0; f < nf; ++f) {
+            const size_t n = c->h_counts[f];
+            if (n > c->h_vis_cap[f]) {
+                if (c->h_vis[f]) cudaFreeHost(c->h_vis[f]);
+                c->h_vis[f] = nullptr;
+                size_t cap = std::max<size_t>(1024, n + n / 2);
+                CU(cudaHostAlloc(reinterpret_cast<void **>(&c->h_vis[f]), cap * sizeof(uint32_t), cudaHostAllocDefault));
+                c->h_vis_cap[f] = cap;
+            }
+            if (n) CU(cudaMemcpyAsync(c->h_vis[f], c->b_vis[f].p, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+        }
+        CU(cudaStreamSynchronize(c->stream));
+        c->lists_on_host = true;
+    }
+    return FYX_OK;
+}
+
+} // namespace
+
+// --------------------------------------------------------------------------------------------
+// life cycle
+// --------------------------------------------------------------------------------------------
+extern "C" uint32_t fyx_abi_version(void) { return FYX_ABI_VERSION; }
+
+extern "C" const char *fyx_last_error(const fyx_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+extern "C" int32_t fyx_create(const fyx_config *cfg, fyx_ctx **out_ctx)
+{
+    fyx_ctx *c = nullptr; // for CU(): errors before the context exists go to the thread-local string
+    if (!out_ctx) return fail(nullptr, FYX_ERR_INVALID_ARGUMENT, "out_ctx is NULL");
+    *out_ctx = nullptr;
+    int dev = -1;
+    void *stream = nullptr;
+    if (cfg) {
+        if (cfg->struct_size < sizeof(fyx_config)) return fail(nullptr, FYX_ERR_INVALID_ARGUMENT, "fyx_config.struct_size too small");
+        dev = cfg->device;
+        stream = cfg->stream;
+    }
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+        return fail(nullptr, FYX_ERR_CUDA, "no CUDA device available (%s): libfyrox_b200 has no CPU fallback",
+                    e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+    if (dev < 0) CU(cudaGetDevice(&dev));
+    if (dev >= count) return fail(nullptr, FYX_ERR_INVALID_ARGUMENT, "device %d out of range (%d devices)", dev, count);
+    CU(cudaSetDevice(dev));
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, dev));
+    if (prop.major != 10)
+        return fail(nullptr, FYX_ERR_CUDA, "device %d is sm_%d%d; this library ships sm_100a code only", dev, prop.major, prop.minor);
+
+    fyx_ctx *ctx = new (std::nothrow) fyx_ctx();
+    if (!ctx) return fail(nullptr, FYX_ERR_OUT_OF_MEMORY, "host allocation failed");
+    c = ctx;
+    c->device = dev;
+    auto bail = [&](int32_t rc) {
+        g_create_error = c->err;
+        fyx_destroy(c);
+        return rc;
+    };
+#define CUB(call)                                                                                   \
+    do {                                                                                            \
+        cudaError_t e__ = (call);                                                                   \
+        if (e__ != cudaSuccess) {                                                                   \
+            fail(c, FYX_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(e__));                 \
+            return bail(FYX_ERR_CUDA);                                                              \
+        }                                                                                           \
+    } while (0)
+    if (stream) {
+        c->stream = static_cast<cudaStream_t>(stream);
+    } else {
+        CUB(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+        c->own_stream = true;
+    }
+    CUB(cudaMalloc(reinterpret_cast<void **>(&c->d_err), sizeof(uint32_t)));
+    CUB(cudaMemset(c->d_err, 0, sizeof(uint32_t)));
+    CUB(cudaHostAlloc(reinterpret_cast<void **>(&c->h_err), sizeof(uint32_t), cudaHostAllocDefault));
+    *c->h_err = 0;
+    CUB(cudaMalloc(reinterpret_cast<void **>(&c->d_counts), sizeof(uint32_t) * kCountStride * FYX_MAX_FRUSTA));
+    CUB(cudaMemset(c->d_counts, 0, sizeof(uint32_t) * kCountStride * FYX_MAX_FRUSTA));
+    CUB(cudaHostAlloc(reinterpret_cast<void **>(&c->h_counts), sizeof(uint32_t) * FYX_MAX_FRUSTA, cudaHostAllocDefault));
+    memset(c->h_counts, 0, sizeof(uint32_t) * FYX_MAX_FRUSTA);
+    for (int i = 0; i < EV_COUNT; ++i) CUB(cudaEventCreate(&c->ev[i]));
+#undef CUB
+    *out_ctx = c;
+    return FYX_OK;
+}
+
+static void fyx_comm_destroy_internal(fyx_ctx *c); // fyx_comm.inl
+
+extern "C" void fyx_destroy(fyx_ctx *c)
+{
+    if (!c) return;
+    cudaSetDevice(c->device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    fyx_comm_destroy_internal(c);
+    DevBuf *bufs[] = {&c->b_parent, &c->b_flags, &c->b_mask, &c->b_gidx, &c->b_slot_of_node, &c->d_stage, &c->b_vpos, &c->b_vnrm,
+                      &c->b_vw, &c->b_vidx, &c->b_opos, &c->b_onrm, &c->b_palette, &c->b_bone_slot, &c->b_tiles, &c->b_fold_node,
+                      &c->b_fold_begin, &c->b_fold_bone, &c->b_counts_packed, &c->b_counts_all};
+    for (DevBuf *b : bufs) dev_free(*b);
+    for (int i = 0; i < 3; ++i) {
+        dev_free(c->b_L[i]);
+        dev_free(c->b_G[i]);
+        dev_free(c->b_la[i]);
+        dev_free(c->b_wa[i]);
+        dev_free(c->b_ib[i]);
+    }
+    for (uint32_t f = 0; f < FYX_MAX_FRUSTA; ++f) {
+        dev_free(c->b_vis[f]);
+        dev_free(c->b_gath_pad[f]);
+        dev_free(c->b_gath[f]);
+        if (c->h_vis[f]) cudaFreeHost(c->h_vis[f]);
+        if (c->h_gath[f]) cudaFreeHost(c->h_gath[f]);
+    }
+    if (c->d_err) cudaFree(c->d_err);
+    if (c->h_err) cudaFreeHost(c->h_err);
+    if (c->d_counts) cudaFree(c->d_counts);
+    if (c->h_counts) cudaFreeHost(c->h_counts);
+    if (c->h_counts_all) cudaFreeHost(c->h_counts_all);
+    if (c->h_stage) cudaFreeHost(c->h_stage);
+    for (int i = 0; i < EV_COUNT; ++i)
+        if (c->ev[i]) cudaEventDestroy(c->ev[i]);
+    if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+extern "C" int32_t fyx_sync(fyx_ctx *c)
+{
+    if (!c) return FYX_ERR_INVALID_ARGUMENT;
+    return sync_and_check(c);
+}
+
+extern "C" void *fyx_host_alloc(size_t bytes)
+{
+    void *p = nullptr;
+    if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) {
+        cudaGetLastError();
+        return nullptr;
+    }
+    return p;
+}
+
+extern "C" void fyx_host_free(void *p)
+{
+    if (p) cudaFreeHost(p);
+}
+
+extern "C" uint64_t fyx_kernel_launch_count(const fyx_ctx *c) { return c ? c->launches : 0; }
+
+// --------------------------------------------------------------------------------------------
+// host-side math (tiny, per frustum).  Built with -ffp-contract=off.
+// --------------------------------------------------------------------------------------------
+namespace {
+inline float h_dot3(const float *u, const float *v) { return (u[0] * v[0] + u[1] * v[1]) + u[2] * v[2]; }
+inline void h_cross(const float *u, const float *v, float *o)
+{
+    o[0] = u[1] * v[2] - u[2] * v[1];
+    o[1] = u[2] * v[0] - u[0] * v[2];
+    o[2] = u[0] * v[1] - u[1] * v[0];
+}
+// Plane::from_abcd — fyrox-math/src/plane.rs:63-75
+bool h_plane(float a, float b, float c_, float d, float *out)
+{
+    const float n[3] = {a, b, c_};
+    const float len = std::sqrt(h_dot3(n, n));
+    if (len == 0.0f) return false;
+    const float coeff = 1.0f / len;
+    out[0] = a * coeff;
+    out[1] = b * coeff;
+    out[2] = c_ * coeff;
+    out[3] = d * coeff;
+    return true;
+}
+// Plane::intersection_point — plane.rs:94-102
+void h_isect(const float *a, const float *b, const float *c_, float *out)
+{
+    float bc[3], ca[3], ab[3];
+    h_cross(b, c_, bc);
+    const float f = -1.0f / h_dot3(a, bc);
+    h_cross(c_, a, ca);
+    h_cross(a, b, ab);
+    for (int i = 0; i < 3; ++i) out[i] = ((bc[i] * a[3] + ca[i] * b[3]) + ab[i] * c_[3]) * f;
+}
+} // namespace
+
+extern "C" int32_t fyx_frustum_from_view_projection_matrix(const float m[16], fyx_frustum *out)
+{
+    if (!m || !out) return FYX_ERR_INVALID_ARGUMENT;
+    float(*p)[4] = out->planes; // frustum.rs:55-68; m[] is nalgebra's linear (column-major) index
+    if (!h_plane(m[3] + m[0], m[7] + m[4], m[11] + m[8], m[15] + m[12], p[0])) return FYX_ERR_INVALID_ARGUMENT;
+    if (!h_plane(m[3] - m[0], m[7] - m[4], m[11] - m[8], m[15] - m[12], p[1])) return FYX_ERR_INVALID_ARGUMENT;
+    if (!h_plane(m[3] - m[1], m[7] - m[5], m[11] - m[9], m[15] - m[13], p[2])) return FYX_ERR_INVALID_ARGUMENT;
+    if (!h_plane(m[3] + m[1], m[7] + m[5], m[11] + m[9], m[15] + m[13], p[3])) return FYX_ERR_INVALID_ARGUMENT;
+    if (!h_plane(m[3] - m[2], m[7] - m[6], m[11] - m[10], m[15] - m[14], p[4])) return FYX_ERR_INVALID_ARGUMENT;
+    if (!h_plane(m[3] + m[2], m[7] + m[6], m[11] + m[10], m[15] + m[14], p[5])) return FYX_ERR_INVALID_ARGUMENT;
+    enum { L = 0, R = 1, T = 2, B = 3, F = 4, N = 5 }; // frustum.rs:70-79
+    h_isect(p[L], p[T], p[F], out->corners[0]);
+    h_isect(p[L], p[B], p[F], out->corners[1]);
+    h_isect(p[R], p[B], p[F], out->corners[2]);
+    h_isect(p[R], p[T], p[F], out->corners[3]);
+    h_isect(p[L], p[T], p[N], out->corners[4]);
+    h_isect(p[L], p[B], p[N], out->corners[5]);
+    h_isect(p[R], p[B], p[N], out->corners[6]);
+    h_isect(p[R], p[T], p[N], out->corners[7]);
+    return FYX_OK;
+}
+
+extern "C" void fyx_frustum_default(fyx_frustum *out)
+{
+    // Frustum::default: new_perspective(1.0, FRAC_PI_2, 0.01, 1024.0) (frustum.rs:32-43)
+    float m[16] = {0};
+    const float znear = 0.01f, zfar = 1024.0f;
+    const float m22 = 1.0f / std::tan(1.57079632679489661923f / 2.0f);
+    m[5] = m22;
+    m[0] = m22 / 1.0f;
+    m[10] = (zfar + znear) / (znear - zfar);
+    m[14] = zfar * znear * 2.0f / (znear - zfar);
+    m[11] = -1.0f;
+    fyx_frustum_from_view_projection_matrix(m, out);
+}
+
+extern "C" void fyx_mat4_mul(const float a[16], const float b[16], float out[16])
+{
+    float r[16];
+    for (int j = 0; j < 4; ++j)
+        for (int i = 0; i < 4; ++i) {
+            float y = a[i] * b[j * 4];
+            y = y + a[4 + i] * b[j * 4 + 1];
+            y = y + a[8 + i] * b[j * 4 + 2];
+            y = y + a[12 + i] * b[j * 4 + 3];
+            r[j * 4 + i] = y;
+        }
+    memcpy(out, r, sizeof r);
+}
+
+// --------------------------------------------------------------------------------------------
+// scene description
+// --------------------------------------------------------------------------------------------
+extern "C" int32_t fyx_set_topology(fyx_ctx *c, uint32_t capacity, uint32_t root, const uint32_t *parent, const uint32_t *flags,
+                                    const uint32_t *render_mask, const float *local_aabb, const uint32_t *global_index)
+{
+    if (!c) return FYX_ERR_INVALID_ARGUMENT;
+    if (capacity && !parent) return fail(c, FYX_ERR_INVALID_ARGUMENT, "parent is NULL");
+    if (capacity == FYX_NONE) return fail(c, FYX_ERR_INVALID_ARGUMENT, "capacity too large");
+    CU(cudaSetDevice(c->device));
+    const uint32_t def_flags = FYX_NODE_VISIBILITY | FYX_NODE_ENABLED | FYX_NODE_FRUSTUM_CULLING | FYX_NODE_CAST_SHADOWS | FYX_NODE_ALIVE;
+    auto fl = [&](uint32_t i) { return flags ? (flags[i] & FYX_NODE_INPUT_MASK) : def_flags; };
+    auto alive = [&](uint32_t i) { return i < capacity && (fl(i) & FYX_NODE_ALIVE); };
+
+    // depth of every alive node (parent chains; a dead / out-of-range parent counts as "no parent",
+    // like Pool::try_borrow failing in graph/mod.rs:1210)
+    std::vector<int32_t> depth(capacity, -1);
+    std::vector<uint32_t> path;
+    uint32_t max_depth = 0;
+    for (uint32_t i = 0; i < capacity; ++i) {
+        if (!alive(i) || depth[i] >= 0) continue;
+        path.clear();
+        uint32_t n = i;
+        int32_t base = -1;
+        while (true) {
+            if (depth[n] >= 0) { base = depth[n]; break; }
+            if (depth[n] == -2) return fail(c, FYX_ERR_TOPOLOGY, "cycle in parent[] through node %u", n);
+            depth[n] = -2;
+            path.push_back(n);
+            const uint32_t p = parent[n];
+            if (p == FYX_NONE || !alive(p)) break;
+            n = p;
+        }
+        for (size_t k = path.size(); k-- > 0;) {
+            base += 1;
+            depth[path[k]] = base;
+            max_depth = std::max<uint32_t>(max_depth, (uint32_t)base);
+        }
+    }
+    // counting sort by depth, stable in node index
+    std::vector<uint32_t> level_off(capacity ? max_depth + 2 : 1, 0);
+    uint32_t n_slots = 0;
+    for (uint32_t i = 0; i < capacity; ++i)
+        if (alive(i)) { level_off[depth[i] + 1]++; n_slots++; }
+    for (size_t l = 1; l < level_off.size(); ++l) level_off[l] += level_off[l - 1];
+    std::vector<uint32_t> cursor(level_off.begin(), level_off.end());
+    std::vector<uint32_t> slot_of_node(capacity, FYX_NONE), node_of_slot(n_slots);
+    for (uint32_t i = 0; i < capacity; ++i)
+        if (alive(i)) {
+            const uint32_t s = cursor[depth[i]]++;
+            slot_of_node[i] = s;
+            node_of_slot[s] = i;
+        }
+
+    // slot-ordered host columns
+    std::vector<uint32_t> h_parent(n_slots), h_flags(n_slots), h_mask(n_slots), h_gidx(n_slots);
+    std::vector<float2> h_la[3];
+    for (auto &v : h_la) v.resize(n_slots);
+    uint32_t n_renderable = 0;
+    for (uint32_t s = 0; s < n_slots; ++s) {
+        const uint32_t i = node_of_slot[s];
+        const uint32_t p = parent[i];
+        h_parent[s] = (p != FYX_NONE && alive(p)) ? slot_of_node[p] : FYX_NONE;
+        uint32_t f = fl(i) | F_DIRTY_SELF;
+        if (i == root) f |= F_ROOT;
+        if (i < c->skinned_node.size() && c->skinned_node[i]) f |= F_SKINNED;
+        h_flags[s] = f;
+        n_renderable += (f & FYX_NODE_RENDERABLE) ? 1u : 0u;
+        h_mask[s] = render_mask ? render_mask[i] : 0xFFFFFFFFu;
+        h_gidx[s] = global_index ? global_index[i] : i;
+        if (local_aabb) {
+            const float *b = local_aabb + 6 * (size_t)i;
+            h_la[0][s] = make_float2(b[0], b[3]);
+            h_la[1][s] = make_float2(b[1], b[4]);
+            h_la[2][s] = make_float2(b[2], b[5]);
+        } else { // AxisAlignedBoundingBox::unit(), scene/base.rs:733-735
+            h_la[0][s] = h_la[1][s] = h_la[2][s] = make_float2(-0.5f, 0.5f);
+        }
+    }
+
+    // device columns
+    int32_t rc;
+    const size_t n = std::max<uint32_t>(n_slots, 1);
+    if ((rc = dev_ensure(c, c->b_parent, n * 4))) return rc;
+    if ((rc = dev_ensure(c, c->b_flags, n * 4))) return rc;
+    if ((rc = dev_ensure(c, c->b_mask, n * 4))) return rc;
+    if ((rc = dev_ensure(c, c->b_gidx, n * 4))) return rc;
+    if ((rc = dev_ensure(c, c->b_slot_of_node, std::max<size_t>(capacity, 1) * 4))) return rc;
+    for (int k = 0; k < 3; ++k) {
+        if ((rc = dev_ensure(c, c->b_L[k], n * sizeof(float4)))) return rc;
+        if ((rc = dev_ensure(c, c->b_G[k], n * sizeof(float4)))) return rc;
+        if ((rc = dev_ensure(c, c->b_la[k], n * sizeof(float2)))) return rc;
+        if ((rc = dev_ensure(c, c->b_wa[k], n * sizeof(float2)))) return rc;
+    }
+    CU(cudaStreamSynchronize(c->stream));
+    if (n_slots) {
+        CU(cudaMemcpy(c->b_parent.p, h_parent.data(), n_slots * 4, cudaMemcpyHostToDevice));
+        CU(cudaMemcpy(c->b_flags.p, h_flags.data(), n_slots * 4, cudaMemcpyHostToDevice));
+        CU(cudaMemcpy(c->b_mask.p, h_mask.data(), n_slots * 4, cudaMemcpyHostToDevice));
+        CU(cudaMemcpy(c->b_gidx.p, h_gidx.data(), n_slots * 4, cudaMemcpyHostToDevice));
+        // local / global matrices start as identity rows; world boxes as AABB::default()
+        std::vector<float4> rows(n_slots);
+        const float4 idr[3] = {make_float4(1, 0, 0, 0), make_float4(0, 1, 0, 0), make_float4(0, 0, 1, 0)};
+        for (int k = 0; k < 3; ++k) {
+            std::fill(rows.begin(), rows.end(), idr[k]);
+            CU(cudaMemcpy(c->b_L[k].p, rows.data(), n_slots * sizeof(float4), cudaMemcpyHostToDevice));
+            CU(cudaMemcpy(c->b_G[k].p, rows.data(), n_slots * sizeof(float4), cudaMemcpyHostToDevice));
+            CU(cudaMemcpy(c->b_la[k].p, h_la[k].data(), n_slots * sizeof(float2), cudaMemcpyHostToDevice));
+        }
+        std::vector<float2> wdef(n_slots, make_float2(3.402823466e38f, -3.402823466e38f));
+        for (int k = 0; k < 3; ++k) CU(cudaMemcpy(c->b_wa[k].p, wdef.data(), n_slots * sizeof(float2), cudaMemcpyHostToDevice));
+    }
+    if (capacity) CU(cudaMemcpy(c->b_slot_of_node.p, slot_of_node.data(), (size_t)capacity * 4, cudaMemcpyHostToDevice));
+
+    c->n_nodes = capacity;
+    c->n_slots = n_slots;
+    c->root = root;
+    c->n_renderable = n_renderable;
+    c->slot_of_node.swap(slot_of_node);
+    c->node_of_slot.swap(node_of_slot);
+    c->level_off.swap(level_off);
+    c->have_topology = true;
+    c->updated_once = false;
+    c->tables_dirty = true; // bone slots depend on the slot order
+    rebuild_node_arrays(c);
+    return FYX_OK;
+}
+
+extern "C" int32_t fyx_set_local_matrices(fyx_ctx *c, uint32_t count, const uint32_t *idx, const float *m16)
+{
+    if (!c) return FYX_ERR_INVALID_ARGUMENT;
+    if (!c->have_topology) return fail(c, FYX_ERR_STATE, "fyx_set_topology has not been called");
+    if (!count) return FYX_OK;
+    if (!m16) return fail(c, FYX_ERR_INVALID_ARGUMENT, "m16 is NULL");
+    CU(cudaSetDevice(c->device));
+    void *d_m = nullptr, *d_i = nullptr;
+    int32_t rc = stage_to_device(c, m16, (size_t)count * 64, idx, idx ? (size_t)count * 4 : 0, false, &d_m, &d_i);
+    if (rc) return rc;
+    launch_scatter_locals(c->stream, c->a, count, static_cast<const uint32_t *>(d_i), static_cast<const float *>(d_m),
+                          c->b_slot_of_node.as<uint32_t>(), c->n_nodes, c->d_err);
+    c->launches++;
+    CU(cudaGetLastError());
+    return FYX_OK;
+}
+
+static int32_t set_u32_column(fyx_ctx *c, uint32_t count, const uint32_t *idx, const uint32_t *val, int mode)
+{
+    if (!c) return FYX_ERR_INVALID_ARGUMENT;
+    if (!c->have_topology) return fail(c, FYX_ERR_STATE, "fyx_set_topology has not been called");
+    if (!count) return FYX_OK;
+    if (!val) return fail(c, FYX_ERR_INVALID_ARGUMENT, "values are NULL");
+    CU(cudaSetDevice(c->device));
+    void *d_v = nullptr, *d_i = nullptr;
+    int32_t rc = stage_to_device(c, val, (size_t)count * 4, idx, idx ? (size_t)count * 4 : 0, false, &d_v, &d_i);
+    if (rc) return rc;
+    launch_scatter_u32(c->stream, mode == 0 ? c->a.flags : c->a.mask, nullptr, count, static_cast<const uint32_t *>(d_i),
+                       static_cast<const uint32_t *>(d_v), c->b_slot_of_node.as<uint32_t>(), c->n_nodes, mode);
+    c->launches++;
+    CU(cudaGetLastError());
+    return FYX_OK;
+}
+
+extern "C" int32_t fyx_set_flags(fyx_ctx *c, uint32_t count, const uint32_t *idx, const uint32_t *flags)
+{
+    return set_u32_column(c, count, idx, flags, 0);
+}
+
+extern "C" int32_t fyx_set_render_masks(fyx_ctx *c, uint32_t count, const uint32_t *idx, const uint32_t *mask)
+{
+    return set_u32_column(c, count, idx, mask, 1);
+}
+
+extern "C" int32_t fyx_set_local_aabbs(fyx_ctx *c, uint32_t count, const uint32_t *idx, const float *aabb)
+{
+    if (!c) return FYX_ERR_INVALID_ARGUMENT;
+    if (!c->have_topology) return fail(c, FYX_ERR_STATE, "fyx_set_topology has not been called");
+    if (!count) return FYX_OK;
+    if (!aabb) return fail(c, FYX_ERR_INVALID_ARGUMENT, "aabb is NULL");
+    CU(cudaSetDevice(c->device));
+    void *d_v = nullptr, *d_i = nullptr;
+    int32_t rc = stage_to_device(c, aabb, (size_t)count * 24, idx, idx ? (size_t)count * 4 : 0, false, &d_v, &d_i);
+    if (rc) return rc;
+    launch_scatter_aabbs(c->stream, c->a, count, static_cast<const uint32_t *>(d_i), static_cast<const float *>(d_v),
+                         c->b_slot_of_node.as<uint32_t>(), c->n_nodes);
+    c->launches++;
+    CU(cudaGetLastError());
+    return FYX_OK;
+}
+
+// --------------------------------------------------------------------------------------------
+// skinned surfaces
+// --------------------------------------------------------------------------------------------
+namespace {
+
+int32_t grow_vertex_streams(fyx_ctx *c, uint64_t need)
+{
+    if (need <= c->vert_cap) return FYX_OK;
+    int32_t rc;
+    if ((rc = dev_ensure(c, c->b_vpos, need * 12, true))) return rc;
+    if ((rc = dev_ensure(c, c->b_vnrm, need * 12, true))) return rc;
+    if ((rc = dev_ensure(c, c->b_vw, need * 16, true))) return rc;
+    if ((rc = dev_ensure(c, c->b_vidx, need * 4, true))) return rc;
+    if ((rc = dev_ensure(c, c->b_opos, need * 12, true))) return rc;
+    if ((rc = dev_ensure(c, c->b_onrm, need * 12, true))) return rc;
+    c->vert_cap = std::min<uint64_t>({c->b_vpos.bytes / 12, c->b_vnrm.bytes / 12, c->b_vw.bytes / 16, c->b_vidx.bytes / 4,
+                                      c->b_opos.bytes / 12, c->b_onrm.bytes / 12});
+    return FYX_OK;
+}
+
+int32_t grow_bone_tables(fyx_ctx *c, uint32_t need)
+{
+    if (need <= c->entry_cap) return FYX_OK;
+    int32_t rc;
+    for (int k = 0; k < 3; ++k)
+        if ((rc = dev_ensure(c, c->b_ib[k], (size_t)need * 16, true))) return rc;
+    if ((rc = dev_ensure(c, c->b_palette, (size_t)need * 64, true))) return rc;
+    c->entry_cap = (uint32_t)std::min<size_t>({c->b_ib[0].bytes / 16, c->b_ib[1].bytes / 16, c->b_ib[2].bytes / 16, c->b_palette.bytes / 64});
+    return FYX_OK;
+}
+
+void rebuild_skin_arrays(fyx_ctx *c)
+{
+    SkinArrays &sk = c->sk;
+    sk.n_entries = c->n_entries;
+    sk.bone_slot = c->b_bone_slot.as<uint32_t>();
+    for (int k = 0; k < 3; ++k) sk.ib[k] = c->b_ib[k].as<float4>();
+    sk.palette = c->b_palette.as<float>();
+    sk.vpos = c->b_vpos.as<float>();
+    sk.vnrm = c->b_vnrm.as<float>();
+    sk.vw = c->b_vw.as<float4>();
+    sk.vidx = c->b_vidx.as<uint32_t>();
+    sk.opos = c->b_opos.as<float>();
+    sk.onrm = c->b_onrm.as<float>();
+}
+
+constexpr uint32_t kTileQuads = 1024; // 4096 vertices per CTA
+
+// (re)build bone-slot, fold and tile tables from the host-side surface list
+int32_t commit_surfaces(fyx_ctx *c)
+{
+    if (!c->tables_dirty) return FYX_OK;
+    if (!c->have_topology) return fail(c, FYX_ERR_STATE, "fyx_set_topology has not been called");
+    const size_t ns = c->surfaces.size();
+    std::vector<uint32_t> bone_slot(c->n_entries);
+    std::vector<SkinTile> tiles;
+    // per skinned node: bones of all its surfaces in surface order
+    std::vector<uint32_t> fold_node, fold_begin, fold_bone;
+    std::vector<int64_t> fold_of_node; // node → index in fold_node, built in first-surface order
+    std::vector<std::vector<uint32_t>> per_node_bones;
+    fold_of_node.assign(c->n_nodes, -1);
+    for (size_t s = 0; s < ns; ++s) {
+        const Surface &sf = c->surfaces[s];
+        for (uint32_t b = 0; b < sf.n_bones; ++b) {
+            const uint32_t bn = sf.bones[b];
+            bone_slot[sf.bone_off + b] = (bn < c->n_nodes) ? c->slot_of_node[bn] : FYX_NONE;
+        }
+        if (sf.n_verts) {
+            const uint32_t quads = (sf.n_verts + 3) / 4;
+            const uint32_t nt = (quads + kTileQuads - 1) / kTileQuads;
+            const uint32_t per = (quads + nt - 1) / nt;
+            for (uint32_t t = 0; t < nt; ++t) {
+                SkinTile tl;
+                tl.bone_off = sf.bone_off;
+                tl.n_bones = sf.n_bones;
+                tl.quad_start = (uint32_t)(sf.vert_off / 4 + (uint64_t)t * per);
+                tl.n_quads = std::min(per, quads - t * per);
+                tiles.push_back(tl);
+            }
+        }
+        if (sf.n_bones && sf.mesh_node < c->n_nodes && c->slot_of_node[sf.mesh_node] != FYX_NONE) {
+            int64_t &fi = fold_of_node[sf.mesh_node];
+            if (fi < 0) {
+                fi = (int64_t)per_node_bones.size();
+                per_node_bones.emplace_back();
+                fold_node.push_back(c->slot_of_node[sf.mesh_node]);
+            }
+            for (uint32_t b = 0; b < sf.n_bones; ++b) per_node_bones[fi].push_back(bone_slot[sf.bone_off + b]);
+        }
+    }
+    fold_begin.push_back(0);
+    for (auto &v : per_node_bones) {
+        fold_bone.insert(fold_bone.end(), v.begin(), v.end());
+        fold_begin.push_back((uint32_t)fold_bone.size());
+    }
+    int32_t rc;
+    if ((rc = dev_ensure(c, c->b_bone_slot, std::max<size_t>(bone_slot.size(), 1) * 4))) return rc;
+    if ((rc = dev_ensure(c, c->b_tiles, std::max<size_t>(tiles.size(), 1) * sizeof(SkinTile)))) return rc;
+    if ((rc = dev_ensure(c, c->b_fold_node, std::max<size_t>(fold_node.size(), 1) * 4))) return rc;
+    if ((rc = dev_ensure(c, c->b_fold_begin, fold_begin.size() * 4))) return rc;
+    if ((rc = dev_ensure(c, c->b_fold_bone, std::max<size_t>(fold_bone.size(), 1) * 4))) return rc;
+    CU(cudaStreamSynchronize(c->stream));
+    if (!bone_slot.empty()) CU(cudaMemcpy(c->b_bone_slot.p, bone_slot.data(), bone_slot.size() * 4, cudaMemcpyHostToDevice));
+    if (!tiles.empty()) CU(cudaMemcpy(c->b_tiles.p, tiles.data(), tiles.size() * sizeof(SkinTile), cudaMemcpyHostToDevice));
+    if (!fold_node.empty()) CU(cudaMemcpy(c->b_fold_node.p, fold_node.data(), fold_node.size() * 4, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(c->b_fold_begin.p, fold_begin.data(), fold_begin.size() * 4, cudaMemcpyHostToDevice));
+    if (!fold_bone.empty()) CU(cudaMemcpy(c->b_fold_bone.p, fold_bone.data(), fold_bone.size() * 4, cudaMemcpyHostToDevice));
+    c->n_tiles = (uint32_t)tiles.size();
+    c->fold.n = (uint32_t)fold_node.size();
+    c->fold.node_slot = c->b_fold_node.as<uint32_t>();
+    c->fold.bone_begin = c->b_fold_begin.as<uint32_t>();
+    c->fold.bone_slot = c->b_fold_bone.as<uint32_t>();
+    rebuild_skin_arrays(c);
+    c->tables_dirty = false;
+    return FYX_OK;
+}
+
+} // namespace
+
+extern "C" int32_t fyx_add_skinned_surface(fyx_ctx *c, uint32_t mesh_node, uint32_t n_bones, const uint32_t *bone_nodes,
+                                           const float *inv_bind, uint32_t n_verts, const void *verts,
+                                           const fyx_vertex_layout *layout, uint32_t *out_id)
+{
+    if (!c) return FYX_ERR_INVALID_ARGUMENT;
+    if (!c->have_topology) return fail(c, FYX_ERR_STATE, "fyx_set_topology has not been called");
+    if (n_bones > FYX_MAX_BONES) return fail(c, FYX_ERR_INVALID_ARGUMENT, "n_bones %u > %u", n_bones, FYX_MAX_BONES);
+    if (n_bones && (!bone_nodes || !inv_bind)) return fail(c, FYX_ERR_INVALID_ARGUMENT, "bone arrays are NULL");
+    if (n_verts && (!verts || !layout)) return fail(c, FYX_ERR_INVALID_ARGUMENT, "verts/layout are NULL");
+    if (n_verts && !n_bones) return fail(c, FYX_ERR_INVALID_ARGUMENT, "a skinned surface needs at least one bone");
+    if (n_verts) {
+        const fyx_vertex_layout &l = *layout;
+        if (l.stride % 4 || l.position_offset % 4 || l.normal_offset % 4 || l.bone_weights_offset % 4 || l.bone_indices_offset % 4)
+            return fail(c, FYX_ERR_UNSUPPORTED, "vertex stride and attribute offsets must be multiples of 4");
+        if (l.position_offset + 12 > l.stride || l.normal_offset + 12 > l.stride || l.bone_weights_offset + 16 > l.stride ||
+            l.bone_indices_offset + 4 > l.stride)
+            return fail(c, FYX_ERR_INVALID_ARGUMENT, "vertex attribute outside the vertex");
+    }
+    CU(cudaSetDevice(c->device));
+    Surface sf;
+    sf.mesh_node = mesh_node;
+    sf.n_bones = n_bones;
+    sf.bone_off = c->n_entries;
+    sf.n_verts = n_verts;
+    sf.vert_off = c->n_verts_total;
+    sf.bones.assign(bone_nodes, bone_nodes + n_bones);
+    int32_t rc;
+    if ((rc = grow_bone_tables(c, c->n_entries + n_bones))) return rc;
+    const uint64_t padded = ((uint64_t)n_verts + 3) & ~uint64_t(3);
+    if ((rc = grow_vertex_streams(c, c->n_verts_total + padded))) return rc;
+    rebuild_skin_arrays(c);
+    if (n_bones) {
+        void *d_m = nullptr;
+        if ((rc = stage_to_device(c, inv_bind, (size_t)n_bones * 64, nullptr, 0, false, &d_m, nullptr))) return rc;
+        launch_ib_rows(c->stream, n_bones, static_cast<const float *>(d_m), c->b_ib[0].as<float4>() + sf.bone_off,
+                       c->b_ib[1].as<float4>() + sf.bone_off, c->b_ib[2].as<float4>() + sf.bone_off, c->d_err);
+        c->launches++;
+    }
+    if (n_verts) {
+        void *d_v = nullptr;
+        if ((rc = stage_to_device(c, verts, (size_t)n_verts * layout->stride, nullptr, 0, false, &d_v, nullptr))) return rc;
+        launch_deinterleave(c->stream, n_verts, static_cast<const unsigned char *>(d_v), *layout, n_bones,
+                            c->b_vpos.as<float>() + 3 * sf.vert_off, c->b_vnrm.as<float>() + 3 * sf.vert_off,
+                            c->b_vw.as<float4>() + sf.vert_off, c->b_vidx.as<uint32_t>() + sf.vert_off, c->d_err);
+        c->launches++;
+    }
+    CU(cudaGetLastError());
+    c->n_entries += n_bones;
+    c->n_verts_total += padded;
+    if (n_bones && mesh_node < c->n_nodes) {
+        if (c->skinned_node.size() < c->n_nodes) c->skinned_node.resize(c->n_nodes, 0);
+        if (!c->skinned_node[mesh_node]) {
+            c->skinned_node[mesh_node] = 1;
+            const uint32_t slot = c->slot_of_node[mesh_node];
+            if (slot != FYX_NONE) {
+                launch_or_u32(c->stream, c->a.flags + slot, F_SKINNED | F_DIRTY_SELF);
+                c->launches++;
+            }
+        }
+    }
+    if (out_id) *out_id = (uint32_t)c->surfaces.size();
+    c->surfaces.push_back(std::move(sf));
+    c->tables_dirty = true;
+    return FYX_OK;
+}
+
+extern "C" int32_t fyx_commit_surfaces(fyx_ctx *c)
+{
+    if (!c) return FYX_ERR_INVALID_ARGUMENT;
+    CU(cudaSetDevice(c->device));
+    int32_t rc = commit_surfaces(c);
+    if (rc) return rc;
+    return sync_and_check(c);
+}
+
+// --------------------------------------------------------------------------------------------
+// per frame
+// --------------------------------------------------------------------------------------------
+extern "C" int32_t fyx_update_transforms(fyx_ctx *c, uint32_t update_flags)
+{
+    if (!c) return FYX_ERR_INVALID_ARGUMENT;
+    if (!c->have_topology) return fail(c, FYX_ERR_STATE, "fyx_set_topology has not been called");
+    CU(cudaSetDevice(c->device));
+    int32_t rc = commit_surfaces(c);
+    if (rc) return rc;
+    CU(cudaEventRecord(c->ev[EV_START], c->stream));
+    rc = run_update(c, update_flags, nullptr);
+    if (rc) return rc;
+    CU(cudaEventRecord(c->ev[EV_UPDATE], c->stream));
+    rc = sync_and_check(c);
+    cudaEventElapsedTime(&c->timings.update_ms, c->ev[EV_START], c->ev[EV_UPDATE]);
+    return rc;
+}
+
+extern "C" int32_t fyx_cull(fyx_ctx *c, uint32_t nf, const fyx_frustum *fr, const uint32_t *cam_mask, const uint32_t *pass_flags)
+{
+    if (!c) return FYX_ERR_INVALID_ARGUMENT;
+    if (!c->have_topology) return fail(c, FYX_ERR_STATE, "fyx_set_topology has not been called");
+    CU(cudaSetDevice(c->device));
+    CU(cudaEventRecord(c->ev[EV_START], c->stream));
+    int32_t rc = prepare_cull(c, nf, fr, cam_mask, pass_flags);
+    if (rc) return rc;
+    if (nf) {
+        launch_cull(c->stream, c->a, c->cp);
+        c->launches++;
+    }
+    CU(cudaEventRecord(c->ev[EV_CULL], c->stream));
+    rc = sync_and_check(c);
+    cudaEventElapsedTime(&c->timings.cull_ms, c->ev[EV_START], c->ev[EV_CULL]);
+    return rc;
+}
+
+extern "C" int32_t fyx_update_and_cull(fyx_ctx *c, uint32_t update_flags, uint32_t nf, const fyx_frustum *fr,
+                                       const uint32_t *cam_mask, const uint32_t *pass_flags)
+{
+    if (!c) return FYX_ERR_INVALID_ARGUMENT;
+    if (!c->have_topology) return fail(c, FYX_ERR_STATE, "fyx_set_topology has not been called");
+    CU(cudaSetDevice(c->device));
+    int32_t rc = commit_surfaces(c);
+    if (rc) return rc;
+    CU(cudaEventRecord(c->ev[EV_START], c->stream));
+    rc = prepare_cull(c, nf, fr, cam_mask, pass_flags);
+    if (rc) return rc;
+    rc = run_update(c, update_flags, nf ? &c->cp : nullptr);
+    if (rc) return rc;
+    CU(cudaEventRecord(c->ev[EV_UPDATE], c->stream));
+    rc = sync_and_check(c);
+    cudaEventElapsedTime(&c->timings.update_ms, c->ev[EV_START], c->ev[EV_UPDATE]);
+    return rc;
+}
+
+extern "C" int32_t fyx_get_visible(fyx_ctx *c, uint32_t f, const uint32_t **out_idx, uint32_t *out_count)
+{
+    if (!c || !out_idx || !out_count) return FYX_ERR_INVALID_ARGUMENT;
+    if (f >= c->last_nf) return fail(c, FYX_ERR_INVALID_ARGUMENT, "frustum %u was not part of the last cull (%u frusta)", f, c->last_nf);
+    CU(cudaSetDevice(c->device));
+    int32_t rc = readback_visible(c);
+    if (rc) return rc;
+    *out_idx = c->h_vis[f];
+    *out_count = c->h_counts[f];
+    return FYX_OK;
+}
+
+extern "C" int32_t fyx_get_visible_device(fyx_ctx *c, uint32_t f, const uint32_t **d_idx, const uint32_t **d_count)
+{
+    if (!c || !d_idx || !d_count) return FYX_ERR_INVALID_ARGUMENT;
+    if (f >= c->last_nf) return fail(c, FYX_ERR_INVALID_ARGUMENT, "frustum %u was not part of the last cull (%u frusta)", f, c->last_nf);
+    *d_idx = c->b_vis[f].as<uint32_t>();
+    *d_count = c->d_counts + f * kCountStride;
+    return FYX_OK;
+}
+
+extern "C" int32_t fyx_build_palettes(fyx_ctx *c)
+{
+    if (!c) return FYX_ERR_INVALID_ARGUMENT;
+    if (!c->have_topology) return fail(c, FYX_ERR_STATE, "fyx_set_topology has not been called");
+    CU(cudaSetDevice(c->device));
+    int32_t rc = commit_surfaces(c);
+    if (rc) return rc;
+    CU(cudaEventRecord(c->ev[EV_START], c->stream));
+    if (c->sk.n_entries) {
+        launch_palette(c->stream, c->a, c->sk);
+        c->launches++;
+    }
+    CU(cudaEventRecord(c->ev[EV_PALETTE], c->stream));
+    rc = sync_and_check(c);
+    cudaEventElapsedTime(&c->timings.palette_ms, c->ev[EV_START], c->ev[EV_PALETTE]);
+    return rc;
+}
+
+extern "C" int32_t fyx_skin(fyx_ctx *c)
+{
+    if (!c) return FYX_ERR_INVALID_ARGUMENT;
+    if (!c->have_topology) return fail(c, FYX_ERR_STATE, "fyx_set_topology has not been called");
+    CU(cudaSetDevice(c->device));
+    int32_t rc = commit_surfaces(c);
+    if (rc) return rc;
+    CU(cudaEventRecord(c->ev[EV_START], c->stream));
+    if (c->n_tiles) {
+        launch_skin(c->stream, c->sk, c->b_tiles.as<SkinTile>(), c->n_tiles);
+        c->launches++;
+    }
+    CU(cudaEventRecord(c->ev[EV_SKIN], c->stream));
+    rc = sync_and_check(c);
+    cudaEventElapsedTime(&c->timings.skin_ms, c->ev[EV_START], c->ev[EV_SKIN]);
+    return rc;
+}
+
+extern "C" int32_t fyx_render_prep(fyx_ctx *c, const fyx_frame_desc *fr)
+{
+    if (!c || !fr) return FYX_ERR_INVALID_ARGUMENT;
+    if (fr->struct_size < sizeof(fyx_frame_desc)) return fail(c, FYX_ERR_INVALID_ARGUMENT, "fyx_frame_desc.struct_size too small");
+    if (!c->have_topology) return fail(c, FYX_ERR_STATE, "fyx_set_topology has not been called");
+    CU(cudaSetDevice(c->device));
+    int32_t rc = commit_surfaces(c);
+    if (rc) return rc;
+    cudaStream_t s = c->stream;
+    CU(cudaEventRecord(c->ev[EV_START], s));
+    // 1. changed local matrices (pinned caller memory is DMA'd in place: this call ends with a sync)
+    if (fr->n_changed) {
+        if (!fr->changed_m16) return fail(c, FYX_ERR_INVALID_ARGUMENT, "changed_m16 is NULL");
+        void *d_m = nullptr, *d_i = nullptr;
+        rc = stage_to_device(c, fr->changed_m16, (size_t)fr->n_changed * 64, fr->changed_idx,
+                             fr->changed_idx ? (size_t)fr->n_changed * 4 : 0, true, &d_m, &d_i);
+        if (rc) return rc;
+        launch_scatter_locals(s, c->a, fr->n_changed, static_cast<const uint32_t *>(d_i), static_cast<const float *>(d_m),
+                              c->b_slot_of_node.as<uint32_t>(), c->n_nodes, c->d_err);
+        c->launches++;
+    }
+    CU(cudaEventRecord(c->ev[EV_UPLOAD], s));
+    // 2. hierarchy + world boxes + cull
+    if (fr->n_frusta) {
+        rc = prepare_cull(c, fr->n_frusta, fr->frusta, fr->cam_mask, fr->pass_flags);
+        if (rc) return rc;
+    }
+    rc = run_update(c, fr->update_flags, fr->n_frusta ? &c->cp : nullptr);
+    if (rc) return rc;
+    CU(cudaEventRecord(c->ev[EV_UPDATE], s));
+    // 3. palettes, 4. skinning
+    if (fr->do_palettes && c->sk.n_entries) {
+        launch_palette(s, c->a, c->sk);
+        c->launches++;
+    }
+    CU(cudaEventRecord(c->ev[EV_PALETTE], s));
+    if (fr->do_skin && c->n_tiles) {
+        launch_skin(s, c->sk, c->b_tiles.as<SkinTile>(), c->n_tiles);
+        c->launches++;
+    }
+    CU(cudaEventRecord(c->ev[EV_SKIN], s));
+    CU(cudaGetLastError());
+    // 5. visible lists to the host
+    if (fr->readback_visible && fr->n_frusta) {
+        rc = readback_visible(c);
+        if (rc) return rc;
+    }
+    CU(cudaEventRecord(c->ev[EV_READBACK], s));
+    rc = sync_and_check(c);
+    fyx_timings &t = c->timings;
+    cudaEventElapsedTime(&t.upload_ms, c->ev[EV_START], c->ev[EV_UPLOAD]);
+    cudaEventElapsedTime(&t.update_ms, c->ev[EV_UPLOAD], c->ev[EV_UPDATE]);
+    cudaEventElapsedTime(&t.palette_ms, c->ev[EV_UPDATE], c->ev[EV_PALETTE]);
+    cudaEventElapsedTime(&t.skin_ms, c->ev[EV_PALETTE], c->ev[EV_SKIN]);
+    cudaEventElapsedTime(&t.readback_ms, c->ev[EV_SKIN], c->ev[EV_READBACK]);
+    cudaEventElapsedTime(&t.total_ms, c->ev[EV_START], c->ev[EV_READBACK]);
+    t.cull_ms = 0.0f;
+    return rc;
+}
+
+// --------------------------------------------------------------------------------------------
+// read-back
+// --------------------------------------------------------------------------------------------
+namespace {
+// gather `count` items of `item_bytes` through a gather launcher into caller memory
+template <class Launch> int32_t gather_out(fyx_ctx *c, uint32_t count, const uint32_t *idx, size_t item_bytes, void *out, Launch launch)
+{
+    if (!c) return FYX_ERR_INVALID_ARGUMENT;
+    if (!c->have_topology) return fail(c, FYX_ERR_STATE, "fyx_set_topology has not been called");
+    if (!count) return FYX_OK;
+    if (!out) return fail(c, FYX_ERR_INVALID_ARGUMENT, "output pointer is NULL");
+    CU(cudaSetDevice(c->device));
+    const size_t out_bytes = (size_t)count * item_bytes;
+    const size_t idx_bytes = idx ? (((size_t)count * 4 + 255) & ~size_t(255)) : 0;
+    int32_t rc = dev_ensure(c, c->d_stage, idx_bytes + out_bytes);
+    if (rc) return rc;
+    char *base = c->d_stage.as<char>();
+    uint32_t *d_idx = nullptr;
+    if (idx) {
+        CU(cudaStreamSynchronize(c->stream));
+        CU(cudaMemcpyAsync(base, idx, (size_t)count * 4, cudaMemcpyHostToDevice, c->stream));
+        d_idx = reinterpret_cast<uint32_t *>(base);
+    }
+    launch(d_idx, base + idx_bytes);
+    c->launches++;
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(out, base + idx_bytes, out_bytes, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return FYX_OK;
+}
+} // namespace
+
+extern "C" int32_t fyx_get_global_matrices(fyx_ctx *c, uint32_t count, const uint32_t *idx, float *out)
+{
+    return gather_out(c, count, idx, 64, out, [&](uint32_t *d_idx, void *d_out) {
+        launch_gather_globals(c->stream, c->a, count, d_idx, c->b_slot_of_node.as<uint32_t>(), c->n_nodes, static_cast<float *>(d_out));
+    });
+}
+
+extern "C" int32_t fyx_get_world_aabbs(fyx_ctx *c, uint32_t count, const uint32_t *idx, float *out)
+{
+    return gather_out(c, count, idx, 24, out, [&](uint32_t *d_idx, void *d_out) {
+        launch_gather_aabbs(c->stream, c->a, count, d_idx, c->b_slot_of_node.as<uint32_t>(), c->n_nodes, static_cast<float *>(d_out));
+    });
+}
+
+extern "C" int32_t fyx_get_global_flags(fyx_ctx *c, uint32_t count, const uint32_t *idx, uint32_t *out)
+{
+    return gather_out(c, count, idx, 4, out, [&](uint32_t *d_idx, void *d_out) {
+        launch_gather_flags(c->stream, c->a, count, d_idx, c->b_slot_of_node.as<uint32_t>(), c->n_nodes, static_cast<uint32_t *>(d_out));
+    });
+}
+
+extern "C" int32_t fyx_get_palette(fyx_ctx *c, uint32_t sid, float *out)
+{
+    if (!c || !out) return FYX_ERR_INVALID_ARGUMENT;
+    if (sid >= c->surfaces.size()) return fail(c, FYX_ERR_INVALID_ARGUMENT, "surface id %u out of range", sid);
+    CU(cudaSetDevice(c->device));
+    const Surface &sf = c->surfaces[sid];
+    if (!sf.n_bones) return FYX_OK;
+    CU(cudaMemcpyAsync(out, c->b_palette.as<float>() + 16 * (size_t)sf.bone_off, (size_t)sf.n_bones * 64, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return FYX_OK;
+}
+
+extern "C" int32_t fyx_get_skinned(fyx_ctx *c, uint32_t sid, float *out_pos, float *out_nrm)
+{
+    if (!c) return FYX_ERR_INVALID_ARGUMENT;
+    if (sid >= c->surfaces.size()) return fail(c, FYX_ERR_INVALID_ARGUMENT, "surface id %u out of range", sid);
+    CU(cudaSetDevice(c->device));
+    const Surface &sf = c->surfaces[sid];
+    if (!sf.n_verts) return FYX_OK;
+    if (out_pos) CU(cudaMemcpyAsync(out_pos, c->b_opos.as<float>() + 3 * sf.vert_off, (size_t)sf.n_verts * 12, cudaMemcpyDeviceToHost, c->stream));
+    if (out_nrm) CU(cudaMemcpyAsync(out_nrm, c->b_onrm.as<float>() + 3 * sf.vert_off, (size_t)sf.n_verts * 12, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return FYX_OK;
+}
+
+extern "C" int32_t fyx_get_skinned_device(fyx_ctx *c, uint32_t sid, const float **d_pos, const float **d_nrm)
+{
+    if (!c) return FYX_ERR_INVALID_ARGUMENT;
+    if (sid >= c->surfaces.size()) return fail(c, FYX_ERR_INVALID_ARGUMENT, "surface id %u out of range", sid);
+    const Surface &sf = c->surfaces[sid];
+    if (d_pos) *d_pos = c->b_opos.as<float>() + 3 * sf.vert_off;
+    if (d_nrm) *d_nrm = c->b_onrm.as<float>() + 3 * sf.vert_off;
+    return FYX_OK;
+}
+
+extern "C" int32_t fyx_get_timings(fyx_ctx *c, fyx_timings *out)
+{
+    if (!c || !out) return FYX_ERR_INVALID_ARGUMENT;
+    *out = c->timings;
+    return FYX_OK;
+}
+
+#include "fyx_comm.inl"

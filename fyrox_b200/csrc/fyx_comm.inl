@@ -1,0 +1,183 @@
+// fyx_comm.inl — multi-GPU exchange of the visible lists (included at the end of fyx_api.cu).
+//
+// One process per GPU, one fyx_ctx per process.  The node array is sharded by sub-tree
+// so transforms / boxes / skinning never cross GPUs; the only exchange step of the path is the
+// all-gather of the compacted visible-index lists, done with NCCL over NVLink 5 / NVSwitch:
+//   1. ncclAllGather of the per-frustum counts (FYX_MAX_FRUSTA u32 per rank)
+//   2. one grouped ncclAllGather per frustum of fixed max-count slots
+//   3. a pack kernel that removes the slot padding (rank order)
+// The reference has no counterpart (it is single-process).
+//
+// NCCL is bound at run time (dlopen "libnccl.so.2"): in a Python host that already imported torch
+// this resolves to torch's bundled NCCL, otherwise to the system library; the C ABI itself has no
+// link-time NCCL dependency, so single-GPU users need no NCCL at all.
+#include <dlfcn.h>
+#include <nccl.h>
+
+namespace {
+
+struct NcclApi {
+    void *lib = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    const char *(*GetErrorString)(ncclResult_t) = nullptr;
+    bool ok = false;
+};
+
+NcclApi &nccl()
+{
+    static NcclApi api;
+    static bool tried = false;
+    if (tried) return api;
+    tried = true;
+    const char *names[] = {"libnccl.so.2", "libnccl.so"};
+    for (const char *n : names) {
+        api.lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+        if (api.lib) break;
+    }
+    if (!api.lib) return api;
+#define SYM(field, name) api.field = reinterpret_cast<decltype(api.field)>(dlsym(api.lib, name))
+    SYM(GetUniqueId, "ncclGetUniqueId");
+    SYM(CommInitRank, "ncclCommInitRank");
+    SYM(CommDestroy, "ncclCommDestroy");
+    SYM(AllGather, "ncclAllGather");
+    SYM(GroupStart, "ncclGroupStart");
+    SYM(GroupEnd, "ncclGroupEnd");
+    SYM(GetErrorString, "ncclGetErrorString");
+#undef SYM
+    api.ok = api.GetUniqueId && api.CommInitRank && api.CommDestroy && api.AllGather && api.GroupStart && api.GroupEnd &&
+             api.GetErrorString;
+    return api;
+}
+
+#define NC(call)                                                                                            \
+    do {                                                                                                    \
+        ncclResult_t r__ = (call);                                                                          \
+        if (r__ != ncclSuccess) return fail(c, FYX_ERR_NCCL, "%s failed: %s", #call, nccl().GetErrorString(r__)); \
+    } while (0)
+
+} // namespace
+
+static void fyx_comm_destroy_internal(fyx_ctx *c)
+{
+    if (c->comm && nccl().ok) nccl().CommDestroy(static_cast<ncclComm_t>(c->comm));
+    c->comm = nullptr;
+}
+
+extern "C" int32_t fyx_comm_get_unique_id(void *out_id128)
+{
+    if (!out_id128) return FYX_ERR_INVALID_ARGUMENT;
+    static_assert(sizeof(ncclUniqueId) == FYX_COMM_ID_BYTES, "ncclUniqueId is 128 bytes");
+    if (!nccl().ok) return fail(nullptr, FYX_ERR_NCCL, "libnccl.so.2 could not be loaded");
+    ncclUniqueId id;
+    ncclResult_t r = nccl().GetUniqueId(&id);
+    if (r != ncclSuccess) return fail(nullptr, FYX_ERR_NCCL, "ncclGetUniqueId failed: %s", nccl().GetErrorString(r));
+    memcpy(out_id128, &id, sizeof id);
+    return FYX_OK;
+}
+
+extern "C" int32_t fyx_comm_init(fyx_ctx *c, int32_t nranks, int32_t rank, const void *id128)
+{
+    if (!c || !id128 || nranks < 1 || rank < 0 || rank >= nranks) return FYX_ERR_INVALID_ARGUMENT;
+    if (!nccl().ok) return fail(c, FYX_ERR_NCCL, "libnccl.so.2 could not be loaded");
+    CU(cudaSetDevice(c->device));
+    fyx_comm_destroy_internal(c);
+    ncclUniqueId id;
+    memcpy(&id, id128, sizeof id);
+    ncclComm_t comm = nullptr;
+    NC(nccl().CommInitRank(&comm, nranks, id, rank));
+    c->comm = comm;
+    c->nranks = nranks;
+    c->rank = rank;
+    int32_t rc;
+    if ((rc = dev_ensure(c, c->b_counts_packed, sizeof(uint32_t) * FYX_MAX_FRUSTA))) return rc;
+    if ((rc = dev_ensure(c, c->b_counts_all, sizeof(uint32_t) * FYX_MAX_FRUSTA * nranks))) return rc;
+    if (c->h_counts_all) cudaFreeHost(c->h_counts_all);
+    CU(cudaHostAlloc(reinterpret_cast<void **>(&c->h_counts_all), sizeof(uint32_t) * FYX_MAX_FRUSTA * nranks, cudaHostAllocDefault));
+    return FYX_OK;
+}
+
+extern "C" int32_t fyx_allgather_visible(fyx_ctx *c)
+{
+    if (!c) return FYX_ERR_INVALID_ARGUMENT;
+    if (!c->comm) return fail(c, FYX_ERR_STATE, "fyx_comm_init has not been called");
+    const uint32_t nf = c->last_nf;
+    if (!nf) return FYX_OK;
+    CU(cudaSetDevice(c->device));
+    ncclComm_t comm = static_cast<ncclComm_t>(c->comm);
+    cudaStream_t s = c->stream;
+    const int R = c->nranks;
+    // 1. counts
+    CU(cudaMemsetAsync(c->b_counts_packed.p, 0, sizeof(uint32_t) * FYX_MAX_FRUSTA, s));
+    CU(cudaMemcpy2DAsync(c->b_counts_packed.p, sizeof(uint32_t), c->d_counts, sizeof(uint32_t) * kCountStride, sizeof(uint32_t), nf,
+                         cudaMemcpyDeviceToDevice, s));
+    NC(nccl().AllGather(c->b_counts_packed.p, c->b_counts_all.p, FYX_MAX_FRUSTA, ncclUint32, comm, s));
+    CU(cudaMemcpyAsync(c->h_counts_all, c->b_counts_all.p, sizeof(uint32_t) * FYX_MAX_FRUSTA * R, cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    // own counts are now known on the host as well
+    for (uint32_t f = 0; f < nf; ++f) c->h_counts[f] = c->h_counts_all[c->rank * FYX_MAX_FRUSTA + f];
+    c->counts_on_host = true;
+    // 2. payload in max-count slots
+    uint32_t maxc[FYX_MAX_FRUSTA] = {};
+    int32_t rc;
+    for (uint32_t f = 0; f < nf; ++f) {
+        uint64_t total = 0;
+        for (int r = 0; r < R; ++r) {
+            const uint32_t n = c->h_counts_all[r * FYX_MAX_FRUSTA + f];
+            maxc[f] = std::max(maxc[f], n);
+            total += n;
+        }
+        c->gath_count[f] = (uint32_t)total;
+        if ((rc = dev_ensure(c, c->b_gath_pad[f], sizeof(uint32_t) * std::max<size_t>((size_t)maxc[f] * R, 1)))) return rc;
+        if ((rc = dev_ensure(c, c->b_gath[f], sizeof(uint32_t) * std::max<size_t>(total, 1)))) return rc;
+        // the send buffer must hold maxc entries: visible lists are sized for every renderable node of
+        // THIS shard, which may be smaller than another rank's count
+        if ((rc = dev_ensure(c, c->b_vis[f], sizeof(uint32_t) * std::max<size_t>(maxc[f], 1), true))) return rc;
+        c->cp.out[f] = c->b_vis[f].as<uint32_t>();
+    }
+    NC(nccl().GroupStart());
+    for (uint32_t f = 0; f < nf; ++f)
+        if (maxc[f]) NC(nccl().AllGather(c->b_vis[f].p, c->b_gath_pad[f].p, maxc[f], ncclUint32, comm, s));
+    NC(nccl().GroupEnd());
+    // 3. pack
+    for (uint32_t f = 0; f < nf; ++f) {
+        launch_compact_gathered(s, c->b_gath_pad[f].as<uint32_t>(), maxc[f], c->b_counts_all.as<uint32_t>(), R, (int)f,
+                                c->b_gath[f].as<uint32_t>());
+        c->launches += maxc[f] ? 1 : 0;
+    }
+    CU(cudaGetLastError());
+    return FYX_OK;
+}
+
+extern "C" int32_t fyx_get_visible_gathered_device(fyx_ctx *c, uint32_t f, const uint32_t **d_idx, uint32_t *out_count)
+{
+    if (!c || !d_idx || !out_count) return FYX_ERR_INVALID_ARGUMENT;
+    if (f >= c->last_nf) return fail(c, FYX_ERR_INVALID_ARGUMENT, "frustum %u was not part of the last cull", f);
+    *d_idx = c->b_gath[f].as<uint32_t>();
+    *out_count = c->gath_count[f];
+    return FYX_OK;
+}
+
+extern "C" int32_t fyx_get_visible_gathered(fyx_ctx *c, uint32_t f, const uint32_t **out_idx, uint32_t *out_count)
+{
+    if (!c || !out_idx || !out_count) return FYX_ERR_INVALID_ARGUMENT;
+    if (f >= c->last_nf) return fail(c, FYX_ERR_INVALID_ARGUMENT, "frustum %u was not part of the last cull", f);
+    CU(cudaSetDevice(c->device));
+    const size_t n = c->gath_count[f];
+    if (n > c->h_gath_cap[f]) {
+        if (c->h_gath[f]) cudaFreeHost(c->h_gath[f]);
+        c->h_gath[f] = nullptr;
+        const size_t cap = std::max<size_t>(1024, n + n / 2);
+        CU(cudaHostAlloc(reinterpret_cast<void **>(&c->h_gath[f]), cap * sizeof(uint32_t), cudaHostAllocDefault));
+        c->h_gath_cap[f] = cap;
+    }
+    if (n) CU(cudaMemcpyAsync(c->h_gath[f], c->b_gath[f].p, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    *out_idx = c->h_gath[f];
+    *out_count = (uint32_t)n;
+    return FYX_OK;
+}

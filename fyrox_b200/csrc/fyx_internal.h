@@ -1,0 +1,106 @@
+// fyx_internal.h — device data layout and kernel launchers shared by fyx_api.cu / fyx_kernels.cu.
+//
+// HBM layout.  Nodes live in SLOT order = sorted by (depth, node index), so every
+// hierarchy level is one contiguous, coalesced range and a parent is always in an earlier range.
+// All per-node columns are SoA planes indexed by slot:
+//   L[3], G[3]   float4 rows of the affine local / global matrix (48 B each; bottom row implicit)
+//   la[3], wa[3] float2 (min_i,max_i) pairs of the local / world AABB (24 B each)
+//   parent       u32 parent slot (FYX_NONE = none)      flags  u32 (input bits + computed bits)
+//   mask         u32 Base::render_mask                  gidx   u32 node index emitted to visible lists
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/fyrox_b200.h"
+#include "fyx_math.cuh"
+
+namespace fyx {
+
+// internal flag bits (above the public ones)
+constexpr uint32_t F_DIRTY_SELF = 1u << 11; // local matrix / topology changed since the last update
+constexpr uint32_t F_DIRTY = 1u << 12;      // in a changed sub-tree during the last update
+constexpr uint32_t F_SKINNED = 1u << 13;    // Mesh with at least one skinned surface
+constexpr uint32_t F_ROOT = 1u << 14;       // Graph::root
+
+constexpr int kCountStride = 32; // u32s between per-frustum counters (128 B: one L2 line each)
+constexpr int kBlock = 256;
+
+struct NodeArrays {
+    uint32_t cap; // number of slots (alive nodes)
+    uint32_t *parent;
+    uint32_t *flags;
+    uint32_t *mask;
+    uint32_t *gidx;
+    float4 *L[3];
+    float4 *G[3];
+    float2 *la[3];
+    float2 *wa[3];
+};
+
+struct CullParams {
+    int nf;
+    FrustumDev f[FYX_MAX_FRUSTA];
+    uint32_t *out[FYX_MAX_FRUSTA]; // visible lists
+    uint32_t *counts;              // counts[f * kCountStride]
+};
+
+struct SkinArrays {
+    // bone table (one entry per (surface, bone))
+    uint32_t n_entries;
+    const uint32_t *bone_slot; // slot of the bone node, FYX_NONE ⇒ identity
+    const float4 *ib[3];       // inverse bind pose rows
+    float *palette;            // n_entries * 16 f32, column-major mat4 (the reference's bone_matrices layout)
+    // vertex streams (each surface padded to a multiple of 4 vertices)
+    const float *vpos, *vnrm;  // packed xyz
+    const float4 *vw;
+    const uint32_t *vidx;      // 4 x u8
+    float *opos, *onrm;        // skinned streams, packed xyz
+};
+
+struct SkinTile {
+    uint32_t bone_off; // first palette entry of the surface
+    uint32_t n_bones;
+    uint32_t quad_start; // absolute index of the first 4-vertex group
+    uint32_t n_quads;
+};
+
+struct FoldArrays {
+    uint32_t n; // skinned mesh nodes
+    const uint32_t *node_slot;
+    const uint32_t *bone_begin; // n+1 offsets into bone_slot
+    const uint32_t *bone_slot;  // bones of all skinned surfaces of the node, in surface order
+};
+
+// ---- launchers (fyx_kernels.cu) ----
+void launch_update_level(cudaStream_t s, const NodeArrays &a, uint32_t lo, uint32_t hi, bool update_all,
+                         const CullParams *cull /* nullptr = no fused cull */);
+void launch_cull(cudaStream_t s, const NodeArrays &a, const CullParams &cp);
+void launch_fold_bones(cudaStream_t s, const NodeArrays &a, const FoldArrays &fa, const CullParams *cull);
+void launch_palette(cudaStream_t s, const NodeArrays &a, const SkinArrays &sk);
+void launch_skin(cudaStream_t s, const SkinArrays &sk, const SkinTile *tiles, uint32_t n_tiles);
+
+void launch_scatter_locals(cudaStream_t s, const NodeArrays &a, uint32_t count, const uint32_t *d_idx,
+                           const float *d_m16, const uint32_t *slot_of_node, uint32_t n_nodes, uint32_t *d_err);
+void launch_scatter_u32(cudaStream_t s, uint32_t *dst_col, uint32_t *flags_col, uint32_t count, const uint32_t *d_idx,
+                        const uint32_t *d_val, const uint32_t *slot_of_node, uint32_t n_nodes, int mode);
+void launch_scatter_aabbs(cudaStream_t s, const NodeArrays &a, uint32_t count, const uint32_t *d_idx,
+                          const float *d_aabb6, const uint32_t *slot_of_node, uint32_t n_nodes);
+void launch_gather_globals(cudaStream_t s, const NodeArrays &a, uint32_t count, const uint32_t *d_idx,
+                           const uint32_t *slot_of_node, uint32_t n_nodes, float *d_out_m16);
+void launch_gather_aabbs(cudaStream_t s, const NodeArrays &a, uint32_t count, const uint32_t *d_idx,
+                         const uint32_t *slot_of_node, uint32_t n_nodes, float *d_out6);
+void launch_gather_flags(cudaStream_t s, const NodeArrays &a, uint32_t count, const uint32_t *d_idx,
+                         const uint32_t *slot_of_node, uint32_t n_nodes, uint32_t *d_out);
+void launch_deinterleave(cudaStream_t s, uint32_t n_verts, const unsigned char *d_bytes, fyx_vertex_layout layout,
+                         uint32_t n_bones, float *vpos, float *vnrm, float4 *vw, uint32_t *vidx, uint32_t *d_err);
+void launch_ib_rows(cudaStream_t s, uint32_t n, const float *d_m16, float4 *r0, float4 *r1, float4 *r2, uint32_t *d_err);
+void launch_or_u32(cudaStream_t s, uint32_t *p, uint32_t bits);
+void launch_compact_gathered(cudaStream_t s, const uint32_t *pad, uint32_t maxc, const uint32_t *counts_all, int nranks, int f,
+                             uint32_t *dst);
+
+// error bits written by kernels into d_err
+constexpr uint32_t E_NOT_AFFINE = 1u;
+constexpr uint32_t E_BAD_BONE_INDEX = 2u;
+constexpr uint32_t E_NONFINITE_VERTEX = 4u;
+
+} // namespace fyx

@@ -1,0 +1,677 @@
+// fyx_kernels.cu — hand-written sm_100a kernels of the render-prep hot path.
+//
+// All kernels are HBM-bandwidth-bound streaming kernels over SoA planes (no tensor cores: 4x4 f32
+// work at ~0.3-1 flop/B).  Arithmetic follows fyx_math.cuh (one rounding per op, reference order).
+// Each kernel names the reference code it replaces (paths relative to the Fyrox tree).
+#include "fyx_internal.h"
+
+namespace fyx {
+
+// ------------------------------------------------------------------------------------------------
+// streaming load/store helpers: node columns are touched once per frame ⇒ bypass L1 allocation for the
+// big streams (read-only path, evict-first), keep default caching for the gathered parent rows.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float4 ld_stream(const float4 *p)
+{
+    float4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+                 : "l"(p));
+    return v;
+}
+__device__ __forceinline__ float2 ld_stream(const float2 *p)
+{
+    float2 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.f32 {%0,%1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ uint4 ld_stream(const uint4 *p)
+{
+    uint4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+                 : "l"(p));
+    return v;
+}
+__device__ __forceinline__ void st_stream(float4 *p, const float4 v)
+{
+    asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
+                 : "memory");
+}
+__device__ __forceinline__ void st_stream(float2 *p, const float2 v)
+{
+    asm volatile("st.global.L1::no_allocate.v2.f32 [%0], {%1,%2};" ::"l"(p), "f"(v.x), "f"(v.y) : "memory");
+}
+
+// ------------------------------------------------------------------------------------------------
+// NodeTrait::should_be_rendered (scene/node/mod.rs:231-256) + the shadow-pass cast_shadows test of
+// Mesh::collect_render_data (scene/mesh/mod.rs:696-698) + reachability from Graph::root
+// (iterate_recursive, renderer/bundle.rs:988-1004), for every frustum of the call.  Bit f of the
+// result = "node is in the visible set of frustum f".
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t cull_bits(const uint32_t nf, const uint32_t mask, const float2 wx, const float2 wy,
+                                              const float2 wz, const CullParams &cp)
+{
+    constexpr uint32_t need = FYX_NODE_ALIVE | FYX_NODE_RENDERABLE | FYX_NODE_REACHABLE | FYX_NODE_GLOBAL_VISIBILITY |
+                              FYX_NODE_GLOBAL_ENABLED;
+    if ((nf & need) != need) return 0u;
+    uint32_t bits = 0u;
+    for (int f = 0; f < cp.nf; ++f) {
+        bool ok = (mask & cp.f[f].cam_mask) != 0u;
+        ok &= !((cp.f[f].pass_flags & FYX_PASS_SHADOW) && !(nf & FYX_NODE_CAST_SHADOWS));
+        if (ok && (nf & FYX_NODE_FRUSTUM_CULLING)) ok = frustum_intersects_aabb(cp.f[f], wx, wy, wz);
+        bits |= ok ? (1u << f) : 0u;
+    }
+    return bits;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Block-wide compaction of the visible node indices: warp ballot + popc rank, one atomicAdd per
+// (CTA, frustum) on a counter that owns its own 128 B line.  Replaces the Vec pushes of
+// RenderDataBundleStorage::push (renderer/bundle.rs:1248-1278).  Order inside a list is unspecified.
+// Must be called by every thread of the CTA.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void compact_emit(const uint32_t vis_bits, const uint32_t node_index, const CullParams &cp)
+{
+    constexpr int kWarps = kBlock / 32;
+    __shared__ uint32_t s_wcount[FYX_MAX_FRUSTA][kWarps];
+    __shared__ uint32_t s_base[FYX_MAX_FRUSTA];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int nf = cp.nf;
+
+    // any visible node in the CTA at all?  (most CTAs of a mostly-culled scene skip the atomics)
+    const int any = __syncthreads_or(vis_bits != 0u);
+    if (!any) return;
+
+    for (int f = 0; f < nf; ++f) {
+        const uint32_t b = __ballot_sync(0xFFFFFFFFu, (vis_bits >> f) & 1u);
+        if (lane == 0) s_wcount[f][warp] = __popc(b);
+    }
+    __syncthreads();
+    if (threadIdx.x < nf) {
+        const int f = threadIdx.x;
+        uint32_t run = 0;
+#pragma unroll
+        for (int w = 0; w < kWarps; ++w) {
+            const uint32_t c = s_wcount[f][w];
+            s_wcount[f][w] = run; // exclusive prefix over warps
+            run += c;
+        }
+        s_base[f] = run ? atomicAdd(cp.counts + f * kCountStride, run) : 0u;
+    }
+    __syncthreads();
+    for (int f = 0; f < nf; ++f) {
+        const uint32_t bit = (vis_bits >> f) & 1u;
+        const uint32_t b = __ballot_sync(0xFFFFFFFFu, bit);
+        if (bit) {
+            const uint32_t pos = s_base[f] + s_wcount[f][warp] + __popc(b & ((1u << lane) - 1u));
+            cp.out[f][pos] = node_index;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// One hierarchy level.  Replaces, for the nodes of this level:
+//   Graph::update_global_transform_recursively   scene/graph/mod.rs:1199-1241   (G = parent.G * local)
+//   Graph::update_visibility_recursively          :1182-1197                      (gv = parent.gv && visibility)
+//   Graph::update_enabled_flag_recursively        :1166-1180                      (ge = parent.ge && enabled)
+//   Mesh::on_global_transform_changed / Base::world_bounding_box   scene/mesh/mod.rs:667-689, scene/base.rs:741-750
+//   (+ FUSE: should_be_rendered + visible-list emission for non-skinned nodes)
+// and the change tracking of process_node_messages (:1303-1399): a node is recomputed iff it or an
+// ancestor changed (or FYX_UPDATE_ALL).  One thread per node; parents were finished by the previous
+// launch on the same stream.
+// Algorithmic bytes per node: 132 (T) + 48 (A) [+ 8 (K)]; moved: 48+4+48 + 24+24 + 4+4(+4+4).
+// ------------------------------------------------------------------------------------------------
+template <bool FUSE>
+__global__ void __launch_bounds__(kBlock) k_update_level(const NodeArrays a, const uint32_t lo, const uint32_t hi,
+                                                         const uint32_t update_all, const CullParams cp)
+{
+    const uint32_t slot = lo + blockIdx.x * kBlock + threadIdx.x;
+    const bool valid = slot < hi;
+    uint32_t vis_bits = 0u, gi = 0u;
+    if (valid) {
+        const uint32_t f = a.flags[slot];
+        const uint32_t p = a.parent[slot];
+        // no parent ⇒ parent values are identity / true (graph/mod.rs:1171-1175,1187-1192,1210-1214)
+        const uint32_t pf = (p != FYX_NONE)
+                                ? a.flags[p]
+                                : (FYX_NODE_GLOBAL_VISIBILITY | FYX_NODE_GLOBAL_ENABLED | ((f & F_ROOT) ? FYX_NODE_REACHABLE : 0u));
+        const bool dirty = update_all || (f & F_DIRTY_SELF) || (pf & F_DIRTY);
+        uint32_t nf = f & ~(FYX_NODE_GLOBAL_VISIBILITY | FYX_NODE_GLOBAL_ENABLED | FYX_NODE_REACHABLE | F_DIRTY | F_DIRTY_SELF);
+        if ((pf & FYX_NODE_GLOBAL_VISIBILITY) && (f & FYX_NODE_VISIBILITY)) nf |= FYX_NODE_GLOBAL_VISIBILITY;
+        if ((pf & FYX_NODE_GLOBAL_ENABLED) && (f & FYX_NODE_ENABLED)) nf |= FYX_NODE_GLOBAL_ENABLED;
+        nf |= pf & FYX_NODE_REACHABLE;
+        if (dirty) nf |= F_DIRTY;
+        a.flags[slot] = nf;
+
+        float2 wx, wy, wz;
+        if (dirty) {
+            Affine L;
+            L.r0 = ld_stream(a.L[0] + slot);
+            L.r1 = ld_stream(a.L[1] + slot);
+            L.r2 = ld_stream(a.L[2] + slot);
+            const float2 lx = ld_stream(a.la[0] + slot);
+            const float2 ly = ld_stream(a.la[1] + slot);
+            const float2 lz = ld_stream(a.la[2] + slot);
+            Affine P;
+            if (p != FYX_NONE) {
+                P.r0 = a.G[0][p]; // siblings share the parent: broadcast / L1 hit
+                P.r1 = a.G[1][p];
+                P.r2 = a.G[2][p];
+            } else {
+                P = affine_identity();
+            }
+            const Affine Gm = affine_mul(P, L);
+            st_stream(a.G[0] + slot, Gm.r0);
+            st_stream(a.G[1] + slot, Gm.r1);
+            st_stream(a.G[2] + slot, Gm.r2);
+            wx = aabb_transform_row(Gm.r0, lx, ly, lz);
+            wy = aabb_transform_row(Gm.r1, lx, ly, lz);
+            wz = aabb_transform_row(Gm.r2, lx, ly, lz);
+            // skinned meshes: this is the box before the bone fold; k_fold_bones finishes it
+            st_stream(a.wa[0] + slot, wx);
+            st_stream(a.wa[1] + slot, wy);
+            st_stream(a.wa[2] + slot, wz);
+        } else if (FUSE) {
+            wx = ld_stream(a.wa[0] + slot);
+            wy = ld_stream(a.wa[1] + slot);
+            wz = ld_stream(a.wa[2] + slot);
+        }
+        if (FUSE && !(nf & F_SKINNED)) {
+            vis_bits = cull_bits(nf, a.mask[slot], wx, wy, wz, cp);
+            if (vis_bits) gi = a.gidx[slot];
+        }
+    }
+    if (FUSE) compact_emit(vis_bits, gi, cp);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Stand-alone cull over all slots (static scene / extra passes: every shadow pass re-runs the cull
+// with its own frustum, renderer/shadow/*.rs).  32 B read per node + 4 B per visible entry.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kBlock) k_cull(const NodeArrays a, const CullParams cp)
+{
+    const uint32_t slot = blockIdx.x * kBlock + threadIdx.x;
+    uint32_t vis_bits = 0u, gi = 0u;
+    if (slot < a.cap) {
+        const uint32_t nf = a.flags[slot];
+        const uint32_t mask = a.mask[slot];
+        const float2 wx = ld_stream(a.wa[0] + slot);
+        const float2 wy = ld_stream(a.wa[1] + slot);
+        const float2 wz = ld_stream(a.wa[2] + slot);
+        vis_bits = cull_bits(nf, mask, wx, wy, wz, cp);
+        if (vis_bits) gi = a.gidx[slot];
+    }
+    compact_emit(vis_bits, gi, cp);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Skinned-mesh world AABB: the "special case for skinned meshes" of Mesh::on_global_transform_changed
+// (scene/mesh/mod.rs:673-684): world_aabb.add_point(bone.global_position()) for every bone of every
+// surface, strict </> updates in bone order (aabb.rs:86-106) — sequential per mesh so that even the
+// sign of a zero bound matches.  Runs after all levels (bones may be deeper than the mesh node);
+// only meshes in a changed sub-tree are refreshed, as in the reference.  With FUSE the skinned
+// nodes are also culled here (they were skipped by the level kernels).
+// ------------------------------------------------------------------------------------------------
+template <bool FUSE>
+__global__ void __launch_bounds__(kBlock) k_fold_bones(const NodeArrays a, const FoldArrays fa, const CullParams cp)
+{
+    const uint32_t i = blockIdx.x * kBlock + threadIdx.x;
+    uint32_t vis_bits = 0u, gi = 0u;
+    if (i < fa.n) {
+        const uint32_t slot = fa.node_slot[i];
+        const uint32_t nf = a.flags[slot];
+        float2 wx = a.wa[0][slot], wy = a.wa[1][slot], wz = a.wa[2][slot];
+        if (nf & F_DIRTY) {
+            const uint32_t b0 = fa.bone_begin[i], b1 = fa.bone_begin[i + 1];
+            for (uint32_t b = b0; b < b1; ++b) {
+                const uint32_t bs = fa.bone_slot[b];
+                if (bs == FYX_NONE) continue; // try_borrow failed ⇒ skipped
+                const float px = a.G[0][bs].w, py = a.G[1][bs].w, pz = a.G[2][bs].w; // global_position()
+                if (px < wx.x) wx.x = px;
+                if (py < wy.x) wy.x = py;
+                if (pz < wz.x) wz.x = pz;
+                if (px > wx.y) wx.y = px;
+                if (py > wy.y) wy.y = py;
+                if (pz > wz.y) wz.y = pz;
+            }
+            a.wa[0][slot] = wx;
+            a.wa[1][slot] = wy;
+            a.wa[2][slot] = wz;
+        }
+        if (FUSE) {
+            vis_bits = cull_bits(nf, a.mask[slot], wx, wy, wz, cp);
+            if (vis_bits) gi = a.gidx[slot];
+        }
+    }
+    if (FUSE) compact_emit(vis_bits, gi, cp);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Bone palette: SurfaceInstanceData::bone_matrices (scene/mesh/mod.rs:781-793):
+// P[k] = bone_k.global_transform() * bone_k.inv_bind_pose_transform(), identity for an invalid
+// handle.  One thread per (surface, bone) entry; G is gathered by bone slot, inv_bind streams.
+// Output: column-major mat4 (the layout write_uniforms copies into the UBO, renderer/bundle.rs:484-496).
+// Algorithmic bytes per bone: 196 (G 64 + inv_bind 64 + idx 4 + P 64); moved: 48 + 48 + 4 + 64.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kBlock) k_palette(const NodeArrays a, const SkinArrays sk)
+{
+    const uint32_t e = blockIdx.x * kBlock + threadIdx.x;
+    if (e >= sk.n_entries) return;
+    const uint32_t bs = sk.bone_slot[e];
+    Affine P;
+    if (bs != FYX_NONE) {
+        Affine Gm, IB;
+        Gm.r0 = a.G[0][bs];
+        Gm.r1 = a.G[1][bs];
+        Gm.r2 = a.G[2][bs];
+        IB.r0 = ld_stream(sk.ib[0] + e);
+        IB.r1 = ld_stream(sk.ib[1] + e);
+        IB.r2 = ld_stream(sk.ib[2] + e);
+        P = affine_mul(Gm, IB);
+    } else {
+        P = affine_identity();
+    }
+    float4 *o = reinterpret_cast<float4 *>(sk.palette + 16 * (size_t)e);
+    o[0] = make_float4(P.r0.x, P.r1.x, P.r2.x, 0.0f);
+    o[1] = make_float4(P.r0.y, P.r1.y, P.r2.y, 0.0f);
+    o[2] = make_float4(P.r0.z, P.r1.z, P.r2.z, 0.0f);
+    o[3] = make_float4(P.r0.w, P.r1.w, P.r2.w, 1.0f);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Linear-blend skinning.  Positions: the skinned branch of Mesh::accurate_world_bounding_box
+// (scene/mesh/mod.rs:501-522): acc = 0; for k in 0..4: acc += P[idx_k].transform_point(p) * w_k, where
+// transform_point = ((m_i0*x + m_i1*y) + m_i2*z) + m_i3, then / n with n = row3·p + m33 — exactly 1
+// for the affine palette and finite p, so the division is the identity and is skipped.  Normals:
+// standard.shader:192-195, acc += (mat3(P[idx_k]) * n) * w_k in the same order.
+//
+// One CTA per tile (a run of 4-vertex groups of one surface).  The surface's palette is staged in
+// shared memory as 3 float4 rows per bone (48 B stride ⇒ 8 consecutive bones hit 8 distinct 4-bank
+// groups).  Each thread owns 4 consecutive vertices so every stream access is a 128-bit load/store:
+// 3 (pos) + 3 (normal) + 4 (weights) + 1 (indices) LDG.128, 3 + 3 STG.128.
+// Algorithmic bytes per vertex: 44 read + 24 written = 68.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kBlock) k_skin(const SkinArrays sk, const SkinTile *__restrict__ tiles)
+{
+    extern __shared__ float4 s_pal[]; // n_bones * 3 rows
+    const SkinTile t = tiles[blockIdx.x];
+    for (uint32_t b = threadIdx.x; b < t.n_bones; b += kBlock) {
+        const float4 *m = reinterpret_cast<const float4 *>(sk.palette + 16 * (size_t)(t.bone_off + b));
+        const float4 c0 = m[0], c1 = m[1], c2 = m[2], c3 = m[3];
+        s_pal[3 * b + 0] = make_float4(c0.x, c1.x, c2.x, c3.x);
+        s_pal[3 * b + 1] = make_float4(c0.y, c1.y, c2.y, c3.y);
+        s_pal[3 * b + 2] = make_float4(c0.z, c1.z, c2.z, c3.z);
+    }
+    __syncthreads();
+
+    for (uint32_t q = threadIdx.x; q < t.n_quads; q += kBlock) {
+        const size_t quad = (size_t)t.quad_start + q;
+        const float4 *pp = reinterpret_cast<const float4 *>(sk.vpos) + 3 * quad;
+        const float4 *np = reinterpret_cast<const float4 *>(sk.vnrm) + 3 * quad;
+        const float4 p0 = ld_stream(pp), p1 = ld_stream(pp + 1), p2 = ld_stream(pp + 2);
+        const float4 n0 = ld_stream(np), n1 = ld_stream(np + 1), n2 = ld_stream(np + 2);
+        const float4 w0 = ld_stream(sk.vw + 4 * quad), w1 = ld_stream(sk.vw + 4 * quad + 1);
+        const float4 w2 = ld_stream(sk.vw + 4 * quad + 2), w3 = ld_stream(sk.vw + 4 * quad + 3);
+        const uint4 iq = ld_stream(reinterpret_cast<const uint4 *>(sk.vidx) + quad);
+
+        const float px[4] = {p0.x, p0.w, p1.z, p2.y}, py[4] = {p0.y, p1.x, p1.w, p2.z}, pz[4] = {p0.z, p1.y, p2.x, p2.w};
+        const float nx[4] = {n0.x, n0.w, n1.z, n2.y}, ny[4] = {n0.y, n1.x, n1.w, n2.z}, nz[4] = {n0.z, n1.y, n2.x, n2.w};
+        const float4 wv[4] = {w0, w1, w2, w3};
+        const uint32_t iv[4] = {iq.x, iq.y, iq.z, iq.w};
+        float ox[4], oy[4], oz[4], mx[4], my[4], mz[4];
+#pragma unroll
+        for (int v = 0; v < 4; ++v) {
+            float ax = 0.0f, ay = 0.0f, az = 0.0f, bx = 0.0f, by = 0.0f, bz = 0.0f;
+            const float wk[4] = {wv[v].x, wv[v].y, wv[v].z, wv[v].w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const uint32_t bone = (iv[v] >> (8 * k)) & 0xFFu;
+                const float4 r0 = s_pal[3 * bone + 0], r1 = s_pal[3 * bone + 1], r2 = s_pal[3 * bone + 2];
+                const float w = wk[k];
+                const float tx = FYX_ADD(FYX_ADD(FYX_ADD(FYX_MUL(r0.x, px[v]), FYX_MUL(r0.y, py[v])), FYX_MUL(r0.z, pz[v])), r0.w);
+                const float ty = FYX_ADD(FYX_ADD(FYX_ADD(FYX_MUL(r1.x, px[v]), FYX_MUL(r1.y, py[v])), FYX_MUL(r1.z, pz[v])), r1.w);
+                const float tz = FYX_ADD(FYX_ADD(FYX_ADD(FYX_MUL(r2.x, px[v]), FYX_MUL(r2.y, py[v])), FYX_MUL(r2.z, pz[v])), r2.w);
+                ax = FYX_ADD(ax, FYX_MUL(tx, w));
+                ay = FYX_ADD(ay, FYX_MUL(ty, w));
+                az = FYX_ADD(az, FYX_MUL(tz, w));
+                const float rx = FYX_ADD(FYX_ADD(FYX_MUL(r0.x, nx[v]), FYX_MUL(r0.y, ny[v])), FYX_MUL(r0.z, nz[v]));
+                const float ry = FYX_ADD(FYX_ADD(FYX_MUL(r1.x, nx[v]), FYX_MUL(r1.y, ny[v])), FYX_MUL(r1.z, nz[v]));
+                const float rz = FYX_ADD(FYX_ADD(FYX_MUL(r2.x, nx[v]), FYX_MUL(r2.y, ny[v])), FYX_MUL(r2.z, nz[v]));
+                bx = FYX_ADD(bx, FYX_MUL(rx, w));
+                by = FYX_ADD(by, FYX_MUL(ry, w));
+                bz = FYX_ADD(bz, FYX_MUL(rz, w));
+            }
+            ox[v] = ax; oy[v] = ay; oz[v] = az;
+            mx[v] = bx; my[v] = by; mz[v] = bz;
+        }
+        float4 *po = reinterpret_cast<float4 *>(sk.opos) + 3 * quad;
+        float4 *no = reinterpret_cast<float4 *>(sk.onrm) + 3 * quad;
+        st_stream(po + 0, make_float4(ox[0], oy[0], oz[0], ox[1]));
+        st_stream(po + 1, make_float4(oy[1], oz[1], ox[2], oy[2]));
+        st_stream(po + 2, make_float4(oz[2], ox[3], oy[3], oz[3]));
+        st_stream(no + 0, make_float4(mx[0], my[0], mz[0], mx[1]));
+        st_stream(no + 1, make_float4(my[1], mz[1], mx[2], my[2]));
+        st_stream(no + 2, make_float4(mz[2], mx[3], my[3], mz[3]));
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Host-facing scatter / gather between the caller's AoS-by-node-index arrays and the slot-ordered
+// SoA planes.  Invalid indices are skipped (Pool::try_borrow semantics).
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t resolve_slot(const uint32_t *d_idx, uint32_t e, const uint32_t *slot_of_node,
+                                                 uint32_t n_nodes)
+{
+    const uint32_t node = d_idx ? d_idx[e] : e;
+    if (node >= n_nodes) return FYX_NONE;
+    return slot_of_node[node];
+}
+
+__device__ __forceinline__ bool finite4(const float4 v)
+{
+    return (fabsf(v.x) <= 3.402823466e38f) & (fabsf(v.y) <= 3.402823466e38f) & (fabsf(v.z) <= 3.402823466e38f) &
+           (fabsf(v.w) <= 3.402823466e38f);
+}
+
+// bottom row must be bit-exactly (+0,+0,+0,1) — what Transform::calculate_local_transform writes
+// (scene/transform.rs:479-536) — and all entries finite; returns false otherwise
+__device__ __forceinline__ bool load_affine_rows(const float *m16, Affine &A)
+{
+    const float4 *c = reinterpret_cast<const float4 *>(m16);
+    const float4 c0 = c[0], c1 = c[1], c2 = c[2], c3 = c[3];
+    A.r0 = make_float4(c0.x, c1.x, c2.x, c3.x);
+    A.r1 = make_float4(c0.y, c1.y, c2.y, c3.y);
+    A.r2 = make_float4(c0.z, c1.z, c2.z, c3.z);
+    const bool bottom = (__float_as_uint(c0.w) == 0u) & (__float_as_uint(c1.w) == 0u) & (__float_as_uint(c2.w) == 0u) &
+                        (c3.w == 1.0f);
+    return bottom & finite4(A.r0) & finite4(A.r1) & finite4(A.r2);
+}
+
+__global__ void __launch_bounds__(kBlock) k_scatter_locals(const NodeArrays a, const uint32_t count, const uint32_t *d_idx,
+                                                           const float *d_m16, const uint32_t *slot_of_node,
+                                                           const uint32_t n_nodes, uint32_t *d_err)
+{
+    const uint32_t e = blockIdx.x * kBlock + threadIdx.x;
+    if (e >= count) return;
+    const uint32_t slot = resolve_slot(d_idx, e, slot_of_node, n_nodes);
+    if (slot == FYX_NONE) return;
+    Affine A;
+    if (!load_affine_rows(d_m16 + 16 * (size_t)e, A)) {
+        atomicOr(d_err, E_NOT_AFFINE);
+        return;
+    }
+    a.L[0][slot] = A.r0;
+    a.L[1][slot] = A.r1;
+    a.L[2][slot] = A.r2;
+    atomicOr(a.flags + slot, F_DIRTY_SELF); // NodeMessageKind::TransformChanged
+}
+
+// mode 0: node flags (public input bits except ALIVE are replaced); mode 1: plain column store
+__global__ void __launch_bounds__(kBlock) k_scatter_u32(uint32_t *dst_col, const uint32_t count, const uint32_t *d_idx,
+                                                        const uint32_t *d_val, const uint32_t *slot_of_node,
+                                                        const uint32_t n_nodes, const int mode)
+{
+    const uint32_t e = blockIdx.x * kBlock + threadIdx.x;
+    if (e >= count) return;
+    const uint32_t slot = resolve_slot(d_idx, e, slot_of_node, n_nodes);
+    if (slot == FYX_NONE) return;
+    if (mode == 0) {
+        constexpr uint32_t settable = FYX_NODE_INPUT_MASK & ~FYX_NODE_ALIVE;
+        const uint32_t old = dst_col[slot];
+        dst_col[slot] = (old & ~settable) | (d_val[e] & settable);
+    } else {
+        dst_col[slot] = d_val[e];
+    }
+}
+
+__global__ void __launch_bounds__(kBlock) k_scatter_aabbs(const NodeArrays a, const uint32_t count, const uint32_t *d_idx,
+                                                          const float *d_aabb6, const uint32_t *slot_of_node,
+                                                          const uint32_t n_nodes)
+{
+    const uint32_t e = blockIdx.x * kBlock + threadIdx.x;
+    if (e >= count) return;
+    const uint32_t slot = resolve_slot(d_idx, e, slot_of_node, n_nodes);
+    if (slot == FYX_NONE) return;
+    const float *b = d_aabb6 + 6 * (size_t)e;
+    a.la[0][slot] = make_float2(b[0], b[3]);
+    a.la[1][slot] = make_float2(b[1], b[4]);
+    a.la[2][slot] = make_float2(b[2], b[5]);
+    atomicOr(a.flags + slot, F_DIRTY_SELF); // world box must be rebuilt
+}
+
+__global__ void __launch_bounds__(kBlock) k_gather_globals(const NodeArrays a, const uint32_t count, const uint32_t *d_idx,
+                                                           const uint32_t *slot_of_node, const uint32_t n_nodes,
+                                                           float *d_out)
+{
+    const uint32_t e = blockIdx.x * kBlock + threadIdx.x;
+    if (e >= count) return;
+    const uint32_t slot = resolve_slot(d_idx, e, slot_of_node, n_nodes);
+    Affine Gm = affine_identity();
+    if (slot != FYX_NONE) {
+        Gm.r0 = a.G[0][slot];
+        Gm.r1 = a.G[1][slot];
+        Gm.r2 = a.G[2][slot];
+    }
+    float4 *o = reinterpret_cast<float4 *>(d_out + 16 * (size_t)e);
+    o[0] = make_float4(Gm.r0.x, Gm.r1.x, Gm.r2.x, 0.0f);
+    o[1] = make_float4(Gm.r0.y, Gm.r1.y, Gm.r2.y, 0.0f);
+    o[2] = make_float4(Gm.r0.z, Gm.r1.z, Gm.r2.z, 0.0f);
+    o[3] = make_float4(Gm.r0.w, Gm.r1.w, Gm.r2.w, 1.0f);
+}
+
+__global__ void __launch_bounds__(kBlock) k_gather_aabbs(const NodeArrays a, const uint32_t count, const uint32_t *d_idx,
+                                                         const uint32_t *slot_of_node, const uint32_t n_nodes, float *d_out)
+{
+    const uint32_t e = blockIdx.x * kBlock + threadIdx.x;
+    if (e >= count) return;
+    const uint32_t slot = resolve_slot(d_idx, e, slot_of_node, n_nodes);
+    float *o = d_out + 6 * (size_t)e;
+    if (slot == FYX_NONE) { // AxisAlignedBoundingBox::default()
+        o[0] = o[1] = o[2] = 3.402823466e38f;
+        o[3] = o[4] = o[5] = -3.402823466e38f;
+        return;
+    }
+    const float2 x = a.wa[0][slot], y = a.wa[1][slot], z = a.wa[2][slot];
+    o[0] = x.x; o[1] = y.x; o[2] = z.x;
+    o[3] = x.y; o[4] = y.y; o[5] = z.y;
+}
+
+__global__ void __launch_bounds__(kBlock) k_gather_flags(const NodeArrays a, const uint32_t count, const uint32_t *d_idx,
+                                                         const uint32_t *slot_of_node, const uint32_t n_nodes,
+                                                         uint32_t *d_out)
+{
+    const uint32_t e = blockIdx.x * kBlock + threadIdx.x;
+    if (e >= count) return;
+    const uint32_t slot = resolve_slot(d_idx, e, slot_of_node, n_nodes);
+    d_out[e] = (slot == FYX_NONE) ? 0u
+                                  : (a.flags[slot] & (FYX_NODE_INPUT_MASK | FYX_NODE_GLOBAL_VISIBILITY |
+                                                      FYX_NODE_GLOBAL_ENABLED | FYX_NODE_REACHABLE));
+}
+
+// VertexBuffer bytes (scene/mesh/buffer.rs:404-414) → SoA streams.  Done once per surface at load.
+__global__ void __launch_bounds__(kBlock) k_deinterleave(const uint32_t n_verts, const uint32_t n_padded,
+                                                         const unsigned char *d_bytes, const fyx_vertex_layout l,
+                                                         const uint32_t n_bones, float *vpos, float *vnrm, float4 *vw,
+                                                         uint32_t *vidx, uint32_t *d_err)
+{
+    const uint32_t v = blockIdx.x * kBlock + threadIdx.x;
+    if (v >= n_padded) return;
+    float p[3] = {0.f, 0.f, 0.f}, n[3] = {0.f, 0.f, 0.f};
+    float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
+    uint32_t bi = 0u;
+    if (v < n_verts) {
+        const unsigned char *vp = d_bytes + (size_t)v * l.stride;
+        const float *fp = reinterpret_cast<const float *>(vp + l.position_offset);
+        const float *fn = reinterpret_cast<const float *>(vp + l.normal_offset);
+        const float *fw = reinterpret_cast<const float *>(vp + l.bone_weights_offset);
+        p[0] = fp[0]; p[1] = fp[1]; p[2] = fp[2];
+        n[0] = fn[0]; n[1] = fn[1]; n[2] = fn[2];
+        w = make_float4(fw[0], fw[1], fw[2], fw[3]);
+        bi = *reinterpret_cast<const uint32_t *>(vp + l.bone_indices_offset);
+        uint32_t bad = 0u;
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            if (((bi >> (8 * k)) & 0xFFu) >= n_bones) bad = 1u;
+        if (bad) { // the reference would panic on the out-of-range index (mesh/mod.rs:515)
+            atomicOr(d_err, E_BAD_BONE_INDEX);
+            bi = 0u;
+            w = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        if (!((fabsf(p[0]) <= 3.402823466e38f) & (fabsf(p[1]) <= 3.402823466e38f) & (fabsf(p[2]) <= 3.402823466e38f)))
+            atomicOr(d_err, E_NONFINITE_VERTEX);
+    }
+    vpos[3 * (size_t)v + 0] = p[0]; vpos[3 * (size_t)v + 1] = p[1]; vpos[3 * (size_t)v + 2] = p[2];
+    vnrm[3 * (size_t)v + 0] = n[0]; vnrm[3 * (size_t)v + 1] = n[1]; vnrm[3 * (size_t)v + 2] = n[2];
+    vw[v] = w;
+    vidx[v] = bi;
+}
+
+__global__ void __launch_bounds__(kBlock) k_ib_rows(const uint32_t n, const float *d_m16, float4 *r0, float4 *r1, float4 *r2,
+                                                    uint32_t *d_err)
+{
+    const uint32_t e = blockIdx.x * kBlock + threadIdx.x;
+    if (e >= n) return;
+    Affine A;
+    if (!load_affine_rows(d_m16 + 16 * (size_t)e, A)) {
+        atomicOr(d_err, E_NOT_AFFINE);
+        A = affine_identity();
+    }
+    r0[e] = A.r0;
+    r1[e] = A.r1;
+    r2[e] = A.r2;
+}
+
+__global__ void k_or_u32(uint32_t *p, const uint32_t bits) { atomicOr(p, bits); }
+
+// After the fixed-slot NCCL all-gather of a visible list: rank r's entries sit at pad[r*maxc ..];
+// pack them back to back (rank order) so every rank holds one contiguous list per frustum.
+__global__ void __launch_bounds__(kBlock) k_compact_gathered(const uint32_t *pad, const uint32_t maxc,
+                                                             const uint32_t *counts_all, const int nranks, const int f,
+                                                             uint32_t *dst)
+{
+    const uint64_t i = (uint64_t)blockIdx.x * kBlock + threadIdx.x;
+    if (!maxc) return;
+    const uint32_t r = (uint32_t)(i / maxc), j = (uint32_t)(i % maxc);
+    if (r >= (uint32_t)nranks) return;
+    if (j >= counts_all[r * FYX_MAX_FRUSTA + f]) return;
+    uint32_t off = 0;
+    for (uint32_t q = 0; q < r; ++q) off += counts_all[q * FYX_MAX_FRUSTA + f];
+    dst[off + j] = pad[(size_t)r * maxc + j];
+}
+
+// ------------------------------------------------------------------------------------------------
+// launchers
+// ------------------------------------------------------------------------------------------------
+static inline unsigned grid_for(uint64_t n) { return (unsigned)((n + kBlock - 1) / kBlock); }
+
+void launch_update_level(cudaStream_t s, const NodeArrays &a, uint32_t lo, uint32_t hi, bool update_all, const CullParams *cull)
+{
+    if (hi <= lo) return;
+    if (cull) {
+        k_update_level<true><<<grid_for(hi - lo), kBlock, 0, s>>>(a, lo, hi, update_all ? 1u : 0u, *cull);
+    } else {
+        CullParams none;
+        none.nf = 0;
+        k_update_level<false><<<grid_for(hi - lo), kBlock, 0, s>>>(a, lo, hi, update_all ? 1u : 0u, none);
+    }
+}
+
+void launch_cull(cudaStream_t s, const NodeArrays &a, const CullParams &cp)
+{
+    if (!a.cap) return;
+    k_cull<<<grid_for(a.cap), kBlock, 0, s>>>(a, cp);
+}
+
+void launch_fold_bones(cudaStream_t s, const NodeArrays &a, const FoldArrays &fa, const CullParams *cull)
+{
+    if (!fa.n) return;
+    if (cull) {
+        k_fold_bones<true><<<grid_for(fa.n), kBlock, 0, s>>>(a, fa, *cull);
+    } else {
+        CullParams none;
+        none.nf = 0;
+        k_fold_bones<false><<<grid_for(fa.n), kBlock, 0, s>>>(a, fa, none);
+    }
+}
+
+void launch_palette(cudaStream_t s, const NodeArrays &a, const SkinArrays &sk)
+{
+    if (!sk.n_entries) return;
+    k_palette<<<grid_for(sk.n_entries), kBlock, 0, s>>>(a, sk);
+}
+
+void launch_skin(cudaStream_t s, const SkinArrays &sk, const SkinTile *tiles, uint32_t n_tiles)
+{
+    if (!n_tiles) return;
+    const size_t smem = (size_t)FYX_MAX_BONES * 3 * sizeof(float4); // 12 240 B: fits the default 48 KB window
+    k_skin<<<n_tiles, kBlock, smem, s>>>(sk, tiles);
+}
+
+void launch_scatter_locals(cudaStream_t s, const NodeArrays &a, uint32_t count, const uint32_t *d_idx, const float *d_m16,
+                           const uint32_t *slot_of_node, uint32_t n_nodes, uint32_t *d_err)
+{
+    if (!count) return;
+    k_scatter_locals<<<grid_for(count), kBlock, 0, s>>>(a, count, d_idx, d_m16, slot_of_node, n_nodes, d_err);
+}
+
+void launch_scatter_u32(cudaStream_t s, uint32_t *dst_col, uint32_t *, uint32_t count, const uint32_t *d_idx,
+                        const uint32_t *d_val, const uint32_t *slot_of_node, uint32_t n_nodes, int mode)
+{
+    if (!count) return;
+    k_scatter_u32<<<grid_for(count), kBlock, 0, s>>>(dst_col, count, d_idx, d_val, slot_of_node, n_nodes, mode);
+}
+
+void launch_scatter_aabbs(cudaStream_t s, const NodeArrays &a, uint32_t count, const uint32_t *d_idx, const float *d_aabb6,
+                          const uint32_t *slot_of_node, uint32_t n_nodes)
+{
+    if (!count) return;
+    k_scatter_aabbs<<<grid_for(count), kBlock, 0, s>>>(a, count, d_idx, d_aabb6, slot_of_node, n_nodes);
+}
+
+void launch_gather_globals(cudaStream_t s, const NodeArrays &a, uint32_t count, const uint32_t *d_idx,
+                           const uint32_t *slot_of_node, uint32_t n_nodes, float *d_out)
+{
+    if (!count) return;
+    k_gather_globals<<<grid_for(count), kBlock, 0, s>>>(a, count, d_idx, slot_of_node, n_nodes, d_out);
+}
+
+void launch_gather_aabbs(cudaStream_t s, const NodeArrays &a, uint32_t count, const uint32_t *d_idx,
+                         const uint32_t *slot_of_node, uint32_t n_nodes, float *d_out6)
+{
+    if (!count) return;
+    k_gather_aabbs<<<grid_for(count), kBlock, 0, s>>>(a, count, d_idx, slot_of_node, n_nodes, d_out6);
+}
+
+void launch_gather_flags(cudaStream_t s, const NodeArrays &a, uint32_t count, const uint32_t *d_idx,
+                         const uint32_t *slot_of_node, uint32_t n_nodes, uint32_t *d_out)
+{
+    if (!count) return;
+    k_gather_flags<<<grid_for(count), kBlock, 0, s>>>(a, count, d_idx, slot_of_node, n_nodes, d_out);
+}
+
+void launch_deinterleave(cudaStream_t s, uint32_t n_verts, const unsigned char *d_bytes, fyx_vertex_layout layout,
+                         uint32_t n_bones, float *vpos, float *vnrm, float4 *vw, uint32_t *vidx, uint32_t *d_err)
+{
+    const uint32_t n_padded = (n_verts + 3u) & ~3u;
+    if (!n_padded) return;
+    k_deinterleave<<<grid_for(n_padded), kBlock, 0, s>>>(n_verts, n_padded, d_bytes, layout, n_bones, vpos, vnrm, vw, vidx,
+                                                         d_err);
+}
+
+void launch_ib_rows(cudaStream_t s, uint32_t n, const float *d_m16, float4 *r0, float4 *r1, float4 *r2, uint32_t *d_err)
+{
+    if (!n) return;
+    k_ib_rows<<<grid_for(n), kBlock, 0, s>>>(n, d_m16, r0, r1, r2, d_err);
+}
+
+void launch_or_u32(cudaStream_t s, uint32_t *p, uint32_t bits) { k_or_u32<<<1, 1, 0, s>>>(p, bits); }
+
+void launch_compact_gathered(cudaStream_t s, const uint32_t *pad, uint32_t maxc, const uint32_t *counts_all, int nranks, int f,
+                             uint32_t *dst)
+{
+    if (!maxc || nranks <= 0) return;
+    k_compact_gathered<<<grid_for((uint64_t)maxc * nranks), kBlock, 0, s>>>(pad, maxc, counts_all, nranks, f, dst);
+}
+
+} // namespace fyx

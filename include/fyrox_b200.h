@@ -1,0 +1,240 @@
+/*
+ * fyrox_b200.h — C ABI of libfyrox_b200: Fyrox's per-frame render-prep hot path on B200 (sm_100a).
+ *
+ * The reference (Rust) has no FFI seam on this path; these entry points are what
+ * a Rust `-sys` shim would bind.  Each one names the reference interface it replaces (paths relative
+ * to the Fyrox tree).  See INTEGRATION.md for the Rust-side binding and call sites.
+ *
+ * Conventions
+ *  - extern "C", plain pointers and sizes; no exceptions cross the boundary.
+ *  - Return value: FYX_OK (0) or a negative fyx_status; fyx_last_error(ctx) gives a message.  This mirrors
+ *    the reference's "log and continue" policy: invalid handles are skipped, never fatal
+ *    (scene/graph/mod.rs:1167,1206; scene/mesh/mod.rs:785-791).
+ *  - Node index i == Handle::index() of the node in Graph's Pool<Node>; capacity == Pool::get_capacity()
+ *    (fyrox-core/src/pool/mod.rs:1104).  0xFFFFFFFF == Handle::NONE.
+ *  - Matrices are 16 f32, column-major — nalgebra's Matrix4<f32> memory layout (bytemuck-castable).
+ *    Only affine matrices (bottom row exactly 0,0,0,1) are accepted: that is all Transform::matrix()
+ *    can produce (scene/transform.rs:476-539).
+ *  - Caller owns every pointer it passes in; inputs are consumed before the call returns.  Pointers
+ *    returned by fyx_get_visible* are library-owned and valid until the next fyx_cull*, fyx_render_prep or
+ *    fyx_destroy on that context.
+ *  - One fyx_ctx is used from one thread at a time (the engine's game-loop thread, engine/executor.rs:470-517).
+ *  - There is no CPU fallback: every compute entry point runs hand-written sm_100a kernels and fails
+ *    with FYX_ERR_CUDA if no device is usable.
+ */
+#ifndef FYROX_B200_H
+#define FYROX_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FYX_ABI_VERSION 1u
+#define FYX_NONE 0xFFFFFFFFu
+#define FYX_MAX_FRUSTA 8u      /* frusta per fyx_cull call: 1 camera, 3 CSM cascades, 6 cube faces */
+#define FYX_MAX_BONES 255u     /* fyrox-material/src/shader/mod.rs:613; u8 indices scene/mesh/vertex.rs:154 */
+
+typedef enum fyx_status {
+    FYX_OK = 0,
+    FYX_ERR_INVALID_ARGUMENT = -1,
+    FYX_ERR_CUDA = -2,            /* CUDA runtime/driver error, or no sm_100 device */
+    FYX_ERR_OUT_OF_MEMORY = -3,
+    FYX_ERR_NOT_AFFINE = -4,      /* a matrix with a bottom row other than (0,0,0,1) or a non-finite entry */
+    FYX_ERR_TOPOLOGY = -5,        /* cycle in parent[] / parent out of range */
+    FYX_ERR_STATE = -6,           /* call order (e.g. cull before set_topology) */
+    FYX_ERR_NCCL = -7,
+    FYX_ERR_UNSUPPORTED = -8
+} fyx_status;
+
+/* Per-node flag word (inputs).  Bits 0..3 are Base's fields (scene/base.rs:412-432 and TrackedProperty
+ * visibility/enabled :441-450), bit 4 the pool record's liveness, bit 5 "this node kind emits render
+ * data and is frustum-tested" (Mesh::collect_render_data, scene/mesh/mod.rs:691-698). */
+#define FYX_NODE_VISIBILITY      (1u << 0)
+#define FYX_NODE_ENABLED         (1u << 1)
+#define FYX_NODE_FRUSTUM_CULLING (1u << 2)
+#define FYX_NODE_CAST_SHADOWS    (1u << 3)
+#define FYX_NODE_ALIVE           (1u << 4)
+#define FYX_NODE_RENDERABLE      (1u << 5)
+#define FYX_NODE_INPUT_MASK      0x3Fu
+/* Computed bits, readable through fyx_get_global_flags (Base::global_visibility / is_globally_enabled,
+ * scene/base.rs:751-770) */
+#define FYX_NODE_GLOBAL_VISIBILITY (1u << 8)
+#define FYX_NODE_GLOBAL_ENABLED    (1u << 9)
+#define FYX_NODE_REACHABLE         (1u << 10)  /* reached by the DFS from Graph::root (renderer/bundle.rs:1004) */
+
+/* fyx_update_transforms flags */
+#define FYX_UPDATE_INCREMENTAL 0u  /* Graph::update semantics: only sub-trees under changed nodes (process_node_messages) */
+#define FYX_UPDATE_ALL         1u  /* Graph::update_hierarchical_data semantics: everything from the root */
+
+/* fyx_cull pass flags */
+#define FYX_PASS_SHADOW (1u << 0)  /* renderer::is_shadow_pass ⇒ nodes without cast_shadows are dropped */
+
+typedef struct fyx_ctx fyx_ctx;
+
+typedef struct fyx_config {
+    uint32_t struct_size;   /* = sizeof(fyx_config) */
+    int32_t  device;        /* CUDA device ordinal; -1 = current device */
+    void    *stream;        /* cudaStream_t to launch on; NULL = the context creates its own */
+    uint32_t flags;         /* reserved, 0 */
+} fyx_config;
+
+/* Frustum as fyrox-math/src/frustum.rs:26-30: planes 0 left,1 right,2 top,3 bottom,4 far,5 near, each
+ * (nx,ny,nz,d) normalised; 8 corners in the order of frustum.rs:70-79. */
+typedef struct fyx_frustum {
+    float planes[6][4];
+    float corners[8][3];
+} fyx_frustum;
+
+/* Where the attributes live inside one interleaved vertex (VertexBuffer layout, scene/mesh/buffer.rs:404-414).
+ * AnimatedVertex (scene/mesh/vertex.rs:140-210): stride 68, position 0, normal 20, weights 48, indices 64. */
+typedef struct fyx_vertex_layout {
+    uint32_t stride;
+    uint32_t position_offset;      /* f32 x3 */
+    uint32_t normal_offset;        /* f32 x3 */
+    uint32_t bone_weights_offset;  /* f32 x4 */
+    uint32_t bone_indices_offset;  /* u8  x4 */
+} fyx_vertex_layout;
+
+/* Device-side durations of the stages run by the last fyx_render_prep / individual calls, in ms
+ * (the GPU path's counterpart of GraphPerformanceStatistics, scene/graph/mod.rs:94-122). */
+typedef struct fyx_timings {
+    float upload_ms;    /* H2D + scatter of changed local matrices / flags */
+    float update_ms;    /* hierarchy + world AABB (+ fused cull) */
+    float cull_ms;      /* stand-alone cull */
+    float palette_ms;
+    float skin_ms;
+    float readback_ms;  /* D2H of visible counts + lists */
+    float total_ms;
+} fyx_timings;
+
+/* ---- life cycle -------------------------------------------------------------------------- */
+uint32_t    fyx_abi_version(void);
+int32_t     fyx_create(const fyx_config *cfg, fyx_ctx **out_ctx);
+void        fyx_destroy(fyx_ctx *ctx);
+const char *fyx_last_error(const fyx_ctx *ctx);   /* ctx may be NULL: last error of fyx_create on this thread */
+int32_t     fyx_sync(fyx_ctx *ctx);
+/* Pinned host memory for zero-staging transfers (optional; any host pointer is accepted everywhere). */
+void       *fyx_host_alloc(size_t bytes);
+void        fyx_host_free(void *p);
+
+/* ---- host-side math on the path (tiny, per frustum) ---------------------------------------- */
+/* Frustum::from_view_projection_matrix (fyrox-math/src/frustum.rs:54-82) with Plane::from_abcd /
+ * intersection_point (plane.rs:63-75,94-102).  Returns FYX_ERR_INVALID_ARGUMENT where the reference
+ * returns None (a zero-length plane normal); callers then use fyx_frustum_default like
+ * renderer/bundle.rs:893-896 (`unwrap_or_default`). */
+int32_t fyx_frustum_from_view_projection_matrix(const float vp_m16[16], fyx_frustum *out);
+void    fyx_frustum_default(fyx_frustum *out);                      /* frustum.rs:32-43 */
+/* Matrix4 * Matrix4 in nalgebra's accumulation order (projection * view, renderer/bundle.rs:894). */
+void    fyx_mat4_mul(const float a_m16[16], const float b_m16[16], float out_m16[16]);
+
+/* ---- scene description (on load / when the hierarchy changes) ------------------------------ */
+/* Replaces the pointer graph walked by Graph::update_hierarchical_data (scene/graph/mod.rs:1272-1292):
+ * parent[i] = Base::parent index or FYX_NONE; flags[i] = FYX_NODE_* input bits; render_mask[i] =
+ * Base::render_mask (NULL = all ones); local_aabb_minmax = 6 f32 per node (min xyz, max xyz) —
+ * NodeTrait::local_bounding_box (Mesh: scene/mesh/mod.rs:631-656; others the unit box, scene/base.rs:733-735;
+ * NULL = unit box everywhere).  root = Graph::root index.  global_index (optional, NULL = identity) is the
+ * value written to visible lists for node i — used when a context holds one shard of a larger graph.
+ * Marks every node changed (like Base::on_connected_to_graph, scene/base.rs:520-540). */
+int32_t fyx_set_topology(fyx_ctx *ctx, uint32_t capacity, uint32_t root, const uint32_t *parent,
+                         const uint32_t *flags, const uint32_t *render_mask, const float *local_aabb_minmax,
+                         const uint32_t *global_index);
+
+/* Transform::matrix() of `count` nodes (scene/transform.rs:544-550); idx NULL = nodes 0..count-1.
+ * Equivalent of `local_transform_mut()` → NodeMessageKind::TransformChanged (scene/base.rs:343-352). */
+int32_t fyx_set_local_matrices(fyx_ctx *ctx, uint32_t count, const uint32_t *idx, const float *m16_colmajor);
+/* Base::set_visibility / set_enabled / frustum_culling / cast_shadows (VisibilityChanged / EnabledFlagChanged). */
+int32_t fyx_set_flags(fyx_ctx *ctx, uint32_t count, const uint32_t *idx, const uint32_t *flags);
+int32_t fyx_set_render_masks(fyx_ctx *ctx, uint32_t count, const uint32_t *idx, const uint32_t *render_mask);
+int32_t fyx_set_local_aabbs(fyx_ctx *ctx, uint32_t count, const uint32_t *idx, const float *aabb_minmax);
+
+/* One skinned Surface of Mesh node `mesh_node` (scene/mesh/surface.rs:1249-1271): `bone_nodes` = Surface::bones
+ * indices (≤255), inv_bind_m16 = each bone's Base::inv_bind_pose_transform (scene/base.rs:482), verts = the
+ * surface's VertexBuffer bytes (n_verts * layout->stride).  Surfaces of one mesh are folded into its world
+ * AABB in call order (scene/mesh/mod.rs:676-682).  verts may be NULL with n_verts 0 (palette only). */
+int32_t fyx_add_skinned_surface(fyx_ctx *ctx, uint32_t mesh_node, uint32_t n_bones, const uint32_t *bone_nodes,
+                                const float *inv_bind_m16, uint32_t n_verts, const void *verts,
+                                const fyx_vertex_layout *layout, uint32_t *out_surface_id);
+/* Finish a batch of fyx_add_skinned_surface calls (builds the device-side bone/vertex tables). Called
+ * implicitly by the first per-frame call that needs them. */
+int32_t fyx_commit_surfaces(fyx_ctx *ctx);
+
+/* ---- per frame ----------------------------------------------------------------------------- */
+/* Graph::update → process_node_messages (scene/graph/mod.rs:1303-1399, 1459-1473): global transforms
+ * (update_global_transform_recursively :1199-1241), global visibility / enabled (:1166-1197), world AABBs
+ * (AxisAlignedBoundingBox::transform, fyrox-math/src/aabb.rs:264-287; Mesh::on_global_transform_changed,
+ * scene/mesh/mod.rs:667-689). */
+int32_t fyx_update_transforms(fyx_ctx *ctx, uint32_t update_flags);
+
+/* RenderDataBundleStorage::from_graph reduced to its visible-node set (renderer/bundle.rs:873-1009):
+ * for each frustum f, the nodes for which NodeTrait::should_be_rendered(frustum, cam_mask[f])
+ * (scene/node/mod.rs:231-256, Frustum::is_intersects_aabb fyrox-math/src/frustum.rs:222-245) holds, that are
+ * alive, renderable and reachable from the root, and (pass_flags[f] & FYX_PASS_SHADOW) ⇒ cast_shadows.
+ * cam_mask NULL = all ones; pass_flags NULL = 0.  The list is a SET: its order is unspecified. */
+int32_t fyx_cull(fyx_ctx *ctx, uint32_t n_frusta, const fyx_frustum *frusta, const uint32_t *cam_mask,
+                 const uint32_t *pass_flags);
+/* fyx_update_transforms + fyx_cull in one pass over the node arrays (world AABBs stay in registers). */
+int32_t fyx_update_and_cull(fyx_ctx *ctx, uint32_t update_flags, uint32_t n_frusta, const fyx_frustum *frusta,
+                            const uint32_t *cam_mask, const uint32_t *pass_flags);
+/* Visible list of frustum f as node indices (global_index values): host copy (pinned) ... */
+int32_t fyx_get_visible(fyx_ctx *ctx, uint32_t frustum, const uint32_t **out_idx, uint32_t *out_count);
+/* ... or device-resident (for a GPU consumer / a collective); *d_count points at one device u32. */
+int32_t fyx_get_visible_device(fyx_ctx *ctx, uint32_t frustum, const uint32_t **d_idx, const uint32_t **d_count);
+
+/* SurfaceInstanceData::bone_matrices for every skinned surface (scene/mesh/mod.rs:781-793):
+ * P[k] = bone_k.global_transform * bone_k.inv_bind_pose_transform; dead / FYX_NONE bone ⇒ identity. */
+int32_t fyx_build_palettes(fyx_ctx *ctx);
+/* Linear-blend skinning of every skinned surface: positions as Mesh::accurate_world_bounding_box
+ * (scene/mesh/mod.rs:501-522), normals as the standard shader (fyrox-material/src/shader/standard/opengl/
+ * standard.shader:192-195) — into device-resident position / normal streams. */
+int32_t fyx_skin(fyx_ctx *ctx);
+
+/* One whole frame of render prep, in stream order, with one host synchronisation at the end:
+ * upload changed local matrices → update (+cull) → palettes → skin → visible lists to the host.
+ * Any of the parts may be empty (count 0 / n_frusta 0 / no surfaces). */
+typedef struct fyx_frame_desc {
+    uint32_t struct_size;
+    uint32_t update_flags;
+    uint32_t n_changed;            /* changed local matrices this frame */
+    const uint32_t *changed_idx;   /* NULL = nodes 0..n_changed-1 */
+    const float *changed_m16;
+    uint32_t n_frusta;
+    const fyx_frustum *frusta;
+    const uint32_t *cam_mask;
+    const uint32_t *pass_flags;
+    uint32_t do_palettes;
+    uint32_t do_skin;
+    uint32_t readback_visible;     /* copy counts + lists to the host before returning */
+} fyx_frame_desc;
+int32_t fyx_render_prep(fyx_ctx *ctx, const fyx_frame_desc *frame);
+
+/* ---- read-back (tests, tools, and the parts of the engine that stay on the CPU) -------------- */
+int32_t fyx_get_global_matrices(fyx_ctx *ctx, uint32_t count, const uint32_t *idx, float *out_m16);   /* Base::global_transform */
+int32_t fyx_get_world_aabbs(fyx_ctx *ctx, uint32_t count, const uint32_t *idx, float *out_minmax);    /* NodeTrait::world_bounding_box */
+int32_t fyx_get_global_flags(fyx_ctx *ctx, uint32_t count, const uint32_t *idx, uint32_t *out_flags);
+int32_t fyx_get_palette(fyx_ctx *ctx, uint32_t surface_id, float *out_m16 /* n_bones*16 */);
+int32_t fyx_get_skinned(fyx_ctx *ctx, uint32_t surface_id, float *out_pos3, float *out_nrm3 /* n_verts*3 each; either may be NULL */);
+int32_t fyx_get_skinned_device(fyx_ctx *ctx, uint32_t surface_id, const float **d_pos3, const float **d_nrm3);
+int32_t fyx_get_timings(fyx_ctx *ctx, fyx_timings *out);
+/* Number of kernels this context has launched so far (bench.py's gpu_launches). */
+uint64_t fyx_kernel_launch_count(const fyx_ctx *ctx);
+
+/* ---- multi-GPU: one context per GPU, one process per GPU ------------------------------------- */
+/* The node array is sharded (sub-trees + replicated ancestors); each context culls its
+ * shard; the per-frustum visible lists are all-gathered with NCCL over NVLink so every rank holds
+ * the whole list.  Rank 0 obtains an id, the host broadcasts it, every rank calls fyx_comm_init. */
+#define FYX_COMM_ID_BYTES 128
+int32_t fyx_comm_get_unique_id(void *out_id128);
+int32_t fyx_comm_init(fyx_ctx *ctx, int32_t nranks, int32_t rank, const void *id128);
+/* All-gather the visible lists of the last cull (counts, then payload in max-count slots). */
+int32_t fyx_allgather_visible(fyx_ctx *ctx);
+/* Gathered list of frustum f: concatenation over ranks (device-resident and, if readback, on the host). */
+int32_t fyx_get_visible_gathered(fyx_ctx *ctx, uint32_t frustum, const uint32_t **out_idx, uint32_t *out_count);
+int32_t fyx_get_visible_gathered_device(fyx_ctx *ctx, uint32_t frustum, const uint32_t **d_idx, uint32_t *out_count);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FYROX_B200_H */
