@@ -6,7 +6,6 @@ import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
-REPO = os.path.dirname(_HERE)
 
 
 def _run(cmd, cwd):
@@ -20,12 +19,5 @@ def build_all(verbose: bool = False) -> None:
     """libfyrox_b200.so (CUDA, sm_100a) + libfyrox_scenegen.so (host) into fyrox_b200/lib/."""
     os.makedirs(os.path.join(_HERE, "lib"), exist_ok=True)
     out = _run(["make", "-C", CSRC, "all"], CSRC)
-    if verbose:
-        print(out)
-
-
-def build_oracle(verbose: bool = False) -> None:
-    """The CPU oracle (test infrastructure, oracle/)."""
-    out = _run(["make", "-C", os.path.join(REPO, "oracle"), "all"], REPO)
     if verbose:
         print(out)

@@ -1,0 +1,410 @@
+"""GPU parity: the CUDA path (through the C ABI) against the oracle on the same seeded inputs.
+Bit-exact for matrices, boxes, flags, palettes and skinned streams; identical visible SETS."""
+import numpy as np
+import pytest
+
+import fyrox_b200 as fb
+import oracle_binding as ob
+from fyrox_b200.scenegen import Scene
+from helpers import (NONE, UNIT_BOX, assert_same_hierarchy, assert_same_visible, camera_frustum, cube_frusta, random_graph,
+                     scene_pair)
+
+pytestmark = pytest.mark.gpu
+
+
+def reachable_from_root(parent, flags):
+    n = len(parent)
+    alive = (flags & fb.NODE_ALIVE) != 0
+    reach = np.zeros(n, bool)
+    reach[0] = True
+    # iterate to a fixed point (parents may come after children in index order)
+    changed = True
+    while changed:
+        ok = alive & (parent != NONE)
+        new = reach.copy()
+        new[ok] |= reach[parent[ok]] & alive[parent[ok]]
+        changed = bool((new != reach).any())
+        reach = new
+    return reach
+
+
+# ---- hierarchy + boxes -------------------------------------------------------------------------------
+@pytest.mark.parametrize("n,units", [(2000, 0), (30000, 0), (30000, 50)])
+def test_update_matches_oracle_on_generated_scenes(ctx, n, units):
+    sc = Scene(n, n_units=units, verts_per_unit=40)
+    og, _ = scene_pair(sc, ctx)
+    og.update_hierarchical_data()
+    ctx.update_transforms(fb.UPDATE_ALL)
+    assert_same_hierarchy(og, ctx)
+
+
+@pytest.mark.parametrize("seed,chain", [(1, 0.0), (2, 0.3), (3, 0.9)])
+def test_update_matches_oracle_on_random_forests(ctx, seed, chain):
+    rng = np.random.default_rng(seed)
+    parent, flags, mask, local, aabb = random_graph(rng, 3000, max_depth_bias=chain)
+    og = ob.Graph.build(parent, flags, mask, local, aabb)
+    og.update_hierarchical_data()
+    ctx.set_topology(parent, flags, mask, aabb)
+    ctx.set_local_matrices(local)
+    ctx.update_transforms(fb.UPDATE_ALL)
+    reach = reachable_from_root(parent, flags)
+    F = ctx.get_global_flags()
+    assert (((F & fb.NODE_REACHABLE) != 0) == reach).all()
+    assert_same_hierarchy(og, ctx, np.nonzero(reach)[0])
+    # free pool records read back as identity / default box / 0
+    dead = np.nonzero((flags & fb.NODE_ALIVE) == 0)[0]
+    if dead.size:
+        assert (ctx.get_global_matrices(dead) == np.eye(4, dtype=np.float32).reshape(16)).all()
+        assert (ctx.get_global_flags(dead) == 0).all()
+
+
+def test_incremental_update_equals_process_node_messages(ctx):
+    """Graph::update semantics: only changed sub-trees are recomputed; result equals the oracle's
+    message-driven update, including the stale skinned-mesh box when only bones move."""
+    sc = Scene(20000, n_units=30, verts_per_unit=20)
+    og, _ = scene_pair(sc, ctx)
+    og.update_hierarchical_data()
+    ctx.update_transforms(fb.UPDATE_ALL)
+    rng = np.random.default_rng(5)
+    for frame in range(3):
+        # animate every bone + move a few random static nodes + toggle some flags
+        idx, m = sc.animate(frame)
+        static_nodes = np.setdiff1d(np.arange(1, sc.capacity), idx)  # a node must not get two different matrices in one batch
+        extra = rng.choice(static_nodes, 25, replace=False).astype(np.uint32)
+        em = sc.local_m16[extra].copy()
+        em[:, 12:15] += rng.uniform(-5, 5, (25, 3)).astype(np.float32)
+        all_idx = np.concatenate([idx, extra])
+        all_m = np.concatenate([m, em])
+        for i, mm in zip(all_idx, all_m):
+            og.set_local_matrix(int(i), mm)
+        tog = rng.choice(np.arange(1, sc.capacity), 10, replace=False).astype(np.uint32)
+        newf = sc.flags[tog] ^ np.uint32(fb.NODE_VISIBILITY)
+        for i, f in zip(tog, newf):
+            og.set_visibility(int(i), bool(f & fb.NODE_VISIBILITY))
+        sc.flags[tog] = newf  # scene arrays are views of generator memory: keep them in step
+        og.update()
+        ctx.set_local_matrices(all_m, all_idx)
+        ctx.set_flags(newf, tog)
+        ctx.update_transforms(fb.UPDATE_INCREMENTAL)
+        assert_same_hierarchy(og, ctx)
+
+
+def test_skinned_mesh_box_quirk_matches(ctx):
+    """Bones visited before the mesh contribute their new position; a mesh whose own transform did
+    not change keeps its cached box (scene/mesh/mod.rs:667-689)."""
+    parent = np.array([NONE, 0, 0], np.uint32)
+    flags = np.array([fb.NODE_DEFAULT, fb.NODE_DEFAULT, fb.NODE_DEFAULT | fb.NODE_RENDERABLE], np.uint32)
+    aabb = np.stack([UNIT_BOX, UNIT_BOX, np.array([-1, -1, -1, 1, 1, 1], np.float32)])
+    local = np.tile(np.eye(4, dtype=np.float32).reshape(16), (3, 1))
+    local[1] = ob.translation(10, 0, 0)
+    ctx.set_topology(parent, flags, None, aabb)
+    ctx.set_local_matrices(local)
+    ctx.add_skinned_surface(2, [1], np.eye(4, dtype=np.float32).reshape(1, 16))
+    ctx.update_transforms(fb.UPDATE_INCREMENTAL)
+    assert ctx.get_world_aabbs([2])[0].tolist() == [-1, -1, -1, 10, 1, 1]
+    ctx.set_local_matrices(ob.translation(20, 0, 0).reshape(1, 16), [1])
+    ctx.update_transforms(fb.UPDATE_INCREMENTAL)
+    assert ctx.get_world_aabbs([2])[0].tolist() == [-1, -1, -1, 10, 1, 1]  # stale, like the reference
+    ctx.set_local_matrices(np.eye(4, dtype=np.float32).reshape(1, 16), [2])
+    ctx.update_transforms(fb.UPDATE_INCREMENTAL)
+    assert ctx.get_world_aabbs([2])[0].tolist() == [-1, -1, -1, 20, 1, 1]
+
+
+# ---- cull --------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("fused", [False, True])
+def test_cull_one_frustum_matches_oracle(ctx, fused):
+    sc = Scene(60000, n_units=40, verts_per_unit=20)
+    og, _ = scene_pair(sc, ctx)
+    og.update_hierarchical_data()
+    fo, ff = camera_frustum()
+    if fused:
+        ctx.update_and_cull([ff], fb.UPDATE_ALL)
+    else:
+        ctx.update_transforms(fb.UPDATE_ALL)
+        ctx.cull([ff])
+    n_vis = assert_same_visible(og, ctx, [fo])
+    assert 0 < n_vis < sc.n_renderable
+
+
+@pytest.mark.parametrize("fused", [False, True])
+def test_cull_six_cube_faces_with_masks_and_shadow_pass(ctx, fused):
+    sc = Scene(60000, n_units=40, verts_per_unit=20)
+    og, _ = scene_pair(sc, ctx)
+    og.update_hierarchical_data()
+    fos, ffs = cube_frusta()
+    cam_mask = np.array([0xFFFFFFFF, 0xFFFFFFFF, 0x0000FFFF, 0xFFFFFFFF, 0x00000001, 0xFFFFFFFF], np.uint32)
+    pass_flags = np.array([fb.PASS_SHADOW] * 3 + [0] * 3, np.uint32)
+    if fused:
+        ctx.update_and_cull(ffs, fb.UPDATE_ALL, cam_mask, pass_flags)
+    else:
+        ctx.update_transforms(fb.UPDATE_ALL)
+        ctx.cull(ffs, cam_mask, pass_flags)
+    assert_same_visible(og, ctx, fos, cam_mask, pass_flags)
+
+
+def test_cull_random_forest_with_orphans_and_dead_nodes(ctx):
+    rng = np.random.default_rng(11)
+    parent, flags, mask, local, aabb = random_graph(rng, 5000, p_orphan=0.03)
+    og = ob.Graph.build(parent, flags, mask, local, aabb)
+    og.update_hierarchical_data()
+    ctx.set_topology(parent, flags, mask, aabb)
+    ctx.set_local_matrices(local)
+    fo, ff = camera_frustum(eye=(0, 0, 60), zfar=200.0)
+    ctx.update_and_cull([ff], fb.UPDATE_ALL)
+    assert_same_visible(og, ctx, [fo])
+    ctx.cull([ff])
+    assert_same_visible(og, ctx, [fo])
+
+
+def test_cull_degenerate_boxes_and_frustum_inside_box(ctx):
+    """Edge cases of Frustum::is_intersects_aabb: a huge box containing the whole frustum (corner-in-box
+    fallback), an inverted default box (Mesh without vertices), NaN / inf bounds, box touching a plane."""
+    n = 8
+    parent = np.array([NONE] + [0] * (n - 1), np.uint32)
+    flags = np.full(n, fb.NODE_DEFAULT | fb.NODE_RENDERABLE, np.uint32)
+    flags[0] = fb.NODE_DEFAULT
+    fm = np.finfo(np.float32).max
+    aabb = np.array([
+        [-0.5, -0.5, -0.5, 0.5, 0.5, 0.5],
+        [-1e6, -1e6, -1e6, 1e6, 1e6, 1e6],       # contains the frustum
+        [fm, fm, fm, -fm, -fm, -fm],             # AxisAlignedBoundingBox::default()
+        [np.nan, 0, 0, 1, 1, 1],
+        [-np.inf, -np.inf, -np.inf, np.inf, np.inf, np.inf],
+        [-1, -1, -20, 1, 1, -10],                # in front of the camera
+        [200, 200, 200, 201, 201, 201],          # far outside
+        [-1, -1, -0.1, 1, 1, 0.0],               # touching the near plane region
+    ], np.float32)
+    local = np.tile(np.eye(4, dtype=np.float32).reshape(16), (n, 1))
+    og = ob.Graph.build(parent, flags, None, local, aabb)
+    og.update_hierarchical_data()
+    ctx.set_topology(parent, flags, None, aabb)
+    ctx.set_local_matrices(local)
+    fo, ff = camera_frustum()
+    ctx.update_and_cull([ff], fb.UPDATE_ALL)
+    assert_same_hierarchy(og, ctx)
+    assert_same_visible(og, ctx, [fo])
+    # K4 on the GPU: identity view-projection, unit box in, [5,15]^3 out
+    fo_i = ob.frustum_from_vp(np.eye(4, dtype=np.float32).reshape(16))
+    ff_i = fb.frustum_from_view_projection_matrix(np.eye(4, dtype=np.float32).reshape(16))
+    aabb2 = aabb.copy()
+    aabb2[1] = [5, 5, 5, 15, 15, 15]
+    og2 = ob.Graph.build(parent, flags, None, local, aabb2)
+    og2.update_hierarchical_data()
+    ctx.set_local_aabbs(aabb2)
+    ctx.update_and_cull([ff_i], fb.UPDATE_ALL)
+    assert_same_visible(og2, ctx, [fo_i])
+    vis = set(ctx.get_visible(0).tolist())
+    assert 0 not in vis and 1 not in vis and 5 not in vis and 7 in vis  # node 0 is a pivot; 7's box straddles z in [-1,1]
+
+
+def test_empty_and_tiny_graphs(ctx):
+    fo, ff = camera_frustum()
+    ctx.set_topology(np.array([NONE], np.uint32), np.array([fb.NODE_DEFAULT], np.uint32))
+    ctx.update_and_cull([ff], fb.UPDATE_ALL)
+    assert ctx.get_visible(0).size == 0
+    assert ctx.get_global_matrices()[0].tolist() == np.eye(4, dtype=np.float32).reshape(16).tolist()
+    ctx.set_topology(np.empty(0, np.uint32), np.empty(0, np.uint32))
+    ctx.update_and_cull([ff], fb.UPDATE_ALL)
+    assert ctx.get_visible(0).size == 0
+    ctx.cull([])
+
+
+# ---- the reference's own hierarchy test, through the host mirror -----------------------------------
+def test_k6_hierarchy_changes_propagation_reads_like_the_reference():
+    """fyrox-impl/src/scene/graph/mod.rs:2646-2739 transcribed onto fyrox_b200.scene."""
+    from fyrox_b200.scene import BaseBuilder, Graph, PivotBuilder, TransformBuilder
+
+    graph = Graph()
+    c = PivotBuilder(BaseBuilder().with_local_transform(TransformBuilder().with_local_position((0.0, 0.0, 1.0)).build())).build(graph)
+    b = PivotBuilder(
+        BaseBuilder().with_visibility(False).with_enabled(False)
+        .with_local_transform(TransformBuilder().with_local_position((0.0, 1.0, 0.0)).build()).with_child(c)
+    ).build(graph)
+    d = PivotBuilder(BaseBuilder().with_local_transform(TransformBuilder().with_local_position((1.0, 1.0, 1.0)).build())).build(graph)
+    a = PivotBuilder(
+        BaseBuilder().with_local_transform(TransformBuilder().with_local_position((1.0, 0.0, 0.0)).build()).with_child(b).with_child(d)
+    ).build(graph)
+    assert (graph.root.index, graph.root.generation) == (0, 1) and (c.index, c.generation) == (1, 1)  # K10
+
+    graph.update((1.0, 1.0), 1.0 / 60.0)
+    assert graph[a].global_position().tolist() == [1.0, 0.0, 0.0]
+    assert graph[b].global_position().tolist() == [1.0, 1.0, 0.0]
+    assert graph[c].global_position().tolist() == [1.0, 1.0, 1.0]
+    assert graph[d].global_position().tolist() == [2.0, 1.0, 1.0]
+    assert graph[a].global_visibility() and not graph[b].global_visibility()
+    assert not graph[c].global_visibility() and graph[d].global_visibility()
+    assert graph[a].is_globally_enabled() and not graph[b].is_globally_enabled()
+    assert not graph[c].is_globally_enabled() and graph[d].is_globally_enabled()
+
+    graph[b].local_transform_mut().set_position((0.0, 2.0, 0.0))
+    graph[a].set_enabled(False)
+    graph[b].set_visibility(True)
+    graph.update((1.0, 1.0), 1.0 / 60.0)
+    assert graph[a].global_position().tolist() == [1.0, 0.0, 0.0]
+    assert graph[b].global_position().tolist() == [1.0, 2.0, 0.0]
+    assert graph[c].global_position().tolist() == [1.0, 2.0, 1.0]
+    assert graph[d].global_position().tolist() == [2.0, 1.0, 1.0]
+    assert all(graph[h].global_visibility() for h in (a, b, c, d))
+    assert not any(graph[h].is_globally_enabled() for h in (a, b, c, d))
+    graph.ctx.close()
+
+
+def test_k7_global_scale_and_from_graph_through_the_host_mirror():
+    from fyrox_b200.scene import BaseBuilder, Graph, MeshBuilder, ObserverPosition, PivotBuilder, RenderDataBundleStorage, TransformBuilder
+
+    graph = Graph()
+    c = PivotBuilder(BaseBuilder().with_local_transform(TransformBuilder().with_local_scale((1.0, 2.0, 3.0)).build())).build(graph)
+    b = PivotBuilder(BaseBuilder().with_local_transform(TransformBuilder().with_local_scale((3.0, 2.0, 1.0)).build()).with_child(c)).build(graph)
+    a = PivotBuilder(BaseBuilder().with_local_transform(TransformBuilder().with_local_scale((1.0, 1.0, 2.0)).build()).with_child(b)).build(graph)
+    assert graph.global_scale(a).tolist() == [1.0, 1.0, 2.0]
+    assert graph.global_scale(b).tolist() == [3.0, 2.0, 2.0]
+    assert graph.global_scale(c).tolist() == [3.0, 4.0, 6.0]
+    near = MeshBuilder(BaseBuilder().with_local_bounding_box([-1, -1, -1, 1, 1, 1])
+                       .with_local_transform(TransformBuilder().with_local_position((0.0, 0.0, -10.0)).build())).build(graph)
+    behind = MeshBuilder(BaseBuilder().with_local_bounding_box([-1, -1, -1, 1, 1, 1])
+                         .with_local_transform(TransformBuilder().with_local_position((0.0, 0.0, 50.0)).build())).build(graph)
+    noshadow = MeshBuilder(BaseBuilder().with_cast_shadows(False).with_local_bounding_box([-1, -1, -1, 1, 1, 1])
+                           .with_local_transform(TransformBuilder().with_local_position((2.0, 0.0, -10.0)).build())).build(graph)
+    graph.update()
+    op = ObserverPosition(np.zeros(3, np.float32), 0.1, 150.0, ob.look_at_rh((0, 0, 0), (0, 0, -1), (0, 1, 0)), ob.perspective(16 / 9, np.deg2rad(60.0), 0.1, 150.0))
+    main = RenderDataBundleStorage.from_graph(graph, 0xFFFFFFFF, 0.0, op, "GBuffer")
+    assert set(h.index for h in main.visible_handles) == {near.index, noshadow.index}
+    shadow = RenderDataBundleStorage.from_graph(graph, 0xFFFFFFFF, 0.0, op, "SpotShadow")
+    assert set(h.index for h in shadow.visible_handles) == {near.index}
+    assert behind.index not in set(h.index for h in main.visible_handles)
+    graph.ctx.close()
+
+
+# ---- palette + skinning -------------------------------------------------------------------------------
+def test_palette_and_skinning_match_oracle(ctx):
+    sc = Scene(6000, n_units=24, verts_per_unit=1237)  # 1237: not a multiple of 4 ⇒ padded quads
+    og, sids = scene_pair(sc, ctx)
+    idx, m = sc.animate(3)
+    for i, mm in zip(idx, m):
+        og.set_local_matrix(int(i), mm)
+    og.update_hierarchical_data()
+    ctx.set_local_matrices(m, idx)
+    ctx.update_transforms(fb.UPDATE_ALL)
+    ctx.build_palettes()
+    ctx.skin()
+    max_err = 0.0
+    for u, sid in enumerate(sids):
+        mesh = sc.unit_mesh_node(u)
+        pal_o = og.bone_matrices(mesh, 0, sc.bones_per_unit)
+        pal_g = ctx.get_palette(sid)
+        assert pal_g.tobytes() == pal_o.tobytes(), f"palette of unit {u} differs"
+        pos_o, nrm_o = og.skin(mesh, 0, sc.verts_per_unit)
+        pos_g, nrm_g = ctx.get_skinned(sid)
+        max_err = max(max_err, float(np.abs(pos_g - pos_o).max()))
+        assert np.abs(pos_g - pos_o).max() <= 1e-5  # the tolerance BASELINE.json's north_star states
+        assert pos_g.tobytes() == pos_o.tobytes(), f"skinned positions of unit {u} are not bit-identical"
+        assert nrm_g.tobytes() == nrm_o.tobytes(), f"skinned normals of unit {u} are not bit-identical"
+    assert max_err == 0.0
+
+
+def test_skinning_edge_cases(ctx):
+    """Zero weights, repeated indices, a dead / NONE bone (identity matrix), 255 bones, 1 vertex."""
+    nb = 255
+    n = nb + 2
+    parent = np.array([NONE] + [0] * (n - 1), np.uint32)
+    flags = np.full(n, fb.NODE_DEFAULT, np.uint32)
+    flags[n - 1] |= fb.NODE_RENDERABLE
+    flags[7] = 0  # a dead bone node ⇒ identity palette entry
+    rng = np.random.default_rng(3)
+    local = np.tile(np.eye(4, dtype=np.float32).reshape(16), (n, 1))
+    local[1:, 12:15] = rng.uniform(-5, 5, (n - 1, 3)).astype(np.float32)
+    bones = np.arange(1, nb + 1, dtype=np.uint32)
+    bones[9] = NONE
+    ib = np.tile(np.eye(4, dtype=np.float32).reshape(16), (nb, 1))
+    ib[:, 12:15] = rng.uniform(-1, 1, (nb, 3)).astype(np.float32)
+    nv = 1001
+    rec = np.zeros((nv, 68), np.uint8)
+    f = rec[:, :64].view(np.float32)
+    f[:, 0:3] = rng.uniform(-3, 3, (nv, 3))
+    f[:, 5:8] = rng.normal(size=(nv, 3))
+    w = rng.random((nv, 4)).astype(np.float32)
+    w[::3, 2:] = 0.0
+    w[1::7, 1:] = 0.0
+    f[:, 12:16] = w / w.sum(axis=1, keepdims=True)
+    bi = rng.integers(0, nb, (nv, 4)).astype(np.uint8)
+    bi[::5] = bi[::5, :1]  # all four influences on the same bone
+    bi[0] = [7 - 1, 9, 254, 0]  # dead bone, NONE bone, last bone, first bone
+    rec[:, 64:68] = bi
+    og = ob.Graph.build(parent, flags, None, local, None)
+    for k in range(nb):
+        if bones[k] != NONE and flags[bones[k]] & fb.NODE_ALIVE:
+            og.set_inv_bind(int(bones[k]), ib[k])
+    og.add_surface(n - 1, bones, rec.reshape(-1))
+    og.L.orc_graph_drop_messages(og.h)
+    og.update_hierarchical_data()
+    ctx.set_topology(parent, flags)
+    ctx.set_local_matrices(local)
+    sid = ctx.add_skinned_surface(n - 1, bones, ib, rec.reshape(-1))
+    sid1 = ctx.add_skinned_surface(n - 1, bones[:3], ib[:3], np.ascontiguousarray(np.concatenate([rec[:1, :64], np.zeros((1, 4), np.uint8)], axis=1)).reshape(-1))
+    ctx.update_transforms(fb.UPDATE_ALL)
+    ctx.build_palettes()
+    ctx.skin()
+    pal_o = og.bone_matrices(n - 1, 0, nb)
+    pal_g = ctx.get_palette(sid)
+    assert pal_g[6].tolist() == np.eye(4, dtype=np.float32).reshape(16).tolist()  # dead bone
+    assert pal_g[9].tolist() == np.eye(4, dtype=np.float32).reshape(16).tolist()  # NONE bone
+    assert pal_g.tobytes() == pal_o.tobytes()
+    pos_o, nrm_o = og.skin(n - 1, 0, nv)
+    pos_g, nrm_g = ctx.get_skinned(sid)
+    assert pos_g.tobytes() == pos_o.tobytes() and nrm_g.tobytes() == nrm_o.tobytes()
+    p1, _ = ctx.get_skinned(sid1)
+    assert p1.shape == (1, 3)
+
+
+def test_errors_are_reported_not_fatal(ctx):
+    parent = np.array([NONE, 0], np.uint32)
+    ctx.set_topology(parent, np.full(2, fb.NODE_DEFAULT, np.uint32))
+    bad = np.eye(4, dtype=np.float32).reshape(16).copy()
+    bad[3] = 0.5  # projective row
+    ctx.set_local_matrices(bad.reshape(1, 16), [1])
+    with pytest.raises(fb.FyxError) as e:
+        ctx.update_transforms(fb.UPDATE_ALL)
+    assert e.value.code == fb._lib.FYX_ERR_NOT_AFFINE
+    ctx.update_transforms(fb.UPDATE_ALL)  # the bad matrix was skipped; the context is still usable
+    assert ctx.get_global_matrices([1])[0].tolist() == np.eye(4, dtype=np.float32).reshape(16).tolist()
+    with pytest.raises(fb.FyxError) as e:
+        ctx.set_topology(np.array([1, 0], np.uint32), np.full(2, fb.NODE_DEFAULT, np.uint32))  # 2-cycle
+    assert e.value.code == fb._lib.FYX_ERR_TOPOLOGY
+    rec = np.zeros((4, 68), np.uint8)
+    rec[:, 64] = 9  # bone index out of range for a 2-bone surface
+    ctx.add_skinned_surface(1, [0, 1], np.tile(np.eye(4, dtype=np.float32).reshape(16), (2, 1)), rec.reshape(-1))
+    with pytest.raises(fb.FyxError) as e:
+        ctx.commit_surfaces()
+    assert e.value.code == fb._lib.FYX_ERR_INVALID_ARGUMENT
+    with pytest.raises(fb.FyxError):
+        ctx.get_visible(5)
+
+
+def test_render_prep_one_call_frame(ctx):
+    sc = Scene(30000, n_units=30, verts_per_unit=200)
+    og, sids = scene_pair(sc, ctx)
+    fos, ffs = cube_frusta()
+    for frame in range(2):
+        idx, m = sc.animate(frame)
+        for i, mm in zip(idx, m):
+            og.set_local_matrix(int(i), mm)
+        og.update_hierarchical_data()
+        ctx.render_prep(update_flags=fb.UPDATE_ALL, changed_m16=m, changed_idx=idx, frusta=ffs)
+        assert_same_hierarchy(og, ctx)
+        assert_same_visible(og, ctx, fos)
+        for u in (0, len(sids) - 1):
+            mesh = sc.unit_mesh_node(u)
+            pos_o, nrm_o = og.skin(mesh, 0, sc.verts_per_unit)
+            pos_g, nrm_g = ctx.get_skinned(sids[u])
+            assert pos_g.tobytes() == pos_o.tobytes() and nrm_g.tobytes() == nrm_o.tobytes()
+    t = ctx.timings()
+    assert t["total_ms"] > 0 and ctx.kernel_launch_count() > 0
+    # pinned inputs take the zero-staging path
+    pin_m = fb.PinnedBuffer((idx.size, 16), np.float32)
+    pin_i = fb.PinnedBuffer((idx.size,), np.uint32)
+    pin_m.array[:] = m
+    pin_i.array[:] = idx
+    ctx.render_prep(update_flags=fb.UPDATE_ALL, changed_m16=pin_m.ptr, changed_idx=pin_i.ptr, n_changed=idx.size, frusta=ffs)
+    assert_same_visible(og, ctx, fos)
+    pin_m.free()
+    pin_i.free()

@@ -1,0 +1,316 @@
+"""Pins the oracle (oracle/fyrox_oracle.c) against the reference's own unit-test vectors K1..K10
+(tests/golden/reference_kats.json, transcribed from the cited Rust tests), and the product's
+host-side math (fyx_frustum_from_view_projection_matrix / fyx_mat4_mul) against the same vectors.
+CPU only."""
+import ctypes as C
+import json
+import os
+
+import numpy as np
+import pytest
+
+import oracle_binding as ob
+from oracle_binding import Aabb, Frustum, Plane, fp, vec
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+KATS = json.load(open(os.path.join(HERE, "golden", "reference_kats.json")))
+L = ob.lib()
+
+
+def col_major(row_major16):
+    return np.array(row_major16, dtype=np.float32).reshape(4, 4).T.reshape(16).copy()
+
+
+def identity_frustum() -> Frustum:
+    f = ob.frustum_from_vp(col_major(KATS["K3_frustum_from_identity"]["vp_row_major"]))
+    assert f is not None
+    return f
+
+
+def test_k1_aabb_transform():
+    k = KATS["K1_aabb_transform"]
+    m = ob.mat4_mul(ob.translation(*k["translation"]), ob.scaling(*k["scaling"]))
+    a = Aabb.make(k["aabb"][:3], k["aabb"][3:])
+    out = Aabb()
+    L.orc_aabb_transform(C.byref(a), fp(m), C.byref(out))
+    assert out.to_np().tolist() == k["expected"]
+
+
+def test_k2_aabb_basics():
+    k = KATS["K2_aabb_basics"]
+    a = Aabb()
+    L.orc_aabb_default(C.byref(a))
+    assert a.to_np().tolist() == np.array(k["default"], np.float32).tolist()
+    assert not L.orc_aabb_is_valid(C.byref(a))
+    L.orc_aabb_add_point(C.byref(a), fp(vec(1, 1, 1)))
+    assert L.orc_aabb_is_valid(C.byref(a))
+    L.orc_aabb_add_point(C.byref(a), fp(vec(-1, -1, -1)))
+    assert L.orc_aabb_is_valid(C.byref(a))
+
+    u = Aabb()
+    L.orc_aabb_unit(C.byref(u))
+    assert u.to_np().tolist() == k["unit"]
+    assert not L.orc_aabb_is_degenerate(C.byref(u))
+    col = Aabb.make([0, 0, 0], [0, 0, 0])
+    assert L.orc_aabb_is_degenerate(C.byref(col))
+
+    b = Aabb()
+    L.orc_aabb_default(C.byref(b))
+    for p in k["add_point"]["points"]:
+        L.orc_aabb_add_point(C.byref(b), fp(vec(*p)))
+    assert b.to_np().tolist() == k["add_point"]["expected"]
+
+    c = Aabb.make(k["add_box"]["start"][:3], k["add_box"]["start"][3:])
+    bx = Aabb.make(k["add_box"]["box"][:3], k["add_box"]["box"][3:])
+    L.orc_aabb_add_box(C.byref(c), C.byref(bx))
+    assert c.to_np().tolist() == k["add_box"]["expected"]
+
+    r1 = Aabb.make([-1, -1, -1], [1, 1, 1])
+    corners = np.empty((8, 3), np.float32)
+    L.orc_aabb_corners(C.byref(r1), fp(corners.reshape(-1)))
+    assert corners.tolist() == k["corners_of_radius_1"]
+    # is_contains_point is inclusive on all corners of the unit box (aabb.rs:511-519)
+    L.orc_aabb_corners(C.byref(u), fp(corners.reshape(-1)))
+    assert L.orc_aabb_is_contains_point(C.byref(u), fp(vec(0, 0, 0)))
+    for p in corners:
+        assert L.orc_aabb_is_contains_point(C.byref(u), fp(np.ascontiguousarray(p)))
+
+
+def test_k3_frustum_from_identity():
+    k = KATS["K3_frustum_from_identity"]
+    f = identity_frustum()
+    planes, corners = ob.frustum_planes_corners(f)
+    for i, (a, b, c, d) in enumerate(k["planes_abcd"]):
+        p = Plane()
+        assert L.orc_plane_from_abcd(a, b, c, d, C.byref(p))
+        assert planes[i].tolist() == [p.n[0], p.n[1], p.n[2], p.d]
+        assert planes[i].tolist() == [a, b, c, d]  # already unit length
+    assert (corners == np.array(k["corners"], np.float32)).all()
+
+
+def test_k3_product_host_math_matches():
+    """fyx_frustum_from_view_projection_matrix is the product's copy of the same extraction."""
+    import fyrox_b200 as fb
+
+    k = KATS["K3_frustum_from_identity"]
+    f = fb.frustum_from_view_projection_matrix(col_major(k["vp_row_major"]))
+    planes, corners = fb.frustum_to_numpy(f)
+    assert planes.tolist() == k["planes_abcd"]
+    assert (corners == np.array(k["corners"], np.float32)).all()
+    # and on random view-projection matrices it equals the oracle bit for bit
+    rng = np.random.default_rng(7)
+    for _ in range(200):
+        eye = rng.uniform(-50, 50, 3).astype(np.float32)
+        tgt = eye + rng.normal(size=3).astype(np.float32)
+        view = ob.look_at_rh(eye, tgt, (0, 1, 0))
+        proj = ob.perspective(float(rng.uniform(0.5, 2.5)), float(rng.uniform(0.3, 2.0)), 0.1, float(rng.uniform(50, 500)))
+        vp_o = ob.mat4_mul(proj, view)
+        vp_p = fb.mat4_mul(proj, view)
+        assert vp_o.tobytes() == vp_p.tobytes()
+        fo = ob.frustum_from_vp(vp_o)
+        fpz = fb.frustum_from_view_projection_matrix(vp_p)
+        po, co = ob.frustum_planes_corners(fo)
+        pp, cp = fb.frustum_to_numpy(fpz)
+        assert po.tobytes() == pp.tobytes() and co.tobytes() == cp.tobytes()
+    assert fb.frustum_from_view_projection_matrix(np.zeros(16, np.float32)) is None
+    dflt_p, dflt_c = fb.frustum_to_numpy(fb.frustum_default())
+    fo = Frustum()
+    L.orc_frustum_default(C.byref(fo))
+    po, co = ob.frustum_planes_corners(fo)
+    assert po.tobytes() == dflt_p.tobytes() and co.tobytes() == dflt_c.tobytes()
+
+
+def test_k4_frustum_queries():
+    k = KATS["K4_frustum_queries"]
+    f = identity_frustum()
+    pts = np.array(k["cloud_true"], np.float32)
+    assert L.orc_frustum_is_intersects_point_cloud(C.byref(f), fp(pts.reshape(-1)), len(pts))
+    pts = np.array(k["cloud_false"], np.float32)
+    assert not L.orc_frustum_is_intersects_point_cloud(C.byref(f), fp(pts.reshape(-1)), len(pts))
+    t = Aabb.make(k["aabb_true"][:3], k["aabb_true"][3:])
+    assert L.orc_frustum_is_intersects_aabb(C.byref(f), C.byref(t))
+    fa = Aabb.make(k["aabb_false"][:3], k["aabb_false"][3:])
+    assert not L.orc_frustum_is_intersects_aabb(C.byref(f), C.byref(fa))
+    assert L.orc_frustum_is_intersects_aabb_offset(C.byref(f), C.byref(t), fp(vec(*k["offset_true"])))
+    assert not L.orc_frustum_is_intersects_aabb_offset(C.byref(f), C.byref(t), fp(vec(*k["offset_false"])))
+    assert L.orc_frustum_is_contains_point(C.byref(f), fp(vec(*k["contains_true"])))
+    assert not L.orc_frustum_is_contains_point(C.byref(f), fp(vec(*k["contains_false"])))
+
+
+def test_k5_plane():
+    k = KATS["K5_plane"]
+    p = Plane()
+    assert L.orc_plane_from_abcd(1.0, 1.0, 1.0, 0.0, C.byref(p))
+    assert [p.n[0], p.n[1], p.n[2]] == np.array(k["from_abcd_1110"]["normal"], np.float32).tolist()
+    assert p.d == k["from_abcd_1110"]["d"]
+    assert not L.orc_plane_from_abcd(0.0, 0.0, 0.0, 0.0, C.byref(p))
+    d = k["dot"]
+    q = Plane()
+    for i in range(3):
+        q.n[i] = d["normal"][i]
+    q.d = d["d"]
+    assert L.orc_plane_dot(C.byref(q), fp(vec(*d["point"]))) == d["expected"]
+    planes = []
+    for n in ((0, 0, 1), (0, 1, 0), (1, 0, 0)):
+        pl = Plane()
+        for i in range(3):
+            pl.n[i] = n[i]
+        pl.d = 0.0
+        planes.append(pl)
+    out = np.empty(3, np.float32)
+    L.orc_plane_intersection_point(C.byref(planes[0]), C.byref(planes[1]), C.byref(planes[2]), fp(out))
+    assert (out == np.array(k["intersection_of_axis_planes"], np.float32)).all()  # -0.0 == 0.0, as assert_eq! on f32
+
+
+def build_k6_graph():
+    """Same construction order as the reference test: c, b, d are built before a (children first)."""
+    k = KATS["K6_hierarchy_propagation"]
+    g = ob.Graph()
+    c = g.add_node()
+    g.set_local_matrix(c, ob.translation(*k["local_positions"]["c"]))
+    b = g.add_node()
+    g.set_local_matrix(b, ob.translation(*k["local_positions"]["b"]))
+    g.set_visibility(b, k["b_visibility"])
+    g.set_enabled(b, k["b_enabled"])
+    g.link_nodes(c, b)
+    d = g.add_node()
+    g.set_local_matrix(d, ob.translation(*k["local_positions"]["d"]))
+    a = g.add_node()
+    g.set_local_matrix(a, ob.translation(*k["local_positions"]["a"]))
+    g.link_nodes(b, a)
+    g.link_nodes(d, a)
+    return g, dict(a=a, b=b, c=c, d=d)
+
+
+def check_k6(g, h, exp):
+    for n, pos in exp["global_positions"].items():
+        assert g.global_position(h[n]).tolist() == pos, n
+    for n, v in exp["global_visibility"].items():
+        assert g.global_visibility(h[n]) == v, n
+    for n, v in exp["global_enabled"].items():
+        assert g.is_globally_enabled(h[n]) == v, n
+
+
+def test_k6_hierarchy_changes_propagation():
+    k = KATS["K6_hierarchy_propagation"]
+    g, h = build_k6_graph()
+    assert h["c"] == 1 and h["a"] == 4  # K10 numbering: first added node is index 1
+    g.update()
+    check_k6(g, h, k["first"])
+    g.set_local_matrix(h["b"], ob.translation(0.0, 2.0, 0.0))
+    g.set_enabled(h["a"], False)
+    g.set_visibility(h["b"], True)
+    g.update()
+    check_k6(g, h, k["second"])
+    # a full recompute gives the same state
+    g.update_hierarchical_data()
+    check_k6(g, h, k["second"])
+
+
+def test_k7_global_scale():
+    k = KATS["K7_global_scale"]
+    g = ob.Graph()
+    c = g.add_node()
+    b = g.add_node()
+    g.link_nodes(c, b)
+    a = g.add_node()
+    g.link_nodes(b, a)
+    h = dict(a=a, b=b, c=c)
+    ls = np.ones((g.capacity, 3), np.float32)
+    for n, s in k["local_scales"].items():
+        ls[h[n]] = s
+    for n, e in k["expected"].items():
+        out = np.empty(3, np.float32)
+        L.orc_graph_global_scale(g.h, h[n], fp(ls.reshape(-1)), fp(out))
+        assert out.tolist() == e
+
+
+def test_k8_matrix_layout():
+    """Matrix4Ext accessors are plain linear (column-major) indices; orc matrices use the same layout."""
+    k = KATS["K8_matrix4_ext"]
+    m = np.empty(16, np.float32)
+    L.orc_mat4_identity(fp(m))
+    for name in ("side", "up", "look", "position"):
+        assert m[k["linear_indices"][name]].tolist() == k[name]
+    t = ob.translation(7, 8, 9)
+    assert t[k["linear_indices"]["position"]].tolist() == [7, 8, 9]
+
+
+def test_k9_sorting_index():
+    k = KATS["K9_sorting_index"]
+    view = np.empty(16, np.float32)
+    L.orc_mat4_identity(fp(view))
+    for case in k["cases"]:
+        got = L.orc_calculate_sorting_index(fp(view), fp(vec(0, 0, case["z"])))
+        assert got == k["range_center"] + case["delta"]
+
+
+def test_k10_handle_numbering():
+    k = KATS["K10_handle_numbering"]
+    g = ob.Graph()
+    assert L.orc_graph_root(g.h) == k["root"][0]
+    assert g.add_node() == k["first_added"][0]
+
+
+# ---- unpinned parts: self-consistency of the restatement -------------------------------------------
+def test_mat4_mul_matches_numpy_within_rounding_and_order_is_left_to_right():
+    rng = np.random.default_rng(1)
+    a = rng.normal(size=16).astype(np.float32)
+    b = rng.normal(size=16).astype(np.float32)
+    c = ob.mat4_mul(a, b)
+    A, B = a.reshape(4, 4).T, b.reshape(4, 4).T
+    ref = (A.astype(np.float64) @ B.astype(np.float64)).T.reshape(16)
+    assert np.allclose(c, ref, rtol=1e-5, atol=1e-5)
+    # exact left-to-right accumulation, one rounding per op
+    f = np.float32
+    for j in range(4):
+        for i in range(4):
+            y = f(A[i, 0] * B[0, j])
+            y = f(y + f(A[i, 1] * B[1, j]))
+            y = f(y + f(A[i, 2] * B[2, j]))
+            y = f(y + f(A[i, 3] * B[3, j]))
+            assert c[j * 4 + i] == y
+
+
+def test_calculate_local_transform_reduces_to_trs():
+    t = ob.Transform()
+    L.orc_transform_identity(C.byref(t))
+    t.local_position[:] = (1.0, 2.0, 3.0)
+    t.local_scale[:] = (2.0, 3.0, 4.0)
+    q = np.array([0.1, -0.2, 0.3, 0.9], np.float32)
+    q /= np.linalg.norm(q)
+    t.local_rotation[:] = q.tolist()
+    m = np.empty(16, np.float32)
+    L.orc_transform_calculate_local(C.byref(t), fp(m))
+    r = np.empty(9, np.float32)
+    L.orc_quat_to_rotation_matrix(fp(q), fp(r))
+    R = r.reshape(3, 3).T
+    M = m.reshape(4, 4).T
+    assert np.allclose(M[:3, :3], R * np.array([2.0, 3.0, 4.0], np.float32)[None, :], atol=1e-6)
+    assert M[:3, 3].tolist() == [1.0, 2.0, 3.0]
+    assert M[3].tolist() == [0.0, 0.0, 0.0, 1.0]
+    # the Python host mirror computes the same matrix bit for bit
+    from fyrox_b200.scene import TransformBuilder
+
+    tm = TransformBuilder().with_local_position((1, 2, 3)).with_local_scale((2, 3, 4)).with_local_rotation(q).build().matrix()
+    assert tm.tobytes() == m.tobytes()
+
+
+def test_skinned_mesh_world_aabb_reads_current_bone_positions():
+    """The DFS-order quirk: bones visited before the mesh contribute their NEW position."""
+    g = ob.Graph()
+    bone = g.add_node()
+    mesh = g.add_node(ob.KIND_MESH)
+    g.set_local_aabb(mesh, [-1, -1, -1, 1, 1, 1])
+    g.add_surface(mesh, [bone])
+    g.set_local_matrix(bone, ob.translation(10, 0, 0))
+    g.update()
+    assert g.world_bounding_box(mesh).tolist() == [-1, -1, -1, 10, 1, 1]
+    # the bone moves, the mesh does not: the cached box stays (Mesh world AABB is only refreshed when the
+    # mesh's own global transform changes, mesh/mod.rs:667-689)
+    g.set_local_matrix(bone, ob.translation(20, 0, 0))
+    g.update()
+    assert g.world_bounding_box(mesh).tolist() == [-1, -1, -1, 10, 1, 1]
+    g.set_local_matrix(mesh, ob.translation(0, 0, 0))
+    g.update()
+    assert g.world_bounding_box(mesh).tolist() == [-1, -1, -1, 20, 1, 1]
