@@ -1,0 +1,459 @@
+#!/usr/bin/env python
+"""bench.py — the render-prep hot path on N B200s (one process per GPU).
+
+    python bench.py --gpus 1 --steps K --warmup W                 # this repo's CUDA path
+    torchrun --nproc-per-node N ... bench.py --gpus N ...          # weak scaling, NCCL all-gather of visible lists
+    python bench.py --impl reference --gpus N --steps K --warmup W # the reference's CPU algorithm (oracle port), host cores
+
+A step = one frame of render prep over one batch of synthetic input:
+  hierarchy update (every node recomputed) + world AABBs + cull against F frusta with visible-index
+  compaction + bone palettes + linear-blend skinning (+ NCCL all-gather of the visible lists when N > 1).
+metric = BASELINE.json's "nodes culled + verts skinned /sec"; value = (nodes + skinned vertices) per
+second over all GPUs with every input resident in HBM; e2e = the same frame through fyx_render_prep with
+HOST buffers (changed bone matrices uploaded from pinned memory, visible lists read back) per step.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+if REPO not in sys.path:
+    sys.path.insert(0, REPO)
+
+import numpy as np  # noqa: E402
+
+METRIC = "nodes culled + verts skinned /sec"
+UNIT = "nodes+verts/s"
+SEED = 0xF1A0C5
+
+# BASELINE.json configs (per GPU; weak scaling multiplies by N)
+WORKLOADS = {
+    "C2": dict(nodes=10_000_000, units=0, verts_per_unit=5000, frusta=1, desc="10M static nodes, 1 frustum"),
+    "C3": dict(nodes=1_000_000, units=10_000, verts_per_unit=5000, frusta=1, desc="1M nodes incl. 10k skinned meshes x 64 bones x 5k verts, 1 frustum"),
+    "C4": dict(nodes=10_000_000, units=50_000, verts_per_unit=5000, frusta=6, desc="10M nodes, 50k skinned meshes x 64 bones x 5k verts, 6 frusta (cube faces)"),
+    "target": dict(nodes=10_000_000, units=10_000, verts_per_unit=5000, frusta=1, desc="10M nodes + 50M skinned verts, 1 frustum (north_star target)"),
+    "tiny": dict(nodes=200_000, units=200, verts_per_unit=5000, frusta=6, desc="debug"),
+}
+DEFAULT_WORKLOAD = os.environ.get("FYX_BENCH_WORKLOAD", "C4")
+BONES = 64
+
+# algorithmic bytes per unit (SURVEY.md §8d / DESIGN.md §5)
+B_NODE_FUSED = 188
+B_VISIBLE = 4
+B_BONE = 196
+B_VERT = 68
+
+
+def peaks():
+    p = os.path.join(REPO, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, gpu_index: int):
+        self.rows = []
+        self.proc = None
+        self.gpu = gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self) -> dict:
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------------------------------
+# the reference arm / cpu_baseline: the oracle (CPU restatement of the reference algorithm), 1 thread
+# --------------------------------------------------------------------------------------------------
+def cpu_sample_config(w: dict) -> dict:
+    """A bounded sample of the workload with the same nodes:verts ratio (about 2-5 s of CPU work per frame)."""
+    scale = 10 if w["units"] >= 10_000 else 5
+    nodes = max(w["nodes"] // scale, 100_000)
+    units = w["units"] // scale
+    if w["units"] and w["nodes"] // max(w["units"], 1) < 200:  # C3-like: vertex heavy
+        nodes, units = w["nodes"] // 20, w["units"] // 20
+    return dict(nodes=nodes, units=units, verts_per_unit=w["verts_per_unit"], frusta=w["frusta"])
+
+
+class CpuReference:
+    """Oracle port of the reference's single-threaded path (the reference is not parallel):
+    update_hierarchical_data + from_graph per frustum + palette + CPU LBS (mesh/mod.rs:501-522)."""
+
+    def __init__(self, sample: dict):
+        sys.path.insert(0, os.path.join(REPO, "tests"))
+        import oracle_binding as ob  # the one place bench.py executes oracle/: the CPU baseline
+        from fyrox_b200.scenegen import Scene
+
+        self.ob = ob
+        self.s = sample
+        sc = Scene(sample["nodes"], n_units=sample["units"], verts_per_unit=sample["verts_per_unit"], bones_per_unit=BONES, seed=SEED)
+        self.sc = sc
+        aabb = sc.local_aabb.copy()
+        self.og = ob.Graph.build(sc.parent, sc.flags, sc.render_mask, sc.local_m16, aabb)
+        self.meshes = []
+        for u in range(sc.n_units):
+            mesh, bones, ib = sc.unit_mesh_node(u), sc.unit_bone_nodes(u), sc.unit_inv_bind(u)
+            for k, b in enumerate(bones):
+                self.og.set_inv_bind(int(b), ib[k])
+            verts, _ = sc.unit_vertices(u)
+            self.og.add_surface(mesh, bones, verts)
+            self.og.recalc_local_aabb(mesh)
+            self.meshes.append(mesh)
+        self.og.L.orc_graph_drop_messages(self.og.h)
+        # frusta through the oracle's own restatement
+        self.frusta = []
+        if sample["frusta"] == 1:
+            view = ob.look_at_rh((0, 0, 0), (0, 0, -1), (0, 1, 0))
+            proj = ob.perspective(16 / 9, float(np.deg2rad(60.0)), 0.1, 150.0)
+            self.frusta.append(ob.frustum_from_vp(ob.mat4_mul(proj, view)))
+        else:
+            faces = [((1, 0, 0), (0, -1, 0)), ((-1, 0, 0), (0, -1, 0)), ((0, 1, 0), (0, 0, 1)), ((0, -1, 0), (0, 0, -1)), ((0, 0, 1), (0, -1, 0)), ((0, 0, -1), (0, -1, 0))]
+            for look, up in faces[: sample["frusta"]]:
+                view = ob.look_at_rh((0, 0, 0), look, up)
+                proj = ob.perspective(1.0, float(np.pi / 2), 0.01, 120.0)
+                self.frusta.append(ob.frustum_from_vp(ob.mat4_mul(proj, view)))
+        self.pos = np.empty((sample["verts_per_unit"], 3), np.float32)
+        self.nrm = np.empty((sample["verts_per_unit"], 3), np.float32)
+        self.vis = np.empty(max(sc.capacity, 1), np.uint32)
+        self.frame = 0
+
+    def units_per_frame(self) -> int:
+        return self.s["nodes"] + self.s["units"] * self.s["verts_per_unit"]
+
+    def step(self):
+        ob, og = self.ob, self.og
+        import ctypes as C
+
+        # every bone's local matrix changes each frame (set directly; the full recompute below ignores messages)
+        idx, m = self.sc.animate(self.frame)
+        self.frame += 1
+        t0 = time.perf_counter()
+        L = og.L
+        for i in range(idx.size):
+            L.orc_node_set_local_matrix(og.h, int(idx[i]), ob.fp(m[i]))
+        L.orc_graph_drop_messages(og.h)
+        t_set = time.perf_counter() - t0  # host-side scatter of changed matrices (python loop: excluded below)
+        t1 = time.perf_counter()
+        og.update_hierarchical_data()
+        for f in self.frusta:
+            L.orc_from_graph(og.h, C.byref(f), 0xFFFFFFFF, 0, self.vis.ctypes.data_as(C.c_void_p), self.vis.size)
+        for mesh in self.meshes:
+            L.orc_mesh_skin(og.h, mesh, 0, ob.fp(self.pos.reshape(-1)), ob.fp(self.nrm.reshape(-1)))
+        dt = time.perf_counter() - t1
+        return dt, t_set
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    w = WORKLOADS[args.workload]
+    sample = cpu_sample_config(w)
+    ref = CpuReference(sample)
+    for _ in range(args.warmup):
+        ref.step()
+    t = 0.0
+    for _ in range(args.steps):
+        dt, _ = ref.step()
+        t += dt
+    ms = 1e3 * t / max(args.steps, 1)
+    value = ref.units_per_frame() / (ms * 1e-3)
+    desc = f"{sample['nodes']} nodes, {sample['units']} skinned meshes x {BONES} bones x {sample['verts_per_unit']} verts, {sample['frusta']} frusta, 1 frame per step"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": args.workload, "desc": w["desc"], "sample": desc,
+                   "note": "reference = Fyrox's single-threaded CPU path restated in C (oracle/; the Rust reference is not buildable here: no cargo)"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": "port", "sample": desc},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# --------------------------------------------------------------------------------------------------
+# the CUDA arm
+# --------------------------------------------------------------------------------------------------
+def load_scene(ctx, sc, fb, log):
+    t0 = time.time()
+    ctx.set_topology(sc.parent, sc.flags, sc.render_mask, sc.local_aabb, root=0, global_index=sc.global_index)
+    ctx.set_local_matrices(sc.local_m16)
+    nu, V = sc.n_units, sc.verts_per_unit
+    if nu:
+        ctx.reserve_skinning(nu * BONES, nu * V)
+        chunk = max(1, min(nu, (256 << 20) // (V * 68)))
+        pin = fb.PinnedBuffer((chunk * V * 68,), np.uint8)
+        aabbs = np.empty((chunk, 6), np.float32)
+        mesh_nodes = np.empty(nu, np.uint32)
+        all_aabb = np.empty((nu, 6), np.float32)
+        for u0 in range(0, nu, chunk):
+            cnt = min(chunk, nu - u0)
+            sc.units_vertices_into(u0, cnt, pin.ptr, aabbs)
+            for i in range(cnt):
+                u = u0 + i
+                mesh_nodes[u] = sc.unit_mesh_node(u)
+                ctx.add_skinned_surface(int(mesh_nodes[u]), sc.unit_bone_nodes(u), sc.unit_inv_bind(u), pin.ptr + i * V * 68, n_verts=V)
+            all_aabb[u0:u0 + cnt] = aabbs[:cnt]
+            ctx.sync()
+        ctx.set_local_aabbs(all_aabb, mesh_nodes)  # Mesh::local_bounding_box = bounds of the vertices
+        ctx.commit_surfaces()
+        pin.free()
+    log(f"scene on device in {time.time() - t0:.1f}s: {sc.capacity} nodes, {nu} skinned meshes, {nu * V} verts")
+
+
+def run_cuda(args):
+    import torch
+    import torch.distributed as dist
+
+    import fyrox_b200 as fb
+    from fyrox_b200 import camera
+    from fyrox_b200.scenegen import Scene
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    if args.gpus > 1 and world == 1:
+        raise SystemExit("launch N>1 with torchrun (one process per GPU)")
+    if not torch.cuda.is_available():
+        raise SystemExit("no CUDA device: bench.py has no CPU fallback for the CUDA arm (use --impl reference for the CPU baseline)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def log(msg):
+        if rank == 0 and args.verbose:
+            print("[bench]", msg, file=sys.stderr, flush=True)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+
+    w = WORKLOADS[args.workload]
+    # weak scaling: per-GPU work fixed; the scene grows with N and is sharded by sector sub-tree
+    sc = Scene(w["nodes"] * world, n_units=w["units"] * world, verts_per_unit=w["verts_per_unit"], bones_per_unit=BONES, seed=SEED, rank=rank, nranks=world)
+    stream = torch.cuda.current_stream().cuda_stream
+    ctx = fb.Context(device=local_rank, stream=stream)
+    load_scene(ctx, sc, fb, log)
+    if world > 1:
+        uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            uid.copy_(torch.frombuffer(bytearray(fb.Context.comm_unique_id()), dtype=torch.uint8))
+        dist.broadcast(uid, 0)
+        ctx.comm_init(world, rank, bytes(uid.cpu().numpy().tobytes()))
+
+    frusta = [camera.camera_frustum()] if w["frusta"] == 1 else camera.cube_frusta()[: w["frusta"]]
+    n_local_nodes = sc.capacity
+    n_local_verts = sc.n_units * sc.verts_per_unit
+    n_bones = sc.n_units * BONES
+
+    # per-frame host inputs: two animation frames in pinned memory, alternated
+    anim = []
+    if n_bones:
+        for fr in range(2):
+            pi = fb.PinnedBuffer((n_bones,), np.uint32)
+            pm = fb.PinnedBuffer((n_bones, 16), np.float32)
+            sc.animate_into(fr, pi.ptr, pm.ptr)
+            anim.append((pi, pm))
+
+    def step_device():
+        ctx.render_prep(update_flags=fb.UPDATE_ALL, frusta=frusta, do_palettes=True, do_skin=True, readback_visible=False, async_=True)
+        if world > 1:
+            ctx.allgather_visible()
+
+    vis_counts = [0] * len(frusta)
+
+    def step_e2e(i):
+        if anim:
+            pi, pm = anim[i & 1]
+            ctx.render_prep(update_flags=fb.UPDATE_ALL, changed_m16=pm.ptr, changed_idx=pi.ptr, n_changed=n_bones, frusta=frusta, readback_visible=(world == 1))
+        else:
+            ctx.render_prep(update_flags=fb.UPDATE_ALL, frusta=frusta, readback_visible=(world == 1))
+        if world > 1:
+            ctx.allgather_visible()
+            for f in range(len(frusta)):
+                vis_counts[f] = ctx.get_visible_gathered(f).size
+        else:
+            for f in range(len(frusta)):
+                vis_counts[f] = ctx.get_visible(f).size
+
+    def timed(fn, steps, pass_index=False):
+        barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            fn(i) if pass_index else fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ctx.sync()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device="cuda", dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    # warm-up (both paths), then the timed regions; inputs (>1.6 GB of node columns, vertex streams) exceed the 126 MB L2
+    for i in range(max(args.warmup, 3)):
+        step_device()
+    ctx.sync()
+    for i in range(max(args.warmup, 3)):
+        step_e2e(i)
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
+    launches0 = ctx.kernel_launch_count()
+    total_ms = timed(step_device, args.steps)
+    launches = ctx.kernel_launch_count() - launches0
+    e2e_ms = timed(step_e2e, args.steps, pass_index=True)
+    # per-stage device durations (CUDA events on the launching stream, inside fyx_render_prep), same K frames
+    stage = {"update_ms": 0.0, "palette_ms": 0.0, "skin_ms": 0.0}
+    for i in range(args.steps):
+        ctx.render_prep(update_flags=fb.UPDATE_ALL, frusta=frusta, readback_visible=False)
+        t = ctx.timings()
+        for k in stage:
+            stage[k] += t[k] / args.steps
+    clk = clocks.stop() if rank == 0 else None
+
+    ms_per_step = total_ms / args.steps
+    e2e_ms_per_step = e2e_ms / args.steps
+    units_all = (w["nodes"] + w["units"] * w["verts_per_unit"]) * world  # whole job
+    value = units_all / (ms_per_step * 1e-3)
+    e2e_value = units_all / (e2e_ms_per_step * 1e-3)
+    sum_vis = sum(vis_counts)
+    h2d = n_bones * (64 + 4) + len(frusta) * 0  # frusta travel as kernel parameters
+    d2h = 4 * len(frusta) + 4 * sum_vis
+
+    peak, peak_src = peaks()
+    # dominant kernel: k_skin when the workload skins, else the fused update+cull level kernels
+    stages = {}
+    if n_local_verts:
+        g = B_VERT * n_local_verts / (stage["skin_ms"] * 1e-3) / 1e9
+        stages["k_skin"] = {"ms": stage["skin_ms"], "algorithmic_bytes": B_VERT * n_local_verts, "GBps": g, "frac": g / peak}
+    own_vis = sum_vis if world == 1 else None
+    upd_bytes = B_NODE_FUSED * n_local_nodes + (B_VISIBLE * sum_vis // world)
+    g = upd_bytes / (stage["update_ms"] * 1e-3) / 1e9
+    stages["k_update_level+cull"] = {"ms": stage["update_ms"], "algorithmic_bytes": upd_bytes, "GBps": g, "frac": g / peak}
+    if n_bones:
+        g = B_BONE * n_bones / max(stage["palette_ms"], 1e-6) / 1e-3 / 1e9
+        stages["k_palette"] = {"ms": stage["palette_ms"], "algorithmic_bytes": B_BONE * n_bones, "GBps": g, "frac": g / peak}
+    dom = "k_skin" if n_local_verts and stage["skin_ms"] >= stage["update_ms"] else "k_update_level+cull"
+    traffic = None
+    tpath = os.path.join(REPO, "profiles", "ncu_traffic.json")
+    if os.path.exists(tpath):
+        try:
+            tj = json.load(open(tpath))
+            ent = tj.get(args.workload, {}).get(dom)
+            traffic = ent.get("dram_bytes_per_launch") if ent else None
+        except Exception:
+            traffic = None
+    roofline = {"bound": "hbm", "kernel": dom, "achieved": stages[dom]["GBps"], "peak": peak, "unit": "GB/s", "frac": stages[dom]["frac"],
+                "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": stages[dom]["algorithmic_bytes"], "stages": stages}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": args.workload, "desc": w["desc"], "nodes_per_gpu": w["nodes"], "skinned_meshes_per_gpu": w["units"],
+                   "bones_per_mesh": BONES, "verts_per_mesh": w["verts_per_unit"], "skinned_verts_per_gpu": w["units"] * w["verts_per_unit"],
+                   "frusta": len(frusta), "update": "all-dirty (every node recomputed)", "parallelism": f"shard{world}" if world > 1 else "single",
+                   "l2": "inputs larger than L2 (node columns + vertex streams >> 126 MB); no flush needed", "visible_entries": sum_vis},
+        "fps": 1e3 / ms_per_step,
+        "nodes_per_s": w["nodes"] * world / (ms_per_step * 1e-3), "verts_per_s": w["units"] * w["verts_per_unit"] * world / (ms_per_step * 1e-3),
+        "clocks": clk,
+        "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms_per_step, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "api": "fyx_render_prep (C ABI) with pinned host buffers: changed bone matrices up, visible lists down"},
+        "gpu_launches": int(launches),
+        "roofline": roofline,
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        try:
+            sample = cpu_sample_config(w)
+            ref = CpuReference(sample)
+            ref.step()
+            t, n = 0.0, 0
+            while n < 2:
+                dt, _ = ref.step()
+                t += dt
+                n += 1
+            desc = f"{sample['nodes']} nodes, {sample['units']} skinned meshes x {BONES} bones x {sample['verts_per_unit']} verts, {sample['frusta']} frusta; {n} frames"
+            line["cpu_baseline"] = {"value": ref.units_per_frame() * n / t, "unit": UNIT, "cores": 1, "kind": "port", "sample": desc,
+                                    "host_cores_available": os.cpu_count()}
+        except Exception as ex:  # the baseline is reported, never allowed to break the measurement
+            line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 1, "kind": "port", "sample": f"failed: {ex!r}"}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
+    ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--verbose", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_cuda(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

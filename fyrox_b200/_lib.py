@@ -43,6 +43,7 @@ NODE_DEFAULT = NODE_VISIBILITY | NODE_ENABLED | NODE_FRUSTUM_CULLING | NODE_CAST
 UPDATE_INCREMENTAL = 0
 UPDATE_ALL = 1
 PASS_SHADOW = 1
+FRAME_ASYNC = 1
 
 u32p = C.POINTER(C.c_uint32)
 f32p = C.POINTER(C.c_float)
@@ -84,6 +85,7 @@ class fyx_frame_desc(C.Structure):
         ("do_palettes", C.c_uint32),
         ("do_skin", C.c_uint32),
         ("readback_visible", C.c_uint32),
+        ("flags", C.c_uint32),
     ]
 
 
@@ -109,6 +111,7 @@ SYMBOLS = {
         C.c_int32,
         [ctx_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.POINTER(fyx_vertex_layout), u32p],
     ),
+    "fyx_reserve_skinning": (C.c_int32, [ctx_p, C.c_uint64, C.c_uint64]),
     "fyx_commit_surfaces": (C.c_int32, [ctx_p]),
     "fyx_update_transforms": (C.c_int32, [ctx_p, C.c_uint32]),
     "fyx_cull": (C.c_int32, [ctx_p, C.c_uint32, C.POINTER(fyx_frustum), C.c_void_p, C.c_void_p]),

@@ -204,6 +204,9 @@ class Context:
         self._surfaces.append((int(bone_nodes.size), int(n_verts)))
         return sid.value
 
+    def reserve_skinning(self, total_bones: int, total_verts: int):
+        self._chk(self._lib.fyx_reserve_skinning(self._h, total_bones, total_verts))
+
     def commit_surfaces(self):
         self._chk(self._lib.fyx_commit_surfaces(self._h))
 
@@ -248,7 +251,7 @@ class Context:
         self._chk(self._lib.fyx_skin(self._h))
 
     def render_prep(self, *, update_flags=L.UPDATE_INCREMENTAL, changed_m16=None, changed_idx=None, n_changed=None, frusta=(), cam_mask=None,
-                    pass_flags=None, do_palettes=True, do_skin=True, readback_visible=True):
+                    pass_flags=None, do_palettes=True, do_skin=True, readback_visible=True, async_=False):
         """One frame (fyx_render_prep). changed_m16 / changed_idx may be numpy arrays or raw (pinned) addresses."""
         d = L.fyx_frame_desc()
         d.struct_size = C.sizeof(L.fyx_frame_desc)
@@ -279,7 +282,10 @@ class Context:
         d.pass_flags = None if pf is None else pf.ctypes.data
         d.do_palettes = 1 if do_palettes else 0
         d.do_skin = 1 if do_skin else 0
-        d.readback_visible = 1 if readback_visible else 0
+        d.readback_visible = 1 if (readback_visible and not async_) else 0
+        d.flags = L.FRAME_ASYNC if async_ else 0
+        if async_:
+            self._async_keep = keep  # inputs must outlive the enqueued frame
         self._chk(self._lib.fyx_render_prep(self._h, C.byref(d)))
 
     # -- read-back --

@@ -89,6 +89,7 @@ struct fyx_ctx {
     // timing
     cudaEvent_t ev[EV_COUNT] = {};
     fyx_timings timings{};
+    bool timings_pending = false; // an async frame's events have not been read yet
 
     // multi-GPU (fyx_comm.cu)
     void *comm = nullptr;
@@ -932,6 +933,20 @@ extern "C" int32_t fyx_add_skinned_surface(fyx_ctx *c, uint32_t mesh_node, uint3
     return FYX_OK;
 }
 
+extern "C" int32_t fyx_reserve_skinning(fyx_ctx *c, uint64_t total_bones, uint64_t total_verts)
+{
+    if (!c) return FYX_ERR_INVALID_ARGUMENT;
+    if (total_bones > 0xFFFFFFFFull) return fail(c, FYX_ERR_INVALID_ARGUMENT, "too many bones");
+    CU(cudaSetDevice(c->device));
+    int32_t rc = grow_bone_tables(c, (uint32_t)total_bones);
+    if (rc) return rc;
+    // every surface is padded to a multiple of 4 vertices: leave room for 3 per surface (bounded by bones)
+    rc = grow_vertex_streams(c, total_verts + 4 * total_bones + 4);
+    if (rc) return rc;
+    rebuild_skin_arrays(c);
+    return FYX_OK;
+}
+
 extern "C" int32_t fyx_commit_surfaces(fyx_ctx *c)
 {
     if (!c) return FYX_ERR_INVALID_ARGUMENT;
@@ -1054,10 +1069,25 @@ extern "C" int32_t fyx_skin(fyx_ctx *c)
     return rc;
 }
 
+static void frame_timings_from_events(fyx_ctx *c)
+{
+    fyx_timings &t = c->timings;
+    cudaEventElapsedTime(&t.upload_ms, c->ev[EV_START], c->ev[EV_UPLOAD]);
+    cudaEventElapsedTime(&t.update_ms, c->ev[EV_UPLOAD], c->ev[EV_UPDATE]);
+    cudaEventElapsedTime(&t.palette_ms, c->ev[EV_UPDATE], c->ev[EV_PALETTE]);
+    cudaEventElapsedTime(&t.skin_ms, c->ev[EV_PALETTE], c->ev[EV_SKIN]);
+    cudaEventElapsedTime(&t.readback_ms, c->ev[EV_SKIN], c->ev[EV_READBACK]);
+    cudaEventElapsedTime(&t.total_ms, c->ev[EV_START], c->ev[EV_READBACK]);
+    t.cull_ms = 0.0f;
+    c->timings_pending = false;
+}
+
 extern "C" int32_t fyx_render_prep(fyx_ctx *c, const fyx_frame_desc *fr)
 {
     if (!c || !fr) return FYX_ERR_INVALID_ARGUMENT;
     if (fr->struct_size < sizeof(fyx_frame_desc)) return fail(c, FYX_ERR_INVALID_ARGUMENT, "fyx_frame_desc.struct_size too small");
+    if ((fr->flags & FYX_FRAME_ASYNC) && fr->readback_visible)
+        return fail(c, FYX_ERR_INVALID_ARGUMENT, "FYX_FRAME_ASYNC cannot be combined with readback_visible");
     if (!c->have_topology) return fail(c, FYX_ERR_STATE, "fyx_set_topology has not been called");
     CU(cudaSetDevice(c->device));
     int32_t rc = commit_surfaces(c);
@@ -1102,15 +1132,12 @@ extern "C" int32_t fyx_render_prep(fyx_ctx *c, const fyx_frame_desc *fr)
         if (rc) return rc;
     }
     CU(cudaEventRecord(c->ev[EV_READBACK], s));
+    if (fr->flags & FYX_FRAME_ASYNC) {
+        c->timings_pending = true;
+        return FYX_OK;
+    }
     rc = sync_and_check(c);
-    fyx_timings &t = c->timings;
-    cudaEventElapsedTime(&t.upload_ms, c->ev[EV_START], c->ev[EV_UPLOAD]);
-    cudaEventElapsedTime(&t.update_ms, c->ev[EV_UPLOAD], c->ev[EV_UPDATE]);
-    cudaEventElapsedTime(&t.palette_ms, c->ev[EV_UPDATE], c->ev[EV_PALETTE]);
-    cudaEventElapsedTime(&t.skin_ms, c->ev[EV_PALETTE], c->ev[EV_SKIN]);
-    cudaEventElapsedTime(&t.readback_ms, c->ev[EV_SKIN], c->ev[EV_READBACK]);
-    cudaEventElapsedTime(&t.total_ms, c->ev[EV_START], c->ev[EV_READBACK]);
-    t.cull_ms = 0.0f;
+    frame_timings_from_events(c);
     return rc;
 }
 
@@ -1205,6 +1232,11 @@ extern "C" int32_t fyx_get_skinned_device(fyx_ctx *c, uint32_t sid, const float 
 extern "C" int32_t fyx_get_timings(fyx_ctx *c, fyx_timings *out)
 {
     if (!c || !out) return FYX_ERR_INVALID_ARGUMENT;
+    if (c->timings_pending) {
+        CU(cudaSetDevice(c->device));
+        CU(cudaEventSynchronize(c->ev[EV_READBACK]));
+        frame_timings_from_events(c);
+    }
     *out = c->timings;
     return FYX_OK;
 }

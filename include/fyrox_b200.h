@@ -157,6 +157,9 @@ int32_t fyx_set_local_aabbs(fyx_ctx *ctx, uint32_t count, const uint32_t *idx, c
 int32_t fyx_add_skinned_surface(fyx_ctx *ctx, uint32_t mesh_node, uint32_t n_bones, const uint32_t *bone_nodes,
                                 const float *inv_bind_m16, uint32_t n_verts, const void *verts,
                                 const fyx_vertex_layout *layout, uint32_t *out_surface_id);
+/* Optional: size the device-side bone / vertex tables once for `total_bones` palette entries and
+ * `total_verts` vertices (sum over all surfaces to be added) instead of growing them on demand. */
+int32_t fyx_reserve_skinning(fyx_ctx *ctx, uint64_t total_bones, uint64_t total_verts);
 /* Finish a batch of fyx_add_skinned_surface calls (builds the device-side bone/vertex tables). Called
  * implicitly by the first per-frame call that needs them. */
 int32_t fyx_commit_surfaces(fyx_ctx *ctx);
@@ -207,7 +210,12 @@ typedef struct fyx_frame_desc {
     uint32_t do_palettes;
     uint32_t do_skin;
     uint32_t readback_visible;     /* copy counts + lists to the host before returning */
+    uint32_t flags;                /* FYX_FRAME_* */
 } fyx_frame_desc;
+/* Do not synchronise with the host at the end of fyx_render_prep: the frame is only enqueued on the
+ * context's stream (fyx_sync / any read-back waits for it).  Inputs must then stay untouched until that
+ * wait; incompatible with readback_visible. */
+#define FYX_FRAME_ASYNC (1u << 0)
 int32_t fyx_render_prep(fyx_ctx *ctx, const fyx_frame_desc *frame);
 
 /* ---- read-back (tests, tools, and the parts of the engine that stay on the CPU) -------------- */

@@ -64,6 +64,12 @@ def scene_pair(sc: Scene, ctx: fb.Context, with_vertices=True):
     return og, sids
 
 
+def bits_equal(a: np.ndarray, b: np.ndarray) -> np.ndarray:
+    """Element-wise bit equality of two f32 arrays, except that any NaN equals any NaN (neither Rust nor
+    CUDA defines the sign/payload of a generated NaN: x86 makes 0xFFC00000, the GPU 0x7FFFFFFF)."""
+    return (a.view(np.uint32) == b.view(np.uint32)) | (np.isnan(a) & np.isnan(b))
+
+
 def assert_same_hierarchy(og: ob.Graph, ctx: fb.Context, idx=None):
     n = og.capacity
     idx = np.arange(n, dtype=np.uint32) if idx is None else np.asarray(idx, np.uint32)
@@ -72,8 +78,8 @@ def assert_same_hierarchy(og: ob.Graph, ctx: fb.Context, idx=None):
     F = ctx.get_global_flags(idx)
     Go = og.global_transforms(idx)
     Ao = og.world_bounding_boxes(idx)
-    assert G.tobytes() == Go.tobytes(), f"global transforms differ at {np.nonzero((G.view(np.uint32) != Go.view(np.uint32)).any(axis=1))[0][:10]}"
-    assert A.tobytes() == Ao.tobytes(), f"world AABBs differ at {np.nonzero((A.view(np.uint32) != Ao.view(np.uint32)).any(axis=1))[0][:10]}"
+    assert bits_equal(G, Go).all(), f"global transforms differ at {idx[np.nonzero((~bits_equal(G, Go)).any(axis=1))[0][:10]]}"
+    assert bits_equal(A, Ao).all(), f"world AABBs differ at {idx[np.nonzero((~bits_equal(A, Ao)).any(axis=1))[0][:10]]}"
     gv = np.array([og.global_visibility(int(i)) for i in idx])
     ge = np.array([og.is_globally_enabled(int(i)) for i in idx])
     assert (((F & fb.NODE_GLOBAL_VISIBILITY) != 0) == gv).all()
