@@ -281,8 +281,11 @@ def run_cuda(args):
     w = WORKLOADS[args.workload]
     # weak scaling: per-GPU work fixed; the scene grows with N and is sharded by sector sub-tree
     sc = Scene(w["nodes"] * world, n_units=w["units"] * world, verts_per_unit=w["verts_per_unit"], bones_per_unit=BONES, seed=SEED, rank=rank, nranks=world)
-    stream = torch.cuda.current_stream().cuda_stream
-    ctx = fb.Context(device=local_rank, stream=stream)
+    # the context launches on an explicit torch stream so that torch.cuda.Event brackets exactly its work
+    tstream = torch.cuda.Stream(device=local_rank)
+    torch.cuda.set_stream(tstream)
+    assert tstream.cuda_stream != 0
+    ctx = fb.Context(device=local_rank, stream=tstream.cuda_stream)
     load_scene(ctx, sc, fb, log)
     if world > 1:
         uid = torch.zeros(128, dtype=torch.uint8, device="cuda")

@@ -81,7 +81,7 @@ struct fyx_ctx {
     uint32_t n_entries = 0, entry_cap = 0;
     DevBuf b_vpos, b_vnrm, b_vw, b_vidx, b_opos, b_onrm, b_ib[3], b_palette, b_bone_slot, b_tiles;
     DevBuf b_fold_node, b_fold_begin, b_fold_bone;
-    uint32_t n_tiles = 0;
+    uint32_t n_tiles = 0, max_bones = 0;
     FoldArrays fold{};
     SkinArrays sk{};
     std::vector<uint8_t> skinned_node; // per node: has a skinned surface
@@ -273,6 +273,11 @@ void to_dev_frustum(const fyx_frustum &f, uint32_t cam_mask, uint32_t pass_flags
         }
     d.cam_mask = cam_mask;
     d.pass_flags = pass_flags;
+    d.psel = 0;
+    d.pad_ = 0;
+    for (int p = 0; p < 6; ++p)
+        for (int k = 0; k < 3; ++k)
+            if (f.planes[p][k] < 0.0f) d.psel |= 1u << (3 * p + k);
 }
 
 int32_t prepare_cull(fyx_ctx *c, uint32_t nf, const fyx_frustum *fr, const uint32_t *cam_mask, const uint32_t *pass_flags)
@@ -856,6 +861,9 @@ int32_t commit_surfaces(fyx_ctx *c)
     CU(cudaMemcpy(c->b_fold_begin.p, fold_begin.data(), fold_begin.size() * 4, cudaMemcpyHostToDevice));
     if (!fold_bone.empty()) CU(cudaMemcpy(c->b_fold_bone.p, fold_bone.data(), fold_bone.size() * 4, cudaMemcpyHostToDevice));
     c->n_tiles = (uint32_t)tiles.size();
+    c->max_bones = 0;
+    for (const Surface &sf : c->surfaces)
+        if (sf.n_verts) c->max_bones = std::max(c->max_bones, sf.n_bones);
     c->fold.n = (uint32_t)fold_node.size();
     c->fold.node_slot = c->b_fold_node.as<uint32_t>();
     c->fold.bone_begin = c->b_fold_begin.as<uint32_t>();
@@ -1060,7 +1068,7 @@ extern "C" int32_t fyx_skin(fyx_ctx *c)
     if (rc) return rc;
     CU(cudaEventRecord(c->ev[EV_START], c->stream));
     if (c->n_tiles) {
-        launch_skin(c->stream, c->sk, c->b_tiles.as<SkinTile>(), c->n_tiles);
+        launch_skin(c->stream, c->sk, c->b_tiles.as<SkinTile>(), c->n_tiles, c->max_bones);
         c->launches++;
     }
     CU(cudaEventRecord(c->ev[EV_SKIN], c->stream));
@@ -1121,7 +1129,7 @@ extern "C" int32_t fyx_render_prep(fyx_ctx *c, const fyx_frame_desc *fr)
     }
     CU(cudaEventRecord(c->ev[EV_PALETTE], s));
     if (fr->do_skin && c->n_tiles) {
-        launch_skin(s, c->sk, c->b_tiles.as<SkinTile>(), c->n_tiles);
+        launch_skin(s, c->sk, c->b_tiles.as<SkinTile>(), c->n_tiles, c->max_bones);
         c->launches++;
     }
     CU(cudaEventRecord(c->ev[EV_SKIN], s));

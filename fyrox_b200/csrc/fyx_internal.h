@@ -77,7 +77,7 @@ void launch_update_level(cudaStream_t s, const NodeArrays &a, uint32_t lo, uint3
 void launch_cull(cudaStream_t s, const NodeArrays &a, const CullParams &cp);
 void launch_fold_bones(cudaStream_t s, const NodeArrays &a, const FoldArrays &fa, const CullParams *cull);
 void launch_palette(cudaStream_t s, const NodeArrays &a, const SkinArrays &sk);
-void launch_skin(cudaStream_t s, const SkinArrays &sk, const SkinTile *tiles, uint32_t n_tiles);
+void launch_skin(cudaStream_t s, const SkinArrays &sk, const SkinTile *tiles, uint32_t n_tiles, uint32_t max_bones);
 
 void launch_scatter_locals(cudaStream_t s, const NodeArrays &a, uint32_t count, const uint32_t *d_idx,
                            const float *d_m16, const uint32_t *slot_of_node, uint32_t n_nodes, uint32_t *d_err);

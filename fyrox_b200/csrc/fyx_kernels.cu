@@ -292,18 +292,34 @@ __global__ void __launch_bounds__(kBlock) k_palette(const NodeArrays a, const Sk
 // 3 (pos) + 3 (normal) + 4 (weights) + 1 (indices) LDG.128, 3 + 3 STG.128.
 // Algorithmic bytes per vertex: 44 read + 24 written = 68.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kBlock) k_skin(const SkinArrays sk, const SkinTile *__restrict__ tiles)
+__global__ void __launch_bounds__(kBlock) k_skin(const SkinArrays sk, const SkinTile *__restrict__ tiles, const uint32_t copy_stride,
+                                                  const uint32_t n_copies_log2)
 {
-    extern __shared__ float4 s_pal[]; // n_bones * 3 rows
+    // Palette in shared memory as float4 rows, 3 per bone, REPLICATED 2^n_copies_log2 times.  A 128-bit
+    // shared load is served per quarter-warp (8 lanes x 16 B = all 32 banks once); with one copy, 8 lanes
+    // reading rows of 8 random bones collide on the 8 four-bank groups (measured: 57 % of the wavefronts
+    // were bank-conflict replays).  Copy c starts at float4 index c*copy_stride with copy_stride = 1 mod 8,
+    // so row (b,r) of copy c sits in bank group (3b + r + c) mod 8: lane l reads copy (l - 3b - r) mod 8
+    // and lands in group l mod 8 — conflict-free whatever the bone indices are.
+    extern __shared__ float4 s_pal[];
     const SkinTile t = tiles[blockIdx.x];
+    const uint32_t n_copies = 1u << n_copies_log2;
     for (uint32_t b = threadIdx.x; b < t.n_bones; b += kBlock) {
         const float4 *m = reinterpret_cast<const float4 *>(sk.palette + 16 * (size_t)(t.bone_off + b));
         const float4 c0 = m[0], c1 = m[1], c2 = m[2], c3 = m[3];
-        s_pal[3 * b + 0] = make_float4(c0.x, c1.x, c2.x, c3.x);
-        s_pal[3 * b + 1] = make_float4(c0.y, c1.y, c2.y, c3.y);
-        s_pal[3 * b + 2] = make_float4(c0.z, c1.z, c2.z, c3.z);
+        const float4 r0 = make_float4(c0.x, c1.x, c2.x, c3.x);
+        const float4 r1 = make_float4(c0.y, c1.y, c2.y, c3.y);
+        const float4 r2 = make_float4(c0.z, c1.z, c2.z, c3.z);
+        for (uint32_t c = 0; c < n_copies; ++c) {
+            float4 *dst = s_pal + c * copy_stride + 3 * b;
+            dst[0] = r0;
+            dst[1] = r1;
+            dst[2] = r2;
+        }
     }
     __syncthreads();
+    const uint32_t copy_mask = n_copies - 1u;
+    const uint32_t lane = threadIdx.x & 31u;
 
     for (uint32_t q = threadIdx.x; q < t.n_quads; q += kBlock) {
         const size_t quad = (size_t)t.quad_start + q;
@@ -326,8 +342,11 @@ __global__ void __launch_bounds__(kBlock) k_skin(const SkinArrays sk, const Skin
             const float wk[4] = {wv[v].x, wv[v].y, wv[v].z, wv[v].w};
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-                const uint32_t bone = (iv[v] >> (8 * k)) & 0xFFu;
-                const float4 r0 = s_pal[3 * bone + 0], r1 = s_pal[3 * bone + 1], r2 = s_pal[3 * bone + 2];
+                const uint32_t bone3 = 3u * ((iv[v] >> (8 * k)) & 0xFFu);
+                const uint32_t a0 = bone3 + ((lane - bone3) & copy_mask) * copy_stride;
+                const uint32_t a1 = bone3 + 1u + ((lane - bone3 - 1u) & copy_mask) * copy_stride;
+                const uint32_t a2 = bone3 + 2u + ((lane - bone3 - 2u) & copy_mask) * copy_stride;
+                const float4 r0 = s_pal[a0], r1 = s_pal[a1], r2 = s_pal[a2];
                 const float w = wk[k];
                 const float tx = FYX_ADD(FYX_ADD(FYX_ADD(FYX_MUL(r0.x, px[v]), FYX_MUL(r0.y, py[v])), FYX_MUL(r0.z, pz[v])), r0.w);
                 const float ty = FYX_ADD(FYX_ADD(FYX_ADD(FYX_MUL(r1.x, px[v]), FYX_MUL(r1.y, py[v])), FYX_MUL(r1.z, pz[v])), r1.w);
@@ -601,11 +620,21 @@ void launch_palette(cudaStream_t s, const NodeArrays &a, const SkinArrays &sk)
     k_palette<<<grid_for(sk.n_entries), kBlock, 0, s>>>(a, sk);
 }
 
-void launch_skin(cudaStream_t s, const SkinArrays &sk, const SkinTile *tiles, uint32_t n_tiles)
+void launch_skin(cudaStream_t s, const SkinArrays &sk, const SkinTile *tiles, uint32_t n_tiles, uint32_t max_bones)
 {
     if (!n_tiles) return;
-    const size_t smem = (size_t)FYX_MAX_BONES * 3 * sizeof(float4); // 12 240 B: fits the default 48 KB window
-    k_skin<<<n_tiles, kBlock, smem, s>>>(sk, tiles);
+    if (max_bones < 1) max_bones = 1;
+    // copies of the palette: 8 (conflict-free) while 8 copies stay under ~64 KB, else 4, 2, 1
+    uint32_t stride = ((3u * max_bones + 7u) & ~7u) + 1u; // = 1 mod 8
+    uint32_t log2c = 3;
+    while (log2c > 0 && (size_t)(stride << log2c) * sizeof(float4) > 64u * 1024u) --log2c;
+    const size_t smem = (size_t)(stride << log2c) * sizeof(float4);
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(k_skin, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024 + 16);
+        attr_set = true;
+    }
+    k_skin<<<n_tiles, kBlock, smem, s>>>(sk, tiles, stride, log2c);
 }
 
 void launch_scatter_locals(cudaStream_t s, const NodeArrays &a, uint32_t count, const uint32_t *d_idx, const float *d_m16,

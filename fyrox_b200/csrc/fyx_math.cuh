@@ -86,6 +86,8 @@ struct FrustumDev {
     float cmin[3], cmax[3];
     uint32_t cam_mask;
     uint32_t pass_flags;
+    uint32_t psel;   // bit (3*p + axis): the plane-p normal component on that axis is negative
+    uint32_t pad_;
 };
 
 // Frustum::is_intersects_aabb (fyrox-math/src/frustum.rs:222-245) on (min,max) pairs per axis.
@@ -94,26 +96,28 @@ struct FrustumDev {
 // s(corner) = ((nx*px + ny*py) + nz*pz) + d with one rounding per op (plane.rs:78-80, Appendix A6).
 // Rounding is monotone, so the corner built from the per-axis larger products has the largest s of
 // the eight: "all eight <= 0"  ⇔  that corner's s <= 0 — the same booleans as the reference loop in
-// 13 ops per plane instead of 56.  The argument needs NaN-free arithmetic: boxes with a non-finite or
-// huge (>1e18) bound take the literal 8-corner loop instead (never in practice; the branch is uniform).
+// 10 ops per plane instead of 56.  The argument needs NaN-free arithmetic and min <= max: boxes with a
+// non-finite or huge (>1e18) bound or an inverted axis take the literal 8-corner loop instead (never in
+// practice; the branch is uniform).
 __device__ __forceinline__ bool frustum_intersects_aabb(const FrustumDev &f, const float2 x, const float2 y,
                                                         const float2 z)
 {
     bool cloud = true;
     const float kBig = 1e18f;
     const bool tame = (fabsf(x.x) <= kBig) & (fabsf(x.y) <= kBig) & (fabsf(y.x) <= kBig) & (fabsf(y.y) <= kBig) &
-                      (fabsf(z.x) <= kBig) & (fabsf(z.y) <= kBig);
+                      (fabsf(z.x) <= kBig) & (fabsf(z.y) <= kBig) & (x.x <= x.y) & (y.x <= y.y) & (z.x <= z.y);
     if (tame) {
+        // n*p is monotone in p (rounding is monotone), so max(fl(n*min), fl(n*max)) is fl(n*max) for n >= 0
+        // and fl(n*min) for n < 0: pick the operand first (psel, built on the host) and multiply once.
+        // For n == ±0 both products are zeros; either choice gives the same booleans.
+        const uint32_t sel = f.psel;
 #pragma unroll
         for (int p = 0; p < 6; ++p) {
             const float4 pl = f.plane[p];
-            const float ax = FYX_MUL(pl.x, x.x), bx = FYX_MUL(pl.x, x.y);
-            const float ay = FYX_MUL(pl.y, y.x), by = FYX_MUL(pl.y, y.y);
-            const float az = FYX_MUL(pl.z, z.x), bz = FYX_MUL(pl.z, z.y);
-            const float mx = ax > bx ? ax : bx;
-            const float my = ay > by ? ay : by;
-            const float mz = az > bz ? az : bz;
-            const float s = FYX_ADD(FYX_ADD(FYX_ADD(mx, my), mz), pl.w);
+            const float vx = (sel >> (3 * p + 0)) & 1u ? x.x : x.y;
+            const float vy = (sel >> (3 * p + 1)) & 1u ? y.x : y.y;
+            const float vz = (sel >> (3 * p + 2)) & 1u ? z.x : z.y;
+            const float s = FYX_ADD(FYX_ADD(FYX_ADD(FYX_MUL(pl.x, vx), FYX_MUL(pl.y, vy)), FYX_MUL(pl.z, vz)), pl.w);
             cloud &= !(s <= 0.0f);
         }
     } else {
