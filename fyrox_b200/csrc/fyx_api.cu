@@ -799,7 +799,7 @@ void rebuild_skin_arrays(fyx_ctx *c)
     sk.onrm = c->b_onrm.as<float>();
 }
 
-constexpr uint32_t kTileQuads = 1024; // 4096 vertices per CTA
+constexpr uint32_t kTileQuads = 2048; // up to 8192 vertices per tile (a 5k-vertex surface is one tile)
 
 // (re)build bone-slot, fold and tile tables from the host-side surface list
 int32_t commit_surfaces(fyx_ctx *c)

@@ -3,6 +3,8 @@
 // All kernels are HBM-bandwidth-bound streaming kernels over SoA planes (no tensor cores: 4x4 f32
 // work at ~0.3-1 flop/B).  Arithmetic follows fyx_math.cuh (one rounding per op, reference order).
 // Each kernel names the reference code it replaces (paths relative to the Fyrox tree).
+#include <cstdlib>
+
 #include "fyx_internal.h"
 
 namespace fyx {
@@ -286,43 +288,131 @@ __global__ void __launch_bounds__(kBlock) k_palette(const NodeArrays a, const Sk
 // for the affine palette and finite p, so the division is the identity and is skipped.  Normals:
 // standard.shader:192-195, acc += (mat3(P[idx_k]) * n) * w_k in the same order.
 //
-// One CTA per tile (a run of 4-vertex groups of one surface).  The surface's palette is staged in
-// shared memory as 3 float4 rows per bone (48 B stride ⇒ 8 consecutive bones hit 8 distinct 4-bank
-// groups).  Each thread owns 4 consecutive vertices so every stream access is a 128-bit load/store:
-// 3 (pos) + 3 (normal) + 4 (weights) + 1 (indices) LDG.128, 3 + 3 STG.128.
+// * Each thread owns 4 consecutive vertices, so every stream access is 128 bits wide: 3 (pos) + 3
+//   (normal) + 4 (weights) + 1 (indices) in, 3 + 3 out.
+// * Arithmetic uses Blackwell's packed FP32 pipe (mul.rn.f32x2 / add.rn.f32x2 via __fmul2_rn /
+//   __fadd2_rn: two independently rounded f32 results per issue slot).  The kernel is issue-bound
+//   (ncu: 8.6 warp-instructions per vertex), and FMA contraction is forbidden, so halving the FP
+//   instruction count is the lever.  Pairs: (x,y) of the position, (x,y) of the normal, and
+//   (position.z, normal.z) — same op order per element as the scalar reference.
+// * The surface's palette sits in shared memory as four float4 planes laid out for those pairs:
+//     A = (m00,m10,m01,m11)  B = (m02,m12,m03,m13)  D = (m20,m20,m21,m21)  E = (m22,m22,m23,0)
+//   each plane REPLICATED C times: bone b of copy c at float4 index plane*PL + c*S + b with S = 1 mod 8,
+//   PL = C*S.  A 128-bit shared load is served per quarter-warp; lane l reads copy (l - b) mod C,
+//   which puts it in bank group (plane*PL + l) mod 8: conflict-free for C = 8 whatever the bone
+//   indices are (with one copy, 57 % of the shared-memory wavefronts were conflict replays).
 // Algorithmic bytes per vertex: 44 read + 24 written = 68.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kBlock) k_skin(const SkinArrays sk, const SkinTile *__restrict__ tiles, const uint32_t copy_stride,
-                                                  const uint32_t n_copies_log2)
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src)
 {
-    // Palette in shared memory as float4 rows, 3 per bone, REPLICATED 2^n_copies_log2 times.  A 128-bit
-    // shared load is served per quarter-warp (8 lanes x 16 B = all 32 banks once); with one copy, 8 lanes
-    // reading rows of 8 random bones collide on the 8 four-bank groups (measured: 57 % of the wavefronts
-    // were bank-conflict replays).  Copy c starts at float4 index c*copy_stride with copy_stride = 1 mod 8,
-    // so row (b,r) of copy c sits in bank group (3b + r + c) mod 8: lane l reads copy (l - 3b - r) mod 8
-    // and lands in group l mod 8 — conflict-free whatever the bone indices are.
-    extern __shared__ float4 s_pal[];
-    const SkinTile t = tiles[blockIdx.x];
-    const uint32_t n_copies = 1u << n_copies_log2;
-    for (uint32_t b = threadIdx.x; b < t.n_bones; b += kBlock) {
-        const float4 *m = reinterpret_cast<const float4 *>(sk.palette + 16 * (size_t)(t.bone_off + b));
+    const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+// Packed f32x2 product / sum with ONE rounding each.  ptxas 12.9 contracts mul.rn.f32x2 + add.rn.f32x2 into
+// FFMA2 even with --fmad=false (the GPU parity tests catch the resulting 1-ulp differences), so both are
+// written as FMAs it cannot contract or simplify: a*b + (-0) is the correctly rounded product with the
+// right zero sign, a*1 + c the correctly rounded sum.  `one` / `negzero` arrive as kernel parameters so
+// that the assembler cannot fold them.
+struct PackedConsts {
+    float2 one, negzero;
+};
+__device__ __forceinline__ float2 mul2(const float2 a, const float2 b, const PackedConsts &k) { return __ffma2_rn(a, b, k.negzero); }
+__device__ __forceinline__ float2 add2(const float2 a, const float2 c, const PackedConsts &k) { return __ffma2_rn(a, k.one, c); }
+
+__device__ __forceinline__ float2 lo2(const float4 v) { return make_float2(v.x, v.y); }
+__device__ __forceinline__ float2 hi2(const float4 v) { return make_float2(v.z, v.w); }
+
+// palette (column-major mat4 in global memory) → the four replicated planes
+template <int S, int LOG2C>
+__device__ __forceinline__ void skin_fill_palette(float4 *s_pal, const float *palette, const uint32_t bone_off, const uint32_t n_bones)
+{
+    constexpr int C = 1 << LOG2C;
+    constexpr int PL = S * C;
+    for (uint32_t b = threadIdx.x; b < n_bones; b += kBlock) {
+        const float4 *m = reinterpret_cast<const float4 *>(palette + 16 * (size_t)(bone_off + b));
         const float4 c0 = m[0], c1 = m[1], c2 = m[2], c3 = m[3];
-        const float4 r0 = make_float4(c0.x, c1.x, c2.x, c3.x);
-        const float4 r1 = make_float4(c0.y, c1.y, c2.y, c3.y);
-        const float4 r2 = make_float4(c0.z, c1.z, c2.z, c3.z);
-        for (uint32_t c = 0; c < n_copies; ++c) {
-            float4 *dst = s_pal + c * copy_stride + 3 * b;
-            dst[0] = r0;
-            dst[1] = r1;
-            dst[2] = r2;
+        const float4 A = make_float4(c0.x, c0.y, c1.x, c1.y);
+        const float4 B = make_float4(c2.x, c2.y, c3.x, c3.y);
+        const float4 D = make_float4(c0.z, c0.z, c1.z, c1.z);
+        const float4 E = make_float4(c2.z, c2.z, c3.z, 0.0f);
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+            s_pal[0 * PL + c * S + b] = A;
+            s_pal[1 * PL + c * S + b] = B;
+            s_pal[2 * PL + c * S + b] = D;
+            s_pal[3 * PL + c * S + b] = E;
         }
     }
-    __syncthreads();
-    const uint32_t copy_mask = n_copies - 1u;
-    const uint32_t lane = threadIdx.x & 31u;
+}
 
-    for (uint32_t q = threadIdx.x; q < t.n_quads; q += kBlock) {
-        const size_t quad = (size_t)t.quad_start + q;
+// four vertices (one thread's group) from registers to the two output streams
+template <int S, int LOG2C>
+__device__ __forceinline__ void skin_quad(const float4 *s_pal, const uint32_t lane, const float4 p0, const float4 p1, const float4 p2,
+                                          const float4 n0, const float4 n1, const float4 n2, const float4 w0, const float4 w1,
+                                          const float4 w2, const float4 w3, const uint4 iq, float4 *po, float4 *no,
+                                          const PackedConsts kc)
+{
+    constexpr int C = 1 << LOG2C;
+    constexpr int PL = S * C;
+    const float px[4] = {p0.x, p0.w, p1.z, p2.y}, py[4] = {p0.y, p1.x, p1.w, p2.z}, pz[4] = {p0.z, p1.y, p2.x, p2.w};
+    const float nx[4] = {n0.x, n0.w, n1.z, n2.y}, ny[4] = {n0.y, n1.x, n1.w, n2.z}, nz[4] = {n0.z, n1.y, n2.x, n2.w};
+    const float4 wv[4] = {w0, w1, w2, w3};
+    const uint32_t iv[4] = {iq.x, iq.y, iq.z, iq.w};
+    float ox[4], oy[4], oz[4], mx[4], my[4], mz[4];
+#pragma unroll
+    for (int v = 0; v < 4; ++v) {
+        const float2 pxx = make_float2(px[v], px[v]), pyy = make_float2(py[v], py[v]), pzz = make_float2(pz[v], pz[v]);
+        const float2 nxx = make_float2(nx[v], nx[v]), nyy = make_float2(ny[v], ny[v]), nzz = make_float2(nz[v], nz[v]);
+        const float2 pnx = make_float2(px[v], nx[v]), pny = make_float2(py[v], ny[v]), pnz = make_float2(pz[v], nz[v]);
+        float2 acc_p = make_float2(0.0f, 0.0f), acc_n = make_float2(0.0f, 0.0f), acc_z = make_float2(0.0f, 0.0f);
+        const float wk[4] = {wv[v].x, wv[v].y, wv[v].z, wv[v].w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const uint32_t bone = (iv[v] >> (8 * k)) & 0xFFu;
+            const float4 *row = s_pal + (((lane - bone) & (uint32_t)(C - 1)) * S + bone);
+            const float4 A = row[0], B = row[PL], D = row[2 * PL], E = row[3 * PL];
+            const float2 ww = make_float2(wk[k], wk[k]);
+            // (tx, ty) = ((m_i0*x + m_i1*y) + m_i2*z) + m_i3, i = 0,1
+            const float2 t = add2(add2(add2(mul2(lo2(A), pxx, kc), mul2(hi2(A), pyy, kc), kc), mul2(lo2(B), pzz, kc), kc), hi2(B), kc);
+            acc_p = add2(acc_p, mul2(t, ww, kc), kc);
+            // (rx, ry) = (m_i0*nx + m_i1*ny) + m_i2*nz
+            const float2 r = add2(add2(mul2(lo2(A), nxx, kc), mul2(hi2(A), nyy, kc), kc), mul2(lo2(B), nzz, kc), kc);
+            acc_n = add2(acc_n, mul2(r, ww, kc), kc);
+            // (tz', rz) = (m_20*{x,nx} + m_21*{y,ny}) + m_22*{z,nz};  tz = tz' + m_23
+            float2 z = add2(add2(mul2(lo2(D), pnx, kc), mul2(hi2(D), pny, kc), kc), mul2(lo2(E), pnz, kc), kc);
+            z.x = FYX_ADD(z.x, E.z);
+            acc_z = add2(acc_z, mul2(z, ww, kc), kc);
+        }
+        ox[v] = acc_p.x; oy[v] = acc_p.y; oz[v] = acc_z.x;
+        mx[v] = acc_n.x; my[v] = acc_n.y; mz[v] = acc_z.y;
+    }
+    st_stream(po + 0, make_float4(ox[0], oy[0], oz[0], ox[1]));
+    st_stream(po + 1, make_float4(oy[1], oz[1], ox[2], oy[2]));
+    st_stream(po + 2, make_float4(oz[2], ox[3], oy[3], oz[3]));
+    st_stream(no + 0, make_float4(mx[0], my[0], mz[0], mx[1]));
+    st_stream(no + 1, make_float4(my[1], mz[1], mx[2], my[2]));
+    st_stream(no + 2, make_float4(mz[2], mx[3], my[3], mz[3]));
+}
+
+// Variant "direct": one CTA per tile, inputs loaded straight into registers (LDG.128, L1-bypassing).
+template <int S, int LOG2C>
+__global__ void __launch_bounds__(kBlock, 3) k_skin(const SkinArrays sk, const SkinTile *__restrict__ tiles, const uint32_t n_tiles,
+                                                     const float one, const float negzero)
+{
+    extern __shared__ float4 smem[];
+    float4 *const s_pal = smem;
+    PackedConsts kc;
+    kc.one = make_float2(one, one);
+    kc.negzero = make_float2(negzero, negzero);
+    const SkinTile T = tiles[blockIdx.x];
+    skin_fill_palette<S, LOG2C>(s_pal, sk.palette, T.bone_off, T.n_bones);
+    __syncthreads();
+    const uint32_t lane = threadIdx.x & 31u;
+    for (uint32_t q = threadIdx.x; q < T.n_quads; q += kBlock) {
+        const size_t quad = (size_t)T.quad_start + q;
         const float4 *pp = reinterpret_cast<const float4 *>(sk.vpos) + 3 * quad;
         const float4 *np = reinterpret_cast<const float4 *>(sk.vnrm) + 3 * quad;
         const float4 p0 = ld_stream(pp), p1 = ld_stream(pp + 1), p2 = ld_stream(pp + 2);
@@ -330,49 +420,78 @@ __global__ void __launch_bounds__(kBlock) k_skin(const SkinArrays sk, const Skin
         const float4 w0 = ld_stream(sk.vw + 4 * quad), w1 = ld_stream(sk.vw + 4 * quad + 1);
         const float4 w2 = ld_stream(sk.vw + 4 * quad + 2), w3 = ld_stream(sk.vw + 4 * quad + 3);
         const uint4 iq = ld_stream(reinterpret_cast<const uint4 *>(sk.vidx) + quad);
-
-        const float px[4] = {p0.x, p0.w, p1.z, p2.y}, py[4] = {p0.y, p1.x, p1.w, p2.z}, pz[4] = {p0.z, p1.y, p2.x, p2.w};
-        const float nx[4] = {n0.x, n0.w, n1.z, n2.y}, ny[4] = {n0.y, n1.x, n1.w, n2.z}, nz[4] = {n0.z, n1.y, n2.x, n2.w};
-        const float4 wv[4] = {w0, w1, w2, w3};
-        const uint32_t iv[4] = {iq.x, iq.y, iq.z, iq.w};
-        float ox[4], oy[4], oz[4], mx[4], my[4], mz[4];
-#pragma unroll
-        for (int v = 0; v < 4; ++v) {
-            float ax = 0.0f, ay = 0.0f, az = 0.0f, bx = 0.0f, by = 0.0f, bz = 0.0f;
-            const float wk[4] = {wv[v].x, wv[v].y, wv[v].z, wv[v].w};
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const uint32_t bone3 = 3u * ((iv[v] >> (8 * k)) & 0xFFu);
-                const uint32_t a0 = bone3 + ((lane - bone3) & copy_mask) * copy_stride;
-                const uint32_t a1 = bone3 + 1u + ((lane - bone3 - 1u) & copy_mask) * copy_stride;
-                const uint32_t a2 = bone3 + 2u + ((lane - bone3 - 2u) & copy_mask) * copy_stride;
-                const float4 r0 = s_pal[a0], r1 = s_pal[a1], r2 = s_pal[a2];
-                const float w = wk[k];
-                const float tx = FYX_ADD(FYX_ADD(FYX_ADD(FYX_MUL(r0.x, px[v]), FYX_MUL(r0.y, py[v])), FYX_MUL(r0.z, pz[v])), r0.w);
-                const float ty = FYX_ADD(FYX_ADD(FYX_ADD(FYX_MUL(r1.x, px[v]), FYX_MUL(r1.y, py[v])), FYX_MUL(r1.z, pz[v])), r1.w);
-                const float tz = FYX_ADD(FYX_ADD(FYX_ADD(FYX_MUL(r2.x, px[v]), FYX_MUL(r2.y, py[v])), FYX_MUL(r2.z, pz[v])), r2.w);
-                ax = FYX_ADD(ax, FYX_MUL(tx, w));
-                ay = FYX_ADD(ay, FYX_MUL(ty, w));
-                az = FYX_ADD(az, FYX_MUL(tz, w));
-                const float rx = FYX_ADD(FYX_ADD(FYX_MUL(r0.x, nx[v]), FYX_MUL(r0.y, ny[v])), FYX_MUL(r0.z, nz[v]));
-                const float ry = FYX_ADD(FYX_ADD(FYX_MUL(r1.x, nx[v]), FYX_MUL(r1.y, ny[v])), FYX_MUL(r1.z, nz[v]));
-                const float rz = FYX_ADD(FYX_ADD(FYX_MUL(r2.x, nx[v]), FYX_MUL(r2.y, ny[v])), FYX_MUL(r2.z, nz[v]));
-                bx = FYX_ADD(bx, FYX_MUL(rx, w));
-                by = FYX_ADD(by, FYX_MUL(ry, w));
-                bz = FYX_ADD(bz, FYX_MUL(rz, w));
-            }
-            ox[v] = ax; oy[v] = ay; oz[v] = az;
-            mx[v] = bx; my[v] = by; mz[v] = bz;
-        }
-        float4 *po = reinterpret_cast<float4 *>(sk.opos) + 3 * quad;
-        float4 *no = reinterpret_cast<float4 *>(sk.onrm) + 3 * quad;
-        st_stream(po + 0, make_float4(ox[0], oy[0], oz[0], ox[1]));
-        st_stream(po + 1, make_float4(oy[1], oz[1], ox[2], oy[2]));
-        st_stream(po + 2, make_float4(oz[2], ox[3], oy[3], oz[3]));
-        st_stream(no + 0, make_float4(mx[0], my[0], mz[0], mx[1]));
-        st_stream(no + 1, make_float4(my[1], mz[1], mx[2], my[2]));
-        st_stream(no + 2, make_float4(mz[2], mx[3], my[3], mz[3]));
+        skin_quad<S, LOG2C>(s_pal, lane, p0, p1, p2, n0, n1, n2, w0, w1, w2, w3, iq, reinterpret_cast<float4 *>(sk.opos) + 3 * quad,
+                            reinterpret_cast<float4 *>(sk.onrm) + 3 * quad, kc);
     }
+}
+
+// Variant "async": persistent CTAs, each walking a contiguous run of tiles; the 11 input vectors of a
+// thread's NEXT group are fetched with cp.async (LDGSTS) into a per-thread shared-memory slot while the
+// current group is computed (prefetch runs across tile boundaries).
+template <int S, int LOG2C>
+__global__ void __launch_bounds__(kBlock, 3) k_skin_async(const SkinArrays sk, const SkinTile *__restrict__ tiles, const uint32_t n_tiles,
+                                                           const float one, const float negzero)
+{
+    PackedConsts kc;
+    kc.one = make_float2(one, one);
+    kc.negzero = make_float2(negzero, negzero);
+    constexpr int C = 1 << LOG2C;
+    constexpr int PL = S * C;
+    extern __shared__ float4 smem[];
+    float4 *const s_pal = smem;             // 4 * PL
+    float4 *const s_in = smem + 4 * PL;     // 11 * kBlock: slot j of thread t at j*kBlock + t
+    const uint32_t tid = threadIdx.x;
+    const uint32_t lane = tid & 31u;
+    const uint32_t t0 = (uint32_t)(((uint64_t)n_tiles * blockIdx.x) / gridDim.x);
+    const uint32_t t1 = (uint32_t)(((uint64_t)n_tiles * (blockIdx.x + 1)) / gridDim.x);
+    if (t0 >= t1) return;
+
+    auto prefetch = [&](const size_t quad) {
+        const float4 *pp = reinterpret_cast<const float4 *>(sk.vpos) + 3 * quad;
+        const float4 *np = reinterpret_cast<const float4 *>(sk.vnrm) + 3 * quad;
+        const float4 *wp = sk.vw + 4 * quad;
+        const uint4 *ip = reinterpret_cast<const uint4 *>(sk.vidx) + quad;
+        float4 *d = s_in + tid;
+        cp_async16(d + 0 * kBlock, pp + 0);
+        cp_async16(d + 1 * kBlock, pp + 1);
+        cp_async16(d + 2 * kBlock, pp + 2);
+        cp_async16(d + 3 * kBlock, np + 0);
+        cp_async16(d + 4 * kBlock, np + 1);
+        cp_async16(d + 5 * kBlock, np + 2);
+        cp_async16(d + 6 * kBlock, wp + 0);
+        cp_async16(d + 7 * kBlock, wp + 1);
+        cp_async16(d + 8 * kBlock, wp + 2);
+        cp_async16(d + 9 * kBlock, wp + 3);
+        cp_async16(d + 10 * kBlock, ip);
+        cp_async_commit();
+    };
+
+    SkinTile T = tiles[t0];
+    if (tid < T.n_quads) prefetch((size_t)T.quad_start + tid);
+    for (uint32_t tile = t0; tile < t1; ++tile) {
+        SkinTile Tn;
+        Tn.bone_off = 0; Tn.n_bones = 0; Tn.quad_start = 0; Tn.n_quads = 0;
+        if (tile + 1 < t1) Tn = tiles[tile + 1];
+        __syncthreads(); // every thread is done with the previous tile's palette
+        skin_fill_palette<S, LOG2C>(s_pal, sk.palette, T.bone_off, T.n_bones);
+        __syncthreads();
+        for (uint32_t q = tid; q < T.n_quads; q += kBlock) {
+            const size_t quad = (size_t)T.quad_start + q;
+            cp_async_wait_all();
+            const float4 *d = s_in + tid;
+            const float4 p0 = d[0 * kBlock], p1 = d[1 * kBlock], p2 = d[2 * kBlock];
+            const float4 n0 = d[3 * kBlock], n1 = d[4 * kBlock], n2 = d[5 * kBlock];
+            const float4 w0 = d[6 * kBlock], w1 = d[7 * kBlock], w2 = d[8 * kBlock], w3 = d[9 * kBlock];
+            const uint4 iq = *reinterpret_cast<const uint4 *>(d + 10 * kBlock);
+            if (q + kBlock < T.n_quads) prefetch(quad + kBlock);
+            else if (tid < Tn.n_quads) prefetch((size_t)Tn.quad_start + tid);
+            skin_quad<S, LOG2C>(s_pal, lane, p0, p1, p2, n0, n1, n2, w0, w1, w2, w3, iq, reinterpret_cast<float4 *>(sk.opos) + 3 * quad,
+                                reinterpret_cast<float4 *>(sk.onrm) + 3 * quad, kc);
+        }
+        if (tid >= T.n_quads && tid < Tn.n_quads) prefetch((size_t)Tn.quad_start + tid);
+        T = Tn;
+    }
+    cp_async_wait_all();
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -620,21 +739,50 @@ void launch_palette(cudaStream_t s, const NodeArrays &a, const SkinArrays &sk)
     k_palette<<<grid_for(sk.n_entries), kBlock, 0, s>>>(a, sk);
 }
 
+static int skin_variant()
+{
+    // FYX_SKIN_VARIANT=async selects the cp.async-prefetching persistent kernel (kept for experiments)
+    static int v = -1;
+    if (v < 0) {
+        const char *e = getenv("FYX_SKIN_VARIANT");
+        v = (e && e[0] == 'a') ? 1 : 0;
+    }
+    return v;
+}
+
+template <int S, int LOG2C> static void launch_skin_t(cudaStream_t s, const SkinArrays &sk, const SkinTile *tiles, uint32_t n_tiles)
+{
+    constexpr size_t smem_pal = (size_t)4 * S * (1 << LOG2C) * sizeof(float4);
+    if (skin_variant() == 0) {
+        static bool init = false;
+        if (!init) {
+            cudaFuncSetAttribute(k_skin<S, LOG2C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_pal);
+            init = true;
+        }
+        k_skin<S, LOG2C><<<n_tiles, kBlock, smem_pal, s>>>(sk, tiles, n_tiles, 1.0f, -0.0f);
+        return;
+    }
+    constexpr size_t smem = smem_pal + (size_t)11 * kBlock * sizeof(float4);
+    static int ctas_per_sm = 0, n_sm = 0;
+    if (!ctas_per_sm) {
+        cudaFuncSetAttribute(k_skin_async<S, LOG2C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, k_skin_async<S, LOG2C>, kBlock, smem);
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+        if (ctas_per_sm < 1) ctas_per_sm = 1;
+    }
+    uint32_t grid = (uint32_t)(ctas_per_sm * n_sm); // persistent: every SM filled exactly
+    if (grid > n_tiles) grid = n_tiles;
+    k_skin_async<S, LOG2C><<<grid, kBlock, smem, s>>>(sk, tiles, n_tiles, 1.0f, -0.0f);
+}
+
 void launch_skin(cudaStream_t s, const SkinArrays &sk, const SkinTile *tiles, uint32_t n_tiles, uint32_t max_bones)
 {
     if (!n_tiles) return;
-    if (max_bones < 1) max_bones = 1;
-    // copies of the palette: 8 (conflict-free) while 8 copies stay under ~64 KB, else 4, 2, 1
-    uint32_t stride = ((3u * max_bones + 7u) & ~7u) + 1u; // = 1 mod 8
-    uint32_t log2c = 3;
-    while (log2c > 0 && (size_t)(stride << log2c) * sizeof(float4) > 64u * 1024u) --log2c;
-    const size_t smem = (size_t)(stride << log2c) * sizeof(float4);
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaFuncSetAttribute(k_skin, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024 + 16);
-        attr_set = true;
-    }
-    k_skin<<<n_tiles, kBlock, smem, s>>>(sk, tiles, stride, log2c);
+    if (max_bones <= 64) launch_skin_t<65, 3>(s, sk, tiles, n_tiles);        // 8 copies: 33 KB of palette planes
+    else if (max_bones <= 128) launch_skin_t<129, 3>(s, sk, tiles, n_tiles); // 8 copies: 66 KB
+    else launch_skin_t<257, 2>(s, sk, tiles, n_tiles);                        // 4 copies (2-way worst case): 66 KB
 }
 
 void launch_scatter_locals(cudaStream_t s, const NodeArrays &a, uint32_t count, const uint32_t *d_idx, const float *d_m16,
