@@ -250,31 +250,37 @@ void rebuild_node_arrays(fyx_ctx *c)
 void to_dev_frustum(const fyx_frustum &f, uint32_t cam_mask, uint32_t pass_flags, FrustumDev &d)
 {
     for (int p = 0; p < 6; ++p) d.plane[p] = make_float4(f.planes[p][0], f.planes[p][1], f.planes[p][2], f.planes[p][3]);
-    bool finite = true;
+    for (int q = 0; q < 3; ++q)
+        for (int k = 0; k < 4; ++k) d.pn[q][k] = make_float2(f.planes[2 * q][k], f.planes[2 * q + 1][k]);
+    // distinct corner coordinates per axis (bit-pattern equality, so -0/+0 and NaNs stay separate entries:
+    // each entry is compared exactly like the corner it came from)
+    d.n_ax = 0;
     for (int k = 0; k < 3; ++k) {
-        d.cmin[k] = f.corners[0][k];
-        d.cmax[k] = f.corners[0][k];
-    }
-    for (int i = 0; i < 8; ++i) {
-        d.cx[i] = f.corners[i][0];
-        d.cy[i] = f.corners[i][1];
-        d.cz[i] = f.corners[i][2];
-        for (int k = 0; k < 3; ++k) {
+        int n = 0;
+        uint32_t masks[8] = {0};
+        d.ax_mask[k][0] = d.ax_mask[k][1] = 0;
+        for (int i = 0; i < 8; ++i) {
             const float v = f.corners[i][k];
-            if (!std::isfinite(v)) finite = false;
-            if (v < d.cmin[k]) d.cmin[k] = v;
-            if (v > d.cmax[k]) d.cmax[k] = v;
+            uint32_t vb, ub;
+            memcpy(&vb, &v, 4);
+            int j = 0;
+            for (; j < n; ++j) {
+                memcpy(&ub, &d.ax_val[k][j], 4);
+                if (ub == vb) break;
+            }
+            if (j == n) {
+                d.ax_val[k][n] = v;
+                ++n;
+            }
+            masks[j] |= 1u << i;
         }
+        for (int j = n; j < 8; ++j) d.ax_val[k][j] = 0.0f;
+        for (int j = 0; j < n; ++j) d.ax_mask[k][j >> 2] |= masks[j] << (8 * (j & 3));
+        d.n_ax |= (uint32_t)n << (8 * k);
     }
-    if (!finite) // disable the conservative early-out; the exact test decides
-        for (int k = 0; k < 3; ++k) {
-            d.cmin[k] = -INFINITY;
-            d.cmax[k] = INFINITY;
-        }
     d.cam_mask = cam_mask;
     d.pass_flags = pass_flags;
     d.psel = 0;
-    d.pad_ = 0;
     for (int p = 0; p < 6; ++p)
         for (int k = 0; k < 3; ++k)
             if (f.planes[p][k] < 0.0f) d.psel |= 1u << (3 * p + k);
@@ -286,6 +292,8 @@ int32_t prepare_cull(fyx_ctx *c, uint32_t nf, const fyx_frustum *fr, const uint3
     if (nf && !fr) return fail(c, FYX_ERR_INVALID_ARGUMENT, "frusta is NULL");
     c->cp.nf = (int)nf;
     c->cp.counts = c->d_counts;
+    c->cp.one = 1.0f;
+    c->cp.negzero = -0.0f;
     for (uint32_t f = 0; f < nf; ++f) {
         to_dev_frustum(fr[f], cam_mask ? cam_mask[f] : 0xFFFFFFFFu, pass_flags ? pass_flags[f] : 0u, c->cp.f[f]);
         // worst case every renderable node is visible

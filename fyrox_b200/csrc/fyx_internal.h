@@ -42,6 +42,7 @@ struct CullParams {
     FrustumDev f[FYX_MAX_FRUSTA];
     uint32_t *out[FYX_MAX_FRUSTA]; // visible lists
     uint32_t *counts;              // counts[f * kCountStride]
+    float one, negzero;            // 1.0f, -0.0f: run-time operands of the unfusable packed FMAs (fyx_math.cuh)
 };
 
 struct SkinArrays {

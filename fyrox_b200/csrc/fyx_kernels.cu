@@ -57,11 +57,14 @@ __device__ __forceinline__ uint32_t cull_bits(const uint32_t nf, const uint32_t 
     constexpr uint32_t need = FYX_NODE_ALIVE | FYX_NODE_RENDERABLE | FYX_NODE_REACHABLE | FYX_NODE_GLOBAL_VISIBILITY |
                               FYX_NODE_GLOBAL_ENABLED;
     if ((nf & need) != need) return 0u;
+    PackedConsts kc;
+    kc.one = make_float2(cp.one, cp.one);
+    kc.negzero = make_float2(cp.negzero, cp.negzero);
     uint32_t bits = 0u;
     for (int f = 0; f < cp.nf; ++f) {
         bool ok = (mask & cp.f[f].cam_mask) != 0u;
         ok &= !((cp.f[f].pass_flags & FYX_PASS_SHADOW) && !(nf & FYX_NODE_CAST_SHADOWS));
-        if (ok && (nf & FYX_NODE_FRUSTUM_CULLING)) ok = frustum_intersects_aabb(cp.f[f], wx, wy, wz);
+        if (ok && (nf & FYX_NODE_FRUSTUM_CULLING)) ok = frustum_intersects_aabb(cp.f[f], wx, wy, wz, kc);
         bits |= ok ? (1u << f) : 0u;
     }
     return bits;
@@ -295,9 +298,10 @@ __global__ void __launch_bounds__(kBlock) k_palette(const NodeArrays a, const Sk
 //   (ncu: 8.6 warp-instructions per vertex), and FMA contraction is forbidden, so halving the FP
 //   instruction count is the lever.  Pairs: (x,y) of the position, (x,y) of the normal, and
 //   (position.z, normal.z) — same op order per element as the scalar reference.
-// * The surface's palette sits in shared memory as four float4 planes laid out for those pairs:
-//     A = (m00,m10,m01,m11)  B = (m02,m12,m03,m13)  D = (m20,m20,m21,m21)  E = (m22,m22,m23,0)
-//   each plane REPLICATED C times: bone b of copy c at float4 index plane*PL + c*S + b with S = 1 mod 8,
+// * The surface's palette sits in shared memory as three float4 planes laid out for those pairs:
+//     A = (m00,m10,m01,m11)  B = (m02,m12,m03,m13)  Z = (m20,m21,m22,m23)
+//   (the z pair multiplies the register pair (p,n) by a scalar-broadcast operand of FFMA2, so the third
+//   row needs no duplication), each plane REPLICATED C times: bone b of copy c at float4 index plane*PL + c*S + b with S = 1 mod 8,
 //   PL = C*S.  A 128-bit shared load is served per quarter-warp; lane l reads copy (l - b) mod C,
 //   which puts it in bank group (plane*PL + l) mod 8: conflict-free for C = 8 whatever the bone
 //   indices are (with one copy, 57 % of the shared-memory wavefronts were conflict replays).
@@ -310,17 +314,6 @@ __device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src)
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
-
-// Packed f32x2 product / sum with ONE rounding each.  ptxas 12.9 contracts mul.rn.f32x2 + add.rn.f32x2 into
-// FFMA2 even with --fmad=false (the GPU parity tests catch the resulting 1-ulp differences), so both are
-// written as FMAs it cannot contract or simplify: a*b + (-0) is the correctly rounded product with the
-// right zero sign, a*1 + c the correctly rounded sum.  `one` / `negzero` arrive as kernel parameters so
-// that the assembler cannot fold them.
-struct PackedConsts {
-    float2 one, negzero;
-};
-__device__ __forceinline__ float2 mul2(const float2 a, const float2 b, const PackedConsts &k) { return __ffma2_rn(a, b, k.negzero); }
-__device__ __forceinline__ float2 add2(const float2 a, const float2 c, const PackedConsts &k) { return __ffma2_rn(a, k.one, c); }
 
 __device__ __forceinline__ float2 lo2(const float4 v) { return make_float2(v.x, v.y); }
 __device__ __forceinline__ float2 hi2(const float4 v) { return make_float2(v.z, v.w); }
@@ -336,14 +329,12 @@ __device__ __forceinline__ void skin_fill_palette(float4 *s_pal, const float *pa
         const float4 c0 = m[0], c1 = m[1], c2 = m[2], c3 = m[3];
         const float4 A = make_float4(c0.x, c0.y, c1.x, c1.y);
         const float4 B = make_float4(c2.x, c2.y, c3.x, c3.y);
-        const float4 D = make_float4(c0.z, c0.z, c1.z, c1.z);
-        const float4 E = make_float4(c2.z, c2.z, c3.z, 0.0f);
+        const float4 Z = make_float4(c0.z, c1.z, c2.z, c3.z);
 #pragma unroll
         for (int c = 0; c < C; ++c) {
             s_pal[0 * PL + c * S + b] = A;
             s_pal[1 * PL + c * S + b] = B;
-            s_pal[2 * PL + c * S + b] = D;
-            s_pal[3 * PL + c * S + b] = E;
+            s_pal[2 * PL + c * S + b] = Z;
         }
     }
 }
@@ -373,7 +364,7 @@ __device__ __forceinline__ void skin_quad(const float4 *s_pal, const uint32_t la
         for (int k = 0; k < 4; ++k) {
             const uint32_t bone = (iv[v] >> (8 * k)) & 0xFFu;
             const float4 *row = s_pal + (((lane - bone) & (uint32_t)(C - 1)) * S + bone);
-            const float4 A = row[0], B = row[PL], D = row[2 * PL], E = row[3 * PL];
+            const float4 A = row[0], B = row[PL], Z = row[2 * PL];
             const float2 ww = make_float2(wk[k], wk[k]);
             // (tx, ty) = ((m_i0*x + m_i1*y) + m_i2*z) + m_i3, i = 0,1
             const float2 t = add2(add2(add2(mul2(lo2(A), pxx, kc), mul2(hi2(A), pyy, kc), kc), mul2(lo2(B), pzz, kc), kc), hi2(B), kc);
@@ -382,8 +373,8 @@ __device__ __forceinline__ void skin_quad(const float4 *s_pal, const uint32_t la
             const float2 r = add2(add2(mul2(lo2(A), nxx, kc), mul2(hi2(A), nyy, kc), kc), mul2(lo2(B), nzz, kc), kc);
             acc_n = add2(acc_n, mul2(r, ww, kc), kc);
             // (tz', rz) = (m_20*{x,nx} + m_21*{y,ny}) + m_22*{z,nz};  tz = tz' + m_23
-            float2 z = add2(add2(mul2(lo2(D), pnx, kc), mul2(hi2(D), pny, kc), kc), mul2(lo2(E), pnz, kc), kc);
-            z.x = FYX_ADD(z.x, E.z);
+            float2 z = add2(add2(mul2(pnx, make_float2(Z.x, Z.x), kc), mul2(pny, make_float2(Z.y, Z.y), kc), kc), mul2(pnz, make_float2(Z.z, Z.z), kc), kc);
+            z.x = FYX_ADD(z.x, Z.w);
             acc_z = add2(acc_z, mul2(z, ww, kc), kc);
         }
         ox[v] = acc_p.x; oy[v] = acc_p.y; oz[v] = acc_z.x;
@@ -397,9 +388,9 @@ __device__ __forceinline__ void skin_quad(const float4 *s_pal, const uint32_t la
     st_stream(no + 2, make_float4(mz[2], mx[3], my[3], mz[3]));
 }
 
-// Variant "direct": one CTA per tile, inputs loaded straight into registers (LDG.128, L1-bypassing).
-template <int S, int LOG2C>
-__global__ void __launch_bounds__(kBlock, 3) k_skin(const SkinArrays sk, const SkinTile *__restrict__ tiles, const uint32_t n_tiles,
+// One CTA per tile, inputs loaded straight into registers (LDG.128, L1-bypassing).
+template <int S, int LOG2C, int MINB>
+__global__ void __launch_bounds__(kBlock, MINB) k_skin(const SkinArrays sk, const SkinTile *__restrict__ tiles, const uint32_t n_tiles,
                                                      const float one, const float negzero)
 {
     extern __shared__ float4 smem[];
@@ -423,75 +414,6 @@ __global__ void __launch_bounds__(kBlock, 3) k_skin(const SkinArrays sk, const S
         skin_quad<S, LOG2C>(s_pal, lane, p0, p1, p2, n0, n1, n2, w0, w1, w2, w3, iq, reinterpret_cast<float4 *>(sk.opos) + 3 * quad,
                             reinterpret_cast<float4 *>(sk.onrm) + 3 * quad, kc);
     }
-}
-
-// Variant "async": persistent CTAs, each walking a contiguous run of tiles; the 11 input vectors of a
-// thread's NEXT group are fetched with cp.async (LDGSTS) into a per-thread shared-memory slot while the
-// current group is computed (prefetch runs across tile boundaries).
-template <int S, int LOG2C>
-__global__ void __launch_bounds__(kBlock, 3) k_skin_async(const SkinArrays sk, const SkinTile *__restrict__ tiles, const uint32_t n_tiles,
-                                                           const float one, const float negzero)
-{
-    PackedConsts kc;
-    kc.one = make_float2(one, one);
-    kc.negzero = make_float2(negzero, negzero);
-    constexpr int C = 1 << LOG2C;
-    constexpr int PL = S * C;
-    extern __shared__ float4 smem[];
-    float4 *const s_pal = smem;             // 4 * PL
-    float4 *const s_in = smem + 4 * PL;     // 11 * kBlock: slot j of thread t at j*kBlock + t
-    const uint32_t tid = threadIdx.x;
-    const uint32_t lane = tid & 31u;
-    const uint32_t t0 = (uint32_t)(((uint64_t)n_tiles * blockIdx.x) / gridDim.x);
-    const uint32_t t1 = (uint32_t)(((uint64_t)n_tiles * (blockIdx.x + 1)) / gridDim.x);
-    if (t0 >= t1) return;
-
-    auto prefetch = [&](const size_t quad) {
-        const float4 *pp = reinterpret_cast<const float4 *>(sk.vpos) + 3 * quad;
-        const float4 *np = reinterpret_cast<const float4 *>(sk.vnrm) + 3 * quad;
-        const float4 *wp = sk.vw + 4 * quad;
-        const uint4 *ip = reinterpret_cast<const uint4 *>(sk.vidx) + quad;
-        float4 *d = s_in + tid;
-        cp_async16(d + 0 * kBlock, pp + 0);
-        cp_async16(d + 1 * kBlock, pp + 1);
-        cp_async16(d + 2 * kBlock, pp + 2);
-        cp_async16(d + 3 * kBlock, np + 0);
-        cp_async16(d + 4 * kBlock, np + 1);
-        cp_async16(d + 5 * kBlock, np + 2);
-        cp_async16(d + 6 * kBlock, wp + 0);
-        cp_async16(d + 7 * kBlock, wp + 1);
-        cp_async16(d + 8 * kBlock, wp + 2);
-        cp_async16(d + 9 * kBlock, wp + 3);
-        cp_async16(d + 10 * kBlock, ip);
-        cp_async_commit();
-    };
-
-    SkinTile T = tiles[t0];
-    if (tid < T.n_quads) prefetch((size_t)T.quad_start + tid);
-    for (uint32_t tile = t0; tile < t1; ++tile) {
-        SkinTile Tn;
-        Tn.bone_off = 0; Tn.n_bones = 0; Tn.quad_start = 0; Tn.n_quads = 0;
-        if (tile + 1 < t1) Tn = tiles[tile + 1];
-        __syncthreads(); // every thread is done with the previous tile's palette
-        skin_fill_palette<S, LOG2C>(s_pal, sk.palette, T.bone_off, T.n_bones);
-        __syncthreads();
-        for (uint32_t q = tid; q < T.n_quads; q += kBlock) {
-            const size_t quad = (size_t)T.quad_start + q;
-            cp_async_wait_all();
-            const float4 *d = s_in + tid;
-            const float4 p0 = d[0 * kBlock], p1 = d[1 * kBlock], p2 = d[2 * kBlock];
-            const float4 n0 = d[3 * kBlock], n1 = d[4 * kBlock], n2 = d[5 * kBlock];
-            const float4 w0 = d[6 * kBlock], w1 = d[7 * kBlock], w2 = d[8 * kBlock], w3 = d[9 * kBlock];
-            const uint4 iq = *reinterpret_cast<const uint4 *>(d + 10 * kBlock);
-            if (q + kBlock < T.n_quads) prefetch(quad + kBlock);
-            else if (tid < Tn.n_quads) prefetch((size_t)Tn.quad_start + tid);
-            skin_quad<S, LOG2C>(s_pal, lane, p0, p1, p2, n0, n1, n2, w0, w1, w2, w3, iq, reinterpret_cast<float4 *>(sk.opos) + 3 * quad,
-                                reinterpret_cast<float4 *>(sk.onrm) + 3 * quad, kc);
-        }
-        if (tid >= T.n_quads && tid < Tn.n_quads) prefetch((size_t)Tn.quad_start + tid);
-        T = Tn;
-    }
-    cp_async_wait_all();
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -739,50 +661,28 @@ void launch_palette(cudaStream_t s, const NodeArrays &a, const SkinArrays &sk)
     k_palette<<<grid_for(sk.n_entries), kBlock, 0, s>>>(a, sk);
 }
 
-static int skin_variant()
+template <int S, int LOG2C, int MINB> static void launch_skin_t(cudaStream_t s, const SkinArrays &sk, const SkinTile *tiles, uint32_t n_tiles)
 {
-    // FYX_SKIN_VARIANT=async selects the cp.async-prefetching persistent kernel (kept for experiments)
-    static int v = -1;
-    if (v < 0) {
-        const char *e = getenv("FYX_SKIN_VARIANT");
-        v = (e && e[0] == 'a') ? 1 : 0;
+    constexpr size_t smem_pal = (size_t)3 * S * (1 << LOG2C) * sizeof(float4);
+    static bool init = false;
+    if (!init) {
+        cudaFuncSetAttribute(k_skin<S, LOG2C, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_pal);
+        init = true;
     }
-    return v;
-}
-
-template <int S, int LOG2C> static void launch_skin_t(cudaStream_t s, const SkinArrays &sk, const SkinTile *tiles, uint32_t n_tiles)
-{
-    constexpr size_t smem_pal = (size_t)4 * S * (1 << LOG2C) * sizeof(float4);
-    if (skin_variant() == 0) {
-        static bool init = false;
-        if (!init) {
-            cudaFuncSetAttribute(k_skin<S, LOG2C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_pal);
-            init = true;
-        }
-        k_skin<S, LOG2C><<<n_tiles, kBlock, smem_pal, s>>>(sk, tiles, n_tiles, 1.0f, -0.0f);
-        return;
-    }
-    constexpr size_t smem = smem_pal + (size_t)11 * kBlock * sizeof(float4);
-    static int ctas_per_sm = 0, n_sm = 0;
-    if (!ctas_per_sm) {
-        cudaFuncSetAttribute(k_skin_async<S, LOG2C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, k_skin_async<S, LOG2C>, kBlock, smem);
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
-        if (ctas_per_sm < 1) ctas_per_sm = 1;
-    }
-    uint32_t grid = (uint32_t)(ctas_per_sm * n_sm); // persistent: every SM filled exactly
-    if (grid > n_tiles) grid = n_tiles;
-    k_skin_async<S, LOG2C><<<grid, kBlock, smem, s>>>(sk, tiles, n_tiles, 1.0f, -0.0f);
+    k_skin<S, LOG2C, MINB><<<n_tiles, kBlock, smem_pal, s>>>(sk, tiles, n_tiles, 1.0f, -0.0f);
 }
 
 void launch_skin(cudaStream_t s, const SkinArrays &sk, const SkinTile *tiles, uint32_t n_tiles, uint32_t max_bones)
 {
     if (!n_tiles) return;
-    if (max_bones <= 64) launch_skin_t<65, 3>(s, sk, tiles, n_tiles);        // 8 copies: 33 KB of palette planes
-    else if (max_bones <= 128) launch_skin_t<129, 3>(s, sk, tiles, n_tiles); // 8 copies: 66 KB
-    else launch_skin_t<257, 2>(s, sk, tiles, n_tiles);                        // 4 copies (2-way worst case): 66 KB
+    // 3 CTAs/SM (<= 85 registers): capping at 64 registers for 4 CTAs/SM spills and measured 28 % slower
+    if (max_bones <= 64) {       // 8 copies: 25 KB of palette planes
+        launch_skin_t<65, 3, 3>(s, sk, tiles, n_tiles);
+    } else if (max_bones <= 128) { // 8 copies: 50 KB
+        launch_skin_t<129, 3, 3>(s, sk, tiles, n_tiles);
+    } else {                       // 4 copies (2-way worst case): 49 KB
+        launch_skin_t<257, 2, 3>(s, sk, tiles, n_tiles);
+    }
 }
 
 void launch_scatter_locals(cudaStream_t s, const NodeArrays &a, uint32_t count, const uint32_t *d_idx, const float *d_m16,

@@ -77,17 +77,30 @@ __host__ __device__ __forceinline__ float2 aabb_transform_row(const float4 row, 
     return make_float2(mn, mx);
 }
 
-// Frustum in kernel-parameter space.  planes as in frustum.rs:26-30; corner_min/max = component-wise
-// bounds of the 8 corners (exact min/max, no rounding) used only as a conservative early-out for
-// the corner-in-AABB fallback.
+// Packed f32x2 product / sum with ONE rounding each (Blackwell FFMA2: two independently rounded f32
+// results per issue slot).  ptxas 12.9 contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2 even with
+// --fmad=false (the GPU parity tests catch the resulting 1-ulp differences), so both are written as FMAs
+// it can neither contract nor simplify: a*b + (-0) is the correctly rounded product with the right zero
+// sign, a*1 + c the correctly rounded sum.  `one` / `negzero` arrive as kernel parameters so that the
+// assembler cannot fold them.
+struct PackedConsts {
+    float2 one, negzero;
+};
+__device__ __forceinline__ float2 mul2(const float2 a, const float2 b, const PackedConsts &k) { return __ffma2_rn(a, b, k.negzero); }
+__device__ __forceinline__ float2 add2(const float2 a, const float2 c, const PackedConsts &k) { return __ffma2_rn(a, k.one, c); }
+
+// Frustum in kernel-parameter space.  planes as in frustum.rs:26-30; the 8 corners are kept as per-axis
+// lists of distinct coordinates with the mask of corners sharing each (see the fallback below).
 struct FrustumDev {
     float4 plane[6];
-    float cx[8], cy[8], cz[8];
-    float cmin[3], cmax[3];
+    float2 pn[3][4]; // planes (2q, 2q+1) as pairs: [q][0..2] = normal x,y,z pairs, [q][3] = d pair
     uint32_t cam_mask;
     uint32_t pass_flags;
     uint32_t psel;   // bit (3*p + axis): the plane-p normal component on that axis is negative
-    uint32_t pad_;
+    uint32_t n_ax;   // n_ax >> (8*axis) & 0xFF: number of distinct corner coordinates on that axis
+    // distinct corner coordinates per axis and, for each, the mask of the corners that have it
+    float ax_val[3][8];
+    uint32_t ax_mask[3][2]; // 8 x 8-bit corner masks per axis, packed little-endian
 };
 
 // Frustum::is_intersects_aabb (fyrox-math/src/frustum.rs:222-245) on (min,max) pairs per axis.
@@ -100,7 +113,7 @@ struct FrustumDev {
 // non-finite or huge (>1e18) bound or an inverted axis take the literal 8-corner loop instead (never in
 // practice; the branch is uniform).
 __device__ __forceinline__ bool frustum_intersects_aabb(const FrustumDev &f, const float2 x, const float2 y,
-                                                        const float2 z)
+                                                        const float2 z, const PackedConsts &kc)
 {
     bool cloud = true;
     const float kBig = 1e18f;
@@ -110,15 +123,16 @@ __device__ __forceinline__ bool frustum_intersects_aabb(const FrustumDev &f, con
         // n*p is monotone in p (rounding is monotone), so max(fl(n*min), fl(n*max)) is fl(n*max) for n >= 0
         // and fl(n*min) for n < 0: pick the operand first (psel, built on the host) and multiply once.
         // For n == ±0 both products are zeros; either choice gives the same booleans.
+        // Two planes per packed instruction: s = ((nx*vx + ny*vy) + nz*vz) + d element-wise.
         const uint32_t sel = f.psel;
 #pragma unroll
-        for (int p = 0; p < 6; ++p) {
-            const float4 pl = f.plane[p];
-            const float vx = (sel >> (3 * p + 0)) & 1u ? x.x : x.y;
-            const float vy = (sel >> (3 * p + 1)) & 1u ? y.x : y.y;
-            const float vz = (sel >> (3 * p + 2)) & 1u ? z.x : z.y;
-            const float s = FYX_ADD(FYX_ADD(FYX_ADD(FYX_MUL(pl.x, vx), FYX_MUL(pl.y, vy)), FYX_MUL(pl.z, vz)), pl.w);
-            cloud &= !(s <= 0.0f);
+        for (int q = 0; q < 3; ++q) {
+            const int b0 = 6 * q, b1 = 6 * q + 3;
+            const float2 vx = make_float2((sel >> (b0 + 0)) & 1u ? x.x : x.y, (sel >> (b1 + 0)) & 1u ? x.x : x.y);
+            const float2 vy = make_float2((sel >> (b0 + 1)) & 1u ? y.x : y.y, (sel >> (b1 + 1)) & 1u ? y.x : y.y);
+            const float2 vz = make_float2((sel >> (b0 + 2)) & 1u ? z.x : z.y, (sel >> (b1 + 2)) & 1u ? z.x : z.y);
+            const float2 s = add2(add2(add2(mul2(f.pn[q][0], vx, kc), mul2(f.pn[q][1], vy, kc), kc), mul2(f.pn[q][2], vz, kc), kc), f.pn[q][3], kc);
+            cloud &= !(s.x <= 0.0f) & !(s.y <= 0.0f);
         }
     } else {
         // literal restatement of the 8-corner loop (NaN-correct)
@@ -135,17 +149,26 @@ __device__ __forceinline__ bool frustum_intersects_aabb(const FrustumDev &f, con
         }
     }
     if (cloud) return true;
-    // Fallback: any frustum corner inside the AABB, inclusive compares (aabb.rs:193-200).
-    // Early-out: if the AABB misses the corners' bounding box on any axis no corner can be inside.
-    if (x.y < f.cmin[0] || x.x > f.cmax[0] || y.y < f.cmin[1] || y.x > f.cmax[1] || z.y < f.cmin[2] || z.x > f.cmax[2])
-        return false;
-    bool inside = false;
+    // Fallback: any frustum corner inside the AABB, inclusive compares (aabb.rs:193-200):
+    //   exists c: min <= corner_c <= max on all three axes.
+    // Evaluated as three 8-bit corner masks (one per axis, built from the DISTINCT corner coordinates of
+    // that axis — a frustum has few) ANDed together, leaving after the first axis that no corner
+    // satisfies: the same booleans as the reference's loop, ~10 instructions for the typical rejected box.
+    uint32_t alive = 0xFFu;
+    const float2 box[3] = {x, y, z};
 #pragma unroll
-    for (int c = 0; c < 8; ++c) {
-        inside |= (f.cx[c] >= x.x) & (f.cx[c] <= x.y) & (f.cy[c] >= y.x) & (f.cy[c] <= y.y) & (f.cz[c] >= z.x) &
-                  (f.cz[c] <= z.y);
+    for (int a = 0; a < 3; ++a) {
+        const int n = (int)((f.n_ax >> (8 * a)) & 0xFFu);
+        uint32_t m = 0u;
+        for (int k = 0; k < n; ++k) {
+            const float v = f.ax_val[a][k];
+            const uint32_t cm = (f.ax_mask[a][k >> 2] >> (8 * (k & 3))) & 0xFFu;
+            m |= ((v >= box[a].x) & (v <= box[a].y)) ? cm : 0u;
+        }
+        alive &= m;
+        if (!alive) return false;
     }
-    return inside;
+    return true;
 }
 
 } // namespace fyx
