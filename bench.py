@@ -315,19 +315,36 @@ def run_cuda(args):
 
     vis_counts = [0] * len(frusta)
 
-    def step_e2e(i):
+    def submit_e2e(i, pipelined):
+        kw = dict(update_flags=fb.UPDATE_ALL, frusta=frusta, readback_visible=(world == 1), async_=pipelined)
         if anim:
             pi, pm = anim[i & 1]
-            ctx.render_prep(update_flags=fb.UPDATE_ALL, changed_m16=pm.ptr, changed_idx=pi.ptr, n_changed=n_bones, frusta=frusta, readback_visible=(world == 1))
-        else:
-            ctx.render_prep(update_flags=fb.UPDATE_ALL, frusta=frusta, readback_visible=(world == 1))
+            kw.update(changed_m16=pm.ptr, changed_idx=pi.ptr, n_changed=n_bones)
+        ctx.render_prep(**kw)
+
+    def collect_e2e():
+        for f in range(len(frusta)):
+            v = ctx.get_visible_gathered(f, copy=False) if world > 1 else ctx.get_visible(f, copy=False)
+            vis_counts[f] = v.size
+
+    def step_e2e(i):
+        """One frame through the C ABI with host buffers, synchronous: upload -> kernels -> read-back."""
+        submit_e2e(i, False)
         if world > 1:
             ctx.allgather_visible()
-            for f in range(len(frusta)):
-                vis_counts[f] = ctx.get_visible_gathered(f).size
-        else:
-            for f in range(len(frusta)):
-                vis_counts[f] = ctx.get_visible(f).size
+        collect_e2e()
+
+    def run_e2e_pipelined(steps):
+        """The same K frames, two in flight (FYX_FRAME_ASYNC + fyx_frame_wait): the upload of frame i+1 and
+        the read-back of frame i-1 overlap the kernels of frame i.  Every frame's inputs still travel
+        host->device and every frame's visible lists device->host inside the timed region."""
+        submit_e2e(0, True)
+        for i in range(1, steps):
+            submit_e2e(i, True)
+            ctx.frame_wait()
+            collect_e2e()
+        ctx.frame_wait()
+        collect_e2e()
 
     def timed(fn, steps, pass_index=False):
         barrier()
@@ -357,7 +374,14 @@ def run_cuda(args):
     launches0 = ctx.kernel_launch_count()
     total_ms = timed(step_device, args.steps)
     launches = ctx.kernel_launch_count() - launches0
-    e2e_ms = timed(step_e2e, args.steps, pass_index=True)
+    e2e_sync_ms = timed(step_e2e, args.steps, pass_index=True)
+    if world == 1:
+        for _ in range(2):
+            run_e2e_pipelined(3)
+        e2e_pipe_ms = timed(lambda: run_e2e_pipelined(args.steps), 1)
+    else:
+        e2e_pipe_ms = e2e_sync_ms
+    e2e_ms = min(e2e_sync_ms, e2e_pipe_ms)
     # per-stage device durations (CUDA events on the launching stream, inside fyx_render_prep), same K frames
     stage = {"update_ms": 0.0, "palette_ms": 0.0, "skin_ms": 0.0}
     for i in range(args.steps):
@@ -418,7 +442,9 @@ def run_cuda(args):
         "nodes_per_s": w["nodes"] * world / (ms_per_step * 1e-3), "verts_per_s": w["units"] * w["verts_per_unit"] * world / (ms_per_step * 1e-3),
         "clocks": clk,
         "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms_per_step, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "api": "fyx_render_prep (C ABI) with pinned host buffers: changed bone matrices up, visible lists down"},
+                "api": "fyx_render_prep (C ABI) with pinned host buffers: changed bone matrices up, visible lists down",
+                "mode": "pipelined (2 frames in flight, fyx_frame_wait)" if e2e_pipe_ms < e2e_sync_ms else "synchronous",
+                "ms_per_step_synchronous": e2e_sync_ms / args.steps, "ms_per_step_pipelined": e2e_pipe_ms / args.steps},
         "gpu_launches": int(launches),
         "roofline": roofline,
     }

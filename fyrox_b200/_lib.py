@@ -121,6 +121,7 @@ SYMBOLS = {
     "fyx_build_palettes": (C.c_int32, [ctx_p]),
     "fyx_skin": (C.c_int32, [ctx_p]),
     "fyx_render_prep": (C.c_int32, [ctx_p, C.POINTER(fyx_frame_desc)]),
+    "fyx_frame_wait": (C.c_int32, [ctx_p]),
     "fyx_get_global_matrices": (C.c_int32, [ctx_p, C.c_uint32, C.c_void_p, C.c_void_p]),
     "fyx_get_world_aabbs": (C.c_int32, [ctx_p, C.c_uint32, C.c_void_p, C.c_void_p]),
     "fyx_get_global_flags": (C.c_int32, [ctx_p, C.c_uint32, C.c_void_p, C.c_void_p]),

@@ -231,13 +231,16 @@ class Context:
         cm, pf = _u32(cam_mask), _u32(pass_flags)
         self._chk(self._lib.fyx_update_and_cull(self._h, update_flags, len(frusta), arr, _ptr(cm), _ptr(pf)))
 
-    def get_visible(self, frustum: int = 0) -> np.ndarray:
+    def get_visible(self, frustum: int = 0, copy: bool = True) -> np.ndarray:
+        """Visible node indices of one frustum.  copy=False returns a view of the library's pinned buffer
+        (valid until the next cull / frame on this context)."""
         p = L.u32p()
         n = C.c_uint32()
         self._chk(self._lib.fyx_get_visible(self._h, frustum, C.byref(p), C.byref(n)))
         if n.value == 0:
             return np.empty(0, dtype=np.uint32)
-        return np.ctypeslib.as_array(p, shape=(n.value,)).copy()
+        v = np.ctypeslib.as_array(p, shape=(n.value,))
+        return v.copy() if copy else v
 
     def get_visible_device(self, frustum: int = 0):
         d_idx, d_cnt = C.c_void_p(), C.c_void_p()
@@ -282,11 +285,15 @@ class Context:
         d.pass_flags = None if pf is None else pf.ctypes.data
         d.do_palettes = 1 if do_palettes else 0
         d.do_skin = 1 if do_skin else 0
-        d.readback_visible = 1 if (readback_visible and not async_) else 0
+        d.readback_visible = 1 if readback_visible else 0
         d.flags = L.FRAME_ASYNC if async_ else 0
         if async_:
             self._async_keep = keep  # inputs must outlive the enqueued frame
         self._chk(self._lib.fyx_render_prep(self._h, C.byref(d)))
+
+    def frame_wait(self):
+        """Collect the oldest pipelined (async + read-back) frame; its visible lists become readable."""
+        self._chk(self._lib.fyx_frame_wait(self._h))
 
     # -- read-back --
     def _gather(self, fn, idx, count, width, dtype):
@@ -348,13 +355,14 @@ class Context:
     def allgather_visible(self):
         self._chk(self._lib.fyx_allgather_visible(self._h))
 
-    def get_visible_gathered(self, frustum: int = 0) -> np.ndarray:
+    def get_visible_gathered(self, frustum: int = 0, copy: bool = True) -> np.ndarray:
         p = L.u32p()
         n = C.c_uint32()
         self._chk(self._lib.fyx_get_visible_gathered(self._h, frustum, C.byref(p), C.byref(n)))
         if n.value == 0:
             return np.empty(0, dtype=np.uint32)
-        return np.ctypeslib.as_array(p, shape=(n.value,)).copy()
+        v = np.ctypeslib.as_array(p, shape=(n.value,))
+        return v.copy() if copy else v
 
     def get_visible_gathered_device(self, frustum: int = 0):
         p = C.c_void_p()

@@ -38,6 +38,21 @@ struct Surface {
 
 enum { EV_START = 0, EV_UPLOAD, EV_UPDATE, EV_CULL, EV_PALETTE, EV_SKIN, EV_READBACK, EV_COUNT };
 
+// Output of one cull: per-frustum visible lists + counters, device and (pinned) host side.  Two slots
+// alternate so that the lists of frame i can travel to the host while frame i+1 is being culled.
+struct VisSlot {
+    DevBuf b_vis[FYX_MAX_FRUSTA];
+    uint32_t *d_counts = nullptr; // kCountStride * FYX_MAX_FRUSTA, each counter on its own 128 B line
+    uint32_t *h_counts = nullptr; // pinned, FYX_MAX_FRUSTA
+    uint32_t *h_vis[FYX_MAX_FRUSTA] = {};
+    size_t h_vis_cap[FYX_MAX_FRUSTA] = {};
+    uint32_t nf = 0;
+    bool counts_on_host = false, lists_on_host = false;
+    bool pending = false; // written by a pipelined (async + read-back) frame that fyx_frame_wait has not collected yet
+    uint64_t frame_no = 0;
+    cudaEvent_t ev_cull = nullptr, ev_counts = nullptr, ev_done = nullptr;
+};
+
 } // namespace
 
 struct fyx_ctx {
@@ -65,13 +80,18 @@ struct fyx_ctx {
 
     // cull outputs
     CullParams cp{};
-    uint32_t *d_counts = nullptr;
-    uint32_t *h_counts = nullptr; // pinned, FYX_MAX_FRUSTA
-    DevBuf b_vis[FYX_MAX_FRUSTA];
-    uint32_t *h_vis[FYX_MAX_FRUSTA] = {};
-    size_t h_vis_cap[FYX_MAX_FRUSTA] = {};
-    uint32_t last_nf = 0;
-    bool counts_on_host = false, lists_on_host = false;
+    VisSlot vs[2];
+    int cur = 0;      // slot written by the most recent cull
+    int readable = 0; // slot fyx_get_visible reads
+    uint64_t frame_counter = 0;
+
+    // frame pipelining (FYX_FRAME_ASYNC): uploads on their own stream into alternating staging buffers,
+    // read-backs on a third stream
+    cudaStream_t copy_stream = nullptr, d2h_stream = nullptr;
+    DevBuf d_stage_frame[2];
+    cudaEvent_t ev_upload[2] = {}, ev_slot_free[2] = {};
+    bool slot_used[2] = {false, false};
+    int upload_parity = 0;
 
     // skinning
     std::vector<Surface> surfaces;
@@ -290,20 +310,25 @@ int32_t prepare_cull(fyx_ctx *c, uint32_t nf, const fyx_frustum *fr, const uint3
 {
     if (nf > FYX_MAX_FRUSTA) return fail(c, FYX_ERR_INVALID_ARGUMENT, "n_frusta %u > FYX_MAX_FRUSTA", nf);
     if (nf && !fr) return fail(c, FYX_ERR_INVALID_ARGUMENT, "frusta is NULL");
+    const int slot = c->cur ^ 1;
+    VisSlot &V = c->vs[slot];
+    if (V.pending) return fail(c, FYX_ERR_STATE, "two pipelined frames are already in flight: call fyx_frame_wait first");
+    c->cur = slot;
     c->cp.nf = (int)nf;
-    c->cp.counts = c->d_counts;
+    c->cp.counts = V.d_counts;
     c->cp.one = 1.0f;
     c->cp.negzero = -0.0f;
     for (uint32_t f = 0; f < nf; ++f) {
         to_dev_frustum(fr[f], cam_mask ? cam_mask[f] : 0xFFFFFFFFu, pass_flags ? pass_flags[f] : 0u, c->cp.f[f]);
         // worst case every renderable node is visible
-        int32_t rc = dev_ensure(c, c->b_vis[f], sizeof(uint32_t) * std::max<size_t>(c->n_renderable, 1));
+        int32_t rc = dev_ensure(c, V.b_vis[f], sizeof(uint32_t) * std::max<size_t>(c->n_renderable, 1));
         if (rc) return rc;
-        c->cp.out[f] = c->b_vis[f].as<uint32_t>();
+        c->cp.out[f] = V.b_vis[f].as<uint32_t>();
     }
-    CU(cudaMemsetAsync(c->d_counts, 0, sizeof(uint32_t) * kCountStride * FYX_MAX_FRUSTA, c->stream));
-    c->last_nf = nf;
-    c->counts_on_host = c->lists_on_host = false;
+    CU(cudaMemsetAsync(V.d_counts, 0, sizeof(uint32_t) * kCountStride * FYX_MAX_FRUSTA, c->stream));
+    V.nf = nf;
+    V.counts_on_host = V.lists_on_host = false;
+    c->readable = slot;
     return FYX_OK;
 }
 
@@ -326,30 +351,37 @@ int32_t run_update(fyx_ctx *c, uint32_t update_flags, const CullParams *cull)
 
 int32_t commit_surfaces(fyx_ctx *c);
 
-int32_t readback_visible(fyx_ctx *c)
+int32_t host_list_ensure(fyx_ctx *c, VisSlot &V, uint32_t f, size_t n)
 {
-    const uint32_t nf = c->last_nf;
+    if (n <= V.h_vis_cap[f]) return FYX_OK;
+    if (V.h_vis[f]) cudaFreeHost(V.h_vis[f]);
+    V.h_vis[f] = nullptr;
+    const size_t cap = std::max<size_t>(1024, n + n / 2);
+    CU(cudaHostAlloc(reinterpret_cast<void **>(&V.h_vis[f]), cap * sizeof(uint32_t), cudaHostAllocDefault));
+    V.h_vis_cap[f] = cap;
+    return FYX_OK;
+}
+
+// counts, then the lists sized by them, to pinned host memory (stream `s`, two synchronisations)
+int32_t readback_visible(fyx_ctx *c, VisSlot &V, cudaStream_t s)
+{
+    const uint32_t nf = V.nf;
     if (!nf) return FYX_OK;
-    if (!c->counts_on_host) {
-        CU(cudaMemcpy2DAsync(c->h_counts, sizeof(uint32_t), c->d_counts, sizeof(uint32_t) * kCountStride, sizeof(uint32_t), nf,
-                             cudaMemcpyDeviceToHost, c->stream));
-        CU(cudaStreamSynchronize(c->stream));
-        c->counts_on_host = true;
+    if (!V.counts_on_host) {
+        CU(cudaMemcpy2DAsync(V.h_counts, sizeof(uint32_t), V.d_counts, sizeof(uint32_t) * kCountStride, sizeof(uint32_t), nf,
+                             cudaMemcpyDeviceToHost, s));
+        CU(cudaStreamSynchronize(s));
+        V.counts_on_host = true;
     }
-    if (!c->lists_on_host) {
+    if (!V.lists_on_host) {
         for (uint32_t f = 0; f < nf; ++f) {
-            const size_t n = c->h_counts[f];
-            if (n > c->h_vis_cap[f]) {
-                if (c->h_vis[f]) cudaFreeHost(c->h_vis[f]);
-                c->h_vis[f] = nullptr;
-                size_t cap = std::max<size_t>(1024, n + n / 2);
-                CU(cudaHostAlloc(reinterpret_cast<void **>(&c->h_vis[f]), cap * sizeof(uint32_t), cudaHostAllocDefault));
-                c->h_vis_cap[f] = cap;
-            }
-            if (n) CU(cudaMemcpyAsync(c->h_vis[f], c->b_vis[f].p, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+            const size_t n = V.h_counts[f];
+            int32_t rc = host_list_ensure(c, V, f, n);
+            if (rc) return rc;
+            if (n) CU(cudaMemcpyAsync(V.h_vis[f], V.b_vis[f].p, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
         }
-        CU(cudaStreamSynchronize(c->stream));
-        c->lists_on_host = true;
+        CU(cudaStreamSynchronize(s));
+        V.lists_on_host = true;
     }
     return FYX_OK;
 }
@@ -415,10 +447,21 @@ extern "C" int32_t fyx_create(const fyx_config *cfg, fyx_ctx **out_ctx)
     CUB(cudaMemset(c->d_err, 0, sizeof(uint32_t)));
     CUB(cudaHostAlloc(reinterpret_cast<void **>(&c->h_err), sizeof(uint32_t), cudaHostAllocDefault));
     *c->h_err = 0;
-    CUB(cudaMalloc(reinterpret_cast<void **>(&c->d_counts), sizeof(uint32_t) * kCountStride * FYX_MAX_FRUSTA));
-    CUB(cudaMemset(c->d_counts, 0, sizeof(uint32_t) * kCountStride * FYX_MAX_FRUSTA));
-    CUB(cudaHostAlloc(reinterpret_cast<void **>(&c->h_counts), sizeof(uint32_t) * FYX_MAX_FRUSTA, cudaHostAllocDefault));
-    memset(c->h_counts, 0, sizeof(uint32_t) * FYX_MAX_FRUSTA);
+    for (VisSlot &V : c->vs) {
+        CUB(cudaMalloc(reinterpret_cast<void **>(&V.d_counts), sizeof(uint32_t) * kCountStride * FYX_MAX_FRUSTA));
+        CUB(cudaMemset(V.d_counts, 0, sizeof(uint32_t) * kCountStride * FYX_MAX_FRUSTA));
+        CUB(cudaHostAlloc(reinterpret_cast<void **>(&V.h_counts), sizeof(uint32_t) * FYX_MAX_FRUSTA, cudaHostAllocDefault));
+        memset(V.h_counts, 0, sizeof(uint32_t) * FYX_MAX_FRUSTA);
+        CUB(cudaEventCreateWithFlags(&V.ev_cull, cudaEventDisableTiming));
+        CUB(cudaEventCreateWithFlags(&V.ev_counts, cudaEventDisableTiming));
+        CUB(cudaEventCreateWithFlags(&V.ev_done, cudaEventDisableTiming));
+    }
+    CUB(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    CUB(cudaStreamCreateWithFlags(&c->d2h_stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; ++i) {
+        CUB(cudaEventCreateWithFlags(&c->ev_upload[i], cudaEventDisableTiming));
+        CUB(cudaEventCreateWithFlags(&c->ev_slot_free[i], cudaEventDisableTiming));
+    }
     for (int i = 0; i < EV_COUNT; ++i) CUB(cudaEventCreate(&c->ev[i]));
 #undef CUB
     *out_ctx = c;
@@ -444,17 +487,33 @@ extern "C" void fyx_destroy(fyx_ctx *c)
         dev_free(c->b_wa[i]);
         dev_free(c->b_ib[i]);
     }
+    if (c->copy_stream) cudaStreamSynchronize(c->copy_stream);
+    if (c->d2h_stream) cudaStreamSynchronize(c->d2h_stream);
     for (uint32_t f = 0; f < FYX_MAX_FRUSTA; ++f) {
-        dev_free(c->b_vis[f]);
         dev_free(c->b_gath_pad[f]);
         dev_free(c->b_gath[f]);
-        if (c->h_vis[f]) cudaFreeHost(c->h_vis[f]);
         if (c->h_gath[f]) cudaFreeHost(c->h_gath[f]);
     }
+    for (VisSlot &V : c->vs) {
+        for (uint32_t f = 0; f < FYX_MAX_FRUSTA; ++f) {
+            dev_free(V.b_vis[f]);
+            if (V.h_vis[f]) cudaFreeHost(V.h_vis[f]);
+        }
+        if (V.d_counts) cudaFree(V.d_counts);
+        if (V.h_counts) cudaFreeHost(V.h_counts);
+        if (V.ev_cull) cudaEventDestroy(V.ev_cull);
+        if (V.ev_counts) cudaEventDestroy(V.ev_counts);
+        if (V.ev_done) cudaEventDestroy(V.ev_done);
+    }
+    for (int i = 0; i < 2; ++i) {
+        dev_free(c->d_stage_frame[i]);
+        if (c->ev_upload[i]) cudaEventDestroy(c->ev_upload[i]);
+        if (c->ev_slot_free[i]) cudaEventDestroy(c->ev_slot_free[i]);
+    }
+    if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+    if (c->d2h_stream) cudaStreamDestroy(c->d2h_stream);
     if (c->d_err) cudaFree(c->d_err);
     if (c->h_err) cudaFreeHost(c->h_err);
-    if (c->d_counts) cudaFree(c->d_counts);
-    if (c->h_counts) cudaFreeHost(c->h_counts);
     if (c->h_counts_all) cudaFreeHost(c->h_counts_all);
     if (c->h_stage) cudaFreeHost(c->h_stage);
     for (int i = 0; i < EV_COUNT; ++i)
@@ -1031,21 +1090,24 @@ extern "C" int32_t fyx_update_and_cull(fyx_ctx *c, uint32_t update_flags, uint32
 extern "C" int32_t fyx_get_visible(fyx_ctx *c, uint32_t f, const uint32_t **out_idx, uint32_t *out_count)
 {
     if (!c || !out_idx || !out_count) return FYX_ERR_INVALID_ARGUMENT;
-    if (f >= c->last_nf) return fail(c, FYX_ERR_INVALID_ARGUMENT, "frustum %u was not part of the last cull (%u frusta)", f, c->last_nf);
+    VisSlot &V = c->vs[c->readable];
+    if (V.pending) return fail(c, FYX_ERR_STATE, "the frame is still in flight: call fyx_frame_wait first");
+    if (f >= V.nf) return fail(c, FYX_ERR_INVALID_ARGUMENT, "frustum %u was not part of the last cull (%u frusta)", f, V.nf);
     CU(cudaSetDevice(c->device));
-    int32_t rc = readback_visible(c);
+    int32_t rc = readback_visible(c, V, c->stream);
     if (rc) return rc;
-    *out_idx = c->h_vis[f];
-    *out_count = c->h_counts[f];
+    *out_idx = V.h_vis[f];
+    *out_count = V.h_counts[f];
     return FYX_OK;
 }
 
 extern "C" int32_t fyx_get_visible_device(fyx_ctx *c, uint32_t f, const uint32_t **d_idx, const uint32_t **d_count)
 {
     if (!c || !d_idx || !d_count) return FYX_ERR_INVALID_ARGUMENT;
-    if (f >= c->last_nf) return fail(c, FYX_ERR_INVALID_ARGUMENT, "frustum %u was not part of the last cull (%u frusta)", f, c->last_nf);
-    *d_idx = c->b_vis[f].as<uint32_t>();
-    *d_count = c->d_counts + f * kCountStride;
+    VisSlot &V = c->vs[c->cur];
+    if (f >= V.nf) return fail(c, FYX_ERR_INVALID_ARGUMENT, "frustum %u was not part of the last cull (%u frusta)", f, V.nf);
+    *d_idx = V.b_vis[f].as<uint32_t>();
+    *d_count = V.d_counts + f * kCountStride;
     return FYX_OK;
 }
 
@@ -1102,23 +1164,42 @@ extern "C" int32_t fyx_render_prep(fyx_ctx *c, const fyx_frame_desc *fr)
 {
     if (!c || !fr) return FYX_ERR_INVALID_ARGUMENT;
     if (fr->struct_size < sizeof(fyx_frame_desc)) return fail(c, FYX_ERR_INVALID_ARGUMENT, "fyx_frame_desc.struct_size too small");
-    if ((fr->flags & FYX_FRAME_ASYNC) && fr->readback_visible)
-        return fail(c, FYX_ERR_INVALID_ARGUMENT, "FYX_FRAME_ASYNC cannot be combined with readback_visible");
     if (!c->have_topology) return fail(c, FYX_ERR_STATE, "fyx_set_topology has not been called");
     CU(cudaSetDevice(c->device));
     int32_t rc = commit_surfaces(c);
     if (rc) return rc;
     cudaStream_t s = c->stream;
     CU(cudaEventRecord(c->ev[EV_START], s));
-    // 1. changed local matrices (pinned caller memory is DMA'd in place: this call ends with a sync)
+    const bool async = (fr->flags & FYX_FRAME_ASYNC) != 0;
+    const bool pipelined = async && fr->readback_visible && fr->n_frusta; // read-back deferred to fyx_frame_wait
+    // 1. changed local matrices.  Pinned caller memory is DMA'd in place (the caller keeps it untouched until
+    //    the frame is synchronised / waited for).  Async frames upload on the copy stream into alternating
+    //    staging buffers, so the H2D of frame i+1 overlaps the kernels of frame i.
     if (fr->n_changed) {
         if (!fr->changed_m16) return fail(c, FYX_ERR_INVALID_ARGUMENT, "changed_m16 is NULL");
-        void *d_m = nullptr, *d_i = nullptr;
-        rc = stage_to_device(c, fr->changed_m16, (size_t)fr->n_changed * 64, fr->changed_idx,
-                             fr->changed_idx ? (size_t)fr->n_changed * 4 : 0, true, &d_m, &d_i);
-        if (rc) return rc;
-        launch_scatter_locals(s, c->a, fr->n_changed, static_cast<const uint32_t *>(d_i), static_cast<const float *>(d_m),
-                              c->b_slot_of_node.as<uint32_t>(), c->n_nodes, c->d_err);
+        const size_t mb = (size_t)fr->n_changed * 64, ib = fr->changed_idx ? (size_t)fr->n_changed * 4 : 0;
+        if (async && is_pinned(fr->changed_m16) && (!fr->changed_idx || is_pinned(fr->changed_idx))) {
+            const int u = (c->upload_parity ^= 1);
+            if (c->slot_used[u]) CU(cudaEventSynchronize(c->ev_slot_free[u])); // its previous scatter has consumed it
+            const size_t off = (mb + 255) & ~size_t(255);
+            rc = dev_ensure(c, c->d_stage_frame[u], off + ib + 256);
+            if (rc) return rc;
+            char *base = c->d_stage_frame[u].as<char>();
+            CU(cudaMemcpyAsync(base, fr->changed_m16, mb, cudaMemcpyHostToDevice, c->copy_stream));
+            if (ib) CU(cudaMemcpyAsync(base + off, fr->changed_idx, ib, cudaMemcpyHostToDevice, c->copy_stream));
+            CU(cudaEventRecord(c->ev_upload[u], c->copy_stream));
+            CU(cudaStreamWaitEvent(s, c->ev_upload[u], 0));
+            launch_scatter_locals(s, c->a, fr->n_changed, ib ? reinterpret_cast<const uint32_t *>(base + off) : nullptr,
+                                  reinterpret_cast<const float *>(base), c->b_slot_of_node.as<uint32_t>(), c->n_nodes, c->d_err);
+            CU(cudaEventRecord(c->ev_slot_free[u], s));
+            c->slot_used[u] = true;
+        } else {
+            void *d_m = nullptr, *d_i = nullptr;
+            rc = stage_to_device(c, fr->changed_m16, mb, fr->changed_idx, ib, true, &d_m, &d_i);
+            if (rc) return rc;
+            launch_scatter_locals(s, c->a, fr->n_changed, static_cast<const uint32_t *>(d_i), static_cast<const float *>(d_m),
+                                  c->b_slot_of_node.as<uint32_t>(), c->n_nodes, c->d_err);
+        }
         c->launches++;
     }
     CU(cudaEventRecord(c->ev[EV_UPLOAD], s));
@@ -1130,6 +1211,7 @@ extern "C" int32_t fyx_render_prep(fyx_ctx *c, const fyx_frame_desc *fr)
     rc = run_update(c, fr->update_flags, fr->n_frusta ? &c->cp : nullptr);
     if (rc) return rc;
     CU(cudaEventRecord(c->ev[EV_UPDATE], s));
+    if (fr->n_frusta) CU(cudaEventRecord(c->vs[c->cur].ev_cull, s));
     // 3. palettes, 4. skinning
     if (fr->do_palettes && c->sk.n_entries) {
         launch_palette(s, c->a, c->sk);
@@ -1143,18 +1225,56 @@ extern "C" int32_t fyx_render_prep(fyx_ctx *c, const fyx_frame_desc *fr)
     CU(cudaEventRecord(c->ev[EV_SKIN], s));
     CU(cudaGetLastError());
     // 5. visible lists to the host
-    if (fr->readback_visible && fr->n_frusta) {
-        rc = readback_visible(c);
+    VisSlot &V = c->vs[c->cur];
+    if (pipelined) {
+        // deferred: counts travel on the read-back stream as soon as the cull is done; fyx_frame_wait fetches the lists
+        CU(cudaEventRecord(V.ev_done, s));
+        CU(cudaStreamWaitEvent(c->d2h_stream, V.ev_cull, 0));
+        CU(cudaMemcpy2DAsync(V.h_counts, sizeof(uint32_t), V.d_counts, sizeof(uint32_t) * kCountStride, sizeof(uint32_t), V.nf,
+                             cudaMemcpyDeviceToHost, c->d2h_stream));
+        CU(cudaEventRecord(V.ev_counts, c->d2h_stream));
+        V.pending = true;
+        V.frame_no = ++c->frame_counter;
+    } else if (fr->readback_visible && fr->n_frusta) {
+        rc = readback_visible(c, V, s);
         if (rc) return rc;
     }
     CU(cudaEventRecord(c->ev[EV_READBACK], s));
-    if (fr->flags & FYX_FRAME_ASYNC) {
+    if (async) {
         c->timings_pending = true;
         return FYX_OK;
     }
     rc = sync_and_check(c);
     frame_timings_from_events(c);
     return rc;
+}
+
+// Collect the oldest pipelined frame: wait for its kernels, bring its visible lists to the host, make it
+// the frame fyx_get_visible reads.  No-op when nothing is in flight.
+extern "C" int32_t fyx_frame_wait(fyx_ctx *c)
+{
+    if (!c) return FYX_ERR_INVALID_ARGUMENT;
+    int slot = -1;
+    for (int i = 0; i < 2; ++i)
+        if (c->vs[i].pending && (slot < 0 || c->vs[i].frame_no < c->vs[slot].frame_no)) slot = i;
+    if (slot < 0) return FYX_OK;
+    CU(cudaSetDevice(c->device));
+    VisSlot &V = c->vs[slot];
+    CU(cudaEventSynchronize(V.ev_counts));
+    V.counts_on_host = true;
+    for (uint32_t f = 0; f < V.nf; ++f) {
+        const size_t n = V.h_counts[f];
+        int32_t rc = host_list_ensure(c, V, f, n);
+        if (rc) return rc;
+        if (n) CU(cudaMemcpyAsync(V.h_vis[f], V.b_vis[f].p, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->d2h_stream));
+    }
+    CU(cudaStreamWaitEvent(c->d2h_stream, V.ev_done, 0)); // the error word is final once the frame's last kernel ran
+    CU(cudaMemcpyAsync(c->h_err, c->d_err, sizeof(uint32_t), cudaMemcpyDeviceToHost, c->d2h_stream));
+    CU(cudaStreamSynchronize(c->d2h_stream));
+    V.lists_on_host = true;
+    V.pending = false;
+    c->readable = slot;
+    return check_device_errors(c);
 }
 
 // --------------------------------------------------------------------------------------------

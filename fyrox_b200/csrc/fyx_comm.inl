@@ -105,7 +105,8 @@ extern "C" int32_t fyx_allgather_visible(fyx_ctx *c)
 {
     if (!c) return FYX_ERR_INVALID_ARGUMENT;
     if (!c->comm) return fail(c, FYX_ERR_STATE, "fyx_comm_init has not been called");
-    const uint32_t nf = c->last_nf;
+    VisSlot &V = c->vs[c->cur];
+    const uint32_t nf = V.nf;
     if (!nf) return FYX_OK;
     CU(cudaSetDevice(c->device));
     ncclComm_t comm = static_cast<ncclComm_t>(c->comm);
@@ -113,14 +114,14 @@ extern "C" int32_t fyx_allgather_visible(fyx_ctx *c)
     const int R = c->nranks;
     // 1. counts
     CU(cudaMemsetAsync(c->b_counts_packed.p, 0, sizeof(uint32_t) * FYX_MAX_FRUSTA, s));
-    CU(cudaMemcpy2DAsync(c->b_counts_packed.p, sizeof(uint32_t), c->d_counts, sizeof(uint32_t) * kCountStride, sizeof(uint32_t), nf,
+    CU(cudaMemcpy2DAsync(c->b_counts_packed.p, sizeof(uint32_t), V.d_counts, sizeof(uint32_t) * kCountStride, sizeof(uint32_t), nf,
                          cudaMemcpyDeviceToDevice, s));
     NC(nccl().AllGather(c->b_counts_packed.p, c->b_counts_all.p, FYX_MAX_FRUSTA, ncclUint32, comm, s));
     CU(cudaMemcpyAsync(c->h_counts_all, c->b_counts_all.p, sizeof(uint32_t) * FYX_MAX_FRUSTA * R, cudaMemcpyDeviceToHost, s));
     CU(cudaStreamSynchronize(s));
     // own counts are now known on the host as well
-    for (uint32_t f = 0; f < nf; ++f) c->h_counts[f] = c->h_counts_all[c->rank * FYX_MAX_FRUSTA + f];
-    c->counts_on_host = true;
+    for (uint32_t f = 0; f < nf; ++f) V.h_counts[f] = c->h_counts_all[c->rank * FYX_MAX_FRUSTA + f];
+    V.counts_on_host = true;
     // 2. payload in max-count slots
     uint32_t maxc[FYX_MAX_FRUSTA] = {};
     int32_t rc;
@@ -136,12 +137,12 @@ extern "C" int32_t fyx_allgather_visible(fyx_ctx *c)
         if ((rc = dev_ensure(c, c->b_gath[f], sizeof(uint32_t) * std::max<size_t>(total, 1)))) return rc;
         // the send buffer must hold maxc entries: visible lists are sized for every renderable node of
         // THIS shard, which may be smaller than another rank's count
-        if ((rc = dev_ensure(c, c->b_vis[f], sizeof(uint32_t) * std::max<size_t>(maxc[f], 1), true))) return rc;
-        c->cp.out[f] = c->b_vis[f].as<uint32_t>();
+        if ((rc = dev_ensure(c, V.b_vis[f], sizeof(uint32_t) * std::max<size_t>(maxc[f], 1), true))) return rc;
+        c->cp.out[f] = V.b_vis[f].as<uint32_t>();
     }
     NC(nccl().GroupStart());
     for (uint32_t f = 0; f < nf; ++f)
-        if (maxc[f]) NC(nccl().AllGather(c->b_vis[f].p, c->b_gath_pad[f].p, maxc[f], ncclUint32, comm, s));
+        if (maxc[f]) NC(nccl().AllGather(V.b_vis[f].p, c->b_gath_pad[f].p, maxc[f], ncclUint32, comm, s));
     NC(nccl().GroupEnd());
     // 3. pack
     for (uint32_t f = 0; f < nf; ++f) {
@@ -156,7 +157,7 @@ extern "C" int32_t fyx_allgather_visible(fyx_ctx *c)
 extern "C" int32_t fyx_get_visible_gathered_device(fyx_ctx *c, uint32_t f, const uint32_t **d_idx, uint32_t *out_count)
 {
     if (!c || !d_idx || !out_count) return FYX_ERR_INVALID_ARGUMENT;
-    if (f >= c->last_nf) return fail(c, FYX_ERR_INVALID_ARGUMENT, "frustum %u was not part of the last cull", f);
+    if (f >= c->vs[c->cur].nf) return fail(c, FYX_ERR_INVALID_ARGUMENT, "frustum %u was not part of the last cull", f);
     *d_idx = c->b_gath[f].as<uint32_t>();
     *out_count = c->gath_count[f];
     return FYX_OK;
@@ -165,7 +166,7 @@ extern "C" int32_t fyx_get_visible_gathered_device(fyx_ctx *c, uint32_t f, const
 extern "C" int32_t fyx_get_visible_gathered(fyx_ctx *c, uint32_t f, const uint32_t **out_idx, uint32_t *out_count)
 {
     if (!c || !out_idx || !out_count) return FYX_ERR_INVALID_ARGUMENT;
-    if (f >= c->last_nf) return fail(c, FYX_ERR_INVALID_ARGUMENT, "frustum %u was not part of the last cull", f);
+    if (f >= c->vs[c->cur].nf) return fail(c, FYX_ERR_INVALID_ARGUMENT, "frustum %u was not part of the last cull", f);
     CU(cudaSetDevice(c->device));
     const size_t n = c->gath_count[f];
     if (n > c->h_gath_cap[f]) {

@@ -212,10 +212,13 @@ typedef struct fyx_frame_desc {
     uint32_t readback_visible;     /* copy counts + lists to the host before returning */
     uint32_t flags;                /* FYX_FRAME_* */
 } fyx_frame_desc;
-/* Do not synchronise with the host at the end of fyx_render_prep: the frame is only enqueued on the
- * context's stream (fyx_sync / any read-back waits for it).  Inputs must then stay untouched until that
- * wait; incompatible with readback_visible. */
+/* Do not synchronise with the host at the end of fyx_render_prep: the frame is only enqueued.  Inputs must
+ * stay untouched until the frame is waited for (fyx_frame_wait / fyx_sync).  Pinned inputs are uploaded on
+ * a copy stream into alternating staging buffers, so the upload of frame i+1 overlaps the kernels of
+ * frame i.  With readback_visible the read-back is deferred: at most two such frames may be in flight,
+ * fyx_frame_wait collects the oldest one and makes its visible lists the ones fyx_get_visible returns. */
 #define FYX_FRAME_ASYNC (1u << 0)
+int32_t fyx_frame_wait(fyx_ctx *ctx);
 int32_t fyx_render_prep(fyx_ctx *ctx, const fyx_frame_desc *frame);
 
 /* ---- read-back (tests, tools, and the parts of the engine that stay on the CPU) -------------- */

@@ -408,3 +408,56 @@ def test_render_prep_one_call_frame(ctx):
     assert_same_visible(og, ctx, fos)
     pin_m.free()
     pin_i.free()
+
+
+def test_pipelined_frames_match_oracle(ctx):
+    """FYX_FRAME_ASYNC + fyx_frame_wait: two frames in flight, uploads on the copy stream; every collected
+    frame equals the oracle's frame."""
+    sc = Scene(30000, n_units=30, verts_per_unit=64)
+    og, sids = scene_pair(sc, ctx)
+    fos, ffs = cube_frusta()
+    n_frames = 5
+    pins = []
+    for fr in range(n_frames):
+        idx, m = sc.animate(fr)
+        pm = fb.PinnedBuffer(m.shape, np.float32)
+        pi = fb.PinnedBuffer(idx.shape, np.uint32)
+        pm.array[:] = m
+        pi.array[:] = idx
+        pins.append((pi, pm, idx, m))
+
+    def oracle_frame(fr):
+        _, _, idx, m = pins[fr]
+        for i, mm in zip(idx, m):
+            og.set_local_matrix(int(i), mm)
+        og.update_hierarchical_data()
+        return [np.sort(og.from_graph(fo)) for fo in fos]
+
+    def submit(fr):
+        pi, pm, idx, _ = pins[fr]
+        ctx.render_prep(update_flags=fb.UPDATE_ALL, changed_m16=pm.ptr, changed_idx=pi.ptr, n_changed=idx.size, frusta=ffs,
+                        readback_visible=True, async_=True)
+
+    def check(fr):
+        want = oracle_frame(fr)
+        for f in range(len(ffs)):
+            assert np.array_equal(np.sort(ctx.get_visible(f)), want[f]), f"frame {fr} frustum {f}"
+
+    submit(0)
+    with pytest.raises(fb.FyxError):
+        ctx.get_visible(0)  # still in flight
+    for fr in range(1, n_frames):
+        submit(fr)
+        ctx.frame_wait()
+        check(fr - 1)
+    with pytest.raises(fb.FyxError):
+        submit(0)
+        submit(1)
+        submit(2)  # a third frame in flight is refused
+    ctx.frame_wait()
+    ctx.frame_wait()
+    ctx.frame_wait()  # no-op
+    ctx.sync()
+    for p in pins:
+        p[0].free()
+        p[1].free()
