@@ -309,14 +309,14 @@ def run_cuda(args):
             anim.append((pi, pm))
 
     def step_device():
-        ctx.render_prep(update_flags=fb.UPDATE_ALL, frusta=frusta, do_palettes=True, do_skin=True, readback_visible=False, async_=True)
-        if world > 1:
-            ctx.allgather_visible()
+        # N > 1: the all-gather of the visible lists is part of the frame (overlapped with the skinning kernel)
+        ctx.render_prep(update_flags=fb.UPDATE_ALL, frusta=frusta, do_palettes=True, do_skin=True, readback_visible=False, async_=True,
+                        allgather=(world > 1))
 
     vis_counts = [0] * len(frusta)
 
     def submit_e2e(i, pipelined):
-        kw = dict(update_flags=fb.UPDATE_ALL, frusta=frusta, readback_visible=(world == 1), async_=pipelined)
+        kw = dict(update_flags=fb.UPDATE_ALL, frusta=frusta, readback_visible=(world == 1), async_=pipelined, allgather=(world > 1))
         if anim:
             pi, pm = anim[i & 1]
             kw.update(changed_m16=pm.ptr, changed_idx=pi.ptr, n_changed=n_bones)
@@ -330,8 +330,6 @@ def run_cuda(args):
     def step_e2e(i):
         """One frame through the C ABI with host buffers, synchronous: upload -> kernels -> read-back."""
         submit_e2e(i, False)
-        if world > 1:
-            ctx.allgather_visible()
         collect_e2e()
 
     def run_e2e_pipelined(steps):

@@ -44,6 +44,7 @@ UPDATE_INCREMENTAL = 0
 UPDATE_ALL = 1
 PASS_SHADOW = 1
 FRAME_ASYNC = 1
+FRAME_ALLGATHER = 2
 
 u32p = C.POINTER(C.c_uint32)
 f32p = C.POINTER(C.c_float)

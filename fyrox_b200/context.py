@@ -254,7 +254,7 @@ class Context:
         self._chk(self._lib.fyx_skin(self._h))
 
     def render_prep(self, *, update_flags=L.UPDATE_INCREMENTAL, changed_m16=None, changed_idx=None, n_changed=None, frusta=(), cam_mask=None,
-                    pass_flags=None, do_palettes=True, do_skin=True, readback_visible=True, async_=False):
+                    pass_flags=None, do_palettes=True, do_skin=True, readback_visible=True, async_=False, allgather=False):
         """One frame (fyx_render_prep). changed_m16 / changed_idx may be numpy arrays or raw (pinned) addresses."""
         d = L.fyx_frame_desc()
         d.struct_size = C.sizeof(L.fyx_frame_desc)
@@ -286,7 +286,7 @@ class Context:
         d.do_palettes = 1 if do_palettes else 0
         d.do_skin = 1 if do_skin else 0
         d.readback_visible = 1 if readback_visible else 0
-        d.flags = L.FRAME_ASYNC if async_ else 0
+        d.flags = (L.FRAME_ASYNC if async_ else 0) | (L.FRAME_ALLGATHER if allgather else 0)
         if async_:
             self._async_keep = keep  # inputs must outlive the enqueued frame
         self._chk(self._lib.fyx_render_prep(self._h, C.byref(d)))

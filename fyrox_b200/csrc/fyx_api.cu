@@ -114,6 +114,8 @@ struct fyx_ctx {
     // multi-GPU (fyx_comm.cu)
     void *comm = nullptr;
     int nranks = 1, rank = 0;
+    cudaStream_t comm_stream = nullptr; // the collective runs beside the palette / skinning kernels
+    cudaEvent_t ev_gather = nullptr;
     DevBuf b_counts_packed, b_counts_all, b_gath_pad[FYX_MAX_FRUSTA], b_gath[FYX_MAX_FRUSTA];
     uint32_t *h_counts_all = nullptr; // pinned nranks*FYX_MAX_FRUSTA
     uint32_t gath_count[FYX_MAX_FRUSTA] = {};
@@ -469,6 +471,8 @@ extern "C" int32_t fyx_create(const fyx_config *cfg, fyx_ctx **out_ctx)
 }
 
 static void fyx_comm_destroy_internal(fyx_ctx *c); // fyx_comm.inl
+static int32_t allgather_begin(fyx_ctx *c, VisSlot &V, cudaStream_t s);
+static int32_t allgather_finish(fyx_ctx *c, VisSlot &V, cudaStream_t s);
 
 extern "C" void fyx_destroy(fyx_ctx *c)
 {
@@ -1212,6 +1216,15 @@ extern "C" int32_t fyx_render_prep(fyx_ctx *c, const fyx_frame_desc *fr)
     if (rc) return rc;
     CU(cudaEventRecord(c->ev[EV_UPDATE], s));
     if (fr->n_frusta) CU(cudaEventRecord(c->vs[c->cur].ev_cull, s));
+    // multi-GPU: the visible lists are complete here; their all-gather runs on the collective stream beside
+    // the palette / skinning kernels below (the path's one exchange step)
+    const bool gather = (fr->flags & FYX_FRAME_ALLGATHER) && fr->n_frusta;
+    if (gather) {
+        if (!c->comm) return fail(c, FYX_ERR_STATE, "FYX_FRAME_ALLGATHER without fyx_comm_init");
+        CU(cudaStreamWaitEvent(c->comm_stream, c->vs[c->cur].ev_cull, 0));
+        rc = allgather_begin(c, c->vs[c->cur], c->comm_stream);
+        if (rc) return rc;
+    }
     // 3. palettes, 4. skinning
     if (fr->do_palettes && c->sk.n_entries) {
         launch_palette(s, c->a, c->sk);
@@ -1224,6 +1237,13 @@ extern "C" int32_t fyx_render_prep(fyx_ctx *c, const fyx_frame_desc *fr)
     }
     CU(cudaEventRecord(c->ev[EV_SKIN], s));
     CU(cudaGetLastError());
+    if (gather) {
+        // the host waits only for the cull + the counts (the skinning kernel keeps running), then enqueues the payload
+        rc = allgather_finish(c, c->vs[c->cur], c->comm_stream);
+        if (rc) return rc;
+        CU(cudaEventRecord(c->ev_gather, c->comm_stream));
+        CU(cudaStreamWaitEvent(s, c->ev_gather, 0)); // the frame is complete when the gathered lists are
+    }
     // 5. visible lists to the host
     VisSlot &V = c->vs[c->cur];
     if (pipelined) {

@@ -64,6 +64,15 @@ NcclApi &nccl()
 
 static void fyx_comm_destroy_internal(fyx_ctx *c)
 {
+    if (c->comm_stream) {
+        cudaStreamSynchronize(c->comm_stream);
+        cudaStreamDestroy(c->comm_stream);
+        c->comm_stream = nullptr;
+    }
+    if (c->ev_gather) {
+        cudaEventDestroy(c->ev_gather);
+        c->ev_gather = nullptr;
+    }
     if (c->comm && nccl().ok) nccl().CommDestroy(static_cast<ncclComm_t>(c->comm));
     c->comm = nullptr;
 }
@@ -98,31 +107,32 @@ extern "C" int32_t fyx_comm_init(fyx_ctx *c, int32_t nranks, int32_t rank, const
     if ((rc = dev_ensure(c, c->b_counts_all, sizeof(uint32_t) * FYX_MAX_FRUSTA * nranks))) return rc;
     if (c->h_counts_all) cudaFreeHost(c->h_counts_all);
     CU(cudaHostAlloc(reinterpret_cast<void **>(&c->h_counts_all), sizeof(uint32_t) * FYX_MAX_FRUSTA * nranks, cudaHostAllocDefault));
+    if (!c->comm_stream) CU(cudaStreamCreateWithFlags(&c->comm_stream, cudaStreamNonBlocking));
+    if (!c->ev_gather) CU(cudaEventCreateWithFlags(&c->ev_gather, cudaEventDisableTiming));
     return FYX_OK;
 }
 
-extern "C" int32_t fyx_allgather_visible(fyx_ctx *c)
+// Step 1 of the exchange, enqueued on stream `s`: pack the counters, all-gather them, start their copy to the host.
+static int32_t allgather_begin(fyx_ctx *c, VisSlot &V, cudaStream_t s)
 {
-    if (!c) return FYX_ERR_INVALID_ARGUMENT;
-    if (!c->comm) return fail(c, FYX_ERR_STATE, "fyx_comm_init has not been called");
-    VisSlot &V = c->vs[c->cur];
-    const uint32_t nf = V.nf;
-    if (!nf) return FYX_OK;
-    CU(cudaSetDevice(c->device));
     ncclComm_t comm = static_cast<ncclComm_t>(c->comm);
-    cudaStream_t s = c->stream;
-    const int R = c->nranks;
-    // 1. counts
     CU(cudaMemsetAsync(c->b_counts_packed.p, 0, sizeof(uint32_t) * FYX_MAX_FRUSTA, s));
-    CU(cudaMemcpy2DAsync(c->b_counts_packed.p, sizeof(uint32_t), V.d_counts, sizeof(uint32_t) * kCountStride, sizeof(uint32_t), nf,
+    CU(cudaMemcpy2DAsync(c->b_counts_packed.p, sizeof(uint32_t), V.d_counts, sizeof(uint32_t) * kCountStride, sizeof(uint32_t), V.nf,
                          cudaMemcpyDeviceToDevice, s));
     NC(nccl().AllGather(c->b_counts_packed.p, c->b_counts_all.p, FYX_MAX_FRUSTA, ncclUint32, comm, s));
-    CU(cudaMemcpyAsync(c->h_counts_all, c->b_counts_all.p, sizeof(uint32_t) * FYX_MAX_FRUSTA * R, cudaMemcpyDeviceToHost, s));
+    CU(cudaMemcpyAsync(c->h_counts_all, c->b_counts_all.p, sizeof(uint32_t) * FYX_MAX_FRUSTA * c->nranks, cudaMemcpyDeviceToHost, s));
+    return FYX_OK;
+}
+
+// Steps 2+3: wait (host) for the counts, then enqueue the payload all-gathers in max-count slots and the pack kernels.
+static int32_t allgather_finish(fyx_ctx *c, VisSlot &V, cudaStream_t s)
+{
+    ncclComm_t comm = static_cast<ncclComm_t>(c->comm);
+    const uint32_t nf = V.nf;
+    const int R = c->nranks;
     CU(cudaStreamSynchronize(s));
-    // own counts are now known on the host as well
     for (uint32_t f = 0; f < nf; ++f) V.h_counts[f] = c->h_counts_all[c->rank * FYX_MAX_FRUSTA + f];
-    V.counts_on_host = true;
-    // 2. payload in max-count slots
+    V.counts_on_host = true; // own counts are now known on the host as well
     uint32_t maxc[FYX_MAX_FRUSTA] = {};
     int32_t rc;
     for (uint32_t f = 0; f < nf; ++f) {
@@ -135,16 +145,19 @@ extern "C" int32_t fyx_allgather_visible(fyx_ctx *c)
         c->gath_count[f] = (uint32_t)total;
         if ((rc = dev_ensure(c, c->b_gath_pad[f], sizeof(uint32_t) * std::max<size_t>((size_t)maxc[f] * R, 1)))) return rc;
         if ((rc = dev_ensure(c, c->b_gath[f], sizeof(uint32_t) * std::max<size_t>(total, 1)))) return rc;
-        // the send buffer must hold maxc entries: visible lists are sized for every renderable node of
-        // THIS shard, which may be smaller than another rank's count
-        if ((rc = dev_ensure(c, V.b_vis[f], sizeof(uint32_t) * std::max<size_t>(maxc[f], 1), true))) return rc;
-        c->cp.out[f] = V.b_vis[f].as<uint32_t>();
+        // the send buffer must hold maxc entries: visible lists are sized for every renderable node of THIS
+        // shard, which may be fewer than another rank's count (rare: grow it with everything quiesced)
+        if ((size_t)maxc[f] * sizeof(uint32_t) > V.b_vis[f].bytes) {
+            CU(cudaDeviceSynchronize());
+            if ((rc = dev_ensure(c, V.b_vis[f], sizeof(uint32_t) * (size_t)maxc[f], true))) return rc;
+            CU(cudaDeviceSynchronize());
+            c->cp.out[f] = V.b_vis[f].as<uint32_t>();
+        }
     }
     NC(nccl().GroupStart());
     for (uint32_t f = 0; f < nf; ++f)
         if (maxc[f]) NC(nccl().AllGather(V.b_vis[f].p, c->b_gath_pad[f].p, maxc[f], ncclUint32, comm, s));
     NC(nccl().GroupEnd());
-    // 3. pack
     for (uint32_t f = 0; f < nf; ++f) {
         launch_compact_gathered(s, c->b_gath_pad[f].as<uint32_t>(), maxc[f], c->b_counts_all.as<uint32_t>(), R, (int)f,
                                 c->b_gath[f].as<uint32_t>());
@@ -152,6 +165,18 @@ extern "C" int32_t fyx_allgather_visible(fyx_ctx *c)
     }
     CU(cudaGetLastError());
     return FYX_OK;
+}
+
+extern "C" int32_t fyx_allgather_visible(fyx_ctx *c)
+{
+    if (!c) return FYX_ERR_INVALID_ARGUMENT;
+    if (!c->comm) return fail(c, FYX_ERR_STATE, "fyx_comm_init has not been called");
+    VisSlot &V = c->vs[c->cur];
+    if (!V.nf) return FYX_OK;
+    CU(cudaSetDevice(c->device));
+    int32_t rc = allgather_begin(c, V, c->stream);
+    if (rc) return rc;
+    return allgather_finish(c, V, c->stream);
 }
 
 extern "C" int32_t fyx_get_visible_gathered_device(fyx_ctx *c, uint32_t f, const uint32_t **d_idx, uint32_t *out_count)

@@ -213,15 +213,28 @@ __global__ void __launch_bounds__(kBlock) k_cull(const NodeArrays a, const CullP
 // ------------------------------------------------------------------------------------------------
 // Skinned-mesh world AABB: the "special case for skinned meshes" of Mesh::on_global_transform_changed
 // (scene/mesh/mod.rs:673-684): world_aabb.add_point(bone.global_position()) for every bone of every
-// surface, strict </> updates in bone order (aabb.rs:86-106) — sequential per mesh so that even the
-// sign of a zero bound matches.  Runs after all levels (bones may be deeper than the mesh node);
+// surface, strict </> updates in bone order (aabb.rs:86-106).  Runs after all levels (bones may be deeper than the mesh node);
 // only meshes in a changed sub-tree are refreshed, as in the reference.  With FUSE the skinned
 // nodes are also culled here (they were skipped by the level kernels).
 // ------------------------------------------------------------------------------------------------
+// One WARP per skinned mesh: lanes take the bones round-robin, then the per-lane candidates are merged with
+// a shuffle reduction keyed (value, position in the bone list) so that among numerically equal bounds
+// (only -0 / +0 can differ in bits) the first one in the reference's order wins — the result is the
+// reference's sequential add_point loop, bit for bit.
+__device__ __forceinline__ void fold_min(float &v, uint32_t &k, const float ov, const uint32_t ok)
+{
+    if (ov < v || (ov == v && ok < k)) { v = ov; k = ok; }
+}
+__device__ __forceinline__ void fold_max(float &v, uint32_t &k, const float ov, const uint32_t ok)
+{
+    if (ov > v || (ov == v && ok < k)) { v = ov; k = ok; }
+}
+
 template <bool FUSE>
 __global__ void __launch_bounds__(kBlock) k_fold_bones(const NodeArrays a, const FoldArrays fa, const CullParams cp)
 {
-    const uint32_t i = blockIdx.x * kBlock + threadIdx.x;
+    const uint32_t i = (blockIdx.x * kBlock + threadIdx.x) >> 5; // mesh = warp
+    const uint32_t lane = threadIdx.x & 31u;
     uint32_t vis_bits = 0u, gi = 0u;
     if (i < fa.n) {
         const uint32_t slot = fa.node_slot[i];
@@ -229,22 +242,41 @@ __global__ void __launch_bounds__(kBlock) k_fold_bones(const NodeArrays a, const
         float2 wx = a.wa[0][slot], wy = a.wa[1][slot], wz = a.wa[2][slot];
         if (nf & F_DIRTY) {
             const uint32_t b0 = fa.bone_begin[i], b1 = fa.bone_begin[i + 1];
-            for (uint32_t b = b0; b < b1; ++b) {
+            // candidates start as the transformed box (order key 0 = "already there"); bones get keys 1..
+            float mnx = wx.x, mny = wy.x, mnz = wz.x, mxx = wx.y, mxy = wy.y, mxz = wz.y;
+            uint32_t kmnx = 0, kmny = 0, kmnz = 0, kmxx = 0, kmxy = 0, kmxz = 0;
+            for (uint32_t b = b0 + lane; b < b1; b += 32) {
                 const uint32_t bs = fa.bone_slot[b];
                 if (bs == FYX_NONE) continue; // try_borrow failed ⇒ skipped
                 const float px = a.G[0][bs].w, py = a.G[1][bs].w, pz = a.G[2][bs].w; // global_position()
-                if (px < wx.x) wx.x = px;
-                if (py < wy.x) wy.x = py;
-                if (pz < wz.x) wz.x = pz;
-                if (px > wx.y) wx.y = px;
-                if (py > wy.y) wy.y = py;
-                if (pz > wz.y) wz.y = pz;
+                const uint32_t key = b - b0 + 1u;
+                // within a lane keys increase, so the strict compares keep the earliest of equal values
+                if (px < mnx) { mnx = px; kmnx = key; }
+                if (py < mny) { mny = py; kmny = key; }
+                if (pz < mnz) { mnz = pz; kmnz = key; }
+                if (px > mxx) { mxx = px; kmxx = key; }
+                if (py > mxy) { mxy = py; kmxy = key; }
+                if (pz > mxz) { mxz = pz; kmxz = key; }
             }
-            a.wa[0][slot] = wx;
-            a.wa[1][slot] = wy;
-            a.wa[2][slot] = wz;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                fold_min(mnx, kmnx, __shfl_xor_sync(0xFFFFFFFFu, mnx, o), __shfl_xor_sync(0xFFFFFFFFu, kmnx, o));
+                fold_min(mny, kmny, __shfl_xor_sync(0xFFFFFFFFu, mny, o), __shfl_xor_sync(0xFFFFFFFFu, kmny, o));
+                fold_min(mnz, kmnz, __shfl_xor_sync(0xFFFFFFFFu, mnz, o), __shfl_xor_sync(0xFFFFFFFFu, kmnz, o));
+                fold_max(mxx, kmxx, __shfl_xor_sync(0xFFFFFFFFu, mxx, o), __shfl_xor_sync(0xFFFFFFFFu, kmxx, o));
+                fold_max(mxy, kmxy, __shfl_xor_sync(0xFFFFFFFFu, mxy, o), __shfl_xor_sync(0xFFFFFFFFu, kmxy, o));
+                fold_max(mxz, kmxz, __shfl_xor_sync(0xFFFFFFFFu, mxz, o), __shfl_xor_sync(0xFFFFFFFFu, kmxz, o));
+            }
+            wx = make_float2(mnx, mxx);
+            wy = make_float2(mny, mxy);
+            wz = make_float2(mnz, mxz);
+            if (lane == 0) {
+                a.wa[0][slot] = wx;
+                a.wa[1][slot] = wy;
+                a.wa[2][slot] = wz;
+            }
         }
-        if (FUSE) {
+        if (FUSE && lane == 0) {
             vis_bits = cull_bits(nf, a.mask[slot], wx, wy, wz, cp);
             if (vis_bits) gi = a.gidx[slot];
         }
@@ -646,12 +678,13 @@ void launch_cull(cudaStream_t s, const NodeArrays &a, const CullParams &cp)
 void launch_fold_bones(cudaStream_t s, const NodeArrays &a, const FoldArrays &fa, const CullParams *cull)
 {
     if (!fa.n) return;
+    const unsigned grid = grid_for((uint64_t)fa.n * 32); // one warp per skinned mesh
     if (cull) {
-        k_fold_bones<true><<<grid_for(fa.n), kBlock, 0, s>>>(a, fa, *cull);
+        k_fold_bones<true><<<grid, kBlock, 0, s>>>(a, fa, *cull);
     } else {
         CullParams none;
         none.nf = 0;
-        k_fold_bones<false><<<grid_for(fa.n), kBlock, 0, s>>>(a, fa, none);
+        k_fold_bones<false><<<grid, kBlock, 0, s>>>(a, fa, none);
     }
 }
 

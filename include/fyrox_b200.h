@@ -218,6 +218,10 @@ typedef struct fyx_frame_desc {
  * frame i.  With readback_visible the read-back is deferred: at most two such frames may be in flight,
  * fyx_frame_wait collects the oldest one and makes its visible lists the ones fyx_get_visible returns. */
 #define FYX_FRAME_ASYNC (1u << 0)
+/* Multi-GPU (after fyx_comm_init): all-gather the frame's visible lists as soon as the cull is done, on a
+ * separate stream, overlapped with the palette / skinning kernels of the same frame; the frame is complete
+ * when the gathered lists are (fyx_get_visible_gathered*). */
+#define FYX_FRAME_ALLGATHER (1u << 1)
 int32_t fyx_frame_wait(fyx_ctx *ctx);
 int32_t fyx_render_prep(fyx_ctx *ctx, const fyx_frame_desc *frame);
 
