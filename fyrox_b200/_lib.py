@@ -72,6 +72,15 @@ class fyx_timings(C.Structure):
     _fields_ = [(n, C.c_float) for n in ("upload_ms", "update_ms", "cull_ms", "palette_ms", "skin_ms", "readback_ms", "total_ms")]
 
 
+class fyx_trs(C.Structure):
+    _fields_ = [("position", C.c_float * 3), ("rotation", C.c_float * 4), ("scale", C.c_float * 3)]
+
+
+class fyx_transform_statics(C.Structure):
+    _fields_ = [("pre_rotation", C.c_float * 4), ("post_rotation_matrix", C.c_float * 9), ("rotation_offset", C.c_float * 3),
+                ("rotation_pivot", C.c_float * 3), ("scaling_offset", C.c_float * 3), ("scaling_pivot", C.c_float * 3)]
+
+
 class fyx_frame_desc(C.Structure):
     _fields_ = [
         ("struct_size", C.c_uint32),
@@ -79,6 +88,7 @@ class fyx_frame_desc(C.Structure):
         ("n_changed", C.c_uint32),
         ("changed_idx", C.c_void_p),
         ("changed_m16", C.c_void_p),
+        ("changed_trs", C.c_void_p),
         ("n_frusta", C.c_uint32),
         ("frusta", C.POINTER(fyx_frustum)),
         ("cam_mask", C.c_void_p),
@@ -105,6 +115,8 @@ SYMBOLS = {
     "fyx_mat4_mul": (None, [f32p, f32p, f32p]),
     "fyx_set_topology": (C.c_int32, [ctx_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "fyx_set_local_matrices": (C.c_int32, [ctx_p, C.c_uint32, C.c_void_p, C.c_void_p]),
+    "fyx_set_local_trs": (C.c_int32, [ctx_p, C.c_uint32, C.c_void_p, C.c_void_p]),
+    "fyx_set_transform_statics": (C.c_int32, [ctx_p, C.c_uint32, C.c_void_p, C.c_void_p]),
     "fyx_set_flags": (C.c_int32, [ctx_p, C.c_uint32, C.c_void_p, C.c_void_p]),
     "fyx_set_render_masks": (C.c_int32, [ctx_p, C.c_uint32, C.c_void_p, C.c_void_p]),
     "fyx_set_local_aabbs": (C.c_int32, [ctx_p, C.c_uint32, C.c_void_p, C.c_void_p]),
@@ -190,6 +202,7 @@ SG_SYMBOLS = {
     "sg_unit_vertices": (None, [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]),
     "sg_units_vertices": (None, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p]),
     "sg_animate": (C.c_uint32, [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]),
+    "sg_animate_trs": (C.c_uint32, [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]),
 }
 
 

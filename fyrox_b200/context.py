@@ -167,6 +167,23 @@ class Context:
         assert idx is None or idx.size == count
         self._chk(self._lib.fyx_set_local_matrices(self._h, count, _ptr(idx), _ptr(m16)))
 
+    def set_local_trs(self, trs, idx=None):
+        """trs: (count, 10) f32 rows of position xyz, rotation quaternion ijkw, scale xyz (fyx_trs)."""
+        trs = _f32(trs)
+        idx = _u32(idx)
+        count = trs.size // 10
+        assert idx is None or idx.size == count
+        self._chk(self._lib.fyx_set_local_trs(self._h, count, _ptr(idx), _ptr(trs)))
+
+    def set_transform_statics(self, statics, idx=None):
+        """statics: (count, 25) f32 rows: pre_rotation ijkw, post_rotation_matrix (9, column-major), rotation_offset,
+        rotation_pivot, scaling_offset, scaling_pivot (fyx_transform_statics)."""
+        statics = _f32(statics)
+        idx = _u32(idx)
+        count = statics.size // 25
+        assert idx is None or idx.size == count
+        self._chk(self._lib.fyx_set_transform_statics(self._h, count, _ptr(idx), _ptr(statics)))
+
     def set_flags(self, flags, idx=None):
         flags, idx = _u32(flags), _u32(idx)
         self._chk(self._lib.fyx_set_flags(self._h, flags.size, _ptr(idx), _ptr(flags)))
@@ -253,21 +270,22 @@ class Context:
     def skin(self):
         self._chk(self._lib.fyx_skin(self._h))
 
-    def render_prep(self, *, update_flags=L.UPDATE_INCREMENTAL, changed_m16=None, changed_idx=None, n_changed=None, frusta=(), cam_mask=None,
+    def render_prep(self, *, update_flags=L.UPDATE_INCREMENTAL, changed_m16=None, changed_trs=None, changed_idx=None, n_changed=None, frusta=(), cam_mask=None,
                     pass_flags=None, do_palettes=True, do_skin=True, readback_visible=True, async_=False, allgather=False):
         """One frame (fyx_render_prep). changed_m16 / changed_idx may be numpy arrays or raw (pinned) addresses."""
         d = L.fyx_frame_desc()
         d.struct_size = C.sizeof(L.fyx_frame_desc)
         d.update_flags = update_flags
         keep = []
-        if changed_m16 is not None:
-            if isinstance(changed_m16, np.ndarray):
-                m = _f32(changed_m16)
+        payload, width, field = (changed_trs, 10, "changed_trs") if changed_trs is not None else (changed_m16, 16, "changed_m16")
+        if payload is not None:
+            if isinstance(payload, np.ndarray):
+                m = _f32(payload)
                 keep.append(m)
-                d.changed_m16 = m.ctypes.data
-                d.n_changed = m.size // 16 if n_changed is None else n_changed
+                setattr(d, field, m.ctypes.data)
+                d.n_changed = m.size // width if n_changed is None else n_changed
             else:
-                d.changed_m16 = int(changed_m16)
+                setattr(d, field, int(payload))
                 d.n_changed = int(n_changed)
             if changed_idx is not None:
                 if isinstance(changed_idx, np.ndarray):

@@ -68,6 +68,8 @@ struct fyx_ctx {
     NodeArrays a{};
     DevBuf b_parent, b_flags, b_mask, b_gidx, b_L[3], b_G[3], b_la[3], b_wa[3], b_slot_of_node;
     bool have_topology = false, updated_once = false;
+    DevBuf b_statics; // fyx_transform_statics per slot, allocated by the first fyx_set_transform_statics
+    bool have_statics = false;
 
     // error word written by kernels
     uint32_t *d_err = nullptr;
@@ -480,7 +482,7 @@ extern "C" void fyx_destroy(fyx_ctx *c)
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     fyx_comm_destroy_internal(c);
-    DevBuf *bufs[] = {&c->b_parent, &c->b_flags, &c->b_mask, &c->b_gidx, &c->b_slot_of_node, &c->d_stage, &c->b_vpos, &c->b_vnrm,
+    DevBuf *bufs[] = {&c->b_parent, &c->b_flags, &c->b_mask, &c->b_gidx, &c->b_slot_of_node, &c->d_stage, &c->b_statics, &c->b_vpos, &c->b_vnrm,
                       &c->b_vw, &c->b_vidx, &c->b_opos, &c->b_onrm, &c->b_palette, &c->b_bone_slot, &c->b_tiles, &c->b_fold_node,
                       &c->b_fold_begin, &c->b_fold_bone, &c->b_counts_packed, &c->b_counts_all};
     for (DevBuf *b : bufs) dev_free(*b);
@@ -758,6 +760,7 @@ extern "C" int32_t fyx_set_topology(fyx_ctx *c, uint32_t capacity, uint32_t root
     c->level_off.swap(level_off);
     c->have_topology = true;
     c->updated_once = false;
+    c->have_statics = false; // slots moved: the caller re-sends non-default statics after a topology change
     c->tables_dirty = true; // bone slots depend on the slot order
     rebuild_node_arrays(c);
     return FYX_OK;
@@ -775,6 +778,48 @@ extern "C" int32_t fyx_set_local_matrices(fyx_ctx *c, uint32_t count, const uint
     if (rc) return rc;
     launch_scatter_locals(c->stream, c->a, count, static_cast<const uint32_t *>(d_i), static_cast<const float *>(d_m),
                           c->b_slot_of_node.as<uint32_t>(), c->n_nodes, c->d_err);
+    c->launches++;
+    CU(cudaGetLastError());
+    return FYX_OK;
+}
+
+extern "C" int32_t fyx_set_local_trs(fyx_ctx *c, uint32_t count, const uint32_t *idx, const fyx_trs *trs)
+{
+    if (!c) return FYX_ERR_INVALID_ARGUMENT;
+    if (!c->have_topology) return fail(c, FYX_ERR_STATE, "fyx_set_topology has not been called");
+    if (!count) return FYX_OK;
+    if (!trs) return fail(c, FYX_ERR_INVALID_ARGUMENT, "trs is NULL");
+    CU(cudaSetDevice(c->device));
+    void *d_t = nullptr, *d_i = nullptr;
+    int32_t rc = stage_to_device(c, trs, (size_t)count * sizeof(fyx_trs), idx, idx ? (size_t)count * 4 : 0, false, &d_t, &d_i);
+    if (rc) return rc;
+    launch_scatter_trs(c->stream, c->a, count, static_cast<const uint32_t *>(d_i), static_cast<const fyx_trs *>(d_t),
+                       c->have_statics ? c->b_statics.as<fyx_transform_statics>() : nullptr, c->b_slot_of_node.as<uint32_t>(), c->n_nodes,
+                       c->d_err);
+    c->launches++;
+    CU(cudaGetLastError());
+    return FYX_OK;
+}
+
+extern "C" int32_t fyx_set_transform_statics(fyx_ctx *c, uint32_t count, const uint32_t *idx, const fyx_transform_statics *statics)
+{
+    if (!c) return FYX_ERR_INVALID_ARGUMENT;
+    if (!c->have_topology) return fail(c, FYX_ERR_STATE, "fyx_set_topology has not been called");
+    if (!count) return FYX_OK;
+    if (!statics) return fail(c, FYX_ERR_INVALID_ARGUMENT, "statics is NULL");
+    CU(cudaSetDevice(c->device));
+    int32_t rc;
+    if (!c->have_statics) {
+        if ((rc = dev_ensure(c, c->b_statics, std::max<size_t>(c->n_slots, 1) * sizeof(fyx_transform_statics)))) return rc;
+        launch_fill_default_statics(c->stream, c->b_statics.as<fyx_transform_statics>(), c->n_slots);
+        c->launches++;
+        c->have_statics = true;
+    }
+    void *d_s = nullptr, *d_i = nullptr;
+    rc = stage_to_device(c, statics, (size_t)count * sizeof(fyx_transform_statics), idx, idx ? (size_t)count * 4 : 0, false, &d_s, &d_i);
+    if (rc) return rc;
+    launch_scatter_statics(c->stream, c->a, count, static_cast<const uint32_t *>(d_i), static_cast<const fyx_transform_statics *>(d_s),
+                           c->b_statics.as<fyx_transform_statics>(), c->b_slot_of_node.as<uint32_t>(), c->n_nodes);
     c->launches++;
     CU(cudaGetLastError());
     return FYX_OK;
@@ -1180,29 +1225,38 @@ extern "C" int32_t fyx_render_prep(fyx_ctx *c, const fyx_frame_desc *fr)
     //    the frame is synchronised / waited for).  Async frames upload on the copy stream into alternating
     //    staging buffers, so the H2D of frame i+1 overlaps the kernels of frame i.
     if (fr->n_changed) {
-        if (!fr->changed_m16) return fail(c, FYX_ERR_INVALID_ARGUMENT, "changed_m16 is NULL");
-        const size_t mb = (size_t)fr->n_changed * 64, ib = fr->changed_idx ? (size_t)fr->n_changed * 4 : 0;
-        if (async && is_pinned(fr->changed_m16) && (!fr->changed_idx || is_pinned(fr->changed_idx))) {
+        const bool as_trs = fr->changed_trs != nullptr;
+        const void *payload = as_trs ? static_cast<const void *>(fr->changed_trs) : static_cast<const void *>(fr->changed_m16);
+        if (!payload) return fail(c, FYX_ERR_INVALID_ARGUMENT, "changed_m16 / changed_trs is NULL");
+        const size_t mb = (size_t)fr->n_changed * (as_trs ? sizeof(fyx_trs) : 64), ib = fr->changed_idx ? (size_t)fr->n_changed * 4 : 0;
+        const fyx_transform_statics *st = c->have_statics ? c->b_statics.as<fyx_transform_statics>() : nullptr;
+        auto scatter = [&](const void *d_p, const uint32_t *d_i) {
+            if (as_trs)
+                launch_scatter_trs(s, c->a, fr->n_changed, d_i, static_cast<const fyx_trs *>(d_p), st, c->b_slot_of_node.as<uint32_t>(),
+                                   c->n_nodes, c->d_err);
+            else
+                launch_scatter_locals(s, c->a, fr->n_changed, d_i, static_cast<const float *>(d_p), c->b_slot_of_node.as<uint32_t>(),
+                                      c->n_nodes, c->d_err);
+        };
+        if (async && is_pinned(payload) && (!fr->changed_idx || is_pinned(fr->changed_idx))) {
             const int u = (c->upload_parity ^= 1);
             if (c->slot_used[u]) CU(cudaEventSynchronize(c->ev_slot_free[u])); // its previous scatter has consumed it
             const size_t off = (mb + 255) & ~size_t(255);
             rc = dev_ensure(c, c->d_stage_frame[u], off + ib + 256);
             if (rc) return rc;
             char *base = c->d_stage_frame[u].as<char>();
-            CU(cudaMemcpyAsync(base, fr->changed_m16, mb, cudaMemcpyHostToDevice, c->copy_stream));
+            CU(cudaMemcpyAsync(base, payload, mb, cudaMemcpyHostToDevice, c->copy_stream));
             if (ib) CU(cudaMemcpyAsync(base + off, fr->changed_idx, ib, cudaMemcpyHostToDevice, c->copy_stream));
             CU(cudaEventRecord(c->ev_upload[u], c->copy_stream));
             CU(cudaStreamWaitEvent(s, c->ev_upload[u], 0));
-            launch_scatter_locals(s, c->a, fr->n_changed, ib ? reinterpret_cast<const uint32_t *>(base + off) : nullptr,
-                                  reinterpret_cast<const float *>(base), c->b_slot_of_node.as<uint32_t>(), c->n_nodes, c->d_err);
+            scatter(base, ib ? reinterpret_cast<const uint32_t *>(base + off) : nullptr);
             CU(cudaEventRecord(c->ev_slot_free[u], s));
             c->slot_used[u] = true;
         } else {
             void *d_m = nullptr, *d_i = nullptr;
-            rc = stage_to_device(c, fr->changed_m16, mb, fr->changed_idx, ib, true, &d_m, &d_i);
+            rc = stage_to_device(c, payload, mb, fr->changed_idx, ib, true, &d_m, &d_i);
             if (rc) return rc;
-            launch_scatter_locals(s, c->a, fr->n_changed, static_cast<const uint32_t *>(d_i), static_cast<const float *>(d_m),
-                                  c->b_slot_of_node.as<uint32_t>(), c->n_nodes, c->d_err);
+            scatter(d_m, static_cast<const uint32_t *>(d_i));
         }
         c->launches++;
     }

@@ -357,34 +357,57 @@ extern "C" void sg_units_vertices(const sg_scene *s, uint32_t u0, uint32_t count
                          out_aabb6 ? out_aabb6 + 6 * (size_t)i : nullptr);
 }
 
+static void animate_one(const sg_scene *s, int64_t e, uint32_t frame, Trs &t)
+{
+    const uint32_t li = s->bone_nodes[e];
+    t = s->bone_rest[e];
+    // small-angle perturbation about a per-bone axis, phase from the global id
+    Pcg32 r(s->cfg.seed ^ 0x51DE5EEDull, s->gidx[li]);
+    float ax[3] = {r.gauss(), r.gauss(), r.gauss()};
+    float al = std::sqrt(ax[0] * ax[0] + ax[1] * ax[1] + ax[2] * ax[2]);
+    if (al < 1e-6f) { ax[0] = 1; ax[1] = 0; ax[2] = 0; al = 1; }
+    const float phase = 6.2831853f * r.uni();
+    const float ang = 0.15f * std::sin(0.37f * (float)(frame + 1) + phase);
+    const float sh = std::sin(0.5f * ang) / al, ch = std::cos(0.5f * ang);
+    const float d[4] = {ax[0] * sh, ax[1] * sh, ax[2] * sh, ch};
+    const float *q = t.q;
+    float qn[4] = {
+        q[3] * d[0] + q[0] * d[3] + q[1] * d[2] - q[2] * d[1],
+        q[3] * d[1] - q[0] * d[2] + q[1] * d[3] + q[2] * d[0],
+        q[3] * d[2] + q[0] * d[1] - q[1] * d[0] + q[2] * d[3],
+        q[3] * d[3] - q[0] * d[0] - q[1] * d[1] - q[2] * d[2],
+    };
+    quat_normalize(qn);
+    memcpy(t.q, qn, sizeof qn);
+}
+
 extern "C" uint32_t sg_animate(const sg_scene *s, uint32_t frame, uint32_t *out_idx, float *out_m16)
 {
     const uint32_t B = s->cfg.bones_per_unit;
     const int64_t n = (int64_t)s->unit_global.size() * B;
 #pragma omp parallel for schedule(static)
     for (int64_t e = 0; e < n; ++e) {
-        const uint32_t li = s->bone_nodes[e];
-        Trs t = s->bone_rest[e];
-        // small-angle perturbation about a per-bone axis, phase from the global id
-        Pcg32 r(s->cfg.seed ^ 0x51DE5EEDull, s->gidx[li]);
-        float ax[3] = {r.gauss(), r.gauss(), r.gauss()};
-        float al = std::sqrt(ax[0] * ax[0] + ax[1] * ax[1] + ax[2] * ax[2]);
-        if (al < 1e-6f) { ax[0] = 1; ax[1] = 0; ax[2] = 0; al = 1; }
-        const float phase = 6.2831853f * r.uni();
-        const float ang = 0.15f * std::sin(0.37f * (float)(frame + 1) + phase);
-        const float sh = std::sin(0.5f * ang) / al, ch = std::cos(0.5f * ang);
-        const float d[4] = {ax[0] * sh, ax[1] * sh, ax[2] * sh, ch};
-        const float *q = t.q;
-        float qn[4] = {
-            q[3] * d[0] + q[0] * d[3] + q[1] * d[2] - q[2] * d[1],
-            q[3] * d[1] - q[0] * d[2] + q[1] * d[3] + q[2] * d[0],
-            q[3] * d[2] + q[0] * d[1] - q[1] * d[0] + q[2] * d[3],
-            q[3] * d[3] - q[0] * d[0] - q[1] * d[1] - q[2] * d[2],
-        };
-        quat_normalize(qn);
-        memcpy(t.q, qn, sizeof qn);
-        if (out_idx) out_idx[e] = li;
+        Trs t;
+        animate_one(s, e, frame, t);
+        if (out_idx) out_idx[e] = s->bone_nodes[e];
         trs_to_m16(t, out_m16 + 16 * (size_t)e);
+    }
+    return (uint32_t)n;
+}
+
+extern "C" uint32_t sg_animate_trs(const sg_scene *s, uint32_t frame, uint32_t *out_idx, float *out)
+{
+    const uint32_t B = s->cfg.bones_per_unit;
+    const int64_t n = (int64_t)s->unit_global.size() * B;
+#pragma omp parallel for schedule(static)
+    for (int64_t e = 0; e < n; ++e) {
+        Trs t;
+        animate_one(s, e, frame, t);
+        if (out_idx) out_idx[e] = s->bone_nodes[e];
+        float *o = out + 10 * (size_t)e;
+        o[0] = t.t[0]; o[1] = t.t[1]; o[2] = t.t[2];
+        o[3] = t.q[0]; o[4] = t.q[1]; o[5] = t.q[2]; o[6] = t.q[3];
+        o[7] = t.s[0]; o[8] = t.s[1]; o[9] = t.s[2];
     }
     return (uint32_t)n;
 }

@@ -60,6 +60,9 @@ void            sg_units_vertices(const sg_scene *s, uint32_t u0, uint32_t count
 /* per-frame animation: every bone's local rotation is perturbed; writes n_units*bones_per_unit entries
  * (local node index + Transform::matrix()).  Returns the number of entries. */
 uint32_t        sg_animate(const sg_scene *s, uint32_t frame, uint32_t *out_idx, float *out_m16);
+/* the same poses as position / rotation (i,j,k,w) / scale records (10 f32 each, fyx_trs): what an animation
+ * system hands to Transform; the matrix is then Transform::calculate_local_transform's job */
+uint32_t        sg_animate_trs(const sg_scene *s, uint32_t frame, uint32_t *out_idx, float *out_trs10);
 
 #ifdef __cplusplus
 }

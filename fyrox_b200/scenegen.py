@@ -79,3 +79,14 @@ class Scene:
         m = np.empty((n, 16), dtype=np.float32)
         self._sg.sg_animate(self._h, frame, idx.ctypes.data_as(C.c_void_p), m.ctypes.data_as(C.c_void_p))
         return idx, m
+
+    def animate_trs_into(self, frame: int, idx_addr: int, trs_addr: int) -> int:
+        return self._sg.sg_animate_trs(self._h, frame, C.c_void_p(idx_addr) if idx_addr else None, C.c_void_p(trs_addr))
+
+    def animate_trs(self, frame: int):
+        """(node indices, (n,10) f32 rows: position xyz, rotation ijkw, scale xyz)."""
+        n = self.n_units * self.bones_per_unit
+        idx = np.empty(n, dtype=np.uint32)
+        t = np.empty((n, 10), dtype=np.float32)
+        self._sg.sg_animate_trs(self._h, frame, idx.ctypes.data_as(C.c_void_p), t.ctypes.data_as(C.c_void_p))
+        return idx, t

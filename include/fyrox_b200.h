@@ -145,6 +145,24 @@ int32_t fyx_set_topology(fyx_ctx *ctx, uint32_t capacity, uint32_t root, const u
 /* Transform::matrix() of `count` nodes (scene/transform.rs:544-550); idx NULL = nodes 0..count-1.
  * Equivalent of `local_transform_mut()` → NodeMessageKind::TransformChanged (scene/base.rs:343-352). */
 int32_t fyx_set_local_matrices(fyx_ctx *ctx, uint32_t count, const uint32_t *idx, const float *m16_colmajor);
+/* The same, but the library evaluates Transform::calculate_local_transform (scene/transform.rs:421-540) on the
+ * device from the Transform's fields instead of receiving the 64-byte matrix: 40 B per changed node go over
+ * PCIe instead of 64.  position / rotation (unit quaternion i,j,k,w) / scale are what animation writes every
+ * frame (AnimationPose::apply, scene/animation/mod.rs:147-179); the remaining fields of Transform rarely
+ * change and are set once with fyx_set_transform_statics (default: identity pre-rotation and post-rotation
+ * matrix, zero pivots/offsets — TransformBuilder's defaults, scene/transform.rs:176-200). */
+typedef struct fyx_trs {
+    float position[3];
+    float rotation[4];
+    float scale[3];
+} fyx_trs;
+typedef struct fyx_transform_statics {
+    float pre_rotation[4];            /* unit quaternion i,j,k,w */
+    float post_rotation_matrix[9];    /* column-major 3x3: Transform::post_rotation_matrix (inverse of the post rotation, :160-172) */
+    float rotation_offset[3], rotation_pivot[3], scaling_offset[3], scaling_pivot[3];
+} fyx_transform_statics;
+int32_t fyx_set_local_trs(fyx_ctx *ctx, uint32_t count, const uint32_t *idx, const fyx_trs *trs);
+int32_t fyx_set_transform_statics(fyx_ctx *ctx, uint32_t count, const uint32_t *idx, const fyx_transform_statics *statics);
 /* Base::set_visibility / set_enabled / frustum_culling / cast_shadows (VisibilityChanged / EnabledFlagChanged). */
 int32_t fyx_set_flags(fyx_ctx *ctx, uint32_t count, const uint32_t *idx, const uint32_t *flags);
 int32_t fyx_set_render_masks(fyx_ctx *ctx, uint32_t count, const uint32_t *idx, const uint32_t *render_mask);
@@ -202,7 +220,8 @@ typedef struct fyx_frame_desc {
     uint32_t update_flags;
     uint32_t n_changed;            /* changed local matrices this frame */
     const uint32_t *changed_idx;   /* NULL = nodes 0..n_changed-1 */
-    const float *changed_m16;
+    const float *changed_m16;      /* n_changed * 16 f32 ... */
+    const fyx_trs *changed_trs;    /* ... or, if non-NULL, n_changed fyx_trs records (changed_m16 ignored) */
     uint32_t n_frusta;
     const fyx_frustum *frusta;
     const uint32_t *cam_mask;

@@ -461,3 +461,87 @@ def test_pipelined_frames_match_oracle(ctx):
     for p in pins:
         p[0].free()
         p[1].free()
+
+
+def _oracle_transform(pos, rot, scale, statics=None):
+    tr = ob.Transform()
+    ob.lib().orc_transform_identity(tr)
+    tr.local_position[:] = pos.tolist()
+    tr.local_rotation[:] = rot.tolist()
+    tr.local_scale[:] = scale.tolist()
+    if statics is not None:
+        tr.pre_rotation[:] = statics[0:4].tolist()
+        tr.post_rotation_matrix[:] = statics[4:13].tolist()
+        tr.rotation_offset[:] = statics[13:16].tolist()
+        tr.rotation_pivot[:] = statics[16:19].tolist()
+        tr.scaling_offset[:] = statics[19:22].tolist()
+        tr.scaling_pivot[:] = statics[22:25].tolist()
+    m = np.empty(16, np.float32)
+    ob.lib().orc_transform_calculate_local(tr, ob.fp(m))
+    return m
+
+
+@pytest.mark.parametrize("with_statics", [False, True])
+def test_trs_upload_equals_calculate_local_transform(ctx, with_statics):
+    """N1: Transform::calculate_local_transform on the device (fyx_set_local_trs) is bit-identical to the
+    oracle's restatement of scene/transform.rs:421-540, with default and with arbitrary pivots / offsets /
+    pre- and post-rotation; the hierarchy built on top matches too."""
+    rng = np.random.default_rng(21 + with_statics)
+    n = 4000
+    parent = np.full(n, NONE, np.uint32)
+    parent[1:] = (rng.random(n - 1) * np.arange(1, n)).astype(np.uint32)  # parent index < own index
+    flags = np.full(n, fb.NODE_DEFAULT | fb.NODE_RENDERABLE, np.uint32)
+    flags[0] = fb.NODE_DEFAULT
+    pos = rng.uniform(-30, 30, (n, 3)).astype(np.float32)
+    rot = rng.normal(size=(n, 4)).astype(np.float32)
+    rot /= np.linalg.norm(rot, axis=1, keepdims=True)
+    scale = rng.uniform(0.3, 2.0, (n, 3)).astype(np.float32)
+    pos[0] = 0
+    rot[0] = (0, 0, 0, 1)
+    scale[0] = 1
+    # exercise exact zeros / negative zeros / denormals in the inputs
+    pos[5] = (0.0, -0.0, 1e-42)
+    rot[6] = (0.0, 0.0, 0.0, 1.0)
+    rot[7] = (1.0, 0.0, -0.0, 0.0)
+    scale[8] = (1.0, -1.0, 0.0)
+    statics = None
+    if with_statics:
+        statics = np.zeros((n, 25), np.float32)
+        q = rng.normal(size=(n, 4)).astype(np.float32)
+        statics[:, 0:4] = q / np.linalg.norm(q, axis=1, keepdims=True)
+        post = rng.normal(size=(n, 3, 3)).astype(np.float32)
+        statics[:, 4:13] = post.reshape(n, 9)
+        statics[:, 13:25] = rng.uniform(-2, 2, (n, 12)).astype(np.float32)
+        statics[0, :] = 0
+        statics[0, 3] = 1
+        statics[0, [4, 8, 12]] = 1
+    local = np.stack([_oracle_transform(pos[i], rot[i], scale[i], None if statics is None else statics[i]) for i in range(n)])
+    og = ob.Graph.build(parent, flags, None, local, None)
+    og.update_hierarchical_data()
+    ctx.set_topology(parent, flags)
+    if statics is not None:
+        ctx.set_transform_statics(statics)
+    trs = np.concatenate([pos, rot, scale], axis=1)
+    half = n // 2
+    ctx.set_local_trs(trs[:half])                                    # idx NULL = nodes 0..count-1
+    ctx.set_local_trs(trs[half:], np.arange(half, n, dtype=np.uint32))
+    ctx.update_transforms(fb.UPDATE_ALL)
+    from helpers import bits_equal
+
+    G = ctx.get_global_matrices()
+    Go = og.global_transforms()
+    assert bits_equal(G, Go).all(), np.nonzero((~bits_equal(G, Go)).any(axis=1))[0][:10]
+    # node 0 has no parent: its global matrix is I * local, i.e. the local matrix up to the sign of zeros
+    assert np.array_equal(G[0], local[0])
+    # one-call frame with TRS payload (pinned, pipelined)
+    pt = fb.PinnedBuffer(trs.shape, np.float32)
+    pt.array[:] = trs
+    pt.array[:, 0] += 1.0
+    local2 = np.stack([_oracle_transform(pt.array[i, 0:3], pt.array[i, 3:7], pt.array[i, 7:10], None if statics is None else statics[i]) for i in range(n)])
+    for i in range(n):
+        og.set_local_matrix(i, local2[i])
+    og.update_hierarchical_data()
+    ctx.render_prep(update_flags=fb.UPDATE_INCREMENTAL, changed_trs=pt.ptr, n_changed=n, frusta=[], readback_visible=False, async_=True)
+    ctx.sync()
+    assert bits_equal(ctx.get_global_matrices(), og.global_transforms()).all()
+    pt.free()
