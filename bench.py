@@ -279,6 +279,8 @@ def run_cuda(args):
             dist.barrier()
 
     w = WORKLOADS[args.workload]
+    from fyrox_b200 import scenegen as _sg
+    _sg.set_threads(max(1, (os.cpu_count() or 8) // max(world, 1)))  # torchrun exports OMP_NUM_THREADS=1
     # weak scaling: per-GPU work fixed; the scene grows with N and is sharded by sector sub-tree
     sc = Scene(w["nodes"] * world, n_units=w["units"] * world, verts_per_unit=w["verts_per_unit"], bones_per_unit=BONES, seed=SEED, rank=rank, nranks=world)
     # the context launches on an explicit torch stream so that torch.cuda.Event brackets exactly its work

@@ -187,6 +187,7 @@ class sg_config(C.Structure):
 SG_SYMBOLS = {
     "sg_create": (C.c_void_p, [C.POINTER(sg_config)]),
     "sg_free": (None, [C.c_void_p]),
+    "sg_set_threads": (None, [C.c_int]),
     "sg_capacity": (C.c_uint32, [C.c_void_p]),
     "sg_n_renderable": (C.c_uint32, [C.c_void_p]),
     "sg_parent": (u32p, [C.c_void_p]),

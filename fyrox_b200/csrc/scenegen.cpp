@@ -6,6 +6,8 @@
 #include <cstring>
 #include <vector>
 
+#include <omp.h>
+
 namespace {
 
 constexpr uint32_t NONE = 0xFFFFFFFFu;
@@ -290,6 +292,7 @@ extern "C" sg_scene *sg_create(const sg_config *cfg)
 }
 
 extern "C" void sg_free(sg_scene *s) { delete s; }
+extern "C" void sg_set_threads(int n) { omp_set_num_threads(n > 0 ? n : 1); }
 extern "C" uint32_t sg_capacity(const sg_scene *s) { return (uint32_t)s->parent.size(); }
 extern "C" uint32_t sg_n_renderable(const sg_scene *s) { return s->n_rend; }
 extern "C" const uint32_t *sg_parent(const sg_scene *s) { return s->parent.data(); }

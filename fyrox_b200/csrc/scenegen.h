@@ -35,6 +35,8 @@ typedef struct sg_scene sg_scene;
 
 sg_scene *sg_create(const sg_config *cfg);
 void      sg_free(sg_scene *s);
+/* OpenMP threads used by the generator (launchers such as torchrun export OMP_NUM_THREADS=1) */
+void      sg_set_threads(int n);
 
 /* shard-local node arrays (index = local node index; local 0 is the root) */
 uint32_t        sg_capacity(const sg_scene *s);

@@ -11,6 +11,11 @@ from . import _lib as L
 VERTEX_BYTES = 68  # AnimatedVertex, scene/mesh/vertex.rs:140-155
 
 
+def set_threads(n: int):
+    """OpenMP threads of the generator (torchrun exports OMP_NUM_THREADS=1)."""
+    L.load_scenegen().sg_set_threads(int(n))
+
+
 class Scene:
     def __init__(self, n_nodes: int, n_units: int = 0, verts_per_unit: int = 5000, bones_per_unit: int = 64, seed: int = 0xF1A0C5,
                  rank: int = 0, nranks: int = 1):
