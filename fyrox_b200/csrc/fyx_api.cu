@@ -101,7 +101,7 @@ struct fyx_ctx {
     uint64_t n_verts_total = 0; // padded
     uint64_t vert_cap = 0;
     uint32_t n_entries = 0, entry_cap = 0;
-    DevBuf b_vpos, b_vnrm, b_vw, b_vidx, b_opos, b_onrm, b_ib[3], b_palette, b_bone_slot, b_tiles;
+    DevBuf b_vblk, b_opos, b_onrm, b_ib[3], b_palette, b_bone_slot, b_tiles;
     DevBuf b_fold_node, b_fold_begin, b_fold_bone;
     uint32_t n_tiles = 0, max_bones = 0;
     FoldArrays fold{};
@@ -482,8 +482,8 @@ extern "C" void fyx_destroy(fyx_ctx *c)
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     fyx_comm_destroy_internal(c);
-    DevBuf *bufs[] = {&c->b_parent, &c->b_flags, &c->b_mask, &c->b_gidx, &c->b_slot_of_node, &c->d_stage, &c->b_statics, &c->b_vpos, &c->b_vnrm,
-                      &c->b_vw, &c->b_vidx, &c->b_opos, &c->b_onrm, &c->b_palette, &c->b_bone_slot, &c->b_tiles, &c->b_fold_node,
+    DevBuf *bufs[] = {&c->b_parent, &c->b_flags, &c->b_mask, &c->b_gidx, &c->b_slot_of_node, &c->d_stage, &c->b_statics, &c->b_vblk,
+                      &c->b_opos, &c->b_onrm, &c->b_palette, &c->b_bone_slot, &c->b_tiles, &c->b_fold_node,
                       &c->b_fold_begin, &c->b_fold_bone, &c->b_counts_packed, &c->b_counts_all};
     for (DevBuf *b : bufs) dev_free(*b);
     for (int i = 0; i < 3; ++i) {
@@ -690,6 +690,27 @@ extern "C" int32_t fyx_set_topology(fyx_ctx *c, uint32_t capacity, uint32_t root
             slot_of_node[i] = s;
             node_of_slot[s] = i;
         }
+    // within a level, order by parent slot (counting sort, stable in node index): siblings become
+    // contiguous, so a warp's gather of parent rows touches one or two parents instead of 32
+    {
+        std::vector<uint32_t> tmp, cnt;
+        for (size_t d = 1; d + 1 < level_off.size(); ++d) {
+            const uint32_t plo = level_off[d - 1], phi = level_off[d], lo = level_off[d], hi = level_off[d + 1];
+            if (hi - lo < 2) continue;
+            cnt.assign((size_t)(phi - plo) + 1, 0);
+            for (uint32_t s = lo; s < hi; ++s) cnt[slot_of_node[parent[node_of_slot[s]]] - plo + 1]++;
+            for (size_t k = 1; k < cnt.size(); ++k) cnt[k] += cnt[k - 1];
+            tmp.resize(hi - lo);
+            for (uint32_t s = lo; s < hi; ++s) {
+                const uint32_t i = node_of_slot[s];
+                tmp[cnt[slot_of_node[parent[i]] - plo]++] = i;
+            }
+            for (uint32_t k = 0; k < hi - lo; ++k) {
+                node_of_slot[lo + k] = tmp[k];
+                slot_of_node[tmp[k]] = lo + k;
+            }
+        }
+    }
 
     // slot-ordered host columns
     std::vector<uint32_t> h_parent(n_slots), h_flags(n_slots), h_mask(n_slots), h_gidx(n_slots);
@@ -878,14 +899,11 @@ int32_t grow_vertex_streams(fyx_ctx *c, uint64_t need)
 {
     if (need <= c->vert_cap) return FYX_OK;
     int32_t rc;
-    if ((rc = dev_ensure(c, c->b_vpos, need * 12, true))) return rc;
-    if ((rc = dev_ensure(c, c->b_vnrm, need * 12, true))) return rc;
-    if ((rc = dev_ensure(c, c->b_vw, need * 16, true))) return rc;
-    if ((rc = dev_ensure(c, c->b_vidx, need * 4, true))) return rc;
+    const uint64_t blocks = (need + 127) / 128 + 1; // 128-vertex blocks of 11 x 512 B
+    if ((rc = dev_ensure(c, c->b_vblk, blocks * kVblkStride * sizeof(float4), true))) return rc;
     if ((rc = dev_ensure(c, c->b_opos, need * 12, true))) return rc;
     if ((rc = dev_ensure(c, c->b_onrm, need * 12, true))) return rc;
-    c->vert_cap = std::min<uint64_t>({c->b_vpos.bytes / 12, c->b_vnrm.bytes / 12, c->b_vw.bytes / 16, c->b_vidx.bytes / 4,
-                                      c->b_opos.bytes / 12, c->b_onrm.bytes / 12});
+    c->vert_cap = std::min<uint64_t>({(c->b_vblk.bytes / (kVblkStride * sizeof(float4)) - 1) * 128, c->b_opos.bytes / 12, c->b_onrm.bytes / 12});
     return FYX_OK;
 }
 
@@ -907,10 +925,7 @@ void rebuild_skin_arrays(fyx_ctx *c)
     sk.bone_slot = c->b_bone_slot.as<uint32_t>();
     for (int k = 0; k < 3; ++k) sk.ib[k] = c->b_ib[k].as<float4>();
     sk.palette = c->b_palette.as<float>();
-    sk.vpos = c->b_vpos.as<float>();
-    sk.vnrm = c->b_vnrm.as<float>();
-    sk.vw = c->b_vw.as<float4>();
-    sk.vidx = c->b_vidx.as<uint32_t>();
+    sk.vblk = c->b_vblk.as<float4>();
     sk.opos = c->b_opos.as<float>();
     sk.onrm = c->b_onrm.as<float>();
 }
@@ -1033,8 +1048,7 @@ extern "C" int32_t fyx_add_skinned_surface(fyx_ctx *c, uint32_t mesh_node, uint3
         void *d_v = nullptr;
         if ((rc = stage_to_device(c, verts, (size_t)n_verts * layout->stride, nullptr, 0, false, &d_v, nullptr))) return rc;
         launch_deinterleave(c->stream, n_verts, static_cast<const unsigned char *>(d_v), *layout, n_bones,
-                            c->b_vpos.as<float>() + 3 * sf.vert_off, c->b_vnrm.as<float>() + 3 * sf.vert_off,
-                            c->b_vw.as<float4>() + sf.vert_off, c->b_vidx.as<uint32_t>() + sf.vert_off, c->d_err);
+                            c->b_vblk.as<float4>(), sf.vert_off, c->d_err);
         c->launches++;
     }
     CU(cudaGetLastError());

@@ -51,11 +51,12 @@ struct SkinArrays {
     const uint32_t *bone_slot; // slot of the bone node, FYX_NONE ⇒ identity
     const float4 *ib[3];       // inverse bind pose rows
     float *palette;            // n_entries * 16 f32, column-major mat4 (the reference's bone_matrices layout)
-    // vertex streams (each surface padded to a multiple of 4 vertices)
-    const float *vpos, *vnrm;  // packed xyz
-    const float4 *vw;
-    const uint32_t *vidx;      // 4 x u8
-    float *opos, *onrm;        // skinned streams, packed xyz
+    // input vertices: blocks of 128 vertices (32 four-vertex groups), 11 rows of 32 float4 (512 B) each:
+    //   rows 0-2 position x,y,z   rows 3-5 normal x,y,z   rows 6-9 weight 0..3   row 10 the 4x u8 bone indices;
+    // element l of a row belongs to group l of the block and holds the value of its 4 vertices.  A warp reads
+    // a row with one perfectly coalesced 512 B access and every 32 B sector exactly once (44 B/vertex).
+    const float4 *vblk;
+    float *opos, *onrm;        // skinned streams, packed xyz (each surface padded to a multiple of 4 vertices)
 };
 
 struct SkinTile {
@@ -100,7 +101,9 @@ void launch_gather_aabbs(cudaStream_t s, const NodeArrays &a, uint32_t count, co
 void launch_gather_flags(cudaStream_t s, const NodeArrays &a, uint32_t count, const uint32_t *d_idx,
                          const uint32_t *slot_of_node, uint32_t n_nodes, uint32_t *d_out);
 void launch_deinterleave(cudaStream_t s, uint32_t n_verts, const unsigned char *d_bytes, fyx_vertex_layout layout,
-                         uint32_t n_bones, float *vpos, float *vnrm, float4 *vw, uint32_t *vidx, uint32_t *d_err);
+                         uint32_t n_bones, float4 *vblk, uint64_t first_vertex, uint32_t *d_err);
+constexpr int kVblkRows = 11;                    // float4 rows per block
+constexpr int kVblkStride = kVblkRows * 32;      // float4 per block of 128 vertices
 void launch_ib_rows(cudaStream_t s, uint32_t n, const float *d_m16, float4 *r0, float4 *r1, float4 *r2, uint32_t *d_err);
 void launch_or_u32(cudaStream_t s, uint32_t *p, uint32_t bits);
 void launch_compact_gathered(cudaStream_t s, const uint32_t *pad, uint32_t maxc, const uint32_t *counts_all, int nranks, int f,

@@ -323,8 +323,10 @@ __global__ void __launch_bounds__(kBlock) k_palette(const NodeArrays a, const Sk
 // for the affine palette and finite p, so the division is the identity and is skipped.  Normals:
 // standard.shader:192-195, acc += (mat3(P[idx_k]) * n) * w_k in the same order.
 //
-// * Each thread owns 4 consecutive vertices, so every stream access is 128 bits wide: 3 (pos) + 3
-//   (normal) + 4 (weights) + 1 (indices) in, 3 + 3 out.
+// * Each thread owns 4 consecutive vertices.  Inputs live in blocks of 128 vertices x 11 rows of 512 B
+//   (x, y, z, nx, ny, nz, w0..w3, indices; fyx_internal.h): a warp reads a row with ONE coalesced 512 B
+//   access and each 32 B sector exactly once (the packed-xyz layout made every sector travel L2->SM
+//   twice).  Outputs are packed xyz streams, 3 + 3 128-bit stores per thread.
 // * Arithmetic uses Blackwell's packed FP32 pipe (mul.rn.f32x2 / add.rn.f32x2 via __fmul2_rn /
 //   __fadd2_rn: two independently rounded f32 results per issue slot).  The kernel is issue-bound
 //   (ncu: 8.6 warp-instructions per vertex), and FMA contraction is forbidden, so halving the FP
@@ -373,16 +375,17 @@ __device__ __forceinline__ void skin_fill_palette(float4 *s_pal, const float *pa
 
 // four vertices (one thread's group) from registers to the two output streams
 template <int S, int LOG2C>
-__device__ __forceinline__ void skin_quad(const float4 *s_pal, const uint32_t lane, const float4 p0, const float4 p1, const float4 p2,
-                                          const float4 n0, const float4 n1, const float4 n2, const float4 w0, const float4 w1,
+__device__ __forceinline__ void skin_quad(const float4 *s_pal, const uint32_t lane, const float4 x4, const float4 y4, const float4 z4,
+                                          const float4 nx4, const float4 ny4, const float4 nz4, const float4 w0, const float4 w1,
                                           const float4 w2, const float4 w3, const uint4 iq, float4 *po, float4 *no,
                                           const PackedConsts kc)
 {
     constexpr int C = 1 << LOG2C;
     constexpr int PL = S * C;
-    const float px[4] = {p0.x, p0.w, p1.z, p2.y}, py[4] = {p0.y, p1.x, p1.w, p2.z}, pz[4] = {p0.z, p1.y, p2.x, p2.w};
-    const float nx[4] = {n0.x, n0.w, n1.z, n2.y}, ny[4] = {n0.y, n1.x, n1.w, n2.z}, nz[4] = {n0.z, n1.y, n2.x, n2.w};
-    const float4 wv[4] = {w0, w1, w2, w3};
+    const float px[4] = {x4.x, x4.y, x4.z, x4.w}, py[4] = {y4.x, y4.y, y4.z, y4.w}, pz[4] = {z4.x, z4.y, z4.z, z4.w};
+    const float nx[4] = {nx4.x, nx4.y, nx4.z, nx4.w}, ny[4] = {ny4.x, ny4.y, ny4.z, ny4.w}, nz[4] = {nz4.x, nz4.y, nz4.z, nz4.w};
+    // w_k holds weight k of the four vertices
+    const float wk4[4][4] = {{w0.x, w1.x, w2.x, w3.x}, {w0.y, w1.y, w2.y, w3.y}, {w0.z, w1.z, w2.z, w3.z}, {w0.w, w1.w, w2.w, w3.w}};
     const uint32_t iv[4] = {iq.x, iq.y, iq.z, iq.w};
     float ox[4], oy[4], oz[4], mx[4], my[4], mz[4];
 #pragma unroll
@@ -391,7 +394,7 @@ __device__ __forceinline__ void skin_quad(const float4 *s_pal, const uint32_t la
         const float2 nxx = make_float2(nx[v], nx[v]), nyy = make_float2(ny[v], ny[v]), nzz = make_float2(nz[v], nz[v]);
         const float2 pnx = make_float2(px[v], nx[v]), pny = make_float2(py[v], ny[v]), pnz = make_float2(pz[v], nz[v]);
         float2 acc_p = make_float2(0.0f, 0.0f), acc_n = make_float2(0.0f, 0.0f), acc_z = make_float2(0.0f, 0.0f);
-        const float wk[4] = {wv[v].x, wv[v].y, wv[v].z, wv[v].w};
+        const float *wk = wk4[v];
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
             const uint32_t bone = (iv[v] >> (8 * k)) & 0xFFu;
@@ -436,14 +439,12 @@ __global__ void __launch_bounds__(kBlock, MINB) k_skin(const SkinArrays sk, cons
     const uint32_t lane = threadIdx.x & 31u;
     for (uint32_t q = threadIdx.x; q < T.n_quads; q += kBlock) {
         const size_t quad = (size_t)T.quad_start + q;
-        const float4 *pp = reinterpret_cast<const float4 *>(sk.vpos) + 3 * quad;
-        const float4 *np = reinterpret_cast<const float4 *>(sk.vnrm) + 3 * quad;
-        const float4 p0 = ld_stream(pp), p1 = ld_stream(pp + 1), p2 = ld_stream(pp + 2);
-        const float4 n0 = ld_stream(np), n1 = ld_stream(np + 1), n2 = ld_stream(np + 2);
-        const float4 w0 = ld_stream(sk.vw + 4 * quad), w1 = ld_stream(sk.vw + 4 * quad + 1);
-        const float4 w2 = ld_stream(sk.vw + 4 * quad + 2), w3 = ld_stream(sk.vw + 4 * quad + 3);
-        const uint4 iq = ld_stream(reinterpret_cast<const uint4 *>(sk.vidx) + quad);
-        skin_quad<S, LOG2C>(s_pal, lane, p0, p1, p2, n0, n1, n2, w0, w1, w2, w3, iq, reinterpret_cast<float4 *>(sk.opos) + 3 * quad,
+        const float4 *row = sk.vblk + (quad >> 5) * kVblkStride + (quad & 31); // block, then this group's column
+        const float4 x4 = ld_stream(row + 0 * 32), y4 = ld_stream(row + 1 * 32), z4 = ld_stream(row + 2 * 32);
+        const float4 nx4 = ld_stream(row + 3 * 32), ny4 = ld_stream(row + 4 * 32), nz4 = ld_stream(row + 5 * 32);
+        const float4 w0 = ld_stream(row + 6 * 32), w1 = ld_stream(row + 7 * 32), w2 = ld_stream(row + 8 * 32), w3 = ld_stream(row + 9 * 32);
+        const uint4 iq = ld_stream(reinterpret_cast<const uint4 *>(row + 10 * 32));
+        skin_quad<S, LOG2C>(s_pal, lane, x4, y4, z4, nx4, ny4, nz4, w0, w1, w2, w3, iq, reinterpret_cast<float4 *>(sk.opos) + 3 * quad,
                             reinterpret_cast<float4 *>(sk.onrm) + 3 * quad, kc);
     }
 }
@@ -710,16 +711,17 @@ __global__ void __launch_bounds__(kBlock) k_gather_flags(const NodeArrays a, con
                                                       FYX_NODE_GLOBAL_ENABLED | FYX_NODE_REACHABLE));
 }
 
-// VertexBuffer bytes (scene/mesh/buffer.rs:404-414) → SoA streams.  Done once per surface at load.
+// VertexBuffer bytes (scene/mesh/buffer.rs:404-414) → the blocked input layout of k_skin (fyx_internal.h).
+// Done once per surface at load.  Vertex v (absolute) = group Q = v/4, element j = v%4 of block Q/32.
 __global__ void __launch_bounds__(kBlock) k_deinterleave(const uint32_t n_verts, const uint32_t n_padded,
                                                          const unsigned char *d_bytes, const fyx_vertex_layout l,
-                                                         const uint32_t n_bones, float *vpos, float *vnrm, float4 *vw,
-                                                         uint32_t *vidx, uint32_t *d_err)
+                                                         const uint32_t n_bones, float4 *vblk, const uint64_t first_vertex,
+                                                         uint32_t *d_err)
 {
     const uint32_t v = blockIdx.x * kBlock + threadIdx.x;
     if (v >= n_padded) return;
     float p[3] = {0.f, 0.f, 0.f}, n[3] = {0.f, 0.f, 0.f};
-    float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
+    float w[4] = {0.f, 0.f, 0.f, 0.f};
     uint32_t bi = 0u;
     if (v < n_verts) {
         const unsigned char *vp = d_bytes + (size_t)v * l.stride;
@@ -728,7 +730,7 @@ __global__ void __launch_bounds__(kBlock) k_deinterleave(const uint32_t n_verts,
         const float *fw = reinterpret_cast<const float *>(vp + l.bone_weights_offset);
         p[0] = fp[0]; p[1] = fp[1]; p[2] = fp[2];
         n[0] = fn[0]; n[1] = fn[1]; n[2] = fn[2];
-        w = make_float4(fw[0], fw[1], fw[2], fw[3]);
+        w[0] = fw[0]; w[1] = fw[1]; w[2] = fw[2]; w[3] = fw[3];
         bi = *reinterpret_cast<const uint32_t *>(vp + l.bone_indices_offset);
         uint32_t bad = 0u;
 #pragma unroll
@@ -737,15 +739,20 @@ __global__ void __launch_bounds__(kBlock) k_deinterleave(const uint32_t n_verts,
         if (bad) { // the reference would panic on the out-of-range index (mesh/mod.rs:515)
             atomicOr(d_err, E_BAD_BONE_INDEX);
             bi = 0u;
-            w = make_float4(0.f, 0.f, 0.f, 0.f);
+            w[0] = w[1] = w[2] = w[3] = 0.f;
         }
         if (!((fabsf(p[0]) <= 3.402823466e38f) & (fabsf(p[1]) <= 3.402823466e38f) & (fabsf(p[2]) <= 3.402823466e38f)))
             atomicOr(d_err, E_NONFINITE_VERTEX);
     }
-    vpos[3 * (size_t)v + 0] = p[0]; vpos[3 * (size_t)v + 1] = p[1]; vpos[3 * (size_t)v + 2] = p[2];
-    vnrm[3 * (size_t)v + 0] = n[0]; vnrm[3 * (size_t)v + 1] = n[1]; vnrm[3 * (size_t)v + 2] = n[2];
-    vw[v] = w;
-    vidx[v] = bi;
+    const uint64_t av = first_vertex + v;
+    const uint64_t Q = av >> 2;
+    const uint32_t j = (uint32_t)(av & 3);
+    float *blk = reinterpret_cast<float *>(vblk + (Q >> 5) * kVblkStride + (Q & 31)); // row 0, this group's float4
+    const size_t rs = 32 * 4; // floats between rows
+    blk[0 * rs + j] = p[0]; blk[1 * rs + j] = p[1]; blk[2 * rs + j] = p[2];
+    blk[3 * rs + j] = n[0]; blk[4 * rs + j] = n[1]; blk[5 * rs + j] = n[2];
+    blk[6 * rs + j] = w[0]; blk[7 * rs + j] = w[1]; blk[8 * rs + j] = w[2]; blk[9 * rs + j] = w[3];
+    reinterpret_cast<uint32_t *>(blk)[10 * rs + j] = bi;
 }
 
 __global__ void __launch_bounds__(kBlock) k_ib_rows(const uint32_t n, const float *d_m16, float4 *r0, float4 *r1, float4 *r2,
@@ -911,12 +918,11 @@ void launch_gather_flags(cudaStream_t s, const NodeArrays &a, uint32_t count, co
 }
 
 void launch_deinterleave(cudaStream_t s, uint32_t n_verts, const unsigned char *d_bytes, fyx_vertex_layout layout,
-                         uint32_t n_bones, float *vpos, float *vnrm, float4 *vw, uint32_t *vidx, uint32_t *d_err)
+                         uint32_t n_bones, float4 *vblk, uint64_t first_vertex, uint32_t *d_err)
 {
     const uint32_t n_padded = (n_verts + 3u) & ~3u;
     if (!n_padded) return;
-    k_deinterleave<<<grid_for(n_padded), kBlock, 0, s>>>(n_verts, n_padded, d_bytes, layout, n_bones, vpos, vnrm, vw, vidx,
-                                                         d_err);
+    k_deinterleave<<<grid_for(n_padded), kBlock, 0, s>>>(n_verts, n_padded, d_bytes, layout, n_bones, vblk, first_vertex, d_err);
 }
 
 void launch_ib_rows(cudaStream_t s, uint32_t n, const float *d_m16, float4 *r0, float4 *r1, float4 *r2, uint32_t *d_err)
