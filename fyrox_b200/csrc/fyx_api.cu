@@ -282,6 +282,7 @@ void to_dev_frustum(const fyx_frustum &f, uint32_t cam_mask, uint32_t pass_flags
     for (int k = 0; k < 3; ++k) {
         int n = 0;
         uint32_t masks[8] = {0};
+        float vals[8];
         d.ax_mask[k][0] = d.ax_mask[k][1] = 0;
         for (int i = 0; i < 8; ++i) {
             const float v = f.corners[i][k];
@@ -289,16 +290,18 @@ void to_dev_frustum(const fyx_frustum &f, uint32_t cam_mask, uint32_t pass_flags
             memcpy(&vb, &v, 4);
             int j = 0;
             for (; j < n; ++j) {
-                memcpy(&ub, &d.ax_val[k][j], 4);
+                memcpy(&ub, &vals[j], 4);
                 if (ub == vb) break;
             }
             if (j == n) {
-                d.ax_val[k][n] = v;
+                vals[n] = v;
                 ++n;
             }
             masks[j] |= 1u << i;
         }
-        for (int j = n; j < 8; ++j) d.ax_val[k][j] = 0.0f;
+        for (int j = n; j < 8; ++j) vals[j] = std::nanf(""); // never inside any box
+        d.ax_val[k][0] = make_float4(vals[0], vals[1], vals[2], vals[3]);
+        d.ax_val[k][1] = make_float4(vals[4], vals[5], vals[6], vals[7]);
         for (int j = 0; j < n; ++j) d.ax_mask[k][j >> 2] |= masks[j] << (8 * (j & 3));
         d.n_ax |= (uint32_t)n << (8 * k);
     }

@@ -60,11 +60,12 @@ __device__ __forceinline__ uint32_t cull_bits(const uint32_t nf, const uint32_t 
     PackedConsts kc;
     kc.one = make_float2(cp.one, cp.one);
     kc.negzero = make_float2(cp.negzero, cp.negzero);
+    const bool tame = aabb_is_tame(wx, wy, wz);
     uint32_t bits = 0u;
     for (int f = 0; f < cp.nf; ++f) {
         bool ok = (mask & cp.f[f].cam_mask) != 0u;
         ok &= !((cp.f[f].pass_flags & FYX_PASS_SHADOW) && !(nf & FYX_NODE_CAST_SHADOWS));
-        if (ok && (nf & FYX_NODE_FRUSTUM_CULLING)) ok = frustum_intersects_aabb(cp.f[f], wx, wy, wz, kc);
+        if (ok && (nf & FYX_NODE_FRUSTUM_CULLING)) ok = frustum_intersects_aabb(cp.f[f], wx, wy, wz, kc, tame);
         bits |= ok ? (1u << f) : 0u;
     }
     return bits;

@@ -98,8 +98,9 @@ struct FrustumDev {
     uint32_t pass_flags;
     uint32_t psel;   // bit (3*p + axis): the plane-p normal component on that axis is negative
     uint32_t n_ax;   // n_ax >> (8*axis) & 0xFF: number of distinct corner coordinates on that axis
-    // distinct corner coordinates per axis and, for each, the mask of the corners that have it
-    float ax_val[3][8];
+    // distinct corner coordinates per axis (unused entries are NaN: they compare false) and, for each, the
+    // mask of the corners that have it
+    float4 ax_val[3][2];
     uint32_t ax_mask[3][2]; // 8 x 8-bit corner masks per axis, packed little-endian
 };
 
@@ -112,13 +113,17 @@ struct FrustumDev {
 // 10 ops per plane instead of 56.  The argument needs NaN-free arithmetic and min <= max: boxes with a
 // non-finite or huge (>1e18) bound or an inverted axis take the literal 8-corner loop instead (never in
 // practice; the branch is uniform).
+__device__ __forceinline__ bool aabb_is_tame(const float2 x, const float2 y, const float2 z)
+{
+    const float kBig = 1e18f;
+    return (fabsf(x.x) <= kBig) & (fabsf(x.y) <= kBig) & (fabsf(y.x) <= kBig) & (fabsf(y.y) <= kBig) & (fabsf(z.x) <= kBig) &
+           (fabsf(z.y) <= kBig) & (x.x <= x.y) & (y.x <= y.y) & (z.x <= z.y);
+}
+
 __device__ __forceinline__ bool frustum_intersects_aabb(const FrustumDev &f, const float2 x, const float2 y,
-                                                        const float2 z, const PackedConsts &kc)
+                                                        const float2 z, const PackedConsts &kc, const bool tame)
 {
     bool cloud = true;
-    const float kBig = 1e18f;
-    const bool tame = (fabsf(x.x) <= kBig) & (fabsf(x.y) <= kBig) & (fabsf(y.x) <= kBig) & (fabsf(y.y) <= kBig) &
-                      (fabsf(z.x) <= kBig) & (fabsf(z.y) <= kBig) & (x.x <= x.y) & (y.x <= y.y) & (z.x <= z.y);
     if (tame) {
         // n*p is monotone in p (rounding is monotone), so max(fl(n*min), fl(n*max)) is fl(n*max) for n >= 0
         // and fl(n*min) for n < 0: pick the operand first (psel, built on the host) and multiply once.
@@ -152,18 +157,27 @@ __device__ __forceinline__ bool frustum_intersects_aabb(const FrustumDev &f, con
     // Fallback: any frustum corner inside the AABB, inclusive compares (aabb.rs:193-200):
     //   exists c: min <= corner_c <= max on all three axes.
     // Evaluated as three 8-bit corner masks (one per axis, built from the DISTINCT corner coordinates of
-    // that axis — a frustum has few) ANDed together, leaving after the first axis that no corner
-    // satisfies: the same booleans as the reference's loop, ~10 instructions for the typical rejected box.
+    // that axis — a frustum usually has <= 4) ANDed together, leaving after the first axis that no corner
+    // satisfies: the same booleans as the reference's loop, ~15 instructions for the typical rejected box.
     uint32_t alive = 0xFFu;
     const float2 box[3] = {x, y, z};
 #pragma unroll
     for (int a = 0; a < 3; ++a) {
-        const int n = (int)((f.n_ax >> (8 * a)) & 0xFFu);
+        const float lo = box[a].x, hi = box[a].y;
+        const float4 v0 = f.ax_val[a][0];
+        const uint32_t m0 = f.ax_mask[a][0];
         uint32_t m = 0u;
-        for (int k = 0; k < n; ++k) {
-            const float v = f.ax_val[a][k];
-            const uint32_t cm = (f.ax_mask[a][k >> 2] >> (8 * (k & 3))) & 0xFFu;
-            m |= ((v >= box[a].x) & (v <= box[a].y)) ? cm : 0u;
+        m |= ((v0.x >= lo) & (v0.x <= hi)) ? (m0 & 0xFFu) : 0u;
+        m |= ((v0.y >= lo) & (v0.y <= hi)) ? ((m0 >> 8) & 0xFFu) : 0u;
+        m |= ((v0.z >= lo) & (v0.z <= hi)) ? ((m0 >> 16) & 0xFFu) : 0u;
+        m |= ((v0.w >= lo) & (v0.w <= hi)) ? (m0 >> 24) : 0u;
+        if (((f.n_ax >> (8 * a)) & 0xFFu) > 4u) { // more than four distinct coordinates on this axis (uniform branch)
+            const float4 v1 = f.ax_val[a][1];
+            const uint32_t m1 = f.ax_mask[a][1];
+            m |= ((v1.x >= lo) & (v1.x <= hi)) ? (m1 & 0xFFu) : 0u;
+            m |= ((v1.y >= lo) & (v1.y <= hi)) ? ((m1 >> 8) & 0xFFu) : 0u;
+            m |= ((v1.z >= lo) & (v1.z <= hi)) ? ((m1 >> 16) & 0xFFu) : 0u;
+            m |= ((v1.w >= lo) & (v1.w <= hi)) ? (m1 >> 24) : 0u;
         }
         alive &= m;
         if (!alive) return false;
