@@ -545,3 +545,16 @@ def test_trs_upload_equals_calculate_local_transform(ctx, with_statics):
     ctx.sync()
     assert bits_equal(ctx.get_global_matrices(), og.global_transforms()).all()
     pt.free()
+
+
+def test_cpp_host_mirror_runs_the_reference_hierarchy_tests():
+    """tests/cpp/test_host.cpp: K6 / K7 / K10 and a from_graph cull through the C++ host mirror
+    (fyrox_b200/host/fyrox_host.hpp), which drives the device through fyx_set_local_trs."""
+    import os
+    import subprocess
+
+    d = os.path.join(os.path.dirname(os.path.abspath(__file__)), "cpp")
+    r = subprocess.run(["make", "-C", d, "test_host"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    r = subprocess.run([os.path.join(d, "test_host")], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0 and r.stdout.strip() == "OK", r.stdout + r.stderr
