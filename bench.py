@@ -395,6 +395,21 @@ def run_cuda(args):
         t = ctx.timings()
         for k in stage:
             stage[k] += t[k] / args.steps
+    # second mode BASELINE.md asks for: "static + skeletons" — only the bones change (uploaded every frame),
+    # Graph::update semantics (FYX_UPDATE_INCREMENTAL): clean sub-trees keep their matrices / boxes, everything is culled
+    inc_ms = None
+    if anim and world == 1:
+        def inc_frames(steps):
+            for i in range(steps):
+                pi, pm = anim[i & 1]
+                kw = {"changed_trs": pm.ptr} if args.upload == "trs" else {"changed_m16": pm.ptr}
+                ctx.render_prep(update_flags=fb.UPDATE_INCREMENTAL, changed_idx=pi.ptr, n_changed=n_bones, frusta=frusta,
+                                readback_visible=True, async_=True, **kw)
+                if i:
+                    ctx.frame_wait()
+            ctx.frame_wait()
+        inc_frames(3)
+        inc_ms = timed(lambda: inc_frames(args.steps), 1) / args.steps
     clk = clocks.stop() if rank == 0 else None
 
     ms_per_step = total_ms / args.steps
@@ -453,6 +468,7 @@ def run_cuda(args):
                 "ms_per_step_synchronous": e2e_sync_ms / args.steps, "ms_per_step_pipelined": e2e_pipe_ms / args.steps},
         "gpu_launches": int(launches),
         "roofline": roofline,
+        "modes": {"all_dirty_ms_per_step": ms_per_step, "static_plus_skeletons_e2e_ms_per_step": inc_ms},
     }
     if world == 1 and not args.no_cpu_baseline:
         try:
