@@ -324,7 +324,7 @@ def run_cuda(args):
     vis_counts = [0] * len(frusta)
 
     def submit_e2e(i, pipelined):
-        kw = dict(update_flags=fb.UPDATE_ALL, frusta=frusta, readback_visible=(world == 1), async_=pipelined, allgather=(world > 1))
+        kw = dict(update_flags=fb.UPDATE_ALL, frusta=frusta, readback_visible=True, async_=pipelined, allgather=(world > 1))
         if anim:
             pi, pm = anim[i & 1]
             kw.update(changed_idx=pi.ptr, n_changed=n_bones, **({"changed_trs": pm.ptr} if args.upload == "trs" else {"changed_m16": pm.ptr}))
@@ -381,12 +381,9 @@ def run_cuda(args):
     total_ms = timed(step_device, args.steps)
     launches = ctx.kernel_launch_count() - launches0
     e2e_sync_ms = timed(step_e2e, args.steps, pass_index=True)
-    if world == 1:
-        for _ in range(2):
-            run_e2e_pipelined(3)
-        e2e_pipe_ms = timed(lambda: run_e2e_pipelined(args.steps), 1)
-    else:
-        e2e_pipe_ms = e2e_sync_ms
+    for _ in range(2):
+        run_e2e_pipelined(3)
+    e2e_pipe_ms = timed(lambda: run_e2e_pipelined(args.steps), 1)
     e2e_ms = min(e2e_sync_ms, e2e_pipe_ms)
     # per-stage device durations (CUDA events on the launching stream, inside fyx_render_prep), same K frames
     stage = {"update_ms": 0.0, "palette_ms": 0.0, "skin_ms": 0.0}
@@ -419,7 +416,7 @@ def run_cuda(args):
     e2e_value = units_all / (e2e_ms_per_step * 1e-3)
     sum_vis = sum(vis_counts)
     h2d = n_bones * ((40 if args.upload == "trs" else 64) + 4)  # frusta travel as kernel parameters
-    d2h = 4 * len(frusta) + 4 * sum_vis
+    d2h = 4 * len(frusta) + 4 * sum_vis  # per rank: at N > 1 every rank reads back the whole gathered lists
 
     peak, peak_src = peaks()
     # dominant kernel: k_skin when the workload skins, else the fused update+cull level kernels

@@ -48,6 +48,13 @@ struct VisSlot {
     size_t h_vis_cap[FYX_MAX_FRUSTA] = {};
     uint32_t nf = 0;
     bool counts_on_host = false, lists_on_host = false;
+    // multi-GPU: the all-gathered lists of this frame (padded slots, packed list, host copy)
+    DevBuf b_gath_pad[FYX_MAX_FRUSTA], b_gath[FYX_MAX_FRUSTA];
+    uint32_t gath_count[FYX_MAX_FRUSTA] = {};
+    uint32_t *h_gath[FYX_MAX_FRUSTA] = {};
+    size_t h_gath_cap[FYX_MAX_FRUSTA] = {};
+    bool gathered = false, gathered_on_host = false;
+    cudaEvent_t ev_gather = nullptr;
     bool pending = false; // written by a pipelined (async + read-back) frame that fyx_frame_wait has not collected yet
     uint64_t frame_no = 0;
     cudaEvent_t ev_cull = nullptr, ev_counts = nullptr, ev_done = nullptr;
@@ -116,13 +123,9 @@ struct fyx_ctx {
     // multi-GPU (fyx_comm.cu)
     void *comm = nullptr;
     int nranks = 1, rank = 0;
-    cudaStream_t comm_stream = nullptr; // the collective runs beside the palette / skinning kernels
-    cudaEvent_t ev_gather = nullptr;
-    DevBuf b_counts_packed, b_counts_all, b_gath_pad[FYX_MAX_FRUSTA], b_gath[FYX_MAX_FRUSTA];
+    cudaStream_t comm_stream = nullptr; // the collective runs beside the palette / skinning kernels (highest priority)
+    DevBuf b_counts_packed, b_counts_all;
     uint32_t *h_counts_all = nullptr; // pinned nranks*FYX_MAX_FRUSTA
-    uint32_t gath_count[FYX_MAX_FRUSTA] = {};
-    uint32_t *h_gath[FYX_MAX_FRUSTA] = {};
-    size_t h_gath_cap[FYX_MAX_FRUSTA] = {};
 };
 
 namespace {
@@ -327,14 +330,15 @@ int32_t prepare_cull(fyx_ctx *c, uint32_t nf, const fyx_frustum *fr, const uint3
     c->cp.negzero = -0.0f;
     for (uint32_t f = 0; f < nf; ++f) {
         to_dev_frustum(fr[f], cam_mask ? cam_mask[f] : 0xFFFFFFFFu, pass_flags ? pass_flags[f] : 0u, c->cp.f[f]);
-        // worst case every renderable node is visible
-        int32_t rc = dev_ensure(c, V.b_vis[f], sizeof(uint32_t) * std::max<size_t>(c->n_renderable, 1));
+        // worst case every alive node is visible (fyx_set_flags may turn any of them renderable)
+        int32_t rc = dev_ensure(c, V.b_vis[f], sizeof(uint32_t) * std::max<size_t>(c->n_slots, 1));
         if (rc) return rc;
         c->cp.out[f] = V.b_vis[f].as<uint32_t>();
     }
     CU(cudaMemsetAsync(V.d_counts, 0, sizeof(uint32_t) * kCountStride * FYX_MAX_FRUSTA, c->stream));
     V.nf = nf;
     V.counts_on_host = V.lists_on_host = false;
+    V.gathered = V.gathered_on_host = false;
     c->readable = slot;
     return FYX_OK;
 }
@@ -366,6 +370,17 @@ int32_t host_list_ensure(fyx_ctx *c, VisSlot &V, uint32_t f, size_t n)
     const size_t cap = std::max<size_t>(1024, n + n / 2);
     CU(cudaHostAlloc(reinterpret_cast<void **>(&V.h_vis[f]), cap * sizeof(uint32_t), cudaHostAllocDefault));
     V.h_vis_cap[f] = cap;
+    return FYX_OK;
+}
+
+int32_t host_gath_ensure(fyx_ctx *c, VisSlot &V, uint32_t f, size_t n)
+{
+    if (n <= V.h_gath_cap[f]) return FYX_OK;
+    if (V.h_gath[f]) cudaFreeHost(V.h_gath[f]);
+    V.h_gath[f] = nullptr;
+    const size_t cap = std::max<size_t>(1024, n + n / 2);
+    CU(cudaHostAlloc(reinterpret_cast<void **>(&V.h_gath[f]), cap * sizeof(uint32_t), cudaHostAllocDefault));
+    V.h_gath_cap[f] = cap;
     return FYX_OK;
 }
 
@@ -462,6 +477,7 @@ extern "C" int32_t fyx_create(const fyx_config *cfg, fyx_ctx **out_ctx)
         CUB(cudaEventCreateWithFlags(&V.ev_cull, cudaEventDisableTiming));
         CUB(cudaEventCreateWithFlags(&V.ev_counts, cudaEventDisableTiming));
         CUB(cudaEventCreateWithFlags(&V.ev_done, cudaEventDisableTiming));
+        CUB(cudaEventCreateWithFlags(&V.ev_gather, cudaEventDisableTiming));
     }
     CUB(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
     CUB(cudaStreamCreateWithFlags(&c->d2h_stream, cudaStreamNonBlocking));
@@ -498,16 +514,15 @@ extern "C" void fyx_destroy(fyx_ctx *c)
     }
     if (c->copy_stream) cudaStreamSynchronize(c->copy_stream);
     if (c->d2h_stream) cudaStreamSynchronize(c->d2h_stream);
-    for (uint32_t f = 0; f < FYX_MAX_FRUSTA; ++f) {
-        dev_free(c->b_gath_pad[f]);
-        dev_free(c->b_gath[f]);
-        if (c->h_gath[f]) cudaFreeHost(c->h_gath[f]);
-    }
     for (VisSlot &V : c->vs) {
         for (uint32_t f = 0; f < FYX_MAX_FRUSTA; ++f) {
             dev_free(V.b_vis[f]);
             if (V.h_vis[f]) cudaFreeHost(V.h_vis[f]);
+            dev_free(V.b_gath_pad[f]);
+            dev_free(V.b_gath[f]);
+            if (V.h_gath[f]) cudaFreeHost(V.h_gath[f]);
         }
+        if (V.ev_gather) cudaEventDestroy(V.ev_gather);
         if (V.d_counts) cudaFree(V.d_counts);
         if (V.h_counts) cudaFreeHost(V.h_counts);
         if (V.ev_cull) cudaEventDestroy(V.ev_cull);
@@ -1293,6 +1308,7 @@ extern "C" int32_t fyx_render_prep(fyx_ctx *c, const fyx_frame_desc *fr)
     if (gather) {
         if (!c->comm) return fail(c, FYX_ERR_STATE, "FYX_FRAME_ALLGATHER without fyx_comm_init");
         CU(cudaStreamWaitEvent(c->comm_stream, c->vs[c->cur].ev_cull, 0));
+        if (c->vs[c->cur ^ 1].gathered) CU(cudaStreamWaitEvent(c->comm_stream, c->vs[c->cur ^ 1].ev_gather, 0)); // a stand-alone exchange of the previous frame
         rc = allgather_begin(c, c->vs[c->cur], c->comm_stream);
         if (rc) return rc;
     }
@@ -1312,8 +1328,8 @@ extern "C" int32_t fyx_render_prep(fyx_ctx *c, const fyx_frame_desc *fr)
         // the host waits only for the cull + the counts (the skinning kernel keeps running), then enqueues the payload
         rc = allgather_finish(c, c->vs[c->cur], c->comm_stream);
         if (rc) return rc;
-        CU(cudaEventRecord(c->ev_gather, c->comm_stream));
-        CU(cudaStreamWaitEvent(s, c->ev_gather, 0)); // the frame is complete when the gathered lists are
+        CU(cudaEventRecord(c->vs[c->cur].ev_gather, c->comm_stream));
+        CU(cudaStreamWaitEvent(s, c->vs[c->cur].ev_gather, 0)); // the frame is complete when the gathered lists are
     }
     // 5. visible lists to the host
     VisSlot &V = c->vs[c->cur];
@@ -1326,10 +1342,10 @@ extern "C" int32_t fyx_render_prep(fyx_ctx *c, const fyx_frame_desc *fr)
         CU(cudaEventRecord(V.ev_counts, c->d2h_stream));
         V.pending = true;
         V.frame_no = ++c->frame_counter;
-    } else if (fr->readback_visible && fr->n_frusta) {
+    } else if (fr->readback_visible && fr->n_frusta && !gather) {
         rc = readback_visible(c, V, s);
         if (rc) return rc;
-    }
+    } // with FYX_FRAME_ALLGATHER the frame's result is the gathered lists: fyx_get_visible_gathered fetches them
     CU(cudaEventRecord(c->ev[EV_READBACK], s));
     if (async) {
         c->timings_pending = true;
@@ -1353,16 +1369,26 @@ extern "C" int32_t fyx_frame_wait(fyx_ctx *c)
     VisSlot &V = c->vs[slot];
     CU(cudaEventSynchronize(V.ev_counts));
     V.counts_on_host = true;
-    for (uint32_t f = 0; f < V.nf; ++f) {
+    for (uint32_t f = 0; f < V.nf && !V.gathered; ++f) {
         const size_t n = V.h_counts[f];
         int32_t rc = host_list_ensure(c, V, f, n);
         if (rc) return rc;
         if (n) CU(cudaMemcpyAsync(V.h_vis[f], V.b_vis[f].p, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->d2h_stream));
     }
+    if (V.gathered) { // multi-GPU frame: the host wants the whole (all-gathered) lists
+        CU(cudaStreamWaitEvent(c->d2h_stream, V.ev_gather, 0));
+        for (uint32_t f = 0; f < V.nf; ++f) {
+            const size_t n = V.gath_count[f];
+            int32_t rc = host_gath_ensure(c, V, f, n);
+            if (rc) return rc;
+            if (n) CU(cudaMemcpyAsync(V.h_gath[f], V.b_gath[f].p, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->d2h_stream));
+        }
+        V.gathered_on_host = true;
+    }
     CU(cudaStreamWaitEvent(c->d2h_stream, V.ev_done, 0)); // the error word is final once the frame's last kernel ran
     CU(cudaMemcpyAsync(c->h_err, c->d_err, sizeof(uint32_t), cudaMemcpyDeviceToHost, c->d2h_stream));
     CU(cudaStreamSynchronize(c->d2h_stream));
-    V.lists_on_host = true;
+    V.lists_on_host = !V.gathered;
     V.pending = false;
     c->readable = slot;
     return check_device_errors(c);

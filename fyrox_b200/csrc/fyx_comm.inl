@@ -69,10 +69,7 @@ static void fyx_comm_destroy_internal(fyx_ctx *c)
         cudaStreamDestroy(c->comm_stream);
         c->comm_stream = nullptr;
     }
-    if (c->ev_gather) {
-        cudaEventDestroy(c->ev_gather);
-        c->ev_gather = nullptr;
-    }
+
     if (c->comm && nccl().ok) nccl().CommDestroy(static_cast<ncclComm_t>(c->comm));
     c->comm = nullptr;
 }
@@ -107,8 +104,13 @@ extern "C" int32_t fyx_comm_init(fyx_ctx *c, int32_t nranks, int32_t rank, const
     if ((rc = dev_ensure(c, c->b_counts_all, sizeof(uint32_t) * FYX_MAX_FRUSTA * nranks))) return rc;
     if (c->h_counts_all) cudaFreeHost(c->h_counts_all);
     CU(cudaHostAlloc(reinterpret_cast<void **>(&c->h_counts_all), sizeof(uint32_t) * FYX_MAX_FRUSTA * nranks, cudaHostAllocDefault));
-    if (!c->comm_stream) CU(cudaStreamCreateWithFlags(&c->comm_stream, cudaStreamNonBlocking));
-    if (!c->ev_gather) CU(cudaEventCreateWithFlags(&c->ev_gather, cudaEventDisableTiming));
+    if (!c->comm_stream) {
+        // highest priority: its few CTAs are placed as soon as a skinning CTA retires, so the exchange really
+        // runs beside k_skin instead of after it (k_skin alone fills the register file of every SM)
+        int lo = 0, hi = 0;
+        CU(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        CU(cudaStreamCreateWithPriority(&c->comm_stream, cudaStreamNonBlocking, hi));
+    }
     return FYX_OK;
 }
 
@@ -116,6 +118,8 @@ extern "C" int32_t fyx_comm_init(fyx_ctx *c, int32_t nranks, int32_t rank, const
 static int32_t allgather_begin(fyx_ctx *c, VisSlot &V, cudaStream_t s)
 {
     ncclComm_t comm = static_cast<ncclComm_t>(c->comm);
+    // a new exchange may only start once the previous one's pack kernels have read the shared count table
+    // (same stream in every caller ⇒ stream order guarantees it)
     CU(cudaMemsetAsync(c->b_counts_packed.p, 0, sizeof(uint32_t) * FYX_MAX_FRUSTA, s));
     CU(cudaMemcpy2DAsync(c->b_counts_packed.p, sizeof(uint32_t), V.d_counts, sizeof(uint32_t) * kCountStride, sizeof(uint32_t), V.nf,
                          cudaMemcpyDeviceToDevice, s));
@@ -142,9 +146,9 @@ static int32_t allgather_finish(fyx_ctx *c, VisSlot &V, cudaStream_t s)
             maxc[f] = std::max(maxc[f], n);
             total += n;
         }
-        c->gath_count[f] = (uint32_t)total;
-        if ((rc = dev_ensure(c, c->b_gath_pad[f], sizeof(uint32_t) * std::max<size_t>((size_t)maxc[f] * R, 1)))) return rc;
-        if ((rc = dev_ensure(c, c->b_gath[f], sizeof(uint32_t) * std::max<size_t>(total, 1)))) return rc;
+        V.gath_count[f] = (uint32_t)total;
+        if ((rc = dev_ensure(c, V.b_gath_pad[f], sizeof(uint32_t) * std::max<size_t>((size_t)maxc[f] * R, 1)))) return rc;
+        if ((rc = dev_ensure(c, V.b_gath[f], sizeof(uint32_t) * std::max<size_t>(total, 1)))) return rc;
         // the send buffer must hold maxc entries: visible lists are sized for every renderable node of THIS
         // shard, which may be fewer than another rank's count (rare: grow it with everything quiesced)
         if ((size_t)maxc[f] * sizeof(uint32_t) > V.b_vis[f].bytes) {
@@ -156,14 +160,16 @@ static int32_t allgather_finish(fyx_ctx *c, VisSlot &V, cudaStream_t s)
     }
     NC(nccl().GroupStart());
     for (uint32_t f = 0; f < nf; ++f)
-        if (maxc[f]) NC(nccl().AllGather(V.b_vis[f].p, c->b_gath_pad[f].p, maxc[f], ncclUint32, comm, s));
+        if (maxc[f]) NC(nccl().AllGather(V.b_vis[f].p, V.b_gath_pad[f].p, maxc[f], ncclUint32, comm, s));
     NC(nccl().GroupEnd());
     for (uint32_t f = 0; f < nf; ++f) {
-        launch_compact_gathered(s, c->b_gath_pad[f].as<uint32_t>(), maxc[f], c->b_counts_all.as<uint32_t>(), R, (int)f,
-                                c->b_gath[f].as<uint32_t>());
+        launch_compact_gathered(s, V.b_gath_pad[f].as<uint32_t>(), maxc[f], c->b_counts_all.as<uint32_t>(), R, (int)f,
+                                V.b_gath[f].as<uint32_t>());
         c->launches += maxc[f] ? 1 : 0;
     }
     CU(cudaGetLastError());
+    V.gathered = true;
+    V.gathered_on_host = false;
     return FYX_OK;
 }
 
@@ -174,36 +180,47 @@ extern "C" int32_t fyx_allgather_visible(fyx_ctx *c)
     VisSlot &V = c->vs[c->cur];
     if (!V.nf) return FYX_OK;
     CU(cudaSetDevice(c->device));
+    // order after any in-frame exchange of the other slot (it ran on the collective stream)
+    if (c->comm_stream && c->vs[c->cur ^ 1].gathered) CU(cudaStreamWaitEvent(c->stream, c->vs[c->cur ^ 1].ev_gather, 0));
     int32_t rc = allgather_begin(c, V, c->stream);
     if (rc) return rc;
-    return allgather_finish(c, V, c->stream);
+    rc = allgather_finish(c, V, c->stream);
+    if (rc) return rc;
+    CU(cudaEventRecord(V.ev_gather, c->stream));
+    return FYX_OK;
 }
 
 extern "C" int32_t fyx_get_visible_gathered_device(fyx_ctx *c, uint32_t f, const uint32_t **d_idx, uint32_t *out_count)
 {
     if (!c || !d_idx || !out_count) return FYX_ERR_INVALID_ARGUMENT;
-    if (f >= c->vs[c->cur].nf) return fail(c, FYX_ERR_INVALID_ARGUMENT, "frustum %u was not part of the last cull", f);
-    *d_idx = c->b_gath[f].as<uint32_t>();
-    *out_count = c->gath_count[f];
+    VisSlot &V = c->vs[c->cur];
+    if (f >= V.nf || !V.gathered) return fail(c, FYX_ERR_INVALID_ARGUMENT, "frustum %u has no gathered list", f);
+    *d_idx = V.b_gath[f].as<uint32_t>();
+    *out_count = V.gath_count[f];
     return FYX_OK;
 }
 
 extern "C" int32_t fyx_get_visible_gathered(fyx_ctx *c, uint32_t f, const uint32_t **out_idx, uint32_t *out_count)
 {
     if (!c || !out_idx || !out_count) return FYX_ERR_INVALID_ARGUMENT;
-    if (f >= c->vs[c->cur].nf) return fail(c, FYX_ERR_INVALID_ARGUMENT, "frustum %u was not part of the last cull", f);
+    VisSlot &V = c->vs[c->readable];
+    if (V.pending) return fail(c, FYX_ERR_STATE, "the frame is still in flight: call fyx_frame_wait first");
+    if (f >= V.nf || !V.gathered) return fail(c, FYX_ERR_INVALID_ARGUMENT, "frustum %u has no gathered list", f);
     CU(cudaSetDevice(c->device));
-    const size_t n = c->gath_count[f];
-    if (n > c->h_gath_cap[f]) {
-        if (c->h_gath[f]) cudaFreeHost(c->h_gath[f]);
-        c->h_gath[f] = nullptr;
-        const size_t cap = std::max<size_t>(1024, n + n / 2);
-        CU(cudaHostAlloc(reinterpret_cast<void **>(&c->h_gath[f]), cap * sizeof(uint32_t), cudaHostAllocDefault));
-        c->h_gath_cap[f] = cap;
+    const size_t n = V.gath_count[f];
+    if (!V.gathered_on_host) {
+        // bring all frusta at once (one synchronisation), after the collective stream has produced them
+        CU(cudaStreamWaitEvent(c->stream, V.ev_gather, 0));
+        for (uint32_t g = 0; g < V.nf; ++g) {
+            const size_t m = V.gath_count[g];
+            int32_t rc = host_gath_ensure(c, V, g, m);
+            if (rc) return rc;
+            if (m) CU(cudaMemcpyAsync(V.h_gath[g], V.b_gath[g].p, m * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+        }
+        CU(cudaStreamSynchronize(c->stream));
+        V.gathered_on_host = true;
     }
-    if (n) CU(cudaMemcpyAsync(c->h_gath[f], c->b_gath[f].p, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
-    CU(cudaStreamSynchronize(c->stream));
-    *out_idx = c->h_gath[f];
+    *out_idx = V.h_gath[f];
     *out_count = (uint32_t)n;
     return FYX_OK;
 }

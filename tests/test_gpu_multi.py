@@ -49,12 +49,18 @@ def _worker(rank, world, port, out_dir):
     ctx.comm_init(world, rank, uid)
     frusta = camera.cube_frusta()
     out = {}
-    for mode in ("fused", "separate"):
+    for mode in ("fused", "separate", "pipelined"):
         if mode == "fused":
             ctx.render_prep(update_flags=fb.UPDATE_ALL, frusta=frusta, readback_visible=False, allgather=True)
-        else:
+        elif mode == "separate":
             ctx.update_and_cull(frusta, fb.UPDATE_ALL)
             ctx.allgather_visible()
+        else:  # two frames in flight, gathered lists collected by fyx_frame_wait
+            for k in range(3):
+                ctx.render_prep(update_flags=fb.UPDATE_ALL, frusta=frusta, readback_visible=True, allgather=True, async_=True)
+                if k:
+                    ctx.frame_wait()
+            ctx.frame_wait()
         for f in range(len(frusta)):
             out[f"{mode}_{f}"] = np.sort(ctx.get_visible_gathered(f))
     np.savez(os.path.join(out_dir, f"rank{rank}.npz"), **out)
@@ -87,7 +93,7 @@ def test_sharded_gpu_cull_and_nccl_allgather_match_the_unsharded_oracle(tmp_path
     want = [np.sort(og.from_graph(fo)) for fo in fos]
     for r in range(world):
         z = np.load(os.path.join(str(tmp_path), f"rank{r}.npz"))
-        for mode in ("fused", "separate"):
+        for mode in ("fused", "separate", "pipelined"):
             for f in range(len(fos)):
                 got = z[f"{mode}_{f}"]
                 assert np.array_equal(got, want[f]), f"rank {r} {mode} frustum {f}: {got.size} vs {want[f].size}"

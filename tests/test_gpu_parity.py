@@ -558,3 +558,51 @@ def test_cpp_host_mirror_runs_the_reference_hierarchy_tests():
     assert r.returncode == 0, r.stdout + r.stderr
     r = subprocess.run([os.path.join(d, "test_host")], capture_output=True, text=True, timeout=120)
     assert r.returncode == 0 and r.stdout.strip() == "OK", r.stdout + r.stderr
+
+
+def test_topology_change_keeps_surfaces_and_flag_changes_resize_nothing(ctx):
+    """A second fyx_set_topology (nodes added / re-parented) with skinned surfaces already uploaded, and
+    fyx_set_flags turning pivots into renderable nodes, still match an oracle rebuilt from scratch."""
+    sc = Scene(8000, n_units=10, verts_per_unit=50)
+    og, sids = scene_pair(sc, ctx)
+    fo, ff = camera_frustum(zfar=500.0, fovy=np.deg2rad(100.0))
+    ctx.update_and_cull([ff], fb.UPDATE_ALL)
+    # grow the graph: 500 new meshes hanging under existing nodes, and move 100 old leaves under new parents
+    rng = np.random.default_rng(9)
+    n0, extra = sc.capacity, 500
+    parent = np.concatenate([sc.parent, rng.integers(0, n0, extra).astype(np.uint32)])
+    flags = np.concatenate([sc.flags, np.full(extra, fb.NODE_DEFAULT | fb.NODE_RENDERABLE, np.uint32)])
+    mask = np.concatenate([sc.render_mask, np.full(extra, 0xFFFFFFFF, np.uint32)])
+    local = np.concatenate([sc.local_m16, np.tile(ob.translation(1, 2, 3), (extra, 1))])
+    aabb = np.concatenate([sc.local_aabb, np.tile(np.array([-1, -1, -1, 1, 1, 1], np.float32), (extra, 1))])
+    for u in range(sc.n_units):  # keep the skinned meshes' vertex-derived boxes
+        aabb[sc.unit_mesh_node(u)] = sc.unit_vertices(u)[1]
+    movers = np.nonzero((sc.flags & fb.NODE_RENDERABLE) != 0)[0][:100]
+    parent[movers] = np.arange(n0, n0 + 100, dtype=np.uint32)  # old leaves under the new nodes (larger indices)
+    # every pivot becomes renderable through fyx_set_flags afterwards
+    piv = np.nonzero((flags & fb.NODE_RENDERABLE) == 0)[0].astype(np.uint32)
+    piv = piv[piv != 0]
+    flags2 = flags.copy()
+    flags2[piv] |= fb.NODE_RENDERABLE
+    og2 = ob.Graph.build(parent, flags2, mask, local, aabb)
+    for u in range(sc.n_units):
+        bones = sc.unit_bone_nodes(u)
+        for k, b in enumerate(bones):
+            og2.set_inv_bind(int(b), sc.unit_inv_bind(u)[k])
+        og2.add_surface(sc.unit_mesh_node(u), bones, sc.unit_vertices(u)[0])
+    og2.L.orc_graph_drop_messages(og2.h)
+    og2.update_hierarchical_data()
+    ctx.set_topology(parent, flags, mask, aabb)
+    ctx.set_local_matrices(local)
+    ctx.set_flags(flags2[piv], piv)
+    ctx.update_and_cull([ff], fb.UPDATE_INCREMENTAL)  # everything is marked changed by the new topology
+    # pivots of the oracle are Base nodes (unit box); the GPU got the same unit boxes from scenegen
+    reach = np.ones(len(parent), bool)
+    assert_same_hierarchy(og2, ctx, np.arange(len(parent), dtype=np.uint32)[(flags2 & fb.NODE_RENDERABLE) != 0][:3000])
+    assert_same_visible(og2, ctx, [fo])
+    ctx.build_palettes()
+    ctx.skin()
+    for u in (0, sc.n_units - 1):
+        pos_o, nrm_o = og2.skin(sc.unit_mesh_node(u), 0, sc.verts_per_unit)
+        pos_g, nrm_g = ctx.get_skinned(sids[u])
+        assert pos_g.tobytes() == pos_o.tobytes() and nrm_g.tobytes() == nrm_o.tobytes()
