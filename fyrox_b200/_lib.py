@@ -114,6 +114,7 @@ SYMBOLS = {
     "fyx_frustum_default": (None, [C.POINTER(fyx_frustum)]),
     "fyx_mat4_mul": (None, [f32p, f32p, f32p]),
     "fyx_set_topology": (C.c_int32, [ctx_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "fyx_set_dfs_order": (C.c_int32, [ctx_p, C.c_uint32, C.c_void_p]),
     "fyx_set_local_matrices": (C.c_int32, [ctx_p, C.c_uint32, C.c_void_p, C.c_void_p]),
     "fyx_set_local_trs": (C.c_int32, [ctx_p, C.c_uint32, C.c_void_p, C.c_void_p]),
     "fyx_set_transform_statics": (C.c_int32, [ctx_p, C.c_uint32, C.c_void_p, C.c_void_p]),

@@ -160,6 +160,11 @@ class Context:
         self._chk(self._lib.fyx_set_topology(self._h, n, root, _ptr(parent), _ptr(flags), _ptr(render_mask), _ptr(local_aabb), _ptr(global_index)))
         self.n_nodes = n
 
+    def set_dfs_order(self, preorder_rank):
+        """Pre-order DFS rank of every node (children order of the host graph); None clears it."""
+        r = _u32(preorder_rank)
+        self._chk(self._lib.fyx_set_dfs_order(self._h, 0 if r is None else r.size, _ptr(r)))
+
     def set_local_matrices(self, m16, idx=None):
         m16 = _f32(m16)
         idx = _u32(idx)

@@ -109,7 +109,9 @@ struct fyx_ctx {
     uint64_t vert_cap = 0;
     uint32_t n_entries = 0, entry_cap = 0;
     DevBuf b_vblk, b_opos, b_onrm, b_ib[3], b_palette, b_bone_slot, b_tiles;
-    DevBuf b_fold_node, b_fold_begin, b_fold_bone;
+    DevBuf b_fold_node, b_fold_begin, b_fold_bone, b_fold_stale_idx, b_late_slot, b_stale_pos;
+    std::vector<uint32_t> dfs_rank; // optional: pre-order rank of every node in the reference's DFS (fyx_set_dfs_order)
+    uint32_t n_late = 0;
     uint32_t n_tiles = 0, max_bones = 0;
     FoldArrays fold{};
     SkinArrays sk{};
@@ -347,6 +349,10 @@ int32_t run_update(fyx_ctx *c, uint32_t update_flags, const CullParams *cull)
 {
     const bool all = (update_flags & FYX_UPDATE_ALL) || !c->updated_once;
     const size_t nl = c->level_off.size() ? c->level_off.size() - 1 : 0;
+    if (c->n_late) {
+        launch_snapshot_bones(c->stream, c->a, c->n_late, c->b_late_slot.as<uint32_t>(), c->b_stale_pos.as<float4>());
+        c->launches++;
+    }
     for (size_t l = 0; l < nl; ++l) {
         launch_update_level(c->stream, c->a, c->level_off[l], c->level_off[l + 1], all, cull);
         c->launches += (c->level_off[l + 1] > c->level_off[l]);
@@ -503,7 +509,7 @@ extern "C" void fyx_destroy(fyx_ctx *c)
     fyx_comm_destroy_internal(c);
     DevBuf *bufs[] = {&c->b_parent, &c->b_flags, &c->b_mask, &c->b_gidx, &c->b_slot_of_node, &c->d_stage, &c->b_statics, &c->b_vblk,
                       &c->b_opos, &c->b_onrm, &c->b_palette, &c->b_bone_slot, &c->b_tiles, &c->b_fold_node,
-                      &c->b_fold_begin, &c->b_fold_bone, &c->b_counts_packed, &c->b_counts_all};
+                      &c->b_fold_begin, &c->b_fold_bone, &c->b_fold_stale_idx, &c->b_late_slot, &c->b_stale_pos, &c->b_counts_packed, &c->b_counts_all};
     for (DevBuf *b : bufs) dev_free(*b);
     for (int i = 0; i < 3; ++i) {
         dev_free(c->b_L[i]);
@@ -800,8 +806,20 @@ extern "C" int32_t fyx_set_topology(fyx_ctx *c, uint32_t capacity, uint32_t root
     c->have_topology = true;
     c->updated_once = false;
     c->have_statics = false; // slots moved: the caller re-sends non-default statics after a topology change
+    c->dfs_rank.clear();     // ... and the DFS order, if it uses it
     c->tables_dirty = true; // bone slots depend on the slot order
     rebuild_node_arrays(c);
+    return FYX_OK;
+}
+
+extern "C" int32_t fyx_set_dfs_order(fyx_ctx *c, uint32_t capacity, const uint32_t *preorder_rank)
+{
+    if (!c) return FYX_ERR_INVALID_ARGUMENT;
+    if (!c->have_topology) return fail(c, FYX_ERR_STATE, "fyx_set_topology has not been called");
+    if (preorder_rank && capacity != c->n_nodes) return fail(c, FYX_ERR_INVALID_ARGUMENT, "capacity %u != topology capacity %u", capacity, c->n_nodes);
+    if (preorder_rank) c->dfs_rank.assign(preorder_rank, preorder_rank + capacity);
+    else c->dfs_rank.clear();
+    c->tables_dirty = true;
     return FYX_OK;
 }
 
@@ -961,7 +979,8 @@ int32_t commit_surfaces(fyx_ctx *c)
     // per skinned node: bones of all its surfaces in surface order
     std::vector<uint32_t> fold_node, fold_begin, fold_bone;
     std::vector<int64_t> fold_of_node; // node → index in fold_node, built in first-surface order
-    std::vector<std::vector<uint32_t>> per_node_bones;
+    std::vector<std::vector<uint32_t>> per_node_bones, per_node_bone_nodes;
+    std::vector<uint32_t> fold_mesh_node;
     fold_of_node.assign(c->n_nodes, -1);
     for (size_t s = 0; s < ns; ++s) {
         const Surface &sf = c->surfaces[s];
@@ -987,13 +1006,31 @@ int32_t commit_surfaces(fyx_ctx *c)
             if (fi < 0) {
                 fi = (int64_t)per_node_bones.size();
                 per_node_bones.emplace_back();
+                per_node_bone_nodes.emplace_back();
                 fold_node.push_back(c->slot_of_node[sf.mesh_node]);
+                fold_mesh_node.push_back(sf.mesh_node);
             }
-            for (uint32_t b = 0; b < sf.n_bones; ++b) per_node_bones[fi].push_back(bone_slot[sf.bone_off + b]);
+            for (uint32_t b = 0; b < sf.n_bones; ++b) {
+                per_node_bones[fi].push_back(bone_slot[sf.bone_off + b]);
+                per_node_bone_nodes[fi].push_back(sf.bones[b]);
+            }
         }
     }
     fold_begin.push_back(0);
-    for (auto &v : per_node_bones) {
+    // bones visited after their mesh by the reference's DFS (needs fyx_set_dfs_order) keep their pre-update position
+    std::vector<uint32_t> stale_idx, late_slot;
+    const bool have_rank = c->dfs_rank.size() == c->n_nodes && c->n_nodes > 0;
+    for (size_t m = 0; m < per_node_bones.size(); ++m) {
+        const auto &v = per_node_bones[m];
+        for (size_t k = 0; k < v.size(); ++k) {
+            uint32_t si = FYX_NONE;
+            const uint32_t bn = per_node_bone_nodes[m][k];
+            if (have_rank && v[k] != FYX_NONE && c->dfs_rank[bn] > c->dfs_rank[fold_mesh_node[m]]) {
+                si = (uint32_t)late_slot.size();
+                late_slot.push_back(v[k]);
+            }
+            stale_idx.push_back(si);
+        }
         fold_bone.insert(fold_bone.end(), v.begin(), v.end());
         fold_begin.push_back((uint32_t)fold_bone.size());
     }
@@ -1017,6 +1054,18 @@ int32_t commit_surfaces(fyx_ctx *c)
     c->fold.node_slot = c->b_fold_node.as<uint32_t>();
     c->fold.bone_begin = c->b_fold_begin.as<uint32_t>();
     c->fold.bone_slot = c->b_fold_bone.as<uint32_t>();
+    c->n_late = (uint32_t)late_slot.size();
+    c->fold.stale_idx = nullptr;
+    c->fold.stale_pos = nullptr;
+    if (c->n_late) {
+        if ((rc = dev_ensure(c, c->b_fold_stale_idx, stale_idx.size() * 4))) return rc;
+        if ((rc = dev_ensure(c, c->b_late_slot, late_slot.size() * 4))) return rc;
+        if ((rc = dev_ensure(c, c->b_stale_pos, late_slot.size() * sizeof(float4)))) return rc;
+        CU(cudaMemcpy(c->b_fold_stale_idx.p, stale_idx.data(), stale_idx.size() * 4, cudaMemcpyHostToDevice));
+        CU(cudaMemcpy(c->b_late_slot.p, late_slot.data(), late_slot.size() * 4, cudaMemcpyHostToDevice));
+        c->fold.stale_idx = c->b_fold_stale_idx.as<uint32_t>();
+        c->fold.stale_pos = c->b_stale_pos.as<float4>();
+    }
     rebuild_skin_arrays(c);
     c->tables_dirty = false;
     return FYX_OK;

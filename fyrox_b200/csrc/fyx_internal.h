@@ -71,6 +71,10 @@ struct FoldArrays {
     const uint32_t *node_slot;
     const uint32_t *bone_begin; // n+1 offsets into bone_slot
     const uint32_t *bone_slot;  // bones of all skinned surfaces of the node, in surface order
+    // bones the reference's DFS visits AFTER their mesh contribute the position they had before this update
+    // (scene/mesh/mod.rs:676-682 reads the stored value): per entry an index into stale_pos, FYX_NONE = use the new one
+    const uint32_t *stale_idx;  // nullptr when no such bone exists
+    const float4 *stale_pos;
 };
 
 // ---- launchers (fyx_kernels.cu) ----
@@ -78,6 +82,7 @@ void launch_update_level(cudaStream_t s, const NodeArrays &a, uint32_t lo, uint3
                          const CullParams *cull /* nullptr = no fused cull */);
 void launch_cull(cudaStream_t s, const NodeArrays &a, const CullParams &cp);
 void launch_fold_bones(cudaStream_t s, const NodeArrays &a, const FoldArrays &fa, const CullParams *cull);
+void launch_snapshot_bones(cudaStream_t s, const NodeArrays &a, uint32_t n_late, const uint32_t *late_slot, float4 *stale_pos);
 void launch_palette(cudaStream_t s, const NodeArrays &a, const SkinArrays &sk);
 void launch_skin(cudaStream_t s, const SkinArrays &sk, const SkinTile *tiles, uint32_t n_tiles, uint32_t max_bones);
 

@@ -249,7 +249,14 @@ __global__ void __launch_bounds__(kBlock) k_fold_bones(const NodeArrays a, const
             for (uint32_t b = b0 + lane; b < b1; b += 32) {
                 const uint32_t bs = fa.bone_slot[b];
                 if (bs == FYX_NONE) continue; // try_borrow failed ⇒ skipped
-                const float px = a.G[0][bs].w, py = a.G[1][bs].w, pz = a.G[2][bs].w; // global_position()
+                float px, py, pz; // global_position()
+                const uint32_t si = fa.stale_idx ? fa.stale_idx[b] : FYX_NONE;
+                if (si != FYX_NONE) { // visited after the mesh by the reference's DFS: its value from before this update
+                    const float4 o = fa.stale_pos[si];
+                    px = o.x; py = o.y; pz = o.z;
+                } else {
+                    px = a.G[0][bs].w; py = a.G[1][bs].w; pz = a.G[2][bs].w;
+                }
                 const uint32_t key = b - b0 + 1u;
                 // within a lane keys increase, so the strict compares keep the earliest of equal values
                 if (px < mnx) { mnx = px; kmnx = key; }
@@ -283,6 +290,16 @@ __global__ void __launch_bounds__(kBlock) k_fold_bones(const NodeArrays a, const
         }
     }
     if (FUSE) compact_emit(vis_bits, gi, cp);
+}
+
+// positions of the "late" bones (see FoldArrays) as stored before the update starts
+__global__ void __launch_bounds__(kBlock) k_snapshot_bones(const NodeArrays a, const uint32_t n_late, const uint32_t *late_slot,
+                                                           float4 *stale_pos)
+{
+    const uint32_t e = blockIdx.x * kBlock + threadIdx.x;
+    if (e >= n_late) return;
+    const uint32_t s = late_slot[e];
+    stale_pos[e] = make_float4(a.G[0][s].w, a.G[1][s].w, a.G[2][s].w, 0.0f);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -823,6 +840,12 @@ void launch_fold_bones(cudaStream_t s, const NodeArrays &a, const FoldArrays &fa
         none.nf = 0;
         k_fold_bones<false><<<grid, kBlock, 0, s>>>(a, fa, none);
     }
+}
+
+void launch_snapshot_bones(cudaStream_t s, const NodeArrays &a, uint32_t n_late, const uint32_t *late_slot, float4 *stale_pos)
+{
+    if (!n_late) return;
+    k_snapshot_bones<<<grid_for(n_late), kBlock, 0, s>>>(a, n_late, late_slot, stale_pos);
 }
 
 void launch_palette(cudaStream_t s, const NodeArrays &a, const SkinArrays &sk)

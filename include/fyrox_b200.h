@@ -142,6 +142,15 @@ int32_t fyx_set_topology(fyx_ctx *ctx, uint32_t capacity, uint32_t root, const u
                          const uint32_t *flags, const uint32_t *render_mask, const float *local_aabb_minmax,
                          const uint32_t *global_index);
 
+/* Optional.  preorder_rank[i] = position of node i in the pre-order DFS from the root in `children` order — the
+ * order Graph::update_global_transform_recursively visits nodes (scene/graph/mod.rs:1199-1241).  Only one thing
+ * depends on it: Mesh::on_global_transform_changed (scene/mesh/mod.rs:676-682) folds each bone's position AS STORED
+ * when the mesh is visited, so a bone that comes later in that order contributes its position from before the
+ * update.  With the order given, such bones are snapshotted before every update and the skinned-mesh boxes equal
+ * the reference's; without it (or NULL) every bone contributes its new position — identical whenever skeletons
+ * precede their meshes.  Reset by fyx_set_topology. */
+int32_t fyx_set_dfs_order(fyx_ctx *ctx, uint32_t capacity, const uint32_t *preorder_rank);
+
 /* Transform::matrix() of `count` nodes (scene/transform.rs:544-550); idx NULL = nodes 0..count-1.
  * Equivalent of `local_transform_mut()` → NodeMessageKind::TransformChanged (scene/base.rs:343-352). */
 int32_t fyx_set_local_matrices(fyx_ctx *ctx, uint32_t count, const uint32_t *idx, const float *m16_colmajor);

@@ -606,3 +606,102 @@ def test_topology_change_keeps_surfaces_and_flag_changes_resize_nothing(ctx):
         pos_o, nrm_o = og2.skin(sc.unit_mesh_node(u), 0, sc.verts_per_unit)
         pos_g, nrm_g = ctx.get_skinned(sids[u])
         assert pos_g.tobytes() == pos_o.tobytes() and nrm_g.tobytes() == nrm_o.tobytes()
+
+
+def _preorder_rank(parent):
+    """Pre-order DFS rank from node 0 with children in index order (what ob.Graph.build produces)."""
+    n = len(parent)
+    kids = [[] for _ in range(n)]
+    for i in range(1, n):
+        if parent[i] != NONE:
+            kids[int(parent[i])].append(i)
+    rank = np.full(n, NONE, np.uint32)
+    stack, r = [0], 0
+    while stack:
+        x = stack.pop()
+        rank[x] = r
+        r += 1
+        stack.extend(reversed(kids[x]))
+    return rank
+
+
+def test_dfs_order_quirk_is_reproduced_exactly(ctx):
+    """Skinned meshes that come BEFORE (some of) their bones in the reference's DFS: the reference folds those
+    bones' positions from before the update (scene/mesh/mod.rs:676-682).  With fyx_set_dfs_order the boxes
+    match the oracle's real DFS over several frames, full and incremental updates."""
+    rng = np.random.default_rng(33)
+    n_units, nb = 40, 12
+    # per unit: mesh first, then its bones (chain), all under the root => every bone is "late"; every second unit
+    # the other way round (bones first)
+    parent, flags, surf = [NONE], [fb.NODE_DEFAULT], []
+    for u in range(n_units):
+        base = len(parent)
+        if u % 2 == 0:
+            mesh = base
+            parent.append(0)
+            flags.append(fb.NODE_DEFAULT | fb.NODE_RENDERABLE)
+            bones = list(range(base + 1, base + 1 + nb))
+            for k in range(nb):
+                parent.append(0 if k == 0 else bones[k - 1])
+                flags.append(fb.NODE_DEFAULT)
+        else:
+            bones = list(range(base, base + nb))
+            for k in range(nb):
+                parent.append(0 if k == 0 else bones[k - 1])
+                flags.append(fb.NODE_DEFAULT)
+            mesh = base + nb
+            parent.append(0)
+            flags.append(fb.NODE_DEFAULT | fb.NODE_RENDERABLE)
+        surf.append((mesh, bones))
+    parent = np.array(parent, np.uint32)
+    flags = np.array(flags, np.uint32)
+    n = len(parent)
+    aabb = np.tile(UNIT_BOX, (n, 1))
+
+    def random_locals():
+        m = np.tile(np.eye(4, dtype=np.float32).reshape(16), (n, 1))
+        m[1:, 12:15] = rng.uniform(-6, 6, (n - 1, 3)).astype(np.float32)
+        return m
+
+    local = random_locals()
+    og = ob.Graph.build(parent, flags, None, local, aabb)
+    ctx.set_topology(parent, flags, None, aabb)
+    ctx.set_dfs_order(_preorder_rank(parent))
+    ctx.set_local_matrices(local)
+    meshes = np.array([m for m, _ in surf], np.uint32)
+    for mesh, bones in surf:
+        og.add_surface(mesh, bones)
+        ctx.add_skinned_surface(mesh, bones, np.tile(np.eye(4, dtype=np.float32).reshape(16), (nb, 1)))
+    og.L.orc_graph_drop_messages(og.h)
+    fo, ff = camera_frustum(zfar=400.0)
+    for frame in range(4):
+        if frame:
+            local = random_locals()
+            for i in range(1, n):
+                og.set_local_matrix(i, local[i])
+            ctx.set_local_matrices(local[1:], np.arange(1, n, dtype=np.uint32))
+        if frame % 2 == 0:
+            og.L.orc_graph_drop_messages(og.h)
+            og.update_hierarchical_data()
+            ctx.update_and_cull([ff], fb.UPDATE_ALL)
+        else:
+            # one message root (the scene root): a single DFS, like the full update
+            og.L.orc_graph_drop_messages(og.h)
+            og.set_local_matrix(0, np.eye(4, dtype=np.float32).reshape(16))
+            ctx.set_local_matrices(np.eye(4, dtype=np.float32).reshape(1, 16), [0])
+            og.update()
+            ctx.update_and_cull([ff], fb.UPDATE_INCREMENTAL)
+        assert_same_hierarchy(og, ctx)
+        assert_same_visible(og, ctx, [fo])
+    # sanity: the quirk is real — without the order the late-bone meshes differ from the reference
+    ctx.set_dfs_order(None)
+    local = random_locals()
+    for i in range(1, n):
+        og.set_local_matrix(i, local[i])
+    og.L.orc_graph_drop_messages(og.h)
+    og.update_hierarchical_data()
+    ctx.set_local_matrices(local[1:], np.arange(1, n, dtype=np.uint32))
+    ctx.update_transforms(fb.UPDATE_ALL)
+    A, Ao = ctx.get_world_aabbs(meshes), og.world_bounding_boxes(meshes)
+    early = np.arange(n_units) % 2 == 1
+    assert (A[early] == Ao[early]).all() and not (A[~early] == Ao[~early]).all()
