@@ -49,6 +49,8 @@ B_NODE_FUSED = 188
 B_VISIBLE = 4
 B_BONE = 196
 B_VERT = 68
+UPLOAD_FIELD = {"rot": "changed_rot", "trs": "changed_trs", "m16": "changed_m16"}
+UPLOAD_BYTES = {"rot": 16, "trs": 40, "m16": 64}
 
 
 def peaks():
@@ -302,13 +304,22 @@ def run_cuda(args):
     n_bones = sc.n_units * BONES
 
     # per-frame host inputs: two animation frames in pinned memory, alternated
-    # upload format of the changed bones: "trs" = position/rotation/scale records (40 B; the device evaluates
-    # Transform::calculate_local_transform — SURVEY §8f N1), "m16" = the 64-byte matrices
+    # upload format of the changed bones: "rot" = the rotations the animation rewrote (16 B; position / scale stay on the
+    # device), "trs" = position/rotation/scale records (40 B) — the device evaluates Transform::calculate_local_transform
+    #  in both — or "m16" = the 64-byte matrices
     anim = []
     if n_bones:
         for fr in range(2):
             pi = fb.PinnedBuffer((n_bones,), np.uint32)
-            if args.upload == "trs":
+            if args.upload == "rot":
+                full = fb.PinnedBuffer((n_bones, 10), np.float32)
+                sc.animate_trs_into(fr, pi.ptr, full.ptr)
+                if fr == 0:
+                    ctx.set_local_trs(full.array, pi.array)  # the device keeps every bone's position / scale from here on
+                pm = fb.PinnedBuffer((n_bones, 4), np.float32)
+                pm.array[:] = full.array[:, 3:7]
+                full.free()
+            elif args.upload == "trs":
                 pm = fb.PinnedBuffer((n_bones, 10), np.float32)
                 sc.animate_trs_into(fr, pi.ptr, pm.ptr)
             else:
@@ -327,7 +338,7 @@ def run_cuda(args):
         kw = dict(update_flags=fb.UPDATE_ALL, frusta=frusta, readback_visible=True, async_=pipelined, allgather=(world > 1))
         if anim:
             pi, pm = anim[i & 1]
-            kw.update(changed_idx=pi.ptr, n_changed=n_bones, **({"changed_trs": pm.ptr} if args.upload == "trs" else {"changed_m16": pm.ptr}))
+            kw.update(changed_idx=pi.ptr, n_changed=n_bones, **{UPLOAD_FIELD[args.upload]: pm.ptr})
         ctx.render_prep(**kw)
 
     def collect_e2e():
@@ -399,7 +410,7 @@ def run_cuda(args):
         def inc_frames(steps):
             for i in range(steps):
                 pi, pm = anim[i & 1]
-                kw = {"changed_trs": pm.ptr} if args.upload == "trs" else {"changed_m16": pm.ptr}
+                kw = {UPLOAD_FIELD[args.upload]: pm.ptr}
                 ctx.render_prep(update_flags=fb.UPDATE_INCREMENTAL, changed_idx=pi.ptr, n_changed=n_bones, frusta=frusta,
                                 readback_visible=True, async_=True, **kw)
                 if i:
@@ -415,7 +426,7 @@ def run_cuda(args):
     value = units_all / (ms_per_step * 1e-3)
     e2e_value = units_all / (e2e_ms_per_step * 1e-3)
     sum_vis = sum(vis_counts)
-    h2d = n_bones * ((40 if args.upload == "trs" else 64) + 4)  # frusta travel as kernel parameters
+    h2d = n_bones * (UPLOAD_BYTES[args.upload] + 4)  # frusta travel as kernel parameters
     d2h = 4 * len(frusta) + 4 * sum_vis  # per rank: at N > 1 every rank reads back the whole gathered lists
 
     peak, peak_src = peaks()
@@ -460,7 +471,7 @@ def run_cuda(args):
         "nodes_per_s": w["nodes"] * world / (ms_per_step * 1e-3), "verts_per_s": w["units"] * w["verts_per_unit"] * world / (ms_per_step * 1e-3),
         "clocks": clk,
         "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms_per_step, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "api": "fyx_render_prep (C ABI) with pinned host buffers: changed bone " + ("TRS records (40 B)" if args.upload == "trs" else "matrices (64 B)") + " up, visible lists down",
+                "api": "fyx_render_prep (C ABI) with pinned host buffers: changed bone " + {"rot": "rotations (16 B)", "trs": "TRS records (40 B)", "m16": "matrices (64 B)"}[args.upload] + " up, visible lists down",
                 "mode": "pipelined (2 frames in flight, fyx_frame_wait)" if e2e_pipe_ms < e2e_sync_ms else "synchronous",
                 "ms_per_step_synchronous": e2e_sync_ms / args.steps, "ms_per_step_pipelined": e2e_pipe_ms / args.steps},
         "gpu_launches": int(launches),
@@ -495,7 +506,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
     ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
-    ap.add_argument("--upload", default="trs", choices=["trs", "m16"], help="per-frame upload format of the changed bones")
+    ap.add_argument("--upload", default="rot", choices=["rot", "trs", "m16"], help="per-frame upload format of the changed bones")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--verbose", action="store_true")
     args = ap.parse_args()

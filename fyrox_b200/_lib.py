@@ -89,6 +89,7 @@ class fyx_frame_desc(C.Structure):
         ("changed_idx", C.c_void_p),
         ("changed_m16", C.c_void_p),
         ("changed_trs", C.c_void_p),
+        ("changed_rot", C.c_void_p),
         ("n_frusta", C.c_uint32),
         ("frusta", C.POINTER(fyx_frustum)),
         ("cam_mask", C.c_void_p),
@@ -117,6 +118,7 @@ SYMBOLS = {
     "fyx_set_dfs_order": (C.c_int32, [ctx_p, C.c_uint32, C.c_void_p]),
     "fyx_set_local_matrices": (C.c_int32, [ctx_p, C.c_uint32, C.c_void_p, C.c_void_p]),
     "fyx_set_local_trs": (C.c_int32, [ctx_p, C.c_uint32, C.c_void_p, C.c_void_p]),
+    "fyx_set_local_rotations": (C.c_int32, [ctx_p, C.c_uint32, C.c_void_p, C.c_void_p]),
     "fyx_set_transform_statics": (C.c_int32, [ctx_p, C.c_uint32, C.c_void_p, C.c_void_p]),
     "fyx_set_flags": (C.c_int32, [ctx_p, C.c_uint32, C.c_void_p, C.c_void_p]),
     "fyx_set_render_masks": (C.c_int32, [ctx_p, C.c_uint32, C.c_void_p, C.c_void_p]),

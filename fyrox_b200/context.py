@@ -180,6 +180,14 @@ class Context:
         assert idx is None or idx.size == count
         self._chk(self._lib.fyx_set_local_trs(self._h, count, _ptr(idx), _ptr(trs)))
 
+    def set_local_rotations(self, quats, idx=None):
+        """quats: (count, 4) f32 unit quaternions i,j,k,w; position/scale stay what the last set_local_trs sent."""
+        q = _f32(quats)
+        idx = _u32(idx)
+        count = q.size // 4
+        assert idx is None or idx.size == count
+        self._chk(self._lib.fyx_set_local_rotations(self._h, count, _ptr(idx), _ptr(q)))
+
     def set_transform_statics(self, statics, idx=None):
         """statics: (count, 25) f32 rows: pre_rotation ijkw, post_rotation_matrix (9, column-major), rotation_offset,
         rotation_pivot, scaling_offset, scaling_pivot (fyx_transform_statics)."""
@@ -275,14 +283,19 @@ class Context:
     def skin(self):
         self._chk(self._lib.fyx_skin(self._h))
 
-    def render_prep(self, *, update_flags=L.UPDATE_INCREMENTAL, changed_m16=None, changed_trs=None, changed_idx=None, n_changed=None, frusta=(), cam_mask=None,
+    def render_prep(self, *, update_flags=L.UPDATE_INCREMENTAL, changed_m16=None, changed_trs=None, changed_rot=None, changed_idx=None, n_changed=None, frusta=(), cam_mask=None,
                     pass_flags=None, do_palettes=True, do_skin=True, readback_visible=True, async_=False, allgather=False):
         """One frame (fyx_render_prep). changed_m16 / changed_idx may be numpy arrays or raw (pinned) addresses."""
         d = L.fyx_frame_desc()
         d.struct_size = C.sizeof(L.fyx_frame_desc)
         d.update_flags = update_flags
         keep = []
-        payload, width, field = (changed_trs, 10, "changed_trs") if changed_trs is not None else (changed_m16, 16, "changed_m16")
+        if changed_rot is not None:
+            payload, width, field = changed_rot, 4, "changed_rot"
+        elif changed_trs is not None:
+            payload, width, field = changed_trs, 10, "changed_trs"
+        else:
+            payload, width, field = changed_m16, 16, "changed_m16"
         if payload is not None:
             if isinstance(payload, np.ndarray):
                 m = _f32(payload)

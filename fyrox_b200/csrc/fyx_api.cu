@@ -77,6 +77,8 @@ struct fyx_ctx {
     bool have_topology = false, updated_once = false;
     DevBuf b_statics; // fyx_transform_statics per slot, allocated by the first fyx_set_transform_statics
     bool have_statics = false;
+    DevBuf b_trs;     // fyx_trs per slot: the last position/rotation/scale sent for each node (first TRS call allocates)
+    bool have_trs = false;
 
     // error word written by kernels
     uint32_t *d_err = nullptr;
@@ -507,7 +509,7 @@ extern "C" void fyx_destroy(fyx_ctx *c)
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     fyx_comm_destroy_internal(c);
-    DevBuf *bufs[] = {&c->b_parent, &c->b_flags, &c->b_mask, &c->b_gidx, &c->b_slot_of_node, &c->d_stage, &c->b_statics, &c->b_vblk,
+    DevBuf *bufs[] = {&c->b_parent, &c->b_flags, &c->b_mask, &c->b_gidx, &c->b_slot_of_node, &c->d_stage, &c->b_statics, &c->b_trs, &c->b_vblk,
                       &c->b_opos, &c->b_onrm, &c->b_palette, &c->b_bone_slot, &c->b_tiles, &c->b_fold_node,
                       &c->b_fold_begin, &c->b_fold_bone, &c->b_fold_stale_idx, &c->b_late_slot, &c->b_stale_pos, &c->b_counts_packed, &c->b_counts_all};
     for (DevBuf *b : bufs) dev_free(*b);
@@ -807,6 +809,7 @@ extern "C" int32_t fyx_set_topology(fyx_ctx *c, uint32_t capacity, uint32_t root
     c->updated_once = false;
     c->have_statics = false; // slots moved: the caller re-sends non-default statics after a topology change
     c->dfs_rank.clear();     // ... and the DFS order, if it uses it
+    c->have_trs = false;     // ... and full TRS records before the next rotation-only update
     c->tables_dirty = true; // bone slots depend on the slot order
     rebuild_node_arrays(c);
     return FYX_OK;
@@ -840,6 +843,37 @@ extern "C" int32_t fyx_set_local_matrices(fyx_ctx *c, uint32_t count, const uint
     return FYX_OK;
 }
 
+static int32_t ensure_trs_store(fyx_ctx *c)
+{
+    if (c->have_trs) return FYX_OK;
+    int32_t rc = dev_ensure(c, c->b_trs, std::max<size_t>(c->n_slots, 1) * sizeof(fyx_trs));
+    if (rc) return rc;
+    launch_fill_identity_trs(c->stream, c->b_trs.as<fyx_trs>(), c->n_slots);
+    c->launches++;
+    c->have_trs = true;
+    return FYX_OK;
+}
+
+extern "C" int32_t fyx_set_local_rotations(fyx_ctx *c, uint32_t count, const uint32_t *idx, const float *quat_ijkw)
+{
+    if (!c) return FYX_ERR_INVALID_ARGUMENT;
+    if (!c->have_topology) return fail(c, FYX_ERR_STATE, "fyx_set_topology has not been called");
+    if (!count) return FYX_OK;
+    if (!quat_ijkw) return fail(c, FYX_ERR_INVALID_ARGUMENT, "rotations are NULL");
+    CU(cudaSetDevice(c->device));
+    int32_t rc = ensure_trs_store(c);
+    if (rc) return rc;
+    void *d_q = nullptr, *d_i = nullptr;
+    rc = stage_to_device(c, quat_ijkw, (size_t)count * 16, idx, idx ? (size_t)count * 4 : 0, false, &d_q, &d_i);
+    if (rc) return rc;
+    launch_scatter_trs(c->stream, c->a, count, static_cast<const uint32_t *>(d_i), d_q, true, c->b_trs.as<fyx_trs>(),
+                       c->have_statics ? c->b_statics.as<fyx_transform_statics>() : nullptr, c->b_slot_of_node.as<uint32_t>(), c->n_nodes,
+                       c->d_err);
+    c->launches++;
+    CU(cudaGetLastError());
+    return FYX_OK;
+}
+
 extern "C" int32_t fyx_set_local_trs(fyx_ctx *c, uint32_t count, const uint32_t *idx, const fyx_trs *trs)
 {
     if (!c) return FYX_ERR_INVALID_ARGUMENT;
@@ -847,10 +881,12 @@ extern "C" int32_t fyx_set_local_trs(fyx_ctx *c, uint32_t count, const uint32_t 
     if (!count) return FYX_OK;
     if (!trs) return fail(c, FYX_ERR_INVALID_ARGUMENT, "trs is NULL");
     CU(cudaSetDevice(c->device));
-    void *d_t = nullptr, *d_i = nullptr;
-    int32_t rc = stage_to_device(c, trs, (size_t)count * sizeof(fyx_trs), idx, idx ? (size_t)count * 4 : 0, false, &d_t, &d_i);
+    int32_t rc = ensure_trs_store(c);
     if (rc) return rc;
-    launch_scatter_trs(c->stream, c->a, count, static_cast<const uint32_t *>(d_i), static_cast<const fyx_trs *>(d_t),
+    void *d_t = nullptr, *d_i = nullptr;
+    rc = stage_to_device(c, trs, (size_t)count * sizeof(fyx_trs), idx, idx ? (size_t)count * 4 : 0, false, &d_t, &d_i);
+    if (rc) return rc;
+    launch_scatter_trs(c->stream, c->a, count, static_cast<const uint32_t *>(d_i), d_t, false, c->b_trs.as<fyx_trs>(),
                        c->have_statics ? c->b_statics.as<fyx_transform_statics>() : nullptr, c->b_slot_of_node.as<uint32_t>(), c->n_nodes,
                        c->d_err);
     c->launches++;
@@ -1306,14 +1342,19 @@ extern "C" int32_t fyx_render_prep(fyx_ctx *c, const fyx_frame_desc *fr)
     //    the frame is synchronised / waited for).  Async frames upload on the copy stream into alternating
     //    staging buffers, so the H2D of frame i+1 overlaps the kernels of frame i.
     if (fr->n_changed) {
-        const bool as_trs = fr->changed_trs != nullptr;
-        const void *payload = as_trs ? static_cast<const void *>(fr->changed_trs) : static_cast<const void *>(fr->changed_m16);
-        if (!payload) return fail(c, FYX_ERR_INVALID_ARGUMENT, "changed_m16 / changed_trs is NULL");
-        const size_t mb = (size_t)fr->n_changed * (as_trs ? sizeof(fyx_trs) : 64), ib = fr->changed_idx ? (size_t)fr->n_changed * 4 : 0;
+        const bool as_rot = fr->changed_rot != nullptr, as_trs = !as_rot && fr->changed_trs != nullptr;
+        const void *payload = as_rot ? static_cast<const void *>(fr->changed_rot)
+                                     : (as_trs ? static_cast<const void *>(fr->changed_trs) : static_cast<const void *>(fr->changed_m16));
+        if (!payload) return fail(c, FYX_ERR_INVALID_ARGUMENT, "changed_m16 / changed_trs / changed_rot is NULL");
+        if (as_rot || as_trs) {
+            rc = ensure_trs_store(c);
+            if (rc) return rc;
+        }
+        const size_t mb = (size_t)fr->n_changed * (as_rot ? 16 : (as_trs ? sizeof(fyx_trs) : 64)), ib = fr->changed_idx ? (size_t)fr->n_changed * 4 : 0;
         const fyx_transform_statics *st = c->have_statics ? c->b_statics.as<fyx_transform_statics>() : nullptr;
         auto scatter = [&](const void *d_p, const uint32_t *d_i) {
-            if (as_trs)
-                launch_scatter_trs(s, c->a, fr->n_changed, d_i, static_cast<const fyx_trs *>(d_p), st, c->b_slot_of_node.as<uint32_t>(),
+            if (as_rot || as_trs)
+                launch_scatter_trs(s, c->a, fr->n_changed, d_i, d_p, as_rot, c->b_trs.as<fyx_trs>(), st, c->b_slot_of_node.as<uint32_t>(),
                                    c->n_nodes, c->d_err);
             else
                 launch_scatter_locals(s, c->a, fr->n_changed, d_i, static_cast<const float *>(d_p), c->b_slot_of_node.as<uint32_t>(),

@@ -88,9 +88,11 @@ void launch_skin(cudaStream_t s, const SkinArrays &sk, const SkinTile *tiles, ui
 
 void launch_scatter_locals(cudaStream_t s, const NodeArrays &a, uint32_t count, const uint32_t *d_idx,
                            const float *d_m16, const uint32_t *slot_of_node, uint32_t n_nodes, uint32_t *d_err);
-void launch_scatter_trs(cudaStream_t s, const NodeArrays &a, uint32_t count, const uint32_t *d_idx, const fyx_trs *d_trs,
+void launch_scatter_trs(cudaStream_t s, const NodeArrays &a, uint32_t count, const uint32_t *d_idx, const void *d_payload /* fyx_trs or float4 quats */,
+                        bool rot_only, fyx_trs *trs_by_slot /* device copy of the last records; may be nullptr unless rot_only */,
                         const fyx_transform_statics *statics_by_slot /* nullptr = defaults */, const uint32_t *slot_of_node,
                         uint32_t n_nodes, uint32_t *d_err);
+void launch_fill_identity_trs(cudaStream_t s, fyx_trs *trs_by_slot, uint32_t n);
 void launch_scatter_statics(cudaStream_t s, const NodeArrays &a, uint32_t count, const uint32_t *d_idx,
                             const fyx_transform_statics *d_in, fyx_transform_statics *statics_by_slot,
                             const uint32_t *slot_of_node, uint32_t n_nodes);

@@ -543,16 +543,28 @@ __device__ __forceinline__ float dot3s(const float a0, const float b0, const flo
 
 // Transform::calculate_local_transform (scene/transform.rs:421-540), expression by expression (Rust's
 // a + b - c ... is left-associative; x - y is x + (-y)).  One thread per changed node.
-template <bool HAS_STATICS>
+// ROT_ONLY: the payload is just the new rotation (16 B); position and scale come from the device-resident copy of
+// the node's last full record (trs_by_slot), which every call keeps up to date — property-level change tracking:
+// skeletal animation mostly rewrites rotations (Transform::set_rotation), so 20 B per bone cross PCIe instead of 44.
+template <bool HAS_STATICS, bool ROT_ONLY>
 __global__ void __launch_bounds__(kBlock) k_scatter_trs(const NodeArrays a, const uint32_t count, const uint32_t *d_idx,
-                                                        const fyx_trs *d_trs, const fyx_transform_statics *st_by_slot,
-                                                        const uint32_t *slot_of_node, const uint32_t n_nodes, uint32_t *d_err)
+                                                        const void *d_payload, fyx_trs *trs_by_slot,
+                                                        const fyx_transform_statics *st_by_slot, const uint32_t *slot_of_node,
+                                                        const uint32_t n_nodes, uint32_t *d_err)
 {
     const uint32_t e = blockIdx.x * kBlock + threadIdx.x;
     if (e >= count) return;
     const uint32_t slot = resolve_slot(d_idx, e, slot_of_node, n_nodes);
     if (slot == FYX_NONE) return;
-    const fyx_trs t = d_trs[e];
+    fyx_trs t;
+    if (ROT_ONLY) {
+        t = trs_by_slot[slot];
+        const float4 q = static_cast<const float4 *>(d_payload)[e];
+        t.rotation[0] = q.x; t.rotation[1] = q.y; t.rotation[2] = q.z; t.rotation[3] = q.w;
+    } else {
+        t = static_cast<const fyx_trs *>(d_payload)[e];
+    }
+    if (trs_by_slot) trs_by_slot[slot] = t;
     float prq[4] = {0.f, 0.f, 0.f, 1.f};
     float por[9] = {1.f, 0.f, 0.f, 0.f, 1.f, 0.f, 0.f, 0.f, 1.f};
     float ro[3] = {0.f, 0.f, 0.f}, rp[3] = {0.f, 0.f, 0.f}, so[3] = {0.f, 0.f, 0.f}, sp[3] = {0.f, 0.f, 0.f};
@@ -885,12 +897,37 @@ void launch_scatter_locals(cudaStream_t s, const NodeArrays &a, uint32_t count, 
     k_scatter_locals<<<grid_for(count), kBlock, 0, s>>>(a, count, d_idx, d_m16, slot_of_node, n_nodes, d_err);
 }
 
-void launch_scatter_trs(cudaStream_t s, const NodeArrays &a, uint32_t count, const uint32_t *d_idx, const fyx_trs *d_trs,
-                        const fyx_transform_statics *st, const uint32_t *slot_of_node, uint32_t n_nodes, uint32_t *d_err)
+void launch_scatter_trs(cudaStream_t s, const NodeArrays &a, uint32_t count, const uint32_t *d_idx, const void *d_payload, bool rot_only,
+                        fyx_trs *trs_by_slot, const fyx_transform_statics *st, const uint32_t *slot_of_node, uint32_t n_nodes,
+                        uint32_t *d_err)
 {
     if (!count) return;
-    if (st) k_scatter_trs<true><<<grid_for(count), kBlock, 0, s>>>(a, count, d_idx, d_trs, st, slot_of_node, n_nodes, d_err);
-    else k_scatter_trs<false><<<grid_for(count), kBlock, 0, s>>>(a, count, d_idx, d_trs, st, slot_of_node, n_nodes, d_err);
+    const unsigned g = grid_for(count);
+    if (rot_only) {
+        if (st) k_scatter_trs<true, true><<<g, kBlock, 0, s>>>(a, count, d_idx, d_payload, trs_by_slot, st, slot_of_node, n_nodes, d_err);
+        else k_scatter_trs<false, true><<<g, kBlock, 0, s>>>(a, count, d_idx, d_payload, trs_by_slot, st, slot_of_node, n_nodes, d_err);
+    } else {
+        if (st) k_scatter_trs<true, false><<<g, kBlock, 0, s>>>(a, count, d_idx, d_payload, trs_by_slot, st, slot_of_node, n_nodes, d_err);
+        else k_scatter_trs<false, false><<<g, kBlock, 0, s>>>(a, count, d_idx, d_payload, trs_by_slot, st, slot_of_node, n_nodes, d_err);
+    }
+}
+
+__global__ void __launch_bounds__(kBlock) k_fill_identity_trs(fyx_trs *t, const uint32_t n)
+{
+    const uint32_t e = blockIdx.x * kBlock + threadIdx.x;
+    if (e >= n) return;
+    fyx_trs r;
+    r.position[0] = r.position[1] = r.position[2] = 0.f;
+    r.rotation[0] = r.rotation[1] = r.rotation[2] = 0.f;
+    r.rotation[3] = 1.f;
+    r.scale[0] = r.scale[1] = r.scale[2] = 1.f;
+    t[e] = r;
+}
+
+void launch_fill_identity_trs(cudaStream_t s, fyx_trs *t, uint32_t n)
+{
+    if (!n) return;
+    k_fill_identity_trs<<<grid_for(n), kBlock, 0, s>>>(t, n);
 }
 
 void launch_scatter_statics(cudaStream_t s, const NodeArrays &a, uint32_t count, const uint32_t *d_idx, const fyx_transform_statics *d_in,

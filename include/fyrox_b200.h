@@ -171,6 +171,9 @@ typedef struct fyx_transform_statics {
     float rotation_offset[3], rotation_pivot[3], scaling_offset[3], scaling_pivot[3];
 } fyx_transform_statics;
 int32_t fyx_set_local_trs(fyx_ctx *ctx, uint32_t count, const uint32_t *idx, const fyx_trs *trs);
+/* Transform::set_rotation only (what skeletal animation does to most bones every frame): 16 B per node; position and
+ * scale stay what the node's last fyx_set_local_trs sent (identity for a node that never got one). */
+int32_t fyx_set_local_rotations(fyx_ctx *ctx, uint32_t count, const uint32_t *idx, const float *quat_ijkw);
 int32_t fyx_set_transform_statics(fyx_ctx *ctx, uint32_t count, const uint32_t *idx, const fyx_transform_statics *statics);
 /* Base::set_visibility / set_enabled / frustum_culling / cast_shadows (VisibilityChanged / EnabledFlagChanged). */
 int32_t fyx_set_flags(fyx_ctx *ctx, uint32_t count, const uint32_t *idx, const uint32_t *flags);
@@ -231,6 +234,7 @@ typedef struct fyx_frame_desc {
     const uint32_t *changed_idx;   /* NULL = nodes 0..n_changed-1 */
     const float *changed_m16;      /* n_changed * 16 f32 ... */
     const fyx_trs *changed_trs;    /* ... or, if non-NULL, n_changed fyx_trs records (changed_m16 ignored) */
+    const float *changed_rot;      /* ... or, if non-NULL, n_changed rotations (4 f32 each; the others ignored) */
     uint32_t n_frusta;
     const fyx_frustum *frusta;
     const uint32_t *cam_mask;

@@ -544,6 +544,25 @@ def test_trs_upload_equals_calculate_local_transform(ctx, with_statics):
     ctx.render_prep(update_flags=fb.UPDATE_INCREMENTAL, changed_trs=pt.ptr, n_changed=n, frusta=[], readback_visible=False, async_=True)
     ctx.sync()
     assert bits_equal(ctx.get_global_matrices(), og.global_transforms()).all()
+    # rotation-only updates (Transform::set_rotation): position / scale stay what the last full record said
+    rot2 = rng.normal(size=(n, 4)).astype(np.float32)
+    rot2 /= np.linalg.norm(rot2, axis=1, keepdims=True)
+    some = np.sort(rng.choice(np.arange(1, n), n // 3, replace=False)).astype(np.uint32)
+    for i in some:
+        og.set_local_matrix(int(i), _oracle_transform(pt.array[i, 0:3], rot2[i], pt.array[i, 7:10], None if statics is None else statics[i]))
+    og.update()
+    ctx.set_local_rotations(rot2[some], some)
+    ctx.update_transforms(fb.UPDATE_INCREMENTAL)
+    assert bits_equal(ctx.get_global_matrices(), og.global_transforms()).all()
+    pq = fb.PinnedBuffer((n, 4), np.float32)
+    pq.array[:] = rot
+    for i in range(n):
+        og.set_local_matrix(i, _oracle_transform(pt.array[i, 0:3], rot[i], pt.array[i, 7:10], None if statics is None else statics[i]))
+    og.update_hierarchical_data()
+    ctx.render_prep(update_flags=fb.UPDATE_INCREMENTAL, changed_rot=pq.ptr, n_changed=n, frusta=[], readback_visible=False, async_=True)
+    ctx.sync()
+    assert bits_equal(ctx.get_global_matrices(), og.global_transforms()).all()
+    pq.free()
     pt.free()
 
 
