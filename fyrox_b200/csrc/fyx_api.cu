@@ -928,7 +928,7 @@ static int32_t set_u32_column(fyx_ctx *c, uint32_t count, const uint32_t *idx, c
     void *d_v = nullptr, *d_i = nullptr;
     int32_t rc = stage_to_device(c, val, (size_t)count * 4, idx, idx ? (size_t)count * 4 : 0, false, &d_v, &d_i);
     if (rc) return rc;
-    launch_scatter_u32(c->stream, mode == 0 ? c->a.flags : c->a.mask, nullptr, count, static_cast<const uint32_t *>(d_i),
+    launch_scatter_u32(c->stream, mode == 0 ? c->a.flags : c->a.mask, count, static_cast<const uint32_t *>(d_i),
                        static_cast<const uint32_t *>(d_v), c->b_slot_of_node.as<uint32_t>(), c->n_nodes, mode);
     c->launches++;
     CU(cudaGetLastError());

@@ -97,7 +97,7 @@ void launch_scatter_statics(cudaStream_t s, const NodeArrays &a, uint32_t count,
                             const fyx_transform_statics *d_in, fyx_transform_statics *statics_by_slot,
                             const uint32_t *slot_of_node, uint32_t n_nodes);
 void launch_fill_default_statics(cudaStream_t s, fyx_transform_statics *statics_by_slot, uint32_t n);
-void launch_scatter_u32(cudaStream_t s, uint32_t *dst_col, uint32_t *flags_col, uint32_t count, const uint32_t *d_idx,
+void launch_scatter_u32(cudaStream_t s, uint32_t *dst_col, uint32_t count, const uint32_t *d_idx,
                         const uint32_t *d_val, const uint32_t *slot_of_node, uint32_t n_nodes, int mode);
 void launch_scatter_aabbs(cudaStream_t s, const NodeArrays &a, uint32_t count, const uint32_t *d_idx,
                           const float *d_aabb6, const uint32_t *slot_of_node, uint32_t n_nodes);

@@ -943,7 +943,7 @@ void launch_fill_default_statics(cudaStream_t s, fyx_transform_statics *st, uint
     k_fill_default_statics<<<grid_for(n), kBlock, 0, s>>>(st, n);
 }
 
-void launch_scatter_u32(cudaStream_t s, uint32_t *dst_col, uint32_t *, uint32_t count, const uint32_t *d_idx,
+void launch_scatter_u32(cudaStream_t s, uint32_t *dst_col, uint32_t count, const uint32_t *d_idx,
                         const uint32_t *d_val, const uint32_t *slot_of_node, uint32_t n_nodes, int mode)
 {
     if (!count) return;
