@@ -442,13 +442,14 @@ def run_cuda(args):
     if n_bones:
         g = B_BONE * n_bones / max(stage["palette_ms"], 1e-6) / 1e-3 / 1e9
         stages["k_palette"] = {"ms": stage["palette_ms"], "algorithmic_bytes": B_BONE * n_bones, "GBps": g, "frac": g / peak}
-    dom = "k_skin" if n_local_verts and stage["skin_ms"] >= stage["update_ms"] else "k_update_level+cull"
+    upd_key = [k for k in stages if k.startswith("k_update")][0]
+    dom = "k_skin" if n_local_verts and stage["skin_ms"] >= stage["update_ms"] else upd_key
     traffic = None
     tpath = os.path.join(REPO, "profiles", "ncu_traffic.json")
     if os.path.exists(tpath):
         try:
             tj = json.load(open(tpath))
-            ent = tj.get(args.workload, {}).get(dom)
+            ent = tj.get(args.workload, {}).get("k_skin" if dom == "k_skin" else "k_update_level+cull")
             traffic = ent.get("dram_bytes_per_launch") if ent else None
         except Exception:
             traffic = None

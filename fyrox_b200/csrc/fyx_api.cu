@@ -347,6 +347,7 @@ int32_t prepare_cull(fyx_ctx *c, uint32_t nf, const fyx_frustum *fr, const uint3
     return FYX_OK;
 }
 
+// Hierarchy + boxes (+ fused cull): one launch per level (parents first), then the skinned-mesh fold.
 int32_t run_update(fyx_ctx *c, uint32_t update_flags, const CullParams *cull)
 {
     const bool all = (update_flags & FYX_UPDATE_ALL) || !c->updated_once;

@@ -128,66 +128,73 @@ __device__ __forceinline__ void compact_emit(const uint32_t vis_bits, const uint
 // launch on the same stream.
 // Algorithmic bytes per node: 132 (T) + 48 (A) [+ 8 (K)]; moved: 48+4+48 + 24+24 + 4+4(+4+4).
 // ------------------------------------------------------------------------------------------------
+// (A single cooperative launch walking all levels with grid-wide barriers was tried and rejected: the
+// persistent grid, L2-only parent loads and the barriers cost more than the launches they save —
+// C2 0.357 -> 0.416 ms, target 0.990 -> 1.051 ms per frame; profiles/README.md.)
+template <bool FUSE>
+__device__ __forceinline__ void update_node(const NodeArrays &a, const uint32_t slot, const uint32_t update_all, const CullParams &cp,
+                                            uint32_t &vis_bits, uint32_t &gi)
+{
+    const uint32_t f = a.flags[slot];
+    const uint32_t p = a.parent[slot];
+    // no parent ⇒ parent values are identity / true (graph/mod.rs:1171-1175,1187-1192,1210-1214)
+    const uint32_t pf = (p != FYX_NONE)
+                            ? a.flags[p]
+                            : (FYX_NODE_GLOBAL_VISIBILITY | FYX_NODE_GLOBAL_ENABLED | ((f & F_ROOT) ? FYX_NODE_REACHABLE : 0u));
+    const bool dirty = update_all || (f & F_DIRTY_SELF) || (pf & F_DIRTY);
+    uint32_t nf = f & ~(FYX_NODE_GLOBAL_VISIBILITY | FYX_NODE_GLOBAL_ENABLED | FYX_NODE_REACHABLE | F_DIRTY | F_DIRTY_SELF);
+    if ((pf & FYX_NODE_GLOBAL_VISIBILITY) && (f & FYX_NODE_VISIBILITY)) nf |= FYX_NODE_GLOBAL_VISIBILITY;
+    if ((pf & FYX_NODE_GLOBAL_ENABLED) && (f & FYX_NODE_ENABLED)) nf |= FYX_NODE_GLOBAL_ENABLED;
+    nf |= pf & FYX_NODE_REACHABLE;
+    if (dirty) nf |= F_DIRTY;
+    a.flags[slot] = nf;
+
+    float2 wx, wy, wz;
+    if (dirty) {
+        Affine L;
+        L.r0 = ld_stream(a.L[0] + slot);
+        L.r1 = ld_stream(a.L[1] + slot);
+        L.r2 = ld_stream(a.L[2] + slot);
+        const float2 lx = ld_stream(a.la[0] + slot);
+        const float2 ly = ld_stream(a.la[1] + slot);
+        const float2 lz = ld_stream(a.la[2] + slot);
+        Affine P;
+        if (p != FYX_NONE) {
+            P.r0 = a.G[0][p]; // siblings are adjacent slots: one or two parents per warp (L1 hits)
+            P.r1 = a.G[1][p];
+            P.r2 = a.G[2][p];
+        } else {
+            P = affine_identity();
+        }
+        const Affine Gm = affine_mul(P, L);
+        st_stream(a.G[0] + slot, Gm.r0);
+        st_stream(a.G[1] + slot, Gm.r1);
+        st_stream(a.G[2] + slot, Gm.r2);
+        wx = aabb_transform_row(Gm.r0, lx, ly, lz);
+        wy = aabb_transform_row(Gm.r1, lx, ly, lz);
+        wz = aabb_transform_row(Gm.r2, lx, ly, lz);
+        // skinned meshes: this is the box before the bone fold; fold_mesh finishes it
+        st_stream(a.wa[0] + slot, wx);
+        st_stream(a.wa[1] + slot, wy);
+        st_stream(a.wa[2] + slot, wz);
+    } else if (FUSE) {
+        wx = ld_stream(a.wa[0] + slot);
+        wy = ld_stream(a.wa[1] + slot);
+        wz = ld_stream(a.wa[2] + slot);
+    }
+    if (FUSE && !(nf & F_SKINNED)) {
+        vis_bits = cull_bits(nf, a.mask[slot], wx, wy, wz, cp);
+        if (vis_bits) gi = a.gidx[slot];
+    }
+}
+
 template <bool FUSE>
 __global__ void __launch_bounds__(kBlock) k_update_level(const NodeArrays a, const uint32_t lo, const uint32_t hi,
                                                          const uint32_t update_all, const CullParams cp)
 {
     const uint32_t slot = lo + blockIdx.x * kBlock + threadIdx.x;
-    const bool valid = slot < hi;
     uint32_t vis_bits = 0u, gi = 0u;
-    if (valid) {
-        const uint32_t f = a.flags[slot];
-        const uint32_t p = a.parent[slot];
-        // no parent ⇒ parent values are identity / true (graph/mod.rs:1171-1175,1187-1192,1210-1214)
-        const uint32_t pf = (p != FYX_NONE)
-                                ? a.flags[p]
-                                : (FYX_NODE_GLOBAL_VISIBILITY | FYX_NODE_GLOBAL_ENABLED | ((f & F_ROOT) ? FYX_NODE_REACHABLE : 0u));
-        const bool dirty = update_all || (f & F_DIRTY_SELF) || (pf & F_DIRTY);
-        uint32_t nf = f & ~(FYX_NODE_GLOBAL_VISIBILITY | FYX_NODE_GLOBAL_ENABLED | FYX_NODE_REACHABLE | F_DIRTY | F_DIRTY_SELF);
-        if ((pf & FYX_NODE_GLOBAL_VISIBILITY) && (f & FYX_NODE_VISIBILITY)) nf |= FYX_NODE_GLOBAL_VISIBILITY;
-        if ((pf & FYX_NODE_GLOBAL_ENABLED) && (f & FYX_NODE_ENABLED)) nf |= FYX_NODE_GLOBAL_ENABLED;
-        nf |= pf & FYX_NODE_REACHABLE;
-        if (dirty) nf |= F_DIRTY;
-        a.flags[slot] = nf;
-
-        float2 wx, wy, wz;
-        if (dirty) {
-            Affine L;
-            L.r0 = ld_stream(a.L[0] + slot);
-            L.r1 = ld_stream(a.L[1] + slot);
-            L.r2 = ld_stream(a.L[2] + slot);
-            const float2 lx = ld_stream(a.la[0] + slot);
-            const float2 ly = ld_stream(a.la[1] + slot);
-            const float2 lz = ld_stream(a.la[2] + slot);
-            Affine P;
-            if (p != FYX_NONE) {
-                P.r0 = a.G[0][p]; // siblings share the parent: broadcast / L1 hit
-                P.r1 = a.G[1][p];
-                P.r2 = a.G[2][p];
-            } else {
-                P = affine_identity();
-            }
-            const Affine Gm = affine_mul(P, L);
-            st_stream(a.G[0] + slot, Gm.r0);
-            st_stream(a.G[1] + slot, Gm.r1);
-            st_stream(a.G[2] + slot, Gm.r2);
-            wx = aabb_transform_row(Gm.r0, lx, ly, lz);
-            wy = aabb_transform_row(Gm.r1, lx, ly, lz);
-            wz = aabb_transform_row(Gm.r2, lx, ly, lz);
-            // skinned meshes: this is the box before the bone fold; k_fold_bones finishes it
-            st_stream(a.wa[0] + slot, wx);
-            st_stream(a.wa[1] + slot, wy);
-            st_stream(a.wa[2] + slot, wz);
-        } else if (FUSE) {
-            wx = ld_stream(a.wa[0] + slot);
-            wy = ld_stream(a.wa[1] + slot);
-            wz = ld_stream(a.wa[2] + slot);
-        }
-        if (FUSE && !(nf & F_SKINNED)) {
-            vis_bits = cull_bits(nf, a.mask[slot], wx, wy, wz, cp);
-            if (vis_bits) gi = a.gidx[slot];
-        }
-    }
+    if (slot < hi) update_node<FUSE>(a, slot, update_all, cp, vis_bits, gi);
     if (FUSE) compact_emit(vis_bits, gi, cp);
 }
 
@@ -231,64 +238,71 @@ __device__ __forceinline__ void fold_max(float &v, uint32_t &k, const float ov, 
     if (ov > v || (ov == v && ok < k)) { v = ov; k = ok; }
 }
 
+// one warp = one skinned mesh (i); lane 0 returns the cull result
+template <bool FUSE>
+__device__ __forceinline__ void fold_mesh(const NodeArrays &a, const FoldArrays &fa, const uint32_t i, const uint32_t lane,
+                                          const CullParams &cp, uint32_t &vis_bits, uint32_t &gi)
+{
+    const uint32_t slot = fa.node_slot[i];
+    const uint32_t nf = a.flags[slot];
+    float2 wx = a.wa[0][slot], wy = a.wa[1][slot], wz = a.wa[2][slot];
+    if (nf & F_DIRTY) {
+        const uint32_t b0 = fa.bone_begin[i], b1 = fa.bone_begin[i + 1];
+        // candidates start as the transformed box (order key 0 = "already there"); bones get keys 1..
+        float mnx = wx.x, mny = wy.x, mnz = wz.x, mxx = wx.y, mxy = wy.y, mxz = wz.y;
+        uint32_t kmnx = 0, kmny = 0, kmnz = 0, kmxx = 0, kmxy = 0, kmxz = 0;
+        for (uint32_t b = b0 + lane; b < b1; b += 32) {
+            const uint32_t bs = fa.bone_slot[b];
+            if (bs == FYX_NONE) continue; // try_borrow failed ⇒ skipped
+            float px, py, pz; // global_position()
+            const uint32_t si = fa.stale_idx ? fa.stale_idx[b] : FYX_NONE;
+            if (si != FYX_NONE) { // visited after the mesh by the reference's DFS: its value from before this update
+                const float4 o = fa.stale_pos[si];
+                px = o.x; py = o.y; pz = o.z;
+            } else {
+                px = a.G[0][bs].w;
+                py = a.G[1][bs].w;
+                pz = a.G[2][bs].w;
+            }
+            const uint32_t key = b - b0 + 1u;
+            // within a lane keys increase, so the strict compares keep the earliest of equal values
+            if (px < mnx) { mnx = px; kmnx = key; }
+            if (py < mny) { mny = py; kmny = key; }
+            if (pz < mnz) { mnz = pz; kmnz = key; }
+            if (px > mxx) { mxx = px; kmxx = key; }
+            if (py > mxy) { mxy = py; kmxy = key; }
+            if (pz > mxz) { mxz = pz; kmxz = key; }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            fold_min(mnx, kmnx, __shfl_xor_sync(0xFFFFFFFFu, mnx, o), __shfl_xor_sync(0xFFFFFFFFu, kmnx, o));
+            fold_min(mny, kmny, __shfl_xor_sync(0xFFFFFFFFu, mny, o), __shfl_xor_sync(0xFFFFFFFFu, kmny, o));
+            fold_min(mnz, kmnz, __shfl_xor_sync(0xFFFFFFFFu, mnz, o), __shfl_xor_sync(0xFFFFFFFFu, kmnz, o));
+            fold_max(mxx, kmxx, __shfl_xor_sync(0xFFFFFFFFu, mxx, o), __shfl_xor_sync(0xFFFFFFFFu, kmxx, o));
+            fold_max(mxy, kmxy, __shfl_xor_sync(0xFFFFFFFFu, mxy, o), __shfl_xor_sync(0xFFFFFFFFu, kmxy, o));
+            fold_max(mxz, kmxz, __shfl_xor_sync(0xFFFFFFFFu, mxz, o), __shfl_xor_sync(0xFFFFFFFFu, kmxz, o));
+        }
+        wx = make_float2(mnx, mxx);
+        wy = make_float2(mny, mxy);
+        wz = make_float2(mnz, mxz);
+        if (lane == 0) {
+            a.wa[0][slot] = wx;
+            a.wa[1][slot] = wy;
+            a.wa[2][slot] = wz;
+        }
+    }
+    if (FUSE && lane == 0) {
+        vis_bits = cull_bits(nf, a.mask[slot], wx, wy, wz, cp);
+        if (vis_bits) gi = a.gidx[slot];
+    }
+}
+
 template <bool FUSE>
 __global__ void __launch_bounds__(kBlock) k_fold_bones(const NodeArrays a, const FoldArrays fa, const CullParams cp)
 {
     const uint32_t i = (blockIdx.x * kBlock + threadIdx.x) >> 5; // mesh = warp
-    const uint32_t lane = threadIdx.x & 31u;
     uint32_t vis_bits = 0u, gi = 0u;
-    if (i < fa.n) {
-        const uint32_t slot = fa.node_slot[i];
-        const uint32_t nf = a.flags[slot];
-        float2 wx = a.wa[0][slot], wy = a.wa[1][slot], wz = a.wa[2][slot];
-        if (nf & F_DIRTY) {
-            const uint32_t b0 = fa.bone_begin[i], b1 = fa.bone_begin[i + 1];
-            // candidates start as the transformed box (order key 0 = "already there"); bones get keys 1..
-            float mnx = wx.x, mny = wy.x, mnz = wz.x, mxx = wx.y, mxy = wy.y, mxz = wz.y;
-            uint32_t kmnx = 0, kmny = 0, kmnz = 0, kmxx = 0, kmxy = 0, kmxz = 0;
-            for (uint32_t b = b0 + lane; b < b1; b += 32) {
-                const uint32_t bs = fa.bone_slot[b];
-                if (bs == FYX_NONE) continue; // try_borrow failed ⇒ skipped
-                float px, py, pz; // global_position()
-                const uint32_t si = fa.stale_idx ? fa.stale_idx[b] : FYX_NONE;
-                if (si != FYX_NONE) { // visited after the mesh by the reference's DFS: its value from before this update
-                    const float4 o = fa.stale_pos[si];
-                    px = o.x; py = o.y; pz = o.z;
-                } else {
-                    px = a.G[0][bs].w; py = a.G[1][bs].w; pz = a.G[2][bs].w;
-                }
-                const uint32_t key = b - b0 + 1u;
-                // within a lane keys increase, so the strict compares keep the earliest of equal values
-                if (px < mnx) { mnx = px; kmnx = key; }
-                if (py < mny) { mny = py; kmny = key; }
-                if (pz < mnz) { mnz = pz; kmnz = key; }
-                if (px > mxx) { mxx = px; kmxx = key; }
-                if (py > mxy) { mxy = py; kmxy = key; }
-                if (pz > mxz) { mxz = pz; kmxz = key; }
-            }
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                fold_min(mnx, kmnx, __shfl_xor_sync(0xFFFFFFFFu, mnx, o), __shfl_xor_sync(0xFFFFFFFFu, kmnx, o));
-                fold_min(mny, kmny, __shfl_xor_sync(0xFFFFFFFFu, mny, o), __shfl_xor_sync(0xFFFFFFFFu, kmny, o));
-                fold_min(mnz, kmnz, __shfl_xor_sync(0xFFFFFFFFu, mnz, o), __shfl_xor_sync(0xFFFFFFFFu, kmnz, o));
-                fold_max(mxx, kmxx, __shfl_xor_sync(0xFFFFFFFFu, mxx, o), __shfl_xor_sync(0xFFFFFFFFu, kmxx, o));
-                fold_max(mxy, kmxy, __shfl_xor_sync(0xFFFFFFFFu, mxy, o), __shfl_xor_sync(0xFFFFFFFFu, kmxy, o));
-                fold_max(mxz, kmxz, __shfl_xor_sync(0xFFFFFFFFu, mxz, o), __shfl_xor_sync(0xFFFFFFFFu, kmxz, o));
-            }
-            wx = make_float2(mnx, mxx);
-            wy = make_float2(mny, mxy);
-            wz = make_float2(mnz, mxz);
-            if (lane == 0) {
-                a.wa[0][slot] = wx;
-                a.wa[1][slot] = wy;
-                a.wa[2][slot] = wz;
-            }
-        }
-        if (FUSE && lane == 0) {
-            vis_bits = cull_bits(nf, a.mask[slot], wx, wy, wz, cp);
-            if (vis_bits) gi = a.gidx[slot];
-        }
-    }
+    if (i < fa.n) fold_mesh<FUSE>(a, fa, i, threadIdx.x & 31u, cp, vis_bits, gi);
     if (FUSE) compact_emit(vis_bits, gi, cp);
 }
 
@@ -309,10 +323,8 @@ __global__ void __launch_bounds__(kBlock) k_snapshot_bones(const NodeArrays a, c
 // Output: column-major mat4 (the layout write_uniforms copies into the UBO, renderer/bundle.rs:484-496).
 // Algorithmic bytes per bone: 196 (G 64 + inv_bind 64 + idx 4 + P 64); moved: 48 + 48 + 4 + 64.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kBlock) k_palette(const NodeArrays a, const SkinArrays sk)
+__device__ __forceinline__ void palette_entry(const NodeArrays &a, const SkinArrays &sk, const uint32_t e)
 {
-    const uint32_t e = blockIdx.x * kBlock + threadIdx.x;
-    if (e >= sk.n_entries) return;
     const uint32_t bs = sk.bone_slot[e];
     Affine P;
     if (bs != FYX_NONE) {
@@ -332,6 +344,12 @@ __global__ void __launch_bounds__(kBlock) k_palette(const NodeArrays a, const Sk
     o[1] = make_float4(P.r0.y, P.r1.y, P.r2.y, 0.0f);
     o[2] = make_float4(P.r0.z, P.r1.z, P.r2.z, 0.0f);
     o[3] = make_float4(P.r0.w, P.r1.w, P.r2.w, 1.0f);
+}
+
+__global__ void __launch_bounds__(kBlock) k_palette(const NodeArrays a, const SkinArrays sk)
+{
+    const uint32_t e = blockIdx.x * kBlock + threadIdx.x;
+    if (e < sk.n_entries) palette_entry(a, sk, e);
 }
 
 // ------------------------------------------------------------------------------------------------
