@@ -46,6 +46,32 @@ __device__ __forceinline__ void st_stream(float2 *p, const float2 v)
 }
 
 // ------------------------------------------------------------------------------------------------
+// Programmatic dependent launch: the kernels of a frame form a chain of true data dependencies (level l
+// needs level l-1, the fold needs every level, the palettes the bones, the skinning the palettes), several
+// of them tiny.  Each is launched with programmatic stream serialization: it lets the next kernel's CTAs be
+// scheduled right away (pdl_trigger) and waits for the previous kernel's results only where it first needs
+// them (pdl_wait) — launch latency and the loads that do not depend on the predecessor overlap its tail.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+template <class... Params, class... Args>
+static void launch_pdl(void (*kernel)(Params...), unsigned grid, unsigned block, size_t smem, cudaStream_t s, Args... args)
+{
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(block);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    cudaLaunchKernelEx(&cfg, kernel, static_cast<Params>(args)...);
+}
+
+// ------------------------------------------------------------------------------------------------
 // NodeTrait::should_be_rendered (scene/node/mod.rs:231-256) + the shadow-pass cast_shadows test of
 // Mesh::collect_render_data (scene/mesh/mod.rs:696-698) + reachability from Graph::root
 // (iterate_recursive, renderer/bundle.rs:988-1004), for every frustum of the call.  Bit f of the
@@ -137,6 +163,7 @@ __device__ __forceinline__ void update_node(const NodeArrays &a, const uint32_t 
 {
     const uint32_t f = a.flags[slot];
     const uint32_t p = a.parent[slot];
+    pdl_wait(); // everything below reads what the previous level (or the previous frame's tail) wrote
     // no parent ⇒ parent values are identity / true (graph/mod.rs:1171-1175,1187-1192,1210-1214)
     const uint32_t pf = (p != FYX_NONE)
                             ? a.flags[p]
@@ -192,9 +219,11 @@ template <bool FUSE>
 __global__ void __launch_bounds__(kBlock) k_update_level(const NodeArrays a, const uint32_t lo, const uint32_t hi,
                                                          const uint32_t update_all, const CullParams cp)
 {
+    pdl_trigger();
     const uint32_t slot = lo + blockIdx.x * kBlock + threadIdx.x;
     uint32_t vis_bits = 0u, gi = 0u;
     if (slot < hi) update_node<FUSE>(a, slot, update_all, cp, vis_bits, gi);
+    else pdl_wait();
     if (FUSE) compact_emit(vis_bits, gi, cp);
 }
 
@@ -300,6 +329,8 @@ __device__ __forceinline__ void fold_mesh(const NodeArrays &a, const FoldArrays 
 template <bool FUSE>
 __global__ void __launch_bounds__(kBlock) k_fold_bones(const NodeArrays a, const FoldArrays fa, const CullParams cp)
 {
+    pdl_trigger();
+    pdl_wait();
     const uint32_t i = (blockIdx.x * kBlock + threadIdx.x) >> 5; // mesh = warp
     uint32_t vis_bits = 0u, gi = 0u;
     if (i < fa.n) fold_mesh<FUSE>(a, fa, i, threadIdx.x & 31u, cp, vis_bits, gi);
@@ -348,6 +379,8 @@ __device__ __forceinline__ void palette_entry(const NodeArrays &a, const SkinArr
 
 __global__ void __launch_bounds__(kBlock) k_palette(const NodeArrays a, const SkinArrays sk)
 {
+    pdl_trigger();
+    pdl_wait();
     const uint32_t e = blockIdx.x * kBlock + threadIdx.x;
     if (e < sk.n_entries) palette_entry(a, sk, e);
 }
@@ -470,6 +503,7 @@ __global__ void __launch_bounds__(kBlock, MINB) k_skin(const SkinArrays sk, cons
     kc.one = make_float2(one, one);
     kc.negzero = make_float2(negzero, negzero);
     const SkinTile T = tiles[blockIdx.x];
+    pdl_wait(); // the palettes come from k_palette
     skin_fill_palette<S, LOG2C>(s_pal, sk.palette, T.bone_off, T.n_bones);
     __syncthreads();
     const uint32_t lane = threadIdx.x & 31u;
@@ -845,11 +879,11 @@ void launch_update_level(cudaStream_t s, const NodeArrays &a, uint32_t lo, uint3
 {
     if (hi <= lo) return;
     if (cull) {
-        k_update_level<true><<<grid_for(hi - lo), kBlock, 0, s>>>(a, lo, hi, update_all ? 1u : 0u, *cull);
+        launch_pdl(k_update_level<true>, grid_for(hi - lo), kBlock, 0, s, a, lo, hi, update_all ? 1u : 0u, *cull);
     } else {
         CullParams none;
         none.nf = 0;
-        k_update_level<false><<<grid_for(hi - lo), kBlock, 0, s>>>(a, lo, hi, update_all ? 1u : 0u, none);
+        launch_pdl(k_update_level<false>, grid_for(hi - lo), kBlock, 0, s, a, lo, hi, update_all ? 1u : 0u, none);
     }
 }
 
@@ -864,11 +898,11 @@ void launch_fold_bones(cudaStream_t s, const NodeArrays &a, const FoldArrays &fa
     if (!fa.n) return;
     const unsigned grid = grid_for((uint64_t)fa.n * 32); // one warp per skinned mesh
     if (cull) {
-        k_fold_bones<true><<<grid, kBlock, 0, s>>>(a, fa, *cull);
+        launch_pdl(k_fold_bones<true>, grid, kBlock, 0, s, a, fa, *cull);
     } else {
         CullParams none;
         none.nf = 0;
-        k_fold_bones<false><<<grid, kBlock, 0, s>>>(a, fa, none);
+        launch_pdl(k_fold_bones<false>, grid, kBlock, 0, s, a, fa, none);
     }
 }
 
@@ -881,7 +915,7 @@ void launch_snapshot_bones(cudaStream_t s, const NodeArrays &a, uint32_t n_late,
 void launch_palette(cudaStream_t s, const NodeArrays &a, const SkinArrays &sk)
 {
     if (!sk.n_entries) return;
-    k_palette<<<grid_for(sk.n_entries), kBlock, 0, s>>>(a, sk);
+    launch_pdl(k_palette, grid_for(sk.n_entries), kBlock, 0, s, a, sk);
 }
 
 template <int S, int LOG2C, int MINB> static void launch_skin_t(cudaStream_t s, const SkinArrays &sk, const SkinTile *tiles, uint32_t n_tiles)
@@ -892,7 +926,7 @@ template <int S, int LOG2C, int MINB> static void launch_skin_t(cudaStream_t s, 
         cudaFuncSetAttribute(k_skin<S, LOG2C, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_pal);
         init = true;
     }
-    k_skin<S, LOG2C, MINB><<<n_tiles, kBlock, smem_pal, s>>>(sk, tiles, n_tiles, 1.0f, -0.0f);
+    launch_pdl(k_skin<S, LOG2C, MINB>, n_tiles, kBlock, smem_pal, s, sk, tiles, n_tiles, 1.0f, -0.0f);
 }
 
 void launch_skin(cudaStream_t s, const SkinArrays &sk, const SkinTile *tiles, uint32_t n_tiles, uint32_t max_bones)
