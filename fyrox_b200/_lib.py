@@ -101,6 +101,21 @@ class fyx_frame_desc(C.Structure):
     ]
 
 
+class fyx_bundle(C.Structure):
+    _fields_ = [("id", C.c_uint32), ("first", C.c_uint32), ("count", C.c_uint32), ("reserved", C.c_uint32), ("sort_index", C.c_uint64)]
+
+
+class fyx_instances(C.Structure):
+    _fields_ = [
+        ("count", C.c_uint32),
+        ("n_bundles", C.c_uint32),
+        ("node", C.c_void_p),
+        ("sort_index", C.c_void_p),
+        ("matrices", C.c_void_p),
+        ("bundles", C.c_void_p),
+    ]
+
+
 # every symbol include/fyrox_b200.h declares: name -> (restype, argtypes)
 ctx_p = C.c_void_p
 SYMBOLS = {
@@ -146,6 +161,11 @@ SYMBOLS = {
     "fyx_get_skinned_device": (C.c_int32, [ctx_p, C.c_uint32, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]),
     "fyx_get_timings": (C.c_int32, [ctx_p, C.POINTER(fyx_timings)]),
     "fyx_kernel_launch_count": (C.c_uint64, [ctx_p]),
+    "fyx_set_bundle_ids": (C.c_int32, [ctx_p, C.c_uint32, C.c_void_p, C.c_void_p]),
+    "fyx_enable_instances": (C.c_int32, [ctx_p, C.c_uint32]),
+    "fyx_pack_instances": (C.c_int32, [ctx_p, C.c_uint32, C.c_void_p, C.c_void_p]),
+    "fyx_get_instances": (C.c_int32, [ctx_p, C.c_uint32, C.POINTER(fyx_instances)]),
+    "fyx_get_instances_device": (C.c_int32, [ctx_p, C.c_uint32, C.POINTER(fyx_instances)]),
     "fyx_comm_get_unique_id": (C.c_int32, [C.c_void_p]),
     "fyx_comm_init": (C.c_int32, [ctx_p, C.c_int32, C.c_int32, C.c_void_p]),
     "fyx_allgather_visible": (C.c_int32, [ctx_p]),

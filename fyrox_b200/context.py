@@ -277,6 +277,43 @@ class Context:
         self._chk(self._lib.fyx_get_visible_device(self._h, frustum, C.byref(d_idx), C.byref(d_cnt)))
         return d_idx.value, d_cnt.value
 
+    # ---- N3: draw-prep after the cull ----
+    def set_bundle_ids(self, ids, idx=None):
+        """Per-node bundle id = dense id of the (material, surface data, render path) key of
+        RenderDataBundleStorage::push (renderer/bundle.rs:1253-1257)."""
+        ids = np.ascontiguousarray(ids, dtype=np.uint32)
+        ix = _u32(idx)
+        self._chk(self._lib.fyx_set_bundle_ids(self._h, len(ids), _ptr(ix), _ptr(ids)))
+
+    def enable_instances(self, enable: bool = True):
+        self._chk(self._lib.fyx_enable_instances(self._h, 1 if enable else 0))
+
+    def pack_instances(self, frustum: int, view_m16, view_projection_m16) -> dict:
+        """Instances of the frustum's visible list grouped by bundle: dict with node (u32[n]), sort_index (u64[n]),
+        world / wvp (f32[n,16], column-major) and bundles (structured array: id, first, count, sort_index)."""
+        v = np.ascontiguousarray(view_m16, dtype=np.float32).reshape(16)
+        vp = np.ascontiguousarray(view_projection_m16, dtype=np.float32).reshape(16)
+        self._chk(self._lib.fyx_pack_instances(self._h, frustum, _ptr(v), _ptr(vp)))
+        out = L.fyx_instances()
+        self._chk(self._lib.fyx_get_instances(self._h, frustum, C.byref(out)))
+        n, nb = out.count, out.n_bundles
+        bdt = np.dtype([("id", "<u4"), ("first", "<u4"), ("count", "<u4"), ("reserved", "<u4"), ("sort_index", "<u8")])
+
+        def arr(p, dtype, count):
+            if count == 0:
+                return np.empty(0, dtype=dtype)
+            buf = (C.c_char * (count * np.dtype(dtype).itemsize)).from_address(p)
+            return np.frombuffer(buf, dtype=dtype, count=count).copy()
+
+        mats = arr(out.matrices, np.float32, n * 32).reshape(n, 2, 16)
+        return {
+            "node": arr(out.node, np.uint32, n),
+            "sort_index": arr(out.sort_index, np.uint64, n),
+            "world": mats[:, 0, :].copy(),
+            "wvp": mats[:, 1, :].copy(),
+            "bundles": arr(out.bundles, bdt, nb),
+        }
+
     def build_palettes(self):
         self._chk(self._lib.fyx_build_palettes(self._h))
 

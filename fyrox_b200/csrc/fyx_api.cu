@@ -42,6 +42,8 @@ enum { EV_START = 0, EV_UPLOAD, EV_UPDATE, EV_CULL, EV_PALETTE, EV_SKIN, EV_READ
 // alternate so that the lists of frame i can travel to the host while frame i+1 is being culled.
 struct VisSlot {
     DevBuf b_vis[FYX_MAX_FRUSTA];
+    DevBuf b_vis_slot[FYX_MAX_FRUSTA]; // the same entries as HBM slots (fyx_enable_instances)
+    bool have_slots = false;
     uint32_t *d_counts = nullptr; // kCountStride * FYX_MAX_FRUSTA, each counter on its own 128 B line
     uint32_t *h_counts = nullptr; // pinned, FYX_MAX_FRUSTA
     uint32_t *h_vis[FYX_MAX_FRUSTA] = {};
@@ -58,6 +60,15 @@ struct VisSlot {
     bool pending = false; // written by a pipelined (async + read-back) frame that fyx_frame_wait has not collected yet
     uint64_t frame_no = 0;
     cudaEvent_t ev_cull = nullptr, ev_counts = nullptr, ev_done = nullptr;
+};
+
+// N3: packed instances of one frustum (fyx_drawprep.inl)
+struct InstOut {
+    DevBuf b_node, b_sort, b_mats, b_bundles;
+    void *h[4] = {};
+    size_t h_cap[4] = {};
+    uint32_t count = 0, n_bundles = 0;
+    bool valid = false, on_host = false;
 };
 
 } // namespace
@@ -123,6 +134,13 @@ struct fyx_ctx {
     cudaEvent_t ev[EV_COUNT] = {};
     fyx_timings timings{};
     bool timings_pending = false; // an async frame's events have not been read yet
+
+    // N3 draw-prep (fyx_drawprep.inl)
+    bool instances_enabled = false, have_bundles = false, rank_on_device = false;
+    uint32_t n_bundle_ids = 1;
+    DevBuf b_bundle, b_rank_slot, b_inst_hist, b_inst_first, b_inst_offset, b_inst_tmp, b_inst_nb;
+    uint32_t *h_inst_nb = nullptr;
+    InstOut inst[FYX_MAX_FRUSTA];
 
     // multi-GPU (fyx_comm.cu)
     void *comm = nullptr;
@@ -338,7 +356,15 @@ int32_t prepare_cull(fyx_ctx *c, uint32_t nf, const fyx_frustum *fr, const uint3
         int32_t rc = dev_ensure(c, V.b_vis[f], sizeof(uint32_t) * std::max<size_t>(c->n_slots, 1));
         if (rc) return rc;
         c->cp.out[f] = V.b_vis[f].as<uint32_t>();
+        c->cp.out_slot[f] = nullptr;
+        if (c->instances_enabled) {
+            rc = dev_ensure(c, V.b_vis_slot[f], sizeof(uint32_t) * std::max<size_t>(c->n_slots, 1));
+            if (rc) return rc;
+            c->cp.out_slot[f] = V.b_vis_slot[f].as<uint32_t>();
+        }
     }
+    V.have_slots = c->instances_enabled;
+    for (auto &o : c->inst) o.valid = false;
     CU(cudaMemsetAsync(V.d_counts, 0, sizeof(uint32_t) * kCountStride * FYX_MAX_FRUSTA, c->stream));
     V.nf = nf;
     V.counts_on_host = V.lists_on_host = false;
@@ -501,6 +527,7 @@ extern "C" int32_t fyx_create(const fyx_config *cfg, fyx_ctx **out_ctx)
 }
 
 static void fyx_comm_destroy_internal(fyx_ctx *c); // fyx_comm.inl
+namespace { void inst_free(fyx_ctx *c); }              // fyx_drawprep.inl
 static int32_t allgather_begin(fyx_ctx *c, VisSlot &V, cudaStream_t s);
 static int32_t allgather_finish(fyx_ctx *c, VisSlot &V, cudaStream_t s);
 
@@ -510,6 +537,7 @@ extern "C" void fyx_destroy(fyx_ctx *c)
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     fyx_comm_destroy_internal(c);
+    inst_free(c);
     DevBuf *bufs[] = {&c->b_parent, &c->b_flags, &c->b_mask, &c->b_gidx, &c->b_slot_of_node, &c->d_stage, &c->b_statics, &c->b_trs, &c->b_vblk,
                       &c->b_opos, &c->b_onrm, &c->b_palette, &c->b_bone_slot, &c->b_tiles, &c->b_fold_node,
                       &c->b_fold_begin, &c->b_fold_bone, &c->b_fold_stale_idx, &c->b_late_slot, &c->b_stale_pos, &c->b_counts_packed, &c->b_counts_all};
@@ -810,6 +838,9 @@ extern "C" int32_t fyx_set_topology(fyx_ctx *c, uint32_t capacity, uint32_t root
     c->updated_once = false;
     c->have_statics = false; // slots moved: the caller re-sends non-default statics after a topology change
     c->dfs_rank.clear();     // ... and the DFS order, if it uses it
+    c->rank_on_device = false;
+    c->have_bundles = false; // ... and the bundle ids (every node is back in bundle 0)
+    c->n_bundle_ids = 1;
     c->have_trs = false;     // ... and full TRS records before the next rotation-only update
     c->tables_dirty = true; // bone slots depend on the slot order
     rebuild_node_arrays(c);
@@ -823,6 +854,7 @@ extern "C" int32_t fyx_set_dfs_order(fyx_ctx *c, uint32_t capacity, const uint32
     if (preorder_rank && capacity != c->n_nodes) return fail(c, FYX_ERR_INVALID_ARGUMENT, "capacity %u != topology capacity %u", capacity, c->n_nodes);
     if (preorder_rank) c->dfs_rank.assign(preorder_rank, preorder_rank + capacity);
     else c->dfs_rank.clear();
+    c->rank_on_device = false;
     c->tables_dirty = true;
     return FYX_OK;
 }
@@ -1586,3 +1618,4 @@ extern "C" int32_t fyx_get_timings(fyx_ctx *c, fyx_timings *out)
 }
 
 #include "fyx_comm.inl"
+#include "fyx_drawprep.inl"

@@ -1,0 +1,198 @@
+// fyx_drawprep.inl — N3: instances of a visible list grouped by bundle (included at the end of fyx_api.cu).
+// Kernels: fyx_drawprep.cu.  Reference: renderer/bundle.rs:118-127 (sort index), :483-487 (instance block),
+// :1248-1278 (push into the bundle keyed by material / surface data / render path).
+
+namespace {
+
+int32_t inst_host_ensure(fyx_ctx *c, void **p, size_t *cap, size_t bytes)
+{
+    if (bytes <= *cap) return FYX_OK;
+    if (*p) cudaFreeHost(*p);
+    *p = nullptr;
+    *cap = 0;
+    const size_t nb = std::max<size_t>(4096, bytes + bytes / 2);
+    CU(cudaHostAlloc(p, nb, cudaHostAllocDefault));
+    *cap = nb;
+    return FYX_OK;
+}
+
+void inst_free(fyx_ctx *c)
+{
+    for (auto &o : c->inst) {
+        dev_free(o.b_node);
+        dev_free(o.b_sort);
+        dev_free(o.b_mats);
+        dev_free(o.b_bundles);
+        for (int k = 0; k < 4; ++k) {
+            if (o.h[k]) cudaFreeHost(o.h[k]);
+            o.h[k] = nullptr;
+            o.h_cap[k] = 0;
+        }
+        o.valid = false;
+    }
+    for (auto &V : c->vs)
+        for (auto &b : V.b_vis_slot) dev_free(b);
+    dev_free(c->b_bundle);
+    dev_free(c->b_rank_slot);
+    dev_free(c->b_inst_hist);
+    dev_free(c->b_inst_first);
+    dev_free(c->b_inst_offset);
+    dev_free(c->b_inst_tmp);
+    dev_free(c->b_inst_nb);
+    if (c->h_inst_nb) cudaFreeHost(c->h_inst_nb);
+    c->h_inst_nb = nullptr;
+}
+
+} // namespace
+
+extern "C" int32_t fyx_set_bundle_ids(fyx_ctx *c, uint32_t count, const uint32_t *idx, const uint32_t *ids)
+{
+    if (!c) return FYX_ERR_INVALID_ARGUMENT;
+    if (!c->have_topology) return fail(c, FYX_ERR_STATE, "fyx_set_topology has not been called");
+    if (!count) return FYX_OK;
+    if (!ids) return fail(c, FYX_ERR_INVALID_ARGUMENT, "bundle_ids is NULL");
+    CU(cudaSetDevice(c->device));
+    uint32_t mx = 0;
+    for (uint32_t i = 0; i < count; ++i) mx = std::max(mx, ids[i]);
+    if (mx >= (1u << 24)) return fail(c, FYX_ERR_INVALID_ARGUMENT, "bundle id %u too large: ids must be dense (< 2^24)", mx);
+    if (!c->have_bundles) {
+        int32_t rc = dev_ensure(c, c->b_bundle, std::max<size_t>(c->n_slots, 1) * 4);
+        if (rc) return rc;
+        CU(cudaMemsetAsync(c->b_bundle.p, 0, std::max<size_t>(c->n_slots, 1) * 4, c->stream));
+        c->have_bundles = true;
+        c->n_bundle_ids = 1;
+    }
+    c->n_bundle_ids = std::max(c->n_bundle_ids, mx + 1);
+    void *d_v = nullptr, *d_i = nullptr;
+    int32_t rc = stage_to_device(c, ids, (size_t)count * 4, idx, idx ? (size_t)count * 4 : 0, false, &d_v, &d_i);
+    if (rc) return rc;
+    launch_scatter_u32(c->stream, c->b_bundle.as<uint32_t>(), count, static_cast<const uint32_t *>(d_i),
+                       static_cast<const uint32_t *>(d_v), c->b_slot_of_node.as<uint32_t>(), c->n_nodes, 1);
+    c->launches++;
+    CU(cudaGetLastError());
+    return FYX_OK;
+}
+
+extern "C" int32_t fyx_enable_instances(fyx_ctx *c, uint32_t enable)
+{
+    if (!c) return FYX_ERR_INVALID_ARGUMENT;
+    c->instances_enabled = enable != 0;
+    return FYX_OK;
+}
+
+extern "C" int32_t fyx_pack_instances(fyx_ctx *c, uint32_t f, const float *view, const float *vp)
+{
+    if (!c) return FYX_ERR_INVALID_ARGUMENT;
+    if (!view || !vp) return fail(c, FYX_ERR_INVALID_ARGUMENT, "view / view_projection matrix is NULL");
+    if (!c->have_topology) return fail(c, FYX_ERR_STATE, "fyx_set_topology has not been called");
+    VisSlot &V = c->vs[c->cur];
+    if (V.pending) return fail(c, FYX_ERR_STATE, "the frame is still in flight: call fyx_frame_wait first");
+    if (f >= V.nf) return fail(c, FYX_ERR_INVALID_ARGUMENT, "frustum %u was not part of the last cull (%u frusta)", f, V.nf);
+    if (!V.have_slots) return fail(c, FYX_ERR_STATE, "the last cull was made without fyx_enable_instances");
+    CU(cudaSetDevice(c->device));
+    cudaStream_t s = c->stream;
+    if (!V.counts_on_host) {
+        CU(cudaMemcpy2DAsync(V.h_counts, sizeof(uint32_t), V.d_counts, sizeof(uint32_t) * kCountStride, sizeof(uint32_t), V.nf,
+                             cudaMemcpyDeviceToHost, s));
+        CU(cudaStreamSynchronize(s));
+        V.counts_on_host = true;
+    }
+    const uint32_t n = V.h_counts[f];
+    const uint32_t nb = c->have_bundles ? c->n_bundle_ids : 1u;
+    InstOut &o = c->inst[f];
+    o.valid = false;
+    int32_t rc;
+    const size_t n1 = std::max<uint32_t>(n, 1);
+    if ((rc = dev_ensure(c, o.b_node, n1 * 4))) return rc;
+    if ((rc = dev_ensure(c, o.b_sort, n1 * 8))) return rc;
+    if ((rc = dev_ensure(c, o.b_mats, n1 * 128))) return rc;
+    if ((rc = dev_ensure(c, o.b_bundles, (size_t)nb * sizeof(fyx_bundle)))) return rc;
+    if ((rc = dev_ensure(c, c->b_inst_hist, (size_t)nb * 4))) return rc;
+    if ((rc = dev_ensure(c, c->b_inst_first, (size_t)nb * 8))) return rc;
+    if ((rc = dev_ensure(c, c->b_inst_offset, (size_t)nb * 4))) return rc;
+    if ((rc = dev_ensure(c, c->b_inst_tmp, n1 * 8))) return rc;
+    if ((rc = dev_ensure(c, c->b_inst_nb, 256))) return rc;
+    if (!c->h_inst_nb) CU(cudaHostAlloc(reinterpret_cast<void **>(&c->h_inst_nb), 64, cudaHostAllocDefault));
+    // DFS rank per slot (bundle sort index = that of the instance the reference's DFS pushes first)
+    const bool have_rank = c->dfs_rank.size() == c->n_nodes && c->n_nodes > 0;
+    if (have_rank && !c->rank_on_device) {
+        std::vector<uint32_t> r(c->n_slots);
+        for (uint32_t sl = 0; sl < c->n_slots; ++sl) r[sl] = c->dfs_rank[c->node_of_slot[sl]];
+        if ((rc = dev_ensure(c, c->b_rank_slot, std::max<size_t>(c->n_slots, 1) * 4))) return rc;
+        CU(cudaStreamSynchronize(s));
+        if (c->n_slots) CU(cudaMemcpy(c->b_rank_slot.p, r.data(), (size_t)c->n_slots * 4, cudaMemcpyHostToDevice));
+        c->rank_on_device = true;
+    }
+    CU(cudaMemsetAsync(c->b_inst_hist.p, 0, (size_t)nb * 4, s));
+    CU(cudaMemsetAsync(c->b_inst_first.p, 0xFF, (size_t)nb * 8, s));
+
+    InstParams ip{};
+    ip.n = n;
+    ip.vis_node = V.b_vis[f].as<uint32_t>();
+    ip.vis_slot = V.b_vis_slot[f].as<uint32_t>();
+    ip.bundle_of_slot = c->have_bundles ? c->b_bundle.as<uint32_t>() : nullptr;
+    ip.rank_of_slot = have_rank ? c->b_rank_slot.as<uint32_t>() : nullptr;
+    memcpy(ip.view, view, 64);
+    memcpy(ip.vp, vp, 64);
+    ip.n_bundle_ids = nb;
+    ip.hist = c->b_inst_hist.as<uint32_t>();
+    ip.first_key = c->b_inst_first.as<unsigned long long>();
+    ip.offset = c->b_inst_offset.as<uint32_t>();
+    ip.tmp_sort = c->b_inst_tmp.as<uint64_t>();
+    ip.o_node = o.b_node.as<uint32_t>();
+    ip.o_sort = o.b_sort.as<uint64_t>();
+    ip.o_mats = o.b_mats.as<float4>();
+    ip.o_bundles = o.b_bundles.as<fyx_bundle>();
+    ip.o_n_bundles = c->b_inst_nb.as<uint32_t>();
+    launch_pack_instances(s, c->a, ip);
+    c->launches += n ? 3 : 1;
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(c->h_inst_nb, c->b_inst_nb.p, 4, cudaMemcpyDeviceToHost, s));
+    rc = sync_and_check(c);
+    if (rc) return rc;
+    o.count = n;
+    o.n_bundles = *c->h_inst_nb;
+    o.on_host = false;
+    o.valid = true;
+    return FYX_OK;
+}
+
+extern "C" int32_t fyx_get_instances_device(fyx_ctx *c, uint32_t f, fyx_instances *out)
+{
+    if (!c || !out) return FYX_ERR_INVALID_ARGUMENT;
+    if (f >= FYX_MAX_FRUSTA || !c->inst[f].valid) return fail(c, FYX_ERR_STATE, "fyx_pack_instances has not been called for frustum %u", f);
+    const InstOut &o = c->inst[f];
+    out->count = o.count;
+    out->n_bundles = o.n_bundles;
+    out->node = o.b_node.as<uint32_t>();
+    out->sort_index = o.b_sort.as<uint64_t>();
+    out->matrices = o.b_mats.as<float>();
+    out->bundles = o.b_bundles.as<fyx_bundle>();
+    return FYX_OK;
+}
+
+extern "C" int32_t fyx_get_instances(fyx_ctx *c, uint32_t f, fyx_instances *out)
+{
+    if (!c || !out) return FYX_ERR_INVALID_ARGUMENT;
+    if (f >= FYX_MAX_FRUSTA || !c->inst[f].valid) return fail(c, FYX_ERR_STATE, "fyx_pack_instances has not been called for frustum %u", f);
+    InstOut &o = c->inst[f];
+    CU(cudaSetDevice(c->device));
+    if (!o.on_host) {
+        const size_t bytes[4] = {(size_t)o.count * 4, (size_t)o.count * 8, (size_t)o.count * 128, (size_t)o.n_bundles * sizeof(fyx_bundle)};
+        const void *src[4] = {o.b_node.p, o.b_sort.p, o.b_mats.p, o.b_bundles.p};
+        for (int k = 0; k < 4; ++k) {
+            int32_t rc = inst_host_ensure(c, &o.h[k], &o.h_cap[k], std::max<size_t>(bytes[k], 1));
+            if (rc) return rc;
+            if (bytes[k]) CU(cudaMemcpyAsync(o.h[k], src[k], bytes[k], cudaMemcpyDeviceToHost, c->stream));
+        }
+        CU(cudaStreamSynchronize(c->stream));
+        o.on_host = true;
+    }
+    out->count = o.count;
+    out->n_bundles = o.n_bundles;
+    out->node = static_cast<const uint32_t *>(o.h[0]);
+    out->sort_index = static_cast<const uint64_t *>(o.h[1]);
+    out->matrices = static_cast<const float *>(o.h[2]);
+    out->bundles = static_cast<const fyx_bundle *>(o.h[3]);
+    return FYX_OK;
+}

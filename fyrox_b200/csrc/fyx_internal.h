@@ -41,6 +41,7 @@ struct CullParams {
     int nf;
     FrustumDev f[FYX_MAX_FRUSTA];
     uint32_t *out[FYX_MAX_FRUSTA]; // visible lists
+    uint32_t *out_slot[FYX_MAX_FRUSTA]; // the same entries as HBM slots (nullptr unless fyx_enable_instances)
     uint32_t *counts;              // counts[f * kCountStride]
     float one, negzero;            // 1.0f, -0.0f: run-time operands of the unfusable packed FMAs (fyx_math.cuh)
 };
@@ -76,6 +77,29 @@ struct FoldArrays {
     const uint32_t *stale_idx;  // nullptr when no such bone exists
     const float4 *stale_pos;
 };
+
+// N3 draw-prep (fyx_drawprep.cu): one frustum's visible list -> instances grouped by bundle
+struct InstParams {
+    uint32_t n;                     // visible entries
+    const uint32_t *vis_node;       // the visible list (node indices)
+    const uint32_t *vis_slot;       // the same entries as slots
+    const uint32_t *bundle_of_slot; // nullptr = every node in bundle 0
+    const uint32_t *rank_of_slot;   // pre-order DFS rank (fyx_set_dfs_order); nullptr = node index order
+    float view[16], vp[16];         // column-major
+    uint32_t n_bundle_ids;
+    // scratch (hist and first_key are cleared by the caller: 0 / ~0)
+    uint32_t *hist;                 // n_bundle_ids: instances per bundle, then the scatter cursor
+    unsigned long long *first_key;  // n_bundle_ids: min (rank << 32 | list position) of the bundle
+    uint32_t *offset;               // n_bundle_ids: first instance of the bundle
+    uint64_t *tmp_sort;             // n
+    // outputs
+    uint32_t *o_node;
+    uint64_t *o_sort;
+    float4 *o_mats;                 // 8 float4 per instance: world (4 columns), view_projection * world (4 columns)
+    fyx_bundle *o_bundles;
+    uint32_t *o_n_bundles;
+};
+void launch_pack_instances(cudaStream_t s, const NodeArrays &a, const InstParams &ip);
 
 // ---- launchers (fyx_kernels.cu) ----
 void launch_update_level(cudaStream_t s, const NodeArrays &a, uint32_t lo, uint32_t hi, bool update_all,

@@ -103,7 +103,8 @@ __device__ __forceinline__ uint32_t cull_bits(const uint32_t nf, const uint32_t 
 // RenderDataBundleStorage::push (renderer/bundle.rs:1248-1278).  Order inside a list is unspecified.
 // Must be called by every thread of the CTA.
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void compact_emit(const uint32_t vis_bits, const uint32_t node_index, const CullParams &cp)
+__device__ __forceinline__ void compact_emit(const uint32_t vis_bits, const uint32_t node_index, const uint32_t slot,
+                                             const CullParams &cp)
 {
     constexpr int kWarps = kBlock / 32;
     __shared__ uint32_t s_wcount[FYX_MAX_FRUSTA][kWarps];
@@ -138,6 +139,7 @@ __device__ __forceinline__ void compact_emit(const uint32_t vis_bits, const uint
         if (bit) {
             const uint32_t pos = s_base[f] + s_wcount[f][warp] + __popc(b & ((1u << lane) - 1u));
             cp.out[f][pos] = node_index;
+            if (cp.out_slot[f]) cp.out_slot[f][pos] = slot; // where the node lives in HBM (fyx_pack_instances)
         }
     }
 }
@@ -224,7 +226,7 @@ __global__ void __launch_bounds__(kBlock) k_update_level(const NodeArrays a, con
     uint32_t vis_bits = 0u, gi = 0u;
     if (slot < hi) update_node<FUSE>(a, slot, update_all, cp, vis_bits, gi);
     else pdl_wait();
-    if (FUSE) compact_emit(vis_bits, gi, cp);
+    if (FUSE) compact_emit(vis_bits, gi, slot, cp);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -244,7 +246,7 @@ __global__ void __launch_bounds__(kBlock) k_cull(const NodeArrays a, const CullP
         vis_bits = cull_bits(nf, mask, wx, wy, wz, cp);
         if (vis_bits) gi = a.gidx[slot];
     }
-    compact_emit(vis_bits, gi, cp);
+    compact_emit(vis_bits, gi, slot, cp);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -334,7 +336,7 @@ __global__ void __launch_bounds__(kBlock) k_fold_bones(const NodeArrays a, const
     const uint32_t i = (blockIdx.x * kBlock + threadIdx.x) >> 5; // mesh = warp
     uint32_t vis_bits = 0u, gi = 0u;
     if (i < fa.n) fold_mesh<FUSE>(a, fa, i, threadIdx.x & 31u, cp, vis_bits, gi);
-    if (FUSE) compact_emit(vis_bits, gi, cp);
+    if (FUSE) compact_emit(vis_bits, gi, vis_bits ? fa.node_slot[i] : 0u, cp);
 }
 
 // positions of the "late" bones (see FoldArrays) as stored before the update starts

@@ -268,6 +268,46 @@ int32_t fyx_get_timings(fyx_ctx *ctx, fyx_timings *out);
 /* Number of kernels this context has launched so far (bench.py's gpu_launches). */
 uint64_t fyx_kernel_launch_count(const fyx_ctx *ctx);
 
+/* ---- N3: draw-prep after the cull ------------------------------------------------ */
+/* What RenderDataBundleStorage::push and RenderDataBundle::write_uniforms do per visible surface on the CPU
+ * (renderer/bundle.rs:1248-1278, 483-487), for nodes with ONE surface: the instances of a frustum's visible
+ * list grouped by bundle, each with its sort index, world matrix and view_projection * world. */
+
+/* Per-node bundle id = the host's dense id for the (material, surface data, render path) key that push()
+ * hashes (renderer/bundle.rs:1253-1257); every node starts in bundle 0.  idx NULL = nodes 0..count-1. */
+int32_t fyx_set_bundle_ids(fyx_ctx *ctx, uint32_t count, const uint32_t *idx, const uint32_t *bundle_ids);
+/* Ask the culls that follow to also record where each visible node lives in HBM (4 more bytes written per
+ * visible entry); required before fyx_pack_instances. */
+int32_t fyx_enable_instances(fyx_ctx *ctx, uint32_t enable);
+
+typedef struct fyx_bundle {
+    uint32_t id;          /* the bundle id given to fyx_set_bundle_ids */
+    uint32_t first;       /* first instance of the bundle in the packed arrays */
+    uint32_t count;       /* RenderDataBundle::instances.len() */
+    uint32_t reserved;
+    uint64_t sort_index;  /* RenderDataBundle::sort_index: that of the instance pushed first (bundle.rs:1264-1268), i.e.
+                           * first in the DFS order given to fyx_set_dfs_order, else the lowest node index */
+} fyx_bundle;
+
+typedef struct fyx_instances {
+    uint32_t count;             /* instances (== the visible count of the frustum) */
+    uint32_t n_bundles;         /* non-empty bundles */
+    const uint32_t *node;       /* [count]   SurfaceInstanceData::node_handle (index) */
+    const uint64_t *sort_index; /* [count]   RenderContext::calculate_sorting_index(global_position) (bundle.rs:118-127) */
+    const float *matrices;      /* [count*32] per instance: world_transform (identity for a skinned surface,
+                                 * scene/mesh/mod.rs:733-737), then view_projection * world_transform (bundle.rs:485);
+                                 * both column-major — the first 128 bytes of the instance uniform block */
+    const fyx_bundle *bundles;  /* [n_bundles] ascending id; bundle b owns instances [first, first+count) in unspecified order */
+} fyx_instances;
+
+/* Pack the visible list of `frustum` (of the most recent cull, made with instances enabled) for an observer
+ * with the given view and view-projection matrices (ObserverPosition, renderer/observer.rs). */
+int32_t fyx_pack_instances(fyx_ctx *ctx, uint32_t frustum, const float *view_m16, const float *view_projection_m16);
+/* Result of the last fyx_pack_instances for that frustum: pointers to pinned host copies ... */
+int32_t fyx_get_instances(fyx_ctx *ctx, uint32_t frustum, fyx_instances *out);
+/* ... or to the device-resident arrays (count / n_bundles still come back as host values). */
+int32_t fyx_get_instances_device(fyx_ctx *ctx, uint32_t frustum, fyx_instances *out);
+
 /* ---- multi-GPU: one context per GPU, one process per GPU ------------------------------------- */
 /* The node array is sharded (sub-trees + replicated ancestors); each context culls its
  * shard; the per-frustum visible lists are all-gathered with NCCL over NVLink so every rank holds

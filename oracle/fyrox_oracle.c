@@ -1041,6 +1041,29 @@ uint32_t orc_mesh_skin(const orc_graph *g, uint32_t mesh, uint32_t surface, floa
     return s->n_verts;
 }
 
+/* N3 — what Mesh::collect_render_data pushes for a node with ONE surface (scene/mesh/mod.rs:700 sort index of
+ * global_position(); :731-737 world = identity if the surface is skinned, else global_transform()) and what
+ * RenderDataBundle::write_uniforms derives from it (renderer/bundle.rs:483-487: world, view_projection * world).
+ * A node without surfaces is treated as unskinned.  Returns the sort index. */
+uint64_t orc_node_instance(const orc_graph *g, uint32_t node, const float view[16], const float vp[16],
+                           float world[16], float wvp[16])
+{
+    const orc_node *n = node_at(g, node);
+    if (!n) {
+        orc_mat4_identity(world);
+        orc_mat4_mul(vp, world, wvp);
+        return 0;
+    }
+    int skinned = 0;
+    for (uint32_t si = 0; si < n->n_surfaces; ++si)
+        if (n->surfaces[si].n_bones) skinned = 1;
+    if (skinned) orc_mat4_identity(world);
+    else memcpy(world, n->global_transform, 64);
+    orc_mat4_mul(vp, world, wvp);
+    const float gp[3] = {n->global_transform[12], n->global_transform[13], n->global_transform[14]};
+    return orc_calculate_sorting_index(view, gp);
+}
+
 /* Mesh::accurate_world_bounding_box — scene/mesh/mod.rs:468-526 */
 void orc_mesh_accurate_world_bounding_box(const orc_graph *g, uint32_t mesh, orc_aabb *out)
 {

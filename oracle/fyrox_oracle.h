@@ -166,6 +166,8 @@ size_t orc_from_graph(const orc_graph *g, const orc_frustum *f, uint32_t render_
  * standard.shader:192-195 in the same op order) */
 uint32_t orc_mesh_bone_matrices(const orc_graph *g, uint32_t mesh, uint32_t surface, float *out_m16);
 uint32_t orc_mesh_skin(const orc_graph *g, uint32_t mesh, uint32_t surface, float *out_pos3, float *out_nrm3);
+uint64_t orc_node_instance(const orc_graph *g, uint32_t node, const float view[16], const float vp[16],
+                           float world[16], float wvp[16]);   /* N3: mesh/mod.rs:700,731-737 + bundle.rs:483-487 */
 void     orc_mesh_accurate_world_bounding_box(const orc_graph *g, uint32_t mesh, orc_aabb *out);
 
 /* free-standing skin of one vertex array with a given palette (used by the bench CPU baseline) */

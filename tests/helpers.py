@@ -142,3 +142,20 @@ def random_graph(rng, n, p_dead=0.05, p_orphan=0.01, p_mesh=0.6, max_depth_bias=
     aabb[is_mesh, :3] = -h[is_mesh]
     aabb[is_mesh, 3:] = h[is_mesh]
     return parent, flags, mask, local, aabb
+
+
+def preorder_rank(parent):
+    """Pre-order DFS rank from node 0 with children in index order (what ob.Graph.build produces)."""
+    n = len(parent)
+    kids = [[] for _ in range(n)]
+    for i in range(1, n):
+        if parent[i] != NONE:
+            kids[int(parent[i])].append(i)
+    rank = np.full(n, NONE, np.uint32)
+    stack, r = [0], 0
+    while stack:
+        x = stack.pop()
+        rank[x] = r
+        r += 1
+        stack.extend(reversed(kids[x]))
+    return rank

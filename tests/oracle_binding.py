@@ -145,6 +145,7 @@ def lib() -> C.CDLL:
         "orc_from_graph": (C.c_size_t, [vp, C.POINTER(Frustum), C.c_uint32, C.c_int, vp, C.c_size_t]),
         "orc_mesh_bone_matrices": (C.c_uint32, [vp, C.c_uint32, C.c_uint32, f32p]),
         "orc_mesh_skin": (C.c_uint32, [vp, C.c_uint32, C.c_uint32, f32p, f32p]),
+        "orc_node_instance": (C.c_uint64, [vp, C.c_uint32, f32p, f32p, f32p, f32p]),
         "orc_mesh_accurate_world_bounding_box": (None, [vp, C.c_uint32, C.POINTER(Aabb)]),
         "orc_skin_vertices": (None, [f32p, C.c_uint32, vp, C.POINTER(VertexLayout), f32p, f32p]),
     }
@@ -325,6 +326,15 @@ class Graph:
         out = np.empty(max(cap, 1), dtype=np.uint32)
         n = self.L.orc_from_graph(self.h, C.byref(frustum) if frustum is not None else None, render_mask, int(shadow_pass), out.ctypes.data_as(C.c_void_p), cap)
         return out[:n].copy()
+
+    def instance(self, node, view_m16, vp_m16):
+        """(sort_index, world[16], wvp[16]) of what collect_render_data / write_uniforms produce for the node."""
+        v = np.ascontiguousarray(view_m16, dtype=np.float32).reshape(16)
+        p = np.ascontiguousarray(vp_m16, dtype=np.float32).reshape(16)
+        w = np.empty(16, dtype=np.float32)
+        wvp = np.empty(16, dtype=np.float32)
+        si = self.L.orc_node_instance(self.h, int(node), fp(v), fp(p), fp(w), fp(wvp))
+        return int(si), w, wvp
 
     def bone_matrices(self, mesh, surface, n_bones):
         out = np.empty((n_bones, 16), dtype=np.float32)

@@ -1,0 +1,140 @@
+"""N3 — draw-prep after the cull: fyx_pack_instances against the oracle.
+
+Reference: Mesh::collect_render_data (scene/mesh/mod.rs:691-805: sort index, world = identity for skinned
+surfaces), RenderDataBundleStorage::push (renderer/bundle.rs:1248-1278: bundle = (material, data, path) key, its
+sort index is that of the first instance pushed, i.e. first in DFS order), RenderDataBundle::write_uniforms
+(renderer/bundle.rs:483-487: world, view_projection * world).  Bit-exact per instance; order inside a bundle is a set.
+"""
+import numpy as np
+import pytest
+
+import fyrox_b200 as fb
+import oracle_binding as ob
+from fyrox_b200.scenegen import Scene
+from helpers import bits_equal, preorder_rank, random_graph, scene_pair
+
+pytestmark = pytest.mark.gpu
+
+
+def observer(eye, target, up=(0, 1, 0), aspect=16 / 9, fovy=np.deg2rad(60.0), zn=0.1, zf=150.0):
+    view = ob.look_at_rh(eye, target, up)
+    proj = ob.perspective(float(aspect), float(fovy), float(zn), float(zf))
+    vp = ob.mat4_mul(proj, view)  # bundle.rs:894: projection * view
+    return view, vp, ob.frustum_from_vp(vp), fb.frustum_from_view_projection_matrix(vp)
+
+
+def check_instances(og, ctx, f, fo, view, vp, bundle_of_node, rank=None, mask=0xFFFFFFFF, shadow=False):
+    inst = ctx.pack_instances(f, view, vp)
+    dfs = og.from_graph(fo, mask, shadow)  # the reference's push order
+    node = inst["node"]
+    assert node.size == dfs.size and np.array_equal(np.sort(node), np.sort(dfs))
+    assert np.array_equal(np.sort(node), np.sort(ctx.get_visible(f)))
+    # per instance: sort index, world, wvp
+    for k in range(node.size):
+        si, w, wvp = og.instance(int(node[k]), view, vp)
+        assert int(inst["sort_index"][k]) == si, f"sort index of node {node[k]}"
+        assert bits_equal(inst["world"][k], w).all(), f"world of node {node[k]}"
+        assert bits_equal(inst["wvp"][k], wvp).all(), f"wvp of node {node[k]}"
+    # bundle table: ascending ids of the non-empty bundles, a partition of [0, n)
+    b = inst["bundles"]
+    ids_vis = bundle_of_node[node]
+    want_ids = np.unique(ids_vis)
+    assert np.array_equal(b["id"], want_ids)
+    assert b["first"][0] == 0 if b.size else node.size == 0
+    assert np.array_equal(b["first"][1:], np.cumsum(b["count"])[:-1])
+    assert int(b["count"].sum()) == node.size
+    first_pushed = {}
+    if rank is not None:
+        for n_ in dfs:  # DFS order: the first instance of each bundle fixes RenderDataBundle::sort_index
+            first_pushed.setdefault(int(bundle_of_node[n_]), int(n_))
+    for row in b:
+        sl = slice(int(row["first"]), int(row["first"] + row["count"]))
+        assert (ids_vis[sl] == row["id"]).all(), "an instance sits in the wrong bundle"
+        members = node[sl]
+        lead = first_pushed[int(row["id"])] if rank is not None else int(members.min())
+        assert int(row["sort_index"]) == og.instance(lead, view, vp)[0]
+    return node.size
+
+
+def test_instances_of_generated_scene_match_oracle(ctx):
+    sc = Scene(6000, 12)
+    og, _ = scene_pair(sc, ctx, with_vertices=False)
+    og.update_hierarchical_data()
+    rng = np.random.default_rng(5)
+    bundle = rng.integers(0, 41, sc.capacity).astype(np.uint32)
+    bundle[bundle == 7] = 8  # leave holes in the id space
+    ctx.set_bundle_ids(bundle)
+    ctx.enable_instances()
+    view, vp, fo, ff = observer((3, 2, 25), (0, 0, -10))
+    ctx.update_and_cull([ff], fb.UPDATE_ALL)
+    n = check_instances(og, ctx, 0, fo, view, vp, bundle)
+    assert n > 50
+    # skinned meshes among them carry identity
+    meshes = {sc.unit_mesh_node(u) for u in range(sc.n_units)}
+    inst = ctx.pack_instances(0, view, vp)
+    hit = [k for k, nd in enumerate(inst["node"]) if int(nd) in meshes]
+    for k in hit:
+        assert np.array_equal(inst["world"][k], np.eye(4, dtype=np.float32).reshape(16))
+    # stand-alone cull, several frusta, each with its own observer
+    obs = [observer((0, 0, 0), (1, 0, 0), (0, -1, 0), 1.0, np.pi / 2, 0.01, 120.0), observer((0, 0, 0), (0, 0, -1)), observer((10, 5, 0), (0, 0, 0))]
+    ctx.cull([o[3] for o in obs])
+    for f, (v, p, fo_, _) in enumerate(obs):
+        check_instances(og, ctx, f, fo_, v, p, bundle)
+
+
+def test_bundle_sort_index_follows_the_dfs_push_order(ctx):
+    rng = np.random.default_rng(77)
+    parent, flags, mask, local, aabb = random_graph(rng, 3000, p_orphan=0.02)
+    og = ob.Graph.build(parent, flags, mask, local, aabb)
+    og.update_hierarchical_data()
+    ctx.set_topology(parent, flags, mask, aabb)
+    rank = preorder_rank(parent)
+    ctx.set_dfs_order(rank)
+    ctx.set_local_matrices(local)
+    bundle = rng.integers(0, 9, len(parent)).astype(np.uint32)
+    ctx.set_bundle_ids(bundle)
+    ctx.enable_instances()
+    view, vp, fo, ff = observer((0, 0, 60), (0, 0, 0), zf=200.0)
+    ctx.update_and_cull([ff], fb.UPDATE_ALL)
+    assert check_instances(og, ctx, 0, fo, view, vp, bundle, rank=rank) > 20
+    # index-shuffled forest: the first-pushed instance is generally NOT the lowest node index
+    dfs = og.from_graph(fo)
+    differs = 0
+    for b_ in np.unique(bundle[dfs]):
+        m = dfs[bundle[dfs] == b_]
+        differs += int(m[0] != m.min())
+    assert differs > 0
+    # shadow pass + camera mask go through the same lists
+    ctx.cull([ff], cam_mask=[0x0000FFFF], pass_flags=[fb.PASS_SHADOW])
+    check_instances(og, ctx, 0, fo, view, vp, bundle, rank=rank, mask=0x0000FFFF, shadow=True)
+
+
+def test_instances_edge_cases(ctx):
+    # default bundle (no ids given), empty visible list, projective / degenerate view matrices, errors
+    sc = Scene(800, 2)
+    og, _ = scene_pair(sc, ctx, with_vertices=False)
+    og.update_hierarchical_data()
+    view, vp, fo, ff = observer((0, 0, 0), (0, 0, -1))
+    ctx.update_and_cull([ff], fb.UPDATE_ALL)
+    with pytest.raises(fb.FyxError):
+        ctx.pack_instances(0, view, vp)  # cull made without enable_instances
+    ctx.enable_instances()
+    ctx.cull([ff])
+    zeros = np.zeros(sc.capacity, np.uint32)
+    check_instances(og, ctx, 0, fo, view, vp, zeros)
+    with pytest.raises(fb.FyxError):
+        ctx.pack_instances(3, view, vp)
+    # a view matrix with a projective bottom row and one whose n is 0 for some points (transform_point skips the divide)
+    weird = view.copy()
+    weird[3], weird[7], weird[11], weird[15] = 0.01, -0.02, 0.005, 0.0
+    check_instances(og, ctx, 0, fo, weird, vp, zeros)
+    huge = view.copy() * np.float32(1e30)  # sort index saturates at both ends / NaN -> centre
+    check_instances(og, ctx, 0, fo, huge, vp, zeros)
+    # nothing visible
+    _, _, fo2, ff2 = observer((0, 5000, 0), (0, 6000, 0), (1, 0, 0))
+    ctx.cull([ff2])
+    inst = ctx.pack_instances(0, view, vp)
+    assert inst["node"].size == 0 and inst["bundles"].size == 0
+    # ids must be dense
+    with pytest.raises(fb.FyxError):
+        ctx.set_bundle_ids(np.array([1 << 30], np.uint32), [1])

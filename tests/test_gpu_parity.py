@@ -6,7 +6,7 @@ import pytest
 import fyrox_b200 as fb
 import oracle_binding as ob
 from fyrox_b200.scenegen import Scene
-from helpers import (NONE, UNIT_BOX, assert_same_hierarchy, assert_same_visible, camera_frustum, cube_frusta, random_graph,
+from helpers import (NONE, preorder_rank, UNIT_BOX, assert_same_hierarchy, assert_same_visible, camera_frustum, cube_frusta, random_graph,
                      scene_pair)
 
 pytestmark = pytest.mark.gpu
@@ -627,23 +627,6 @@ def test_topology_change_keeps_surfaces_and_flag_changes_resize_nothing(ctx):
         assert pos_g.tobytes() == pos_o.tobytes() and nrm_g.tobytes() == nrm_o.tobytes()
 
 
-def _preorder_rank(parent):
-    """Pre-order DFS rank from node 0 with children in index order (what ob.Graph.build produces)."""
-    n = len(parent)
-    kids = [[] for _ in range(n)]
-    for i in range(1, n):
-        if parent[i] != NONE:
-            kids[int(parent[i])].append(i)
-    rank = np.full(n, NONE, np.uint32)
-    stack, r = [0], 0
-    while stack:
-        x = stack.pop()
-        rank[x] = r
-        r += 1
-        stack.extend(reversed(kids[x]))
-    return rank
-
-
 def test_dfs_order_quirk_is_reproduced_exactly(ctx):
     """Skinned meshes that come BEFORE (some of) their bones in the reference's DFS: the reference folds those
     bones' positions from before the update (scene/mesh/mod.rs:676-682).  With fyx_set_dfs_order the boxes
@@ -685,7 +668,7 @@ def test_dfs_order_quirk_is_reproduced_exactly(ctx):
     local = random_locals()
     og = ob.Graph.build(parent, flags, None, local, aabb)
     ctx.set_topology(parent, flags, None, aabb)
-    ctx.set_dfs_order(_preorder_rank(parent))
+    ctx.set_dfs_order(preorder_rank(parent))
     ctx.set_local_matrices(local)
     meshes = np.array([m for m, _ in surf], np.uint32)
     for mesh, bones in surf:
