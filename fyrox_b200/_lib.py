@@ -98,7 +98,39 @@ class fyx_frame_desc(C.Structure):
         ("do_skin", C.c_uint32),
         ("readback_visible", C.c_uint32),
         ("flags", C.c_uint32),
+        ("do_animate", C.c_uint32),
+        ("animate_dt", C.c_float),
     ]
+
+
+class fyx_curve_key(C.Structure):
+    _fields_ = [("location", C.c_float), ("value", C.c_float), ("kind", C.c_uint32), ("left_tangent", C.c_float), ("right_tangent", C.c_float)]
+
+
+class fyx_anim_track(C.Structure):
+    _fields_ = [("target_node", C.c_uint32), ("binding", C.c_uint32), ("value_kind", C.c_uint32), ("enabled", C.c_uint32),
+                ("n_curves", C.c_uint32), ("first_key", C.c_uint32 * 4), ("n_keys", C.c_uint32 * 4)]
+
+
+class fyx_animation_desc(C.Structure):
+    _fields_ = [
+        ("struct_size", C.c_uint32),
+        ("n_tracks", C.c_uint32),
+        ("tracks", C.c_void_p),
+        ("n_keys", C.c_uint32),
+        ("keys", C.c_void_p),
+        ("speed", C.c_float),
+        ("time_position", C.c_float),
+        ("time_slice_start", C.c_float),
+        ("time_slice_end", C.c_float),
+        ("looped", C.c_uint32),
+        ("enabled", C.c_uint32),
+    ]
+
+
+KEY_CONSTANT, KEY_LINEAR, KEY_CUBIC = 0, 1, 2
+TV_REAL, TV_VECTOR2, TV_VECTOR3, TV_VECTOR4, TV_QUAT_EULER, TV_QUAT = range(6)
+BIND_POSITION, BIND_SCALE, BIND_ROTATION = 0, 1, 2
 
 
 class fyx_bundle(C.Structure):
@@ -161,6 +193,14 @@ SYMBOLS = {
     "fyx_get_skinned_device": (C.c_int32, [ctx_p, C.c_uint32, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]),
     "fyx_get_timings": (C.c_int32, [ctx_p, C.POINTER(fyx_timings)]),
     "fyx_kernel_launch_count": (C.c_uint64, [ctx_p]),
+    "fyx_anim_add": (C.c_int32, [ctx_p, C.POINTER(fyx_animation_desc), u32p]),
+    "fyx_anim_clear": (C.c_int32, [ctx_p]),
+    "fyx_anim_set_enabled": (C.c_int32, [ctx_p, C.c_uint32, C.c_uint32]),
+    "fyx_anim_set_track_enabled": (C.c_int32, [ctx_p, C.c_uint32, C.c_uint32, C.c_uint32]),
+    "fyx_anim_set_speed": (C.c_int32, [ctx_p, C.c_uint32, C.c_float]),
+    "fyx_anim_set_time_position": (C.c_int32, [ctx_p, C.c_uint32, C.c_float]),
+    "fyx_anim_get_time_positions": (C.c_int32, [ctx_p, C.c_uint32, C.c_uint32, C.c_void_p]),
+    "fyx_animate": (C.c_int32, [ctx_p, C.c_float]),
     "fyx_set_bundle_ids": (C.c_int32, [ctx_p, C.c_uint32, C.c_void_p, C.c_void_p]),
     "fyx_enable_instances": (C.c_int32, [ctx_p, C.c_uint32]),
     "fyx_pack_instances": (C.c_int32, [ctx_p, C.c_uint32, C.c_void_p, C.c_void_p]),

@@ -277,6 +277,52 @@ class Context:
         self._chk(self._lib.fyx_get_visible_device(self._h, frustum, C.byref(d_idx), C.byref(d_cnt)))
         return d_idx.value, d_cnt.value
 
+    # ---- N2: animation sampling on the device ----
+    KEY_DTYPE = np.dtype([("location", "<f4"), ("value", "<f4"), ("kind", "<u4"), ("left_tangent", "<f4"), ("right_tangent", "<f4")])
+    TRACK_DTYPE = np.dtype([("target_node", "<u4"), ("binding", "<u4"), ("value_kind", "<u4"), ("enabled", "<u4"), ("n_curves", "<u4"),
+                            ("first_key", "<u4", 4), ("n_keys", "<u4", 4)])
+
+    def anim_add(self, tracks, keys, speed=1.0, looped=True, time_slice=(0.0, 0.0), time_position=0.0, enabled=True) -> int:
+        """Add an Animation (fyrox-animation/src/lib.rs): tracks = TRACK_DTYPE array, keys = KEY_DTYPE array."""
+        tracks = np.ascontiguousarray(tracks, dtype=self.TRACK_DTYPE)
+        keys = np.ascontiguousarray(keys, dtype=self.KEY_DTYPE)
+        d = L.fyx_animation_desc()
+        d.struct_size = C.sizeof(L.fyx_animation_desc)
+        d.n_tracks, d.tracks = len(tracks), tracks.ctypes.data
+        d.n_keys, d.keys = len(keys), keys.ctypes.data
+        d.speed, d.time_position = float(speed), float(time_position)
+        d.time_slice_start, d.time_slice_end = float(time_slice[0]), float(time_slice[1])
+        d.looped, d.enabled = int(bool(looped)), int(bool(enabled))
+        out = C.c_uint32()
+        self._chk(self._lib.fyx_anim_add(self._h, C.byref(d), C.byref(out)))
+        return out.value
+
+    def anim_clear(self):
+        self._chk(self._lib.fyx_anim_clear(self._h))
+
+    def anim_set_enabled(self, anim: int, enabled: bool):
+        self._chk(self._lib.fyx_anim_set_enabled(self._h, anim, int(bool(enabled))))
+
+    def anim_set_track_enabled(self, anim: int, track: int, enabled: bool):
+        self._chk(self._lib.fyx_anim_set_track_enabled(self._h, anim, track, int(bool(enabled))))
+
+    def anim_set_speed(self, anim: int, speed: float):
+        self._chk(self._lib.fyx_anim_set_speed(self._h, anim, float(speed)))
+
+    def anim_set_time_position(self, anim: int, t: float):
+        self._chk(self._lib.fyx_anim_set_time_position(self._h, anim, float(t)))
+
+    def anim_time_positions(self, first: int = 0, count: Optional[int] = None) -> np.ndarray:
+        out = np.empty(0 if count is None else count, dtype=np.float32)
+        if count is None:
+            raise ValueError("count is required")
+        self._chk(self._lib.fyx_anim_get_time_positions(self._h, first, count, out.ctypes.data_as(C.c_void_p)))
+        return out
+
+    def animate(self, dt: float):
+        """AnimationContainer::update_animations(dt) for every animation (scene/animation/mod.rs:83-88)."""
+        self._chk(self._lib.fyx_animate(self._h, float(dt)))
+
     # ---- N3: draw-prep after the cull ----
     def set_bundle_ids(self, ids, idx=None):
         """Per-node bundle id = dense id of the (material, surface data, render path) key of
@@ -321,7 +367,8 @@ class Context:
         self._chk(self._lib.fyx_skin(self._h))
 
     def render_prep(self, *, update_flags=L.UPDATE_INCREMENTAL, changed_m16=None, changed_trs=None, changed_rot=None, changed_idx=None, n_changed=None, frusta=(), cam_mask=None,
-                    pass_flags=None, do_palettes=True, do_skin=True, readback_visible=True, async_=False, allgather=False):
+                    pass_flags=None, do_palettes=True, do_skin=True, readback_visible=True, async_=False, allgather=False,
+                    animate_dt=None):
         """One frame (fyx_render_prep). changed_m16 / changed_idx may be numpy arrays or raw (pinned) addresses."""
         d = L.fyx_frame_desc()
         d.struct_size = C.sizeof(L.fyx_frame_desc)
@@ -360,6 +407,9 @@ class Context:
         d.do_skin = 1 if do_skin else 0
         d.readback_visible = 1 if readback_visible else 0
         d.flags = (L.FRAME_ASYNC if async_ else 0) | (L.FRAME_ALLGATHER if allgather else 0)
+        if animate_dt is not None:
+            d.do_animate = 1
+            d.animate_dt = float(animate_dt)
         if async_:
             self._async_keep = keep  # inputs must outlive the enqueued frame
         self._chk(self._lib.fyx_render_prep(self._h, C.byref(d)))

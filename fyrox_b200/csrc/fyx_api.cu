@@ -62,6 +62,12 @@ struct VisSlot {
     cudaEvent_t ev_cull = nullptr, ev_counts = nullptr, ev_done = nullptr;
 };
 
+// N2: one animation on the host side (fyx_anim.inl)
+struct AnimHost {
+    uint32_t first_track = 0, n_tracks = 0;
+    AnimStateDev st{};
+};
+
 // N3: packed instances of one frustum (fyx_drawprep.inl)
 struct InstOut {
     DevBuf b_node, b_sort, b_mats, b_bundles;
@@ -134,6 +140,15 @@ struct fyx_ctx {
     cudaEvent_t ev[EV_COUNT] = {};
     fyx_timings timings{};
     bool timings_pending = false; // an async frame's events have not been read yet
+
+    // N2 animation sampling (fyx_anim.inl)
+    std::vector<AnimHost> anims;
+    std::vector<fyx_anim_track> anim_tracks; // all tracks, animation after animation
+    uint32_t n_anim_keys = 0;
+    bool anim_csr_dirty = true;
+    AnimArrays an{};
+    DevBuf b_anim_keys, b_anim_tracks, b_anim_state, b_anim_hints, b_anim_values, b_anim_ok, b_anim_bk, b_anim_node_slot,
+        b_anim_node_begin, b_anim_node_tracks;
 
     // N3 draw-prep (fyx_drawprep.inl)
     bool instances_enabled = false, have_bundles = false, rank_on_device = false;
@@ -528,6 +543,8 @@ extern "C" int32_t fyx_create(const fyx_config *cfg, fyx_ctx **out_ctx)
 
 static void fyx_comm_destroy_internal(fyx_ctx *c); // fyx_comm.inl
 namespace { void inst_free(fyx_ctx *c); }              // fyx_drawprep.inl
+namespace { void anim_free(fyx_ctx *c); }              // fyx_anim.inl
+static int32_t animate_enqueue(fyx_ctx *c, float dt);  // fyx_anim.inl
 static int32_t allgather_begin(fyx_ctx *c, VisSlot &V, cudaStream_t s);
 static int32_t allgather_finish(fyx_ctx *c, VisSlot &V, cudaStream_t s);
 
@@ -538,6 +555,7 @@ extern "C" void fyx_destroy(fyx_ctx *c)
     if (c->stream) cudaStreamSynchronize(c->stream);
     fyx_comm_destroy_internal(c);
     inst_free(c);
+    anim_free(c);
     DevBuf *bufs[] = {&c->b_parent, &c->b_flags, &c->b_mask, &c->b_gidx, &c->b_slot_of_node, &c->d_stage, &c->b_statics, &c->b_trs, &c->b_vblk,
                       &c->b_opos, &c->b_onrm, &c->b_palette, &c->b_bone_slot, &c->b_tiles, &c->b_fold_node,
                       &c->b_fold_begin, &c->b_fold_bone, &c->b_fold_stale_idx, &c->b_late_slot, &c->b_stale_pos, &c->b_counts_packed, &c->b_counts_all};
@@ -839,6 +857,7 @@ extern "C" int32_t fyx_set_topology(fyx_ctx *c, uint32_t capacity, uint32_t root
     c->have_statics = false; // slots moved: the caller re-sends non-default statics after a topology change
     c->dfs_rank.clear();     // ... and the DFS order, if it uses it
     c->rank_on_device = false;
+    c->anim_csr_dirty = true; // animated nodes are addressed by slot
     c->have_bundles = false; // ... and the bundle ids (every node is back in bundle 0)
     c->n_bundle_ids = 1;
     c->have_trs = false;     // ... and full TRS records before the next rotation-only update
@@ -1362,13 +1381,18 @@ static void frame_timings_from_events(fyx_ctx *c)
 extern "C" int32_t fyx_render_prep(fyx_ctx *c, const fyx_frame_desc *fr)
 {
     if (!c || !fr) return FYX_ERR_INVALID_ARGUMENT;
-    if (fr->struct_size < sizeof(fyx_frame_desc)) return fail(c, FYX_ERR_INVALID_ARGUMENT, "fyx_frame_desc.struct_size too small");
+    if (fr->struct_size < offsetof(fyx_frame_desc, do_animate)) return fail(c, FYX_ERR_INVALID_ARGUMENT, "fyx_frame_desc.struct_size too small");
     if (!c->have_topology) return fail(c, FYX_ERR_STATE, "fyx_set_topology has not been called");
     CU(cudaSetDevice(c->device));
     int32_t rc = commit_surfaces(c);
     if (rc) return rc;
     cudaStream_t s = c->stream;
     CU(cudaEventRecord(c->ev[EV_START], s));
+    // 0. animation players tick before Graph::update (N2): curves are device-resident, nothing to upload
+    if (fr->struct_size >= sizeof(fyx_frame_desc) && fr->do_animate) {
+        rc = animate_enqueue(c, fr->animate_dt);
+        if (rc) return rc;
+    }
     const bool async = (fr->flags & FYX_FRAME_ASYNC) != 0;
     const bool pipelined = async && fr->readback_visible && fr->n_frusta; // read-back deferred to fyx_frame_wait
     // 1. changed local matrices.  Pinned caller memory is DMA'd in place (the caller keeps it untouched until
@@ -1619,3 +1643,4 @@ extern "C" int32_t fyx_get_timings(fyx_ctx *c, fyx_timings *out)
 
 #include "fyx_comm.inl"
 #include "fyx_drawprep.inl"
+#include "fyx_anim.inl"

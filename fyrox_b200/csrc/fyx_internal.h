@@ -78,6 +78,36 @@ struct FoldArrays {
     const float4 *stale_pos;
 };
 
+// N2 animation sampling (fyx_anim.cu)
+struct AnimTrackDev {
+    uint32_t anim;       // owning animation
+    uint32_t value_kind; // FYX_TV_*
+    uint32_t enabled;
+    uint32_t n_curves;
+    uint32_t first_key[4]; // offsets into the context-wide key array
+    uint32_t n_keys[4];
+};
+struct AnimStateDev {
+    float time, speed, slice_start, slice_end;
+    uint32_t looped, enabled;
+};
+struct AnimArrays {
+    uint32_t n_tracks, n_anims, n_nodes;
+    const fyx_curve_key *keys;
+    AnimTrackDev *tracks;
+    AnimStateDev *state;
+    uint4 *hints;                    // TrackBinding::fetch_hints per track
+    float4 *values;                  // sampled value per track
+    uint32_t *value_ok;              // fetch returned Some
+    const uint32_t *track_bind_kind; // binding | value_kind << 8
+    // animated nodes (distinct live targets) and, per node, its tracks in (animation, track) order
+    const uint32_t *node_slot;
+    const uint32_t *node_begin;
+    const uint32_t *node_tracks;
+};
+void launch_animate(cudaStream_t s, const NodeArrays &a, const AnimArrays &an, fyx_trs *trs_by_slot,
+                    const fyx_transform_statics *st_by_slot, float dt, uint32_t *d_err);
+
 // N3 draw-prep (fyx_drawprep.cu): one frustum's visible list -> instances grouped by bundle
 struct InstParams {
     uint32_t n;                     // visible entries

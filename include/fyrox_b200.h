@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define FYX_ABI_VERSION 1u
+#define FYX_ABI_VERSION 2u
 #define FYX_NONE 0xFFFFFFFFu
 #define FYX_MAX_FRUSTA 8u      /* frusta per fyx_cull call: 1 camera, 3 CSM cascades, 6 cube faces */
 #define FYX_MAX_BONES 255u     /* fyrox-material/src/shader/mod.rs:613; u8 indices scene/mesh/vertex.rs:154 */
@@ -243,6 +243,9 @@ typedef struct fyx_frame_desc {
     uint32_t do_skin;
     uint32_t readback_visible;     /* copy counts + lists to the host before returning */
     uint32_t flags;                /* FYX_FRAME_* */
+    /* since ABI 2 (struct_size tells which fields the caller has): */
+    uint32_t do_animate;           /* first run fyx_animate(animate_dt): AnimationPlayer::update before Graph::update */
+    float animate_dt;
 } fyx_frame_desc;
 /* Do not synchronise with the host at the end of fyx_render_prep: the frame is only enqueued.  Inputs must
  * stay untouched until the frame is waited for (fyx_frame_wait / fyx_sync).  Pinned inputs are uploaded on
@@ -267,6 +270,70 @@ int32_t fyx_get_skinned_device(fyx_ctx *ctx, uint32_t surface_id, const float **
 int32_t fyx_get_timings(fyx_ctx *ctx, fyx_timings *out);
 /* Number of kernels this context has launched so far (bench.py's gpu_launches). */
 uint64_t fyx_kernel_launch_count(const fyx_ctx *ctx);
+
+/* ---- N2: animation sampling on the device ---------------------------------------- */
+/* What AnimationPlayer nodes do on the CPU before Graph::update (scene/animation/mod.rs:83-88,340-346): every
+ * enabled animation ticks — its tracks' curves are sampled at the current time position (fyrox-animation/src/
+ * lib.rs:895-914, container.rs:162-301, fyrox-math/src/curve.rs:252-309), the pose is applied to the target
+ * nodes' position / rotation / scale (scene/animation/mod.rs:147-179) and the time position advances
+ * (lib.rs:471-496, 432-440).  With the curves resident in HBM nothing is uploaded per frame.
+ * Properties no track writes keep the value of the node's last fyx_set_local_trs record (identity if none);
+ * pivots / offsets / pre- and post-rotation come from fyx_set_transform_statics.
+ * Parity: Vector3 and UnitQuaternion tracks bit-exact; UnitQuaternionEuler tracks use sin/cos (platform libm in the
+ * reference): ~1e-7 absolute on the quaternion.  Signals, root motion, property bindings and the blend-machine
+ * (ABSM) layers are not modelled. */
+#define FYX_KEY_CONSTANT 0u /* CurveKeyKind (fyrox-math/src/curve.rs:33-45) */
+#define FYX_KEY_LINEAR 1u
+#define FYX_KEY_CUBIC 2u
+typedef struct fyx_curve_key {
+    float location, value;
+    uint32_t kind;                     /* FYX_KEY_* */
+    float left_tangent, right_tangent; /* tan(angle), Cubic only */
+} fyx_curve_key;
+
+#define FYX_TV_REAL 0u /* TrackValueKind (fyrox-animation/src/container.rs:41-54) */
+#define FYX_TV_VECTOR2 1u
+#define FYX_TV_VECTOR3 2u
+#define FYX_TV_VECTOR4 3u
+#define FYX_TV_QUAT_EULER 4u
+#define FYX_TV_QUAT 5u
+#define FYX_BIND_POSITION 0u /* ValueBinding (fyrox-animation/src/value.rs:358-374) */
+#define FYX_BIND_SCALE 1u
+#define FYX_BIND_ROTATION 2u
+typedef struct fyx_anim_track {
+    uint32_t target_node;  /* TrackBinding::target (node index) */
+    uint32_t binding;      /* FYX_BIND_* */
+    uint32_t value_kind;   /* FYX_TV_* */
+    uint32_t enabled;      /* TrackBinding::enabled */
+    uint32_t n_curves;     /* TrackDataContainer::curves.len(): fewer than the kind needs = fetch returns None */
+    uint32_t first_key[4]; /* curve c = keys[first_key[c] .. first_key[c] + n_keys[c]), sorted by location */
+    uint32_t n_keys[4];
+} fyx_anim_track;
+
+typedef struct fyx_animation_desc {
+    uint32_t struct_size;
+    uint32_t n_tracks;
+    const fyx_anim_track *tracks; /* in AnimationTracksData::tracks order */
+    uint32_t n_keys;
+    const fyx_curve_key *keys;
+    float speed;                  /* Animation defaults (lib.rs:922-945): 1.0 */
+    float time_position;
+    float time_slice_start, time_slice_end;
+    uint32_t looped;
+    uint32_t enabled;
+} fyx_animation_desc;
+
+/* Add an animation; ids are 0,1,2,... in call order = the order update_animations walks them. */
+int32_t fyx_anim_add(fyx_ctx *ctx, const fyx_animation_desc *desc, uint32_t *out_id);
+int32_t fyx_anim_clear(fyx_ctx *ctx);
+int32_t fyx_anim_set_enabled(fyx_ctx *ctx, uint32_t anim, uint32_t enabled);                        /* Animation::set_enabled */
+int32_t fyx_anim_set_track_enabled(fyx_ctx *ctx, uint32_t anim, uint32_t track, uint32_t enabled);  /* TrackBinding::set_enabled */
+int32_t fyx_anim_set_speed(fyx_ctx *ctx, uint32_t anim, float speed);
+int32_t fyx_anim_set_time_position(fyx_ctx *ctx, uint32_t anim, float time); /* wraps / clamps into the time slice (lib.rs:432-440) */
+int32_t fyx_anim_get_time_positions(fyx_ctx *ctx, uint32_t first, uint32_t count, float *out);
+/* AnimationContainer::update_animations(dt) for every animation of the context.  The touched nodes are marked
+ * changed exactly like fyx_set_local_trs; follow with fyx_update_transforms / fyx_render_prep. */
+int32_t fyx_animate(fyx_ctx *ctx, float dt);
 
 /* ---- N3: draw-prep after the cull ------------------------------------------------ */
 /* What RenderDataBundleStorage::push and RenderDataBundle::write_uniforms do per visible surface on the CPU

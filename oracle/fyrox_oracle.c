@@ -1041,6 +1041,8 @@ uint32_t orc_mesh_skin(const orc_graph *g, uint32_t mesh, uint32_t surface, floa
     return s->n_verts;
 }
 
+int orc_node_is_alive(const orc_graph *g, uint32_t n) { return node_at(g, n) != NULL; }
+
 /* N3 — what Mesh::collect_render_data pushes for a node with ONE surface (scene/mesh/mod.rs:700 sort index of
  * global_position(); :731-737 world = identity if the surface is skinned, else global_transform()) and what
  * RenderDataBundle::write_uniforms derives from it (renderer/bundle.rs:483-487: world, view_projection * world).

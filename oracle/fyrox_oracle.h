@@ -174,6 +174,44 @@ void     orc_mesh_accurate_world_bounding_box(const orc_graph *g, uint32_t mesh,
 void orc_skin_vertices(const float *palette_m16, uint32_t n_verts, const void *verts,
                        const orc_vertex_layout *layout, float *out_pos3, float *out_nrm3);
 
+/* ---- N2: animation sampling (fyrox_anim_oracle.c) ---- */
+enum { ORC_KEY_CONSTANT = 0, ORC_KEY_LINEAR = 1, ORC_KEY_CUBIC = 2 };            /* CurveKeyKind, fyrox-math/src/curve.rs:33-45 */
+typedef struct { float location, value; uint32_t kind; float left_tangent, right_tangent; } orc_curve_key; /* curve.rs:57-63 */
+enum { ORC_TV_REAL = 0, ORC_TV_VECTOR2, ORC_TV_VECTOR3, ORC_TV_VECTOR4, ORC_TV_QUAT_EULER, ORC_TV_QUAT }; /* TrackValueKind, container.rs:41-54 */
+enum { ORC_BIND_POSITION = 0, ORC_BIND_SCALE = 1, ORC_BIND_ROTATION = 2 };      /* ValueBinding, value.rs:358-374 */
+typedef struct {
+    uint32_t target_node;  /* TrackBinding::target */
+    uint32_t binding;      /* ORC_BIND_* */
+    uint32_t value_kind;   /* ORC_TV_* */
+    uint32_t enabled;      /* TrackBinding::enabled */
+    uint32_t n_curves;     /* TrackDataContainer::curves.len() */
+    uint32_t first_key[4]; /* curve c = keys[first_key[c] .. first_key[c] + n_keys[c]) sorted by location */
+    uint32_t n_keys[4];
+} orc_track;
+typedef struct orc_animation orc_animation;
+
+float orc_wrapf(float n, float min_limit, float max_limit);                       /* fyrox-math/src/lib.rs:179-203 */
+float orc_lerpf(float a, float b, float t);                                       /* lib.rs:206-208 */
+float orc_cubicf(float p0, float p1, float t, float m0, float m1);                /* lib.rs:212-221 */
+float orc_key_interpolate(const orc_curve_key *l, const orc_curve_key *r, float t); /* curve.rs:87-136 */
+float orc_curve_value_at(const orc_curve_key *keys, uint32_t n, float location, uint32_t *hint); /* curve.rs:252-309 */
+void  orc_quat_from_euler_xyz(const float euler[3], float q[4]);                  /* lib.rs:725-740 */
+void  orc_track_value_blend(int is_quat, float a[4], const float b[4], float w);  /* value.rs:201-227,449-454 */
+int   orc_track_fetch(const orc_track *t, const orc_curve_key *keys, float time, uint32_t hints[4], float out[4]); /* container.rs:162-301 */
+orc_animation *orc_animation_new(const orc_track *tracks, uint32_t n_tracks, const orc_curve_key *keys, uint32_t n_keys);
+void  orc_animation_free(orc_animation *a);
+void  orc_animation_set_time_position(orc_animation *a, float time);              /* fyrox-animation/src/lib.rs:432-440 */
+void  orc_animation_set_time_slice(orc_animation *a, float start, float end);     /* lib.rs:445-452 */
+void  orc_animation_set_speed(orc_animation *a, float s);
+void  orc_animation_set_looped(orc_animation *a, int l);
+void  orc_animation_set_enabled(orc_animation *a, int e);
+void  orc_animation_set_track_enabled(orc_animation *a, uint32_t track, int e);
+float orc_animation_time_position(const orc_animation *a);
+int   orc_animation_is_enabled(const orc_animation *a);
+void  orc_update_animations(orc_animation **anims, uint32_t n, float dt, orc_graph *g, orc_transform *transforms,
+                            uint32_t n_nodes);                                    /* scene/animation/mod.rs:83-88,107-179 */
+int   orc_node_is_alive(const orc_graph *g, uint32_t n);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Emit tests/golden/reference_kats.json: the known-answer vectors of the reference's own unit tests
-for the render-prep path (SURVEY.md §8c K1–K10), transcribed from the cited test sources.
+for the render-prep path (SURVEY.md §8c K1–K10) and of the animation-sampling step before it (K11–K13), transcribed from the cited test sources.
 
 The reference is Rust (no toolchain here), so the vectors cannot be produced by running it.  When
 /root/reference exists (the build container) this script also checks that each cited file still
@@ -99,6 +99,34 @@ KATS = {
         "quote": "fn test_calculate_sorting_index()",
         "range_center": (2**64 - 1) // 2,
         "cases": [{"z": 0.0, "delta": 0}, {"z": 1.0, "delta": 1000}, {"z": 2.0, "delta": 2000}, {"z": -3.0, "delta": -3000}],
+    },
+    "K11_wrapf": {
+        "source": "fyrox-math/src/lib.rs:1141-1147",
+        "quote": "assert_eq!(wrapf(12.0, 5.0, 10.0), 7.0);",
+        "cases": [[5.0, 0.0, 10.0, 5.0], [5.0, 0.0, 0.0, 0.0], [2.0, 5.0, 10.0, 7.0], [12.0, 5.0, 10.0, 7.0]],
+    },
+    "K12_curve_value_at": {
+        "source": "fyrox-math/src/curve.rs:428-471",
+        "quote": "assert_eq!(curve.value_at(0.5, &mut 0), 0.5);",
+        # keys are (location, value, kind) with kind Linear; every query starts from hint 0
+        "steps": [
+            {"keys": [], "queries": [[0.0, 0.0]]},
+            {"keys": [[0.0, 1.0]], "queries": [[-1.0, 1.0], [1.0, 1.0], [0.0, 1.0]]},
+            {"keys": [[0.0, 1.0], [1.0, 0.0]], "queries": [[-1.0, 1.0], [2.0, 0.0], [0.5, 0.5]]},
+            {"keys": [[0.0, 1.0], [1.0, 0.0], [2.0, 1.0]], "queries": [[-1.0, 1.0], [3.0, 1.0], [0.0, 1.0], [2.0, 1.0], [0.5, 0.5]]},
+        ],
+    },
+    "K13_curve_key_interpolate": {
+        "source": "fyrox-math/src/curve.rs:536-575",
+        "quote": "assert_eq!(key3.interpolate(&key4, 1.0), 30.0);",
+        # kinds: 0 Constant, 1 Linear, 2 Cubic (new_cubic(0.0, 0.0): both tangents tan(0) = 0)
+        "keys": {"key": [0.0, 5.0, 0], "key2": [1.0, 10.0, 1], "key3": [2.0, 20.0, 2], "key4": [3.0, 30.0, 2]},
+        "cases": [
+            ["key", "key2", 1.0, 10.0], ["key", "key2", 0.0, 5.0], ["key", "key3", 1.0, 20.0], ["key", "key3", 0.0, 5.0],
+            ["key2", "key", 1.0, 5.0], ["key2", "key", 0.0, 10.0], ["key2", "key3", 1.0, 20.0], ["key2", "key3", 0.0, 10.0],
+            ["key3", "key", 1.0, 5.0], ["key3", "key", 0.0, 20.0], ["key3", "key2", 1.0, 10.0], ["key3", "key2", 0.0, 20.0],
+            ["key3", "key4", 1.0, 30.0], ["key3", "key4", 0.0, 20.0],
+        ],
     },
     "K10_handle_numbering": {
         "source": "fyrox-impl/src/scene/graph/mod.rs:408-424",

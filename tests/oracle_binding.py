@@ -145,6 +145,26 @@ def lib() -> C.CDLL:
         "orc_from_graph": (C.c_size_t, [vp, C.POINTER(Frustum), C.c_uint32, C.c_int, vp, C.c_size_t]),
         "orc_mesh_bone_matrices": (C.c_uint32, [vp, C.c_uint32, C.c_uint32, f32p]),
         "orc_mesh_skin": (C.c_uint32, [vp, C.c_uint32, C.c_uint32, f32p, f32p]),
+        "orc_wrapf": (C.c_float, [C.c_float] * 3),
+        "orc_lerpf": (C.c_float, [C.c_float] * 3),
+        "orc_cubicf": (C.c_float, [C.c_float] * 5),
+        "orc_key_interpolate": (C.c_float, [C.POINTER(CurveKey), C.POINTER(CurveKey), C.c_float]),
+        "orc_curve_value_at": (C.c_float, [vp, C.c_uint32, C.c_float, C.POINTER(C.c_uint32)]),
+        "orc_quat_from_euler_xyz": (None, [f32p, f32p]),
+        "orc_track_value_blend": (None, [C.c_int, f32p, f32p, C.c_float]),
+        "orc_track_fetch": (C.c_int, [vp, vp, C.c_float, C.POINTER(C.c_uint32), f32p]),
+        "orc_animation_new": (vp, [vp, C.c_uint32, vp, C.c_uint32]),
+        "orc_animation_free": (None, [vp]),
+        "orc_animation_set_time_position": (None, [vp, C.c_float]),
+        "orc_animation_set_time_slice": (None, [vp, C.c_float, C.c_float]),
+        "orc_animation_set_speed": (None, [vp, C.c_float]),
+        "orc_animation_set_looped": (None, [vp, C.c_int]),
+        "orc_animation_set_enabled": (None, [vp, C.c_int]),
+        "orc_animation_set_track_enabled": (None, [vp, C.c_uint32, C.c_int]),
+        "orc_animation_time_position": (C.c_float, [vp]),
+        "orc_animation_is_enabled": (C.c_int, [vp]),
+        "orc_update_animations": (None, [vp, C.c_uint32, C.c_float, vp, vp, C.c_uint32]),
+        "orc_node_is_alive": (C.c_int, [vp, C.c_uint32]),
         "orc_node_instance": (C.c_uint64, [vp, C.c_uint32, f32p, f32p, f32p, f32p]),
         "orc_mesh_accurate_world_bounding_box": (None, [vp, C.c_uint32, C.POINTER(Aabb)]),
         "orc_skin_vertices": (None, [f32p, C.c_uint32, vp, C.POINTER(VertexLayout), f32p, f32p]),
@@ -155,6 +175,23 @@ def lib() -> C.CDLL:
         fn.argtypes = args
     _lib = L
     return L
+
+
+class CurveKey(C.Structure):
+    _fields_ = [("location", C.c_float), ("value", C.c_float), ("kind", C.c_uint32), ("left_tangent", C.c_float), ("right_tangent", C.c_float)]
+
+
+class Track(C.Structure):
+    _fields_ = [("target_node", C.c_uint32), ("binding", C.c_uint32), ("value_kind", C.c_uint32), ("enabled", C.c_uint32),
+                ("n_curves", C.c_uint32), ("first_key", C.c_uint32 * 4), ("n_keys", C.c_uint32 * 4)]
+
+
+KEY_CONSTANT, KEY_LINEAR, KEY_CUBIC = 0, 1, 2
+TV_REAL, TV_VECTOR2, TV_VECTOR3, TV_VECTOR4, TV_QUAT_EULER, TV_QUAT = range(6)
+BIND_POSITION, BIND_SCALE, BIND_ROTATION = 0, 1, 2
+KEY_DTYPE = np.dtype([("location", "<f4"), ("value", "<f4"), ("kind", "<u4"), ("left_tangent", "<f4"), ("right_tangent", "<f4")])
+TRACK_DTYPE = np.dtype([("target_node", "<u4"), ("binding", "<u4"), ("value_kind", "<u4"), ("enabled", "<u4"), ("n_curves", "<u4"),
+                        ("first_key", "<u4", 4), ("n_keys", "<u4", 4)])
 
 
 def fp(a: np.ndarray):
@@ -354,3 +391,45 @@ def frustum_to_fyx(f: Frustum):
 
     planes, corners = frustum_planes_corners(f)
     return frustum_from_numpy(planes, corners)
+
+
+# ---- N2: animation (fyrox_anim_oracle.c) ------------------------------------------------------------
+def curve_value_at(keys: np.ndarray, location: float, hint: int = 0):
+    """Curve::value_at on a KEY_DTYPE array; returns (value, new hint)."""
+    keys = np.ascontiguousarray(keys, dtype=KEY_DTYPE)
+    h = C.c_uint32(hint)
+    v = lib().orc_curve_value_at(keys.ctypes.data_as(C.c_void_p), len(keys), float(location), C.byref(h))
+    return float(np.float32(v)), h.value
+
+
+class Animation:
+    """Animation<Handle<Node>> of the oracle: tracks (TRACK_DTYPE) over one key array (KEY_DTYPE)."""
+
+    def __init__(self, tracks: np.ndarray, keys: np.ndarray, speed=1.0, looped=True, time_slice=(0.0, 0.0), time_position=0.0, enabled=True):
+        self.L = lib()
+        tracks = np.ascontiguousarray(tracks, dtype=TRACK_DTYPE)
+        keys = np.ascontiguousarray(keys, dtype=KEY_DTYPE)
+        self.h = self.L.orc_animation_new(tracks.ctypes.data_as(C.c_void_p), len(tracks), keys.ctypes.data_as(C.c_void_p), len(keys))
+        self.L.orc_animation_set_speed(self.h, float(speed))
+        self.L.orc_animation_set_looped(self.h, int(looped))
+        self.L.orc_animation_set_time_slice(self.h, float(time_slice[0]), float(time_slice[1]))
+        self.L.orc_animation_set_time_position(self.h, float(time_position))
+        self.L.orc_animation_set_enabled(self.h, int(enabled))
+
+    def __del__(self):
+        try:
+            if self.h:
+                self.L.orc_animation_free(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+    @property
+    def time_position(self):
+        return float(np.float32(self.L.orc_animation_time_position(self.h)))
+
+
+def update_animations(anims, dt, graph: "Graph", transforms):
+    """AnimationContainer::update_animations over a list of Animation; `transforms` is a ctypes array of Transform per node."""
+    arr = (C.c_void_p * max(len(anims), 1))(*[a.h for a in anims])
+    lib().orc_update_animations(arr, len(anims), float(dt), graph.h, transforms, len(transforms))

@@ -31,10 +31,11 @@ def test_library_exports_every_declared_symbol():
 
 def test_abi_version_and_struct_sizes():
     lib = L.load()
-    assert lib.fyx_abi_version() == 1
+    assert lib.fyx_abi_version() == 2
     assert C.sizeof(L.fyx_frustum) == 6 * 16 + 8 * 12
     assert C.sizeof(L.fyx_vertex_layout) == 20
     assert C.sizeof(L.fyx_timings) == 28
+    assert C.sizeof(L.fyx_curve_key) == 20 and C.sizeof(L.fyx_anim_track) == 52 and C.sizeof(L.fyx_bundle) == 24
 
 
 def test_only_sm100a_code_is_shipped():

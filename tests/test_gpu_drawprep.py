@@ -130,9 +130,12 @@ def test_instances_edge_cases(ctx):
     check_instances(og, ctx, 0, fo, weird, vp, zeros)
     huge = view.copy() * np.float32(1e30)  # sort index saturates at both ends / NaN -> centre
     check_instances(og, ctx, 0, fo, huge, vp, zeros)
-    # nothing visible
+    # a frustum far away from everything: only the nodes with frustum culling switched off remain
     _, _, fo2, ff2 = observer((0, 5000, 0), (0, 6000, 0), (1, 0, 0))
     ctx.cull([ff2])
+    assert check_instances(og, ctx, 0, fo2, view, vp, zeros) < 50
+    # nothing visible at all (no render-mask bit in common)
+    ctx.cull([ff2], cam_mask=[0])
     inst = ctx.pack_instances(0, view, vp)
     assert inst["node"].size == 0 and inst["bundles"].size == 0
     # ids must be dense

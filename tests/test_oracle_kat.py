@@ -314,3 +314,81 @@ def test_skinned_mesh_world_aabb_reads_current_bone_positions():
     g.set_local_matrix(mesh, ob.translation(0, 0, 0))
     g.update()
     assert g.world_bounding_box(mesh).tolist() == [-1, -1, -1, 20, 1, 1]
+
+
+# ---- N2 (animation sampling): the reference's own curve / wrapf tests ---------------------------------
+def _keys(rows, kind=ob.KEY_LINEAR):
+    k = np.zeros(len(rows), ob.KEY_DTYPE)
+    for i, r in enumerate(rows):
+        k[i]["location"], k[i]["value"] = r[0], r[1]
+        k[i]["kind"] = r[2] if len(r) > 2 else kind
+    return k
+
+
+def test_k11_wrapf():
+    for n, lo, hi, want in KATS["K11_wrapf"]["cases"]:
+        assert L.orc_wrapf(n, lo, hi) == want
+
+
+def test_k12_curve_value_at():
+    for step in KATS["K12_curve_value_at"]["steps"]:
+        keys = _keys(step["keys"])
+        for loc, want in step["queries"]:
+            got, _ = ob.curve_value_at(keys, loc, 0)
+            assert got == want, (step["keys"], loc)
+
+
+def test_k13_curve_key_interpolate():
+    k = KATS["K13_curve_key_interpolate"]
+    keys = {}
+    for name, (loc, val, kind) in k["keys"].items():
+        keys[name] = ob.CurveKey(loc, val, kind, 0.0, 0.0)
+    for a, b, t, want in k["cases"]:
+        assert L.orc_key_interpolate(C.byref(keys[a]), C.byref(keys[b]), t) == want, (a, b, t)
+
+
+def test_curve_hint_is_part_of_the_result():
+    """Not a reference test, a property of curve.rs:275-301 the restatement must keep: on a key's location the span
+    found through the hint (t = 0 on the right span) and the one found by binary search (t = 1 on the left span) are
+    different expressions, so the remembered hint is state."""
+    keys = _keys([(0.0, 0.1), (1.0, 0.7), (2.0, 0.3)])
+    v_search, h = ob.curve_value_at(keys, 1.0, 0)      # hint 0: binary search -> span [0,1], t = 1: 0.1 + (0.7-0.1)*1
+    assert h == 1
+    v_hint, h2 = ob.curve_value_at(keys, 1.0, 2)       # hint 2: span [1,2), t = 0: exactly 0.7
+    assert h2 == 2 and v_hint == float(np.float32(0.7))
+    assert v_search == float(np.float32(0.1) + (np.float32(0.7) - np.float32(0.1)) * np.float32(1.0))
+
+
+def test_animation_tick_applies_pose_then_advances_time():
+    """Animation::tick order (lib.rs:471-496): the pose is sampled at the CURRENT time position, then time advances and
+    wraps (wrapf).  One node, one linear position track (0,0,0)@0 -> (2,4,8)@2, dt 0.5 from t = 0.5."""
+    keys = _keys([(0, 0), (2, 2), (0, 0), (2, 4), (0, 0), (2, 8)])
+    t = np.zeros(1, ob.TRACK_DTYPE)
+    t[0]["target_node"], t[0]["binding"], t[0]["value_kind"], t[0]["enabled"], t[0]["n_curves"] = 1, ob.BIND_POSITION, ob.TV_VECTOR3, 1, 3
+    t[0]["first_key"][:3] = [0, 2, 4]
+    t[0]["n_keys"][:3] = [2, 2, 2]
+    a = ob.Animation(t, keys, speed=1.0, looped=True, time_slice=(0.0, 2.0), time_position=0.5)
+    parent = np.array([0xFFFFFFFF, 0], np.uint32)
+    og = ob.Graph.build(parent, None, None, np.tile(np.eye(4, dtype=np.float32).reshape(16), (2, 1)), None)
+    og.update_hierarchical_data()
+    tr = (ob.Transform * 2)()
+    for i in range(2):
+        L.orc_transform_identity(C.byref(tr[i]))
+    want = [((0.5, 1.0, 2.0), 1.0), ((1.0, 2.0, 4.0), 1.5), ((1.5, 3.0, 6.0), 2.0), ((2.0, 4.0, 8.0), 0.5), ((0.5, 1.0, 2.0), 1.0)]
+    for pos, time_after in want:
+        ob.update_animations([a], 0.5, og, tr)
+        og.update()
+        assert tuple(tr[1].local_position) == pos
+        assert tuple(og.global_transform(1)[12:15]) == pos
+        assert a.time_position == time_after
+    # a clamped (not looped) animation stops at the end of its slice
+    b = ob.Animation(t, keys, speed=1.0, looped=False, time_slice=(0.0, 2.0), time_position=1.75)
+    ob.update_animations([b], 0.5, og, tr)
+    assert b.time_position == 2.0
+    # TrackValue::blend_with: lerp for vectors, shortest-way nlerp for rotations (value.rs:201-227,449-454)
+    va = np.array([1, 2, 3, 4], np.float32)
+    L.orc_track_value_blend(0, fp(va), fp(np.array([3, 2, 1, 0], np.float32)), 0.25)
+    assert va.tolist() == [1.5, 2.0, 2.5, 3.0]
+    qa = np.array([0, 0, 0, 1], np.float32)
+    L.orc_track_value_blend(1, fp(qa), fp(np.array([0, 0, 0, -1], np.float32)), 0.5)
+    assert qa.tolist() == [0.0, 0.0, 0.0, -1.0]  # a is negated first (dot < 0), so the blend does not pass through zero
