@@ -251,6 +251,58 @@ def load_scene(ctx, sc, fb, log):
     log(f"scene on device in {time.time() - t0:.1f}s: {sc.capacity} nodes, {nu} skinned meshes, {nu * V} verts")
 
 
+def device_animation_mode(ctx, sc, fb, frusta, n_bones, steps, timed, log):
+    """N2: one Animation per skinned mesh (64 rotation tracks of kind UnitQuaternion, 4 linear keys per curve over a
+    2 s loop, built from the generator's animation frames), sampled on the device every frame.  Returns the
+    end-to-end ms/frame (two frames in flight, visible lists read back, zero bytes uploaded) and the animation
+    kernels' own time."""
+    K, T = 4, 2.0
+    idx, _ = sc.animate_trs(0)
+    rots = np.stack([sc.animate_trs(k)[1][:, 3:7] for k in range(K)], axis=2)  # (bones, 4 components, K keys)
+    keys = np.zeros((n_bones, 4, K), fb.Context.KEY_DTYPE)
+    keys["location"] = (np.arange(K, dtype=np.float32) * np.float32(T / (K - 1)))[None, None, :]
+    keys["value"] = rots
+    keys["kind"] = 1  # Linear
+    bones = sc.bones_per_unit
+    tracks = np.zeros(n_bones, fb.Context.TRACK_DTYPE)
+    tracks["target_node"] = idx
+    tracks["binding"] = 2  # Rotation
+    tracks["value_kind"] = 5  # UnitQuaternion
+    tracks["enabled"] = 1
+    tracks["n_curves"] = 4
+    local = (np.arange(n_bones, dtype=np.uint32) % bones) * (4 * K)  # key offsets are relative to the animation's own keys
+    tracks["first_key"] = local[:, None] + (np.arange(4, dtype=np.uint32) * K)[None, :]
+    tracks["n_keys"] = K
+    keys = keys.reshape(-1)
+    rng = np.random.default_rng(SEED)
+    phase = rng.uniform(0.0, T, sc.n_units).astype(np.float32)
+    t0 = time.perf_counter()
+    for u in range(sc.n_units):
+        ctx.anim_add(tracks[u * bones:(u + 1) * bones], keys[u * bones * 4 * K:(u + 1) * bones * 4 * K], speed=1.0, looped=True,
+                     time_slice=(0.0, T), time_position=float(phase[u]))
+    dt = 1.0 / 60.0
+
+    def frames(n):
+        for i in range(n):
+            ctx.render_prep(update_flags=fb.UPDATE_ALL, frusta=frusta, readback_visible=True, async_=True, animate_dt=dt)
+            if i:
+                ctx.frame_wait()
+        ctx.frame_wait()
+
+    frames(3)
+    log(f"device animation: {sc.n_units} animations, {n_bones} tracks, {keys.size} keys added in {time.perf_counter() - t0:.1f} s")
+    ms = timed(lambda: frames(steps), 1) / steps
+    anim_ms = 0.0
+    for _ in range(steps):
+        ctx.render_prep(update_flags=fb.UPDATE_ALL, frusta=frusta, readback_visible=False, animate_dt=dt)
+        anim_ms += ctx.timings()["upload_ms"] / steps  # EV_START..EV_UPLOAD brackets the animation kernels (nothing is uploaded)
+    ctx.anim_clear()
+    per_bone = 4 * 2 * 20 + 32 + 48 + 4 + 2 * 16 + 4 + 2 * 40 + 48 + 4  # keys of the span, hints r/w, track, value w/r, TRS r/w, L, flag
+    return {"e2e_ms_per_step": ms, "h2d_bytes_per_step": 0, "animation_kernels_ms": anim_ms, "animations": int(sc.n_units), "tracks": int(n_bones),
+            "keys": int(keys.size), "approx_bytes_per_bone": per_bone,
+            "animation_GBps": per_bone * n_bones / max(anim_ms, 1e-6) / 1e-3 / 1e9}
+
+
 def run_cuda(args):
     import torch
     import torch.distributed as dist
@@ -418,6 +470,11 @@ def run_cuda(args):
             ctx.frame_wait()
         inc_frames(3)
         inc_ms = timed(lambda: inc_frames(args.steps), 1) / args.steps
+    # third mode (N2): the animation players run on the device — the bones' rotation curves are resident in HBM, every
+    # frame samples them (fyx_render_prep do_animate), nothing is uploaded; the visible lists still come down
+    dev_anim = None
+    if anim and world == 1 and not args.no_device_animation:
+        dev_anim = device_animation_mode(ctx, sc, fb, frusta, n_bones, args.steps, timed, log)
     clk = clocks.stop() if rank == 0 else None
 
     ms_per_step = total_ms / args.steps
@@ -477,7 +534,7 @@ def run_cuda(args):
                 "ms_per_step_synchronous": e2e_sync_ms / args.steps, "ms_per_step_pipelined": e2e_pipe_ms / args.steps},
         "gpu_launches": int(launches),
         "roofline": roofline,
-        "modes": {"all_dirty_ms_per_step": ms_per_step, "static_plus_skeletons_e2e_ms_per_step": inc_ms},
+        "modes": {"all_dirty_ms_per_step": ms_per_step, "static_plus_skeletons_e2e_ms_per_step": inc_ms, "device_animation": dev_anim},
     }
     if world == 1 and not args.no_cpu_baseline:
         try:
@@ -509,6 +566,7 @@ def main():
     ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
     ap.add_argument("--upload", default="rot", choices=["rot", "trs", "m16"], help="per-frame upload format of the changed bones")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-device-animation", action="store_true", help="skip the extra mode that samples the bones' animation curves on the device")
     ap.add_argument("--verbose", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -52,18 +52,17 @@ __device__ __forceinline__ float span_value(const fyx_curve_key &l, const fyx_cu
 }
 
 // Curve::value_at (curve.rs:252-309)
-__device__ __forceinline__ float curve_value_at(const fyx_curve_key *keys, const uint32_t n, const float location, uint32_t &hint)
+__device__ __forceinline__ float curve_value_at(const fyx_curve_key *keys, const uint32_t n, const float first_loc,
+                                                const float last_loc, const float location, uint32_t &hint)
 {
     if (n == 0u) return 0.0f;
-    const fyx_curve_key first = keys[0];
-    if (location <= first.location) {
+    if (location <= first_loc) {
         hint = 0u;
-        return first.value;
+        return keys[0].value;
     }
-    const fyx_curve_key last = keys[n - 1u];
-    if (location >= last.location) {
+    if (location >= last_loc) {
         hint = n - 1u;
-        return last.value;
+        return keys[n - 1u].value;
     }
     {
         const uint32_t h = hint, li = h ? h - 1u : 0u;
@@ -134,7 +133,9 @@ __global__ void __launch_bounds__(kBlock) k_anim_sample(const AnimArrays an)
         uint4 h4 = an.hints[i];
         uint32_t h[4] = {h4.x, h4.y, h4.z, h4.w};
         float v[4] = {0.f, 0.f, 0.f, 0.f};
-        for (uint32_t c = 0; c < need; ++c) v[c] = curve_value_at(an.keys + t.first_key[c], t.n_keys[c], st.time, h[c]);
+#pragma unroll
+        for (uint32_t c = 0; c < 4u; ++c)
+            if (c < need) v[c] = curve_value_at(an.keys + t.first_key[c], t.n_keys[c], t.first_loc[c], t.last_loc[c], st.time, h[c]);
         an.hints[i] = make_uint4(h[0], h[1], h[2], h[3]);
         if (t.value_kind == FYX_TV_QUAT_EULER) {
             float q[4];

@@ -35,6 +35,10 @@ void anim_free(fyx_ctx *c)
     for (DevBuf *b : bufs) dev_free(*b);
     c->anims.clear();
     c->anim_tracks.clear();
+    c->pend_keys.clear();
+    c->pend_tracks.clear();
+    c->pend_bk.clear();
+    c->pend_state.clear();
     c->n_anim_keys = 0;
     c->an = AnimArrays{};
     c->anim_csr_dirty = true;
@@ -96,6 +100,41 @@ int32_t anim_build_csr(fyx_ctx *c)
 
 } // namespace
 
+namespace {
+
+// upload what fyx_anim_add queued since the last flush (device buffers grow, keeping hints / time of the older animations)
+int32_t anim_flush(fyx_ctx *c)
+{
+    if (c->pend_state.empty()) return FYX_OK;
+    const uint32_t nt = (uint32_t)c->anim_tracks.size(), nk = c->n_anim_keys, na = (uint32_t)c->anims.size();
+    const uint32_t t0 = nt - (uint32_t)c->pend_tracks.size(), k0 = nk - (uint32_t)c->pend_keys.size(), a0 = na - (uint32_t)c->pend_state.size();
+    int32_t rc;
+    if ((rc = dev_ensure(c, c->b_anim_keys, std::max<size_t>(nk, 1) * sizeof(fyx_curve_key), true))) return rc;
+    if ((rc = dev_ensure(c, c->b_anim_tracks, std::max<size_t>(nt, 1) * sizeof(AnimTrackDev), true))) return rc;
+    if ((rc = dev_ensure(c, c->b_anim_bk, std::max<size_t>(nt, 1) * 4, true))) return rc;
+    if ((rc = dev_ensure(c, c->b_anim_hints, std::max<size_t>(nt, 1) * sizeof(uint4), true))) return rc;
+    if ((rc = dev_ensure(c, c->b_anim_values, std::max<size_t>(nt, 1) * sizeof(float4), true))) return rc;
+    if ((rc = dev_ensure(c, c->b_anim_ok, std::max<size_t>(nt, 1) * 4, true))) return rc;
+    if ((rc = dev_ensure(c, c->b_anim_state, std::max<size_t>(na, 1) * sizeof(AnimStateDev), true))) return rc;
+    CU(cudaStreamSynchronize(c->stream)); // the grown buffers' copies have landed; the sources below are pageable
+    if (!c->pend_keys.empty())
+        CU(cudaMemcpy(c->b_anim_keys.as<fyx_curve_key>() + k0, c->pend_keys.data(), c->pend_keys.size() * sizeof(fyx_curve_key), cudaMemcpyHostToDevice));
+    if (!c->pend_tracks.empty()) {
+        CU(cudaMemcpy(c->b_anim_tracks.as<AnimTrackDev>() + t0, c->pend_tracks.data(), c->pend_tracks.size() * sizeof(AnimTrackDev), cudaMemcpyHostToDevice));
+        CU(cudaMemcpy(c->b_anim_bk.as<uint32_t>() + t0, c->pend_bk.data(), c->pend_bk.size() * 4, cudaMemcpyHostToDevice));
+        CU(cudaMemset(c->b_anim_hints.as<uint4>() + t0, 0, c->pend_tracks.size() * sizeof(uint4))); // HintContainer::default()
+    }
+    CU(cudaMemcpy(c->b_anim_state.as<AnimStateDev>() + a0, c->pend_state.data(), c->pend_state.size() * sizeof(AnimStateDev), cudaMemcpyHostToDevice));
+    std::vector<fyx_curve_key>().swap(c->pend_keys);
+    std::vector<AnimTrackDev>().swap(c->pend_tracks);
+    std::vector<uint32_t>().swap(c->pend_bk);
+    std::vector<AnimStateDev>().swap(c->pend_state);
+    anim_rebuild_arrays(c);
+    return FYX_OK;
+}
+
+} // namespace
+
 extern "C" int32_t fyx_anim_clear(fyx_ctx *c)
 {
     if (!c) return FYX_ERR_INVALID_ARGUMENT;
@@ -120,23 +159,13 @@ extern "C" int32_t fyx_anim_add(fyx_ctx *c, const fyx_animation_desc *d, uint32_
     }
     for (uint32_t k = 0; k < d->n_keys; ++k)
         if (d->keys[k].kind > FYX_KEY_CUBIC) return fail(c, FYX_ERR_INVALID_ARGUMENT, "key %u: bad kind", k);
-    CU(cudaSetDevice(c->device));
     const uint32_t id = (uint32_t)c->anims.size();
     const uint32_t t0 = (uint32_t)c->anim_tracks.size(), k0 = c->n_anim_keys;
-    const uint32_t nt = t0 + d->n_tracks, nk = k0 + d->n_keys, na = id + 1;
-    int32_t rc;
-    if ((rc = dev_ensure(c, c->b_anim_keys, std::max<size_t>(nk, 1) * sizeof(fyx_curve_key), true))) return rc;
-    if ((rc = dev_ensure(c, c->b_anim_tracks, std::max<size_t>(nt, 1) * sizeof(AnimTrackDev), true))) return rc;
-    if ((rc = dev_ensure(c, c->b_anim_bk, std::max<size_t>(nt, 1) * 4, true))) return rc;
-    if ((rc = dev_ensure(c, c->b_anim_hints, std::max<size_t>(nt, 1) * sizeof(uint4), true))) return rc;
-    if ((rc = dev_ensure(c, c->b_anim_values, std::max<size_t>(nt, 1) * sizeof(float4), true))) return rc;
-    if ((rc = dev_ensure(c, c->b_anim_ok, std::max<size_t>(nt, 1) * 4, true))) return rc;
-    if ((rc = dev_ensure(c, c->b_anim_state, std::max<size_t>(na, 1) * sizeof(AnimStateDev), true))) return rc;
-    std::vector<AnimTrackDev> td(d->n_tracks);
-    std::vector<uint32_t> bk(d->n_tracks);
+    // uploads are deferred to the next call that needs the device tables (anim_flush): thousands of animations
+    // (one per skeleton) arrive back to back at load time
     for (uint32_t i = 0; i < d->n_tracks; ++i) {
         const fyx_anim_track &t = d->tracks[i];
-        AnimTrackDev &o = td[i];
+        AnimTrackDev o{};
         o.anim = id;
         o.value_kind = t.value_kind;
         o.enabled = t.enabled ? 1u : 0u;
@@ -144,9 +173,15 @@ extern "C" int32_t fyx_anim_add(fyx_ctx *c, const fyx_animation_desc *d, uint32_
         for (int k = 0; k < 4; ++k) {
             o.first_key[k] = (k < (int)t.n_curves) ? k0 + t.first_key[k] : 0u;
             o.n_keys[k] = (k < (int)t.n_curves) ? t.n_keys[k] : 0u;
+            if (o.n_keys[k]) {
+                o.first_loc[k] = d->keys[t.first_key[k]].location;
+                o.last_loc[k] = d->keys[t.first_key[k] + t.n_keys[k] - 1].location;
+            }
         }
-        bk[i] = t.binding | (t.value_kind << 8);
+        c->pend_tracks.push_back(o);
+        c->pend_bk.push_back(t.binding | (t.value_kind << 8));
     }
+    c->pend_keys.insert(c->pend_keys.end(), d->keys, d->keys + d->n_keys);
     AnimStateDev st{};
     st.speed = d->speed;
     st.slice_start = d->time_slice_start;
@@ -154,23 +189,15 @@ extern "C" int32_t fyx_anim_add(fyx_ctx *c, const fyx_animation_desc *d, uint32_
     st.looped = d->looped ? 1u : 0u;
     st.enabled = d->enabled ? 1u : 0u;
     st.time = host_time_position(st, d->time_position);
-    CU(cudaStreamSynchronize(c->stream)); // the grown buffers' copies have landed; the host vectors below are pageable
-    if (d->n_keys) CU(cudaMemcpy(c->b_anim_keys.as<fyx_curve_key>() + k0, d->keys, (size_t)d->n_keys * sizeof(fyx_curve_key), cudaMemcpyHostToDevice));
-    if (d->n_tracks) {
-        CU(cudaMemcpy(c->b_anim_tracks.as<AnimTrackDev>() + t0, td.data(), td.size() * sizeof(AnimTrackDev), cudaMemcpyHostToDevice));
-        CU(cudaMemcpy(c->b_anim_bk.as<uint32_t>() + t0, bk.data(), bk.size() * 4, cudaMemcpyHostToDevice));
-        CU(cudaMemset(c->b_anim_hints.as<uint4>() + t0, 0, (size_t)d->n_tracks * sizeof(uint4))); // HintContainer::default()
-    }
-    CU(cudaMemcpy(c->b_anim_state.as<AnimStateDev>() + id, &st, sizeof st, cudaMemcpyHostToDevice));
+    c->pend_state.push_back(st);
     AnimHost h;
     h.first_track = t0;
     h.n_tracks = d->n_tracks;
     h.st = st;
     c->anims.push_back(h);
     c->anim_tracks.insert(c->anim_tracks.end(), d->tracks, d->tracks + d->n_tracks);
-    c->n_anim_keys = nk;
+    c->n_anim_keys = k0 + d->n_keys;
     c->anim_csr_dirty = true;
-    anim_rebuild_arrays(c);
     if (out_id) *out_id = id;
     return FYX_OK;
 }
@@ -178,11 +205,12 @@ extern "C" int32_t fyx_anim_add(fyx_ctx *c, const fyx_animation_desc *d, uint32_
 #define ANIM_CHECK(id)                                                                          \
     if (!c) return FYX_ERR_INVALID_ARGUMENT;                                                    \
     if ((id) >= c->anims.size()) return fail(c, FYX_ERR_INVALID_ARGUMENT, "animation %u does not exist", (id)); \
-    CU(cudaSetDevice(c->device))
+    CU(cudaSetDevice(c->device));                                                               \
+    { int32_t rc__ = anim_flush(c); if (rc__) return rc__; }
 
 extern "C" int32_t fyx_anim_set_enabled(fyx_ctx *c, uint32_t anim, uint32_t enabled)
 {
-    ANIM_CHECK(anim);
+    ANIM_CHECK(anim)
     const uint32_t v = enabled ? 1u : 0u;
     c->anims[anim].st.enabled = v;
     CU(cudaMemcpyAsync(&c->b_anim_state.as<AnimStateDev>()[anim].enabled, &v, 4, cudaMemcpyHostToDevice, c->stream));
@@ -191,7 +219,7 @@ extern "C" int32_t fyx_anim_set_enabled(fyx_ctx *c, uint32_t anim, uint32_t enab
 
 extern "C" int32_t fyx_anim_set_track_enabled(fyx_ctx *c, uint32_t anim, uint32_t track, uint32_t enabled)
 {
-    ANIM_CHECK(anim);
+    ANIM_CHECK(anim)
     if (track >= c->anims[anim].n_tracks) return fail(c, FYX_ERR_INVALID_ARGUMENT, "animation %u has no track %u", anim, track);
     const uint32_t v = enabled ? 1u : 0u, gi = c->anims[anim].first_track + track;
     c->anim_tracks[gi].enabled = v;
@@ -201,7 +229,7 @@ extern "C" int32_t fyx_anim_set_track_enabled(fyx_ctx *c, uint32_t anim, uint32_
 
 extern "C" int32_t fyx_anim_set_speed(fyx_ctx *c, uint32_t anim, float speed)
 {
-    ANIM_CHECK(anim);
+    ANIM_CHECK(anim)
     c->anims[anim].st.speed = speed;
     CU(cudaMemcpyAsync(&c->b_anim_state.as<AnimStateDev>()[anim].speed, &speed, 4, cudaMemcpyHostToDevice, c->stream));
     return FYX_OK;
@@ -209,7 +237,7 @@ extern "C" int32_t fyx_anim_set_speed(fyx_ctx *c, uint32_t anim, float speed)
 
 extern "C" int32_t fyx_anim_set_time_position(fyx_ctx *c, uint32_t anim, float time)
 {
-    ANIM_CHECK(anim);
+    ANIM_CHECK(anim)
     const float t = host_time_position(c->anims[anim].st, time);
     CU(cudaMemcpyAsync(&c->b_anim_state.as<AnimStateDev>()[anim].time, &t, 4, cudaMemcpyHostToDevice, c->stream));
     return FYX_OK;
@@ -221,6 +249,8 @@ extern "C" int32_t fyx_anim_get_time_positions(fyx_ctx *c, uint32_t first, uint3
     if (!count) return FYX_OK;
     if (!out || (uint64_t)first + count > c->anims.size()) return fail(c, FYX_ERR_INVALID_ARGUMENT, "animation range out of bounds");
     CU(cudaSetDevice(c->device));
+    int32_t rc = anim_flush(c);
+    if (rc) return rc;
     CU(cudaStreamSynchronize(c->stream));
     CU(cudaMemcpy2D(out, sizeof(float), &c->b_anim_state.as<AnimStateDev>()[first].time, sizeof(AnimStateDev), sizeof(float), count,
                     cudaMemcpyDeviceToHost));
@@ -232,6 +262,7 @@ static int32_t animate_enqueue(fyx_ctx *c, float dt)
     if (c->anims.empty()) return FYX_OK;
     int32_t rc = ensure_trs_store(c);
     if (rc) return rc;
+    if ((rc = anim_flush(c))) return rc;
     if (c->anim_csr_dirty && (rc = anim_build_csr(c))) return rc;
     launch_animate(c->stream, c->a, c->an, c->b_trs.as<fyx_trs>(), c->have_statics ? c->b_statics.as<fyx_transform_statics>() : nullptr, dt,
                    c->d_err);

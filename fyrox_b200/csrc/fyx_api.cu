@@ -146,6 +146,10 @@ struct fyx_ctx {
     std::vector<fyx_anim_track> anim_tracks; // all tracks, animation after animation
     uint32_t n_anim_keys = 0;
     bool anim_csr_dirty = true;
+    std::vector<fyx_curve_key> pend_keys; // queued by fyx_anim_add, uploaded by anim_flush
+    std::vector<AnimTrackDev> pend_tracks;
+    std::vector<uint32_t> pend_bk;
+    std::vector<AnimStateDev> pend_state;
     AnimArrays an{};
     DevBuf b_anim_keys, b_anim_tracks, b_anim_state, b_anim_hints, b_anim_values, b_anim_ok, b_anim_bk, b_anim_node_slot,
         b_anim_node_begin, b_anim_node_tracks;

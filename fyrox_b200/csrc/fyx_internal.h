@@ -86,6 +86,8 @@ struct AnimTrackDev {
     uint32_t n_curves;
     uint32_t first_key[4]; // offsets into the context-wide key array
     uint32_t n_keys[4];
+    float first_loc[4], last_loc[4]; // location of each curve's first / last key (keys are immutable once added): the
+                                     // common in-range fetch touches only the remembered span, not the curve's ends
 };
 struct AnimStateDev {
     float time, speed, slice_start, slice_end;
