@@ -192,6 +192,49 @@ class CpuReference:
         return dt, t_set
 
 
+class CpuMultiCore:
+    """Best-effort multi-core CPU baseline ("soa-omp-NT"): the oracle's arithmetic on flat arrays with
+    OpenMP over levels / nodes / surfaces (oracle/fyrox_oracle_mt.c).  NOT how the reference runs (it is single-threaded);
+    reported next to the reference-shaped number, never instead of it."""
+
+    def __init__(self, ref: "CpuReference", threads: int):
+        ob, sc = ref.ob, ref.sc
+        self.ref = ref
+        self.threads = threads
+        self.mt = ob.MtGraph(sc.parent, sc.flags, sc.render_mask, sc.local_m16, sc.local_aabb.copy(), threads=threads)
+        for u in range(sc.n_units):
+            mesh, bones, ib = sc.unit_mesh_node(u), sc.unit_bone_nodes(u), sc.unit_inv_bind(u)
+            for k, b in enumerate(bones):
+                self.mt.set_inv_bind(int(b), ib[k])
+            verts, _ = sc.unit_vertices(u)
+            self.mt.add_surface(mesh, bones, verts)
+        self.frame = 0
+
+    def step(self):
+        import ctypes as C
+
+        idx, m = self.ref.sc.animate(self.frame)
+        self.frame += 1
+        mt, L = self.mt, self.mt.L
+        t0 = time.perf_counter()
+        mt.set_local_matrices(m, idx)
+        mt.update()
+        vis = self.ref.vis
+        for f in self.ref.frusta:
+            L.orc_mt_cull(mt.h, C.byref(f), 0xFFFFFFFF, 0, vis.ctypes.data_as(C.c_void_p), vis.size)
+        mt.skin_all()
+        return time.perf_counter() - t0
+
+
+def time_multicore(ref: "CpuReference", frames: int) -> dict:
+    threads = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    mc = CpuMultiCore(ref, threads)
+    mc.step()
+    t = sum(mc.step() for _ in range(frames))
+    return {"value": ref.units_per_frame() * frames / t, "unit": UNIT, "cores": threads, "kind": "port-openmp", "ms_per_frame": 1e3 * t / frames,
+            "note": "flat arrays + OpenMP over levels / nodes / surfaces, same arithmetic (oracle/fyrox_oracle_mt.c); best-effort CPU, not how the reference runs"}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -213,10 +256,15 @@ def run_reference(args):
         "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": args.workload, "desc": w["desc"], "sample": desc,
                    "note": "reference = Fyrox's single-threaded CPU path restated in C (oracle/; the Rust reference is not buildable here: no cargo)"},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": "port", "sample": desc},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": "port", "sample": desc,
+                         "note": "1 thread because the reference's path is single-threaded (SURVEY §0 D2); cpu_multicore is the best-effort all-cores variant"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
+    try:
+        line["cpu_multicore"] = time_multicore(ref, max(2, min(args.steps, 5)))
+    except Exception as ex:
+        line["cpu_multicore"] = {"value": None, "note": f"failed: {ex!r}"}
     print(json.dumps(line), flush=True)
     return 0
 
@@ -549,6 +597,10 @@ def run_cuda(args):
             desc = f"{sample['nodes']} nodes, {sample['units']} skinned meshes x {BONES} bones x {sample['verts_per_unit']} verts, {sample['frusta']} frusta; {n} frames"
             line["cpu_baseline"] = {"value": ref.units_per_frame() * n / t, "unit": UNIT, "cores": 1, "kind": "port", "sample": desc,
                                     "host_cores_available": os.cpu_count()}
+            try:
+                line["cpu_baseline"]["multicore"] = time_multicore(ref, 3)
+            except Exception as ex:
+                line["cpu_baseline"]["multicore"] = {"value": None, "note": f"failed: {ex!r}"}
         except Exception as ex:  # the baseline is reported, never allowed to break the measurement
             line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 1, "kind": "port", "sample": f"failed: {ex!r}"}
     print(json.dumps(line), flush=True)

@@ -200,6 +200,8 @@ SYMBOLS = {
     "fyx_anim_set_speed": (C.c_int32, [ctx_p, C.c_uint32, C.c_float]),
     "fyx_anim_set_time_position": (C.c_int32, [ctx_p, C.c_uint32, C.c_float]),
     "fyx_anim_get_time_positions": (C.c_int32, [ctx_p, C.c_uint32, C.c_uint32, C.c_void_p]),
+    "fyx_anim_blend_group": (C.c_int32, [ctx_p, C.c_uint32, C.c_void_p, C.c_void_p, u32p]),
+    "fyx_anim_set_blend_weights": (C.c_int32, [ctx_p, C.c_uint32, C.c_uint32, C.c_void_p]),
     "fyx_animate": (C.c_int32, [ctx_p, C.c_float]),
     "fyx_set_bundle_ids": (C.c_int32, [ctx_p, C.c_uint32, C.c_void_p, C.c_void_p]),
     "fyx_enable_instances": (C.c_int32, [ctx_p, C.c_uint32]),

@@ -319,6 +319,19 @@ class Context:
         self._chk(self._lib.fyx_anim_get_time_positions(self._h, first, count, out.ctypes.data_as(C.c_void_p)))
         return out
 
+    def anim_blend_group(self, anims, weights) -> int:
+        """BlendAnimations over PlayAnimation sources with constant weights (machine/node/blend.rs:136-166)."""
+        a = np.ascontiguousarray(anims, dtype=np.uint32)
+        w = np.ascontiguousarray(weights, dtype=np.float32)
+        assert a.size == w.size
+        out = C.c_uint32()
+        self._chk(self._lib.fyx_anim_blend_group(self._h, a.size, _ptr(a), _ptr(w), C.byref(out)))
+        return out.value
+
+    def anim_set_blend_weights(self, group: int, weights):
+        w = np.ascontiguousarray(weights, dtype=np.float32)
+        self._chk(self._lib.fyx_anim_set_blend_weights(self._h, group, w.size, _ptr(w)))
+
     def animate(self, dt: float):
         """AnimationContainer::update_animations(dt) for every animation (scene/animation/mod.rs:83-88)."""
         self._chk(self._lib.fyx_animate(self._h, float(dt)))

@@ -125,11 +125,12 @@ __global__ void __launch_bounds__(kBlock) k_anim_sample(const AnimArrays an)
     if (i >= an.n_tracks) return;
     const AnimTrackDev t = an.tracks[i];
     const AnimStateDev st = an.state[t.anim];
+    if (!st.enabled) return; // nobody ticks a disabled animation: Animation::pose() keeps what the last tick left
     uint32_t ok = 0u;
     float4 out = make_float4(0.f, 0.f, 0.f, 0.f);
     const uint32_t need = (t.value_kind == FYX_TV_REAL) ? 1u : (t.value_kind == FYX_TV_VECTOR2) ? 2u
                           : (t.value_kind == FYX_TV_VECTOR3 || t.value_kind == FYX_TV_QUAT_EULER) ? 3u : 4u;
-    if (st.enabled && t.enabled && t.n_curves >= need) {
+    if (t.enabled && t.n_curves >= need) {
         uint4 h4 = an.hints[i];
         uint32_t h[4] = {h4.x, h4.y, h4.z, h4.w};
         float v[4] = {0.f, 0.f, 0.f, 0.f};
@@ -158,6 +159,69 @@ __device__ __forceinline__ bool quat_eq(const float a[4], const float4 b)
     return a[0] == -b.x && a[1] == -b.y && a[2] == -b.z && a[3] == -b.w;
 }
 
+// Transform::set_position / set_scale / set_rotation through BoundValueCollection::apply (scene/animation/mod.rs:147-179)
+struct ApplyState {
+    fyx_trs t;
+    bool dirty, touched;
+};
+__device__ __forceinline__ void apply_value(ApplyState &s, const uint32_t binding, const bool is_quat, const bool is_vec3, const float4 v)
+{
+    if (binding == FYX_BIND_POSITION && is_vec3) {
+        s.touched = true;
+        if (s.dirty || s.t.position[0] != v.x || s.t.position[1] != v.y || s.t.position[2] != v.z) {
+            s.t.position[0] = v.x; s.t.position[1] = v.y; s.t.position[2] = v.z;
+            s.dirty = true;
+        }
+    } else if (binding == FYX_BIND_SCALE && is_vec3) {
+        s.touched = true;
+        if (s.dirty || s.t.scale[0] != v.x || s.t.scale[1] != v.y || s.t.scale[2] != v.z) {
+            s.t.scale[0] = v.x; s.t.scale[1] = v.y; s.t.scale[2] = v.z;
+            s.dirty = true;
+        }
+    } else if (binding == FYX_BIND_ROTATION && is_quat) {
+        s.touched = true;
+        if (s.dirty || !quat_eq(s.t.rotation, v)) {
+            s.t.rotation[0] = v.x; s.t.rotation[1] = v.y; s.t.rotation[2] = v.z; s.t.rotation[3] = v.w;
+            s.dirty = true;
+        }
+    }
+}
+
+// TrackValue::blend_with (fyrox-animation/src/value.rs:201-227): nalgebra lerp a*(1-w) + b*w; rotations take the
+// short way (value.rs:449-454) and are re-normalised
+__device__ __forceinline__ float4 blend_value(const float4 a, const float4 b, const float w, const bool is_quat)
+{
+    const float u = sub_rn(1.0f, w);
+    float s[4] = {a.x, a.y, a.z, a.w};
+    if (is_quat) {
+        const float d = FYX_ADD(FYX_ADD(FYX_MUL(s[0], b.x), FYX_MUL(s[2], b.z)), FYX_ADD(FYX_MUL(s[1], b.y), FYX_MUL(s[3], b.w)));
+        if (d < 0.0f) { s[0] = -s[0]; s[1] = -s[1]; s[2] = -s[2]; s[3] = -s[3]; }
+    }
+    float o[4];
+    o[0] = FYX_ADD(FYX_MUL(s[0], u), FYX_MUL(b.x, w));
+    o[1] = FYX_ADD(FYX_MUL(s[1], u), FYX_MUL(b.y, w));
+    o[2] = FYX_ADD(FYX_MUL(s[2], u), FYX_MUL(b.z, w));
+    o[3] = is_quat ? FYX_ADD(FYX_MUL(s[3], u), FYX_MUL(b.w, w)) : 0.0f;
+    if (is_quat) quat_normalize(o);
+    return make_float4(o[0], o[1], o[2], o[3]);
+}
+
+// the output pose of a blend group for one node: at most one value per binding (duplicates are rejected when the group
+// is made), kept in the order the first source pushed them
+struct GroupPose {
+    float4 v[3];
+    uint32_t have, quat, order, n_order; // bit masks by binding; `order` packs the bindings 2 bits each
+};
+__device__ __forceinline__ void group_flush(GroupPose &gp, ApplyState &s)
+{
+    for (uint32_t k = 0; k < gp.n_order; ++k) {
+        const uint32_t b = (gp.order >> (2u * k)) & 3u;
+        const bool q = (gp.quat >> b) & 1u;
+        apply_value(s, b, q, !q, gp.v[b]);
+    }
+    gp.have = gp.quat = gp.order = gp.n_order = 0u;
+}
+
 template <bool HAS_STATICS>
 __global__ void __launch_bounds__(kBlock) k_anim_apply(const NodeArrays a, const AnimArrays an, fyx_trs *trs_by_slot,
                                                        const fyx_transform_statics *st_by_slot, uint32_t *d_err)
@@ -165,38 +229,56 @@ __global__ void __launch_bounds__(kBlock) k_anim_apply(const NodeArrays a, const
     const uint32_t e = blockIdx.x * kBlock + threadIdx.x;
     if (e >= an.n_nodes) return;
     const uint32_t slot = an.node_slot[e];
-    fyx_trs t = trs_by_slot[slot];
-    bool dirty = false, touched = false; // Transform::dirty is clear after the last Graph::update
+    ApplyState s;
+    s.t = trs_by_slot[slot];
+    s.dirty = s.touched = false; // Transform::dirty is clear after the last Graph::update
+    GroupPose gp;
+    gp.have = gp.quat = gp.order = gp.n_order = 0u;
+    gp.v[0] = gp.v[1] = gp.v[2] = make_float4(0.f, 0.f, 0.f, 0.f);
+    uint32_t cur_group = 0u, first_anim = FYX_NONE, cur_anim = FYX_NONE, src_done = 0u;
+    // the node's tracks: direct animations first (animation, track order), then group after group, sources in group order
     for (uint32_t k = an.node_begin[e], k1 = an.node_begin[e + 1]; k < k1; ++k) {
         const uint32_t ti = an.node_tracks[k];
+        const uint32_t anim = an.tracks[ti].anim;
+        const AnimStateDev st = an.state[anim];
+        if (st.group != cur_group) {
+            if (cur_group) group_flush(gp, s);
+            cur_group = st.group;
+            first_anim = cur_anim = FYX_NONE;
+        }
         if (!an.value_ok[ti]) continue;
         const float4 v = an.values[ti];
         const uint32_t bk = an.track_bind_kind[ti]; // binding | value_kind << 8
         const uint32_t binding = bk & 0xFFu, kind = bk >> 8;
-        if (binding == FYX_BIND_POSITION && kind == FYX_TV_VECTOR3) {
-            touched = true;
-            if (dirty || t.position[0] != v.x || t.position[1] != v.y || t.position[2] != v.z) {
-                t.position[0] = v.x; t.position[1] = v.y; t.position[2] = v.z;
-                dirty = true;
+        const bool is_quat = (kind == FYX_TV_QUAT || kind == FYX_TV_QUAT_EULER), is_vec3 = (kind == FYX_TV_VECTOR3);
+        if (st.group == 0u) { // AnimationPlayer: only enabled animations tick and apply (scene/animation/mod.rs:84)
+            if (st.enabled) apply_value(s, binding, is_quat, is_vec3, v);
+            continue;
+        }
+        // blend group (BlendAnimations over PlayAnimation sources, machine/node/blend.rs:136-166, pose.rs:41-101)
+        if (!(is_quat || is_vec3) || binding > FYX_BIND_ROTATION) continue;
+        if (anim != cur_anim) { cur_anim = anim; src_done = 0u; }
+        if (first_anim == FYX_NONE) first_anim = anim;
+        const uint32_t bit = 1u << binding;
+        if (anim == first_anim) { // the output has no values for this node yet: it takes a clone of the source's
+            if (!(gp.have & bit)) {
+                gp.order |= binding << (2u * gp.n_order);
+                gp.n_order++;
             }
-        } else if (binding == FYX_BIND_SCALE && kind == FYX_TV_VECTOR3) {
-            touched = true;
-            if (dirty || t.scale[0] != v.x || t.scale[1] != v.y || t.scale[2] != v.z) {
-                t.scale[0] = v.x; t.scale[1] = v.y; t.scale[2] = v.z;
-                dirty = true;
-            }
-        } else if (binding == FYX_BIND_ROTATION && (kind == FYX_TV_QUAT || kind == FYX_TV_QUAT_EULER)) {
-            touched = true;
-            if (dirty || !quat_eq(t.rotation, v)) {
-                t.rotation[0] = v.x; t.rotation[1] = v.y; t.rotation[2] = v.z; t.rotation[3] = v.w;
-                dirty = true;
-            }
+            gp.have |= bit;
+            gp.quat = is_quat ? (gp.quat | bit) : (gp.quat & ~bit);
+            gp.v[binding] = v;
+        } else if ((gp.have & bit) && !(src_done & bit)) { // blended with the source's first value of that binding
+            src_done |= bit;
+            const bool oq = (gp.quat >> binding) & 1u;
+            if (oq == is_quat) gp.v[binding] = blend_value(gp.v[binding], v, st.weight, oq);
         }
     }
-    if (!touched) return;
-    if (dirty) trs_by_slot[slot] = t;
+    if (cur_group) group_flush(gp, s);
+    if (!s.touched) return;
+    if (s.dirty) trs_by_slot[slot] = s.t;
     Affine A;
-    trs_to_local<HAS_STATICS>(t, HAS_STATICS ? st_by_slot + slot : nullptr, A);
+    trs_to_local<HAS_STATICS>(s.t, HAS_STATICS ? st_by_slot + slot : nullptr, A);
     if (!(finite4(A.r0) & finite4(A.r1) & finite4(A.r2))) {
         atomicOr(d_err, E_NOT_AFFINE);
         return;

@@ -40,6 +40,8 @@ void anim_free(fyx_ctx *c)
     c->pend_bk.clear();
     c->pend_state.clear();
     c->n_anim_keys = 0;
+    c->n_blend_groups = 0;
+    c->blend_groups.clear();
     c->an = AnimArrays{};
     c->anim_csr_dirty = true;
 }
@@ -65,23 +67,34 @@ void anim_rebuild_arrays(fyx_ctx *c)
 int32_t anim_build_csr(fyx_ctx *c)
 {
     const uint32_t nt = (uint32_t)c->anim_tracks.size();
-    std::vector<std::pair<uint32_t, uint32_t>> st; // (slot, track)
+    // per node: directly applied animations first (animation order), then blend group after blend group with the
+    // sources in the group's order; tracks in their own order inside an animation
+    std::vector<uint32_t> track_anim(nt);
+    for (uint32_t a = 0; a < c->anims.size(); ++a)
+        for (uint32_t i = 0; i < c->anims[a].n_tracks; ++i) track_anim[c->anims[a].first_track + i] = a;
+    struct Ent { uint32_t slot, group, pos, track; };
+    std::vector<Ent> st;
     st.reserve(nt);
     for (uint32_t i = 0; i < nt; ++i) {
         const uint32_t node = c->anim_tracks[i].target_node;
         if (node >= c->n_nodes) continue; // invalid handle: logged and skipped by the reference
         const uint32_t slot = c->slot_of_node[node];
         if (slot == FYX_NONE) continue;
-        st.emplace_back(slot, i);
+        const AnimHost &h = c->anims[track_anim[i]];
+        st.push_back(Ent{slot, h.st.group, h.st.group ? h.pos_in_group : track_anim[i], i});
     }
-    std::stable_sort(st.begin(), st.end(), [](const auto &x, const auto &y) { return x.first < y.first; });
+    std::stable_sort(st.begin(), st.end(), [](const Ent &x, const Ent &y) {
+        if (x.slot != y.slot) return x.slot < y.slot;
+        if (x.group != y.group) return x.group < y.group; // 0 = directly applied: first
+        return x.pos < y.pos;                             // tracks of one animation keep their order (stable sort)
+    });
     std::vector<uint32_t> node_slot, node_begin, node_tracks(st.size());
     for (size_t k = 0; k < st.size(); ++k) {
-        if (k == 0 || st[k].first != st[k - 1].first) {
-            node_slot.push_back(st[k].first);
+        if (k == 0 || st[k].slot != st[k - 1].slot) {
+            node_slot.push_back(st[k].slot);
             node_begin.push_back((uint32_t)k);
         }
-        node_tracks[k] = st[k].second;
+        node_tracks[k] = st[k].track;
     }
     node_begin.push_back((uint32_t)st.size());
     int32_t rc;
@@ -123,6 +136,7 @@ int32_t anim_flush(fyx_ctx *c)
         CU(cudaMemcpy(c->b_anim_tracks.as<AnimTrackDev>() + t0, c->pend_tracks.data(), c->pend_tracks.size() * sizeof(AnimTrackDev), cudaMemcpyHostToDevice));
         CU(cudaMemcpy(c->b_anim_bk.as<uint32_t>() + t0, c->pend_bk.data(), c->pend_bk.size() * 4, cudaMemcpyHostToDevice));
         CU(cudaMemset(c->b_anim_hints.as<uint4>() + t0, 0, c->pend_tracks.size() * sizeof(uint4))); // HintContainer::default()
+        CU(cudaMemset(c->b_anim_ok.as<uint32_t>() + t0, 0, c->pend_tracks.size() * 4));            // AnimationPose::default(): no values
     }
     CU(cudaMemcpy(c->b_anim_state.as<AnimStateDev>() + a0, c->pend_state.data(), c->pend_state.size() * sizeof(AnimStateDev), cudaMemcpyHostToDevice));
     std::vector<fyx_curve_key>().swap(c->pend_keys);
@@ -277,4 +291,62 @@ extern "C" int32_t fyx_animate(fyx_ctx *c, float dt)
     if (!c->have_topology) return fail(c, FYX_ERR_STATE, "fyx_set_topology has not been called");
     CU(cudaSetDevice(c->device));
     return animate_enqueue(c, dt);
+}
+
+// A blend group: the animations stop being applied directly (AnimationPlayer::auto_apply = false) and become the
+// PlayAnimation sources of one BlendAnimations pose node with constant weights (machine/node/blend.rs:136-166).
+extern "C" int32_t fyx_anim_blend_group(fyx_ctx *c, uint32_t n, const uint32_t *anims, const float *weights, uint32_t *out_group)
+{
+    if (!c) return FYX_ERR_INVALID_ARGUMENT;
+    if (!n || !anims || !weights) return fail(c, FYX_ERR_INVALID_ARGUMENT, "empty blend group");
+    for (uint32_t i = 0; i < n; ++i) {
+        if (anims[i] >= c->anims.size()) return fail(c, FYX_ERR_INVALID_ARGUMENT, "animation %u does not exist", anims[i]);
+        if (c->anims[anims[i]].st.group) return fail(c, FYX_ERR_INVALID_ARGUMENT, "animation %u already belongs to blend group %u", anims[i], c->anims[anims[i]].st.group);
+        for (uint32_t j = 0; j < i; ++j)
+            if (anims[j] == anims[i]) return fail(c, FYX_ERR_INVALID_ARGUMENT, "animation %u listed twice", anims[i]);
+        // inside a group every (node, property) has one track per animation, of a Vector3 / UnitQuaternion kind
+        const AnimHost &h = c->anims[anims[i]];
+        std::vector<uint64_t> seen;
+        seen.reserve(h.n_tracks);
+        for (uint32_t t = 0; t < h.n_tracks; ++t) {
+            const fyx_anim_track &tr = c->anim_tracks[h.first_track + t];
+            if (tr.value_kind != FYX_TV_VECTOR3 && tr.value_kind != FYX_TV_QUAT && tr.value_kind != FYX_TV_QUAT_EULER)
+                return fail(c, FYX_ERR_UNSUPPORTED, "animation %u track %u: only Vector3 / UnitQuaternion tracks can be blended", anims[i], t);
+            seen.push_back(((uint64_t)tr.target_node << 2) | tr.binding);
+        }
+        std::sort(seen.begin(), seen.end());
+        if (std::adjacent_find(seen.begin(), seen.end()) != seen.end())
+            return fail(c, FYX_ERR_UNSUPPORTED, "animation %u animates one property of one node with two tracks", anims[i]);
+    }
+    CU(cudaSetDevice(c->device));
+    int32_t rc = anim_flush(c);
+    if (rc) return rc;
+    const uint32_t g = ++c->n_blend_groups;
+    for (uint32_t i = 0; i < n; ++i) {
+        AnimHost &h = c->anims[anims[i]];
+        h.st.group = g;
+        h.st.weight = weights[i];
+        h.pos_in_group = i;
+        struct { uint32_t group; float weight; } gw = {g, weights[i]};
+        CU(cudaMemcpyAsync(&c->b_anim_state.as<AnimStateDev>()[anims[i]].group, &gw, 8, cudaMemcpyHostToDevice, c->stream));
+    }
+    c->blend_groups.emplace_back(anims, anims + n);
+    c->anim_csr_dirty = true;
+    if (out_group) *out_group = g;
+    return FYX_OK;
+}
+
+// PoseWeight::Constant values of a group's sources
+extern "C" int32_t fyx_anim_set_blend_weights(fyx_ctx *c, uint32_t group, uint32_t n, const float *weights)
+{
+    if (!c) return FYX_ERR_INVALID_ARGUMENT;
+    if (!group || group > c->blend_groups.size()) return fail(c, FYX_ERR_INVALID_ARGUMENT, "blend group %u does not exist", group);
+    const std::vector<uint32_t> &src = c->blend_groups[group - 1];
+    if (n != src.size() || !weights) return fail(c, FYX_ERR_INVALID_ARGUMENT, "blend group %u has %zu sources", group, src.size());
+    CU(cudaSetDevice(c->device));
+    for (uint32_t i = 0; i < n; ++i) {
+        c->anims[src[i]].st.weight = weights[i];
+        CU(cudaMemcpyAsync(&c->b_anim_state.as<AnimStateDev>()[src[i]].weight, &weights[i], 4, cudaMemcpyHostToDevice, c->stream));
+    }
+    return FYX_OK;
 }

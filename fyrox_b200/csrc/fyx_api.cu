@@ -64,7 +64,7 @@ struct VisSlot {
 
 // N2: one animation on the host side (fyx_anim.inl)
 struct AnimHost {
-    uint32_t first_track = 0, n_tracks = 0;
+    uint32_t first_track = 0, n_tracks = 0, pos_in_group = 0;
     AnimStateDev st{};
 };
 
@@ -144,7 +144,8 @@ struct fyx_ctx {
     // N2 animation sampling (fyx_anim.inl)
     std::vector<AnimHost> anims;
     std::vector<fyx_anim_track> anim_tracks; // all tracks, animation after animation
-    uint32_t n_anim_keys = 0;
+    uint32_t n_anim_keys = 0, n_blend_groups = 0;
+    std::vector<std::vector<uint32_t>> blend_groups; // sources of group g at [g - 1]
     bool anim_csr_dirty = true;
     std::vector<fyx_curve_key> pend_keys; // queued by fyx_anim_add, uploaded by anim_flush
     std::vector<AnimTrackDev> pend_tracks;

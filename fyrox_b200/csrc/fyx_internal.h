@@ -92,6 +92,8 @@ struct AnimTrackDev {
 struct AnimStateDev {
     float time, speed, slice_start, slice_end;
     uint32_t looped, enabled;
+    uint32_t group; // 0 = applied directly (AnimationPlayer, auto_apply); g > 0 = source of blend group g
+    float weight;   // its PoseWeight::Constant inside that group
 };
 struct AnimArrays {
     uint32_t n_tracks, n_anims, n_nodes;

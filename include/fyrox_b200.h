@@ -331,6 +331,18 @@ int32_t fyx_anim_set_track_enabled(fyx_ctx *ctx, uint32_t anim, uint32_t track, 
 int32_t fyx_anim_set_speed(fyx_ctx *ctx, uint32_t anim, float speed);
 int32_t fyx_anim_set_time_position(fyx_ctx *ctx, uint32_t anim, float time); /* wraps / clamps into the time slice (lib.rs:432-440) */
 int32_t fyx_anim_get_time_positions(fyx_ctx *ctx, uint32_t first, uint32_t count, float *out);
+/* Pose blending, the smallest useful subset of the blend machine (fyrox-animation/src/machine): the listed animations
+ * stop being applied directly (AnimationPlayer::auto_apply = false) and become, in this order, the PlayAnimation sources
+ * of ONE PoseNode::BlendAnimations with constant weights (machine/node/blend.rs:136-166) in a one-layer, one-state
+ * machine: every enabled source still ticks (machine/mod.rs:366-372; a disabled one keeps contributing the pose of its
+ * last tick), the output pose takes a clone of the first source that has values for a node and blends every later
+ * source into it per binding — AnimationPose::blend_with / TrackValue::blend_with (pose.rs:41-101, value.rs:201-227:
+ * nalgebra lerp for vectors, shortest-way nlerp for rotations) — and is then applied.  Groups are applied after the
+ * directly applied animations, in creation order.  Restrictions: Vector3 / UnitQuaternion(Euler) tracks only, one track
+ * per (node, property) and animation, an animation in at most one group.  Transitions, parameters, masks, blend
+ * spaces, layers > 1: not modelled. */
+int32_t fyx_anim_blend_group(fyx_ctx *ctx, uint32_t n, const uint32_t *anims, const float *weights, uint32_t *out_group);
+int32_t fyx_anim_set_blend_weights(fyx_ctx *ctx, uint32_t group, uint32_t n, const float *weights);
 /* AnimationContainer::update_animations(dt) for every animation of the context.  The touched nodes are marked
  * changed exactly like fyx_set_local_trs; follow with fyx_update_transforms / fyx_render_prep. */
 int32_t fyx_animate(fyx_ctx *ctx, float dt);

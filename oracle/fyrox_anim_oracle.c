@@ -214,6 +214,10 @@ struct orc_animation {
     uint32_t n_keys;
     float speed, time_position, slice_start, slice_end;
     int looped, enabled;
+    /* Animation::pose (lib.rs:916-919): the values pushed by the last update_pose, in track order; it persists while the
+     * animation is disabled (nobody ticks it), which a blend machine that still reads it can observe */
+    float (*pose_val)[4];
+    uint8_t *pose_ok;
 };
 
 orc_animation *orc_animation_new(const orc_track *tracks, uint32_t n_tracks, const orc_curve_key *keys, uint32_t n_keys)
@@ -222,6 +226,8 @@ orc_animation *orc_animation_new(const orc_track *tracks, uint32_t n_tracks, con
     a->tracks = (orc_track *)malloc(sizeof(orc_track) * (n_tracks ? n_tracks : 1));
     memcpy(a->tracks, tracks, sizeof(orc_track) * n_tracks);
     a->hints = (uint32_t(*)[4])calloc(n_tracks ? n_tracks : 1, sizeof(uint32_t[4]));
+    a->pose_val = (float(*)[4])calloc(n_tracks ? n_tracks : 1, sizeof(float[4]));
+    a->pose_ok = (uint8_t *)calloc(n_tracks ? n_tracks : 1, 1);
     a->n_tracks = n_tracks;
     a->keys = (orc_curve_key *)malloc(sizeof(orc_curve_key) * (n_keys ? n_keys : 1));
     memcpy(a->keys, keys, sizeof(orc_curve_key) * n_keys);
@@ -240,6 +246,8 @@ void orc_animation_free(orc_animation *a)
     if (!a) return;
     free(a->tracks);
     free(a->hints);
+    free(a->pose_val);
+    free(a->pose_ok);
     free(a->keys);
     free(a);
 }
@@ -272,56 +280,78 @@ static int quat_eq(const float a[4], const float b[4])
     return a[0] == -b[0] && a[1] == -b[1] && a[2] == -b[2] && a[3] == -b[3];
 }
 
-/* One tick of one animation:
- *   Animation::tick (lib.rs:471-496): update_pose (lib.rs:895-914: per track, in order, fetch(time_position) and
- *   push into the target's NodePose) then advance the time position (signals / root motion: out of scope);
- *   AnimationPose::apply_internal + BoundValueCollection::apply (scene/animation/mod.rs:107-179): per node the
- *   values in push order: set_position / set_scale / set_rotation (scene/transform.rs:202-262: stored only if the
- *   transform is already dirty or the value differs), each through local_transform_mut() = TransformChanged.
- * Values of different nodes are independent, so walking the tracks in order is the pose map walked in any order.
- * dirty[n] = Transform::dirty of node n (cleared by the matrix() of the last Graph::update), touched[n] = a
- * TransformChanged message was sent. */
-static void tick_apply(orc_animation *a, float dt, const orc_graph *g, orc_transform *transforms, uint32_t n_nodes,
-                       uint8_t *dirty, uint8_t *touched)
+/* Animation::tick (lib.rs:471-496): update_pose (lib.rs:895-914: pose.reset(), then per enabled track, in order,
+ * fetch(time_position) and push into the target's NodePose), then the time position advances (signals / root
+ * motion: out of scope). */
+static void tick(orc_animation *a, float dt)
 {
     for (uint32_t ti = 0; ti < a->n_tracks; ++ti) {
         const orc_track *t = &a->tracks[ti];
+        a->pose_ok[ti] = 0;
         if (!t->enabled) continue;
-        float v[4];
-        if (!orc_track_fetch(t, a->keys, a->time_position, a->hints[ti], v)) continue;
-        uint32_t n = t->target_node;
-        if (n >= n_nodes || !orc_node_is_alive(g, n)) continue; /* try_borrow_mut failed: logged and skipped */
-        orc_transform *tr = &transforms[n];
-        switch (t->binding) {
-        case ORC_BIND_POSITION:
-            if (t->value_kind != ORC_TV_VECTOR3) break; /* "underlying type is not Vector3": logged, skipped */
-            touched[n] = 1;
-            if (dirty[n] || tr->local_position[0] != v[0] || tr->local_position[1] != v[1] || tr->local_position[2] != v[2]) {
-                memcpy(tr->local_position, v, 12);
-                dirty[n] = 1;
-            }
-            break;
-        case ORC_BIND_SCALE:
-            if (t->value_kind != ORC_TV_VECTOR3) break;
-            touched[n] = 1;
-            if (dirty[n] || tr->local_scale[0] != v[0] || tr->local_scale[1] != v[1] || tr->local_scale[2] != v[2]) {
-                memcpy(tr->local_scale, v, 12);
-                dirty[n] = 1;
-            }
-            break;
-        case ORC_BIND_ROTATION:
-            if (t->value_kind != ORC_TV_QUAT && t->value_kind != ORC_TV_QUAT_EULER) break;
-            touched[n] = 1;
-            if (dirty[n] || !quat_eq(tr->local_rotation, v)) {
-                memcpy(tr->local_rotation, v, 16);
-                dirty[n] = 1;
-            }
-            break;
-        default: break; /* ValueBinding::Property: reflection, out of scope */
-        }
+        if (orc_track_fetch(t, a->keys, a->time_position, a->hints[ti], a->pose_val[ti])) a->pose_ok[ti] = 1;
     }
-    /* lib.rs:474-491 */
-    orc_animation_set_time_position(a, a->time_position + dt * a->speed);
+    orc_animation_set_time_position(a, a->time_position + dt * a->speed); /* lib.rs:474-491 */
+}
+
+/* One BoundValue reaching a node: BoundValueCollection::apply (scene/animation/mod.rs:147-179) through
+ * Transform::set_position / set_scale / set_rotation (scene/transform.rs:202-262: stored only if the transform is
+ * already dirty or the value differs), each via local_transform_mut() = TransformChanged.
+ * dirty[n] = Transform::dirty of node n (cleared by the matrix() of the last Graph::update), touched[n] = a
+ * TransformChanged message was sent. */
+static void apply_value(uint32_t binding, int is_quat, int is_vec3, const float v[4], uint32_t n, const orc_graph *g,
+                        orc_transform *transforms, uint32_t n_nodes, uint8_t *dirty, uint8_t *touched)
+{
+    if (n >= n_nodes || !orc_node_is_alive(g, n)) return; /* try_borrow_mut failed: logged and skipped */
+    orc_transform *tr = &transforms[n];
+    switch (binding) {
+    case ORC_BIND_POSITION:
+        if (!is_vec3) break; /* "underlying type is not Vector3": logged, skipped */
+        touched[n] = 1;
+        if (dirty[n] || tr->local_position[0] != v[0] || tr->local_position[1] != v[1] || tr->local_position[2] != v[2]) {
+            memcpy(tr->local_position, v, 12);
+            dirty[n] = 1;
+        }
+        break;
+    case ORC_BIND_SCALE:
+        if (!is_vec3) break;
+        touched[n] = 1;
+        if (dirty[n] || tr->local_scale[0] != v[0] || tr->local_scale[1] != v[1] || tr->local_scale[2] != v[2]) {
+            memcpy(tr->local_scale, v, 12);
+            dirty[n] = 1;
+        }
+        break;
+    case ORC_BIND_ROTATION:
+        if (!is_quat) break;
+        touched[n] = 1;
+        if (dirty[n] || !quat_eq(tr->local_rotation, v)) {
+            memcpy(tr->local_rotation, v, 16);
+            dirty[n] = 1;
+        }
+        break;
+    default: break; /* ValueBinding::Property: reflection, out of scope */
+    }
+}
+
+static int kind_is_quat(uint32_t k) { return k == ORC_TV_QUAT || k == ORC_TV_QUAT_EULER; }
+
+/* AnimationPose::apply_internal of one animation's own pose.  Values of different nodes are independent, so walking
+ * the tracks in order is the pose map walked in any order. */
+static void apply_pose(const orc_animation *a, const orc_graph *g, orc_transform *transforms, uint32_t n_nodes,
+                       uint8_t *dirty, uint8_t *touched)
+{
+    for (uint32_t ti = 0; ti < a->n_tracks; ++ti) {
+        if (!a->pose_ok[ti]) continue;
+        const orc_track *t = &a->tracks[ti];
+        apply_value(t->binding, kind_is_quat(t->value_kind), t->value_kind == ORC_TV_VECTOR3, a->pose_val[ti], t->target_node, g,
+                    transforms, n_nodes, dirty, touched);
+    }
+}
+
+static void refresh_touched(orc_graph *g, orc_transform *transforms, uint32_t n_nodes, const uint8_t *touched)
+{
+    for (uint32_t k = 0; k < n_nodes; ++k)
+        if (touched[k]) orc_node_set_local_transform(g, k, &transforms[k]);
 }
 
 /* AnimationContainer::update_animations — scene/animation/mod.rs:83-88: every enabled animation, in pool order,
@@ -333,9 +363,105 @@ void orc_update_animations(orc_animation **anims, uint32_t n, float dt, orc_grap
     uint8_t *dirty = (uint8_t *)calloc(n_nodes ? n_nodes : 1, 1);
     uint8_t *touched = (uint8_t *)calloc(n_nodes ? n_nodes : 1, 1);
     for (uint32_t i = 0; i < n; ++i)
-        if (anims[i] && anims[i]->enabled) tick_apply(anims[i], dt, g, transforms, n_nodes, dirty, touched);
-    for (uint32_t k = 0; k < n_nodes; ++k)
-        if (touched[k]) orc_node_set_local_transform(g, k, &transforms[k]);
+        if (anims[i] && anims[i]->enabled) {
+            tick(anims[i], dt);
+            apply_pose(anims[i], g, transforms, n_nodes, dirty, touched);
+        }
+    refresh_touched(g, transforms, n_nodes, touched);
+    free(dirty);
+    free(touched);
+}
+
+/* ---- blend machine, the smallest useful subset (fyrox-animation/src/machine) ----
+ * One Machine with one layer, one state whose root is PoseNode::BlendAnimations over PoseNode::PlayAnimation sources
+ * with constant weights, driving nodes through an AnimationPlayer with auto_apply = false:
+ *   Machine::evaluate_pose (machine/mod.rs:344-382): every ENABLED animation the state uses ticks; the layer's pose is
+ *   the state's pose (layer.rs:692-698, one state, no transition, no mask), final_pose = clone of it;
+ *   BlendAnimations::eval_pose (machine/node/blend.rs:136-166): output.reset(); for each source in order
+ *   output.blend_with(source pose, weight) where PlayAnimation::eval_pose (node/play.rs:86-100) is a clone of
+ *   Animation::pose() — stale if that animation is disabled;
+ *   AnimationPose::blend_with (pose.rs:87-101) / NodePose::blend_with (pose.rs:41-49) / BoundValueCollection::blend_with
+ *   (value.rs:437-445): a node the output has no values for takes a CLONE of the source's values (the weight is not
+ *   used), otherwise every output value is blended with the source's FIRST value of the same binding
+ *   (TrackValue::blend_with, value.rs:201-227: same variant only);
+ *   then the pose is applied (AnimationPoseExt::apply, scene/animation/mod.rs:117-125). */
+typedef struct { uint32_t binding, is_quat, is_vec3; float v[4]; } pose_value;
+typedef struct { pose_value *vals; uint32_t n, cap; } node_pose;
+
+static void node_pose_push(node_pose *p, const pose_value *v)
+{
+    if (p->n == p->cap) {
+        p->cap = p->cap ? p->cap * 2 : 4;
+        p->vals = (pose_value *)realloc(p->vals, sizeof(pose_value) * p->cap);
+    }
+    p->vals[p->n++] = *v;
+}
+
+void orc_blend_group_update(orc_animation **anims, const float *weights, uint32_t n, float dt, orc_graph *g,
+                            orc_transform *transforms, uint32_t n_nodes)
+{
+    for (uint32_t i = 0; i < n; ++i) /* animations_cache is a set: an animation ticks once */
+        if (anims[i] && anims[i]->enabled) {
+            int seen = 0;
+            for (uint32_t j = 0; j < i; ++j) seen |= (anims[j] == anims[i]);
+            if (!seen) tick(anims[i], dt);
+        }
+    node_pose *out = (node_pose *)calloc(n_nodes ? n_nodes : 1, sizeof(node_pose));
+    node_pose *src = (node_pose *)calloc(n_nodes ? n_nodes : 1, sizeof(node_pose));
+    for (uint32_t s = 0; s < n; ++s) {
+        const orc_animation *a = anims[s];
+        if (!a) continue;
+        /* the source's pose, grouped by node (values in track order) */
+        for (uint32_t ti = 0; ti < a->n_tracks; ++ti) {
+            if (!a->pose_ok[ti]) continue;
+            const orc_track *t = &a->tracks[ti];
+            if (t->target_node >= n_nodes) continue; /* would fail at apply; blending it changes nothing observable */
+            pose_value pv;
+            pv.binding = t->binding;
+            pv.is_quat = (uint32_t)kind_is_quat(t->value_kind);
+            pv.is_vec3 = (t->value_kind == ORC_TV_VECTOR3);
+            memcpy(pv.v, a->pose_val[ti], 16);
+            node_pose_push(&src[t->target_node], &pv);
+        }
+        for (uint32_t ti = 0; ti < a->n_tracks; ++ti) {
+            if (!a->pose_ok[ti]) continue;
+            const uint32_t nd = a->tracks[ti].target_node;
+            if (nd >= n_nodes || !src[nd].n) continue; /* already merged (n reset below) */
+            node_pose *o = &out[nd], *sp = &src[nd];
+            if (o->n == 0) {
+                for (uint32_t k = 0; k < sp->n; ++k) node_pose_push(o, &sp->vals[k]);
+            } else {
+                for (uint32_t k = 0; k < o->n; ++k) {
+                    pose_value *ov = &o->vals[k];
+                    for (uint32_t q = 0; q < sp->n; ++q)
+                        if (sp->vals[q].binding == ov->binding) { /* find(): the first value with that binding */
+                            if (ov->is_quat && sp->vals[q].is_quat) orc_track_value_blend(1, ov->v, sp->vals[q].v, weights[s]);
+                            else if (ov->is_vec3 && sp->vals[q].is_vec3) {
+                                float b4[4] = {sp->vals[q].v[0], sp->vals[q].v[1], sp->vals[q].v[2], 0.0f};
+                                ov->v[3] = 0.0f;
+                                orc_track_value_blend(0, ov->v, b4, weights[s]);
+                            }
+                            break;
+                        }
+                }
+            }
+            sp->n = 0;
+        }
+    }
+    uint8_t *dirty = (uint8_t *)calloc(n_nodes ? n_nodes : 1, 1);
+    uint8_t *touched = (uint8_t *)calloc(n_nodes ? n_nodes : 1, 1);
+    for (uint32_t nd = 0; nd < n_nodes; ++nd)
+        for (uint32_t k = 0; k < out[nd].n; ++k) {
+            const pose_value *pv = &out[nd].vals[k];
+            apply_value(pv->binding, (int)pv->is_quat, (int)pv->is_vec3, pv->v, nd, g, transforms, n_nodes, dirty, touched);
+        }
+    refresh_touched(g, transforms, n_nodes, touched);
+    for (uint32_t nd = 0; nd < n_nodes; ++nd) {
+        free(out[nd].vals);
+        free(src[nd].vals);
+    }
+    free(out);
+    free(src);
     free(dirty);
     free(touched);
 }

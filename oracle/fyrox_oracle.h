@@ -210,7 +210,26 @@ float orc_animation_time_position(const orc_animation *a);
 int   orc_animation_is_enabled(const orc_animation *a);
 void  orc_update_animations(orc_animation **anims, uint32_t n, float dt, orc_graph *g, orc_transform *transforms,
                             uint32_t n_nodes);                                    /* scene/animation/mod.rs:83-88,107-179 */
+void  orc_blend_group_update(orc_animation **anims, const float *weights, uint32_t n, float dt, orc_graph *g,
+                             orc_transform *transforms, uint32_t n_nodes);       /* machine/mod.rs:344-382, node/blend.rs:136-166, pose.rs:41-101 */
 int   orc_node_is_alive(const orc_graph *g, uint32_t n);
+
+/* ---- "soa-omp-NT": the same arithmetic on flat arrays with OpenMP (fyrox_oracle_mt.c) — a best-effort multi-core CPU
+ * baseline, NOT how the reference runs (it is single-threaded); results equal the restatement above bit for bit ---- */
+typedef struct orc_mt orc_mt;
+orc_mt  *orc_mt_new(uint32_t n, uint32_t root, const uint32_t *parent, const uint32_t *flags, const uint32_t *mask,
+                    const float *local_m16, const float *local_aabb6);
+void     orc_mt_free(orc_mt *m);
+void     orc_mt_set_threads(orc_mt *m, int threads);
+void     orc_mt_set_local_matrices(orc_mt *m, uint32_t count, const uint32_t *idx, const float *m16);
+void     orc_mt_set_inv_bind(orc_mt *m, uint32_t node, const float m16[16]);
+uint32_t orc_mt_add_surface(orc_mt *m, uint32_t mesh, uint32_t n_bones, const uint32_t *bones, uint32_t n_verts,
+                            const void *verts, const orc_vertex_layout *layout);
+void     orc_mt_update(orc_mt *m);
+size_t   orc_mt_cull(const orc_mt *m, const orc_frustum *f, uint32_t render_mask, int shadow_pass, uint32_t *out, size_t cap);
+void     orc_mt_skin_surface(const orc_mt *m, uint32_t surface, float *out_pos3, float *out_nrm3);
+void     orc_mt_skin_all(const orc_mt *m);
+void     orc_mt_get(const orc_mt *m, uint32_t node, float g16[16], orc_aabb *world_aabb, uint32_t *gflags /* vis | en<<1 | reach<<2 */);
 
 #ifdef __cplusplus
 }

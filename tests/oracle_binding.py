@@ -165,6 +165,18 @@ def lib() -> C.CDLL:
         "orc_animation_is_enabled": (C.c_int, [vp]),
         "orc_update_animations": (None, [vp, C.c_uint32, C.c_float, vp, vp, C.c_uint32]),
         "orc_node_is_alive": (C.c_int, [vp, C.c_uint32]),
+        "orc_blend_group_update": (None, [vp, f32p, C.c_uint32, C.c_float, vp, vp, C.c_uint32]),
+        "orc_mt_new": (vp, [C.c_uint32, C.c_uint32, vp, vp, vp, vp, vp]),
+        "orc_mt_free": (None, [vp]),
+        "orc_mt_set_threads": (None, [vp, C.c_int]),
+        "orc_mt_set_local_matrices": (None, [vp, C.c_uint32, vp, vp]),
+        "orc_mt_set_inv_bind": (None, [vp, C.c_uint32, f32p]),
+        "orc_mt_add_surface": (C.c_uint32, [vp, C.c_uint32, C.c_uint32, vp, C.c_uint32, vp, C.POINTER(VertexLayout)]),
+        "orc_mt_update": (None, [vp]),
+        "orc_mt_cull": (C.c_size_t, [vp, C.POINTER(Frustum), C.c_uint32, C.c_int, vp, C.c_size_t]),
+        "orc_mt_skin_surface": (None, [vp, C.c_uint32, f32p, f32p]),
+        "orc_mt_skin_all": (None, [vp]),
+        "orc_mt_get": (None, [vp, C.c_uint32, f32p, C.POINTER(Aabb), C.POINTER(C.c_uint32)]),
         "orc_node_instance": (C.c_uint64, [vp, C.c_uint32, f32p, f32p, f32p, f32p]),
         "orc_mesh_accurate_world_bounding_box": (None, [vp, C.c_uint32, C.POINTER(Aabb)]),
         "orc_skin_vertices": (None, [f32p, C.c_uint32, vp, C.POINTER(VertexLayout), f32p, f32p]),
@@ -433,3 +445,78 @@ def update_animations(anims, dt, graph: "Graph", transforms):
     """AnimationContainer::update_animations over a list of Animation; `transforms` is a ctypes array of Transform per node."""
     arr = (C.c_void_p * max(len(anims), 1))(*[a.h for a in anims])
     lib().orc_update_animations(arr, len(anims), float(dt), graph.h, transforms, len(transforms))
+
+
+def blend_group_update(anims, weights, dt, graph: "Graph", transforms):
+    """One Machine (one layer, one state, BlendAnimations over PlayAnimation sources) evaluated and applied."""
+    arr = (C.c_void_p * max(len(anims), 1))(*[a.h for a in anims])
+    w = np.ascontiguousarray(weights, dtype=np.float32)
+    lib().orc_blend_group_update(arr, fp(w), len(anims), float(dt), graph.h, transforms, len(transforms))
+
+
+# ---- "soa-omp-NT" multi-core baseline (fyrox_oracle_mt.c) ---------------------------------------------------
+class MtGraph:
+    """Flat-array, OpenMP form of the same arithmetic (NOT how the reference runs; see fyrox_oracle_mt.c)."""
+
+    def __init__(self, parent, flags=None, render_mask=None, local_m16=None, local_aabb=None, root=0, threads=None):
+        self.L = lib()
+        n = len(parent)
+
+        def p(a, dt):
+            if a is None:
+                return None, None
+            a = np.ascontiguousarray(a, dtype=dt)
+            return a, a.ctypes.data_as(C.c_void_p)
+
+        keep = [p(parent, np.uint32), p(flags, np.uint32), p(render_mask, np.uint32), p(local_m16, np.float32), p(local_aabb, np.float32)]
+        self.h = self.L.orc_mt_new(n, root, *[k[1] for k in keep])
+        self.n = n
+        if threads:
+            self.L.orc_mt_set_threads(self.h, int(threads))
+
+    def __del__(self):
+        try:
+            if self.h:
+                self.L.orc_mt_free(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+    def set_local_matrices(self, m16, idx=None):
+        m16 = np.ascontiguousarray(m16, dtype=np.float32)
+        ix = None if idx is None else np.ascontiguousarray(idx, dtype=np.uint32)
+        self.L.orc_mt_set_local_matrices(self.h, m16.size // 16, None if ix is None else ix.ctypes.data_as(C.c_void_p), m16.ctypes.data_as(C.c_void_p))
+
+    def set_inv_bind(self, n, m16):
+        m = np.ascontiguousarray(m16, dtype=np.float32).reshape(16)
+        self.L.orc_mt_set_inv_bind(self.h, int(n), fp(m))
+
+    def add_surface(self, mesh, bones, verts=None, layout=ANIMATED_VERTEX):
+        b = np.ascontiguousarray(bones, dtype=np.uint32)
+        nv = 0 if verts is None else len(verts) // layout.stride
+        vptr = None if verts is None else np.ascontiguousarray(verts, dtype=np.uint8).ctypes.data_as(C.c_void_p)
+        return self.L.orc_mt_add_surface(self.h, int(mesh), len(b), b.ctypes.data_as(C.c_void_p), nv, vptr, C.byref(layout))
+
+    def update(self):
+        self.L.orc_mt_update(self.h)
+
+    def cull(self, frustum, render_mask=0xFFFFFFFF, shadow_pass=False):
+        out = np.empty(max(self.n, 1), dtype=np.uint32)
+        n = self.L.orc_mt_cull(self.h, C.byref(frustum) if frustum is not None else None, render_mask, int(shadow_pass), out.ctypes.data_as(C.c_void_p), self.n)
+        return out[:n].copy()
+
+    def skin(self, surface, n_verts):
+        pos = np.empty((n_verts, 3), dtype=np.float32)
+        nrm = np.empty((n_verts, 3), dtype=np.float32)
+        self.L.orc_mt_skin_surface(self.h, surface, fp(pos.reshape(-1)), fp(nrm.reshape(-1)))
+        return pos, nrm
+
+    def skin_all(self):
+        self.L.orc_mt_skin_all(self.h)
+
+    def get(self, i):
+        g = np.empty(16, dtype=np.float32)
+        a = Aabb()
+        f = C.c_uint32()
+        self.L.orc_mt_get(self.h, int(i), fp(g), C.byref(a), C.byref(f))
+        return g, a.to_np(), f.value

@@ -223,6 +223,66 @@ def test_animation_players_match_oracle_bit_for_bit(ctx, with_statics):
         assert_same_hierarchy(og2, ctx)
 
 
+def test_blend_groups_match_oracle_bit_for_bit(ctx):
+    """fyx_anim_blend_group: BlendAnimations over PlayAnimation sources with constant weights in a one-layer, one-state
+    machine (machine/mod.rs:344-382, node/blend.rs:136-166, pose.rs:41-101), next to a directly applied animation."""
+    rng = np.random.default_rng(404)
+    n = 420
+    parent, flags, trs = make_graph(rng, n)
+    og, tr = load_pair(ctx, parent, flags, trs)
+
+    def build(nodes, pos=True, rot=True, scale=False, kinds=(0, 1, 2)):
+        b = Builder(rng)
+        for node in nodes:
+            if pos:
+                b.track(node, ob.BIND_POSITION, ob.TV_VECTOR3, kinds=kinds)
+            if rot:
+                b.track(node, ob.BIND_ROTATION, ob.TV_QUAT, lo=-1.0, hi=1.0, kinds=kinds)
+            if scale:
+                b.track(node, ob.BIND_SCALE, ob.TV_VECTOR3, lo=0.5, hi=2.0, kinds=kinds)
+        return b.arrays()
+
+    specs = [
+        (build(range(1, 101)), dict(speed=1.0, looped=True, time_slice=(0.0, 2.0), time_position=0.0)),                       # 0: A
+        (build(range(50, 151), scale=True), dict(speed=0.5, looped=True, time_slice=(0.0, 2.25), time_position=1.0)),         # 1: B
+        (build(range(1, 151), pos=False), dict(speed=-1.0, looped=False, time_slice=(0.25, 2.0), time_position=2.0)),         # 2: C
+        (build(range(200, 251)), dict(speed=1.0, looped=True, time_slice=(0.0, 2.0), time_position=0.5)),                     # 3: D
+        (build(range(200, 251), kinds=(1,)), dict(speed=2.0, looped=True, time_slice=(0.0, 1.5), time_position=0.0)),         # 4: E
+        (build(range(300, 351), scale=True), dict(speed=1.0, looped=True, time_slice=(0.0, 2.0), time_position=0.25)),        # 5: F (direct)
+    ]
+    anims = []
+    for (t, k), kw in specs:
+        anims.append(ob.Animation(t, k, **kw))
+        ctx.anim_add(t, k, **kw)
+    w1, w2 = [0.9, 0.3, 0.6], [1.0, 0.45]
+    g1 = ctx.anim_blend_group([0, 1, 2], w1)
+    g2 = ctx.anim_blend_group([4, 3], w2)  # source order is the group's, not the animation ids'
+    assert (g1, g2) == (1, 2)
+    with pytest.raises(fb.FyxError):
+        ctx.anim_blend_group([0, 5], [1, 1])  # already in a group
+    dt = 0.125
+    for frame in range(11):
+        if frame == 4:
+            ob.lib().orc_animation_set_enabled(anims[1].h, 0)  # B stops ticking; its last pose keeps blending in
+            ctx.anim_set_enabled(1, False)
+        if frame == 6:
+            w1 = [0.0, 0.75, 0.1]
+            ctx.anim_set_blend_weights(g1, w1)
+        if frame == 8:
+            ob.lib().orc_animation_set_enabled(anims[1].h, 1)
+            ctx.anim_set_enabled(1, True)
+            ob.lib().orc_animation_set_enabled(anims[0].h, 0)  # now the FIRST source is the stale one
+            ctx.anim_set_enabled(0, False)
+        ob.update_animations([anims[5]], dt, og, tr)
+        ob.blend_group_update([anims[0], anims[1], anims[2]], w1, dt, og, tr)
+        ob.blend_group_update([anims[4], anims[3]], w2, dt, og, tr)
+        og.update()
+        ctx.animate(dt)
+        ctx.update_transforms(fb.UPDATE_INCREMENTAL)
+        times_equal(ctx, anims)
+        assert_same_hierarchy(og, ctx)
+
+
 def test_euler_rotation_tracks_within_libm_tolerance(ctx):
     rng = np.random.default_rng(7)
     n = 300

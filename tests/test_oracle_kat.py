@@ -392,3 +392,89 @@ def test_animation_tick_applies_pose_then_advances_time():
     qa = np.array([0, 0, 0, 1], np.float32)
     L.orc_track_value_blend(1, fp(qa), fp(np.array([0, 0, 0, -1], np.float32)), 0.5)
     assert qa.tolist() == [0.0, 0.0, 0.0, -1.0]  # a is negated first (dot < 0), so the blend does not pass through zero
+
+
+def test_mt_oracle_equals_the_single_threaded_one():
+    """The multi-core CPU baseline (fyrox_oracle_mt.c, flat arrays + OpenMP) computes exactly what the reference-shaped
+    restatement does: global transforms, flags, mesh boxes (incl. the skinned-mesh bone fold), visible sets for the
+    camera and the six cube faces, palettes + skinned streams."""
+    from fyrox_b200.scenegen import Scene
+    from helpers import cube_frusta, camera_frustum
+
+    sc = Scene(6000, 8, verts_per_unit=300)
+    aabb = sc.local_aabb.copy()
+    og = ob.Graph.build(sc.parent, sc.flags, sc.render_mask, sc.local_m16, aabb)
+    mt = ob.MtGraph(sc.parent, sc.flags, sc.render_mask, sc.local_m16, aabb, threads=4)
+    for u in range(sc.n_units):
+        mesh, bones, ib = sc.unit_mesh_node(u), sc.unit_bone_nodes(u), sc.unit_inv_bind(u)
+        verts, _ = sc.unit_vertices(u)
+        for k, b in enumerate(bones):
+            og.set_inv_bind(int(b), ib[k])
+            mt.set_inv_bind(int(b), ib[k])
+        og.add_surface(mesh, bones, verts)
+        og.recalc_local_aabb(mesh)
+        assert mt.add_surface(mesh, bones, verts) == u
+    for frame in range(2):
+        idx, m = sc.animate(frame)
+        for i in range(idx.size):
+            og.set_local_matrix(int(idx[i]), m[i])
+        og.L.orc_graph_drop_messages(og.h)
+        mt.set_local_matrices(m, idx)
+        og.update_hierarchical_data()
+        mt.update()
+        G = og.global_transforms()
+        for i in range(sc.capacity):
+            g, wa, fl = mt.get(i)
+            assert np.array_equal(g.view(np.uint32), G[i].view(np.uint32)), i
+            assert (fl & 1) == og.global_visibility(i) and ((fl >> 1) & 1) == og.is_globally_enabled(i)
+            if sc.flags[i] & (1 << 5):
+                assert np.array_equal(wa.view(np.uint32), og.world_bounding_box(i).view(np.uint32)), i
+        fos, _ = cube_frusta()
+        fo, _ = camera_frustum()
+        for k, f in enumerate(fos + [fo]):
+            shadow = k < 6 and k % 2 == 1
+            want = np.sort(og.from_graph(f, 0xFFFF00FF, shadow))
+            got = mt.cull(f, 0xFFFF00FF, shadow)
+            assert np.array_equal(got, want)
+        for u in range(sc.n_units):
+            p0, n0 = og.skin(sc.unit_mesh_node(u), 0, sc.verts_per_unit)
+            p1, n1 = mt.skin(u, sc.verts_per_unit)
+            assert np.array_equal(p0.view(np.uint32), p1.view(np.uint32)) and np.array_equal(n0.view(np.uint32), n1.view(np.uint32))
+    mt.skin_all()
+
+
+def test_blend_group_clones_the_first_source_and_lerps_the_rest():
+    """BlendAnimations::eval_pose / AnimationPose::blend_with (machine/node/blend.rs:136-166, pose.rs:41-101): the first
+    source with values for a node is cloned (its weight is not used), later sources are lerped in per binding; a binding
+    the output does not have is dropped."""
+    def const_track(node, binding, vals):
+        keys = _keys([(0.0, v) for v in vals], kind=ob.KEY_CONSTANT)
+        t = np.zeros(1, ob.TRACK_DTYPE)
+        t[0]["target_node"], t[0]["binding"], t[0]["value_kind"], t[0]["enabled"], t[0]["n_curves"] = node, binding, ob.TV_VECTOR3, 1, 3
+        t[0]["first_key"][:3] = [0, 1, 2]
+        t[0]["n_keys"][:3] = [1, 1, 1]
+        return t, keys
+
+    ta, ka = const_track(1, ob.BIND_POSITION, (0.0, 0.0, 0.0))
+    tb, kb = const_track(1, ob.BIND_POSITION, (2.0, 4.0, 6.0))
+    ts, ks = const_track(1, ob.BIND_SCALE, (3.0, 3.0, 3.0))
+    tb2 = np.concatenate([tb, ts])
+    tb2[1]["first_key"][:3] = [3, 4, 5]
+    kb2 = np.concatenate([kb, ks])
+    a = ob.Animation(ta, ka, time_slice=(0.0, 1.0))
+    b = ob.Animation(tb2, kb2, time_slice=(0.0, 1.0))
+    parent = np.array([0xFFFFFFFF, 0], np.uint32)
+    og = ob.Graph.build(parent, None, None, np.tile(np.eye(4, dtype=np.float32).reshape(16), (2, 1)), None)
+    tr = (ob.Transform * 2)()
+    for i in range(2):
+        L.orc_transform_identity(C.byref(tr[i]))
+    ob.blend_group_update([a, b], [0.9, 0.25], 0.1, og, tr)
+    assert tuple(tr[1].local_position) == (0.5, 1.0, 1.5)   # a*(1-0.25) + b*0.25; a's own weight 0.9 plays no role
+    assert tuple(tr[1].local_scale) == (1.0, 1.0, 1.0)      # b's scale has no counterpart in the output: dropped
+    ob.blend_group_update([b, a], [0.9, 0.25], 0.1, og, tr)
+    assert tuple(tr[1].local_position) == (1.5, 3.0, 4.5) and tuple(tr[1].local_scale) == (3.0, 3.0, 3.0)
+    # a disabled source is not ticked but its last pose still blends in
+    L.orc_animation_set_enabled(b.h, 0)
+    t_before = b.time_position
+    ob.blend_group_update([a, b], [1.0, 0.5], 0.1, og, tr)
+    assert b.time_position == t_before and tuple(tr[1].local_position) == (1.0, 2.0, 3.0)
