@@ -328,7 +328,7 @@ void to_dev_frustum(const fyx_frustum &f, uint32_t cam_mask, uint32_t pass_flags
         int n = 0;
         uint32_t masks[8] = {0};
         float vals[8];
-        d.ax_mask[k][0] = d.ax_mask[k][1] = 0;
+        for (int j = 0; j < 8; ++j) d.ax_mask[k][j] = 0;
         for (int i = 0; i < 8; ++i) {
             const float v = f.corners[i][k];
             uint32_t vb, ub;
@@ -347,15 +347,13 @@ void to_dev_frustum(const fyx_frustum &f, uint32_t cam_mask, uint32_t pass_flags
         for (int j = n; j < 8; ++j) vals[j] = std::nanf(""); // never inside any box
         d.ax_val[k][0] = make_float4(vals[0], vals[1], vals[2], vals[3]);
         d.ax_val[k][1] = make_float4(vals[4], vals[5], vals[6], vals[7]);
-        for (int j = 0; j < n; ++j) d.ax_mask[k][j >> 2] |= masks[j] << (8 * (j & 3));
+        for (int j = 0; j < n; ++j) d.ax_mask[k][j] = masks[j];
         d.n_ax |= (uint32_t)n << (8 * k);
     }
     d.cam_mask = cam_mask;
     d.pass_flags = pass_flags;
-    d.psel = 0;
     for (int p = 0; p < 6; ++p)
-        for (int k = 0; k < 3; ++k)
-            if (f.planes[p][k] < 0.0f) d.psel |= 1u << (3 * p + k);
+        for (int k = 0; k < 3; ++k) d.vsel[p >> 1][k][p & 1] = (f.planes[p][k] < 0.0f) ? 0x3210u : 0x7654u;
 }
 
 int32_t prepare_cull(fyx_ctx *c, uint32_t nf, const fyx_frustum *fr, const uint32_t *cam_mask, const uint32_t *pass_flags)

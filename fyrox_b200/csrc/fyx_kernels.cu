@@ -78,6 +78,9 @@ static void launch_pdl(void (*kernel)(Params...), unsigned grid, unsigned block,
 // (iterate_recursive, renderer/bundle.rs:988-1004), for every frustum of the call.  Bit f of the
 // result = "node is in the visible set of frustum f".
 // ------------------------------------------------------------------------------------------------
+// NFT: number of frusta known at compile time (the loop is unrolled and cp.f[f] becomes constant-bank operands of the
+// arithmetic instead of ~35 indexed parameter loads per frustum), 0 = run-time count.
+template <int NFT>
 __device__ __forceinline__ uint32_t cull_bits(const uint32_t nf, const uint32_t mask, const float2 wx, const float2 wy,
                                               const float2 wz, const CullParams &cp)
 {
@@ -89,11 +92,17 @@ __device__ __forceinline__ uint32_t cull_bits(const uint32_t nf, const uint32_t 
     kc.negzero = make_float2(cp.negzero, cp.negzero);
     const bool tame = aabb_is_tame(wx, wy, wz);
     uint32_t bits = 0u;
-    for (int f = 0; f < cp.nf; ++f) {
+    auto one = [&](const int f) {
         bool ok = (mask & cp.f[f].cam_mask) != 0u;
         ok &= !((cp.f[f].pass_flags & FYX_PASS_SHADOW) && !(nf & FYX_NODE_CAST_SHADOWS));
         if (ok && (nf & FYX_NODE_FRUSTUM_CULLING)) ok = frustum_intersects_aabb(cp.f[f], wx, wy, wz, kc, tame);
         bits |= ok ? (1u << f) : 0u;
+    };
+    if (NFT > 0) {
+#pragma unroll
+        for (int f = 0; f < NFT; ++f) one(f);
+    } else {
+        for (int f = 0; f < cp.nf; ++f) one(f);
     }
     return bits;
 }
@@ -104,6 +113,7 @@ __device__ __forceinline__ uint32_t cull_bits(const uint32_t nf, const uint32_t 
 // RenderDataBundleStorage::push (renderer/bundle.rs:1248-1278).  Order inside a list is unspecified.
 // Must be called by every thread of the CTA.
 // ------------------------------------------------------------------------------------------------
+template <int NFT>
 __device__ __forceinline__ void compact_emit(const uint32_t vis_bits, const uint32_t node_index, const uint32_t slot,
                                              const CullParams &cp)
 {
@@ -111,7 +121,7 @@ __device__ __forceinline__ void compact_emit(const uint32_t vis_bits, const uint
     __shared__ uint32_t s_wcount[FYX_MAX_FRUSTA][kWarps];
     __shared__ uint32_t s_base[FYX_MAX_FRUSTA];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int nf = cp.nf;
+    const int nf = (NFT > 0) ? NFT : cp.nf;
 
     // any visible node in the CTA at all?  (most CTAs of a mostly-culled scene skip the atomics)
     const int any = __syncthreads_or(vis_bits != 0u);
@@ -151,7 +161,7 @@ __device__ __forceinline__ void compact_emit(const uint32_t vis_bits, const uint
 //   Graph::update_visibility_recursively          :1182-1197                      (gv = parent.gv && visibility)
 //   Graph::update_enabled_flag_recursively        :1166-1180                      (ge = parent.ge && enabled)
 //   Mesh::on_global_transform_changed / Base::world_bounding_box   scene/mesh/mod.rs:667-689, scene/base.rs:741-750
-//   (+ FUSE: should_be_rendered + visible-list emission for non-skinned nodes)
+//   (+ (NFT >= 0): should_be_rendered + visible-list emission for non-skinned nodes)
 // and the change tracking of process_node_messages (:1303-1399): a node is recomputed iff it or an
 // ancestor changed (or FYX_UPDATE_ALL).  One thread per node; parents were finished by the previous
 // launch on the same stream.
@@ -160,7 +170,7 @@ __device__ __forceinline__ void compact_emit(const uint32_t vis_bits, const uint
 // (A single cooperative launch walking all levels with grid-wide barriers was tried and rejected: the
 // persistent grid, L2-only parent loads and the barriers cost more than the launches they save —
 // C2 0.357 -> 0.416 ms, target 0.990 -> 1.051 ms per frame; profiles/README.md.)
-template <bool FUSE>
+template <int NFT>
 __device__ __forceinline__ void update_node(const NodeArrays &a, const uint32_t slot, const uint32_t update_all, const CullParams &cp,
                                             uint32_t &vis_bits, uint32_t &gi)
 {
@@ -207,33 +217,34 @@ __device__ __forceinline__ void update_node(const NodeArrays &a, const uint32_t 
         st_stream(a.wa[0] + slot, wx);
         st_stream(a.wa[1] + slot, wy);
         st_stream(a.wa[2] + slot, wz);
-    } else if (FUSE) {
+    } else if ((NFT >= 0)) {
         wx = ld_stream(a.wa[0] + slot);
         wy = ld_stream(a.wa[1] + slot);
         wz = ld_stream(a.wa[2] + slot);
     }
-    if (FUSE && !(nf & F_SKINNED)) {
-        vis_bits = cull_bits(nf, a.mask[slot], wx, wy, wz, cp);
+    if ((NFT >= 0) && !(nf & F_SKINNED)) {
+        vis_bits = cull_bits<(NFT > 0 ? NFT : 0)>(nf, a.mask[slot], wx, wy, wz, cp);
         if (vis_bits) gi = a.gidx[slot];
     }
 }
 
-template <bool FUSE>
+template <int NFT>
 __global__ void __launch_bounds__(kBlock) k_update_level(const NodeArrays a, const uint32_t lo, const uint32_t hi,
                                                          const uint32_t update_all, const CullParams cp)
 {
     pdl_trigger();
     const uint32_t slot = lo + blockIdx.x * kBlock + threadIdx.x;
     uint32_t vis_bits = 0u, gi = 0u;
-    if (slot < hi) update_node<FUSE>(a, slot, update_all, cp, vis_bits, gi);
+    if (slot < hi) update_node<NFT>(a, slot, update_all, cp, vis_bits, gi);
     else pdl_wait();
-    if (FUSE) compact_emit(vis_bits, gi, slot, cp);
+    if (NFT >= 0) compact_emit<(NFT > 0 ? NFT : 0)>(vis_bits, gi, slot, cp);
 }
 
 // ------------------------------------------------------------------------------------------------
 // Stand-alone cull over all slots (static scene / extra passes: every shadow pass re-runs the cull
 // with its own frustum, renderer/shadow/*.rs).  32 B read per node + 4 B per visible entry.
 // ------------------------------------------------------------------------------------------------
+template <int NFT>
 __global__ void __launch_bounds__(kBlock) k_cull(const NodeArrays a, const CullParams cp)
 {
     const uint32_t slot = blockIdx.x * kBlock + threadIdx.x;
@@ -244,17 +255,17 @@ __global__ void __launch_bounds__(kBlock) k_cull(const NodeArrays a, const CullP
         const float2 wx = ld_stream(a.wa[0] + slot);
         const float2 wy = ld_stream(a.wa[1] + slot);
         const float2 wz = ld_stream(a.wa[2] + slot);
-        vis_bits = cull_bits(nf, mask, wx, wy, wz, cp);
+        vis_bits = cull_bits<NFT>(nf, mask, wx, wy, wz, cp);
         if (vis_bits) gi = a.gidx[slot];
     }
-    compact_emit(vis_bits, gi, slot, cp);
+    compact_emit<NFT>(vis_bits, gi, slot, cp);
 }
 
 // ------------------------------------------------------------------------------------------------
 // Skinned-mesh world AABB: the "special case for skinned meshes" of Mesh::on_global_transform_changed
 // (scene/mesh/mod.rs:673-684): world_aabb.add_point(bone.global_position()) for every bone of every
 // surface, strict </> updates in bone order (aabb.rs:86-106).  Runs after all levels (bones may be deeper than the mesh node);
-// only meshes in a changed sub-tree are refreshed, as in the reference.  With FUSE the skinned
+// only meshes in a changed sub-tree are refreshed, as in the reference.  With (NFT >= 0) the skinned
 // nodes are also culled here (they were skipped by the level kernels).
 // ------------------------------------------------------------------------------------------------
 // One WARP per skinned mesh: lanes take the bones round-robin, then the per-lane candidates are merged with
@@ -271,7 +282,7 @@ __device__ __forceinline__ void fold_max(float &v, uint32_t &k, const float ov, 
 }
 
 // one warp = one skinned mesh (i); lane 0 returns the cull result
-template <bool FUSE>
+template <int NFT>
 __device__ __forceinline__ void fold_mesh(const NodeArrays &a, const FoldArrays &fa, const uint32_t i, const uint32_t lane,
                                           const CullParams &cp, uint32_t &vis_bits, uint32_t &gi)
 {
@@ -323,21 +334,21 @@ __device__ __forceinline__ void fold_mesh(const NodeArrays &a, const FoldArrays 
             a.wa[2][slot] = wz;
         }
     }
-    if (FUSE && lane == 0) {
-        vis_bits = cull_bits(nf, a.mask[slot], wx, wy, wz, cp);
+    if ((NFT >= 0) && lane == 0) {
+        vis_bits = cull_bits<(NFT > 0 ? NFT : 0)>(nf, a.mask[slot], wx, wy, wz, cp);
         if (vis_bits) gi = a.gidx[slot];
     }
 }
 
-template <bool FUSE>
+template <int NFT>
 __global__ void __launch_bounds__(kBlock) k_fold_bones(const NodeArrays a, const FoldArrays fa, const CullParams cp)
 {
     pdl_trigger();
     pdl_wait();
     const uint32_t i = (blockIdx.x * kBlock + threadIdx.x) >> 5; // mesh = warp
     uint32_t vis_bits = 0u, gi = 0u;
-    if (i < fa.n) fold_mesh<FUSE>(a, fa, i, threadIdx.x & 31u, cp, vis_bits, gi);
-    if (FUSE) compact_emit(vis_bits, gi, vis_bits ? fa.node_slot[i] : 0u, cp);
+    if (i < fa.n) fold_mesh<NFT>(a, fa, i, threadIdx.x & 31u, cp, vis_bits, gi);
+    if (NFT >= 0) compact_emit<(NFT > 0 ? NFT : 0)>(vis_bits, gi, vis_bits ? fa.node_slot[i] : 0u, cp);
 }
 
 // positions of the "late" bones (see FoldArrays) as stored before the update starts
@@ -794,18 +805,35 @@ void launch_update_level(cudaStream_t s, const NodeArrays &a, uint32_t lo, uint3
 {
     if (hi <= lo) return;
     if (cull) {
-        launch_pdl(k_update_level<true>, grid_for(hi - lo), kBlock, 0, s, a, lo, hi, update_all ? 1u : 0u, *cull);
+        const unsigned g = grid_for(hi - lo);
+        const uint32_t ua = update_all ? 1u : 0u;
+        switch (cull->nf) { // the usual frustum counts get an unrolled cull: camera, CSM cascades, cube faces
+        case 1: launch_pdl(k_update_level<1>, g, kBlock, 0, s, a, lo, hi, ua, *cull); break;
+        case 2: launch_pdl(k_update_level<2>, g, kBlock, 0, s, a, lo, hi, ua, *cull); break;
+        case 3: launch_pdl(k_update_level<3>, g, kBlock, 0, s, a, lo, hi, ua, *cull); break;
+        case 4: launch_pdl(k_update_level<4>, g, kBlock, 0, s, a, lo, hi, ua, *cull); break;
+        case 6: launch_pdl(k_update_level<6>, g, kBlock, 0, s, a, lo, hi, ua, *cull); break;
+        default: launch_pdl(k_update_level<0>, g, kBlock, 0, s, a, lo, hi, ua, *cull); break;
+        }
     } else {
         CullParams none;
         none.nf = 0;
-        launch_pdl(k_update_level<false>, grid_for(hi - lo), kBlock, 0, s, a, lo, hi, update_all ? 1u : 0u, none);
+        launch_pdl(k_update_level<-1>, grid_for(hi - lo), kBlock, 0, s, a, lo, hi, update_all ? 1u : 0u, none);
     }
 }
 
 void launch_cull(cudaStream_t s, const NodeArrays &a, const CullParams &cp)
 {
     if (!a.cap) return;
-    k_cull<<<grid_for(a.cap), kBlock, 0, s>>>(a, cp);
+    const unsigned g = grid_for(a.cap);
+    switch (cp.nf) {
+    case 1: k_cull<1><<<g, kBlock, 0, s>>>(a, cp); break;
+    case 2: k_cull<2><<<g, kBlock, 0, s>>>(a, cp); break;
+    case 3: k_cull<3><<<g, kBlock, 0, s>>>(a, cp); break;
+    case 4: k_cull<4><<<g, kBlock, 0, s>>>(a, cp); break;
+    case 6: k_cull<6><<<g, kBlock, 0, s>>>(a, cp); break;
+    default: k_cull<0><<<g, kBlock, 0, s>>>(a, cp); break;
+    }
 }
 
 void launch_fold_bones(cudaStream_t s, const NodeArrays &a, const FoldArrays &fa, const CullParams *cull)
@@ -813,11 +841,15 @@ void launch_fold_bones(cudaStream_t s, const NodeArrays &a, const FoldArrays &fa
     if (!fa.n) return;
     const unsigned grid = grid_for((uint64_t)fa.n * 32); // one warp per skinned mesh
     if (cull) {
-        launch_pdl(k_fold_bones<true>, grid, kBlock, 0, s, a, fa, *cull);
+        switch (cull->nf) {
+        case 1: launch_pdl(k_fold_bones<1>, grid, kBlock, 0, s, a, fa, *cull); break;
+        case 6: launch_pdl(k_fold_bones<6>, grid, kBlock, 0, s, a, fa, *cull); break;
+        default: launch_pdl(k_fold_bones<0>, grid, kBlock, 0, s, a, fa, *cull); break;
+        }
     } else {
         CullParams none;
         none.nf = 0;
-        launch_pdl(k_fold_bones<false>, grid, kBlock, 0, s, a, fa, none);
+        launch_pdl(k_fold_bones<-1>, grid, kBlock, 0, s, a, fa, none);
     }
 }
 

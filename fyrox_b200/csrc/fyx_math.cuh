@@ -96,12 +96,15 @@ struct FrustumDev {
     float2 pn[3][4]; // planes (2q, 2q+1) as pairs: [q][0..2] = normal x,y,z pairs, [q][3] = d pair
     uint32_t cam_mask;
     uint32_t pass_flags;
-    uint32_t psel;   // bit (3*p + axis): the plane-p normal component on that axis is negative
+    // vsel[q][axis][k]: byte-permute selector that picks, for plane 2q+k, the box bound whose product with the plane
+    // normal's component on that axis is the larger one: 0x3210 = the minimum (component < 0), 0x7654 = the maximum.
+    // One PRMT with a constant-bank operand per selected value (bit tests + predicate + SEL cost four).
+    uint32_t vsel[3][3][2];
     uint32_t n_ax;   // n_ax >> (8*axis) & 0xFF: number of distinct corner coordinates on that axis
     // distinct corner coordinates per axis (unused entries are NaN: they compare false) and, for each, the
     // mask of the corners that have it
     float4 ax_val[3][2];
-    uint32_t ax_mask[3][2]; // 8 x 8-bit corner masks per axis, packed little-endian
+    uint32_t ax_mask[3][8]; // per distinct coordinate: the 8-bit mask of the frustum corners that have it
 };
 
 // Frustum::is_intersects_aabb (fyrox-math/src/frustum.rs:222-245) on (min,max) pairs per axis.
@@ -120,34 +123,49 @@ __device__ __forceinline__ bool aabb_is_tame(const float2 x, const float2 y, con
            (fabsf(z.y) <= kBig) & (x.x <= x.y) & (y.x <= y.y) & (z.x <= z.y);
 }
 
+// prmt.b32 without __byte_perm's selector masking (the selectors are 0x3210 / 0x7654 by construction)
+__device__ __forceinline__ float pick(const uint32_t lo, const uint32_t hi, const uint32_t sel)
+{
+    uint32_t d;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(lo), "r"(hi), "r"(sel));
+    return __uint_as_float(d);
+}
+
 __device__ __forceinline__ bool frustum_intersects_aabb(const FrustumDev &f, const float2 x, const float2 y,
                                                         const float2 z, const PackedConsts &kc, const bool tame)
 {
     bool cloud = true;
     if (tame) {
         // n*p is monotone in p (rounding is monotone), so max(fl(n*min), fl(n*max)) is fl(n*max) for n >= 0
-        // and fl(n*min) for n < 0: pick the operand first (psel, built on the host) and multiply once.
+        // and fl(n*min) for n < 0: pick the operand first (vsel, built on the host) and multiply once.
         // For n == ±0 both products are zeros; either choice gives the same booleans.
         // Two planes per packed instruction: s = ((nx*vx + ny*vy) + nz*vz) + d element-wise.
-        const uint32_t sel = f.psel;
+        const uint32_t xl = __float_as_uint(x.x), xh = __float_as_uint(x.y), yl = __float_as_uint(y.x), yh = __float_as_uint(y.y),
+                       zl = __float_as_uint(z.x), zh = __float_as_uint(z.y);
 #pragma unroll
         for (int q = 0; q < 3; ++q) {
-            const int b0 = 6 * q, b1 = 6 * q + 3;
-            const float2 vx = make_float2((sel >> (b0 + 0)) & 1u ? x.x : x.y, (sel >> (b1 + 0)) & 1u ? x.x : x.y);
-            const float2 vy = make_float2((sel >> (b0 + 1)) & 1u ? y.x : y.y, (sel >> (b1 + 1)) & 1u ? y.x : y.y);
-            const float2 vz = make_float2((sel >> (b0 + 2)) & 1u ? z.x : z.y, (sel >> (b1 + 2)) & 1u ? z.x : z.y);
+            const float2 vx = make_float2(pick(xl, xh, f.vsel[q][0][0]), pick(xl, xh, f.vsel[q][0][1]));
+            const float2 vy = make_float2(pick(yl, yh, f.vsel[q][1][0]), pick(yl, yh, f.vsel[q][1][1]));
+            const float2 vz = make_float2(pick(zl, zh, f.vsel[q][2][0]), pick(zl, zh, f.vsel[q][2][1]));
             const float2 s = add2(add2(add2(mul2(f.pn[q][0], vx, kc), mul2(f.pn[q][1], vy, kc), kc), mul2(f.pn[q][2], vz, kc), kc), f.pn[q][3], kc);
             cloud &= !(s.x <= 0.0f) & !(s.y <= 0.0f);
+            // siblings sit in adjacent slots, so a warp's boxes are usually cut off by the same plane: once every
+            // lane here is rejected the remaining planes cannot change anything (a lane's own result never depends
+            // on the vote: it only ever skips tests whose outcome is already fixed)
+            if (q < 2 && !__any_sync(__activemask(), cloud)) break;
         }
     } else {
-        // literal restatement of the 8-corner loop (NaN-correct)
+        // literal restatement of the 8-corner loop (NaN-correct).  Never taken in practice: kept rolled so that the
+        // per-frustum code of the unrolled kernels stays small.
         const float xs[2] = {x.x, x.y}, ys[2] = {y.x, y.y}, zs[2] = {z.x, z.y};
+#pragma unroll 1
         for (int p = 0; p < 6; ++p) {
             const float4 pl = f.plane[p];
             int back = 0;
+#pragma unroll 1
             for (int c = 0; c < 8; ++c) {
-                const float s = FYX_ADD(FYX_ADD(FYX_ADD(FYX_MUL(pl.x, xs[c & 1]), FYX_MUL(pl.y, ys[(c >> 1) & 1])),
-                                                FYX_MUL(pl.z, zs[(c >> 2) & 1])), pl.w);
+                const float s = FYX_ADD(FYX_ADD(FYX_ADD(FYX_MUL(pl.x, (c & 1) ? xs[1] : xs[0]), FYX_MUL(pl.y, (c & 2) ? ys[1] : ys[0])),
+                                                FYX_MUL(pl.z, (c & 4) ? zs[1] : zs[0])), pl.w);
                 back += (s <= 0.0f) ? 1 : 0;
             }
             if (back >= 8) cloud = false;
@@ -165,19 +183,17 @@ __device__ __forceinline__ bool frustum_intersects_aabb(const FrustumDev &f, con
     for (int a = 0; a < 3; ++a) {
         const float lo = box[a].x, hi = box[a].y;
         const float4 v0 = f.ax_val[a][0];
-        const uint32_t m0 = f.ax_mask[a][0];
         uint32_t m = 0u;
-        m |= ((v0.x >= lo) & (v0.x <= hi)) ? (m0 & 0xFFu) : 0u;
-        m |= ((v0.y >= lo) & (v0.y <= hi)) ? ((m0 >> 8) & 0xFFu) : 0u;
-        m |= ((v0.z >= lo) & (v0.z <= hi)) ? ((m0 >> 16) & 0xFFu) : 0u;
-        m |= ((v0.w >= lo) & (v0.w <= hi)) ? (m0 >> 24) : 0u;
+        m |= ((v0.x >= lo) & (v0.x <= hi)) ? f.ax_mask[a][0] : 0u;
+        m |= ((v0.y >= lo) & (v0.y <= hi)) ? f.ax_mask[a][1] : 0u;
+        m |= ((v0.z >= lo) & (v0.z <= hi)) ? f.ax_mask[a][2] : 0u;
+        m |= ((v0.w >= lo) & (v0.w <= hi)) ? f.ax_mask[a][3] : 0u;
         if (((f.n_ax >> (8 * a)) & 0xFFu) > 4u) { // more than four distinct coordinates on this axis (uniform branch)
             const float4 v1 = f.ax_val[a][1];
-            const uint32_t m1 = f.ax_mask[a][1];
-            m |= ((v1.x >= lo) & (v1.x <= hi)) ? (m1 & 0xFFu) : 0u;
-            m |= ((v1.y >= lo) & (v1.y <= hi)) ? ((m1 >> 8) & 0xFFu) : 0u;
-            m |= ((v1.z >= lo) & (v1.z <= hi)) ? ((m1 >> 16) & 0xFFu) : 0u;
-            m |= ((v1.w >= lo) & (v1.w <= hi)) ? (m1 >> 24) : 0u;
+            m |= ((v1.x >= lo) & (v1.x <= hi)) ? f.ax_mask[a][4] : 0u;
+            m |= ((v1.y >= lo) & (v1.y <= hi)) ? f.ax_mask[a][5] : 0u;
+            m |= ((v1.z >= lo) & (v1.z <= hi)) ? f.ax_mask[a][6] : 0u;
+            m |= ((v1.w >= lo) & (v1.w <= hi)) ? f.ax_mask[a][7] : 0u;
         }
         alive &= m;
         if (!alive) return false;
