@@ -35,6 +35,7 @@ NODE_FRUSTUM_CULLING = 1 << 2
 NODE_CAST_SHADOWS = 1 << 3
 NODE_ALIVE = 1 << 4
 NODE_RENDERABLE = 1 << 5
+NODE_LIGHT = 1 << 6
 NODE_GLOBAL_VISIBILITY = 1 << 8
 NODE_GLOBAL_ENABLED = 1 << 9
 NODE_REACHABLE = 1 << 10
@@ -181,6 +182,8 @@ SYMBOLS = {
     "fyx_update_and_cull": (C.c_int32, [ctx_p, C.c_uint32, C.c_uint32, C.POINTER(fyx_frustum), C.c_void_p, C.c_void_p]),
     "fyx_get_visible": (C.c_int32, [ctx_p, C.c_uint32, C.POINTER(u32p), u32p]),
     "fyx_get_visible_device": (C.c_int32, [ctx_p, C.c_uint32, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]),
+    "fyx_cull_lights": (C.c_int32, [ctx_p]),
+    "fyx_get_visible_lights": (C.c_int32, [ctx_p, C.c_uint32, C.POINTER(u32p), u32p]),
     "fyx_build_palettes": (C.c_int32, [ctx_p]),
     "fyx_skin": (C.c_int32, [ctx_p]),
     "fyx_render_prep": (C.c_int32, [ctx_p, C.POINTER(fyx_frame_desc)]),

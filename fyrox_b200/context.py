@@ -277,6 +277,19 @@ class Context:
         self._chk(self._lib.fyx_get_visible_device(self._h, frustum, C.byref(d_idx), C.byref(d_cnt)))
         return d_idx.value, d_cnt.value
 
+    # ---- N4 (light list) ----
+    def cull_lights(self):
+        """Light sources seen by every frustum of the most recent cull (renderer/bundle.rs:926-974)."""
+        self._chk(self._lib.fyx_cull_lights(self._h))
+
+    def get_visible_lights(self, frustum: int = 0) -> np.ndarray:
+        p = L.u32p()
+        n = C.c_uint32()
+        self._chk(self._lib.fyx_get_visible_lights(self._h, frustum, C.byref(p), C.byref(n)))
+        if n.value == 0:
+            return np.empty(0, dtype=np.uint32)
+        return np.ctypeslib.as_array(p, shape=(n.value,)).copy()
+
     # ---- N2: animation sampling on the device ----
     KEY_DTYPE = np.dtype([("location", "<f4"), ("value", "<f4"), ("kind", "<u4"), ("left_tangent", "<f4"), ("right_tangent", "<f4")])
     TRACK_DTYPE = np.dtype([("target_node", "<u4"), ("binding", "<u4"), ("value_kind", "<u4"), ("enabled", "<u4"), ("n_curves", "<u4"),

@@ -155,6 +155,13 @@ struct fyx_ctx {
     DevBuf b_anim_keys, b_anim_tracks, b_anim_state, b_anim_hints, b_anim_values, b_anim_ok, b_anim_bk, b_anim_node_slot,
         b_anim_node_begin, b_anim_node_tracks;
 
+    // N4 light lists (fyx_drawprep.inl)
+    DevBuf b_light[FYX_MAX_FRUSTA], b_light_ptrs, b_light_counts;
+    uint32_t *h_light_counts = nullptr; // pinned
+    std::vector<uint32_t> h_light[FYX_MAX_FRUSTA];
+    uint32_t light_nf = 0;
+    bool lights_valid = false;
+
     // N3 draw-prep (fyx_drawprep.inl)
     bool instances_enabled = false, have_bundles = false, rank_on_device = false;
     uint32_t n_bundle_ids = 1;
@@ -383,6 +390,7 @@ int32_t prepare_cull(fyx_ctx *c, uint32_t nf, const fyx_frustum *fr, const uint3
     }
     V.have_slots = c->instances_enabled;
     for (auto &o : c->inst) o.valid = false;
+    c->lights_valid = false;
     CU(cudaMemsetAsync(V.d_counts, 0, sizeof(uint32_t) * kCountStride * FYX_MAX_FRUSTA, c->stream));
     V.nf = nf;
     V.counts_on_host = V.lists_on_host = false;

@@ -32,6 +32,11 @@ void inst_free(fyx_ctx *c)
     }
     for (auto &V : c->vs)
         for (auto &b : V.b_vis_slot) dev_free(b);
+    for (auto &b : c->b_light) dev_free(b);
+    dev_free(c->b_light_ptrs);
+    dev_free(c->b_light_counts);
+    if (c->h_light_counts) cudaFreeHost(c->h_light_counts);
+    c->h_light_counts = nullptr;
     dev_free(c->b_bundle);
     dev_free(c->b_rank_slot);
     dev_free(c->b_inst_hist);
@@ -194,5 +199,54 @@ extern "C" int32_t fyx_get_instances(fyx_ctx *c, uint32_t f, fyx_instances *out)
     out->sort_index = static_cast<const uint64_t *>(o.h[1]);
     out->matrices = static_cast<const float *>(o.h[2]);
     out->bundles = static_cast<const fyx_bundle *>(o.h[3]);
+    return FYX_OK;
+}
+
+// ---- N4 (light list): renderer/bundle.rs:926-974 --------------------------------------------------------------------
+extern "C" int32_t fyx_cull_lights(fyx_ctx *c)
+{
+    if (!c) return FYX_ERR_INVALID_ARGUMENT;
+    if (!c->have_topology) return fail(c, FYX_ERR_STATE, "fyx_set_topology has not been called");
+    const uint32_t nf = (uint32_t)c->cp.nf;
+    if (!nf) return fail(c, FYX_ERR_STATE, "no cull has been made yet: the light lists use its frusta");
+    if (c->vs[c->cur].pending) return fail(c, FYX_ERR_STATE, "the frame is still in flight: call fyx_frame_wait first");
+    CU(cudaSetDevice(c->device));
+    int32_t rc;
+    uint32_t *ptrs[FYX_MAX_FRUSTA] = {};
+    for (uint32_t f = 0; f < nf; ++f) {
+        if ((rc = dev_ensure(c, c->b_light[f], std::max<size_t>(c->n_slots, 1) * 4))) return rc;
+        ptrs[f] = c->b_light[f].as<uint32_t>();
+    }
+    if ((rc = dev_ensure(c, c->b_light_ptrs, sizeof ptrs))) return rc;
+    if ((rc = dev_ensure(c, c->b_light_counts, sizeof(uint32_t) * kCountStride * FYX_MAX_FRUSTA))) return rc;
+    if (!c->h_light_counts) CU(cudaHostAlloc(reinterpret_cast<void **>(&c->h_light_counts), sizeof(uint32_t) * FYX_MAX_FRUSTA, cudaHostAllocDefault));
+    cudaStream_t s = c->stream;
+    CU(cudaMemcpyAsync(c->b_light_ptrs.p, ptrs, sizeof ptrs, cudaMemcpyHostToDevice, s));
+    CU(cudaMemsetAsync(c->b_light_counts.p, 0, sizeof(uint32_t) * kCountStride * FYX_MAX_FRUSTA, s));
+    launch_cull_lights(s, c->a, c->cp, c->b_light_ptrs.as<uint32_t *>(), c->b_light_counts.as<uint32_t>());
+    c->launches++;
+    CU(cudaGetLastError());
+    CU(cudaMemcpy2DAsync(c->h_light_counts, sizeof(uint32_t), c->b_light_counts.p, sizeof(uint32_t) * kCountStride, sizeof(uint32_t), nf,
+                         cudaMemcpyDeviceToHost, s));
+    rc = sync_and_check(c);
+    if (rc) return rc;
+    for (uint32_t f = 0; f < nf; ++f) {
+        c->h_light[f].resize(c->h_light_counts[f]);
+        if (c->h_light_counts[f])
+            CU(cudaMemcpy(c->h_light[f].data(), c->b_light[f].p, (size_t)c->h_light_counts[f] * 4, cudaMemcpyDeviceToHost));
+        std::sort(c->h_light[f].begin(), c->h_light[f].end()); // pool order, like the reference's pair_iter
+    }
+    c->light_nf = nf;
+    c->lights_valid = true;
+    return FYX_OK;
+}
+
+extern "C" int32_t fyx_get_visible_lights(fyx_ctx *c, uint32_t f, const uint32_t **out_idx, uint32_t *out_count)
+{
+    if (!c || !out_idx || !out_count) return FYX_ERR_INVALID_ARGUMENT;
+    if (!c->lights_valid) return fail(c, FYX_ERR_STATE, "fyx_cull_lights has not been called for the last cull");
+    if (f >= c->light_nf) return fail(c, FYX_ERR_INVALID_ARGUMENT, "frustum %u was not part of the last cull (%u frusta)", f, c->light_nf);
+    *out_idx = c->h_light[f].data();
+    *out_count = (uint32_t)c->h_light[f].size();
     return FYX_OK;
 }

@@ -139,6 +139,7 @@ void launch_pack_instances(cudaStream_t s, const NodeArrays &a, const InstParams
 void launch_update_level(cudaStream_t s, const NodeArrays &a, uint32_t lo, uint32_t hi, bool update_all,
                          const CullParams *cull /* nullptr = no fused cull */);
 void launch_cull(cudaStream_t s, const NodeArrays &a, const CullParams &cp);
+void launch_cull_lights(cudaStream_t s, const NodeArrays &a, const CullParams &cp, uint32_t *const *d_out_ptrs, uint32_t *counts);
 void launch_fold_bones(cudaStream_t s, const NodeArrays &a, const FoldArrays &fa, const CullParams *cull);
 void launch_snapshot_bones(cudaStream_t s, const NodeArrays &a, uint32_t n_late, const uint32_t *late_slot, float4 *stale_pos);
 void launch_palette(cudaStream_t s, const NodeArrays &a, const SkinArrays &sk);

@@ -262,6 +262,28 @@ __global__ void __launch_bounds__(kBlock) k_cull(const NodeArrays a, const CullP
 }
 
 // ------------------------------------------------------------------------------------------------
+// Light list (N4): the collect_lights loop of RenderDataBundleStorage::from_graph (renderer/bundle.rs:926-974) — for every
+// frustum the light nodes whose world box it intersects and that are globally visible and enabled.  Lights are few:
+// one pass over the flag column (4 B/node), one atomic per visible (light, frustum).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kBlock) k_cull_lights(const NodeArrays a, const CullParams cp, uint32_t *const *out, uint32_t *counts)
+{
+    const uint32_t slot = blockIdx.x * kBlock + threadIdx.x;
+    if (slot >= a.cap) return;
+    const uint32_t nf = a.flags[slot];
+    constexpr uint32_t need = FYX_NODE_ALIVE | FYX_NODE_LIGHT | FYX_NODE_GLOBAL_VISIBILITY | FYX_NODE_GLOBAL_ENABLED;
+    if ((nf & need) != need) return;
+    const float2 wx = a.wa[0][slot], wy = a.wa[1][slot], wz = a.wa[2][slot];
+    PackedConsts kc;
+    kc.one = make_float2(cp.one, cp.one);
+    kc.negzero = make_float2(cp.negzero, cp.negzero);
+    const bool tame = aabb_is_tame(wx, wy, wz);
+    const uint32_t gi = a.gidx[slot];
+    for (int f = 0; f < cp.nf; ++f)
+        if (frustum_intersects_aabb(cp.f[f], wx, wy, wz, kc, tame)) out[f][atomicAdd(counts + f * kCountStride, 1u)] = gi;
+}
+
+// ------------------------------------------------------------------------------------------------
 // Skinned-mesh world AABB: the "special case for skinned meshes" of Mesh::on_global_transform_changed
 // (scene/mesh/mod.rs:673-684): world_aabb.add_point(bone.global_position()) for every bone of every
 // surface, strict </> updates in bone order (aabb.rs:86-106).  Runs after all levels (bones may be deeper than the mesh node);
@@ -820,6 +842,12 @@ void launch_update_level(cudaStream_t s, const NodeArrays &a, uint32_t lo, uint3
         none.nf = 0;
         launch_pdl(k_update_level<-1>, grid_for(hi - lo), kBlock, 0, s, a, lo, hi, update_all ? 1u : 0u, none);
     }
+}
+
+void launch_cull_lights(cudaStream_t s, const NodeArrays &a, const CullParams &cp, uint32_t *const *d_out_ptrs, uint32_t *counts)
+{
+    if (!a.cap) return;
+    k_cull_lights<<<grid_for(a.cap), kBlock, 0, s>>>(a, cp, d_out_ptrs, counts);
 }
 
 void launch_cull(cudaStream_t s, const NodeArrays &a, const CullParams &cp)

@@ -58,7 +58,8 @@ typedef enum fyx_status {
 #define FYX_NODE_CAST_SHADOWS    (1u << 3)
 #define FYX_NODE_ALIVE           (1u << 4)
 #define FYX_NODE_RENDERABLE      (1u << 5)
-#define FYX_NODE_INPUT_MASK      0x3Fu
+#define FYX_NODE_LIGHT           (1u << 6)  /* the node is a BaseLight (point / spot / directional): fyx_cull_lights */
+#define FYX_NODE_INPUT_MASK      0x7Fu
 /* Computed bits, readable through fyx_get_global_flags (Base::global_visibility / is_globally_enabled,
  * scene/base.rs:751-770) */
 #define FYX_NODE_GLOBAL_VISIBILITY (1u << 8)
@@ -215,6 +216,14 @@ int32_t fyx_update_and_cull(fyx_ctx *ctx, uint32_t update_flags, uint32_t n_frus
 int32_t fyx_get_visible(fyx_ctx *ctx, uint32_t frustum, const uint32_t **out_idx, uint32_t *out_count);
 /* ... or device-resident (for a GPU consumer / a collective); *d_count points at one device u32. */
 int32_t fyx_get_visible_device(fyx_ctx *ctx, uint32_t frustum, const uint32_t **d_idx, const uint32_t **d_count);
+
+/* N4 (light list) — the `collect_lights` part of RenderDataBundleStorage::from_graph (renderer/bundle.rs:926-974): for
+ * every frustum of the most recent cull, the FYX_NODE_LIGHT nodes whose world bounding box the frustum intersects and
+ * that are globally visible and enabled (no reachability / render-mask / frustum_culling-flag test, as in the
+ * reference).  Lists come back in ascending node index = the reference's pool order.  Lights in sub-trees detached from
+ * the root are outside the contract: the reference never updates such sub-trees, this library updates every tree. */
+int32_t fyx_cull_lights(fyx_ctx *ctx);
+int32_t fyx_get_visible_lights(fyx_ctx *ctx, uint32_t frustum, const uint32_t **out_idx, uint32_t *out_count);
 
 /* SurfaceInstanceData::bone_matrices for every skinned surface (scene/mesh/mod.rs:781-793):
  * P[k] = bone_k.global_transform * bone_k.inv_bind_pose_transform; dead / FYX_NONE bone ⇒ identity. */

@@ -462,7 +462,7 @@ typedef struct orc_node {
     int kind;
     /* Base (scene/base.rs:389-483) */
     float local_matrix[16]; /* Transform::matrix() cache */
-    int visibility, enabled, frustum_culling, cast_shadows;
+    int visibility, enabled, frustum_culling, cast_shadows, is_light;
     uint32_t render_mask;
     uint32_t parent;
     uint32_t *children;
@@ -654,6 +654,7 @@ orc_graph *orc_graph_build(uint32_t capacity, const uint32_t *parent, const uint
         n->enabled = !!(f & ORC_FLAG_ENABLED);
         n->frustum_culling = !!(f & ORC_FLAG_FRUSTUM_CULLING);
         n->cast_shadows = !!(f & ORC_FLAG_CAST_SHADOWS);
+        n->is_light = !!(f & ORC_FLAG_LIGHT);
         if (render_mask) n->render_mask = render_mask[i];
         if (local_m16) memcpy(n->local_matrix, local_m16 + 16 * (size_t)i, 64);
         if (local_aabb6 && n->kind == ORC_KIND_MESH) {
@@ -1042,6 +1043,25 @@ uint32_t orc_mesh_skin(const orc_graph *g, uint32_t mesh, uint32_t surface, floa
 }
 
 int orc_node_is_alive(const orc_graph *g, uint32_t n) { return node_at(g, n) != NULL; }
+
+/* N4 (light list) — the `options.collect_lights` part of RenderDataBundleStorage::from_graph (renderer/bundle.rs:926-974):
+ * every alive node, in pool order, that is a BaseLight, whose world bounding box the observer's frustum intersects and
+ * that is globally visible and enabled.  No reachability, LOD, render-mask or frustum_culling-flag test here. */
+size_t orc_collect_lights(const orc_graph *g, const orc_frustum *f, uint32_t *out, size_t cap)
+{
+    size_t c = 0;
+    for (uint32_t i = 0; i < g->capacity; ++i) {
+        const orc_node *n = node_at(g, i);
+        if (!n || !n->is_light) continue;
+        orc_aabb w;
+        orc_node_world_bounding_box(g, i, &w);
+        if (orc_frustum_is_intersects_aabb(f, &w) && n->global_visibility && n->global_enabled) {
+            if (c < cap) out[c] = i;
+            c++;
+        }
+    }
+    return c;
+}
 
 /* N3 — what Mesh::collect_render_data pushes for a node with ONE surface (scene/mesh/mod.rs:700 sort index of
  * global_position(); :731-737 world = identity if the surface is skinned, else global_transform()) and what

@@ -123,6 +123,7 @@ orc_graph *orc_graph_build(uint32_t capacity, const uint32_t *parent, const uint
 #define ORC_FLAG_CAST_SHADOWS    (1u << 3)
 #define ORC_FLAG_ALIVE           (1u << 4)
 #define ORC_FLAG_RENDERABLE      (1u << 5)   /* node kind emits render data (Mesh) */
+#define ORC_FLAG_LIGHT           (1u << 6)   /* node is a BaseLight (point / spot / directional) */
 
 /* property setters; the three tracked ones push messages like TrackedProperty::deref_mut (base.rs:343-352) */
 void orc_node_set_local_matrix(orc_graph *g, uint32_t n, const float m16[16]);
@@ -166,6 +167,7 @@ size_t orc_from_graph(const orc_graph *g, const orc_frustum *f, uint32_t render_
  * standard.shader:192-195 in the same op order) */
 uint32_t orc_mesh_bone_matrices(const orc_graph *g, uint32_t mesh, uint32_t surface, float *out_m16);
 uint32_t orc_mesh_skin(const orc_graph *g, uint32_t mesh, uint32_t surface, float *out_pos3, float *out_nrm3);
+size_t   orc_collect_lights(const orc_graph *g, const orc_frustum *f, uint32_t *out_idx, size_t cap);   /* N4: renderer/bundle.rs:926-974 */
 uint64_t orc_node_instance(const orc_graph *g, uint32_t node, const float view[16], const float vp[16],
                            float world[16], float wvp[16]);   /* N3: mesh/mod.rs:700,731-737 + bundle.rs:483-487 */
 void     orc_mesh_accurate_world_bounding_box(const orc_graph *g, uint32_t mesh, orc_aabb *out);

@@ -177,6 +177,7 @@ def lib() -> C.CDLL:
         "orc_mt_skin_surface": (None, [vp, C.c_uint32, f32p, f32p]),
         "orc_mt_skin_all": (None, [vp]),
         "orc_mt_get": (None, [vp, C.c_uint32, f32p, C.POINTER(Aabb), C.POINTER(C.c_uint32)]),
+        "orc_collect_lights": (C.c_size_t, [vp, C.POINTER(Frustum), vp, C.c_size_t]),
         "orc_node_instance": (C.c_uint64, [vp, C.c_uint32, f32p, f32p, f32p, f32p]),
         "orc_mesh_accurate_world_bounding_box": (None, [vp, C.c_uint32, C.POINTER(Aabb)]),
         "orc_skin_vertices": (None, [f32p, C.c_uint32, vp, C.POINTER(VertexLayout), f32p, f32p]),
@@ -374,6 +375,11 @@ class Graph:
         cap = self.capacity
         out = np.empty(max(cap, 1), dtype=np.uint32)
         n = self.L.orc_from_graph(self.h, C.byref(frustum) if frustum is not None else None, render_mask, int(shadow_pass), out.ctypes.data_as(C.c_void_p), cap)
+        return out[:n].copy()
+
+    def collect_lights(self, frustum: Frustum):
+        out = np.empty(max(self.capacity, 1), dtype=np.uint32)
+        n = self.L.orc_collect_lights(self.h, C.byref(frustum), out.ctypes.data_as(C.c_void_p), self.capacity)
         return out[:n].copy()
 
     def instance(self, node, view_m16, vp_m16):

@@ -141,3 +141,46 @@ def test_instances_edge_cases(ctx):
     # ids must be dense
     with pytest.raises(fb.FyxError):
         ctx.set_bundle_ids(np.array([1 << 30], np.uint32), [1])
+
+
+def test_light_lists_match_oracle(ctx):
+    """N4 (light list): the collect_lights loop of from_graph (renderer/bundle.rs:926-974) — lights are tested against the
+    frustum by their world box and by global visibility / enabled only; lights with frustum culling switched off and
+    lights whose render mask misses the camera's still follow exactly that rule.  (Sub-trees detached from the root are
+    left out: the reference never updates them, so a light in one is tested with whatever its last update left.)"""
+    rng = np.random.default_rng(909)
+    parent, flags, mask, local, aabb = random_graph(rng, 4000, p_orphan=0.0, p_mesh=0.5)
+    alive = (flags & fb.NODE_ALIVE) != 0
+    pivots = alive & ((flags & fb.NODE_RENDERABLE) == 0)
+    lights = pivots & (rng.random(len(flags)) < 0.3)
+    lights[0] = False
+    flags = flags.copy()
+    flags[lights] |= fb.NODE_LIGHT
+    og = ob.Graph.build(parent, flags, mask, local, aabb)
+    og.update_hierarchical_data()
+    ctx.set_topology(parent, flags, mask, aabb)
+    ctx.set_local_matrices(local)
+    with pytest.raises(fb.FyxError):
+        ctx.cull_lights()  # no cull yet
+    obs = [observer((0, 0, 60), (0, 0, 0), zf=200.0), observer((0, 0, 0), (1, 0, 0), (0, -1, 0), 1.0, np.pi / 2, 0.01, 120.0),
+           observer((30, 10, -20), (0, 0, 0), zf=80.0)]
+    ctx.update_and_cull([o[3] for o in obs], fb.UPDATE_ALL, cam_mask=[0xFFFFFFFF, 0x0000FFFF, 0xFFFFFFFF])
+    ctx.cull_lights()
+    total = 0
+    for f, o in enumerate(obs):
+        want = og.collect_lights(o[2])
+        got = ctx.get_visible_lights(f)
+        assert np.array_equal(got, want)  # same set AND the reference's pool order
+        total += want.size
+    assert total > 30
+    # a light switched off by an ancestor's visibility disappears; flags can change at run time
+    some = np.nonzero(lights)[0][:40].astype(np.uint32)
+    newf = flags[some] & ~np.uint32(fb.NODE_ENABLED)
+    for i in some:
+        ob.lib().orc_node_set_enabled(og.h, int(i), 0)
+    og.update()
+    ctx.set_flags(newf, some)
+    ctx.update_and_cull([o[3] for o in obs], fb.UPDATE_INCREMENTAL)
+    ctx.cull_lights()
+    for f, o in enumerate(obs):
+        assert np.array_equal(ctx.get_visible_lights(f), og.collect_lights(o[2]))
