@@ -352,6 +352,8 @@ def device_animation_mode(ctx, sc, fb, frusta, n_bones, steps, timed, log):
 
 
 def run_cuda(args):
+    # NCCL writes its banner / debug lines to stdout unless told otherwise: stdout carries exactly one JSON line
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     import torch
     import torch.distributed as dist
 
@@ -433,9 +435,13 @@ def run_cuda(args):
                         allgather=(world > 1))
 
     vis_counts = [0] * len(frusta)
+    own_lists = [False]  # set while the pipelined e2e loop runs on a rank other than 0
 
     def submit_e2e(i, pipelined):
-        kw = dict(update_flags=fb.UPDATE_ALL, frusta=frusta, readback_visible=True, async_=pipelined, allgather=(world > 1))
+        # N > 1: every rank holds the gathered lists on its device; the host copy of the WHOLE lists is made once, by rank 0
+        # ("the host via one pinned copy"); the other ranks read back their own lists
+        kw = dict(update_flags=fb.UPDATE_ALL, frusta=frusta, readback_visible=True, async_=pipelined, allgather=(world > 1),
+                  readback_own=(world > 1 and rank != 0 and pipelined))
         if anim:
             pi, pm = anim[i & 1]
             kw.update(changed_idx=pi.ptr, n_changed=n_bones, **{UPLOAD_FIELD[args.upload]: pm.ptr})
@@ -443,7 +449,7 @@ def run_cuda(args):
 
     def collect_e2e():
         for f in range(len(frusta)):
-            v = ctx.get_visible_gathered(f, copy=False) if world > 1 else ctx.get_visible(f, copy=False)
+            v = ctx.get_visible_gathered(f, copy=False) if (world > 1 and (rank == 0 or not own_lists[0])) else ctx.get_visible(f, copy=False)
             vis_counts[f] = v.size
 
     def step_e2e(i):
@@ -455,6 +461,7 @@ def run_cuda(args):
         """The same K frames, two in flight (FYX_FRAME_ASYNC + fyx_frame_wait): the upload of frame i+1 and
         the read-back of frame i-1 overlap the kernels of frame i.  Every frame's inputs still travel
         host->device and every frame's visible lists device->host inside the timed region."""
+        own_lists[0] = world > 1 and rank != 0
         submit_e2e(0, True)
         for i in range(1, steps):
             submit_e2e(i, True)
@@ -462,6 +469,7 @@ def run_cuda(args):
             collect_e2e()
         ctx.frame_wait()
         collect_e2e()
+        own_lists[0] = False
 
     def timed(fn, steps, pass_index=False):
         barrier()
@@ -532,7 +540,7 @@ def run_cuda(args):
     e2e_value = units_all / (e2e_ms_per_step * 1e-3)
     sum_vis = sum(vis_counts)
     h2d = n_bones * (UPLOAD_BYTES[args.upload] + 4)  # frusta travel as kernel parameters
-    d2h = 4 * len(frusta) + 4 * sum_vis  # per rank: at N > 1 every rank reads back the whole gathered lists
+    d2h = 4 * len(frusta) + 4 * sum_vis  # rank 0: at N > 1 it reads back the whole gathered lists, the other ranks their own
 
     peak, peak_src = peaks()
     # dominant kernel: k_skin when the workload skins, else the fused update+cull level kernels

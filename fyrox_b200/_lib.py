@@ -46,6 +46,7 @@ UPDATE_ALL = 1
 PASS_SHADOW = 1
 FRAME_ASYNC = 1
 FRAME_ALLGATHER = 2
+FRAME_READBACK_OWN = 4
 
 u32p = C.POINTER(C.c_uint32)
 f32p = C.POINTER(C.c_float)

@@ -394,7 +394,7 @@ class Context:
 
     def render_prep(self, *, update_flags=L.UPDATE_INCREMENTAL, changed_m16=None, changed_trs=None, changed_rot=None, changed_idx=None, n_changed=None, frusta=(), cam_mask=None,
                     pass_flags=None, do_palettes=True, do_skin=True, readback_visible=True, async_=False, allgather=False,
-                    animate_dt=None):
+                    animate_dt=None, readback_own=False):
         """One frame (fyx_render_prep). changed_m16 / changed_idx may be numpy arrays or raw (pinned) addresses."""
         d = L.fyx_frame_desc()
         d.struct_size = C.sizeof(L.fyx_frame_desc)
@@ -432,7 +432,7 @@ class Context:
         d.do_palettes = 1 if do_palettes else 0
         d.do_skin = 1 if do_skin else 0
         d.readback_visible = 1 if readback_visible else 0
-        d.flags = (L.FRAME_ASYNC if async_ else 0) | (L.FRAME_ALLGATHER if allgather else 0)
+        d.flags = (L.FRAME_ASYNC if async_ else 0) | (L.FRAME_ALLGATHER if allgather else 0) | (L.FRAME_READBACK_OWN if readback_own else 0)
         if animate_dt is not None:
             d.do_animate = 1
             d.animate_dt = float(animate_dt)

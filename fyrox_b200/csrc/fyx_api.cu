@@ -56,6 +56,7 @@ struct VisSlot {
     uint32_t *h_gath[FYX_MAX_FRUSTA] = {};
     size_t h_gath_cap[FYX_MAX_FRUSTA] = {};
     bool gathered = false, gathered_on_host = false;
+    bool own_only = false; // FYX_FRAME_READBACK_OWN: the host copy of this frame is the rank's own lists
     cudaEvent_t ev_gather = nullptr;
     bool pending = false; // written by a pipelined (async + read-back) frame that fyx_frame_wait has not collected yet
     uint64_t frame_no = 0;
@@ -1499,6 +1500,7 @@ extern "C" int32_t fyx_render_prep(fyx_ctx *c, const fyx_frame_desc *fr)
                              cudaMemcpyDeviceToHost, c->d2h_stream));
         CU(cudaEventRecord(V.ev_counts, c->d2h_stream));
         V.pending = true;
+        V.own_only = gather && (fr->flags & FYX_FRAME_READBACK_OWN);
         V.frame_no = ++c->frame_counter;
     } else if (fr->readback_visible && fr->n_frusta && !gather) {
         rc = readback_visible(c, V, s);
@@ -1527,13 +1529,14 @@ extern "C" int32_t fyx_frame_wait(fyx_ctx *c)
     VisSlot &V = c->vs[slot];
     CU(cudaEventSynchronize(V.ev_counts));
     V.counts_on_host = true;
-    for (uint32_t f = 0; f < V.nf && !V.gathered; ++f) {
+    const bool own = !V.gathered || V.own_only;
+    for (uint32_t f = 0; f < V.nf && own; ++f) {
         const size_t n = V.h_counts[f];
         int32_t rc = host_list_ensure(c, V, f, n);
         if (rc) return rc;
         if (n) CU(cudaMemcpyAsync(V.h_vis[f], V.b_vis[f].p, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->d2h_stream));
     }
-    if (V.gathered) { // multi-GPU frame: the host wants the whole (all-gathered) lists
+    if (V.gathered && !V.own_only) { // multi-GPU frame: the host wants the whole (all-gathered) lists
         CU(cudaStreamWaitEvent(c->d2h_stream, V.ev_gather, 0));
         for (uint32_t f = 0; f < V.nf; ++f) {
             const size_t n = V.gath_count[f];
@@ -1546,7 +1549,7 @@ extern "C" int32_t fyx_frame_wait(fyx_ctx *c)
     CU(cudaStreamWaitEvent(c->d2h_stream, V.ev_done, 0)); // the error word is final once the frame's last kernel ran
     CU(cudaMemcpyAsync(c->h_err, c->d_err, sizeof(uint32_t), cudaMemcpyDeviceToHost, c->d2h_stream));
     CU(cudaStreamSynchronize(c->d2h_stream));
-    V.lists_on_host = !V.gathered;
+    V.lists_on_host = own;
     V.pending = false;
     c->readable = slot;
     return check_device_errors(c);

@@ -266,6 +266,11 @@ typedef struct fyx_frame_desc {
  * separate stream, overlapped with the palette / skinning kernels of the same frame; the frame is complete
  * when the gathered lists are (fyx_get_visible_gathered*). */
 #define FYX_FRAME_ALLGATHER (1u << 1)
+/* With FYX_FRAME_ALLGATHER on a pipelined (async + read-back) frame: bring only THIS rank's lists to the host
+ * (fyx_get_visible); the gathered lists stay device-resident (fyx_get_visible_gathered_device).  One process of the job
+ * — the one that feeds the CPU-side renderer — leaves it off and receives the whole lists through its pinned copy; the
+ * others do not multiply that PCIe traffic by the number of GPUs. */
+#define FYX_FRAME_READBACK_OWN (1u << 2)
 int32_t fyx_frame_wait(fyx_ctx *ctx);
 int32_t fyx_render_prep(fyx_ctx *ctx, const fyx_frame_desc *frame);
 

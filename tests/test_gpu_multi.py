@@ -49,20 +49,25 @@ def _worker(rank, world, port, out_dir):
     ctx.comm_init(world, rank, uid)
     frusta = camera.cube_frusta()
     out = {}
-    for mode in ("fused", "separate", "pipelined"):
+    for mode in ("fused", "separate", "pipelined", "pipelined_own"):
         if mode == "fused":
             ctx.render_prep(update_flags=fb.UPDATE_ALL, frusta=frusta, readback_visible=False, allgather=True)
         elif mode == "separate":
             ctx.update_and_cull(frusta, fb.UPDATE_ALL)
             ctx.allgather_visible()
         else:  # two frames in flight, gathered lists collected by fyx_frame_wait
+            # "pipelined_own": only rank 0 takes the whole lists to the host, the others their own (FYX_FRAME_READBACK_OWN)
+            own = mode == "pipelined_own" and rank != 0
             for k in range(3):
-                ctx.render_prep(update_flags=fb.UPDATE_ALL, frusta=frusta, readback_visible=True, allgather=True, async_=True)
+                ctx.render_prep(update_flags=fb.UPDATE_ALL, frusta=frusta, readback_visible=True, allgather=True, async_=True, readback_own=own)
                 if k:
                     ctx.frame_wait()
             ctx.frame_wait()
+            if own:
+                for f in range(len(frusta)):
+                    out[f"own_{f}"] = np.sort(ctx.get_visible(f))
         for f in range(len(frusta)):
-            out[f"{mode}_{f}"] = np.sort(ctx.get_visible_gathered(f))
+            out[f"{mode}_{f}"] = np.sort(ctx.get_visible_gathered(f))  # still complete: fetched from the device copy on demand
     np.savez(os.path.join(out_dir, f"rank{rank}.npz"), **out)
     dist.barrier()
     ctx.close()
@@ -93,7 +98,12 @@ def test_sharded_gpu_cull_and_nccl_allgather_match_the_unsharded_oracle(tmp_path
     want = [np.sort(og.from_graph(fo)) for fo in fos]
     for r in range(world):
         z = np.load(os.path.join(str(tmp_path), f"rank{r}.npz"))
-        for mode in ("fused", "separate", "pipelined"):
+        for mode in ("fused", "separate", "pipelined", "pipelined_own"):
             for f in range(len(fos)):
                 got = z[f"{mode}_{f}"]
                 assert np.array_equal(got, want[f]), f"rank {r} {mode} frustum {f}: {got.size} vs {want[f].size}"
+        if r:  # the rank's own lists = the part of the oracle's set that lives in its shard
+            shard = Scene(N_NODES, n_units=N_UNITS, verts_per_unit=VERTS, rank=r, nranks=world)
+            mine = np.unique(shard.global_index)
+            for f in range(len(fos)):
+                assert np.array_equal(z[f"own_{f}"], np.intersect1d(want[f], mine))
