@@ -352,8 +352,6 @@ def device_animation_mode(ctx, sc, fb, frusta, n_bones, steps, timed, log):
 
 
 def run_cuda(args):
-    # NCCL writes its banner / debug lines to stdout unless told otherwise: stdout carries exactly one JSON line
-    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     import torch
     import torch.distributed as dist
 
@@ -629,9 +627,18 @@ def main():
     ap.add_argument("--no-device-animation", action="store_true", help="skip the extra mode that samples the bones' animation curves on the device")
     ap.add_argument("--verbose", action="store_true")
     args = ap.parse_args()
-    if args.impl == "reference":
-        return run_reference(args)
-    return run_cuda(args)
+    # stdout carries exactly ONE JSON line: libraries that write to fd 1 (NCCL prints its version banner there when
+    # NCCL_DEBUG=VERSION) are sent to stderr for the whole run, the line goes out through the saved descriptor
+    sys.stdout.flush()
+    saved = os.dup(1)
+    os.dup2(2, 1)
+    sys.stdout = os.fdopen(saved, "w")
+    try:
+        if args.impl == "reference":
+            return run_reference(args)
+        return run_cuda(args)
+    finally:
+        sys.stdout.flush()
 
 
 if __name__ == "__main__":
