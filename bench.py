@@ -226,8 +226,20 @@ class CpuMultiCore:
         return time.perf_counter() - t0
 
 
+def usable_cores() -> int:
+    """Host threads this process may really use: the affinity mask, capped by the cgroup CPU quota if there is one."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        quota, period = open("/sys/fs/cgroup/cpu.max").read().split()[:2]
+        if quota != "max":
+            n = max(1, min(n, int(int(quota) / int(period))))
+    except Exception:
+        pass
+    return n
+
+
 def time_multicore(ref: "CpuReference", frames: int) -> dict:
-    threads = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    threads = usable_cores()
     mc = CpuMultiCore(ref, threads)
     mc.step()
     t = sum(mc.step() for _ in range(frames))
