@@ -10,11 +10,13 @@
  * file, sources absent from /root/reference) cannot be compiled here (no
  * cargo/rustc).  This restatement follows the reference source line by line
  * (each function cites file:line under /root/reference) and is PINNED against
- * the reference's own unit-test vectors K1..K10 (see
- * tests/test_oracle_kat.py).  The functions the reference does not test
+ * the reference's own unit-test vectors K1..K13 (see
+ * tests/test_oracle_kat.py; K11-K13 pin the animation step's curves / wrapf,
+ * fyrox_anim_oracle.c).  The functions the reference does not test
  * (calculate_local_transform, bone palette, LBS, Mesh world AABB,
- * should_be_rendered, from_graph) are "parity unpinned": they follow source
- * only.  nalgebra's accumulation orders (Appendix A of SURVEY.md) are the
+ * should_be_rendered, from_graph, light collection, instance data,
+ * Animation::tick, track fetch, pose blending and application) are
+ * "parity unpinned": they follow source only.  nalgebra's accumulation orders (Appendix A of SURVEY.md) are the
  * restatement's definition.
  *
  * All matrices are 16 floats, column-major (nalgebra storage): M[r,c] = m[c*4+r].
