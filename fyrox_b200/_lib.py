@@ -135,6 +135,10 @@ TV_REAL, TV_VECTOR2, TV_VECTOR3, TV_VECTOR4, TV_QUAT_EULER, TV_QUAT = range(6)
 BIND_POSITION, BIND_SCALE, BIND_ROTATION = 0, 1, 2
 
 
+class fyx_observer(C.Structure):
+    _fields_ = [("translation", C.c_float * 3), ("z_near", C.c_float), ("z_far", C.c_float)]
+
+
 class fyx_bundle(C.Structure):
     _fields_ = [("id", C.c_uint32), ("first", C.c_uint32), ("count", C.c_uint32), ("reserved", C.c_uint32), ("sort_index", C.c_uint64)]
 
@@ -183,6 +187,8 @@ SYMBOLS = {
     "fyx_update_and_cull": (C.c_int32, [ctx_p, C.c_uint32, C.c_uint32, C.POINTER(fyx_frustum), C.c_void_p, C.c_void_p]),
     "fyx_get_visible": (C.c_int32, [ctx_p, C.c_uint32, C.POINTER(u32p), u32p]),
     "fyx_get_visible_device": (C.c_int32, [ctx_p, C.c_uint32, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]),
+    "fyx_set_lod_ranges": (C.c_int32, [ctx_p, C.c_uint32, C.c_void_p, C.c_void_p]),
+    "fyx_set_observers": (C.c_int32, [ctx_p, C.c_uint32, C.c_void_p]),
     "fyx_cull_lights": (C.c_int32, [ctx_p]),
     "fyx_get_visible_lights": (C.c_int32, [ctx_p, C.c_uint32, C.POINTER(u32p), u32p]),
     "fyx_build_palettes": (C.c_int32, [ctx_p]),

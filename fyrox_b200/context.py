@@ -277,6 +277,21 @@ class Context:
         self._chk(self._lib.fyx_get_visible_device(self._h, frustum, C.byref(d_idx), C.byref(d_cnt)))
         return d_idx.value, d_cnt.value
 
+    # ---- N4 (LOD filter) ----
+    def set_lod_ranges(self, begin_end, idx=None):
+        """Per LOD object the [begin, end] of its level (renderer/bundle.rs:898-916); begin NaN removes the node."""
+        be = _f32(begin_end)
+        ix = _u32(idx)
+        self._chk(self._lib.fyx_set_lod_ranges(self._h, be.size // 2, _ptr(ix), _ptr(be)))
+
+    def set_observers(self, observers):
+        """observers = [(translation xyz, z_near, z_far), ...], one per frustum of the culls that follow; [] switches LOD off."""
+        arr = (L.fyx_observer * max(len(observers), 1))()
+        for k, (t, zn, zf) in enumerate(observers):
+            arr[k].translation[:] = [float(x) for x in t]
+            arr[k].z_near, arr[k].z_far = float(zn), float(zf)
+        self._chk(self._lib.fyx_set_observers(self._h, len(observers), C.cast(arr, C.c_void_p)))
+
     # ---- N4 (light list) ----
     def cull_lights(self):
         """Light sources seen by every frustum of the most recent cull (renderer/bundle.rs:926-974)."""

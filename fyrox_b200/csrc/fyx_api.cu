@@ -156,6 +156,11 @@ struct fyx_ctx {
     DevBuf b_anim_keys, b_anim_tracks, b_anim_state, b_anim_hints, b_anim_values, b_anim_ok, b_anim_bk, b_anim_node_slot,
         b_anim_node_begin, b_anim_node_tracks;
 
+    // N4 LOD filter (fyx_drawprep.inl)
+    DevBuf b_lod_range, b_lodp; // float2 (begin, end; begin NaN = not a LOD object) and hidden-frusta bits, per slot
+    bool have_lod = false;
+    std::vector<fyx_observer> observers;
+
     // N4 light lists (fyx_drawprep.inl)
     DevBuf b_light[FYX_MAX_FRUSTA], b_light_ptrs, b_light_counts;
     uint32_t *h_light_counts = nullptr; // pinned
@@ -555,6 +560,8 @@ extern "C" int32_t fyx_create(const fyx_config *cfg, fyx_ctx **out_ctx)
 
 static void fyx_comm_destroy_internal(fyx_ctx *c); // fyx_comm.inl
 namespace { void inst_free(fyx_ctx *c); }              // fyx_drawprep.inl
+static bool lod_active(const fyx_ctx *c, uint32_t nf);  // fyx_drawprep.inl
+static int32_t lod_pass(fyx_ctx *c);                    // fyx_drawprep.inl
 namespace { void anim_free(fyx_ctx *c); }              // fyx_anim.inl
 static int32_t animate_enqueue(fyx_ctx *c, float dt);  // fyx_anim.inl
 static int32_t allgather_begin(fyx_ctx *c, VisSlot &V, cudaStream_t s);
@@ -870,6 +877,7 @@ extern "C" int32_t fyx_set_topology(fyx_ctx *c, uint32_t capacity, uint32_t root
     c->dfs_rank.clear();     // ... and the DFS order, if it uses it
     c->rank_on_device = false;
     c->anim_csr_dirty = true; // animated nodes are addressed by slot
+    c->have_lod = false;      // ... and the LOD ranges
     c->have_bundles = false; // ... and the bundle ids (every node is back in bundle 0)
     c->n_bundle_ids = 1;
     c->have_trs = false;     // ... and full TRS records before the next rotation-only update
@@ -1289,7 +1297,9 @@ extern "C" int32_t fyx_cull(fyx_ctx *c, uint32_t nf, const fyx_frustum *fr, cons
     int32_t rc = prepare_cull(c, nf, fr, cam_mask, pass_flags);
     if (rc) return rc;
     if (nf) {
-        launch_cull(c->stream, c->a, c->cp);
+        const bool lod = lod_active(c, nf);
+        if (lod && (rc = lod_pass(c))) return rc;
+        launch_cull(c->stream, c->a, c->cp, lod ? c->b_lodp.as<uint32_t>() : nullptr);
         c->launches++;
     }
     CU(cudaEventRecord(c->ev[EV_CULL], c->stream));
@@ -1309,8 +1319,17 @@ extern "C" int32_t fyx_update_and_cull(fyx_ctx *c, uint32_t update_flags, uint32
     CU(cudaEventRecord(c->ev[EV_START], c->stream));
     rc = prepare_cull(c, nf, fr, cam_mask, pass_flags);
     if (rc) return rc;
-    rc = run_update(c, update_flags, nf ? &c->cp : nullptr);
-    if (rc) return rc;
+    {
+        // with a LOD filter the cull cannot be fused into the level kernels: the filter bits need every ancestor first
+        const bool lod = lod_active(c, nf);
+        rc = run_update(c, update_flags, (nf && !lod) ? &c->cp : nullptr);
+        if (rc) return rc;
+        if (lod) {
+            if ((rc = lod_pass(c))) return rc;
+            launch_cull(c->stream, c->a, c->cp, c->b_lodp.as<uint32_t>());
+            c->launches++;
+        }
+    }
     CU(cudaEventRecord(c->ev[EV_UPDATE], c->stream));
     rc = sync_and_check(c);
     cudaEventElapsedTime(&c->timings.update_ms, c->ev[EV_START], c->ev[EV_UPDATE]);
@@ -1457,8 +1476,16 @@ extern "C" int32_t fyx_render_prep(fyx_ctx *c, const fyx_frame_desc *fr)
         rc = prepare_cull(c, fr->n_frusta, fr->frusta, fr->cam_mask, fr->pass_flags);
         if (rc) return rc;
     }
-    rc = run_update(c, fr->update_flags, fr->n_frusta ? &c->cp : nullptr);
-    if (rc) return rc;
+    {
+        const bool lod = lod_active(c, fr->n_frusta);
+        rc = run_update(c, fr->update_flags, (fr->n_frusta && !lod) ? &c->cp : nullptr);
+        if (rc) return rc;
+        if (lod) {
+            if ((rc = lod_pass(c))) return rc;
+            launch_cull(s, c->a, c->cp, c->b_lodp.as<uint32_t>());
+            c->launches++;
+        }
+    }
     CU(cudaEventRecord(c->ev[EV_UPDATE], s));
     if (fr->n_frusta) CU(cudaEventRecord(c->vs[c->cur].ev_cull, s));
     // multi-GPU: the visible lists are complete here; their all-gather runs on the collective stream beside

@@ -32,6 +32,8 @@ void inst_free(fyx_ctx *c)
     }
     for (auto &V : c->vs)
         for (auto &b : V.b_vis_slot) dev_free(b);
+    dev_free(c->b_lod_range);
+    dev_free(c->b_lodp);
     for (auto &b : c->b_light) dev_free(b);
     dev_free(c->b_light_ptrs);
     dev_free(c->b_light_counts);
@@ -248,5 +250,72 @@ extern "C" int32_t fyx_get_visible_lights(fyx_ctx *c, uint32_t f, const uint32_t
     if (f >= c->light_nf) return fail(c, FYX_ERR_INVALID_ARGUMENT, "frustum %u was not part of the last cull (%u frusta)", f, c->light_nf);
     *out_idx = c->h_light[f].data();
     *out_count = (uint32_t)c->h_light[f].size();
+    return FYX_OK;
+}
+
+// ---- N4 (LOD filter): renderer/bundle.rs:898-916, 988-1004 -------------------------------------------------------------
+static bool lod_active(const fyx_ctx *c, uint32_t nf) { return c->have_lod && nf && c->observers.size() == nf; }
+
+// hidden-frusta bits of every node, one small launch per hierarchy level (parents first)
+static int32_t lod_pass(fyx_ctx *c)
+{
+    LodParams lp{};
+    lp.nf = (int)c->observers.size();
+    for (int f = 0; f < lp.nf; ++f) {
+        const fyx_observer &o = c->observers[f];
+        lp.ox[f] = o.translation[0];
+        lp.oy[f] = o.translation[1];
+        lp.oz[f] = o.translation[2];
+        lp.zn[f] = o.z_near;
+        lp.zr[f] = o.z_far - o.z_near; // z_range, as the reference computes it
+    }
+    int32_t rc = dev_ensure(c, c->b_lodp, std::max<size_t>(c->n_slots, 1) * 4);
+    if (rc) return rc;
+    const size_t nl = c->level_off.size() ? c->level_off.size() - 1 : 0;
+    for (size_t l = 0; l < nl; ++l) {
+        launch_lod_level(c->stream, c->a, c->level_off[l], c->level_off[l + 1], c->b_lod_range.as<float2>(), c->b_lodp.as<uint32_t>(), lp);
+        c->launches += (c->level_off[l + 1] > c->level_off[l]);
+    }
+    CU(cudaGetLastError());
+    return FYX_OK;
+}
+
+extern "C" int32_t fyx_set_lod_ranges(fyx_ctx *c, uint32_t count, const uint32_t *idx, const float *begin_end)
+{
+    if (!c) return FYX_ERR_INVALID_ARGUMENT;
+    if (!c->have_topology) return fail(c, FYX_ERR_STATE, "fyx_set_topology has not been called");
+    if (!count) return FYX_OK;
+    if (!begin_end) return fail(c, FYX_ERR_INVALID_ARGUMENT, "begin_end is NULL");
+    CU(cudaSetDevice(c->device));
+    // host-side scatter through the slot map into a staging image of the column (LOD objects are few, calls are rare)
+    const size_t n = std::max<size_t>(c->n_slots, 1);
+    std::vector<float2> col(n);
+    int32_t rc = dev_ensure(c, c->b_lod_range, n * sizeof(float2));
+    if (rc) return rc;
+    CU(cudaStreamSynchronize(c->stream));
+    if (c->have_lod) {
+        CU(cudaMemcpy(col.data(), c->b_lod_range.p, n * sizeof(float2), cudaMemcpyDeviceToHost));
+    } else {
+        const float qnan = std::nanf("");
+        std::fill(col.begin(), col.end(), make_float2(qnan, qnan));
+    }
+    for (uint32_t e = 0; e < count; ++e) {
+        const uint32_t node = idx ? idx[e] : e;
+        if (node >= c->n_nodes) continue;
+        const uint32_t slot = c->slot_of_node[node];
+        if (slot == FYX_NONE) continue;
+        col[slot] = make_float2(begin_end[2 * (size_t)e], begin_end[2 * (size_t)e + 1]);
+    }
+    CU(cudaMemcpy(c->b_lod_range.p, col.data(), n * sizeof(float2), cudaMemcpyHostToDevice));
+    c->have_lod = true;
+    return FYX_OK;
+}
+
+extern "C" int32_t fyx_set_observers(fyx_ctx *c, uint32_t count, const fyx_observer *obs)
+{
+    if (!c) return FYX_ERR_INVALID_ARGUMENT;
+    if (count > FYX_MAX_FRUSTA) return fail(c, FYX_ERR_INVALID_ARGUMENT, "more than FYX_MAX_FRUSTA observers");
+    if (count && !obs) return fail(c, FYX_ERR_INVALID_ARGUMENT, "observers is NULL");
+    c->observers.assign(obs, obs + count);
     return FYX_OK;
 }

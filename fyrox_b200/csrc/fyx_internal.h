@@ -138,7 +138,13 @@ void launch_pack_instances(cudaStream_t s, const NodeArrays &a, const InstParams
 // ---- launchers (fyx_kernels.cu) ----
 void launch_update_level(cudaStream_t s, const NodeArrays &a, uint32_t lo, uint32_t hi, bool update_all,
                          const CullParams *cull /* nullptr = no fused cull */);
-void launch_cull(cudaStream_t s, const NodeArrays &a, const CullParams &cp);
+void launch_cull(cudaStream_t s, const NodeArrays &a, const CullParams &cp, const uint32_t *lodp = nullptr /* per slot: frusta hidden by the LOD filter */);
+// N4 LOD filter (fyx_drawprep.cu): per observer translation, z_near and z_far - z_near
+struct LodParams {
+    int nf;
+    float ox[FYX_MAX_FRUSTA], oy[FYX_MAX_FRUSTA], oz[FYX_MAX_FRUSTA], zn[FYX_MAX_FRUSTA], zr[FYX_MAX_FRUSTA];
+};
+void launch_lod_level(cudaStream_t s, const NodeArrays &a, uint32_t lo, uint32_t hi, const float2 *range, uint32_t *lodp, const LodParams &lp);
 void launch_cull_lights(cudaStream_t s, const NodeArrays &a, const CullParams &cp, uint32_t *const *d_out_ptrs, uint32_t *counts);
 void launch_fold_bones(cudaStream_t s, const NodeArrays &a, const FoldArrays &fa, const CullParams *cull);
 void launch_snapshot_bones(cudaStream_t s, const NodeArrays &a, uint32_t n_late, const uint32_t *late_slot, float4 *stale_pos);

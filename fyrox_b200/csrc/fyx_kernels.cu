@@ -245,7 +245,7 @@ __global__ void __launch_bounds__(kBlock) k_update_level(const NodeArrays a, con
 // with its own frustum, renderer/shadow/*.rs).  32 B read per node + 4 B per visible entry.
 // ------------------------------------------------------------------------------------------------
 template <int NFT>
-__global__ void __launch_bounds__(kBlock) k_cull(const NodeArrays a, const CullParams cp)
+__global__ void __launch_bounds__(kBlock) k_cull(const NodeArrays a, const CullParams cp, const uint32_t *lodp)
 {
     const uint32_t slot = blockIdx.x * kBlock + threadIdx.x;
     uint32_t vis_bits = 0u, gi = 0u;
@@ -256,6 +256,7 @@ __global__ void __launch_bounds__(kBlock) k_cull(const NodeArrays a, const CullP
         const float2 wy = ld_stream(a.wa[1] + slot);
         const float2 wz = ld_stream(a.wa[2] + slot);
         vis_bits = cull_bits<NFT>(nf, mask, wx, wy, wz, cp);
+        if (lodp && vis_bits) vis_bits &= ~lodp[slot]; // frusta whose LOD filter hides the node or one of its ancestors
         if (vis_bits) gi = a.gidx[slot];
     }
     compact_emit<NFT>(vis_bits, gi, slot, cp);
@@ -850,17 +851,17 @@ void launch_cull_lights(cudaStream_t s, const NodeArrays &a, const CullParams &c
     k_cull_lights<<<grid_for(a.cap), kBlock, 0, s>>>(a, cp, d_out_ptrs, counts);
 }
 
-void launch_cull(cudaStream_t s, const NodeArrays &a, const CullParams &cp)
+void launch_cull(cudaStream_t s, const NodeArrays &a, const CullParams &cp, const uint32_t *lodp)
 {
     if (!a.cap) return;
     const unsigned g = grid_for(a.cap);
     switch (cp.nf) {
-    case 1: k_cull<1><<<g, kBlock, 0, s>>>(a, cp); break;
-    case 2: k_cull<2><<<g, kBlock, 0, s>>>(a, cp); break;
-    case 3: k_cull<3><<<g, kBlock, 0, s>>>(a, cp); break;
-    case 4: k_cull<4><<<g, kBlock, 0, s>>>(a, cp); break;
-    case 6: k_cull<6><<<g, kBlock, 0, s>>>(a, cp); break;
-    default: k_cull<0><<<g, kBlock, 0, s>>>(a, cp); break;
+    case 1: k_cull<1><<<g, kBlock, 0, s>>>(a, cp, lodp); break;
+    case 2: k_cull<2><<<g, kBlock, 0, s>>>(a, cp, lodp); break;
+    case 3: k_cull<3><<<g, kBlock, 0, s>>>(a, cp, lodp); break;
+    case 4: k_cull<4><<<g, kBlock, 0, s>>>(a, cp, lodp); break;
+    case 6: k_cull<6><<<g, kBlock, 0, s>>>(a, cp, lodp); break;
+    default: k_cull<0><<<g, kBlock, 0, s>>>(a, cp, lodp); break;
     }
 }
 

@@ -225,6 +225,23 @@ int32_t fyx_get_visible_device(fyx_ctx *ctx, uint32_t frustum, const uint32_t **
 int32_t fyx_cull_lights(fyx_ctx *ctx);
 int32_t fyx_get_visible_lights(fyx_ctx *ctx, uint32_t frustum, const uint32_t **out_idx, uint32_t *out_count);
 
+/* N4 (LOD filter) — the lod_filter of RenderDataBundleStorage::from_graph (renderer/bundle.rs:898-916, 988-1004): a node
+ * that is an object of a LOD level is visible for an observer only while its normalised distance
+ * (|observer.translation − global_position| − z_near) / (z_far − z_near) lies in the level's [begin, end]; a node that is
+ * filtered out hides its whole sub-tree (the DFS does not descend).
+ * fyx_set_lod_ranges: per LOD object the range of the level it belongs to (2 floats each: begin, end; begin = NaN removes
+ * the node from LOD control).  The host resolves "listed in several levels" the way the reference's loop does — owners in
+ * pool order, levels and objects in order, the last write wins.  Reset by fyx_set_topology.
+ * fyx_set_observers: ObserverPosition::{translation, z_near, z_far} of the frusta of the culls that follow, one per
+ * frustum (count 0 = no LOD filtering).  While both are set the cull runs un-fused: update, then one small pass per
+ * hierarchy level that propagates the filter bits from parents to children, then the cull over all nodes. */
+typedef struct fyx_observer {
+    float translation[3];
+    float z_near, z_far;
+} fyx_observer;
+int32_t fyx_set_lod_ranges(fyx_ctx *ctx, uint32_t count, const uint32_t *idx, const float *begin_end);
+int32_t fyx_set_observers(fyx_ctx *ctx, uint32_t count, const fyx_observer *observers);
+
 /* SurfaceInstanceData::bone_matrices for every skinned surface (scene/mesh/mod.rs:781-793):
  * P[k] = bone_k.global_transform * bone_k.inv_bind_pose_transform; dead / FYX_NONE bone ⇒ identity. */
 int32_t fyx_build_palettes(fyx_ctx *ctx);

@@ -475,6 +475,11 @@ typedef struct orc_node {
     orc_aabb world_bounding_box;
     orc_surface *surfaces;
     uint32_t n_surfaces;
+    /* Base::lod_group (scene/base.rs:129-160,417-418): levels of (begin, end, objects) */
+    uint32_t n_lod_levels;
+    float *lod_begin, *lod_end;
+    uint32_t *lod_obj_begin; /* n_lod_levels + 1 offsets into lod_objects */
+    uint32_t *lod_objects;
 } orc_node;
 
 enum { MSG_TRANSFORM = 1, MSG_VISIBILITY = 2, MSG_ENABLED = 4 };
@@ -552,6 +557,10 @@ static void free_node(orc_node *n)
     }
     free(n->surfaces);
     free(n->children);
+    free(n->lod_begin);
+    free(n->lod_end);
+    free(n->lod_obj_begin);
+    free(n->lod_objects);
     free(n);
 }
 
@@ -975,6 +984,86 @@ size_t orc_from_graph(const orc_graph *g, const orc_frustum *f, uint32_t render_
     cull_ctx c = { g, f, render_mask, shadow_pass, out_idx, cap, 0 };
     if (g->root != ORC_NONE) iterate_recursive(g->root, &c);
     return c.count;
+}
+
+/* Base::set_lod_group — scene/base.rs:805-807.  Levels carry the (already clamped, LevelOfDetail::new :74-86) range and
+ * the handles of the nodes that represent that level. */
+void orc_node_set_lod_group(orc_graph *g, uint32_t i, uint32_t n_levels, const float *begin, const float *end,
+                            const uint32_t *obj_begin, const uint32_t *objects)
+{
+    orc_node *n = node_at(g, i);
+    if (!n) return;
+    free(n->lod_begin); free(n->lod_end); free(n->lod_obj_begin); free(n->lod_objects);
+    n->n_lod_levels = n_levels;
+    n->lod_begin = n->lod_end = NULL;
+    n->lod_obj_begin = n->lod_objects = NULL;
+    if (!n_levels) return;
+    n->lod_begin = (float *)malloc(4 * (size_t)n_levels);
+    n->lod_end = (float *)malloc(4 * (size_t)n_levels);
+    n->lod_obj_begin = (uint32_t *)malloc(4 * ((size_t)n_levels + 1));
+    memcpy(n->lod_begin, begin, 4 * (size_t)n_levels);
+    memcpy(n->lod_end, end, 4 * (size_t)n_levels);
+    memcpy(n->lod_obj_begin, obj_begin, 4 * ((size_t)n_levels + 1));
+    uint32_t total = obj_begin[n_levels];
+    n->lod_objects = (uint32_t *)malloc(4 * (size_t)(total ? total : 1));
+    memcpy(n->lod_objects, objects, 4 * (size_t)total);
+}
+
+/* The lod_filter of RenderDataBundleStorage::from_graph — renderer/bundle.rs:898-916: every node starts visible; for
+ * every node with a LOD group, in pool order, every object of every level is marked by whether its normalised distance
+ * to the observer lies in the level's range (later writes win).  metric_distance = |a - b| (nalgebra: sqrt of the
+ * left-to-right dot of the difference). */
+void orc_lod_filter(const orc_graph *g, const float observer_translation[3], float z_near, float z_far, uint8_t *filter)
+{
+    for (uint32_t i = 0; i < g->capacity; ++i) filter[i] = 1;
+    for (uint32_t i = 0; i < g->capacity; ++i) {
+        const orc_node *n = node_at(g, i);
+        if (!n || !n->n_lod_levels) continue;
+        for (uint32_t l = 0; l < n->n_lod_levels; ++l)
+            for (uint32_t k = n->lod_obj_begin[l]; k < n->lod_obj_begin[l + 1]; ++k) {
+                const uint32_t obj = n->lod_objects[k];
+                const orc_node *o = node_at(g, obj);
+                if (!o) continue; /* try_get_node failed */
+                float dx = observer_translation[0] - o->global_transform[12];
+                float dy = observer_translation[1] - o->global_transform[13];
+                float dz = observer_translation[2] - o->global_transform[14];
+                float distance = sqrtf(dx * dx + dy * dy + dz * dz);
+                float z_range = z_far - z_near;
+                float normalized = (distance - z_near) / z_range;
+                filter[obj] = (uint8_t)(normalized >= n->lod_begin[l] && normalized <= n->lod_end[l]);
+            }
+    }
+}
+
+typedef struct {
+    cull_ctx c;
+    const uint8_t *filter;
+} cull_lod_ctx;
+
+/* iterate_recursive with the LOD filter — renderer/bundle.rs:988-1004: a filtered-out node hides its whole sub-tree */
+static void iterate_recursive_lod(uint32_t h, cull_lod_ctx *x)
+{
+    const orc_node *n = node_at(x->c.g, h);
+    if (!n) return;
+    if (!x->filter[h]) return;
+    if (n->kind == ORC_KIND_MESH) {
+        if (orc_node_should_be_rendered(x->c.g, h, x->c.f, x->c.render_mask) && !(x->c.shadow_pass && !n->cast_shadows)) {
+            if (x->c.count < x->c.cap) x->c.out[x->c.count] = h;
+            x->c.count++;
+        }
+    }
+    for (uint32_t i = 0; i < n->n_children; ++i) iterate_recursive_lod(n->children[i], x);
+}
+
+size_t orc_from_graph_lod(const orc_graph *g, const orc_frustum *f, uint32_t render_mask, int shadow_pass,
+                          const float observer_translation[3], float z_near, float z_far, uint32_t *out_idx, size_t cap)
+{
+    uint8_t *filter = (uint8_t *)malloc(g->capacity ? g->capacity : 1);
+    orc_lod_filter(g, observer_translation, z_near, z_far, filter);
+    cull_lod_ctx x = { { g, f, render_mask, shadow_pass, out_idx, cap, 0 }, filter };
+    if (g->root != ORC_NONE) iterate_recursive_lod(g->root, &x);
+    free(filter);
+    return x.c.count;
 }
 
 /* ---- palette + LBS ---- */

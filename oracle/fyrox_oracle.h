@@ -169,6 +169,11 @@ size_t orc_from_graph(const orc_graph *g, const orc_frustum *f, uint32_t render_
  * standard.shader:192-195 in the same op order) */
 uint32_t orc_mesh_bone_matrices(const orc_graph *g, uint32_t mesh, uint32_t surface, float *out_m16);
 uint32_t orc_mesh_skin(const orc_graph *g, uint32_t mesh, uint32_t surface, float *out_pos3, float *out_nrm3);
+void     orc_node_set_lod_group(orc_graph *g, uint32_t node, uint32_t n_levels, const float *begin, const float *end,
+                                const uint32_t *obj_begin, const uint32_t *objects);          /* scene/base.rs:805-807 */
+void     orc_lod_filter(const orc_graph *g, const float observer_translation[3], float z_near, float z_far, uint8_t *filter);
+size_t   orc_from_graph_lod(const orc_graph *g, const orc_frustum *f, uint32_t render_mask, int shadow_pass,
+                            const float observer_translation[3], float z_near, float z_far, uint32_t *out_idx, size_t cap); /* N4: bundle.rs:898-916,988-1004 */
 size_t   orc_collect_lights(const orc_graph *g, const orc_frustum *f, uint32_t *out_idx, size_t cap);   /* N4: renderer/bundle.rs:926-974 */
 uint64_t orc_node_instance(const orc_graph *g, uint32_t node, const float view[16], const float vp[16],
                            float world[16], float wvp[16]);   /* N3: mesh/mod.rs:700,731-737 + bundle.rs:483-487 */

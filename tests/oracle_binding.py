@@ -177,6 +177,9 @@ def lib() -> C.CDLL:
         "orc_mt_skin_surface": (None, [vp, C.c_uint32, f32p, f32p]),
         "orc_mt_skin_all": (None, [vp]),
         "orc_mt_get": (None, [vp, C.c_uint32, f32p, C.POINTER(Aabb), C.POINTER(C.c_uint32)]),
+        "orc_node_set_lod_group": (None, [vp, C.c_uint32, C.c_uint32, f32p, f32p, vp, vp]),
+        "orc_lod_filter": (None, [vp, f32p, C.c_float, C.c_float, vp]),
+        "orc_from_graph_lod": (C.c_size_t, [vp, C.POINTER(Frustum), C.c_uint32, C.c_int, f32p, C.c_float, C.c_float, vp, C.c_size_t]),
         "orc_collect_lights": (C.c_size_t, [vp, C.POINTER(Frustum), vp, C.c_size_t]),
         "orc_node_instance": (C.c_uint64, [vp, C.c_uint32, f32p, f32p, f32p, f32p]),
         "orc_mesh_accurate_world_bounding_box": (None, [vp, C.c_uint32, C.POINTER(Aabb)]),
@@ -375,6 +378,31 @@ class Graph:
         cap = self.capacity
         out = np.empty(max(cap, 1), dtype=np.uint32)
         n = self.L.orc_from_graph(self.h, C.byref(frustum) if frustum is not None else None, render_mask, int(shadow_pass), out.ctypes.data_as(C.c_void_p), cap)
+        return out[:n].copy()
+
+    def set_lod_group(self, node, levels):
+        """levels = [(begin, end, [object nodes]), ...] — Base::set_lod_group with LevelOfDetail ranges."""
+        b = np.array([l[0] for l in levels], np.float32)
+        e = np.array([l[1] for l in levels], np.float32)
+        ob_begin = np.zeros(len(levels) + 1, np.uint32)
+        objs = []
+        for k, l in enumerate(levels):
+            objs += list(l[2])
+            ob_begin[k + 1] = len(objs)
+        o = np.array(objs if objs else [0], np.uint32)
+        self.L.orc_node_set_lod_group(self.h, int(node), len(levels), fp(b), fp(e), ob_begin.ctypes.data_as(C.c_void_p), o.ctypes.data_as(C.c_void_p))
+
+    def lod_filter(self, translation, z_near, z_far):
+        t = np.ascontiguousarray(translation, dtype=np.float32)
+        out = np.empty(max(self.capacity, 1), dtype=np.uint8)
+        self.L.orc_lod_filter(self.h, fp(t), float(z_near), float(z_far), out.ctypes.data_as(C.c_void_p))
+        return out[: self.capacity].astype(bool)
+
+    def from_graph_lod(self, frustum: Frustum, translation, z_near, z_far, render_mask=0xFFFFFFFF, shadow_pass=False):
+        t = np.ascontiguousarray(translation, dtype=np.float32)
+        cap = self.capacity
+        out = np.empty(max(cap, 1), dtype=np.uint32)
+        n = self.L.orc_from_graph_lod(self.h, C.byref(frustum), render_mask, int(shadow_pass), fp(t), float(z_near), float(z_far), out.ctypes.data_as(C.c_void_p), cap)
         return out[:n].copy()
 
     def collect_lights(self, frustum: Frustum):

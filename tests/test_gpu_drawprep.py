@@ -184,3 +184,79 @@ def test_light_lists_match_oracle(ctx):
     ctx.cull_lights()
     for f, o in enumerate(obs):
         assert np.array_equal(ctx.get_visible_lights(f), og.collect_lights(o[2]))
+
+
+def test_lod_filter_matches_oracle(ctx):
+    """N4 (LOD filter): from_graph's lod_filter (renderer/bundle.rs:898-916) and the pruned DFS (:988-1004) — a LOD object
+    outside its level's normalised-distance range hides its whole sub-tree for that observer; objects listed by several
+    owners take the verdict written last; fused, stand-alone and one-call culls; switching the filter off again."""
+    rng = np.random.default_rng(1234)
+    parent, flags, mask, local, aabb = random_graph(rng, 3000, p_orphan=0.02, p_mesh=0.7)
+    n = len(parent)
+    og = ob.Graph.build(parent, flags, mask, local, aabb)
+    og.update_hierarchical_data()
+    ctx.set_topology(parent, flags, mask, aabb)
+    ctx.set_local_matrices(local)
+    alive = np.nonzero((flags & fb.NODE_ALIVE) != 0)[0]
+    owners = np.sort(rng.choice(alive, 30, replace=False))
+    levels = [(0.0, 0.25), (0.25, 0.6), (0.6, 1.0)]
+    final = {}
+    for o in owners:  # pool order, levels in order, objects in order: the last write wins (what the host resolves)
+        lv = []
+        for (b, e) in levels:
+            objs = rng.integers(1, n, rng.integers(1, 5)).tolist()  # may hit dead records and other owners' objects
+            lv.append((b, e, objs))
+            for x in objs:
+                if flags[x] & fb.NODE_ALIVE:
+                    final[x] = (b, e)
+        og.set_lod_group(int(o), lv)
+    idx = np.array(sorted(final), np.uint32)
+    ctx.set_lod_ranges(np.array([final[int(i)] for i in idx], np.float32), idx)
+    eyes = [((0, 0, 60), (0, 0, 0), 0.1, 200.0), ((35, 5, -10), (0, 0, 0), 0.5, 90.0), ((-20, -30, 15), (5, 5, 5), 0.1, 60.0)]
+    obs = [observer(e, t, zn=zn, zf=zf) for e, t, zn, zf in eyes]
+    observers = [(e, zn, zf) for e, _, zn, zf in eyes]
+    ffs = [o[3] for o in obs]
+
+    def check(lod=True):
+        hidden = 0
+        for f, (e, _, zn, zf) in enumerate(eyes):
+            plain = og.from_graph(obs[f][2])
+            want = og.from_graph_lod(obs[f][2], e, zn, zf) if lod else plain
+            got = np.sort(ctx.get_visible(f))
+            assert np.array_equal(got, np.sort(want)), f"frustum {f}: {got.size} vs {want.size}"
+            hidden += plain.size - want.size
+        return hidden
+
+    ctx.update_and_cull(ffs, fb.UPDATE_ALL)
+    assert check(lod=False) == 0  # ranges alone do nothing: no observers yet
+    ctx.set_observers(observers)
+    ctx.update_and_cull(ffs, fb.UPDATE_ALL)
+    assert check() > 20  # the filter really removes nodes
+    ctx.cull(ffs)
+    check()
+    ctx.render_prep(update_flags=fb.UPDATE_INCREMENTAL, frusta=ffs, do_palettes=False, do_skin=False)
+    check()
+    # a cull with another frustum count is not LOD-filtered (the observers do not match it)
+    ctx.cull(ffs[:2])
+    for f in range(2):
+        assert np.array_equal(np.sort(ctx.get_visible(f)), np.sort(og.from_graph(obs[f][2])))
+    # remove half of the objects from LOD control, move the graph, cull again
+    drop = idx[::2]
+    ctx.set_lod_ranges(np.full((drop.size, 2), np.nan, np.float32), drop)
+    dropped = set(int(x) for x in drop)
+    for o in owners:
+        og.set_lod_group(int(o), [])
+    # rebuild the oracle's groups from what is left: one single-object level per remaining object keeps the same verdicts
+    rest = [int(i) for i in idx if int(i) not in dropped]
+    for k, x in enumerate(rest):
+        og.set_lod_group(int(owners[k % len(owners)]), [])
+    per_owner = {}
+    for k, x in enumerate(rest):
+        per_owner.setdefault(int(owners[k % len(owners)]), []).append((final[x][0], final[x][1], [x]))
+    for o, lv in per_owner.items():
+        og.set_lod_group(o, lv)
+    ctx.update_and_cull(ffs, fb.UPDATE_ALL)
+    check()
+    ctx.set_observers([])
+    ctx.cull(ffs)
+    assert check(lod=False) == 0

@@ -478,3 +478,31 @@ def test_blend_group_clones_the_first_source_and_lerps_the_rest():
     t_before = b.time_position
     ob.blend_group_update([a, b], [1.0, 0.5], 0.1, og, tr)
     assert b.time_position == t_before and tuple(tr[1].local_position) == (1.0, 2.0, 3.0)
+
+
+def test_lod_filter_prunes_whole_subtrees_and_later_groups_win():
+    """from_graph's lod_filter (renderer/bundle.rs:898-916, 988-1004): an object outside its level's normalised-distance
+    range hides its whole sub-tree; an object listed twice takes the verdict written last (pool order of the owners)."""
+    from helpers import camera_frustum
+
+    NONE_ = 0xFFFFFFFF
+    RENDER = ob.lib() and (1 << 5)
+    DEF = (1 << 0) | (1 << 1) | (1 << 2) | (1 << 3) | (1 << 4)
+    #          0 root   1 owner  2 lvl0   3 lvl1   4 mesh<2  5 mesh<3  6 owner2
+    parent = np.array([NONE_, 0, 1, 1, 2, 3, 0], np.uint32)
+    flags = np.array([DEF, DEF, DEF, DEF, DEF | RENDER, DEF | RENDER, DEF], np.uint32)
+    local = np.tile(np.eye(4, dtype=np.float32).reshape(16), (7, 1))
+    local[1, 12:15] = (0, 0, -10)  # the whole group sits 10 units in front of the camera
+    aabb = np.tile(np.array([-0.5, -0.5, -0.5, 0.5, 0.5, 0.5], np.float32), (7, 1))
+    og = ob.Graph.build(parent, flags, None, local, aabb)
+    og.update_hierarchical_data()
+    og.set_lod_group(1, [(0.0, 0.3, [2]), (0.3, 1.0, [3])])
+    fo, _ = camera_frustum(zfar=100.0)
+    eye = (0.0, 0.0, 0.0)
+    assert og.lod_filter(eye, 0.0, 100.0).tolist() == [True, True, True, False, True, True, True]
+    assert sorted(og.from_graph(fo).tolist()) == [4, 5]                       # no LOD: both meshes
+    assert og.from_graph_lod(fo, eye, 0.0, 100.0).tolist() == [4]             # level 1 is out of range: its mesh goes with it
+    assert og.from_graph_lod(fo, eye, 0.0, 20.0).tolist() == [5]              # normalised 0.5: the other level
+    # a second owner (higher index, so visited later) lists node 2 with a range it falls outside of: the later verdict wins
+    og.set_lod_group(6, [(0.5, 1.0, [2])])
+    assert og.from_graph_lod(fo, eye, 0.0, 100.0).tolist() == []
