@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Emit tests/golden/reference_kats.json: the known-answer vectors of the reference's own unit tests
-for the render-prep path (SURVEY.md §8c K1–K10) and of the animation-sampling step before it (K11–K13), transcribed from the cited test sources.
+for the render-prep path (SURVEY.md §8c K1–K10) and of the animation-sampling step before it (K11–K14), transcribed from the cited test sources.
 
 The reference is Rust (no toolchain here), so the vectors cannot be produced by running it.  When
 /root/reference exists (the build container) this script also checks that each cited file still
@@ -127,6 +127,19 @@ KATS = {
             ["key3", "key", 1.0, 5.0], ["key3", "key", 0.0, 20.0], ["key3", "key2", 1.0, 10.0], ["key3", "key2", 0.0, 20.0],
             ["key3", "key4", 1.0, 30.0], ["key3", "key4", 0.0, 20.0],
         ],
+    },
+    "K14_curve_key_order": {
+        "source": "fyrox-math/src/curve.rs:410-427",
+        "quote": "assert_eq!(curve.keys[0].location, -5.0);",
+        "insert": [0.0, -1.0, 3.0, 2.0, -5.0],
+        "expected": [-5.0, -1.0, 0.0, 2.0, 3.0],
+        # test_curve_from_vec (curve.rs:570-579): keys (location, value) given as [key2, key3, key, key4 = key2.clone()]
+        "from_vec": [[0.0, 0.0], [1.0, 1.0], [-1.0, -1.0], [0.0, 0.0]],
+        "from_vec_expected": [[-1.0, -1.0], [0.0, 0.0], [0.0, 0.0], [1.0, 1.0]],
+        # test_curve (curve.rs:487-520): keys 5@0 (Constant), 10@1 (Linear); a default key (0@0) added lands in front; moved to 20 it ends last
+        "max_location": 1.0,
+        "after_add_default": [[0.0, 0.0], [0.0, 5.0], [1.0, 10.0]],
+        "after_move_key0_to_20": [[0.0, 5.0], [1.0, 10.0], [20.0, 0.0]],
     },
     "K10_handle_numbering": {
         "source": "fyrox-impl/src/scene/graph/mod.rs:408-424",
