@@ -132,3 +132,15 @@ def test_resolved_lod_ranges_reproduce_the_reference_loop():
             nrm = np.float32(np.float32(dist - np.float32(zn)) / np.float32(np.float32(zf) - np.float32(zn)))
             got[x] = (nrm >= ranges[k, 0]) and (nrm <= ranges[k, 1])
         assert np.array_equal(got, want)
+
+
+def test_cpp_host_mirror_of_animation_and_lod():
+    """tests/cpp/test_host_cpu.cpp: the same reference curve tests (K14) and host logic on the C++ mirror
+    (fyrox_b200/host/fyrox_anim_host.hpp); pure host code, no CUDA call."""
+    import subprocess
+
+    d = os.path.join(HERE, "cpp")
+    subprocess.run(["make", "-C", d, "test_host_cpu"], check=True, capture_output=True)
+    out = subprocess.run([os.path.join(d, "test_host_cpu")], capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert "all checks passed" in out.stdout
