@@ -35,6 +35,7 @@ SEED = 0xF1A0C5
 
 # BASELINE.json configs (per GPU; weak scaling multiplies by N)
 WORKLOADS = {
+    "C1": dict(nodes=100_000, units=0, verts_per_unit=5000, frusta=1, desc="100k static nodes, 1 camera frustum (BASELINE.json configs[0]: the reference's CPU-runnable case)"),
     "C2": dict(nodes=10_000_000, units=0, verts_per_unit=5000, frusta=1, desc="10M static nodes, 1 frustum"),
     "C3": dict(nodes=1_000_000, units=10_000, verts_per_unit=5000, frusta=1, desc="1M nodes incl. 10k skinned meshes x 64 bones x 5k verts, 1 frustum"),
     "C4": dict(nodes=10_000_000, units=50_000, verts_per_unit=5000, frusta=6, desc="10M nodes, 50k skinned meshes x 64 bones x 5k verts, 6 frusta (cube faces)"),
@@ -116,6 +117,8 @@ class ClockSampler:
 # --------------------------------------------------------------------------------------------------
 def cpu_sample_config(w: dict) -> dict:
     """A bounded sample of the workload with the same nodes:verts ratio (about 2-5 s of CPU work per frame)."""
+    if w["nodes"] <= 100_000:  # C1 is small enough to run whole
+        return dict(nodes=w["nodes"], units=w["units"], verts_per_unit=w["verts_per_unit"], frusta=w["frusta"])
     scale = 10 if w["units"] >= 10_000 else 5
     nodes = max(w["nodes"] // scale, 100_000)
     units = w["units"] // scale

@@ -24,6 +24,15 @@ def test_reference_arm_prints_exactly_one_json_line_with_the_contract_keys():
     assert mc["kind"] == "port-openmp" and mc["cores"] >= 1 and mc["value"] > 0
 
 
+def test_c1_runs_whole_on_the_cpu():
+    """BASELINE.json configs[0] (100k static nodes, 1 frustum, CPU only) is not sampled down."""
+    out = subprocess.run([sys.executable, os.path.join(REPO, "bench.py"), "--impl", "reference", "--workload", "C1", "--steps", "2", "--warmup", "1"],
+                         capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    d = json.loads(out.stdout)
+    assert d["config"]["sample"].startswith("100000 nodes, 0 skinned meshes") and d["value"] > 0
+
+
 def test_other_ranks_of_the_reference_arm_exit_quietly():
     env = dict(os.environ, RANK="1", WORLD_SIZE="2")
     out = subprocess.run([sys.executable, os.path.join(REPO, "bench.py"), "--impl", "reference", "--gpus", "2", "--workload", "tiny"],
