@@ -67,12 +67,13 @@ def test_create_fails_loudly_without_a_gpu():
 
 
 def test_product_does_not_touch_the_oracle():
-    """Nothing under fyrox_b200/ or include/ may reference oracle/ (the judge checks exactly this)."""
+    """Nothing under fyrox_b200/, include/ or tools/ may reference oracle/ (the judge checks exactly this): only tests/,
+    __graft_entry__.smoke() and bench.py's CPU-baseline legs use it."""
     bad = []
-    for root in ("fyrox_b200", "include"):
+    for root in ("fyrox_b200", "include", "tools"):
         for d, _, files in os.walk(os.path.join(REPO, root)):
             for f in files:
-                if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp", ".inl")):
+                if f.endswith((".py", ".cu", ".cuh", ".h", ".hpp", ".cpp", ".inl", ".sh")):
                     txt = open(os.path.join(d, f), errors="ignore").read()
                     if re.search(r"oracle_binding|fyrox_oracle|liboracle|from oracle|import oracle|oracle/", txt):
                         # scenegen.h mentions the word in a comment only; flag real references
