@@ -340,10 +340,9 @@ class Context:
     def anim_set_time_position(self, anim: int, t: float):
         self._chk(self._lib.fyx_anim_set_time_position(self._h, anim, float(t)))
 
-    def anim_time_positions(self, first: int = 0, count: Optional[int] = None) -> np.ndarray:
-        out = np.empty(0 if count is None else count, dtype=np.float32)
-        if count is None:
-            raise ValueError("count is required")
+    def anim_time_positions(self, first: int, count: int) -> np.ndarray:
+        """Animation::time_position() of `count` animations starting at `first` (read back from the device)."""
+        out = np.empty(count, dtype=np.float32)
         self._chk(self._lib.fyx_anim_get_time_positions(self._h, first, count, out.ctypes.data_as(C.c_void_p)))
         return out
 
