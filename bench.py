@@ -232,12 +232,18 @@ class CpuMultiCore:
 def usable_cores() -> int:
     """Host threads this process may really use: the affinity mask, capped by the cgroup CPU quota if there is one."""
     n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
-    try:
+    try:  # cgroup v2
         quota, period = open("/sys/fs/cgroup/cpu.max").read().split()[:2]
         if quota != "max":
             n = max(1, min(n, int(int(quota) / int(period))))
     except Exception:
-        pass
+        try:  # cgroup v1
+            quota = int(open("/sys/fs/cgroup/cpu/cpu.cfs_quota_us").read())
+            period = int(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+            if quota > 0 and period > 0:
+                n = max(1, min(n, quota // period))
+        except Exception:
+            pass
     return n
 
 
@@ -642,6 +648,9 @@ def main():
     ap.add_argument("--no-device-animation", action="store_true", help="skip the extra mode that samples the bones' animation curves on the device")
     ap.add_argument("--verbose", action="store_true")
     args = ap.parse_args()
+    # OpenMP workers (scene generator, multi-core CPU baseline) that wait at a barrier should sleep, not spin: the host is
+    # shared with the other ranks and possibly quota-limited (must be set before libgomp is loaded)
+    os.environ.setdefault("OMP_WAIT_POLICY", "PASSIVE")
     # stdout carries exactly ONE JSON line: libraries that write to fd 1 (NCCL prints its version banner there when
     # NCCL_DEBUG=VERSION) are sent to stderr for the whole run, the line goes out through the saved descriptor
     sys.stdout.flush()
