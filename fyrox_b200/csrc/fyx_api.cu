@@ -141,6 +141,7 @@ struct fyx_ctx {
     cudaEvent_t ev[EV_COUNT] = {};
     fyx_timings timings{};
     bool timings_pending = false; // an async frame's events have not been read yet
+    bool stage_events_valid = false; // the last frame recorded the per-stage events (synchronous frames only)
 
     // N2 animation sampling (fyx_anim.inl)
     std::vector<AnimHost> anims;
@@ -212,9 +213,14 @@ int32_t dev_ensure(fyx_ctx *c, DevBuf &b, size_t bytes, bool keep = false)
     nb = (nb + 255) & ~size_t(255);
     void *np = nullptr;
     CU(cudaMalloc(&np, nb));
-    if (keep && b.p && b.bytes) CU(cudaMemcpyAsync(np, b.p, b.bytes, cudaMemcpyDeviceToDevice, c->stream));
     if (b.p) {
-        CU(cudaStreamSynchronize(c->stream));
+        cudaError_t e = cudaSuccess;
+        if (keep && b.bytes) e = cudaMemcpyAsync(np, b.p, b.bytes, cudaMemcpyDeviceToDevice, c->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+        if (e != cudaSuccess) {
+            cudaFree(np); // the old buffer stays valid
+            return fail(c, FYX_ERR_CUDA, "growing a device buffer failed: %s", cudaGetErrorString(e));
+        }
         cudaFree(b.p);
     }
     b.p = np;
@@ -1399,11 +1405,14 @@ extern "C" int32_t fyx_skin(fyx_ctx *c)
 static void frame_timings_from_events(fyx_ctx *c)
 {
     fyx_timings &t = c->timings;
-    cudaEventElapsedTime(&t.upload_ms, c->ev[EV_START], c->ev[EV_UPLOAD]);
-    cudaEventElapsedTime(&t.update_ms, c->ev[EV_UPLOAD], c->ev[EV_UPDATE]);
-    cudaEventElapsedTime(&t.palette_ms, c->ev[EV_UPDATE], c->ev[EV_PALETTE]);
-    cudaEventElapsedTime(&t.skin_ms, c->ev[EV_PALETTE], c->ev[EV_SKIN]);
-    cudaEventElapsedTime(&t.readback_ms, c->ev[EV_SKIN], c->ev[EV_READBACK]);
+    t.upload_ms = t.update_ms = t.palette_ms = t.skin_ms = t.readback_ms = 0.0f;
+    if (c->stage_events_valid) {
+        cudaEventElapsedTime(&t.upload_ms, c->ev[EV_START], c->ev[EV_UPLOAD]);
+        cudaEventElapsedTime(&t.update_ms, c->ev[EV_UPLOAD], c->ev[EV_UPDATE]);
+        cudaEventElapsedTime(&t.palette_ms, c->ev[EV_UPDATE], c->ev[EV_PALETTE]);
+        cudaEventElapsedTime(&t.skin_ms, c->ev[EV_PALETTE], c->ev[EV_SKIN]);
+        cudaEventElapsedTime(&t.readback_ms, c->ev[EV_SKIN], c->ev[EV_READBACK]);
+    }
     cudaEventElapsedTime(&t.total_ms, c->ev[EV_START], c->ev[EV_READBACK]);
     t.cull_ms = 0.0f;
     c->timings_pending = false;
@@ -1425,6 +1434,11 @@ extern "C" int32_t fyx_render_prep(fyx_ctx *c, const fyx_frame_desc *fr)
         if (rc) return rc;
     }
     const bool async = (fr->flags & FYX_FRAME_ASYNC) != 0;
+    // Per-stage events sit BETWEEN kernels of the programmatic-dependent-launch chain and would keep a kernel's
+    // prologue from overlapping its predecessor's tail: only synchronous frames record them (their timings are read
+    // right after the call); asynchronous frames record the frame's start and end only (stage fields read 0).
+    const bool stage_events = !async;
+    c->stage_events_valid = stage_events;
     const bool pipelined = async && fr->readback_visible && fr->n_frusta; // read-back deferred to fyx_frame_wait
     // 1. changed local matrices.  Pinned caller memory is DMA'd in place (the caller keeps it untouched until
     //    the frame is synchronised / waited for).  Async frames upload on the copy stream into alternating
@@ -1470,7 +1484,7 @@ extern "C" int32_t fyx_render_prep(fyx_ctx *c, const fyx_frame_desc *fr)
         }
         c->launches++;
     }
-    CU(cudaEventRecord(c->ev[EV_UPLOAD], s));
+    if (stage_events) CU(cudaEventRecord(c->ev[EV_UPLOAD], s));
     // 2. hierarchy + world boxes + cull
     if (fr->n_frusta) {
         rc = prepare_cull(c, fr->n_frusta, fr->frusta, fr->cam_mask, fr->pass_flags);
@@ -1486,8 +1500,8 @@ extern "C" int32_t fyx_render_prep(fyx_ctx *c, const fyx_frame_desc *fr)
             c->launches++;
         }
     }
-    CU(cudaEventRecord(c->ev[EV_UPDATE], s));
-    if (fr->n_frusta) CU(cudaEventRecord(c->vs[c->cur].ev_cull, s));
+    if (stage_events) CU(cudaEventRecord(c->ev[EV_UPDATE], s));
+    if (fr->n_frusta && (async || (fr->flags & FYX_FRAME_ALLGATHER))) CU(cudaEventRecord(c->vs[c->cur].ev_cull, s)); // consumed by the read-back / collective streams
     // multi-GPU: the visible lists are complete here; their all-gather runs on the collective stream beside
     // the palette / skinning kernels below (the path's one exchange step)
     const bool gather = (fr->flags & FYX_FRAME_ALLGATHER) && fr->n_frusta;
@@ -1503,12 +1517,12 @@ extern "C" int32_t fyx_render_prep(fyx_ctx *c, const fyx_frame_desc *fr)
         launch_palette(s, c->a, c->sk);
         c->launches++;
     }
-    CU(cudaEventRecord(c->ev[EV_PALETTE], s));
+    if (stage_events) CU(cudaEventRecord(c->ev[EV_PALETTE], s));
     if (fr->do_skin && c->n_tiles) {
         launch_skin(s, c->sk, c->b_tiles.as<SkinTile>(), c->n_tiles, c->max_bones);
         c->launches++;
     }
-    CU(cudaEventRecord(c->ev[EV_SKIN], s));
+    if (stage_events) CU(cudaEventRecord(c->ev[EV_SKIN], s));
     CU(cudaGetLastError());
     if (gather) {
         // the host waits only for the cull + the counts (the skinning kernel keeps running), then enqueues the payload

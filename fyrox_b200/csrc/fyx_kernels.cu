@@ -174,9 +174,9 @@ template <int NFT>
 __device__ __forceinline__ void update_node(const NodeArrays &a, const uint32_t slot, const uint32_t update_all, const CullParams &cp,
                                             uint32_t &vis_bits, uint32_t &gi)
 {
-    const uint32_t f = a.flags[slot];
-    const uint32_t p = a.parent[slot];
-    pdl_wait(); // everything below reads what the previous level (or the previous frame's tail) wrote
+    const uint32_t p = a.parent[slot]; // static column: may be read before the predecessor has finished
+    pdl_wait(); // everything below reads what the previous level / a scatter kernel / the previous frame's tail wrote
+    const uint32_t f = a.flags[slot]; // mutable (F_DIRTY_SELF is set by the scatter kernels): only after the wait
     // no parent ⇒ parent values are identity / true (graph/mod.rs:1171-1175,1187-1192,1210-1214)
     const uint32_t pf = (p != FYX_NONE)
                             ? a.flags[p]
@@ -447,14 +447,6 @@ __global__ void __launch_bounds__(kBlock) k_palette(const NodeArrays a, const Sk
 //   indices are (with one copy, 57 % of the shared-memory wavefronts were conflict replays).
 // Algorithmic bytes per vertex: 44 read + 24 written = 68.
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src)
-{
-    const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
-
 __device__ __forceinline__ float2 lo2(const float4 v) { return make_float2(v.x, v.y); }
 __device__ __forceinline__ float2 hi2(const float4 v) { return make_float2(v.z, v.w); }
 

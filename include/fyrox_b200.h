@@ -100,7 +100,9 @@ typedef struct fyx_vertex_layout {
 } fyx_vertex_layout;
 
 /* Device-side durations of the stages run by the last fyx_render_prep / individual calls, in ms
- * (the GPU path's counterpart of GraphPerformanceStatistics, scene/graph/mod.rs:94-122). */
+ * (the GPU path's counterpart of GraphPerformanceStatistics, scene/graph/mod.rs:94-122).
+ * Per-stage values are recorded by SYNCHRONOUS frames only: the events sit between the kernels of the frame's
+ * programmatic-dependent-launch chain and would serialise it, so FYX_FRAME_ASYNC frames fill total_ms alone. */
 typedef struct fyx_timings {
     float upload_ms;    /* H2D + scatter of changed local matrices / flags */
     float update_ms;    /* hierarchy + world AABB (+ fused cull) */
