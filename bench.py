@@ -39,6 +39,7 @@ WORKLOADS = {
     "C2": dict(nodes=10_000_000, units=0, verts_per_unit=5000, frusta=1, desc="10M static nodes, 1 frustum"),
     "C3": dict(nodes=1_000_000, units=10_000, verts_per_unit=5000, frusta=1, desc="1M nodes incl. 10k skinned meshes x 64 bones x 5k verts, 1 frustum"),
     "C4": dict(nodes=10_000_000, units=50_000, verts_per_unit=5000, frusta=6, desc="10M nodes, 50k skinned meshes x 64 bones x 5k verts, 6 frusta (cube faces)"),
+    "C5": dict(nodes=100_000_000, units=200_000, verts_per_unit=5000, frusta=6, desc="100M nodes, 200k skinned meshes x 64 bones x 5k verts, 6 frusta: the WHOLE job, sharded over the GPUs (strong scaling)"),
     "target": dict(nodes=10_000_000, units=10_000, verts_per_unit=5000, frusta=1, desc="10M nodes + 50M skinned verts, 1 frustum (north_star target)"),
     "tiny": dict(nodes=200_000, units=200, verts_per_unit=5000, frusta=6, desc="debug"),
 }
@@ -372,44 +373,82 @@ def device_animation_mode(ctx, sc, fb, frusta, n_bones, steps, timed, log):
             "animation_GBps": per_bone * n_bones / max(anim_ms, 1e-6) / 1e-3 / 1e9}
 
 
-def run_cuda(args):
+def oracle_frusta(n_frusta: int):
+    """The bench's observers through the oracle's own restatement (parity block only)."""
+    sys.path.insert(0, os.path.join(REPO, "tests"))
+    import oracle_binding as ob
+
+    if n_frusta == 1:
+        view = ob.look_at_rh((0, 0, 0), (0, 0, -1), (0, 1, 0))
+        return [ob.frustum_from_vp(ob.mat4_mul(ob.perspective(16 / 9, float(np.deg2rad(60.0)), 0.1, 150.0), view))]
+    faces = [((1, 0, 0), (0, -1, 0)), ((-1, 0, 0), (0, -1, 0)), ((0, 1, 0), (0, 0, 1)), ((0, -1, 0), (0, 0, -1)), ((0, 0, 1), (0, -1, 0)), ((0, 0, -1), (0, -1, 0))]
+    return [ob.frustum_from_vp(ob.mat4_mul(ob.perspective(1.0, float(np.pi / 2), 0.01, 120.0), ob.look_at_rh((0, 0, 0), look, up))) for look, up in faces[:n_frusta]]
+
+
+def parity_block(ctx, sc, fb, frusta, upload, world, rank, dist, log):
+    """Sampled-oracle check of the context that was just timed (outside every timed region; the oracle is the checker,
+    never on the product path).  One more synchronous frame with animation frame 0, then per rank: >= 5 000 sampled
+    nodes (global matrix and world box bit-exact, per-frustum visibility identical) incl. skinned-mesh nodes with their
+    bone folds, and 4 skinned meshes bit-exact (palette, positions, normals).  N > 1: rank 0's GATHERED host lists are
+    checked against every rank's sampled truth and against the checksum of every rank's own list."""
+    sys.path.insert(0, os.path.join(REPO, "tests"))
+    import sampled_parity as sp
+
+    t0 = time.time()
+    idx0 = pay0 = None
+    if sc.n_units:
+        idx0, pay0 = sc.animate(0) if upload == "m16" else sc.animate_trs(0)
+    out, res = sp.check_frame(ctx, sc, frusta, oracle_frusta(len(frusta)), upload, idx0, pay0, allgather=(world > 1), seed=SEED + rank)
+    out["ranks"] = world
+    if world > 1:
+        mine = {"gid": res["sample_gid"], "vis": res["sample_vis"], "sums": res["own_sums"], "ok": out["ok"],
+                "nodes": out["checked_nodes"], "verts": out["checked_verts"], "err": out["max_abs_pos_err"]}
+        allp = [None] * world if rank == 0 else None
+        dist.gather_object(mine, allp, dst=0)
+        if rank == 0:
+            gathered = [ctx.get_visible_gathered(f) for f in range(len(frusta))]
+            g_ok, c_ok = True, True
+            for f, lst in enumerate(gathered):
+                g_ok &= np.unique(lst).size == lst.size
+                for p in allp:
+                    g_ok &= bool(np.array_equal(np.isin(p["gid"], lst), p["vis"][:, f]))
+                n, sm, x = sp.list_checksum(lst)
+                c_ok &= n == sum(p["sums"][f][0] for p in allp) and sm == sum(p["sums"][f][1] for p in allp) % (1 << 64)
+                xr = 0
+                for p in allp:
+                    xr ^= p["sums"][f][2]
+                c_ok &= x == xr
+            out["gathered_lists_match_every_ranks_truth"] = bool(g_ok)
+            out["gathered_equals_union_of_own_lists"] = bool(c_ok)
+            out["all_ranks_ok"] = bool(all(p["ok"] for p in allp))
+            out["checked_nodes"] = int(sum(p["nodes"] for p in allp))
+            out["checked_verts"] = int(sum(p["verts"] for p in allp))
+            out["max_abs_pos_err"] = float(max(p["err"] for p in allp))
+            out["visible_set_equal"] = bool(out["visible_set_equal"] and g_ok and c_ok and out["all_ranks_ok"])
+            out["ok"] = bool(out["ok"] and out["visible_set_equal"])
+        else:
+            ctx.sync()
+    out["seconds"] = round(time.time() - t0, 2)
+    out["how"] = "sampled oracle (tests/sampled_parity.py) on the timed context after the timed regions; bit-exact compares"
+    log(f"parity: {out}")
+    return out
+
+
+def measure(args, wname, strong, steps, env, full):
+    """All timed regions (+ the parity block) of one workload on this rank's GPU.  `strong`: the workload's sizes are
+    the WHOLE job, sharded over the ranks (strong scaling); otherwise they are per GPU (weak scaling).
+    `full`: also the secondary modes (static+skeletons, device animation) and the synchronous e2e."""
     import torch
-    import torch.distributed as dist
 
     import fyrox_b200 as fb
     from fyrox_b200 import camera
     from fyrox_b200.scenegen import Scene
 
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if world != args.gpus and world > 1:
-        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
-    if args.gpus > 1 and world == 1:
-        raise SystemExit("launch N>1 with torchrun (one process per GPU)")
-    if not torch.cuda.is_available():
-        raise SystemExit("no CUDA device: bench.py has no CPU fallback for the CUDA arm (use --impl reference for the CPU baseline)")
-    torch.cuda.set_device(local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-
-    def log(msg):
-        if rank == 0 and args.verbose:
-            print("[bench]", msg, file=sys.stderr, flush=True)
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-
-    w = WORKLOADS[args.workload]
-    from fyrox_b200 import scenegen as _sg
-    _sg.set_threads(max(1, (os.cpu_count() or 8) // max(world, 1)))  # torchrun exports OMP_NUM_THREADS=1
-    # weak scaling: per-GPU work fixed; the scene grows with N and is sharded by sector sub-tree
-    sc = Scene(w["nodes"] * world, n_units=w["units"] * world, verts_per_unit=w["verts_per_unit"], bones_per_unit=BONES, seed=SEED, rank=rank, nranks=world)
-    # the context launches on an explicit torch stream so that torch.cuda.Event brackets exactly its work
-    tstream = torch.cuda.Stream(device=local_rank)
-    torch.cuda.set_stream(tstream)
-    assert tstream.cuda_stream != 0
+    rank, world, local_rank, dist, log, barrier = env["rank"], env["world"], env["local_rank"], env["dist"], env["log"], env["barrier"]
+    w = WORKLOADS[wname]
+    mult = 1 if strong else world
+    sc = Scene(w["nodes"] * mult, n_units=w["units"] * mult, verts_per_unit=w["verts_per_unit"], bones_per_unit=BONES, seed=SEED, rank=rank, nranks=world)
+    tstream = env["tstream"]
     ctx = fb.Context(device=local_rank, stream=tstream.cuda_stream)
     load_scene(ctx, sc, fb, log)
     if world > 1:
@@ -433,13 +472,13 @@ def run_cuda(args):
         for fr in range(2):
             pi = fb.PinnedBuffer((n_bones,), np.uint32)
             if args.upload == "rot":
-                full = fb.PinnedBuffer((n_bones, 10), np.float32)
-                sc.animate_trs_into(fr, pi.ptr, full.ptr)
+                full_trs = fb.PinnedBuffer((n_bones, 10), np.float32)
+                sc.animate_trs_into(fr, pi.ptr, full_trs.ptr)
                 if fr == 0:
-                    ctx.set_local_trs(full.array, pi.array)  # the device keeps every bone's position / scale from here on
+                    ctx.set_local_trs(full_trs.array, pi.array)  # the device keeps every bone's position / scale from here on
                 pm = fb.PinnedBuffer((n_bones, 4), np.float32)
-                pm.array[:] = full.array[:, 3:7]
-                full.free()
+                pm.array[:] = full_trs.array[:, 3:7]
+                full_trs.free()
             elif args.upload == "trs":
                 pm = fb.PinnedBuffer((n_bones, 10), np.float32)
                 sc.animate_trs_into(fr, pi.ptr, pm.ptr)
@@ -454,13 +493,11 @@ def run_cuda(args):
                         allgather=(world > 1))
 
     vis_counts = [0] * len(frusta)
-    own_lists = [False]  # set while the pipelined e2e loop runs on a rank other than 0
 
     def submit_e2e(i, pipelined):
-        # N > 1: every rank holds the gathered lists on its device; the host copy of the WHOLE lists is made once, by rank 0
-        # ("the host via one pinned copy"); the other ranks read back their own lists
-        kw = dict(update_flags=fb.UPDATE_ALL, frusta=frusta, readback_visible=True, async_=pipelined, allgather=(world > 1),
-                  readback_own=(world > 1 and rank != 0 and pipelined))
+        # N > 1: every rank holds the gathered lists on its device and brings its OWN lists to the host (its PCIe link);
+        # fyx_get_visible_gathered then reads the whole lists from the host segment all ranks wrote into
+        kw = dict(update_flags=fb.UPDATE_ALL, frusta=frusta, readback_visible=True, async_=pipelined, allgather=(world > 1))
         if anim:
             pi, pm = anim[i & 1]
             kw.update(changed_idx=pi.ptr, n_changed=n_bones, **{UPLOAD_FIELD[args.upload]: pm.ptr})
@@ -468,7 +505,7 @@ def run_cuda(args):
 
     def collect_e2e():
         for f in range(len(frusta)):
-            v = ctx.get_visible_gathered(f, copy=False) if (world > 1 and (rank == 0 or not own_lists[0])) else ctx.get_visible(f, copy=False)
+            v = ctx.get_visible_gathered(f, copy=False) if world > 1 else ctx.get_visible(f, copy=False)
             vis_counts[f] = v.size
 
     def step_e2e(i):
@@ -476,26 +513,24 @@ def run_cuda(args):
         submit_e2e(i, False)
         collect_e2e()
 
-    def run_e2e_pipelined(steps):
+    def run_e2e_pipelined(n):
         """The same K frames, two in flight (FYX_FRAME_ASYNC + fyx_frame_wait): the upload of frame i+1 and
         the read-back of frame i-1 overlap the kernels of frame i.  Every frame's inputs still travel
         host->device and every frame's visible lists device->host inside the timed region."""
-        own_lists[0] = world > 1 and rank != 0
         submit_e2e(0, True)
-        for i in range(1, steps):
+        for i in range(1, n):
             submit_e2e(i, True)
             ctx.frame_wait()
             collect_e2e()
         ctx.frame_wait()
         collect_e2e()
-        own_lists[0] = False
 
-    def timed(fn, steps, pass_index=False):
+    def timed(fn, n, pass_index=False):
         barrier()
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        for i in range(steps):
+        for i in range(n):
             fn(i) if pass_index else fn()
         e1.record()
         torch.cuda.synchronize()
@@ -516,26 +551,28 @@ def run_cuda(args):
     if rank == 0:
         clocks.start()
     launches0 = ctx.kernel_launch_count()
-    total_ms = timed(step_device, args.steps)
+    total_ms = timed(step_device, steps)
     launches = ctx.kernel_launch_count() - launches0
-    e2e_sync_ms = timed(step_e2e, args.steps, pass_index=True)
+    e2e_sync_ms = timed(step_e2e, steps, pass_index=True) if full else None
     for _ in range(2):
         run_e2e_pipelined(3)
-    e2e_pipe_ms = timed(lambda: run_e2e_pipelined(args.steps), 1)
-    e2e_ms = min(e2e_sync_ms, e2e_pipe_ms)
-    # per-stage device durations (CUDA events on the launching stream, inside fyx_render_prep), same K frames
+    e2e_pipe_ms = timed(lambda: run_e2e_pipelined(steps), 1)
+    e2e_ms = e2e_pipe_ms if e2e_sync_ms is None else min(e2e_sync_ms, e2e_pipe_ms)
+    # per-stage device durations: a SEPARATE pass of synchronous frames (CUDA events between the kernels, recorded
+    # inside fyx_render_prep on the launching stream).  Their sum exceeds ms_per_step: the timed frames above are
+    # asynchronous, record no mid-frame events and overlap each kernel's prologue with its predecessor's tail (PDL).
     stage = {"update_ms": 0.0, "palette_ms": 0.0, "skin_ms": 0.0}
-    for i in range(args.steps):
+    for i in range(steps):
         ctx.render_prep(update_flags=fb.UPDATE_ALL, frusta=frusta, readback_visible=False)
         t = ctx.timings()
         for k in stage:
-            stage[k] += t[k] / args.steps
+            stage[k] += t[k] / steps
     # second mode BASELINE.md asks for: "static + skeletons" — only the bones change (uploaded every frame),
     # Graph::update semantics (FYX_UPDATE_INCREMENTAL): clean sub-trees keep their matrices / boxes, everything is culled
     inc_ms = None
-    if anim and world == 1:
-        def inc_frames(steps):
-            for i in range(steps):
+    if full and anim and world == 1:
+        def inc_frames(n):
+            for i in range(n):
                 pi, pm = anim[i & 1]
                 kw = {UPLOAD_FIELD[args.upload]: pm.ptr}
                 ctx.render_prep(update_flags=fb.UPDATE_INCREMENTAL, changed_idx=pi.ptr, n_changed=n_bones, frusta=frusta,
@@ -544,22 +581,30 @@ def run_cuda(args):
                     ctx.frame_wait()
             ctx.frame_wait()
         inc_frames(3)
-        inc_ms = timed(lambda: inc_frames(args.steps), 1) / args.steps
+        inc_ms = timed(lambda: inc_frames(steps), 1) / steps
     # third mode (N2): the animation players run on the device — the bones' rotation curves are resident in HBM, every
     # frame samples them (fyx_render_prep do_animate), nothing is uploaded; the visible lists still come down
     dev_anim = None
-    if anim and world == 1 and not args.no_device_animation:
-        dev_anim = device_animation_mode(ctx, sc, fb, frusta, n_bones, args.steps, timed, log)
+    if full and anim and world == 1 and not args.no_device_animation:
+        dev_anim = device_animation_mode(ctx, sc, fb, frusta, n_bones, steps, timed, log)
     clk = clocks.stop() if rank == 0 else None
 
-    ms_per_step = total_ms / args.steps
-    e2e_ms_per_step = e2e_ms / args.steps
-    units_all = (w["nodes"] + w["units"] * w["verts_per_unit"]) * world  # whole job
-    value = units_all / (ms_per_step * 1e-3)
-    e2e_value = units_all / (e2e_ms_per_step * 1e-3)
+    parity = None
+    if not args.no_parity:
+        try:
+            parity = parity_block(ctx, sc, fb, frusta, args.upload, world, rank, dist, log)
+        except Exception as ex:  # reported, never hidden: a failed check is a failed check
+            parity = {"ok": False, "error": repr(ex)}
+            if world > 1:
+                raise
+
+    ms_per_step = total_ms / steps
+    e2e_ms_per_step = e2e_ms / steps
+    units_all = (w["nodes"] + w["units"] * w["verts_per_unit"]) * mult  # whole job
     sum_vis = sum(vis_counts)
+    own_vis = sum(int(ctx.get_visible(f, copy=False).size) for f in range(len(frusta))) if not args.no_parity else sum_vis // world
     h2d = n_bones * (UPLOAD_BYTES[args.upload] + 4)  # frusta travel as kernel parameters
-    d2h = 4 * len(frusta) + 4 * sum_vis  # rank 0: at N > 1 it reads back the whole gathered lists, the other ranks their own
+    d2h = 4 * len(frusta) + 4 * own_vis  # every rank brings its own lists down (N > 1: into the host segment all ranks share)
 
     peak, peak_src = peaks()
     # dominant kernel: k_skin when the workload skins, else the fused update+cull level kernels
@@ -567,50 +612,127 @@ def run_cuda(args):
     if n_local_verts:
         g = B_VERT * n_local_verts / (stage["skin_ms"] * 1e-3) / 1e9
         stages["k_skin"] = {"ms": stage["skin_ms"], "algorithmic_bytes": B_VERT * n_local_verts, "GBps": g, "frac": g / peak}
-    own_vis = sum_vis if world == 1 else None
-    upd_bytes = B_NODE_FUSED * n_local_nodes + (B_VISIBLE * sum_vis // world)
+    upd_bytes = B_NODE_FUSED * n_local_nodes + B_VISIBLE * own_vis
     g = upd_bytes / (stage["update_ms"] * 1e-3) / 1e9
     stages["k_update_level+cull"] = {"ms": stage["update_ms"], "algorithmic_bytes": upd_bytes, "GBps": g, "frac": g / peak}
     if n_bones:
         g = B_BONE * n_bones / max(stage["palette_ms"], 1e-6) / 1e-3 / 1e9
         stages["k_palette"] = {"ms": stage["palette_ms"], "algorithmic_bytes": B_BONE * n_bones, "GBps": g, "frac": g / peak}
-    upd_key = [k for k in stages if k.startswith("k_update")][0]
-    dom = "k_skin" if n_local_verts and stage["skin_ms"] >= stage["update_ms"] else upd_key
+    dom = "k_skin" if n_local_verts and stage["skin_ms"] >= stage["update_ms"] else "k_update_level+cull"
     traffic = None
     tpath = os.path.join(REPO, "profiles", "ncu_traffic.json")
     if os.path.exists(tpath):
         try:
-            tj = json.load(open(tpath))
-            ent = tj.get(args.workload, {}).get("k_skin" if dom == "k_skin" else "k_update_level+cull")
+            ent = json.load(open(tpath)).get(wname, {}).get(dom)
             traffic = ent.get("dram_bytes_per_launch") if ent else None
         except Exception:
             traffic = None
     roofline = {"bound": "hbm", "kernel": dom, "achieved": stages[dom]["GBps"], "peak": peak, "unit": "GB/s", "frac": stages[dom]["frac"],
-                "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": stages[dom]["algorithmic_bytes"], "stages": stages}
+                "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": stages[dom]["algorithmic_bytes"], "stages": stages,
+                "stages_note": "stage times come from a separate pass of synchronous frames with events between the kernels; "
+                               "ms_per_step is timed on asynchronous frames without them (PDL overlap), so the stage sum exceeds it"}
+    res = dict(w=w, world=world, strong=strong, steps=steps, ms_per_step=ms_per_step, e2e_ms_per_step=e2e_ms_per_step,
+               e2e_sync_ms=None if e2e_sync_ms is None else e2e_sync_ms / steps, e2e_pipe_ms=e2e_pipe_ms / steps, units_all=units_all,
+               sum_vis=sum_vis, own_vis=own_vis, h2d=h2d, d2h=d2h, launches=int(launches), roofline=roofline, clocks=clk, parity=parity,
+               inc_ms=inc_ms, dev_anim=dev_anim, frusta=len(frusta), n_local_nodes=n_local_nodes, n_local_verts=n_local_verts,
+               exchange=ctx.comm_mode() if world > 1 else None)
+    for pi, pm in anim:
+        pi.free()
+        pm.free()
+    ctx.close()
+    sc.close()
+    torch.cuda.empty_cache()
+    return res
+
+
+def run_cuda(args):
+    import torch
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    if args.gpus > 1 and world == 1:
+        raise SystemExit("launch N>1 with torchrun (one process per GPU)")
+    if not torch.cuda.is_available():
+        raise SystemExit("no CUDA device: bench.py has no CPU fallback for the CUDA arm (use --impl reference for the CPU baseline)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def log(msg):
+        if rank == 0 and args.verbose:
+            print("[bench]", msg, file=sys.stderr, flush=True)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+
+    from fyrox_b200 import scenegen as _sg
+    _sg.set_threads(max(1, (os.cpu_count() or 8) // max(world, 1)))  # torchrun exports OMP_NUM_THREADS=1
+    # the contexts launch on an explicit torch stream so that torch.cuda.Event brackets exactly their work
+    tstream = torch.cuda.Stream(device=local_rank)
+    torch.cuda.set_stream(tstream)
+    assert tstream.cuda_stream != 0
+    env = dict(rank=rank, world=world, local_rank=local_rank, dist=dist, log=log, barrier=barrier, tstream=tstream)
+
+    w = WORKLOADS[args.workload]
+    strong_main = args.workload == "C5"
+    r = measure(args, args.workload, strong_main, args.steps, env, full=True)
+    # BASELINE.json configs[4] / north_star: the 100 M-node config, STRONG scaling (the whole job is fixed, sharded N ways)
+    c5 = None
+    if args.workload == "C4" and not args.no_c5:
+        try:
+            c5 = measure(args, "C5", True, max(3, min(args.steps, 10)), env, full=False)
+        except Exception as ex:
+            if world > 1:
+                raise
+            c5 = {"error": repr(ex)}
 
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return 0
 
+    ms_per_step, e2e_ms_per_step = r["ms_per_step"], r["e2e_ms_per_step"]
+    value = r["units_all"] / (ms_per_step * 1e-3)
+    mult = 1 if strong_main else world
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": args.workload, "desc": w["desc"], "nodes_per_gpu": w["nodes"], "skinned_meshes_per_gpu": w["units"],
-                   "bones_per_mesh": BONES, "verts_per_mesh": w["verts_per_unit"], "skinned_verts_per_gpu": w["units"] * w["verts_per_unit"],
-                   "frusta": len(frusta), "update": "all-dirty (every node recomputed)", "parallelism": f"shard{world}" if world > 1 else "single",
-                   "l2": "inputs larger than L2 (node columns + vertex streams >> 126 MB); no flush needed", "visible_entries": sum_vis},
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong" if strong_main else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": args.workload, "desc": w["desc"], "nodes_per_gpu": r["n_local_nodes"], "skinned_meshes_per_gpu": w["units"] * mult // world,
+                   "bones_per_mesh": BONES, "verts_per_mesh": w["verts_per_unit"], "skinned_verts_per_gpu": r["n_local_verts"],
+                   "frusta": r["frusta"], "update": "all-dirty (every node recomputed)", "parallelism": f"shard{world}" if world > 1 else "single",
+                   "l2": "inputs larger than L2 (node columns + vertex streams >> 126 MB); no flush needed", "visible_entries": r["sum_vis"],
+                   "exchange": r["exchange"]},
         "fps": 1e3 / ms_per_step,
-        "nodes_per_s": w["nodes"] * world / (ms_per_step * 1e-3), "verts_per_s": w["units"] * w["verts_per_unit"] * world / (ms_per_step * 1e-3),
-        "clocks": clk,
-        "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms_per_step, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "api": "fyx_render_prep (C ABI) with pinned host buffers: changed bone " + {"rot": "rotations (16 B)", "trs": "TRS records (40 B)", "m16": "matrices (64 B)"}[args.upload] + " up, visible lists down",
-                "mode": "pipelined (2 frames in flight, fyx_frame_wait)" if e2e_pipe_ms < e2e_sync_ms else "synchronous",
-                "ms_per_step_synchronous": e2e_sync_ms / args.steps, "ms_per_step_pipelined": e2e_pipe_ms / args.steps},
-        "gpu_launches": int(launches),
-        "roofline": roofline,
-        "modes": {"all_dirty_ms_per_step": ms_per_step, "static_plus_skeletons_e2e_ms_per_step": inc_ms, "device_animation": dev_anim},
+        "nodes_per_s": w["nodes"] * mult / (ms_per_step * 1e-3), "verts_per_s": w["units"] * w["verts_per_unit"] * mult / (ms_per_step * 1e-3),
+        "clocks": r["clocks"],
+        "e2e": {"value": r["units_all"] / (e2e_ms_per_step * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms_per_step, "h2d_bytes_per_step": r["h2d"], "d2h_bytes_per_step": r["d2h"],
+                "api": "fyx_render_prep (C ABI) with pinned host buffers: changed bone " + {"rot": "rotations (16 B)", "trs": "TRS records (40 B)", "m16": "matrices (64 B)"}[args.upload] + " up, visible lists down"
+                       + ("; per rank: its own lists, into the host segment every rank shares (rank 0 reads the whole lists there)" if world > 1 else ""),
+                "mode": "pipelined (2 frames in flight, fyx_frame_wait)" if r["e2e_sync_ms"] is None or r["e2e_pipe_ms"] < r["e2e_sync_ms"] else "synchronous",
+                "ms_per_step_synchronous": r["e2e_sync_ms"], "ms_per_step_pipelined": r["e2e_pipe_ms"],
+                "consumer": "visible lists on the host; palettes and skinned streams stay device-resident (the consumer of seam S3 is assumed to be on the GPU)"},
+        "gpu_launches": r["launches"],
+        "roofline": r["roofline"],
+        "parity": r["parity"],
+        "modes": {"all_dirty_ms_per_step": ms_per_step, "static_plus_skeletons_e2e_ms_per_step": r["inc_ms"], "device_animation": r["dev_anim"]},
     }
+    if c5 is not None:
+        if "error" in c5:
+            line["modes"]["strong_C5"] = c5
+        else:
+            line["modes"]["strong_C5"] = {
+                "workload": "C5", "desc": WORKLOADS["C5"]["desc"], "scaling": "strong", "n_gpus": world, "steps": c5["steps"],
+                "ms_per_step": c5["ms_per_step"], "value": c5["units_all"] / (c5["ms_per_step"] * 1e-3), "unit": UNIT,
+                "e2e_ms_per_step": c5["e2e_ms_per_step"], "e2e_value": c5["units_all"] / (c5["e2e_ms_per_step"] * 1e-3),
+                "h2d_bytes_per_step": c5["h2d"], "d2h_bytes_per_step": c5["d2h"], "nodes_per_gpu": c5["n_local_nodes"], "skinned_verts_per_gpu": c5["n_local_verts"],
+                "visible_entries": c5["sum_vis"], "gpu_launches": c5["launches"], "roofline_stages": c5["roofline"]["stages"], "parity": c5["parity"],
+                "exchange": c5["exchange"],
+                "note": "whole job = 100 M nodes + 1 G skinned vertices + 6 frusta whatever N is; speed-up at N GPUs = this value / the N=1 line's value"}
     if world == 1 and not args.no_cpu_baseline:
         try:
             sample = cpu_sample_config(w)
@@ -646,6 +768,8 @@ def main():
     ap.add_argument("--upload", default="rot", choices=["rot", "trs", "m16"], help="per-frame upload format of the changed bones")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-device-animation", action="store_true", help="skip the extra mode that samples the bones' animation curves on the device")
+    ap.add_argument("--no-parity", action="store_true", help="skip the sampled-oracle check that follows the timed regions")
+    ap.add_argument("--no-c5", action="store_true", help="skip the strong-scaling C5 measurement that follows the default C4 workload")
     ap.add_argument("--verbose", action="store_true")
     args = ap.parse_args()
     # OpenMP workers (scene generator, multi-core CPU baseline) that wait at a barrier should sleep, not spin: the host is

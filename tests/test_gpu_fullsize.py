@@ -142,3 +142,48 @@ def test_skinning_at_scale_sampled(ctx):
     ctx.skin()
     for u, ref in zip((5, 1000, 1500), chk):
         assert ctx.get_skinned(sids[u])[0].tobytes() == ref.tobytes()
+
+
+def _full_config(ctx, nodes, units, n_frusta, upload):
+    """Load a BASELINE.json config exactly as bench.py does (same generator, seed, loader), run one all-dirty frame and
+    check it with the sampled oracle (tests/sampled_parity.py): >= 5 000 nodes + 4 skinned meshes, bit for bit."""
+    import sys
+
+    import sampled_parity as sp
+
+    sys.path.insert(0, __import__("os").path.dirname(__import__("os").path.dirname(__import__("os").path.abspath(__file__))))
+    import bench
+
+    sc = Scene(nodes, n_units=units, verts_per_unit=5000, bones_per_unit=64, seed=bench.SEED)
+    bench.load_scene(ctx, sc, fb, lambda m: None)
+    ffs = [camera.camera_frustum()] if n_frusta == 1 else camera.cube_frusta()[:n_frusta]
+    fos = bench.oracle_frusta(n_frusta)
+    idx, trs = sc.animate_trs(0)
+    if upload == "rot":
+        ctx.set_local_trs(trs, idx)  # the device keeps position / scale; the frame uploads rotations only
+        idx, trs = sc.animate_trs(1)
+    out, res = sp.check_frame(ctx, sc, ffs, fos, upload, idx, trs, seed=11)
+    assert out["checked_nodes"] >= 5000 and out["checked_units"] >= 3, out
+    assert out["ok"], out
+    assert out["max_abs_pos_err"] <= 1e-5  # north_star's tolerance; the compare above is bit-exact
+    assert 0 < out["visible_entries_own"]
+    # the one-call frame and the separate calls agree on every list (size-independent property)
+    one = [np.sort(ctx.get_visible(f)) for f in range(n_frusta)]
+    ctx.update_and_cull(ffs, fb.UPDATE_ALL)
+    for f in range(n_frusta):
+        assert np.array_equal(np.sort(ctx.get_visible(f)), one[f])
+    sc.close()
+    return out
+
+
+@pytest.mark.timeout(900)
+def test_c3_full(ctx):
+    """configs[2]: 1 M nodes incl. 10 k skinned meshes x 64 bones x 5 k verts (50 M verts), 1 frustum — at its own size."""
+    _full_config(ctx, 1_000_000, 10_000, 1, "trs")
+
+
+@pytest.mark.timeout(1200)
+def test_c4_full(ctx):
+    """configs[3] (the BENCH config): 10 M nodes, 50 k skinned meshes (250 M verts), 6 cube-face frusta — at its own size,
+    with the bench's default upload format (16-byte rotations)."""
+    _full_config(ctx, 10_000_000, 50_000, 6, "rot")
