@@ -47,6 +47,7 @@ PASS_SHADOW = 1
 FRAME_ASYNC = 1
 FRAME_ALLGATHER = 2
 FRAME_READBACK_OWN = 4
+COMM_NCCL, COMM_PEER_STORES, COMM_HOST_SEGMENT, COMM_UNDECIDED = 1, 2, 4, 8
 
 u32p = C.POINTER(C.c_uint32)
 f32p = C.POINTER(C.c_float)
@@ -221,6 +222,7 @@ SYMBOLS = {
     "fyx_comm_get_unique_id": (C.c_int32, [C.c_void_p]),
     "fyx_comm_init": (C.c_int32, [ctx_p, C.c_int32, C.c_int32, C.c_void_p]),
     "fyx_allgather_visible": (C.c_int32, [ctx_p]),
+    "fyx_comm_mode": (C.c_uint32, [ctx_p]),
     "fyx_get_visible_gathered": (C.c_int32, [ctx_p, C.c_uint32, C.POINTER(u32p), u32p]),
     "fyx_get_visible_gathered_device": (C.c_int32, [ctx_p, C.c_uint32, C.POINTER(C.c_void_p), u32p]),
 }

@@ -515,6 +515,17 @@ class Context:
         assert len(uid) == 128
         self._chk(self._lib.fyx_comm_init(self._h, nranks, rank, C.create_string_buffer(uid, 128)))
 
+    def comm_mode(self) -> str:
+        """How the visible lists are exchanged (fyx_comm_mode): decided collectively at the first gathered frame."""
+        m = int(self._lib.fyx_comm_mode(self._h))
+        if not m:
+            return "none"
+        if m & L.COMM_UNDECIDED:
+            return "nccl initialised, exchange not built yet"
+        dev = "peer stores over NVLink (cudaIpc)" if m & L.COMM_PEER_STORES else "ncclAllGather (counts, padded slots, pack kernels)"
+        host = "node-wide host segment (each rank copies its own lists)" if m & L.COMM_HOST_SEGMENT else "private copy of the gathered device lists per rank"
+        return f"device: {dev}; host: {host}"
+
     def allgather_visible(self):
         self._chk(self._lib.fyx_allgather_visible(self._h))
 

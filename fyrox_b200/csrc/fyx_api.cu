@@ -10,6 +10,7 @@
 #include <string>
 #include <vector>
 
+#include "fyx_hostseg.hpp"
 #include "fyx_internal.h"
 
 using namespace fyx;
@@ -57,7 +58,16 @@ struct VisSlot {
     size_t h_gath_cap[FYX_MAX_FRUSTA] = {};
     bool gathered = false, gathered_on_host = false;
     bool own_only = false; // FYX_FRAME_READBACK_OWN: the host copy of this frame is the rank's own lists
-    cudaEvent_t ev_gather = nullptr;
+    cudaEvent_t ev_gather = nullptr, ev_counts_all = nullptr;
+    uint64_t epoch = 0;            // number of this gathered frame (the same on every rank)
+    bool via_peer = false;         // exchanged by peer stores (fyx_peer.cu), else NCCL
+    uint32_t *gath_ptr[FYX_MAX_FRUSTA] = {}; // the gathered list on the device (peer allocation or b_gath)
+    uint32_t counts_all[kPeerMaxRanks][FYX_MAX_FRUSTA] = {};
+    bool counts_all_known = false;
+    // host copy of the gathered lists through the node-wide segment (fyx_hostseg.hpp)
+    bool host_copy_private = false; // the frame did not ask for a read-back: a later fetch copies the device list privately
+    bool seg_published = false, seg_complete = false, own_in_seg = false;
+    uint32_t *seg_own[FYX_MAX_FRUSTA] = {};
     bool pending = false; // written by a pipelined (async + read-back) frame that fyx_frame_wait has not collected yet
     uint64_t frame_no = 0;
     cudaEvent_t ev_cull = nullptr, ev_counts = nullptr, ev_done = nullptr;
@@ -79,6 +89,15 @@ struct InstOut {
 };
 
 } // namespace
+
+struct PeerState {
+    void *local = nullptr;                 // this rank's exchange allocation (control block + 2 x F lists)
+    void *mapped[kPeerMaxRanks] = {};      // the other ranks' allocations (cudaIpcOpenMemHandle)
+    uint32_t *cta_done = nullptr;
+    uint32_t *h_counts = nullptr;          // pinned: [epoch & 1][2][rank][frustum] copy of the count table
+    PeerParams pp{};
+    bool ready = false;
+};
 
 struct fyx_ctx {
     int device = 0;
@@ -182,6 +201,14 @@ struct fyx_ctx {
     cudaStream_t comm_stream = nullptr; // the collective runs beside the palette / skinning kernels (highest priority)
     DevBuf b_counts_packed, b_counts_all;
     uint32_t *h_counts_all = nullptr; // pinned nranks*FYX_MAX_FRUSTA
+    bool want_peer = true, want_hostseg = true;
+    bool exchange_built = false, hostseg_ready = false, hostseg_registered = false;
+    uint32_t exchange_slots = 0, exch_nf_cap = 0;
+    uint64_t exch_total_cap = 0, gather_epoch = 0;
+    PeerState peer;
+    HostSeg hostseg;
+    cudaEvent_t ev_gath_read[2] = {}; // private D2H copies of the gathered device lists (per epoch parity)
+    bool gath_read_valid[2] = {false, false};
 };
 
 namespace {
@@ -307,6 +334,7 @@ int32_t check_device_errors(fyx_ctx *c)
         return fail(c, FYX_ERR_NOT_AFFINE, "a matrix with a bottom row other than (0,0,0,1) or a non-finite entry was skipped");
     if (e & E_BAD_BONE_INDEX) return fail(c, FYX_ERR_INVALID_ARGUMENT, "a vertex references a bone index >= n_bones");
     if (e & E_NONFINITE_VERTEX) return fail(c, FYX_ERR_INVALID_ARGUMENT, "a vertex position is not finite");
+    if (e & E_PEER_TIMEOUT) return fail(c, FYX_ERR_NCCL, "the peer exchange of the visible lists timed out: a rank did not take part in the frame");
     return FYX_OK;
 }
 
@@ -338,6 +366,7 @@ void rebuild_node_arrays(fyx_ctx *c)
 void to_dev_frustum(const fyx_frustum &f, uint32_t cam_mask, uint32_t pass_flags, FrustumDev &d)
 {
     for (int p = 0; p < 6; ++p) d.plane[p] = make_float4(f.planes[p][0], f.planes[p][1], f.planes[p][2], f.planes[p][3]);
+    for (int i = 0; i < 8; ++i) d.corner[i] = make_float4(f.corners[i][0], f.corners[i][1], f.corners[i][2], 0.0f);
     for (int q = 0; q < 3; ++q)
         for (int k = 0; k < 4; ++k) d.pn[q][k] = make_float2(f.planes[2 * q][k], f.planes[2 * q + 1][k]);
     // distinct corner coordinates per axis (bit-pattern equality, so -0/+0 and NaNs stay separate entries:
@@ -407,6 +436,7 @@ int32_t prepare_cull(fyx_ctx *c, uint32_t nf, const fyx_frustum *fr, const uint3
     V.nf = nf;
     V.counts_on_host = V.lists_on_host = false;
     V.gathered = V.gathered_on_host = false;
+    V.seg_published = V.seg_complete = V.own_in_seg = V.counts_all_known = V.host_copy_private = false;
     c->readable = slot;
     return FYX_OK;
 }
@@ -551,7 +581,9 @@ extern "C" int32_t fyx_create(const fyx_config *cfg, fyx_ctx **out_ctx)
         CUB(cudaEventCreateWithFlags(&V.ev_counts, cudaEventDisableTiming));
         CUB(cudaEventCreateWithFlags(&V.ev_done, cudaEventDisableTiming));
         CUB(cudaEventCreateWithFlags(&V.ev_gather, cudaEventDisableTiming));
+        CUB(cudaEventCreateWithFlags(&V.ev_counts_all, cudaEventDisableTiming));
     }
+    for (int i = 0; i < 2; ++i) CUB(cudaEventCreateWithFlags(&c->ev_gath_read[i], cudaEventDisableTiming));
     CUB(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
     CUB(cudaStreamCreateWithFlags(&c->d2h_stream, cudaStreamNonBlocking));
     for (int i = 0; i < 2; ++i) {
@@ -570,8 +602,10 @@ static bool lod_active(const fyx_ctx *c, uint32_t nf);  // fyx_drawprep.inl
 static int32_t lod_pass(fyx_ctx *c);                    // fyx_drawprep.inl
 namespace { void anim_free(fyx_ctx *c); }              // fyx_anim.inl
 static int32_t animate_enqueue(fyx_ctx *c, float dt);  // fyx_anim.inl
-static int32_t allgather_begin(fyx_ctx *c, VisSlot &V, cudaStream_t s);
+static int32_t allgather_enqueue(fyx_ctx *c, VisSlot &V, cudaStream_t s);
 static int32_t allgather_finish(fyx_ctx *c, VisSlot &V, cudaStream_t s);
+static int32_t hostseg_publish(fyx_ctx *c, VisSlot &V, cudaStream_t s);
+static int32_t resolve_counts(fyx_ctx *c, VisSlot &V);
 
 extern "C" void fyx_destroy(fyx_ctx *c)
 {
@@ -603,6 +637,7 @@ extern "C" void fyx_destroy(fyx_ctx *c)
             if (V.h_gath[f]) cudaFreeHost(V.h_gath[f]);
         }
         if (V.ev_gather) cudaEventDestroy(V.ev_gather);
+        if (V.ev_counts_all) cudaEventDestroy(V.ev_counts_all);
         if (V.d_counts) cudaFree(V.d_counts);
         if (V.h_counts) cudaFreeHost(V.h_counts);
         if (V.ev_cull) cudaEventDestroy(V.ev_cull);
@@ -616,6 +651,8 @@ extern "C" void fyx_destroy(fyx_ctx *c)
     }
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     if (c->d2h_stream) cudaStreamDestroy(c->d2h_stream);
+    for (int i = 0; i < 2; ++i)
+        if (c->ev_gath_read[i]) cudaEventDestroy(c->ev_gath_read[i]);
     if (c->d_err) cudaFree(c->d_err);
     if (c->h_err) cudaFreeHost(c->h_err);
     if (c->h_counts_all) cudaFreeHost(c->h_counts_all);
@@ -1351,7 +1388,7 @@ extern "C" int32_t fyx_get_visible(fyx_ctx *c, uint32_t f, const uint32_t **out_
     CU(cudaSetDevice(c->device));
     int32_t rc = readback_visible(c, V, c->stream);
     if (rc) return rc;
-    *out_idx = V.h_vis[f];
+    *out_idx = V.own_in_seg ? V.seg_own[f] : V.h_vis[f]; // a gathered frame's own lists sit inside the node-wide host segment
     *out_count = V.h_counts[f];
     return FYX_OK;
 }
@@ -1509,7 +1546,8 @@ extern "C" int32_t fyx_render_prep(fyx_ctx *c, const fyx_frame_desc *fr)
         if (!c->comm) return fail(c, FYX_ERR_STATE, "FYX_FRAME_ALLGATHER without fyx_comm_init");
         CU(cudaStreamWaitEvent(c->comm_stream, c->vs[c->cur].ev_cull, 0));
         if (c->vs[c->cur ^ 1].gathered) CU(cudaStreamWaitEvent(c->comm_stream, c->vs[c->cur ^ 1].ev_gather, 0)); // a stand-alone exchange of the previous frame
-        rc = allgather_begin(c, c->vs[c->cur], c->comm_stream);
+        c->vs[c->cur].host_copy_private = !fr->readback_visible; // nobody promised that every rank fetches this frame's lists
+        rc = allgather_enqueue(c, c->vs[c->cur], c->comm_stream);
         if (rc) return rc;
     }
     // 3. palettes, 4. skinning
@@ -1554,6 +1592,7 @@ extern "C" int32_t fyx_render_prep(fyx_ctx *c, const fyx_frame_desc *fr)
     }
     rc = sync_and_check(c);
     frame_timings_from_events(c);
+    if (!rc && gather && fr->readback_visible && c->hostseg_ready) rc = hostseg_publish(c, V, s); // every rank's part, without being asked
     return rc;
 }
 
@@ -1570,27 +1609,37 @@ extern "C" int32_t fyx_frame_wait(fyx_ctx *c)
     VisSlot &V = c->vs[slot];
     CU(cudaEventSynchronize(V.ev_counts));
     V.counts_on_host = true;
-    const bool own = !V.gathered || V.own_only;
+    const bool seg = V.gathered && c->hostseg_ready && !V.host_copy_private;
+    const bool own = !seg && (!V.gathered || V.own_only);
     for (uint32_t f = 0; f < V.nf && own; ++f) {
         const size_t n = V.h_counts[f];
         int32_t rc = host_list_ensure(c, V, f, n);
         if (rc) return rc;
         if (n) CU(cudaMemcpyAsync(V.h_vis[f], V.b_vis[f].p, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->d2h_stream));
     }
-    if (V.gathered && !V.own_only) { // multi-GPU frame: the host wants the whole (all-gathered) lists
+    if (seg) {
+        // multi-GPU frame: this rank's own lists go into the node-wide host segment at their offsets (every rank does the
+        // same over its own PCIe link); fyx_get_visible_gathered reads the whole lists there
+        int32_t rc = hostseg_publish(c, V, c->d2h_stream);
+        if (rc) return rc;
+    } else if (V.gathered && !V.own_only) { // no segment: the host wants the whole (all-gathered) lists from this rank's device
+        int32_t rc = resolve_counts(c, V);
+        if (rc) return rc;
         CU(cudaStreamWaitEvent(c->d2h_stream, V.ev_gather, 0));
         for (uint32_t f = 0; f < V.nf; ++f) {
             const size_t n = V.gath_count[f];
-            int32_t rc = host_gath_ensure(c, V, f, n);
+            rc = host_gath_ensure(c, V, f, n);
             if (rc) return rc;
-            if (n) CU(cudaMemcpyAsync(V.h_gath[f], V.b_gath[f].p, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->d2h_stream));
+            if (n) CU(cudaMemcpyAsync(V.h_gath[f], V.gath_ptr[f], n * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->d2h_stream));
         }
+        CU(cudaEventRecord(c->ev_gath_read[V.epoch & 1], c->d2h_stream));
+        c->gath_read_valid[V.epoch & 1] = true;
         V.gathered_on_host = true;
     }
     CU(cudaStreamWaitEvent(c->d2h_stream, V.ev_done, 0)); // the error word is final once the frame's last kernel ran
     CU(cudaMemcpyAsync(c->h_err, c->d_err, sizeof(uint32_t), cudaMemcpyDeviceToHost, c->d2h_stream));
     CU(cudaStreamSynchronize(c->d2h_stream));
-    V.lists_on_host = own;
+    V.lists_on_host = own || V.own_in_seg;
     V.pending = false;
     c->readable = slot;
     return check_device_errors(c);

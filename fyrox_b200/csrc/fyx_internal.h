@@ -181,9 +181,38 @@ void launch_or_u32(cudaStream_t s, uint32_t *p, uint32_t bits);
 void launch_compact_gathered(cudaStream_t s, const uint32_t *pad, uint32_t maxc, const uint32_t *counts_all, int nranks, int f,
                              uint32_t *dst);
 
+// ---- multi-GPU exchange by peer stores (fyx_peer.cu) ----
+constexpr int kPeerMaxRanks = 16;
+struct PeerCtrl { // lives at the start of every rank's exchange allocation; written by the peers
+    uint32_t counts[2][kPeerMaxRanks][FYX_MAX_FRUSTA]; // [epoch & 1][rank][frustum]
+    uint32_t cnt_flag[2][kPeerMaxRanks];               // epoch of rank r's last count publication
+    uint32_t done_flag[2][kPeerMaxRanks];              // epoch of rank r's last completed push into THIS rank's lists
+    uint32_t totals[2][FYX_MAX_FRUSTA];                // gathered count per frustum (written by k_peer_wait)
+};
+constexpr size_t kPeerCtrlBytes = 4096;
+static_assert(sizeof(PeerCtrl) <= kPeerCtrlBytes, "control block fits its page");
+struct PeerParams {
+    int nranks, rank, nf;
+    uint32_t epoch;
+    unsigned char *base[kPeerMaxRanks]; // every rank's exchange allocation as mapped into this process
+    uint64_t total_cap;                 // entries per (slot, frustum) list: all ranks' slots together
+    uint32_t nf_cap;
+    const uint32_t *own_list[FYX_MAX_FRUSTA];
+    const uint32_t *own_counts; // counts[f * kCountStride]
+    uint32_t *cta_done;
+    uint32_t *d_err;
+};
+__host__ __device__ inline PeerCtrl *peer_ctrl(const PeerParams &pp, int r) { return reinterpret_cast<PeerCtrl *>(pp.base[r]); }
+__host__ __device__ inline uint32_t *peer_list(const PeerParams &pp, int r, uint32_t slot, uint32_t f)
+{
+    return reinterpret_cast<uint32_t *>(pp.base[r] + kPeerCtrlBytes) + ((size_t)slot * pp.nf_cap + f) * pp.total_cap;
+}
+void launch_peer_exchange(cudaStream_t s, const PeerParams &pp, unsigned push_ctas);
+
 // error bits written by kernels into d_err
 constexpr uint32_t E_NOT_AFFINE = 1u;
 constexpr uint32_t E_BAD_BONE_INDEX = 2u;
 constexpr uint32_t E_NONFINITE_VERTEX = 4u;
+constexpr uint32_t E_PEER_TIMEOUT = 8u; // a rank never showed up in the peer exchange (bounded spin, fyx_peer.cu)
 
 } // namespace fyx

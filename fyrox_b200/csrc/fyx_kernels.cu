@@ -73,6 +73,109 @@ static void launch_pdl(void (*kernel)(Params...), unsigned grid, unsigned block,
 }
 
 // ------------------------------------------------------------------------------------------------
+// Warp-level pre-reject of whole frusta (the 6-frusta cull is instruction-issue-bound, not HBM-bound).
+//
+// Siblings sit in adjacent slots, so the 32 boxes of a warp are neighbours in the world and most frusta of a
+// multi-frustum call (five of six cube faces, typically) contain none of them.  The warp reduces its boxes to
+// their union U and tests U ONCE, with the work spread over the lanes: lane l < 3*nf evaluates plane pair
+// l%3 of frustum l/3 on U's max-corner, lane c (two rounds) tests frustum corner c against U.  Frustum f is
+// dead for the warp iff some plane rejects U and no corner of f lies in U; then every participating lane's
+// own test is false too, bit for bit:
+//   * cloud test: for a lane box B ⊆ U the operand picked per axis (min for a negative normal component, max
+//     otherwise) is never further along the normal than U's, products by the same constant and sums are
+//     monotone under round-to-nearest, so s_B <= s_U <= 0 on that plane — the lane's max-corner (hence all
+//     eight corners, frustum.rs:205-219) is behind it;
+//   * fallback (frustum.rs:236-242): a corner outside U on some axis (exact compares) is outside B on it.
+// Participating lanes = candidates with frustum culling on and a tame box (finite, ordered: the premise of
+// the max-corner form); everything else keeps its own per-lane test.  CPU check of the claim on random and
+// adversarial warps: tests/test_cull_trick_cpu.py.
+// ------------------------------------------------------------------------------------------------
+struct PrefTable {
+    float4 e[FYX_MAX_FRUSTA * 3][5];      // per (frustum, plane pair): pn[0..3] (2 float4), vsel[3][2] (6 u32), pad: 80 B stride = conflict-free LDS.128
+    float4 corner[FYX_MAX_FRUSTA * 8];
+};
+
+__device__ __forceinline__ void pref_fill(PrefTable &T, const CullParams &cp, const int nf)
+{
+    const int t = threadIdx.x;
+    if (t < 3 * nf) {
+        const int f = t / 3, q = t % 3;
+        const FrustumDev &F = cp.f[f];
+        T.e[t][0] = make_float4(F.pn[q][0].x, F.pn[q][0].y, F.pn[q][1].x, F.pn[q][1].y);
+        T.e[t][1] = make_float4(F.pn[q][2].x, F.pn[q][2].y, F.pn[q][3].x, F.pn[q][3].y);
+        T.e[t][2] = make_float4(__uint_as_float(F.vsel[q][0][0]), __uint_as_float(F.vsel[q][0][1]), __uint_as_float(F.vsel[q][1][0]),
+                                __uint_as_float(F.vsel[q][1][1]));
+        T.e[t][3] = make_float4(__uint_as_float(F.vsel[q][2][0]), __uint_as_float(F.vsel[q][2][1]), 0.f, 0.f);
+    }
+    const int c = t - 64;
+    if (c >= 0 && c < 8 * nf) T.corner[c] = cp.f[c >> 3].corner[c & 7];
+}
+
+__device__ __forceinline__ float warp_min_f32(const float v)
+{
+    float r;
+    asm volatile("redux.sync.min.f32 %0, %1, 0xffffffff;" : "=f"(r) : "f"(v));
+    return r;
+}
+__device__ __forceinline__ float warp_max_f32(const float v)
+{
+    float r;
+    asm volatile("redux.sync.max.f32 %0, %1, 0xffffffff;" : "=f"(r) : "f"(v));
+    return r;
+}
+
+// Must be called by all 32 lanes.  part: this lane's box takes part in the union.  Returns the frusta that are NOT
+// proven dead for the participating lanes (bit f).
+template <int NFT>
+__device__ __forceinline__ uint32_t warp_live_frusta(const bool part, const float2 wx, const float2 wy, const float2 wz, const int nf_rt,
+                                                     const PrefTable &T, const PackedConsts &kc)
+{
+    const int nf = (NFT > 0) ? NFT : nf_rt;
+    if (!__any_sync(0xFFFFFFFFu, part)) return 0u; // nobody needs a geometric test
+    const float inf = __int_as_float(0x7f800000);
+    const float ulx = warp_min_f32(part ? wx.x : inf), uhx = warp_max_f32(part ? wx.y : -inf);
+    const float uly = warp_min_f32(part ? wy.x : inf), uhy = warp_max_f32(part ? wy.y : -inf);
+    const float ulz = warp_min_f32(part ? wz.x : inf), uhz = warp_max_f32(part ? wz.y : -inf);
+    const int lane = threadIdx.x & 31;
+    bool rej = false;
+    if (lane < 3 * nf) {
+        const float4 a = T.e[lane][0], b = T.e[lane][1], s0 = T.e[lane][2], s1 = T.e[lane][3];
+        const uint32_t xl = __float_as_uint(ulx), xh = __float_as_uint(uhx), yl = __float_as_uint(uly), yh = __float_as_uint(uhy),
+                       zl = __float_as_uint(ulz), zh = __float_as_uint(uhz);
+        const float2 vx = make_float2(pick(xl, xh, __float_as_uint(s0.x)), pick(xl, xh, __float_as_uint(s0.y)));
+        const float2 vy = make_float2(pick(yl, yh, __float_as_uint(s0.z)), pick(yl, yh, __float_as_uint(s0.w)));
+        const float2 vz = make_float2(pick(zl, zh, __float_as_uint(s1.x)), pick(zl, zh, __float_as_uint(s1.y)));
+        const float2 s = add2(add2(add2(mul2(make_float2(a.x, a.y), vx, kc), mul2(make_float2(a.z, a.w), vy, kc), kc),
+                                   mul2(make_float2(b.x, b.y), vz, kc), kc), make_float2(b.z, b.w), kc);
+        rej = (s.x <= 0.0f) | (s.y <= 0.0f);
+    }
+    const uint32_t rb = __ballot_sync(0xFFFFFFFFu, rej);
+    uint32_t live = 0u;
+    constexpr int kRounds = (NFT > 0) ? (8 * NFT + 31) / 32 : (8 * (int)FYX_MAX_FRUSTA + 31) / 32;
+#pragma unroll
+    for (int r = 0; r < kRounds; ++r) {
+        if (NFT == 0 && r * 4 >= nf) break;
+        const int c = lane + 32 * r;
+        bool in = false;
+        if (c < 8 * nf) {
+            const float4 k = T.corner[c];
+            in = (k.x >= ulx) & (k.x <= uhx) & (k.y >= uly) & (k.y <= uhy) & (k.z >= ulz) & (k.z <= uhz);
+        }
+        const uint32_t cb = __ballot_sync(0xFFFFFFFFu, in);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int f = 4 * r + j;
+            if (f < nf) {
+                const bool cloud_fail = ((rb >> (3 * f)) & 7u) != 0u;
+                const bool corner_in = ((cb >> (8 * j)) & 0xFFu) != 0u;
+                live |= (!cloud_fail || corner_in) ? (1u << f) : 0u;
+            }
+        }
+    }
+    return live;
+}
+
+// ------------------------------------------------------------------------------------------------
 // NodeTrait::should_be_rendered (scene/node/mod.rs:231-256) + the shadow-pass cast_shadows test of
 // Mesh::collect_render_data (scene/mesh/mod.rs:696-698) + reachability from Graph::root
 // (iterate_recursive, renderer/bundle.rs:988-1004), for every frustum of the call.  Bit f of the
@@ -80,22 +183,24 @@ static void launch_pdl(void (*kernel)(Params...), unsigned grid, unsigned block,
 // ------------------------------------------------------------------------------------------------
 // NFT: number of frusta known at compile time (the loop is unrolled and cp.f[f] becomes constant-bank operands of the
 // arithmetic instead of ~35 indexed parameter loads per frustum), 0 = run-time count.
+// live: frusta whose geometric test this lane still has to run (all ones without the warp-level pre-reject).
+constexpr uint32_t kNeedBits = FYX_NODE_ALIVE | FYX_NODE_RENDERABLE | FYX_NODE_REACHABLE | FYX_NODE_GLOBAL_VISIBILITY | FYX_NODE_GLOBAL_ENABLED;
+
 template <int NFT>
 __device__ __forceinline__ uint32_t cull_bits(const uint32_t nf, const uint32_t mask, const float2 wx, const float2 wy,
-                                              const float2 wz, const CullParams &cp)
+                                              const float2 wz, const CullParams &cp, const PackedConsts &kc, const bool tame, const uint32_t live)
 {
-    constexpr uint32_t need = FYX_NODE_ALIVE | FYX_NODE_RENDERABLE | FYX_NODE_REACHABLE | FYX_NODE_GLOBAL_VISIBILITY |
-                              FYX_NODE_GLOBAL_ENABLED;
-    if ((nf & need) != need) return 0u;
-    PackedConsts kc;
-    kc.one = make_float2(cp.one, cp.one);
-    kc.negzero = make_float2(cp.negzero, cp.negzero);
-    const bool tame = aabb_is_tame(wx, wy, wz);
+    if ((nf & kNeedBits) != kNeedBits) return 0u;
     uint32_t bits = 0u;
     auto one = [&](const int f) {
         bool ok = (mask & cp.f[f].cam_mask) != 0u;
         ok &= !((cp.f[f].pass_flags & FYX_PASS_SHADOW) && !(nf & FYX_NODE_CAST_SHADOWS));
-        if (ok && (nf & FYX_NODE_FRUSTUM_CULLING)) ok = frustum_intersects_aabb(cp.f[f], wx, wy, wz, kc, tame);
+        if (ok && (nf & FYX_NODE_FRUSTUM_CULLING)) {
+            // a frustum proven dead for the warp's union box needs no test — unless this lane's box is not tame (it took
+            // no part in the union)
+            if (((live >> f) & 1u) || !tame) ok = frustum_intersects_aabb(cp.f[f], wx, wy, wz, kc, tame);
+            else ok = false;
+        }
         bits |= ok ? (1u << f) : 0u;
     };
     if (NFT > 0) {
@@ -107,11 +212,30 @@ __device__ __forceinline__ uint32_t cull_bits(const uint32_t nf, const uint32_t 
     return bits;
 }
 
+// Per-warp part of the cull, called by all 32 lanes: cand = this lane holds a node that may be emitted at all.
+// PRE: warp-level pre-reject on.
+template <int NFT, bool PRE>
+__device__ __forceinline__ uint32_t cull_warp(const bool cand, const uint32_t nf, const uint32_t mask, const float2 wx, const float2 wy,
+                                              const float2 wz, const CullParams &cp, const PrefTable *T)
+{
+    PackedConsts kc;
+    kc.one = make_float2(cp.one, cp.one);
+    kc.negzero = make_float2(cp.negzero, cp.negzero);
+    const bool ok = cand && (nf & kNeedBits) == kNeedBits;
+    const bool tame = ok && aabb_is_tame(wx, wy, wz);
+    uint32_t live = 0xFFFFFFFFu;
+    if (PRE) live = warp_live_frusta<NFT>(tame && (nf & FYX_NODE_FRUSTUM_CULLING), wx, wy, wz, cp.nf, *T, kc);
+    return ok ? cull_bits<NFT>(nf, mask, wx, wy, wz, cp, kc, tame, live) : 0u;
+}
+
 // ------------------------------------------------------------------------------------------------
-// Block-wide compaction of the visible node indices: warp ballot + popc rank, one atomicAdd per
-// (CTA, frustum) on a counter that owns its own 128 B line.  Replaces the Vec pushes of
-// RenderDataBundleStorage::push (renderer/bundle.rs:1248-1278).  Order inside a list is unspecified.
-// Must be called by every thread of the CTA.
+// Compaction of the visible node indices.  Replaces the Vec pushes of RenderDataBundleStorage::push
+// (renderer/bundle.rs:1248-1278).  Order inside a list is unspecified.  Two forms:
+//  * CTA-wide: warp ballot + popc rank, per-warp counts in shared memory, one atomicAdd per (CTA, frustum);
+//  * warp-wide: one atomicAdd per (warp, frustum that has a visible lane) — no shared memory, no barriers, and
+//    frusta nobody in the warp is visible in cost nothing (the 6-frusta kernel is issue-bound: ~180 -> ~30
+//    instructions per warp); the counters sit on their own 128 B lines.
+// Both must be called by every thread of the CTA / warp.
 // ------------------------------------------------------------------------------------------------
 template <int NFT>
 __device__ __forceinline__ void compact_emit(const uint32_t vis_bits, const uint32_t node_index, const uint32_t slot,
@@ -155,6 +279,26 @@ __device__ __forceinline__ void compact_emit(const uint32_t vis_bits, const uint
     }
 }
 
+__device__ __forceinline__ void compact_emit_warp(const uint32_t vis_bits, const uint32_t node_index, const uint32_t slot, const CullParams &cp)
+{
+    uint32_t m = __reduce_or_sync(0xFFFFFFFFu, vis_bits); // frusta with a visible lane in this warp (uniform)
+    const uint32_t lane = threadIdx.x & 31u;
+    while (m) {
+        const int f = __ffs(m) - 1;
+        m &= m - 1u;
+        const uint32_t bit = (vis_bits >> f) & 1u;
+        const uint32_t b = __ballot_sync(0xFFFFFFFFu, bit);
+        uint32_t base = 0u;
+        if (lane == 0) base = atomicAdd(cp.counts + f * kCountStride, (uint32_t)__popc(b));
+        base = __shfl_sync(0xFFFFFFFFu, base, 0);
+        if (bit) {
+            const uint32_t pos = base + __popc(b & ((1u << lane) - 1u));
+            cp.out[f][pos] = node_index;
+            if (cp.out_slot[f]) cp.out_slot[f][pos] = slot;
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // One hierarchy level.  Replaces, for the nodes of this level:
 //   Graph::update_global_transform_recursively   scene/graph/mod.rs:1199-1241   (G = parent.G * local)
@@ -170,9 +314,9 @@ __device__ __forceinline__ void compact_emit(const uint32_t vis_bits, const uint
 // (A single cooperative launch walking all levels with grid-wide barriers was tried and rejected: the
 // persistent grid, L2-only parent loads and the barriers cost more than the launches they save —
 // C2 0.357 -> 0.416 ms, target 0.990 -> 1.051 ms per frame; profiles/README.md.)
-template <int NFT>
-__device__ __forceinline__ void update_node(const NodeArrays &a, const uint32_t slot, const uint32_t update_all, const CullParams &cp,
-                                            uint32_t &vis_bits, uint32_t &gi)
+template <bool WANT_BOX>
+__device__ __forceinline__ void update_node(const NodeArrays &a, const uint32_t slot, const uint32_t update_all, uint32_t &nf_out, float2 &wx,
+                                            float2 &wy, float2 &wz)
 {
     const uint32_t p = a.parent[slot]; // static column: may be read before the predecessor has finished
     pdl_wait(); // everything below reads what the previous level / a scatter kernel / the previous frame's tail wrote
@@ -188,8 +332,8 @@ __device__ __forceinline__ void update_node(const NodeArrays &a, const uint32_t 
     nf |= pf & FYX_NODE_REACHABLE;
     if (dirty) nf |= F_DIRTY;
     a.flags[slot] = nf;
+    nf_out = nf;
 
-    float2 wx, wy, wz;
     if (dirty) {
         Affine L;
         L.r0 = ld_stream(a.L[0] + slot);
@@ -217,49 +361,72 @@ __device__ __forceinline__ void update_node(const NodeArrays &a, const uint32_t 
         st_stream(a.wa[0] + slot, wx);
         st_stream(a.wa[1] + slot, wy);
         st_stream(a.wa[2] + slot, wz);
-    } else if ((NFT >= 0)) {
+    } else if (WANT_BOX) {
         wx = ld_stream(a.wa[0] + slot);
         wy = ld_stream(a.wa[1] + slot);
         wz = ld_stream(a.wa[2] + slot);
     }
-    if ((NFT >= 0) && !(nf & F_SKINNED)) {
-        vis_bits = cull_bits<(NFT > 0 ? NFT : 0)>(nf, a.mask[slot], wx, wy, wz, cp);
-        if (vis_bits) gi = a.gidx[slot];
-    }
 }
 
-template <int NFT>
+// VAR: bit 0 = warp-level pre-reject of whole frusta, bit 1 = warp-wide compaction (else CTA-wide)
+template <int NFT, int VAR>
 __global__ void __launch_bounds__(kBlock) k_update_level(const NodeArrays a, const uint32_t lo, const uint32_t hi,
                                                          const uint32_t update_all, const CullParams cp)
 {
     pdl_trigger();
+    constexpr bool PRE = (NFT >= 0) && (VAR & 1);
+    __shared__ __align__(16) unsigned char s_pref[PRE ? sizeof(PrefTable) : 16];
+    PrefTable *T = reinterpret_cast<PrefTable *>(s_pref);
+    if (PRE) {
+        pref_fill(*T, cp, NFT > 0 ? NFT : cp.nf);
+        __syncthreads();
+    }
     const uint32_t slot = lo + blockIdx.x * kBlock + threadIdx.x;
-    uint32_t vis_bits = 0u, gi = 0u;
-    if (slot < hi) update_node<NFT>(a, slot, update_all, cp, vis_bits, gi);
+    uint32_t nf = 0u;
+    float2 wx = make_float2(0.f, 0.f), wy = wx, wz = wx;
+    const bool valid = slot < hi;
+    if (valid) update_node<(NFT >= 0)>(a, slot, update_all, nf, wx, wy, wz);
     else pdl_wait();
-    if (NFT >= 0) compact_emit<(NFT > 0 ? NFT : 0)>(vis_bits, gi, slot, cp);
+    if (NFT >= 0) {
+        const bool cand = valid && !(nf & F_SKINNED);
+        const uint32_t mask = cand ? a.mask[slot] : 0u;
+        const uint32_t vis_bits = cull_warp<(NFT > 0 ? NFT : 0), PRE>(cand, nf, mask, wx, wy, wz, cp, T);
+        const uint32_t gi = vis_bits ? a.gidx[slot] : 0u;
+        if (VAR & 2) compact_emit_warp(vis_bits, gi, slot, cp);
+        else compact_emit<(NFT > 0 ? NFT : 0)>(vis_bits, gi, slot, cp);
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
 // Stand-alone cull over all slots (static scene / extra passes: every shadow pass re-runs the cull
 // with its own frustum, renderer/shadow/*.rs).  32 B read per node + 4 B per visible entry.
 // ------------------------------------------------------------------------------------------------
-template <int NFT>
+template <int NFT, int VAR>
 __global__ void __launch_bounds__(kBlock) k_cull(const NodeArrays a, const CullParams cp, const uint32_t *lodp)
 {
-    const uint32_t slot = blockIdx.x * kBlock + threadIdx.x;
-    uint32_t vis_bits = 0u, gi = 0u;
-    if (slot < a.cap) {
-        const uint32_t nf = a.flags[slot];
-        const uint32_t mask = a.mask[slot];
-        const float2 wx = ld_stream(a.wa[0] + slot);
-        const float2 wy = ld_stream(a.wa[1] + slot);
-        const float2 wz = ld_stream(a.wa[2] + slot);
-        vis_bits = cull_bits<NFT>(nf, mask, wx, wy, wz, cp);
-        if (lodp && vis_bits) vis_bits &= ~lodp[slot]; // frusta whose LOD filter hides the node or one of its ancestors
-        if (vis_bits) gi = a.gidx[slot];
+    constexpr bool PRE = (VAR & 1) != 0;
+    __shared__ __align__(16) unsigned char s_pref[PRE ? sizeof(PrefTable) : 16];
+    PrefTable *T = reinterpret_cast<PrefTable *>(s_pref);
+    if (PRE) {
+        pref_fill(*T, cp, NFT > 0 ? NFT : cp.nf);
+        __syncthreads();
     }
-    compact_emit<NFT>(vis_bits, gi, slot, cp);
+    const uint32_t slot = blockIdx.x * kBlock + threadIdx.x;
+    const bool valid = slot < a.cap;
+    uint32_t nf = 0u, mask = 0u;
+    float2 wx = make_float2(0.f, 0.f), wy = wx, wz = wx;
+    if (valid) {
+        nf = a.flags[slot];
+        mask = a.mask[slot];
+        wx = ld_stream(a.wa[0] + slot);
+        wy = ld_stream(a.wa[1] + slot);
+        wz = ld_stream(a.wa[2] + slot);
+    }
+    uint32_t vis_bits = cull_warp<NFT, PRE>(valid, nf, mask, wx, wy, wz, cp, T);
+    if (lodp && vis_bits) vis_bits &= ~lodp[slot]; // frusta whose LOD filter hides the node or one of its ancestors
+    const uint32_t gi = vis_bits ? a.gidx[slot] : 0u;
+    if (VAR & 2) compact_emit_warp(vis_bits, gi, slot, cp);
+    else compact_emit<NFT>(vis_bits, gi, slot, cp);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -358,7 +525,10 @@ __device__ __forceinline__ void fold_mesh(const NodeArrays &a, const FoldArrays 
         }
     }
     if ((NFT >= 0) && lane == 0) {
-        vis_bits = cull_bits<(NFT > 0 ? NFT : 0)>(nf, a.mask[slot], wx, wy, wz, cp);
+        PackedConsts kc;
+        kc.one = make_float2(cp.one, cp.one);
+        kc.negzero = make_float2(cp.negzero, cp.negzero);
+        vis_bits = cull_bits<(NFT > 0 ? NFT : 0)>(nf, a.mask[slot], wx, wy, wz, cp, kc, aabb_is_tame(wx, wy, wz), 0xFFFFFFFFu);
         if (vis_bits) gi = a.gidx[slot];
     }
 }
@@ -371,7 +541,7 @@ __global__ void __launch_bounds__(kBlock) k_fold_bones(const NodeArrays a, const
     const uint32_t i = (blockIdx.x * kBlock + threadIdx.x) >> 5; // mesh = warp
     uint32_t vis_bits = 0u, gi = 0u;
     if (i < fa.n) fold_mesh<NFT>(a, fa, i, threadIdx.x & 31u, cp, vis_bits, gi);
-    if (NFT >= 0) compact_emit<(NFT > 0 ? NFT : 0)>(vis_bits, gi, vis_bits ? fa.node_slot[i] : 0u, cp);
+    if (NFT >= 0) compact_emit_warp(vis_bits, gi, vis_bits ? fa.node_slot[i] : 0u, cp); // one mesh per warp: lane 0 holds the bits
 }
 
 // positions of the "late" bones (see FoldArrays) as stored before the update starts
@@ -816,24 +986,45 @@ __global__ void __launch_bounds__(kBlock) k_compact_gathered(const uint32_t *pad
 // ------------------------------------------------------------------------------------------------
 static inline unsigned grid_for(uint64_t n) { return (unsigned)((n + kBlock - 1) / kBlock); }
 
+// Cull variant (bit 0: warp-level pre-reject of whole frusta, bit 1: warp-wide compaction).  Default: both for
+// multi-frustum calls, compaction only for a single frustum; FYX_CULL_VARIANT=0..3 overrides (A/B measurements).
+static int cull_variant(int nf)
+{
+    static int forced = [] {
+        const char *e = getenv("FYX_CULL_VARIANT");
+        return (e && *e) ? atoi(e) & 3 : -1;
+    }();
+    if (forced >= 0) return forced;
+    return nf >= 2 ? 3 : 2;
+}
+
+#define FYX_DISPATCH_VAR(KERNEL, NF, VAR, ...)                                   \
+    switch (VAR) {                                                               \
+    case 0: launch_pdl(KERNEL<NF, 0>, __VA_ARGS__); break;                       \
+    case 1: launch_pdl(KERNEL<NF, 1>, __VA_ARGS__); break;                       \
+    case 2: launch_pdl(KERNEL<NF, 2>, __VA_ARGS__); break;                       \
+    default: launch_pdl(KERNEL<NF, 3>, __VA_ARGS__); break;                      \
+    }
+
 void launch_update_level(cudaStream_t s, const NodeArrays &a, uint32_t lo, uint32_t hi, bool update_all, const CullParams *cull)
 {
     if (hi <= lo) return;
     if (cull) {
         const unsigned g = grid_for(hi - lo);
         const uint32_t ua = update_all ? 1u : 0u;
+        const int var = cull_variant(cull->nf);
         switch (cull->nf) { // the usual frustum counts get an unrolled cull: camera, CSM cascades, cube faces
-        case 1: launch_pdl(k_update_level<1>, g, kBlock, 0, s, a, lo, hi, ua, *cull); break;
-        case 2: launch_pdl(k_update_level<2>, g, kBlock, 0, s, a, lo, hi, ua, *cull); break;
-        case 3: launch_pdl(k_update_level<3>, g, kBlock, 0, s, a, lo, hi, ua, *cull); break;
-        case 4: launch_pdl(k_update_level<4>, g, kBlock, 0, s, a, lo, hi, ua, *cull); break;
-        case 6: launch_pdl(k_update_level<6>, g, kBlock, 0, s, a, lo, hi, ua, *cull); break;
-        default: launch_pdl(k_update_level<0>, g, kBlock, 0, s, a, lo, hi, ua, *cull); break;
+        case 1: FYX_DISPATCH_VAR(k_update_level, 1, var, g, kBlock, 0, s, a, lo, hi, ua, *cull); break;
+        case 2: FYX_DISPATCH_VAR(k_update_level, 2, var, g, kBlock, 0, s, a, lo, hi, ua, *cull); break;
+        case 3: FYX_DISPATCH_VAR(k_update_level, 3, var, g, kBlock, 0, s, a, lo, hi, ua, *cull); break;
+        case 4: FYX_DISPATCH_VAR(k_update_level, 4, var, g, kBlock, 0, s, a, lo, hi, ua, *cull); break;
+        case 6: FYX_DISPATCH_VAR(k_update_level, 6, var, g, kBlock, 0, s, a, lo, hi, ua, *cull); break;
+        default: FYX_DISPATCH_VAR(k_update_level, 0, var, g, kBlock, 0, s, a, lo, hi, ua, *cull); break;
         }
     } else {
         CullParams none;
         none.nf = 0;
-        launch_pdl(k_update_level<-1>, grid_for(hi - lo), kBlock, 0, s, a, lo, hi, update_all ? 1u : 0u, none);
+        launch_pdl(k_update_level<-1, 0>, grid_for(hi - lo), kBlock, 0, s, a, lo, hi, update_all ? 1u : 0u, none);
     }
 }
 
@@ -843,17 +1034,28 @@ void launch_cull_lights(cudaStream_t s, const NodeArrays &a, const CullParams &c
     k_cull_lights<<<grid_for(a.cap), kBlock, 0, s>>>(a, cp, d_out_ptrs, counts);
 }
 
+template <int NF> static void launch_cull_t(cudaStream_t s, unsigned g, int var, const NodeArrays &a, const CullParams &cp, const uint32_t *lodp)
+{
+    switch (var) {
+    case 0: k_cull<NF, 0><<<g, kBlock, 0, s>>>(a, cp, lodp); break;
+    case 1: k_cull<NF, 1><<<g, kBlock, 0, s>>>(a, cp, lodp); break;
+    case 2: k_cull<NF, 2><<<g, kBlock, 0, s>>>(a, cp, lodp); break;
+    default: k_cull<NF, 3><<<g, kBlock, 0, s>>>(a, cp, lodp); break;
+    }
+}
+
 void launch_cull(cudaStream_t s, const NodeArrays &a, const CullParams &cp, const uint32_t *lodp)
 {
     if (!a.cap) return;
     const unsigned g = grid_for(a.cap);
+    const int var = cull_variant(cp.nf);
     switch (cp.nf) {
-    case 1: k_cull<1><<<g, kBlock, 0, s>>>(a, cp, lodp); break;
-    case 2: k_cull<2><<<g, kBlock, 0, s>>>(a, cp, lodp); break;
-    case 3: k_cull<3><<<g, kBlock, 0, s>>>(a, cp, lodp); break;
-    case 4: k_cull<4><<<g, kBlock, 0, s>>>(a, cp, lodp); break;
-    case 6: k_cull<6><<<g, kBlock, 0, s>>>(a, cp, lodp); break;
-    default: k_cull<0><<<g, kBlock, 0, s>>>(a, cp, lodp); break;
+    case 1: launch_cull_t<1>(s, g, var, a, cp, lodp); break;
+    case 2: launch_cull_t<2>(s, g, var, a, cp, lodp); break;
+    case 3: launch_cull_t<3>(s, g, var, a, cp, lodp); break;
+    case 4: launch_cull_t<4>(s, g, var, a, cp, lodp); break;
+    case 6: launch_cull_t<6>(s, g, var, a, cp, lodp); break;
+    default: launch_cull_t<0>(s, g, var, a, cp, lodp); break;
     }
 }
 

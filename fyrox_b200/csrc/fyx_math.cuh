@@ -105,6 +105,7 @@ struct FrustumDev {
     // mask of the corners that have it
     float4 ax_val[3][2];
     uint32_t ax_mask[3][8]; // per distinct coordinate: the 8-bit mask of the frustum corners that have it
+    float4 corner[8];       // the corners themselves (frustum.rs:70-79 order), for the warp-level pre-reject
 };
 
 // Frustum::is_intersects_aabb (fyrox-math/src/frustum.rs:222-245) on (min,max) pairs per axis.

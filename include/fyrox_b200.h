@@ -426,8 +426,25 @@ int32_t fyx_get_instances_device(fyx_ctx *ctx, uint32_t frustum, fyx_instances *
  * the whole list.  Rank 0 obtains an id, the host broadcasts it, every rank calls fyx_comm_init. */
 #define FYX_COMM_ID_BYTES 128
 int32_t fyx_comm_get_unique_id(void *out_id128);
+/* Collective.  The exchange buffers are built at the first gathered frame that follows (also collective: every rank
+ * issues gathered frames in lockstep) and sized for every rank's node count at that time; call fyx_comm_init again on
+ * every rank after a topology change that grows a shard. */
 int32_t fyx_comm_init(fyx_ctx *ctx, int32_t nranks, int32_t rank, const void *id128);
-/* All-gather the visible lists of the last cull (counts, then payload in max-count slots). */
+/* How this context exchanges the lists (bit set), decided collectively at the first gathered frame:
+ *   FYX_COMM_NCCL          NCCL is initialised (always; it is also the bootstrap channel of the other two)
+ *   FYX_COMM_PEER_STORES   the device-side all-gather is done by direct stores into the peers' cudaIpc-mapped list
+ *                          buffers over NVLink (no host synchronisation, no padded slots); otherwise ncclAllGather
+ *   FYX_COMM_HOST_SEGMENT  the host copy of the gathered lists is assembled in one node-wide host segment: every rank
+ *                          DMA-copies its own lists there over its own PCIe link
+ *   FYX_COMM_UNDECIDED     no gathered frame has run yet
+ * Environment (read by fyx_comm_init): FYX_EXCHANGE=nccl keeps the collective on NCCL, FYX_HOSTSEG=0 keeps private
+ * host copies. */
+#define FYX_COMM_NCCL 1u
+#define FYX_COMM_PEER_STORES 2u
+#define FYX_COMM_HOST_SEGMENT 4u
+#define FYX_COMM_UNDECIDED 8u
+uint32_t fyx_comm_mode(const fyx_ctx *ctx);
+/* All-gather the visible lists of the last cull.  Collective: every rank calls it for the same frame. */
 int32_t fyx_allgather_visible(fyx_ctx *ctx);
 /* Gathered list of frustum f: concatenation over ranks (device-resident and, if readback, on the host). */
 int32_t fyx_get_visible_gathered(fyx_ctx *ctx, uint32_t frustum, const uint32_t **out_idx, uint32_t *out_count);

@@ -77,3 +77,15 @@ def test_sharded_cull_plus_allgather_equals_unsharded(tmp_path):
             got = z[f"arr_{f}"]
             assert np.array_equal(got, want), f"rank {r} frustum {f}: {got.size} vs {want.size}"
     assert sum(w.size for w in whole) > 0
+
+
+def test_host_segment_protocol_with_forked_ranks():
+    """fyx_hostseg.hpp (the node-wide host segment every rank DMA-copies its own visible lists into): 4 forked processes,
+    400 epochs, two-slot reuse, whole-list verification by the consumer — tests/cpp/test_hostseg.cpp, CPU only."""
+    import subprocess
+
+    d = os.path.join(os.path.dirname(os.path.abspath(__file__)), "cpp")
+    subprocess.run(["make", "-C", d, "test_hostseg"], check=True, capture_output=True)
+    out = subprocess.run([os.path.join(d, "test_hostseg")], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert "hostseg ok" in out.stdout
