@@ -873,9 +873,70 @@ extern "C" int32_t fyx_set_topology(fyx_ctx *c, uint32_t capacity, uint32_t root
         }
     }
 
-    // device columns
+    // Per-node data that is NOT an argument of this call survives it: local matrices, TRS records, transform statics,
+    // bundle ids and LOD ranges of every node that was alive before and still is are carried from their old slot to the
+    // new one on the device (nodes that were not alive start from the defaults).  old_of_new[s] = the old slot.
+    const bool carry = c->have_topology && c->n_slots > 0 && n_slots > 0;
+    DevBuf b_map;
     int32_t rc;
+    if (carry) {
+        std::vector<uint32_t> old_of_new(n_slots, FYX_NONE);
+        for (uint32_t s2 = 0; s2 < n_slots; ++s2) {
+            const uint32_t i = node_of_slot[s2];
+            if (i < c->n_nodes && c->slot_of_node[i] != FYX_NONE) old_of_new[s2] = c->slot_of_node[i];
+        }
+        if ((rc = dev_ensure(c, b_map, (size_t)n_slots * 4))) return rc;
+        CU(cudaStreamSynchronize(c->stream));
+        CU(cudaMemcpy(b_map.p, old_of_new.data(), (size_t)n_slots * 4, cudaMemcpyHostToDevice));
+    }
+    // move one per-slot column (records of `words` u32) into a fresh allocation in the new slot order
+    auto carry_column = [&](DevBuf &col, uint32_t words, const PermuteDefault &def) -> int32_t {
+        DevBuf fresh;
+        int32_t r2 = dev_ensure(c, fresh, std::max<size_t>(n_slots, 1) * words * 4);
+        if (r2) return r2;
+        launch_permute_words(c->stream, fresh.p, col.p, b_map.as<uint32_t>(), n_slots, words, def);
+        c->launches++;
+        cudaError_t e = cudaStreamSynchronize(c->stream);
+        if (e != cudaSuccess) {
+            dev_free(fresh);
+            return fail(c, FYX_ERR_CUDA, "carrying a column over the topology change failed: %s", cudaGetErrorString(e));
+        }
+        dev_free(col);
+        col = fresh;
+        return FYX_OK;
+    };
+    auto f2u = [](float v) { uint32_t u; memcpy(&u, &v, 4); return u; };
+
+    // device columns
     const size_t n = std::max<uint32_t>(n_slots, 1);
+    if (carry) {
+        for (int k = 0; k < 3; ++k) { // identity rows for the new nodes
+            PermuteDefault d{};
+            d.w[k] = f2u(1.0f);
+            if ((rc = carry_column(c->b_L[k], 4, d))) return rc;
+        }
+        if (c->have_trs) {
+            PermuteDefault d{};
+            d.w[6] = d.w[7] = d.w[8] = d.w[9] = f2u(1.0f); // rotation w, scale
+            if ((rc = carry_column(c->b_trs, sizeof(fyx_trs) / 4, d))) return rc;
+        }
+        if (c->have_statics) {
+            PermuteDefault d{};
+            d.w[3] = f2u(1.0f);                               // pre_rotation w
+            d.w[4] = d.w[8] = d.w[12] = f2u(1.0f);            // post_rotation_matrix = identity
+            if ((rc = carry_column(c->b_statics, sizeof(fyx_transform_statics) / 4, d))) return rc;
+        }
+        if (c->have_bundles) {
+            PermuteDefault d{};
+            if ((rc = carry_column(c->b_bundle, 1, d))) return rc;
+        }
+        if (c->have_lod) {
+            PermuteDefault d{};
+            d.w[0] = 0x7FC00000u; // begin = NaN: not a LOD object
+            if ((rc = carry_column(c->b_lod_range, 2, d))) return rc;
+        }
+        dev_free(b_map);
+    }
     if ((rc = dev_ensure(c, c->b_parent, n * 4))) return rc;
     if ((rc = dev_ensure(c, c->b_flags, n * 4))) return rc;
     if ((rc = dev_ensure(c, c->b_mask, n * 4))) return rc;
@@ -893,12 +954,12 @@ extern "C" int32_t fyx_set_topology(fyx_ctx *c, uint32_t capacity, uint32_t root
         CU(cudaMemcpy(c->b_flags.p, h_flags.data(), n_slots * 4, cudaMemcpyHostToDevice));
         CU(cudaMemcpy(c->b_mask.p, h_mask.data(), n_slots * 4, cudaMemcpyHostToDevice));
         CU(cudaMemcpy(c->b_gidx.p, h_gidx.data(), n_slots * 4, cudaMemcpyHostToDevice));
-        // local / global matrices start as identity rows; world boxes as AABB::default()
+        // global matrices start as identity rows (so do the local ones of a first topology); world boxes as AABB::default()
         std::vector<float4> rows(n_slots);
         const float4 idr[3] = {make_float4(1, 0, 0, 0), make_float4(0, 1, 0, 0), make_float4(0, 0, 1, 0)};
         for (int k = 0; k < 3; ++k) {
             std::fill(rows.begin(), rows.end(), idr[k]);
-            CU(cudaMemcpy(c->b_L[k].p, rows.data(), n_slots * sizeof(float4), cudaMemcpyHostToDevice));
+            if (!carry) CU(cudaMemcpy(c->b_L[k].p, rows.data(), n_slots * sizeof(float4), cudaMemcpyHostToDevice));
             CU(cudaMemcpy(c->b_G[k].p, rows.data(), n_slots * sizeof(float4), cudaMemcpyHostToDevice));
             CU(cudaMemcpy(c->b_la[k].p, h_la[k].data(), n_slots * sizeof(float2), cudaMemcpyHostToDevice));
         }
@@ -907,6 +968,7 @@ extern "C" int32_t fyx_set_topology(fyx_ctx *c, uint32_t capacity, uint32_t root
     }
     if (capacity) CU(cudaMemcpy(c->b_slot_of_node.p, slot_of_node.data(), (size_t)capacity * 4, cudaMemcpyHostToDevice));
 
+    const bool same_capacity = c->have_topology && capacity == c->n_nodes;
     c->n_nodes = capacity;
     c->n_slots = n_slots;
     c->root = root;
@@ -916,14 +978,16 @@ extern "C" int32_t fyx_set_topology(fyx_ctx *c, uint32_t capacity, uint32_t root
     c->level_off.swap(level_off);
     c->have_topology = true;
     c->updated_once = false;
-    c->have_statics = false; // slots moved: the caller re-sends non-default statics after a topology change
-    c->dfs_rank.clear();     // ... and the DFS order, if it uses it
-    c->rank_on_device = false;
+    if (!carry) { // nothing to carry over (first topology, or one side empty): per-slot side tables start afresh
+        c->have_statics = false;
+        c->have_lod = false;
+        c->have_bundles = false;
+        c->n_bundle_ids = 1;
+        c->have_trs = false;
+    }
+    if (!same_capacity) c->dfs_rank.clear(); // indexed by node: stays valid while the pool capacity does
+    c->rank_on_device = false; // re-derived from dfs_rank in the new slot order
     c->anim_csr_dirty = true; // animated nodes are addressed by slot
-    c->have_lod = false;      // ... and the LOD ranges
-    c->have_bundles = false; // ... and the bundle ids (every node is back in bundle 0)
-    c->n_bundle_ids = 1;
-    c->have_trs = false;     // ... and full TRS records before the next rotation-only update
     c->tables_dirty = true; // bone slots depend on the slot order
     rebuild_node_arrays(c);
     return FYX_OK;

@@ -178,6 +178,10 @@ constexpr int kVblkRows = 11;                    // float4 rows per block
 constexpr int kVblkStride = kVblkRows * 32;      // float4 per block of 128 vertices
 void launch_ib_rows(cudaStream_t s, uint32_t n, const float *d_m16, float4 *r0, float4 *r1, float4 *r2, uint32_t *d_err);
 void launch_or_u32(cudaStream_t s, uint32_t *p, uint32_t bits);
+// dst[s] = map[s] != FYX_NONE ? src[map[s]] : default, records of `words` 32-bit words (<= 32): carries per-slot data over a
+// topology change (slots move; fyx_set_topology)
+struct PermuteDefault { uint32_t w[32]; };
+void launch_permute_words(cudaStream_t s, void *dst, const void *src, const uint32_t *map, uint32_t n, uint32_t words, const PermuteDefault &def);
 void launch_compact_gathered(cudaStream_t s, const uint32_t *pad, uint32_t maxc, const uint32_t *counts_all, int nranks, int f,
                              uint32_t *dst);
 

@@ -4,6 +4,7 @@
 // work at ~0.3-1 flop/B).  Arithmetic follows fyx_math.cuh (one rounding per op, reference order).
 // Each kernel names the reference code it replaces (paths relative to the Fyrox tree).
 #include <cstdlib>
+#include <cstring>
 
 #include "fyx_internal.h"
 #include "fyx_trs.cuh"
@@ -719,6 +720,110 @@ __global__ void __launch_bounds__(kBlock, MINB) k_skin(const SkinArrays sk, cons
 }
 
 // ------------------------------------------------------------------------------------------------
+// k_skin with TMA bulk staging (the experiment BASELINE.json's north_star names; numbers in profiles/README.md).
+// The vertex input is already laid out for it: a block of 128 vertices is 5 632 contiguous bytes (11 rows x 512 B).
+// Every WARP owns a ring of STAGES block buffers in shared memory and its own mbarriers: lane 0 issues one 1-D
+// cp.async.bulk (global -> shared, completion counted in bytes on the mbarrier) per block, the warp waits on the
+// barrier's phase parity, reads its 11 rows with conflict-free LDS.128 (lane l owns group l of the block), computes,
+// stores, and refills the buffer with the block STAGES ahead.  The vertex blocks are static, so the first copies are
+// issued BEFORE griddepcontrol.wait (they overlap k_palette's tail); the palette planes are then filled as in k_skin.
+// Selected with FYX_SKIN_VARIANT=tma2 (4 palette copies, 2 stages, 2 CTAs/SM) or tma3 (8 copies, 3 stages, 1 CTA/SM).
+// ------------------------------------------------------------------------------------------------
+constexpr uint32_t kVblkBytes = kVblkStride * sizeof(float4); // 5632
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(const uint32_t bar, const uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(const uint32_t bar, const uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(const uint32_t bar, const uint32_t parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(bar),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(const uint32_t dst, const void *src, const uint32_t bytes, const uint32_t bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+
+template <int S, int LOG2C, int STAGES, int MINB>
+__global__ void __launch_bounds__(kBlock, MINB) k_skin_tma(const SkinArrays sk, const SkinTile *__restrict__ tiles, const uint32_t n_tiles,
+                                                         const float one, const float negzero)
+{
+    constexpr int C = 1 << LOG2C;
+    constexpr int W = kBlock / 32;
+    constexpr uint32_t kPalBytes = (3u * S * C * sizeof(float4) + 127u) & ~127u;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float4 *const s_pal = reinterpret_cast<float4 *>(smem_raw);
+    unsigned char *const ring = smem_raw + kPalBytes;
+    uint64_t *const bars = reinterpret_cast<uint64_t *>(ring + (size_t)W * STAGES * kVblkBytes);
+    PackedConsts kc;
+    kc.one = make_float2(one, one);
+    kc.negzero = make_float2(negzero, negzero);
+    const SkinTile T = tiles[blockIdx.x];
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    const uint32_t b0 = T.quad_start >> 5, b1 = (T.quad_start + T.n_quads + 31u) >> 5; // blocks [b0, b1) hold the tile
+    const uint32_t q_lo = T.quad_start, q_hi = T.quad_start + T.n_quads;
+    unsigned char *const my_ring = ring + (size_t)warp * STAGES * kVblkBytes;
+    const uint32_t my_bar = smem_u32(bars + warp * STAGES);
+    if (lane == 0) {
+#pragma unroll
+        for (int st = 0; st < STAGES; ++st) mbar_init(my_bar + 8u * st, 1u);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    // prologue: the first STAGES blocks of this warp (static data: does not wait for the predecessor kernel)
+    if (lane == 0) {
+#pragma unroll
+        for (int st = 0; st < STAGES; ++st) {
+            const uint32_t b = b0 + warp + (uint32_t)st * W;
+            if (b < b1) {
+                mbar_expect_tx(my_bar + 8u * st, kVblkBytes);
+                bulk_g2s(smem_u32(my_ring + (size_t)st * kVblkBytes), sk.vblk + (size_t)b * kVblkStride, kVblkBytes, my_bar + 8u * st);
+            }
+        }
+    }
+    pdl_wait(); // the palettes come from k_palette
+    skin_fill_palette<S, LOG2C>(s_pal, sk.palette, T.bone_off, T.n_bones);
+    __syncthreads();
+    uint32_t j = 0;
+    for (uint32_t b = b0 + warp; b < b1; b += W, ++j) {
+        const uint32_t st = j % STAGES, parity = (j / STAGES) & 1u;
+        mbar_wait(my_bar + 8u * st, parity);
+        const float4 *row = reinterpret_cast<const float4 *>(my_ring + (size_t)st * kVblkBytes) + lane;
+        const size_t quad = ((size_t)b << 5) + lane;
+        if (quad >= q_lo && quad < q_hi) {
+            const float4 x4 = row[0 * 32], y4 = row[1 * 32], z4 = row[2 * 32];
+            const float4 nx4 = row[3 * 32], ny4 = row[4 * 32], nz4 = row[5 * 32];
+            const float4 w0 = row[6 * 32], w1 = row[7 * 32], w2 = row[8 * 32], w3 = row[9 * 32];
+            const uint4 iq = *reinterpret_cast<const uint4 *>(row + 10 * 32);
+            skin_quad<S, LOG2C>(s_pal, lane, x4, y4, z4, nx4, ny4, nz4, w0, w1, w2, w3, iq, reinterpret_cast<float4 *>(sk.opos) + 3 * quad,
+                                reinterpret_cast<float4 *>(sk.onrm) + 3 * quad, kc);
+        }
+        __syncwarp(); // every lane has read the buffer before it is refilled
+        const uint32_t nb = b + (uint32_t)STAGES * W;
+        if (lane == 0 && nb < b1) {
+            mbar_expect_tx(my_bar + 8u * st, kVblkBytes);
+            bulk_g2s(smem_u32(my_ring + (size_t)st * kVblkBytes), sk.vblk + (size_t)nb * kVblkStride, kVblkBytes, my_bar + 8u * st);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // Host-facing scatter / gather between the caller's AoS-by-node-index arrays and the slot-ordered
 // SoA planes.  Invalid indices are skipped (Pool::try_borrow semantics).
 // ------------------------------------------------------------------------------------------------
@@ -965,6 +1070,16 @@ __global__ void __launch_bounds__(kBlock) k_ib_rows(const uint32_t n, const floa
 
 __global__ void k_or_u32(uint32_t *p, const uint32_t bits) { atomicOr(p, bits); }
 
+__global__ void __launch_bounds__(kBlock) k_permute_words(uint32_t *dst, const uint32_t *src, const uint32_t *map, const uint32_t n,
+                                                          const uint32_t words, const PermuteDefault def)
+{
+    const uint64_t t = (uint64_t)blockIdx.x * kBlock + threadIdx.x;
+    if (t >= (uint64_t)n * words) return;
+    const uint32_t s = (uint32_t)(t / words), w = (uint32_t)(t % words);
+    const uint32_t o = map[s];
+    dst[t] = (o != FYX_NONE) ? src[(size_t)o * words + w] : def.w[w];
+}
+
 // After the fixed-slot NCCL all-gather of a visible list: rank r's entries sit at pad[r*maxc ..];
 // pack them back to back (rank order) so every rank holds one contiguous list per frustum.
 __global__ void __launch_bounds__(kBlock) k_compact_gathered(const uint32_t *pad, const uint32_t maxc,
@@ -1099,9 +1214,40 @@ template <int S, int LOG2C, int MINB> static void launch_skin_t(cudaStream_t s, 
     launch_pdl(k_skin<S, LOG2C, MINB>, n_tiles, kBlock, smem_pal, s, sk, tiles, n_tiles, 1.0f, -0.0f);
 }
 
+template <int S, int LOG2C, int STAGES, int MINB> static void launch_skin_tma_t(cudaStream_t s, const SkinArrays &sk, const SkinTile *tiles, uint32_t n_tiles)
+{
+    constexpr size_t pal = ((size_t)3 * S * (1 << LOG2C) * sizeof(float4) + 127) & ~size_t(127);
+    constexpr size_t smem = pal + (size_t)(kBlock / 32) * STAGES * kVblkBytes + (size_t)(kBlock / 32) * STAGES * 8;
+    static bool init = false;
+    if (!init) {
+        cudaFuncSetAttribute(k_skin_tma<S, LOG2C, STAGES, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        init = true;
+    }
+    launch_pdl(k_skin_tma<S, LOG2C, STAGES, MINB>, n_tiles, kBlock, smem, s, sk, tiles, n_tiles, 1.0f, -0.0f);
+}
+
+// 0 = LDG straight into registers (default), 2 = TMA bulk ring (2 stages, 4 palette copies, 2 CTAs/SM), 3 = (3 stages, 8 copies, 1 CTA/SM)
+static int skin_variant()
+{
+    static int v = [] {
+        const char *e = getenv("FYX_SKIN_VARIANT");
+        if (!e || !*e) return 0;
+        if (!strcmp(e, "tma2")) return 2;
+        if (!strcmp(e, "tma3")) return 3;
+        return 0;
+    }();
+    return v;
+}
+
 void launch_skin(cudaStream_t s, const SkinArrays &sk, const SkinTile *tiles, uint32_t n_tiles, uint32_t max_bones)
 {
     if (!n_tiles) return;
+    const int var = skin_variant();
+    if (var && max_bones <= 64) { // the experiment covers the benchmarked palette size
+        if (var == 2) launch_skin_tma_t<65, 2, 2, 2>(s, sk, tiles, n_tiles);
+        else launch_skin_tma_t<65, 3, 3, 1>(s, sk, tiles, n_tiles);
+        return;
+    }
     // 3 CTAs/SM (<= 85 registers): capping at 64 registers for 4 CTAs/SM spills and measured 28 % slower
     if (max_bones <= 64) {       // 8 copies: 25 KB of palette planes
         launch_skin_t<65, 3, 3>(s, sk, tiles, n_tiles);
@@ -1215,6 +1361,12 @@ void launch_ib_rows(cudaStream_t s, uint32_t n, const float *d_m16, float4 *r0, 
 }
 
 void launch_or_u32(cudaStream_t s, uint32_t *p, uint32_t bits) { k_or_u32<<<1, 1, 0, s>>>(p, bits); }
+
+void launch_permute_words(cudaStream_t s, void *dst, const void *src, const uint32_t *map, uint32_t n, uint32_t words, const PermuteDefault &def)
+{
+    if (!n || !words) return;
+    k_permute_words<<<grid_for((uint64_t)n * words), kBlock, 0, s>>>(static_cast<uint32_t *>(dst), static_cast<const uint32_t *>(src), map, n, words, def);
+}
 
 void launch_compact_gathered(cudaStream_t s, const uint32_t *pad, uint32_t maxc, const uint32_t *counts_all, int nranks, int f,
                              uint32_t *dst)

@@ -140,7 +140,13 @@ void    fyx_mat4_mul(const float a_m16[16], const float b_m16[16], float out_m16
  * NodeTrait::local_bounding_box (Mesh: scene/mesh/mod.rs:631-656; others the unit box, scene/base.rs:733-735;
  * NULL = unit box everywhere).  root = Graph::root index.  global_index (optional, NULL = identity) is the
  * value written to visible lists for node i — used when a context holds one shard of a larger graph.
- * Marks every node changed (like Base::on_connected_to_graph, scene/base.rs:520-540). */
+ * Marks every node changed (like Base::on_connected_to_graph, scene/base.rs:520-540): the next update recomputes
+ * every global matrix and world box.
+ * What the call keeps: everything that is per node but not an argument here — local matrices, TRS records, transform
+ * statics, bundle ids, LOD ranges, skinned surfaces and animations — stays with its node index (the data moves to the
+ * node's new place on the device); a node index that was not alive before the call starts from the defaults (identity
+ * local matrix ...).  The DFS order is kept while `capacity` is unchanged.  So the add / link / remove sequence of
+ * INTEGRATION.md is: fyx_set_topology with the new columns, then upload the matrices of the NEW or changed nodes only. */
 int32_t fyx_set_topology(fyx_ctx *ctx, uint32_t capacity, uint32_t root, const uint32_t *parent,
                          const uint32_t *flags, const uint32_t *render_mask, const float *local_aabb_minmax,
                          const uint32_t *global_index);
@@ -151,7 +157,7 @@ int32_t fyx_set_topology(fyx_ctx *ctx, uint32_t capacity, uint32_t root, const u
  * when the mesh is visited, so a bone that comes later in that order contributes its position from before the
  * update.  With the order given, such bones are snapshotted before every update and the skinned-mesh boxes equal
  * the reference's; without it (or NULL) every bone contributes its new position — identical whenever skeletons
- * precede their meshes.  Reset by fyx_set_topology. */
+ * precede their meshes.  Kept by fyx_set_topology while the capacity is unchanged. */
 int32_t fyx_set_dfs_order(fyx_ctx *ctx, uint32_t capacity, const uint32_t *preorder_rank);
 
 /* Transform::matrix() of `count` nodes (scene/transform.rs:544-550); idx NULL = nodes 0..count-1.
@@ -233,7 +239,7 @@ int32_t fyx_get_visible_lights(fyx_ctx *ctx, uint32_t frustum, const uint32_t **
  * filtered out hides its whole sub-tree (the DFS does not descend).
  * fyx_set_lod_ranges: per LOD object the range of the level it belongs to (2 floats each: begin, end; begin = NaN removes
  * the node from LOD control).  The host resolves "listed in several levels" the way the reference's loop does — owners in
- * pool order, levels and objects in order, the last write wins.  Reset by fyx_set_topology.
+ * pool order, levels and objects in order, the last write wins.  Carried over by fyx_set_topology with the node indices.
  * fyx_set_observers: ObserverPosition::{translation, z_near, z_far} of the frusta of the culls that follow, one per
  * frustum (count 0 = no LOD filtering).  While both are set the cull runs un-fused: update, then one small pass per
  * hierarchy level that propagates the filter bits from parents to children, then the cull over all nodes. */

@@ -627,6 +627,69 @@ def test_topology_change_keeps_surfaces_and_flag_changes_resize_nothing(ctx):
         assert pos_g.tobytes() == pos_o.tobytes() and nrm_g.tobytes() == nrm_o.tobytes()
 
 
+def test_add_link_remove_then_incremental_update_with_only_the_new_matrices(ctx):
+    """The sequence INTEGRATION.md gives the Rust shim: fyx_set_topology with the pool's new columns after
+    add / link / remove, then upload ONLY the matrices of the new nodes, then an incremental update.  Locals, TRS records,
+    transform statics, bundle ids and LOD ranges of the surviving nodes must have followed them to their new slots: the
+    result equals an oracle built from scratch with every node's data."""
+    rng = np.random.default_rng(17)
+    n = 6000
+    parent, flags, mask, local, aabb = random_graph(rng, n, p_dead=0.15)
+    ctx.set_topology(parent, flags, mask, aabb)
+    ctx.set_local_matrices(local)
+    # some nodes are driven by TRS records (+ statics): their position / scale live only on the device afterwards
+    alive = np.nonzero((flags & fb.NODE_ALIVE) != 0)[0].astype(np.uint32)
+    trs_nodes = rng.choice(alive[alive != 0], 400, replace=False).astype(np.uint32)
+    trs = np.zeros((len(trs_nodes), 10), np.float32)
+    trs[:, 0:3] = rng.uniform(-5, 5, (len(trs_nodes), 3))
+    q = rng.normal(size=(len(trs_nodes), 4))
+    trs[:, 3:7] = q / np.linalg.norm(q, axis=1, keepdims=True)
+    trs[:, 7:10] = rng.uniform(0.5, 2.0, (len(trs_nodes), 3))
+    ctx.set_local_trs(trs, trs_nodes)
+    fo, ff = camera_frustum(zfar=800.0, fovy=np.deg2rad(110.0))
+    ctx.update_and_cull([ff], fb.UPDATE_ALL)
+
+    # topology B: revive dead pool records as new nodes, re-parent some old nodes, remove some leaves
+    dead = np.nonzero((flags & fb.NODE_ALIVE) == 0)[0]
+    new_nodes = dead[: len(dead) // 2].astype(np.uint32)
+    parent2, flags2, local2 = parent.copy(), flags.copy(), local.copy()
+    flags2[new_nodes] = fb.NODE_DEFAULT | fb.NODE_RENDERABLE
+    parent2[new_nodes] = rng.choice(alive, len(new_nodes)).astype(np.uint32)
+    new_m = np.stack([ob.translation(*rng.uniform(-3, 3, 3)) for _ in new_nodes]).astype(np.float32)
+    local2[new_nodes] = new_m
+    has_child = np.zeros(n, bool)
+    has_child[parent[parent != NONE]] = True
+    leaves = alive[(~has_child[alive]) & (alive != 0) & ~np.isin(alive, trs_nodes)]
+    removed = leaves[:150]
+    flags2[removed] = 0
+    movers = leaves[150:300]
+    parent2[movers] = rng.choice(new_nodes, len(movers)).astype(np.uint32)  # old nodes under the new ones
+    ctx.set_topology(parent2, flags2, mask, aabb)
+    ctx.set_local_matrices(new_m, new_nodes)  # ONLY the new nodes
+    # a rotation-only update of the TRS-driven nodes must still find their positions / scales on the device
+    q2 = rng.normal(size=(len(trs_nodes), 4)).astype(np.float32)
+    q2 /= np.linalg.norm(q2, axis=1, keepdims=True).astype(np.float32)
+    ctx.set_local_rotations(q2, trs_nodes)
+    ctx.update_and_cull([ff], fb.UPDATE_INCREMENTAL)
+
+    # the oracle from scratch, with everybody's data
+    import sampled_parity as sp
+
+    trs2 = trs.copy()
+    trs2[:, 3:7] = q2
+    loc = sp.trs_bone_local(trs2)
+    for k, i in enumerate(trs_nodes):
+        local2[i] = loc(k)
+    og = ob.Graph.build(parent2, flags2, mask, local2, aabb)
+    og.L.orc_graph_drop_messages(og.h)
+    og.update_hierarchical_data()
+    live = np.nonzero((flags2 & fb.NODE_ALIVE) != 0)[0].astype(np.uint32)
+    assert_same_hierarchy(og, ctx, live)
+    assert_same_visible(og, ctx, [fo])
+    # removed nodes read back as "not there" (identity / default box), like Pool::try_borrow failing
+    assert np.array_equal(ctx.get_global_matrices(removed[:5]), np.tile(np.eye(4, dtype=np.float32).reshape(16), (5, 1)))
+
+
 def test_dfs_order_quirk_is_reproduced_exactly(ctx):
     """Skinned meshes that come BEFORE (some of) their bones in the reference's DFS: the reference folds those
     bones' positions from before the update (scene/mesh/mod.rs:676-682).  With fyx_set_dfs_order the boxes

@@ -1,0 +1,35 @@
+"""Kernel variants that are selected through the environment when the library first launches them (A/B switches kept for
+measurement: FYX_CULL_VARIANT, FYX_SKIN_VARIANT) get the same bit-exact parity tests as the defaults, each in its own
+process."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def _run(env, tests, k):
+    e = dict(os.environ)
+    e.update(env)
+    r = subprocess.run([sys.executable, "-m", "pytest", "-q", "-x", "-m", "gpu", "-k", k] + [os.path.join(HERE, t) for t in tests],
+                       capture_output=True, text=True, env=e, timeout=900)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+    assert " passed" in r.stdout
+
+
+@pytest.mark.timeout(1000)
+@pytest.mark.parametrize("variant", ["0", "1", "2", "3"])
+def test_cull_variants_match_the_oracle(variant):
+    """bit 0: warp-union pre-reject of whole frusta, bit 1: warp-wide compaction (fyx_kernels.cu)."""
+    _run({"FYX_CULL_VARIANT": variant}, ["test_gpu_parity.py", "test_gpu_drawprep.py"],
+         "cull or render_prep or pipelined or k7 or lod or light or instances or bundle")
+
+
+@pytest.mark.timeout(1000)
+@pytest.mark.parametrize("variant", ["tma2", "tma3"])
+def test_tma_skinning_variants_match_the_oracle(variant):
+    """k_skin_tma: vertex blocks staged by cp.async.bulk + mbarrier rings (fyx_kernels.cu)."""
+    _run({"FYX_SKIN_VARIANT": variant}, ["test_gpu_parity.py", "test_gpu_fullsize.py"], "skin or render_prep or c3_full")

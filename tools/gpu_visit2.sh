@@ -3,7 +3,7 @@
 set -u
 OUT=gpurun_out
 mkdir -p $OUT
-echo "[v2] small parity tests with the new cull"; timeout 900 python -m pytest tests/test_gpu_parity.py tests/test_gpu_drawprep.py -m gpu -q -x 2>&1 | tail -5
+echo "[v2] all GPU tests (new cull, topology carry-over, kernel variants)"; timeout 1800 python -m pytest tests -m gpu -q -x 2>&1 | tail -8
 for v in 0 1 2 3; do
   for w in C4 C2; do
     echo "[v2] variant $v workload $w"
@@ -31,6 +31,23 @@ try:
 except Exception as ex:
     print("   (no JSON line)", ex)
 PY
+done
+echo "[v2] skin variants on C4"
+for v in tma2 tma3; do
+  FYX_SKIN_VARIANT=$v timeout 300 python bench.py --workload C4 --no-c5 --no-cpu-baseline --no-device-animation --steps 20 > $OUT/r02b_skin_${v}.json 2> $OUT/r02b_skin_${v}.err
+  python - "$OUT/r02b_skin_${v}.json" <<'PY'
+import json, sys
+try:
+    d = json.load(open(sys.argv[1]))
+    st = {k: (round(v["ms"], 4), round(v["frac"], 3)) for k, v in d["roofline"]["stages"].items()}
+    print("   ms/frame", round(d["ms_per_step"], 4), "e2e", round(d["e2e"]["ms_per_step"], 4), st, "parity", d["parity"]["ok"])
+except Exception as ex:
+    print("   (no JSON line)", ex)
+PY
+done
+for v in ldg tma2; do
+  FYX_SKIN_VARIANT=$v timeout 400 ncu --set full --clock-control none --import-source on -k regex:k_skin --launch-skip 2 -c 1 -o $OUT/r02b_full_skin_$v \
+      python bench.py --workload target --steps 2 --warmup 1 --no-c5 --no-parity --no-cpu-baseline --no-device-animation > $OUT/r02b_ncu_skin_$v.log 2>&1
 done
 echo "[v2] ncu of the C4 main level, variant 3 and 0"
 for v in 3 0; do
