@@ -221,6 +221,8 @@ SYMBOLS = {
     "fyx_get_instances_device": (C.c_int32, [ctx_p, C.c_uint32, C.POINTER(fyx_instances)]),
     "fyx_comm_get_unique_id": (C.c_int32, [C.c_void_p]),
     "fyx_comm_init": (C.c_int32, [ctx_p, C.c_int32, C.c_int32, C.c_void_p]),
+    "fyx_set_blend_shapes": (C.c_int32, [ctx_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p]),
+    "fyx_set_blend_shape_weights": (C.c_int32, [ctx_p, C.c_uint32, C.c_uint32, C.c_void_p]),
     "fyx_allgather_visible": (C.c_int32, [ctx_p]),
     "fyx_comm_mode": (C.c_uint32, [ctx_p]),
     "fyx_get_visible_gathered": (C.c_int32, [ctx_p, C.c_uint32, C.POINTER(u32p), u32p]),

@@ -234,6 +234,22 @@ class Context:
         self._surfaces.append((int(bone_nodes.size), int(n_verts)))
         return sid.value
 
+    def set_blend_shapes(self, surface_id: int, records, weights=None):
+        """BlendShapesContainer of a surface: records = uint16 array (n_shapes, layer_stride, 9) of binary16 bit patterns
+        (position, normal, tangent offsets per vertex, scene/mesh/surface.rs:92-218); weights = BlendShape::weight (0..100)."""
+        r = np.ascontiguousarray(records, dtype=np.uint16)
+        if r.size == 0:
+            self._chk(self._lib.fyx_set_blend_shapes(self._h, surface_id, 0, None, 0, None))
+            return
+        assert r.ndim == 3 and r.shape[2] == 9
+        w = None if weights is None else np.ascontiguousarray(weights, dtype=np.float32)
+        assert w is None or w.size == r.shape[0]
+        self._chk(self._lib.fyx_set_blend_shapes(self._h, surface_id, r.shape[0], r.ctypes.data_as(C.c_void_p), r.shape[1], _ptr(w)))
+
+    def set_blend_shape_weights(self, surface_id: int, weights):
+        w = np.ascontiguousarray(weights, dtype=np.float32)
+        self._chk(self._lib.fyx_set_blend_shape_weights(self._h, surface_id, w.size, _ptr(w)))
+
     def reserve_skinning(self, total_bones: int, total_verts: int):
         self._chk(self._lib.fyx_reserve_skinning(self._h, total_bones, total_verts))
 

@@ -35,6 +35,10 @@ struct Surface {
     uint32_t n_verts;
     uint64_t vert_off;  // first vertex (multiple of 4)
     std::vector<uint32_t> bones; // node indices
+    // N4 blend shapes
+    uint32_t n_shapes = 0, bs_blocks = 0, bs_cap = 0; // shapes, 128-vertex blocks per shape, capacity of the region in shape blocks
+    uint64_t bs_off = 0;                               // first shape block of the region
+    uint32_t w_off = 0, w_cap = 0;
 };
 
 enum { EV_START = 0, EV_UPLOAD, EV_UPDATE, EV_CULL, EV_PALETTE, EV_SKIN, EV_READBACK, EV_COUNT };
@@ -148,6 +152,10 @@ struct fyx_ctx {
     uint64_t vert_cap = 0;
     uint32_t n_entries = 0, entry_cap = 0;
     DevBuf b_vblk, b_opos, b_onrm, b_ib[3], b_palette, b_bone_slot, b_tiles;
+    DevBuf b_bs, b_bs_w;          // blend-shape offsets (blocked f16) and weights
+    uint64_t bs_used = 0;         // shape blocks handed out
+    uint32_t bs_w_used = 0;
+    bool any_blend_shapes = false;
     DevBuf b_fold_node, b_fold_begin, b_fold_bone, b_fold_stale_idx, b_late_slot, b_stale_pos;
     std::vector<uint32_t> dfs_rank; // optional: pre-order rank of every node in the reference's DFS (fyx_set_dfs_order)
     uint32_t n_late = 0;
@@ -616,7 +624,7 @@ extern "C" void fyx_destroy(fyx_ctx *c)
     inst_free(c);
     anim_free(c);
     DevBuf *bufs[] = {&c->b_parent, &c->b_flags, &c->b_mask, &c->b_gidx, &c->b_slot_of_node, &c->d_stage, &c->b_statics, &c->b_trs, &c->b_vblk,
-                      &c->b_opos, &c->b_onrm, &c->b_palette, &c->b_bone_slot, &c->b_tiles, &c->b_fold_node,
+                      &c->b_opos, &c->b_onrm, &c->b_bs, &c->b_bs_w, &c->b_palette, &c->b_bone_slot, &c->b_tiles, &c->b_fold_node,
                       &c->b_fold_begin, &c->b_fold_bone, &c->b_fold_stale_idx, &c->b_late_slot, &c->b_stale_pos, &c->b_counts_packed, &c->b_counts_all};
     for (DevBuf *b : bufs) dev_free(*b);
     for (int i = 0; i < 3; ++i) {
@@ -1179,6 +1187,8 @@ void rebuild_skin_arrays(fyx_ctx *c)
     sk.vblk = c->b_vblk.as<float4>();
     sk.opos = c->b_opos.as<float>();
     sk.onrm = c->b_onrm.as<float>();
+    sk.bs = c->b_bs.as<uint2>();
+    sk.bs_w = c->b_bs_w.as<float>();
 }
 
 constexpr uint32_t kTileQuads = 2048; // up to 8192 vertices per tile (a 5k-vertex surface is one tile)
@@ -1208,11 +1218,16 @@ int32_t commit_surfaces(fyx_ctx *c)
             const uint32_t nt = (quads + kTileQuads - 1) / kTileQuads;
             const uint32_t per = (quads + nt - 1) / nt;
             for (uint32_t t = 0; t < nt; ++t) {
-                SkinTile tl;
+                SkinTile tl{};
                 tl.bone_off = sf.bone_off;
                 tl.n_bones = sf.n_bones;
                 tl.quad_start = (uint32_t)(sf.vert_off / 4 + (uint64_t)t * per);
                 tl.n_quads = std::min(per, quads - t * per);
+                tl.n_shapes = sf.n_shapes;
+                tl.bs_off = (uint32_t)sf.bs_off;
+                tl.bs_blocks = sf.bs_blocks;
+                tl.w_off = sf.w_off;
+                tl.local_quad0 = t * per;
                 tiles.push_back(tl);
             }
         }
@@ -1262,6 +1277,8 @@ int32_t commit_surfaces(fyx_ctx *c)
     CU(cudaMemcpy(c->b_fold_begin.p, fold_begin.data(), fold_begin.size() * 4, cudaMemcpyHostToDevice));
     if (!fold_bone.empty()) CU(cudaMemcpy(c->b_fold_bone.p, fold_bone.data(), fold_bone.size() * 4, cudaMemcpyHostToDevice));
     c->n_tiles = (uint32_t)tiles.size();
+    c->any_blend_shapes = false;
+    for (const Surface &sf : c->surfaces) c->any_blend_shapes |= sf.n_shapes != 0 && sf.n_verts != 0;
     c->max_bones = 0;
     for (const Surface &sf : c->surfaces)
         if (sf.n_verts) c->max_bones = std::max(c->max_bones, sf.n_bones);
@@ -1350,6 +1367,73 @@ extern "C" int32_t fyx_add_skinned_surface(fyx_ctx *c, uint32_t mesh_node, uint3
     if (out_id) *out_id = (uint32_t)c->surfaces.size();
     c->surfaces.push_back(std::move(sf));
     c->tables_dirty = true;
+    return FYX_OK;
+}
+
+// N4: blend shapes of a surface (BlendShapesContainer, scene/mesh/surface.rs:92-218) and their weights (Mesh::blend_shapes,
+// scene/mesh/mod.rs:449-456; the renderer passes weight / 100, :794-798)
+extern "C" int32_t fyx_set_blend_shapes(fyx_ctx *c, uint32_t sid, uint32_t n_shapes, const void *records, uint32_t layer_stride, const float *weights)
+{
+    if (!c) return FYX_ERR_INVALID_ARGUMENT;
+    if (sid >= c->surfaces.size()) return fail(c, FYX_ERR_INVALID_ARGUMENT, "surface id %u out of range", sid);
+    if (n_shapes > FYX_MAX_BLEND_SHAPES) return fail(c, FYX_ERR_INVALID_ARGUMENT, "n_shapes %u > %u", n_shapes, FYX_MAX_BLEND_SHAPES);
+    Surface &sf = c->surfaces[sid];
+    if (n_shapes && !records) return fail(c, FYX_ERR_INVALID_ARGUMENT, "records are NULL");
+    if (n_shapes && layer_stride < sf.n_verts) return fail(c, FYX_ERR_INVALID_ARGUMENT, "layer_stride %u < the surface's %u vertices", layer_stride, sf.n_verts);
+    CU(cudaSetDevice(c->device));
+    c->tables_dirty = true;
+    if (!n_shapes || !sf.n_verts) {
+        sf.n_shapes = 0;
+        return FYX_OK;
+    }
+    const uint32_t bs_blocks = (sf.n_verts + 127u) / 128u;
+    const uint64_t need = (uint64_t)n_shapes * bs_blocks;
+    if (need > 0xFFFFFFFFull) return fail(c, FYX_ERR_INVALID_ARGUMENT, "too much blend-shape data");
+    int32_t rc;
+    if (need > sf.bs_cap) { // a new region at the end (an earlier, smaller region of this surface is abandoned)
+        if (c->bs_used + need > 0xFFFFFFFFull) return fail(c, FYX_ERR_OUT_OF_MEMORY, "blend-shape storage exhausted");
+        if ((rc = dev_ensure(c, c->b_bs, (c->bs_used + need) * kBsBlockU2 * sizeof(uint2), true))) return rc;
+        sf.bs_off = c->bs_used;
+        sf.bs_cap = (uint32_t)need;
+        c->bs_used += need;
+    }
+    if (n_shapes > sf.w_cap) {
+        if ((rc = dev_ensure(c, c->b_bs_w, (size_t)(c->bs_w_used + n_shapes) * sizeof(float), true))) return rc;
+        sf.w_off = c->bs_w_used;
+        sf.w_cap = n_shapes;
+        c->bs_w_used += n_shapes;
+    }
+    sf.n_shapes = n_shapes;
+    sf.bs_blocks = bs_blocks;
+    rebuild_skin_arrays(c);
+    std::vector<float> w(n_shapes);
+    for (uint32_t i = 0; i < n_shapes; ++i) w[i] = (weights ? weights[i] : 100.0f) / 100.0f; // bs.weight / 100.0 (mesh/mod.rs:797)
+    void *d_rec = nullptr, *d_w = nullptr;
+    if ((rc = stage_to_device(c, records, (size_t)n_shapes * layer_stride * 18, w.data(), (size_t)n_shapes * 4, false, &d_rec, &d_w))) return rc;
+    launch_bs_layout(c->stream, sf.n_verts, n_shapes, layer_stride, static_cast<const uint16_t *>(d_rec), c->b_bs.as<uint2>() + sf.bs_off * kBsBlockU2, bs_blocks);
+    c->launches++;
+    CU(cudaMemcpyAsync(c->b_bs_w.as<float>() + sf.w_off, d_w, (size_t)n_shapes * 4, cudaMemcpyDeviceToDevice, c->stream));
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(c->stream)); // `w` and the staging buffer are free again
+    return FYX_OK;
+}
+
+extern "C" int32_t fyx_set_blend_shape_weights(fyx_ctx *c, uint32_t sid, uint32_t n, const float *weights)
+{
+    if (!c) return FYX_ERR_INVALID_ARGUMENT;
+    if (sid >= c->surfaces.size()) return fail(c, FYX_ERR_INVALID_ARGUMENT, "surface id %u out of range", sid);
+    Surface &sf = c->surfaces[sid];
+    if (n != sf.n_shapes) return fail(c, FYX_ERR_INVALID_ARGUMENT, "the surface has %u blend shapes, %u weights given", sf.n_shapes, n);
+    if (!n) return FYX_OK;
+    if (!weights) return fail(c, FYX_ERR_INVALID_ARGUMENT, "weights are NULL");
+    CU(cudaSetDevice(c->device));
+    std::vector<float> w(n);
+    for (uint32_t i = 0; i < n; ++i) w[i] = weights[i] / 100.0f;
+    void *d_w = nullptr;
+    int32_t rc = stage_to_device(c, w.data(), (size_t)n * 4, nullptr, 0, false, &d_w, nullptr);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(c->b_bs_w.as<float>() + sf.w_off, d_w, (size_t)n * 4, cudaMemcpyDeviceToDevice, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
     return FYX_OK;
 }
 
@@ -1494,7 +1578,7 @@ extern "C" int32_t fyx_skin(fyx_ctx *c)
     if (rc) return rc;
     CU(cudaEventRecord(c->ev[EV_START], c->stream));
     if (c->n_tiles) {
-        launch_skin(c->stream, c->sk, c->b_tiles.as<SkinTile>(), c->n_tiles, c->max_bones);
+        launch_skin(c->stream, c->sk, c->b_tiles.as<SkinTile>(), c->n_tiles, c->max_bones, c->any_blend_shapes);
         c->launches++;
     }
     CU(cudaEventRecord(c->ev[EV_SKIN], c->stream));
@@ -1621,7 +1705,7 @@ extern "C" int32_t fyx_render_prep(fyx_ctx *c, const fyx_frame_desc *fr)
     }
     if (stage_events) CU(cudaEventRecord(c->ev[EV_PALETTE], s));
     if (fr->do_skin && c->n_tiles) {
-        launch_skin(s, c->sk, c->b_tiles.as<SkinTile>(), c->n_tiles, c->max_bones);
+        launch_skin(s, c->sk, c->b_tiles.as<SkinTile>(), c->n_tiles, c->max_bones, c->any_blend_shapes);
         c->launches++;
     }
     if (stage_events) CU(cudaEventRecord(c->ev[EV_SKIN], s));

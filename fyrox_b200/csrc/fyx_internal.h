@@ -58,6 +58,10 @@ struct SkinArrays {
     // a row with one perfectly coalesced 512 B access and every 32 B sector exactly once (44 B/vertex).
     const float4 *vblk;
     float *opos, *onrm;        // skinned streams, packed xyz (each surface padded to a multiple of 4 vertices)
+    // N4 blend shapes (optional): f16 position / normal offsets per (shape, vertex) in blocks of 128 vertices x 6 rows
+    // (px,py,pz,nx,ny,nz) x 32 groups x 4 halfs = 1536 B per (shape, block); weights = BlendShape::weight / 100
+    const uint2 *bs;
+    const float *bs_w;
 };
 
 struct SkinTile {
@@ -65,7 +69,16 @@ struct SkinTile {
     uint32_t n_bones;
     uint32_t quad_start; // absolute index of the first 4-vertex group
     uint32_t n_quads;
+    // blend shapes of the surface (n_shapes = 0: none)
+    uint32_t n_shapes;
+    uint32_t bs_off;      // index of (shape 0, block 0) of the surface in units of 192 uint2 (one 1536-byte shape block)
+    uint32_t bs_blocks;   // 128-vertex blocks per shape
+    uint32_t w_off;       // first weight in bs_w
+    uint32_t local_quad0; // the tile's first group relative to the surface's first group
+    uint32_t pad[3];
 };
+constexpr uint32_t kBsBlockU2 = 6 * 32; // uint2 per (shape, block)
+void launch_bs_layout(cudaStream_t s, uint32_t n_verts, uint32_t n_shapes, uint32_t layer_stride, const uint16_t *d_records, uint2 *d_dst, uint32_t bs_blocks);
 
 struct FoldArrays {
     uint32_t n; // skinned mesh nodes
@@ -149,7 +162,7 @@ void launch_cull_lights(cudaStream_t s, const NodeArrays &a, const CullParams &c
 void launch_fold_bones(cudaStream_t s, const NodeArrays &a, const FoldArrays &fa, const CullParams *cull);
 void launch_snapshot_bones(cudaStream_t s, const NodeArrays &a, uint32_t n_late, const uint32_t *late_slot, float4 *stale_pos);
 void launch_palette(cudaStream_t s, const NodeArrays &a, const SkinArrays &sk);
-void launch_skin(cudaStream_t s, const SkinArrays &sk, const SkinTile *tiles, uint32_t n_tiles, uint32_t max_bones);
+void launch_skin(cudaStream_t s, const SkinArrays &sk, const SkinTile *tiles, uint32_t n_tiles, uint32_t max_bones, bool blend_shapes);
 
 void launch_scatter_locals(cudaStream_t s, const NodeArrays &a, uint32_t count, const uint32_t *d_idx,
                            const float *d_m16, const uint32_t *slot_of_node, uint32_t n_nodes, uint32_t *d_err);

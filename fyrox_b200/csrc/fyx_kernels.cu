@@ -6,6 +6,8 @@
 #include <cstdlib>
 #include <cstring>
 
+#include <cuda_fp16.h>
+
 #include "fyx_internal.h"
 #include "fyx_trs.cuh"
 
@@ -692,8 +694,68 @@ __device__ __forceinline__ void skin_quad(const float4 *s_pal, const uint32_t la
     st_stream(no + 2, make_float4(mz[2], mx[3], my[3], mz[3]));
 }
 
+// N4: blend shapes ahead of the skinning (standard.shader:167-173): for i in 0..blendShapesCount:
+//   inputPosition.xyz += offsets.position * weight;  inputNormal += offsets.normal * weight
+// in shape order, offsets = the f16 texels of BlendShapesContainer::from_lists (scene/mesh/surface.rs:92-218, exact in
+// f32), weight = BlendShape::weight / 100 (scene/mesh/mod.rs:794-798); one rounding per product and per sum.
+// 12 more bytes read per vertex and shape.  The four vertices of a thread come as 4 halfs per row.
+__device__ __forceinline__ void bs_axpy(float4 &v, const uint2 h, const float w)
+{
+    const __half2 a = *reinterpret_cast<const __half2 *>(&h.x), b = *reinterpret_cast<const __half2 *>(&h.y);
+    const float2 fa = __half22float2(a), fb = __half22float2(b);
+    v.x = FYX_ADD(v.x, FYX_MUL(fa.x, w));
+    v.y = FYX_ADD(v.y, FYX_MUL(fa.y, w));
+    v.z = FYX_ADD(v.z, FYX_MUL(fb.x, w));
+    v.w = FYX_ADD(v.w, FYX_MUL(fb.y, w));
+}
+
+__device__ __forceinline__ void apply_blend_shapes(const SkinArrays &sk, const SkinTile &T, const uint32_t q, float4 &x4, float4 &y4, float4 &z4,
+                                                   float4 &nx4, float4 &ny4, float4 &nz4)
+{
+    const uint32_t e = T.local_quad0 + q;
+    const uint2 *r0 = sk.bs + ((size_t)T.bs_off + (e >> 5)) * kBsBlockU2 + (e & 31u);
+    const size_t shape_stride = (size_t)T.bs_blocks * kBsBlockU2;
+    for (uint32_t sidx = 0; sidx < T.n_shapes; ++sidx) {
+        const float w = sk.bs_w[T.w_off + sidx];
+        const uint2 *r = r0 + sidx * shape_stride;
+        const uint2 hx = r[0 * 32], hy = r[1 * 32], hz = r[2 * 32], hnx = r[3 * 32], hny = r[4 * 32], hnz = r[5 * 32];
+        bs_axpy(x4, hx, w);
+        bs_axpy(y4, hy, w);
+        bs_axpy(z4, hz, w);
+        bs_axpy(nx4, hnx, w);
+        bs_axpy(ny4, hny, w);
+        bs_axpy(nz4, hnz, w);
+    }
+}
+
+// BlendShapesContainer's records (9 halfs per vertex and layer: position, normal, tangent) -> the blocked device layout
+__global__ void __launch_bounds__(kBlock) k_bs_layout(const uint32_t n_verts, const uint32_t n_shapes, const uint32_t layer_stride,
+                                                      const uint16_t *rec, uint16_t *dst, const uint32_t bs_blocks)
+{
+    const uint64_t t = (uint64_t)blockIdx.x * kBlock + threadIdx.x;
+    const uint64_t per_shape = (uint64_t)bs_blocks * 128;
+    if (t >= per_shape * n_shapes) return;
+    const uint32_t sidx = (uint32_t)(t / per_shape), v = (uint32_t)(t % per_shape);
+    uint16_t h[6] = {0, 0, 0, 0, 0, 0};
+    if (v < n_verts) {
+        const uint16_t *r = rec + ((size_t)sidx * layer_stride + v) * 9;
+        for (int k = 0; k < 6; ++k) h[k] = r[k];
+    }
+    // (shape, block) = 6 rows x 32 groups x 4 halfs
+    uint16_t *blk = dst + ((size_t)sidx * bs_blocks + (v >> 7)) * (kBsBlockU2 * 4);
+    const uint32_t g = (v >> 2) & 31u, j = v & 3u;
+    for (int k = 0; k < 6; ++k) blk[(k * 32 + g) * 4 + j] = h[k];
+}
+
+void launch_bs_layout(cudaStream_t s, uint32_t n_verts, uint32_t n_shapes, uint32_t layer_stride, const uint16_t *d_records, uint2 *d_dst, uint32_t bs_blocks)
+{
+    if (!n_shapes || !bs_blocks) return;
+    k_bs_layout<<<(unsigned)(((uint64_t)bs_blocks * 128 * n_shapes + kBlock - 1) / kBlock), kBlock, 0, s>>>(n_verts, n_shapes, layer_stride, d_records,
+                                                                                                        reinterpret_cast<uint16_t *>(d_dst), bs_blocks);
+}
+
 // One CTA per tile, inputs loaded straight into registers (LDG.128, L1-bypassing).
-template <int S, int LOG2C, int MINB>
+template <int S, int LOG2C, int MINB, bool BS>
 __global__ void __launch_bounds__(kBlock, MINB) k_skin(const SkinArrays sk, const SkinTile *__restrict__ tiles, const uint32_t n_tiles,
                                                      const float one, const float negzero)
 {
@@ -710,10 +772,11 @@ __global__ void __launch_bounds__(kBlock, MINB) k_skin(const SkinArrays sk, cons
     for (uint32_t q = threadIdx.x; q < T.n_quads; q += kBlock) {
         const size_t quad = (size_t)T.quad_start + q;
         const float4 *row = sk.vblk + (quad >> 5) * kVblkStride + (quad & 31); // block, then this group's column
-        const float4 x4 = ld_stream(row + 0 * 32), y4 = ld_stream(row + 1 * 32), z4 = ld_stream(row + 2 * 32);
-        const float4 nx4 = ld_stream(row + 3 * 32), ny4 = ld_stream(row + 4 * 32), nz4 = ld_stream(row + 5 * 32);
+        float4 x4 = ld_stream(row + 0 * 32), y4 = ld_stream(row + 1 * 32), z4 = ld_stream(row + 2 * 32);
+        float4 nx4 = ld_stream(row + 3 * 32), ny4 = ld_stream(row + 4 * 32), nz4 = ld_stream(row + 5 * 32);
         const float4 w0 = ld_stream(row + 6 * 32), w1 = ld_stream(row + 7 * 32), w2 = ld_stream(row + 8 * 32), w3 = ld_stream(row + 9 * 32);
         const uint4 iq = ld_stream(reinterpret_cast<const uint4 *>(row + 10 * 32));
+        if (BS && T.n_shapes) apply_blend_shapes(sk, T, q, x4, y4, z4, nx4, ny4, nz4);
         skin_quad<S, LOG2C>(s_pal, lane, x4, y4, z4, nx4, ny4, nz4, w0, w1, w2, w3, iq, reinterpret_cast<float4 *>(sk.opos) + 3 * quad,
                             reinterpret_cast<float4 *>(sk.onrm) + 3 * quad, kc);
     }
@@ -1203,15 +1266,20 @@ void launch_palette(cudaStream_t s, const NodeArrays &a, const SkinArrays &sk)
     launch_pdl(k_palette, grid_for(sk.n_entries), kBlock, 0, s, a, sk);
 }
 
-template <int S, int LOG2C, int MINB> static void launch_skin_t(cudaStream_t s, const SkinArrays &sk, const SkinTile *tiles, uint32_t n_tiles)
+template <int S, int LOG2C, int MINB, bool BS> static void launch_skin_t2(cudaStream_t s, const SkinArrays &sk, const SkinTile *tiles, uint32_t n_tiles)
 {
     constexpr size_t smem_pal = (size_t)3 * S * (1 << LOG2C) * sizeof(float4);
     static bool init = false;
     if (!init) {
-        cudaFuncSetAttribute(k_skin<S, LOG2C, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_pal);
+        cudaFuncSetAttribute(k_skin<S, LOG2C, MINB, BS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_pal);
         init = true;
     }
-    launch_pdl(k_skin<S, LOG2C, MINB>, n_tiles, kBlock, smem_pal, s, sk, tiles, n_tiles, 1.0f, -0.0f);
+    launch_pdl(k_skin<S, LOG2C, MINB, BS>, n_tiles, kBlock, smem_pal, s, sk, tiles, n_tiles, 1.0f, -0.0f);
+}
+template <int S, int LOG2C, int MINB> static void launch_skin_t(cudaStream_t s, const SkinArrays &sk, const SkinTile *tiles, uint32_t n_tiles, bool bs)
+{
+    if (bs) launch_skin_t2<S, LOG2C, MINB, true>(s, sk, tiles, n_tiles);
+    else launch_skin_t2<S, LOG2C, MINB, false>(s, sk, tiles, n_tiles);
 }
 
 template <int S, int LOG2C, int STAGES, int MINB> static void launch_skin_tma_t(cudaStream_t s, const SkinArrays &sk, const SkinTile *tiles, uint32_t n_tiles)
@@ -1239,22 +1307,22 @@ static int skin_variant()
     return v;
 }
 
-void launch_skin(cudaStream_t s, const SkinArrays &sk, const SkinTile *tiles, uint32_t n_tiles, uint32_t max_bones)
+void launch_skin(cudaStream_t s, const SkinArrays &sk, const SkinTile *tiles, uint32_t n_tiles, uint32_t max_bones, bool blend_shapes)
 {
     if (!n_tiles) return;
     const int var = skin_variant();
-    if (var && max_bones <= 64) { // the experiment covers the benchmarked palette size
+    if (var && max_bones <= 64 && !blend_shapes) { // the experiment covers the benchmarked palette size
         if (var == 2) launch_skin_tma_t<65, 2, 2, 2>(s, sk, tiles, n_tiles);
         else launch_skin_tma_t<65, 3, 3, 1>(s, sk, tiles, n_tiles);
         return;
     }
     // 3 CTAs/SM (<= 85 registers): capping at 64 registers for 4 CTAs/SM spills and measured 28 % slower
     if (max_bones <= 64) {       // 8 copies: 25 KB of palette planes
-        launch_skin_t<65, 3, 3>(s, sk, tiles, n_tiles);
+        launch_skin_t<65, 3, 3>(s, sk, tiles, n_tiles, blend_shapes);
     } else if (max_bones <= 128) { // 8 copies: 50 KB
-        launch_skin_t<129, 3, 3>(s, sk, tiles, n_tiles);
+        launch_skin_t<129, 3, 3>(s, sk, tiles, n_tiles, blend_shapes);
     } else {                       // 4 copies (2-way worst case): 49 KB
-        launch_skin_t<257, 2, 3>(s, sk, tiles, n_tiles);
+        launch_skin_t<257, 2, 3>(s, sk, tiles, n_tiles, blend_shapes);
     }
 }
 

@@ -250,6 +250,20 @@ typedef struct fyx_observer {
 int32_t fyx_set_lod_ranges(fyx_ctx *ctx, uint32_t count, const uint32_t *idx, const float *begin_end);
 int32_t fyx_set_observers(fyx_ctx *ctx, uint32_t count, const fyx_observer *observers);
 
+/* ---- N4: blend shapes (morph targets) ahead of the skinning ------------------------------------------------ */
+/* The standard shader adds, for every blend shape i of the surface in order, offsets.position * weight to the vertex
+ * position and offsets.normal * weight to the normal BEFORE skinning (fyrox-material/src/shader/standard/opengl/
+ * standard.shader:167-173), weight = BlendShape::weight / 100 (scene/mesh/mod.rs:794-798).  `records` is the content of
+ * BlendShapesContainer::blend_shape_storage as from_lists builds it (scene/mesh/surface.rs:92-218): n_shapes layers of
+ * layer_stride (= width * height >= n_verts) records of 9 binary16 values — position, normal, tangent offsets of vertex
+ * v at record v of the layer (tangents are not part of the skinned streams and are ignored).  `weights` = the
+ * BlendShape::weight values (0..100), NULL = 100 each (BlendShape::default()).  n_shapes = 0 removes them.
+ * Costs 12 more bytes read per vertex and shape in fyx_skin; surfaces without shapes are unaffected. */
+#define FYX_MAX_BLEND_SHAPES 128u /* ShaderDefinition::MAX_BLEND_SHAPE_WEIGHT_GROUPS * 4, fyrox-material/src/shader/mod.rs:616 */
+int32_t fyx_set_blend_shapes(fyx_ctx *ctx, uint32_t surface_id, uint32_t n_shapes, const void *records, uint32_t layer_stride,
+                             const float *weights);
+int32_t fyx_set_blend_shape_weights(fyx_ctx *ctx, uint32_t surface_id, uint32_t n, const float *weights);
+
 /* SurfaceInstanceData::bone_matrices for every skinned surface (scene/mesh/mod.rs:781-793):
  * P[k] = bone_k.global_transform * bone_k.inv_bind_pose_transform; dead / FYX_NONE bone ⇒ identity. */
 int32_t fyx_build_palettes(fyx_ctx *ctx);

@@ -1117,6 +1117,65 @@ void orc_skin_vertices(const float *pal, uint32_t n_verts, const void *verts, co
     }
 }
 
+/* IEEE binary16 -> binary32, exact (what texelFetch of an RGB16F texel yields). */
+static float orc_half_to_float(uint16_t h)
+{
+    const uint32_t sign = (uint32_t)(h & 0x8000u) << 16;
+    uint32_t exp = (h >> 10) & 0x1Fu, man = h & 0x3FFu, bits;
+    if (exp == 0) {
+        if (man == 0) {
+            bits = sign;
+        } else { /* subnormal: normalise */
+            int e = -1;
+            do {
+                man <<= 1;
+                ++e;
+            } while (!(man & 0x400u));
+            bits = sign | ((uint32_t)(127 - 15 - e) << 23) | ((man & 0x3FFu) << 13);
+        }
+    } else if (exp == 31) {
+        bits = sign | 0x7F800000u | (man << 13);
+    } else {
+        bits = sign | ((exp + 127 - 15) << 23) | (man << 13);
+    }
+    float f;
+    memcpy(&f, &bits, 4);
+    return f;
+}
+
+/* N4 — the blend-shape stage of the standard shader followed by the skinning above
+ * (fyrox-material/src/shader/standard/opengl/standard.shader:167-173):
+ *   for i in 0..blendShapesCount: inputPosition.xyz += offsets.position * weight; inputNormal += offsets.normal * weight;
+ * offsets = S_FetchBlendShapeOffsets(storage, gl_VertexID, i) (fyrox-graphics-gl/src/shaders/shared.glsl:371-378): the
+ * three RGB16F texels of vertex v in layer i of the volume texture BlendShapesContainer::from_lists fills
+ * (scene/mesh/surface.rs:92-218): record v of the layer = 9 halfs (position, normal, tangent).
+ * weight = BlendShape::weight / 100.0 (scene/mesh/mod.rs:794-798), passed in already divided.
+ * One rounding per product and per sum (shader semantics, unpinned: GLSL would allow a fused multiply-add). */
+void orc_skin_vertices_blend(const float *pal, uint32_t n_verts, const void *verts, const orc_vertex_layout *l, uint32_t n_shapes,
+                             const uint16_t *records, uint32_t layer_stride, const float *weights, float *out_pos, float *out_nrm)
+{
+    const unsigned char *base = (const unsigned char *)verts;
+    unsigned char *tmp = (unsigned char *)malloc(l->stride);
+    for (uint32_t v = 0; v < n_verts; ++v) {
+        memcpy(tmp, base + (size_t)v * l->stride, l->stride);
+        float p[3], nr[3];
+        memcpy(p, tmp + l->position_offset, 12);
+        memcpy(nr, tmp + l->normal_offset, 12);
+        for (uint32_t i = 0; i < n_shapes; ++i) {
+            const uint16_t *r = records + ((size_t)i * layer_stride + v) * 9;
+            const float w = weights[i];
+            for (int k = 0; k < 3; ++k) {
+                p[k] = p[k] + orc_half_to_float(r[k]) * w;
+                nr[k] = nr[k] + orc_half_to_float(r[3 + k]) * w;
+            }
+        }
+        memcpy(tmp + l->position_offset, p, 12);
+        memcpy(tmp + l->normal_offset, nr, 12);
+        orc_skin_vertices(pal, 1, tmp, l, out_pos + 3 * (size_t)v, out_nrm ? out_nrm + 3 * (size_t)v : NULL);
+    }
+    free(tmp);
+}
+
 uint32_t orc_mesh_skin(const orc_graph *g, uint32_t mesh, uint32_t surface, float *out_pos, float *out_nrm)
 {
     const orc_node *n = node_at(g, mesh);

@@ -356,6 +356,77 @@ def test_skinning_edge_cases(ctx):
     assert p1.shape == (1, 3)
 
 
+def test_blend_shapes_ahead_of_skinning_match_oracle(ctx):
+    """N4: blend-shape offsets are added to positions / normals before the skinning (standard.shader:167-173), in shape
+    order, with BlendShape::weight / 100 — surfaces with and without shapes in one launch, vertex counts that are not
+    multiples of the 128-vertex blocks, weight updates, removal.  Bit for bit against orc_skin_vertices_blend."""
+    import ctypes as C
+
+    sc = Scene(6000, n_units=9, verts_per_unit=1237)
+    og, sids = scene_pair(sc, ctx)
+    idx, m = sc.animate(2)
+    for i, mm in zip(idx, m):
+        og.set_local_matrix(int(i), mm)
+    og.update_hierarchical_data()
+    ctx.set_local_matrices(m, idx)
+    rng = np.random.default_rng(12)
+    nv = sc.verts_per_unit
+    shapes = {}
+    for u in (0, 3, 4, 8):  # the others have no blend shapes
+        ns = [1, 3, 7, 2][len(shapes)]
+        stride = nv + [0, 11, 300, 1][len(shapes)]  # width * height of the texture >= vertex count
+        off = (rng.normal(size=(ns, stride, 9)) * 0.2).astype(np.float16)
+        off[rng.random((ns, stride, 9)) < 0.6] = 0  # sparse, like the importers' index -> offset maps
+        off[0, 0, :3] = [np.float16(6.1e-5), np.float16(-0.0), np.float16(5.96e-8)]  # smallest normal, -0, a subnormal
+        w = rng.uniform(0, 100, ns).astype(np.float32)
+        w[-1] = 0.0 if ns > 1 else 100.0
+        shapes[u] = (off.view(np.uint16), w)
+        ctx.set_blend_shapes(sids[u], off.view(np.uint16), w)
+
+    def check():
+        ctx.update_transforms(fb.UPDATE_ALL)
+        ctx.build_palettes()
+        ctx.skin()
+        L = ob.lib()
+        lay = ob.ANIMATED_VERTEX
+        for u, sid in enumerate(sids):
+            mesh = sc.unit_mesh_node(u)
+            pal_o = og.bone_matrices(mesh, 0, sc.bones_per_unit)
+            pos_g, nrm_g = ctx.get_skinned(sid)
+            if u in shapes:
+                rec, w = shapes[u]
+                verts = sc.unit_vertices(u)[0]
+                pos_o = np.empty((nv, 3), np.float32)
+                nrm_o = np.empty((nv, 3), np.float32)
+                w100 = (w / np.float32(100.0)).astype(np.float32)
+                L.orc_skin_vertices_blend(ob.fp(np.ascontiguousarray(pal_o.reshape(-1))), nv, verts.ctypes.data_as(C.c_void_p), C.byref(lay), rec.shape[0],
+                                          rec.ctypes.data_as(C.c_void_p), rec.shape[1], ob.fp(w100), ob.fp(pos_o.reshape(-1)), ob.fp(nrm_o.reshape(-1)))
+            else:
+                pos_o, nrm_o = og.skin(mesh, 0, nv)
+            assert pos_g.tobytes() == pos_o.tobytes(), f"unit {u}: positions differ"
+            assert nrm_g.tobytes() == nrm_o.tobytes(), f"unit {u}: normals differ"
+
+    check()
+    base0 = og.skin(sc.unit_mesh_node(0), 0, nv)[0]
+    assert ctx.get_skinned(sids[0])[0].tobytes() != base0.tobytes()  # the shapes really moved something
+    # new weights (Mesh::blend_shapes_mut), then fewer shapes, then none
+    rec, w = shapes[4]
+    w2 = rng.uniform(0, 100, len(w)).astype(np.float32)
+    ctx.set_blend_shape_weights(sids[4], w2)
+    shapes[4] = (rec, w2)
+    check()
+    rec3, w3 = shapes[3]
+    shapes[3] = (np.ascontiguousarray(rec3[:2]), w3[:2].copy())
+    ctx.set_blend_shapes(sids[3], shapes[3][0], shapes[3][1])
+    ctx.set_blend_shapes(sids[0], np.empty((0, 0, 9), np.uint16))
+    del shapes[0]
+    check()
+    with pytest.raises(fb.FyxError):
+        ctx.set_blend_shape_weights(sids[4], w2[:1])  # wrong count
+    with pytest.raises(fb.FyxError):
+        ctx.set_blend_shapes(sids[1], np.zeros((1, nv - 1, 9), np.uint16))  # fewer records than vertices
+
+
 def test_errors_are_reported_not_fatal(ctx):
     parent = np.array([NONE, 0], np.uint32)
     ctx.set_topology(parent, np.full(2, fb.NODE_DEFAULT, np.uint32))
