@@ -416,6 +416,17 @@ class Context:
             "bundles": arr(out.bundles, bdt, nb),
         }
 
+    def pack_bone_matrices(self, frustum: int):
+        """Bone-matrix blocks (255 mat4, zero padded) of the skinned instances of the last pack_instances (bundle.rs:484-496)."""
+        self._chk(self._lib.fyx_pack_bone_matrices(self._h, frustum))
+
+    def get_bone_matrix_block(self, frustum: int, instance: int):
+        """(255,16) f32 block of packed instance `instance`, or None for an unskinned instance."""
+        out = np.empty((255, 16), dtype=np.float32)
+        has = C.c_uint32()
+        self._chk(self._lib.fyx_get_bone_matrix_block(self._h, frustum, instance, out.ctypes.data_as(C.c_void_p), C.byref(has)))
+        return out if has.value else None
+
     def build_palettes(self):
         self._chk(self._lib.fyx_build_palettes(self._h))
 

@@ -86,6 +86,9 @@ struct AnimHost {
 // N3: packed instances of one frustum (fyx_drawprep.inl)
 struct InstOut {
     DevBuf b_node, b_sort, b_mats, b_bundles;
+    DevBuf b_block_of, b_blocks; // bone-matrix blocks of the skinned instances (fyx_pack_bone_matrices)
+    uint32_t n_blocks = 0;
+    bool blocks_valid = false;
     void *h[4] = {};
     size_t h_cap[4] = {};
     uint32_t count = 0, n_bundles = 0;
@@ -152,6 +155,7 @@ struct fyx_ctx {
     uint64_t vert_cap = 0;
     uint32_t n_entries = 0, entry_cap = 0;
     DevBuf b_vblk, b_opos, b_onrm, b_ib[3], b_palette, b_bone_slot, b_tiles;
+    DevBuf b_surf_of_slot, b_surf_bones; // per slot: the node's first skinned surface (FYX_NONE = none); per surface: (first palette entry, n_bones)
     DevBuf b_bs, b_bs_w;          // blend-shape offsets (blocked f16) and weights
     uint64_t bs_used = 0;         // shape blocks handed out
     uint32_t bs_w_used = 0;
@@ -624,7 +628,7 @@ extern "C" void fyx_destroy(fyx_ctx *c)
     inst_free(c);
     anim_free(c);
     DevBuf *bufs[] = {&c->b_parent, &c->b_flags, &c->b_mask, &c->b_gidx, &c->b_slot_of_node, &c->d_stage, &c->b_statics, &c->b_trs, &c->b_vblk,
-                      &c->b_opos, &c->b_onrm, &c->b_bs, &c->b_bs_w, &c->b_palette, &c->b_bone_slot, &c->b_tiles, &c->b_fold_node,
+                      &c->b_opos, &c->b_onrm, &c->b_bs, &c->b_bs_w, &c->b_surf_of_slot, &c->b_surf_bones, &c->b_palette, &c->b_bone_slot, &c->b_tiles, &c->b_fold_node,
                       &c->b_fold_begin, &c->b_fold_bone, &c->b_fold_stale_idx, &c->b_late_slot, &c->b_stale_pos, &c->b_counts_packed, &c->b_counts_all};
     for (DevBuf *b : bufs) dev_free(*b);
     for (int i = 0; i < 3; ++i) {
@@ -1276,6 +1280,21 @@ int32_t commit_surfaces(fyx_ctx *c)
     if (!fold_node.empty()) CU(cudaMemcpy(c->b_fold_node.p, fold_node.data(), fold_node.size() * 4, cudaMemcpyHostToDevice));
     CU(cudaMemcpy(c->b_fold_begin.p, fold_begin.data(), fold_begin.size() * 4, cudaMemcpyHostToDevice));
     if (!fold_bone.empty()) CU(cudaMemcpy(c->b_fold_bone.p, fold_bone.data(), fold_bone.size() * 4, cudaMemcpyHostToDevice));
+    {   // node -> its first skinned surface, surface -> its palette range (fyx_pack_bone_matrices)
+        std::vector<uint32_t> surf_of_slot(std::max<uint32_t>(c->n_slots, 1), FYX_NONE);
+        std::vector<uint2> surf_bones(std::max<size_t>(ns, 1));
+        for (size_t si = 0; si < ns; ++si) {
+            const Surface &sf = c->surfaces[si];
+            surf_bones[si] = make_uint2(sf.bone_off, sf.n_bones);
+            if (!sf.n_bones || sf.mesh_node >= c->n_nodes) continue;
+            const uint32_t sl = c->slot_of_node[sf.mesh_node];
+            if (sl != FYX_NONE && surf_of_slot[sl] == FYX_NONE) surf_of_slot[sl] = (uint32_t)si;
+        }
+        if ((rc = dev_ensure(c, c->b_surf_of_slot, surf_of_slot.size() * 4))) return rc;
+        if ((rc = dev_ensure(c, c->b_surf_bones, surf_bones.size() * sizeof(uint2)))) return rc;
+        CU(cudaMemcpy(c->b_surf_of_slot.p, surf_of_slot.data(), surf_of_slot.size() * 4, cudaMemcpyHostToDevice));
+        CU(cudaMemcpy(c->b_surf_bones.p, surf_bones.data(), surf_bones.size() * sizeof(uint2), cudaMemcpyHostToDevice));
+    }
     c->n_tiles = (uint32_t)tiles.size();
     c->any_blend_shapes = false;
     for (const Surface &sf : c->surfaces) c->any_blend_shapes |= sf.n_shapes != 0 && sf.n_verts != 0;

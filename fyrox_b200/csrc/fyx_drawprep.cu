@@ -206,6 +206,45 @@ void launch_lod_level(cudaStream_t s, const NodeArrays &a, uint32_t lo, uint32_t
     k_lod_level<<<(hi - lo + kBlock - 1) / kBlock, kBlock, 0, s>>>(a, lo, hi, range, lodp, lp);
 }
 
+// N3, bone matrices of the packed instances — RenderDataBundle::write_uniforms (renderer/bundle.rs:484-496): a skinned instance
+// gets a block of MAX_BONE_MATRICES (255) mat4: its bone_matrices, then all-zero matrices; an unskinned one gets none.
+// pass 1: which instance gets which block (order of the blocks is unspecified)
+__global__ void __launch_bounds__(kBlock) k_bone_block_index(const uint32_t n, const uint32_t *inst_node, const uint32_t *slot_of_node, const uint32_t n_nodes,
+                                                             const uint32_t *surf_of_slot, uint32_t *block_of_inst, uint32_t *counter)
+{
+    const uint32_t i = blockIdx.x * kBlock + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t node = inst_node[i];
+    const uint32_t slot = node < n_nodes ? slot_of_node[node] : FYX_NONE;
+    const uint32_t sf = slot != FYX_NONE ? surf_of_slot[slot] : FYX_NONE;
+    block_of_inst[i] = (sf != FYX_NONE) ? atomicAdd(counter, 1u) : FYX_NONE;
+}
+// pass 2: one CTA per instance copies the surface's palette and pads with zeros (1020 float4 per block)
+__global__ void __launch_bounds__(kBlock) k_bone_blocks(const uint32_t *inst_node, const uint32_t *slot_of_node, const uint32_t *surf_of_slot,
+                                                        const uint2 *surf_bones /* (first palette entry, n_bones) */, const float4 *palette,
+                                                        const uint32_t *block_of_inst, float4 *blocks)
+{
+    const uint32_t i = blockIdx.x;
+    const uint32_t blk = block_of_inst[i];
+    if (blk == FYX_NONE) return;
+    const uint2 sb = surf_bones[surf_of_slot[slot_of_node[inst_node[i]]]];
+    float4 *dst = blocks + (size_t)blk * (FYX_MAX_BONES * 4);
+    const float4 *src = palette + (size_t)sb.x * 4;
+    for (uint32_t e = threadIdx.x; e < FYX_MAX_BONES * 4; e += kBlock) dst[e] = (e < sb.y * 4u) ? src[e] : make_float4(0.f, 0.f, 0.f, 0.f);
+}
+
+void launch_bone_block_index(cudaStream_t s, uint32_t n, const uint32_t *inst_node, const uint32_t *slot_of_node, uint32_t n_nodes, const uint32_t *surf_of_slot,
+                             uint32_t *block_of_inst, uint32_t *counter)
+{
+    if (n) k_bone_block_index<<<(n + kBlock - 1) / kBlock, kBlock, 0, s>>>(n, inst_node, slot_of_node, n_nodes, surf_of_slot, block_of_inst, counter);
+}
+void launch_bone_blocks(cudaStream_t s, uint32_t n, const uint32_t *inst_node, const uint32_t *slot_of_node, const uint32_t *surf_of_slot, const uint2 *surf_bones,
+                        const float *palette, const uint32_t *block_of_inst, float *blocks)
+{
+    if (n) k_bone_blocks<<<n, kBlock, 0, s>>>(inst_node, slot_of_node, surf_of_slot, surf_bones, reinterpret_cast<const float4 *>(palette), block_of_inst,
+                                             reinterpret_cast<float4 *>(blocks));
+}
+
 void launch_pack_instances(cudaStream_t s, const NodeArrays &a, const InstParams &ip)
 {
     if (ip.n) k_inst_keys<<<(ip.n + kBlock - 1) / kBlock, kBlock, 0, s>>>(a, ip);

@@ -23,6 +23,8 @@ void inst_free(fyx_ctx *c)
         dev_free(o.b_sort);
         dev_free(o.b_mats);
         dev_free(o.b_bundles);
+        dev_free(o.b_block_of);
+        dev_free(o.b_blocks);
         for (int k = 0; k < 4; ++k) {
             if (o.h[k]) cudaFreeHost(o.h[k]);
             o.h[k] = nullptr;
@@ -161,6 +163,64 @@ extern "C" int32_t fyx_pack_instances(fyx_ctx *c, uint32_t f, const float *view,
     o.n_bundles = *c->h_inst_nb;
     o.on_host = false;
     o.valid = true;
+    o.blocks_valid = false;
+    return FYX_OK;
+}
+
+// N3: the bone-matrix blocks write_uniforms builds per skinned instance (renderer/bundle.rs:484-496), from the palettes of
+// the last fyx_build_palettes / fyx_render_prep
+extern "C" int32_t fyx_pack_bone_matrices(fyx_ctx *c, uint32_t f)
+{
+    if (!c) return FYX_ERR_INVALID_ARGUMENT;
+    if (f >= FYX_MAX_FRUSTA || !c->inst[f].valid) return fail(c, FYX_ERR_STATE, "fyx_pack_instances has not been called for frustum %u", f);
+    CU(cudaSetDevice(c->device));
+    int32_t rc = commit_surfaces(c);
+    if (rc) return rc;
+    InstOut &o = c->inst[f];
+    cudaStream_t s = c->stream;
+    if ((rc = dev_ensure(c, o.b_block_of, std::max<size_t>(o.count, 1) * 4))) return rc;
+    if ((rc = dev_ensure(c, c->b_inst_nb, 256))) return rc;
+    uint32_t *counter = c->b_inst_nb.as<uint32_t>() + 1;
+    CU(cudaMemsetAsync(counter, 0, 4, s));
+    launch_bone_block_index(s, o.count, o.b_node.as<uint32_t>(), c->b_slot_of_node.as<uint32_t>(), c->n_nodes, c->b_surf_of_slot.as<uint32_t>(),
+                            o.b_block_of.as<uint32_t>(), counter);
+    CU(cudaMemcpyAsync(c->h_inst_nb + 1, counter, 4, cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    o.n_blocks = c->h_inst_nb[1];
+    if ((rc = dev_ensure(c, o.b_blocks, std::max<size_t>(o.n_blocks, 1) * FYX_MAX_BONES * 64))) return rc;
+    launch_bone_blocks(s, o.count, o.b_node.as<uint32_t>(), c->b_slot_of_node.as<uint32_t>(), c->b_surf_of_slot.as<uint32_t>(), c->b_surf_bones.as<uint2>(),
+                       c->b_palette.as<float>(), o.b_block_of.as<uint32_t>(), o.b_blocks.as<float>());
+    c->launches += o.count ? 2 : 0;
+    CU(cudaGetLastError());
+    rc = sync_and_check(c);
+    if (rc) return rc;
+    o.blocks_valid = true;
+    return FYX_OK;
+}
+
+extern "C" int32_t fyx_get_bone_matrix_blocks_device(fyx_ctx *c, uint32_t f, fyx_bone_blocks *out)
+{
+    if (!c || !out) return FYX_ERR_INVALID_ARGUMENT;
+    if (f >= FYX_MAX_FRUSTA || !c->inst[f].valid || !c->inst[f].blocks_valid) return fail(c, FYX_ERR_STATE, "fyx_pack_bone_matrices has not been called for frustum %u", f);
+    const InstOut &o = c->inst[f];
+    out->count = o.count;
+    out->n_blocks = o.n_blocks;
+    out->block_of_instance = o.b_block_of.as<uint32_t>();
+    out->blocks = o.b_blocks.as<float>();
+    return FYX_OK;
+}
+
+extern "C" int32_t fyx_get_bone_matrix_block(fyx_ctx *c, uint32_t f, uint32_t instance, float *out_255x16, uint32_t *out_has_block)
+{
+    if (!c || !out_has_block) return FYX_ERR_INVALID_ARGUMENT;
+    if (f >= FYX_MAX_FRUSTA || !c->inst[f].valid || !c->inst[f].blocks_valid) return fail(c, FYX_ERR_STATE, "fyx_pack_bone_matrices has not been called for frustum %u", f);
+    const InstOut &o = c->inst[f];
+    if (instance >= o.count) return fail(c, FYX_ERR_INVALID_ARGUMENT, "instance %u out of range (%u)", instance, o.count);
+    CU(cudaSetDevice(c->device));
+    uint32_t blk = FYX_NONE;
+    CU(cudaMemcpy(&blk, o.b_block_of.as<uint32_t>() + instance, 4, cudaMemcpyDeviceToHost));
+    *out_has_block = blk != FYX_NONE;
+    if (blk != FYX_NONE && out_255x16) CU(cudaMemcpy(out_255x16, o.b_blocks.as<float>() + (size_t)blk * FYX_MAX_BONES * 16, (size_t)FYX_MAX_BONES * 64, cudaMemcpyDeviceToHost));
     return FYX_OK;
 }
 

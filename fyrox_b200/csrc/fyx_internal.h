@@ -147,6 +147,10 @@ struct InstParams {
     uint32_t *o_n_bundles;
 };
 void launch_pack_instances(cudaStream_t s, const NodeArrays &a, const InstParams &ip);
+void launch_bone_block_index(cudaStream_t s, uint32_t n, const uint32_t *inst_node, const uint32_t *slot_of_node, uint32_t n_nodes, const uint32_t *surf_of_slot,
+                             uint32_t *block_of_inst, uint32_t *counter);
+void launch_bone_blocks(cudaStream_t s, uint32_t n, const uint32_t *inst_node, const uint32_t *slot_of_node, const uint32_t *surf_of_slot, const uint2 *surf_bones,
+                        const float *palette, const uint32_t *block_of_inst, float *blocks);
 
 // ---- launchers (fyx_kernels.cu) ----
 void launch_update_level(cudaStream_t s, const NodeArrays &a, uint32_t lo, uint32_t hi, bool update_all,

@@ -440,6 +440,22 @@ int32_t fyx_get_instances(fyx_ctx *ctx, uint32_t frustum, fyx_instances *out);
 /* ... or to the device-resident arrays (count / n_bundles still come back as host values). */
 int32_t fyx_get_instances_device(fyx_ctx *ctx, uint32_t frustum, fyx_instances *out);
 
+/* Bone matrices of the packed instances, as RenderDataBundle::write_uniforms lays them out (renderer/bundle.rs:484-496):
+ * every instance whose node has a skinned surface gets a block of FYX_MAX_BONES (255 = ShaderDefinition::
+ * MAX_BONE_MATRICES) column-major mat4 — its SurfaceInstanceData::bone_matrices, then all-zero matrices — and an
+ * unskinned instance gets none (bone_matrices_block = None).  Uses the palettes of the last fyx_build_palettes /
+ * fyx_render_prep; call after fyx_pack_instances.  Nodes with ONE skinned surface (the first one counts). */
+typedef struct fyx_bone_blocks {
+    uint32_t count;                    /* instances == fyx_instances.count */
+    uint32_t n_blocks;                 /* skinned instances */
+    const uint32_t *block_of_instance; /* [count] block of packed instance i, FYX_NONE = unskinned          (device memory) */
+    const float *blocks;               /* [n_blocks * 255 * 16], 16 320 bytes per block, in unspecified order (device memory) */
+} fyx_bone_blocks;
+int32_t fyx_pack_bone_matrices(fyx_ctx *ctx, uint32_t frustum);
+int32_t fyx_get_bone_matrix_blocks_device(fyx_ctx *ctx, uint32_t frustum, fyx_bone_blocks *out);
+/* Host copy of one instance's block (out_255x16 may be NULL to ask only whether it has one). */
+int32_t fyx_get_bone_matrix_block(fyx_ctx *ctx, uint32_t frustum, uint32_t instance, float *out_255x16, uint32_t *out_has_block);
+
 /* ---- multi-GPU: one context per GPU, one process per GPU ------------------------------------- */
 /* The node array is sharded (sub-trees + replicated ancestors); each context culls its
  * shard; the per-frustum visible lists are all-gathered with NCCL over NVLink so every rank holds

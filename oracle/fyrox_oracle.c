@@ -1234,6 +1234,23 @@ uint64_t orc_node_instance(const orc_graph *g, uint32_t node, const float view[1
     return orc_calculate_sorting_index(view, gp);
 }
 
+/* N3 — the bone-matrix block RenderDataBundle::write_uniforms uploads for one instance (renderer/bundle.rs:484-496):
+ * `matrices = [INIT; MAX_BONE_MATRICES]` (all-zero mat4, MAX_BONE_MATRICES = 255, fyrox-material/src/shader/mod.rs:613),
+ * `matrices[0..n].copy_from_slice(&instance.bone_matrices)`; an instance with empty bone_matrices gets no block.
+ * Returns 1 and fills out[255*16] if node `mesh` has a skinned surface (its first one), else 0. */
+int orc_instance_bone_block(const orc_graph *g, uint32_t mesh, float out[255 * 16])
+{
+    const orc_node *n = node_at(g, mesh);
+    if (!n) return 0;
+    for (uint32_t si = 0; si < n->n_surfaces; ++si) {
+        if (!n->surfaces[si].n_bones) continue;
+        memset(out, 0, 255 * 64); /* +0.0 everywhere */
+        orc_mesh_bone_matrices(g, mesh, si, out);
+        return 1;
+    }
+    return 0;
+}
+
 /* Mesh::accurate_world_bounding_box — scene/mesh/mod.rs:468-526 */
 void orc_mesh_accurate_world_bounding_box(const orc_graph *g, uint32_t mesh, orc_aabb *out)
 {

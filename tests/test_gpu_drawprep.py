@@ -82,6 +82,35 @@ def test_instances_of_generated_scene_match_oracle(ctx):
         check_instances(og, ctx, f, fo_, v, p, bundle)
 
 
+def test_bone_matrix_blocks_of_packed_instances_match_oracle(ctx):
+    """N3: every skinned instance of the packed list carries the 255-mat4 block write_uniforms builds (bone_matrices, then
+    zero matrices, renderer/bundle.rs:484-496); unskinned instances carry none."""
+    sc = Scene(6000, 14, verts_per_unit=64)
+    og, sids = scene_pair(sc, ctx)
+    idx, m = sc.animate(1)
+    for i, mm in zip(idx, m):
+        og.set_local_matrix(int(i), mm)
+    og.update_hierarchical_data()
+    ctx.enable_instances()
+    view, vp, fo, ff = observer((0, 0, 0), (0, 0, -1), zf=500.0, fovy=np.deg2rad(120.0))
+    ctx.render_prep(update_flags=fb.UPDATE_ALL, changed_m16=m, changed_idx=idx, frusta=[ff])
+    inst = ctx.pack_instances(0, view, vp)
+    ctx.pack_bone_matrices(0)
+    meshes = {int(sc.unit_mesh_node(u)) for u in range(sc.n_units)}
+    L = ob.lib()
+    seen = 0
+    for k, nd in enumerate(inst["node"]):
+        blk = ctx.get_bone_matrix_block(0, k)
+        want = np.empty(255 * 16, np.float32)
+        has = L.orc_instance_bone_block(og.h, int(nd), ob.fp(want))
+        assert bool(has) == (int(nd) in meshes) == (blk is not None)
+        if has:
+            assert blk.reshape(-1).tobytes() == want.tobytes()
+            assert not blk[sc.bones_per_unit:].any()
+            seen += 1
+    assert seen >= 3  # several skinned meshes are in view
+
+
 def test_bundle_sort_index_follows_the_dfs_push_order(ctx):
     rng = np.random.default_rng(77)
     parent, flags, mask, local, aabb = random_graph(rng, 3000, p_orphan=0.02)
