@@ -36,6 +36,7 @@ NODE_CAST_SHADOWS = 1 << 3
 NODE_ALIVE = 1 << 4
 NODE_RENDERABLE = 1 << 5
 NODE_LIGHT = 1 << 6
+NODE_STATIC_BATCH = 1 << 7
 NODE_GLOBAL_VISIBILITY = 1 << 8
 NODE_GLOBAL_ENABLED = 1 << 9
 NODE_REACHABLE = 1 << 10

@@ -190,6 +190,8 @@ struct fyx_ctx {
 
     // N4 LOD filter (fyx_drawprep.inl)
     DevBuf b_lod_range, b_lodp; // float2 (begin, end; begin NaN = not a LOD object) and hidden-frusta bits, per slot
+    DevBuf b_prune;             // per slot: frusta in which the node's children are pruned (rendered static batches, hidden ancestors)
+    bool maybe_static_batch = false; // some node carries FYX_NODE_STATIC_BATCH: the cull runs level by level
     bool have_lod = false;
     std::vector<fyx_observer> observers;
 
@@ -612,6 +614,9 @@ static void fyx_comm_destroy_internal(fyx_ctx *c); // fyx_comm.inl
 namespace { void inst_free(fyx_ctx *c); }              // fyx_drawprep.inl
 static bool lod_active(const fyx_ctx *c, uint32_t nf);  // fyx_drawprep.inl
 static int32_t lod_pass(fyx_ctx *c);                    // fyx_drawprep.inl
+// DFS-pruning features (LOD filter, static batches): the cull cannot be fused into the level kernels
+static bool unfused_cull(const fyx_ctx *c, uint32_t nf);
+static int32_t cull_unfused(fyx_ctx *c, uint32_t nf);
 namespace { void anim_free(fyx_ctx *c); }              // fyx_anim.inl
 static int32_t animate_enqueue(fyx_ctx *c, float dt);  // fyx_anim.inl
 static int32_t allgather_enqueue(fyx_ctx *c, VisSlot &V, cudaStream_t s);
@@ -628,7 +633,7 @@ extern "C" void fyx_destroy(fyx_ctx *c)
     inst_free(c);
     anim_free(c);
     DevBuf *bufs[] = {&c->b_parent, &c->b_flags, &c->b_mask, &c->b_gidx, &c->b_slot_of_node, &c->d_stage, &c->b_statics, &c->b_trs, &c->b_vblk,
-                      &c->b_opos, &c->b_onrm, &c->b_bs, &c->b_bs_w, &c->b_surf_of_slot, &c->b_surf_bones, &c->b_palette, &c->b_bone_slot, &c->b_tiles, &c->b_fold_node,
+                      &c->b_prune, &c->b_opos, &c->b_onrm, &c->b_bs, &c->b_bs_w, &c->b_surf_of_slot, &c->b_surf_bones, &c->b_palette, &c->b_bone_slot, &c->b_tiles, &c->b_fold_node,
                       &c->b_fold_begin, &c->b_fold_bone, &c->b_fold_stale_idx, &c->b_late_slot, &c->b_stale_pos, &c->b_counts_packed, &c->b_counts_all};
     for (DevBuf *b : bufs) dev_free(*b);
     for (int i = 0; i < 3; ++i) {
@@ -864,6 +869,7 @@ extern "C" int32_t fyx_set_topology(fyx_ctx *c, uint32_t capacity, uint32_t root
     std::vector<float2> h_la[3];
     for (auto &v : h_la) v.resize(n_slots);
     uint32_t n_renderable = 0;
+    bool any_static = false;
     for (uint32_t s = 0; s < n_slots; ++s) {
         const uint32_t i = node_of_slot[s];
         const uint32_t p = parent[i];
@@ -873,6 +879,7 @@ extern "C" int32_t fyx_set_topology(fyx_ctx *c, uint32_t capacity, uint32_t root
         if (i < c->skinned_node.size() && c->skinned_node[i]) f |= F_SKINNED;
         h_flags[s] = f;
         n_renderable += (f & FYX_NODE_RENDERABLE) ? 1u : 0u;
+        any_static |= (f & FYX_NODE_STATIC_BATCH) != 0;
         h_mask[s] = render_mask ? render_mask[i] : 0xFFFFFFFFu;
         h_gidx[s] = global_index ? global_index[i] : i;
         if (local_aabb) {
@@ -985,6 +992,7 @@ extern "C" int32_t fyx_set_topology(fyx_ctx *c, uint32_t capacity, uint32_t root
     c->n_slots = n_slots;
     c->root = root;
     c->n_renderable = n_renderable;
+    c->maybe_static_batch = any_static;
     c->slot_of_node.swap(slot_of_node);
     c->node_of_slot.swap(node_of_slot);
     c->level_off.swap(level_off);
@@ -1128,6 +1136,9 @@ static int32_t set_u32_column(fyx_ctx *c, uint32_t count, const uint32_t *idx, c
 
 extern "C" int32_t fyx_set_flags(fyx_ctx *c, uint32_t count, const uint32_t *idx, const uint32_t *flags)
 {
+    if (c && flags)
+        for (uint32_t i = 0; i < count; ++i)
+            if (flags[i] & FYX_NODE_STATIC_BATCH) c->maybe_static_batch = true; // conservative: stays on until the next topology
     return set_u32_column(c, count, idx, flags, 0);
 }
 
@@ -1506,12 +1517,7 @@ extern "C" int32_t fyx_cull(fyx_ctx *c, uint32_t nf, const fyx_frustum *fr, cons
     CU(cudaEventRecord(c->ev[EV_START], c->stream));
     int32_t rc = prepare_cull(c, nf, fr, cam_mask, pass_flags);
     if (rc) return rc;
-    if (nf) {
-        const bool lod = lod_active(c, nf);
-        if (lod && (rc = lod_pass(c))) return rc;
-        launch_cull(c->stream, c->a, c->cp, lod ? c->b_lodp.as<uint32_t>() : nullptr);
-        c->launches++;
-    }
+    if (nf && (rc = cull_unfused(c, nf))) return rc;
     CU(cudaEventRecord(c->ev[EV_CULL], c->stream));
     rc = sync_and_check(c);
     cudaEventElapsedTime(&c->timings.cull_ms, c->ev[EV_START], c->ev[EV_CULL]);
@@ -1530,15 +1536,11 @@ extern "C" int32_t fyx_update_and_cull(fyx_ctx *c, uint32_t update_flags, uint32
     rc = prepare_cull(c, nf, fr, cam_mask, pass_flags);
     if (rc) return rc;
     {
-        // with a LOD filter the cull cannot be fused into the level kernels: the filter bits need every ancestor first
-        const bool lod = lod_active(c, nf);
-        rc = run_update(c, update_flags, (nf && !lod) ? &c->cp : nullptr);
+        // with a LOD filter / static batches the cull cannot be fused into the level kernels: the pruning bits need every ancestor first
+        const bool unf = unfused_cull(c, nf);
+        rc = run_update(c, update_flags, (nf && !unf) ? &c->cp : nullptr);
         if (rc) return rc;
-        if (lod) {
-            if ((rc = lod_pass(c))) return rc;
-            launch_cull(c->stream, c->a, c->cp, c->b_lodp.as<uint32_t>());
-            c->launches++;
-        }
+        if (unf && (rc = cull_unfused(c, nf))) return rc;
     }
     CU(cudaEventRecord(c->ev[EV_UPDATE], c->stream));
     rc = sync_and_check(c);
@@ -1695,14 +1697,10 @@ extern "C" int32_t fyx_render_prep(fyx_ctx *c, const fyx_frame_desc *fr)
         if (rc) return rc;
     }
     {
-        const bool lod = lod_active(c, fr->n_frusta);
-        rc = run_update(c, fr->update_flags, (fr->n_frusta && !lod) ? &c->cp : nullptr);
+        const bool unf = unfused_cull(c, fr->n_frusta);
+        rc = run_update(c, fr->update_flags, (fr->n_frusta && !unf) ? &c->cp : nullptr);
         if (rc) return rc;
-        if (lod) {
-            if ((rc = lod_pass(c))) return rc;
-            launch_cull(s, c->a, c->cp, c->b_lodp.as<uint32_t>());
-            c->launches++;
-        }
+        if (unf && (rc = cull_unfused(c, fr->n_frusta))) return rc;
     }
     if (stage_events) CU(cudaEventRecord(c->ev[EV_UPDATE], s));
     if (fr->n_frusta && (async || (fr->flags & FYX_FRAME_ALLGATHER))) CU(cudaEventRecord(c->vs[c->cur].ev_cull, s)); // consumed by the read-back / collective streams

@@ -149,7 +149,7 @@ __global__ void __launch_bounds__(kBlock) k_inst_scatter(const NodeArrays a, con
         // column c of the instance's world matrix: identity for a skinned surface (its vertices are placed by the
         // bone palette, scene/mesh/mod.rs:733-737), else the node's global transform
         float w0, w1, w2, w3 = (c == 3) ? 1.0f : 0.0f;
-        if (a.flags[se] & F_SKINNED) {
+        if (a.flags[se] & (F_SKINNED | FYX_NODE_STATIC_BATCH)) { // a static batch is pushed with the identity too (mesh/mod.rs:716)
             w0 = (c == 0) ? 1.0f : 0.0f;
             w1 = (c == 1) ? 1.0f : 0.0f;
             w2 = (c == 2) ? 1.0f : 0.0f;

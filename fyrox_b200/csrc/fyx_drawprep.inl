@@ -316,6 +316,33 @@ extern "C" int32_t fyx_get_visible_lights(fyx_ctx *c, uint32_t f, const uint32_t
 // ---- N4 (LOD filter): renderer/bundle.rs:898-916, 988-1004 -------------------------------------------------------------
 static bool lod_active(const fyx_ctx *c, uint32_t nf) { return c->have_lod && nf && c->observers.size() == nf; }
 
+static bool unfused_cull(const fyx_ctx *c, uint32_t nf) { return nf && (lod_active(c, nf) || c->maybe_static_batch); }
+
+static int32_t lod_pass(fyx_ctx *c);
+
+// The cull as its own pass over the finished boxes: LOD filter bits first (if any), then either one launch over all slots
+// or — with static batches in the graph — one launch per hierarchy level, parents first, carrying the pruned frusta down.
+static int32_t cull_unfused(fyx_ctx *c, uint32_t nf)
+{
+    const bool lod = lod_active(c, nf);
+    int32_t rc;
+    if (lod && (rc = lod_pass(c))) return rc;
+    const uint32_t *lodp = lod ? c->b_lodp.as<uint32_t>() : nullptr;
+    if (!c->maybe_static_batch) {
+        launch_cull(c->stream, c->a, c->cp, lodp);
+        c->launches++;
+    } else {
+        if ((rc = dev_ensure(c, c->b_prune, std::max<size_t>(c->n_slots, 1) * 4))) return rc;
+        const size_t nl = c->level_off.size() ? c->level_off.size() - 1 : 0;
+        for (size_t l = 0; l < nl; ++l) {
+            launch_cull_range(c->stream, c->a, c->cp, lodp, c->level_off[l], c->level_off[l + 1], c->b_prune.as<uint32_t>());
+            c->launches += (c->level_off[l + 1] > c->level_off[l]);
+        }
+    }
+    CU(cudaGetLastError());
+    return FYX_OK;
+}
+
 // hidden-frusta bits of every node, one small launch per hierarchy level (parents first)
 static int32_t lod_pass(fyx_ctx *c)
 {

@@ -156,6 +156,8 @@ void launch_bone_blocks(cudaStream_t s, uint32_t n, const uint32_t *inst_node, c
 void launch_update_level(cudaStream_t s, const NodeArrays &a, uint32_t lo, uint32_t hi, bool update_all,
                          const CullParams *cull /* nullptr = no fused cull */);
 void launch_cull(cudaStream_t s, const NodeArrays &a, const CullParams &cp, const uint32_t *lodp = nullptr /* per slot: frusta hidden by the LOD filter */);
+// one hierarchy level [lo, hi) with DFS pruning by rendered static batches (prune: per slot, frusta hidden for the children)
+void launch_cull_range(cudaStream_t s, const NodeArrays &a, const CullParams &cp, const uint32_t *lodp, uint32_t lo, uint32_t hi, uint32_t *prune);
 // N4 LOD filter (fyx_drawprep.cu): per observer translation, z_near and z_far - z_near
 struct LodParams {
     int nf;

@@ -317,18 +317,31 @@ __device__ __forceinline__ void compact_emit_warp(const uint32_t vis_bits, const
 // (A single cooperative launch walking all levels with grid-wide barriers was tried and rejected: the
 // persistent grid, L2-only parent loads and the barriers cost more than the launches they save —
 // C2 0.357 -> 0.416 ms, target 0.990 -> 1.051 ms per frame; profiles/README.md.)
-template <bool WANT_BOX>
+// UA: FYX_UPDATE_ALL known at compile time — every load of the node's own columns is issued at once, next to the load of
+// the parent index, instead of after the parent's flags have said whether the node is dirty (two dependent memory
+// round trips per node instead of three; the kernel is latency-bound: ncu long_scoreboard 8 of 17 stalled warps per issue).
+template <bool WANT_BOX, bool UA>
 __device__ __forceinline__ void update_node(const NodeArrays &a, const uint32_t slot, const uint32_t update_all, uint32_t &nf_out, float2 &wx,
                                             float2 &wy, float2 &wz)
 {
     const uint32_t p = a.parent[slot]; // static column: may be read before the predecessor has finished
     pdl_wait(); // everything below reads what the previous level / a scatter kernel / the previous frame's tail wrote
     const uint32_t f = a.flags[slot]; // mutable (F_DIRTY_SELF is set by the scatter kernels): only after the wait
+    Affine L;
+    float2 lx, ly, lz;
+    if (UA) {
+        L.r0 = ld_stream(a.L[0] + slot);
+        L.r1 = ld_stream(a.L[1] + slot);
+        L.r2 = ld_stream(a.L[2] + slot);
+        lx = ld_stream(a.la[0] + slot);
+        ly = ld_stream(a.la[1] + slot);
+        lz = ld_stream(a.la[2] + slot);
+    }
     // no parent ⇒ parent values are identity / true (graph/mod.rs:1171-1175,1187-1192,1210-1214)
     const uint32_t pf = (p != FYX_NONE)
                             ? a.flags[p]
                             : (FYX_NODE_GLOBAL_VISIBILITY | FYX_NODE_GLOBAL_ENABLED | ((f & F_ROOT) ? FYX_NODE_REACHABLE : 0u));
-    const bool dirty = update_all || (f & F_DIRTY_SELF) || (pf & F_DIRTY);
+    const bool dirty = UA || update_all || (f & F_DIRTY_SELF) || (pf & F_DIRTY);
     uint32_t nf = f & ~(FYX_NODE_GLOBAL_VISIBILITY | FYX_NODE_GLOBAL_ENABLED | FYX_NODE_REACHABLE | F_DIRTY | F_DIRTY_SELF);
     if ((pf & FYX_NODE_GLOBAL_VISIBILITY) && (f & FYX_NODE_VISIBILITY)) nf |= FYX_NODE_GLOBAL_VISIBILITY;
     if ((pf & FYX_NODE_GLOBAL_ENABLED) && (f & FYX_NODE_ENABLED)) nf |= FYX_NODE_GLOBAL_ENABLED;
@@ -338,13 +351,14 @@ __device__ __forceinline__ void update_node(const NodeArrays &a, const uint32_t 
     nf_out = nf;
 
     if (dirty) {
-        Affine L;
-        L.r0 = ld_stream(a.L[0] + slot);
-        L.r1 = ld_stream(a.L[1] + slot);
-        L.r2 = ld_stream(a.L[2] + slot);
-        const float2 lx = ld_stream(a.la[0] + slot);
-        const float2 ly = ld_stream(a.la[1] + slot);
-        const float2 lz = ld_stream(a.la[2] + slot);
+        if (!UA) {
+            L.r0 = ld_stream(a.L[0] + slot);
+            L.r1 = ld_stream(a.L[1] + slot);
+            L.r2 = ld_stream(a.L[2] + slot);
+            lx = ld_stream(a.la[0] + slot);
+            ly = ld_stream(a.la[1] + slot);
+            lz = ld_stream(a.la[2] + slot);
+        }
         Affine P;
         if (p != FYX_NONE) {
             P.r0 = a.G[0][p]; // siblings are adjacent slots: one or two parents per warp (L1 hits)
@@ -371,13 +385,15 @@ __device__ __forceinline__ void update_node(const NodeArrays &a, const uint32_t 
     }
 }
 
-// VAR: bit 0 = warp-level pre-reject of whole frusta, bit 1 = warp-wide compaction (else CTA-wide)
+// VAR: bit 0 = warp-level pre-reject of whole frusta, bit 1 = warp-wide compaction (else CTA-wide), bit 2 = FYX_UPDATE_ALL
+// specialisation (own columns, render mask and list index loaded up front)
 template <int NFT, int VAR>
 __global__ void __launch_bounds__(kBlock) k_update_level(const NodeArrays a, const uint32_t lo, const uint32_t hi,
                                                          const uint32_t update_all, const CullParams cp)
 {
     pdl_trigger();
     constexpr bool PRE = (NFT >= 0) && (VAR & 1);
+    constexpr bool UA = (VAR & 4) != 0;
     __shared__ __align__(16) unsigned char s_pref[PRE ? sizeof(PrefTable) : 16];
     PrefTable *T = reinterpret_cast<PrefTable *>(s_pref);
     if (PRE) {
@@ -388,13 +404,18 @@ __global__ void __launch_bounds__(kBlock) k_update_level(const NodeArrays a, con
     uint32_t nf = 0u;
     float2 wx = make_float2(0.f, 0.f), wy = wx, wz = wx;
     const bool valid = slot < hi;
-    if (valid) update_node<(NFT >= 0)>(a, slot, update_all, nf, wx, wy, wz);
+    uint32_t mask = 0u, gi_early = 0u;
+    if (UA && (NFT >= 0) && valid) { // static columns: no reason to wait for anything
+        mask = a.mask[slot];
+        gi_early = a.gidx[slot];
+    }
+    if (valid) update_node<(NFT >= 0), UA>(a, slot, update_all, nf, wx, wy, wz);
     else pdl_wait();
     if (NFT >= 0) {
         const bool cand = valid && !(nf & F_SKINNED);
-        const uint32_t mask = cand ? a.mask[slot] : 0u;
+        if (!UA) mask = cand ? a.mask[slot] : 0u;
         const uint32_t vis_bits = cull_warp<(NFT > 0 ? NFT : 0), PRE>(cand, nf, mask, wx, wy, wz, cp, T);
-        const uint32_t gi = vis_bits ? a.gidx[slot] : 0u;
+        const uint32_t gi = UA ? gi_early : (vis_bits ? a.gidx[slot] : 0u);
         if (VAR & 2) compact_emit_warp(vis_bits, gi, slot, cp);
         else compact_emit<(NFT > 0 ? NFT : 0)>(vis_bits, gi, slot, cp);
     }
@@ -404,8 +425,12 @@ __global__ void __launch_bounds__(kBlock) k_update_level(const NodeArrays a, con
 // Stand-alone cull over all slots (static scene / extra passes: every shadow pass re-runs the cull
 // with its own frustum, renderer/shadow/*.rs).  32 B read per node + 4 B per visible entry.
 // ------------------------------------------------------------------------------------------------
+// prune != nullptr: one launch per hierarchy level [lo, hi) — a node is hidden for the frusta in which an ancestor pruned the
+// DFS: a statically batched mesh that is rendered (RdcControlFlow::Break, scene/mesh/mod.rs:725; renderer/bundle.rs:996-1001)
+// or, through lodp, a LOD object out of range.  prune[slot] = frusta hidden for the node's children.
 template <int NFT, int VAR>
-__global__ void __launch_bounds__(kBlock) k_cull(const NodeArrays a, const CullParams cp, const uint32_t *lodp)
+__global__ void __launch_bounds__(kBlock) k_cull(const NodeArrays a, const CullParams cp, const uint32_t *lodp, const uint32_t lo, const uint32_t hi,
+                                                 uint32_t *prune)
 {
     constexpr bool PRE = (VAR & 1) != 0;
     __shared__ __align__(16) unsigned char s_pref[PRE ? sizeof(PrefTable) : 16];
@@ -414,8 +439,8 @@ __global__ void __launch_bounds__(kBlock) k_cull(const NodeArrays a, const CullP
         pref_fill(*T, cp, NFT > 0 ? NFT : cp.nf);
         __syncthreads();
     }
-    const uint32_t slot = blockIdx.x * kBlock + threadIdx.x;
-    const bool valid = slot < a.cap;
+    const uint32_t slot = lo + blockIdx.x * kBlock + threadIdx.x;
+    const bool valid = slot < hi;
     uint32_t nf = 0u, mask = 0u;
     float2 wx = make_float2(0.f, 0.f), wy = wx, wz = wx;
     if (valid) {
@@ -426,7 +451,16 @@ __global__ void __launch_bounds__(kBlock) k_cull(const NodeArrays a, const CullP
         wz = ld_stream(a.wa[2] + slot);
     }
     uint32_t vis_bits = cull_warp<NFT, PRE>(valid, nf, mask, wx, wy, wz, cp, T);
-    if (lodp && vis_bits) vis_bits &= ~lodp[slot]; // frusta whose LOD filter hides the node or one of its ancestors
+    uint32_t hidden = 0u;
+    if (valid && (lodp || prune)) {
+        if (lodp) hidden = lodp[slot]; // frusta whose LOD filter hides the node or one of its ancestors
+        if (prune) {
+            const uint32_t p = a.parent[slot];
+            if (p != FYX_NONE) hidden |= prune[p];
+        }
+        vis_bits &= ~hidden;
+        if (prune) prune[slot] = hidden | ((nf & FYX_NODE_STATIC_BATCH) ? vis_bits : 0u);
+    }
     const uint32_t gi = vis_bits ? a.gidx[slot] : 0u;
     if (VAR & 2) compact_emit_warp(vis_bits, gi, slot, cp);
     else compact_emit<NFT>(vis_bits, gi, slot, cp);
@@ -1170,10 +1204,11 @@ static int cull_variant(int nf)
 {
     static int forced = [] {
         const char *e = getenv("FYX_CULL_VARIANT");
-        return (e && *e) ? atoi(e) & 3 : -1;
+        return (e && *e) ? atoi(e) & 7 : -1;
     }();
     if (forced >= 0) return forced;
-    return nf >= 2 ? 3 : 2;
+    (void)nf;
+    return 4; // measured (profiles/README.md, round 2): CTA-wide compaction, no pre-reject, FYX_UPDATE_ALL specialisation
 }
 
 #define FYX_DISPATCH_VAR(KERNEL, NF, VAR, ...)                                   \
@@ -1181,7 +1216,11 @@ static int cull_variant(int nf)
     case 0: launch_pdl(KERNEL<NF, 0>, __VA_ARGS__); break;                       \
     case 1: launch_pdl(KERNEL<NF, 1>, __VA_ARGS__); break;                       \
     case 2: launch_pdl(KERNEL<NF, 2>, __VA_ARGS__); break;                       \
-    default: launch_pdl(KERNEL<NF, 3>, __VA_ARGS__); break;                      \
+    case 3: launch_pdl(KERNEL<NF, 3>, __VA_ARGS__); break;                       \
+    case 4: launch_pdl(KERNEL<NF, 4>, __VA_ARGS__); break;                       \
+    case 5: launch_pdl(KERNEL<NF, 5>, __VA_ARGS__); break;                       \
+    case 6: launch_pdl(KERNEL<NF, 6>, __VA_ARGS__); break;                       \
+    default: launch_pdl(KERNEL<NF, 7>, __VA_ARGS__); break;                      \
     }
 
 void launch_update_level(cudaStream_t s, const NodeArrays &a, uint32_t lo, uint32_t hi, bool update_all, const CullParams *cull)
@@ -1190,7 +1229,7 @@ void launch_update_level(cudaStream_t s, const NodeArrays &a, uint32_t lo, uint3
     if (cull) {
         const unsigned g = grid_for(hi - lo);
         const uint32_t ua = update_all ? 1u : 0u;
-        const int var = cull_variant(cull->nf);
+        const int var = (cull_variant(cull->nf) & 3) | ((update_all && (cull_variant(cull->nf) & 4)) ? 4 : 0);
         switch (cull->nf) { // the usual frustum counts get an unrolled cull: camera, CSM cascades, cube faces
         case 1: FYX_DISPATCH_VAR(k_update_level, 1, var, g, kBlock, 0, s, a, lo, hi, ua, *cull); break;
         case 2: FYX_DISPATCH_VAR(k_update_level, 2, var, g, kBlock, 0, s, a, lo, hi, ua, *cull); break;
@@ -1202,7 +1241,8 @@ void launch_update_level(cudaStream_t s, const NodeArrays &a, uint32_t lo, uint3
     } else {
         CullParams none;
         none.nf = 0;
-        launch_pdl(k_update_level<-1, 0>, grid_for(hi - lo), kBlock, 0, s, a, lo, hi, update_all ? 1u : 0u, none);
+        if (update_all && (cull_variant(0) & 4)) launch_pdl(k_update_level<-1, 4>, grid_for(hi - lo), kBlock, 0, s, a, lo, hi, 1u, none);
+        else launch_pdl(k_update_level<-1, 0>, grid_for(hi - lo), kBlock, 0, s, a, lo, hi, update_all ? 1u : 0u, none);
     }
 }
 
@@ -1212,30 +1252,33 @@ void launch_cull_lights(cudaStream_t s, const NodeArrays &a, const CullParams &c
     k_cull_lights<<<grid_for(a.cap), kBlock, 0, s>>>(a, cp, d_out_ptrs, counts);
 }
 
-template <int NF> static void launch_cull_t(cudaStream_t s, unsigned g, int var, const NodeArrays &a, const CullParams &cp, const uint32_t *lodp)
+template <int NF> static void launch_cull_t(cudaStream_t s, unsigned g, int var, const NodeArrays &a, const CullParams &cp, const uint32_t *lodp, uint32_t lo,
+                                            uint32_t hi, uint32_t *prune)
 {
     switch (var) {
-    case 0: k_cull<NF, 0><<<g, kBlock, 0, s>>>(a, cp, lodp); break;
-    case 1: k_cull<NF, 1><<<g, kBlock, 0, s>>>(a, cp, lodp); break;
-    case 2: k_cull<NF, 2><<<g, kBlock, 0, s>>>(a, cp, lodp); break;
-    default: k_cull<NF, 3><<<g, kBlock, 0, s>>>(a, cp, lodp); break;
+    case 0: k_cull<NF, 0><<<g, kBlock, 0, s>>>(a, cp, lodp, lo, hi, prune); break;
+    case 1: k_cull<NF, 1><<<g, kBlock, 0, s>>>(a, cp, lodp, lo, hi, prune); break;
+    case 2: k_cull<NF, 2><<<g, kBlock, 0, s>>>(a, cp, lodp, lo, hi, prune); break;
+    default: k_cull<NF, 3><<<g, kBlock, 0, s>>>(a, cp, lodp, lo, hi, prune); break;
     }
 }
 
-void launch_cull(cudaStream_t s, const NodeArrays &a, const CullParams &cp, const uint32_t *lodp)
+void launch_cull_range(cudaStream_t s, const NodeArrays &a, const CullParams &cp, const uint32_t *lodp, uint32_t lo, uint32_t hi, uint32_t *prune)
 {
-    if (!a.cap) return;
-    const unsigned g = grid_for(a.cap);
-    const int var = cull_variant(cp.nf);
+    if (hi <= lo) return;
+    const unsigned g = grid_for(hi - lo);
+    const int var = cull_variant(cp.nf) & 3;
     switch (cp.nf) {
-    case 1: launch_cull_t<1>(s, g, var, a, cp, lodp); break;
-    case 2: launch_cull_t<2>(s, g, var, a, cp, lodp); break;
-    case 3: launch_cull_t<3>(s, g, var, a, cp, lodp); break;
-    case 4: launch_cull_t<4>(s, g, var, a, cp, lodp); break;
-    case 6: launch_cull_t<6>(s, g, var, a, cp, lodp); break;
-    default: launch_cull_t<0>(s, g, var, a, cp, lodp); break;
+    case 1: launch_cull_t<1>(s, g, var, a, cp, lodp, lo, hi, prune); break;
+    case 2: launch_cull_t<2>(s, g, var, a, cp, lodp, lo, hi, prune); break;
+    case 3: launch_cull_t<3>(s, g, var, a, cp, lodp, lo, hi, prune); break;
+    case 4: launch_cull_t<4>(s, g, var, a, cp, lodp, lo, hi, prune); break;
+    case 6: launch_cull_t<6>(s, g, var, a, cp, lodp, lo, hi, prune); break;
+    default: launch_cull_t<0>(s, g, var, a, cp, lodp, lo, hi, prune); break;
     }
 }
+
+void launch_cull(cudaStream_t s, const NodeArrays &a, const CullParams &cp, const uint32_t *lodp) { launch_cull_range(s, a, cp, lodp, 0u, a.cap, nullptr); }
 
 void launch_fold_bones(cudaStream_t s, const NodeArrays &a, const FoldArrays &fa, const CullParams *cull)
 {

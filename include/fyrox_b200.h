@@ -59,7 +59,10 @@ typedef enum fyx_status {
 #define FYX_NODE_ALIVE           (1u << 4)
 #define FYX_NODE_RENDERABLE      (1u << 5)
 #define FYX_NODE_LIGHT           (1u << 6)  /* the node is a BaseLight (point / spot / directional): fyx_cull_lights */
-#define FYX_NODE_INPUT_MASK      0x7Fu
+#define FYX_NODE_STATIC_BATCH    (1u << 7)  /* Mesh with BatchingMode::Static: when it is rendered for a frustum its children are
+                                            * not visited for that frustum (RdcControlFlow::Break, scene/mesh/mod.rs:701-725) and its
+                                            * instance carries the identity world matrix */
+#define FYX_NODE_INPUT_MASK      0xFFu
 /* Computed bits, readable through fyx_get_global_flags (Base::global_visibility / is_globally_enabled,
  * scene/base.rs:751-770) */
 #define FYX_NODE_GLOBAL_VISIBILITY (1u << 8)

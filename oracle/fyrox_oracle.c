@@ -463,6 +463,7 @@ typedef struct orc_node {
     /* Base (scene/base.rs:389-483) */
     float local_matrix[16]; /* Transform::matrix() cache */
     int visibility, enabled, frustum_culling, cast_shadows, is_light;
+    int static_batch; /* BatchingMode::Static: collect_render_data returns RdcControlFlow::Break when the mesh is rendered */
     uint32_t render_mask;
     uint32_t parent;
     uint32_t *children;
@@ -664,6 +665,7 @@ orc_graph *orc_graph_build(uint32_t capacity, const uint32_t *parent, const uint
         n->frustum_culling = !!(f & ORC_FLAG_FRUSTUM_CULLING);
         n->cast_shadows = !!(f & ORC_FLAG_CAST_SHADOWS);
         n->is_light = !!(f & ORC_FLAG_LIGHT);
+        n->static_batch = !!(f & ORC_FLAG_STATIC_BATCH);
         if (render_mask) n->render_mask = render_mask[i];
         if (local_m16) memcpy(n->local_matrix, local_m16 + 16 * (size_t)i, 64);
         if (local_aabb6 && n->kind == ORC_KIND_MESH) {
@@ -962,8 +964,9 @@ typedef struct {
     size_t cap, count;
 } cull_ctx;
 
-/* iterate_recursive — renderer/bundle.rs:988-1004; Mesh::collect_render_data — scene/mesh/mod.rs:691-698.
- * No LOD groups / static batching in the restated scenes (lod_filter all true; always Continue). */
+/* iterate_recursive — renderer/bundle.rs:988-1004; Mesh::collect_render_data — scene/mesh/mod.rs:691-725.
+ * A statically batched mesh that IS rendered returns RdcControlFlow::Break (mesh/mod.rs:725): the DFS does not descend
+ * into its children; one that fails should_be_rendered / the shadow test returns Continue like everybody else. */
 static void iterate_recursive(uint32_t h, cull_ctx *c)
 {
     const orc_node *n = node_at(c->g, h);
@@ -972,6 +975,7 @@ static void iterate_recursive(uint32_t h, cull_ctx *c)
         if (orc_node_should_be_rendered(c->g, h, c->f, c->render_mask) && !(c->shadow_pass && !n->cast_shadows)) {
             if (c->count < c->cap) c->out[c->count] = h;
             c->count++;
+            if (n->static_batch) return; /* RdcControlFlow::Break */
         }
     }
     for (uint32_t i = 0; i < n->n_children; ++i)
@@ -1050,6 +1054,7 @@ static void iterate_recursive_lod(uint32_t h, cull_lod_ctx *x)
         if (orc_node_should_be_rendered(x->c.g, h, x->c.f, x->c.render_mask) && !(x->c.shadow_pass && !n->cast_shadows)) {
             if (x->c.count < x->c.cap) x->c.out[x->c.count] = h;
             x->c.count++;
+            if (n->static_batch) return; /* RdcControlFlow::Break */
         }
     }
     for (uint32_t i = 0; i < n->n_children; ++i) iterate_recursive_lod(n->children[i], x);
@@ -1224,7 +1229,7 @@ uint64_t orc_node_instance(const orc_graph *g, uint32_t node, const float view[1
         orc_mat4_mul(vp, world, wvp);
         return 0;
     }
-    int skinned = 0;
+    int skinned = n->static_batch; /* a static batch is pushed with world_transform = identity (mesh/mod.rs:716) */
     for (uint32_t si = 0; si < n->n_surfaces; ++si)
         if (n->surfaces[si].n_bones) skinned = 1;
     if (skinned) orc_mat4_identity(world);

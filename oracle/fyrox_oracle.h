@@ -126,6 +126,7 @@ orc_graph *orc_graph_build(uint32_t capacity, const uint32_t *parent, const uint
 #define ORC_FLAG_ALIVE           (1u << 4)
 #define ORC_FLAG_RENDERABLE      (1u << 5)   /* node kind emits render data (Mesh) */
 #define ORC_FLAG_LIGHT           (1u << 6)   /* node is a BaseLight (point / spot / directional) */
+#define ORC_FLAG_STATIC_BATCH    (1u << 7)   /* Mesh::batching_mode == BatchingMode::Static (scene/mesh/mod.rs:701-725) */
 
 /* property setters; the three tracked ones push messages like TrackedProperty::deref_mut (base.rs:343-352) */
 void orc_node_set_local_matrix(orc_graph *g, uint32_t n, const float m16[16]);

@@ -11,7 +11,7 @@ import pytest
 import fyrox_b200 as fb
 import oracle_binding as ob
 from fyrox_b200.scenegen import Scene
-from helpers import bits_equal, preorder_rank, random_graph, scene_pair
+from helpers import bits_equal, cube_frusta, preorder_rank, random_graph, scene_pair
 
 pytestmark = pytest.mark.gpu
 
@@ -80,6 +80,70 @@ def test_instances_of_generated_scene_match_oracle(ctx):
     ctx.cull([o[3] for o in obs])
     for f, (v, p, fo_, _) in enumerate(obs):
         check_instances(og, ctx, f, fo_, v, p, bundle)
+
+
+def test_static_batches_prune_the_dfs_like_rdc_control_flow_break(ctx):
+    """A statically batched mesh (BatchingMode::Static) that is rendered for a frustum returns RdcControlFlow::Break: its
+    children are not visited FOR THAT FRUSTUM (scene/mesh/mod.rs:701-725, renderer/bundle.rs:996-1001); one that is culled
+    lets the DFS continue.  Random forest with static batches at every depth, nested ones, six frusta with masks and a shadow
+    pass; fused-capable entry points (they must notice and run level by level), flags set later through fyx_set_flags."""
+    rng = np.random.default_rng(41)
+    parent, flags, mask, local, aabb = random_graph(rng, 5000, p_orphan=0.01, max_depth_bias=0.2)
+    renderable = np.nonzero((flags & fb.NODE_RENDERABLE) != 0)[0]
+    static = rng.choice(renderable, len(renderable) // 6, replace=False)
+    flags_s = flags.copy()
+    flags_s[static] |= fb.NODE_STATIC_BATCH
+    og = ob.Graph.build(parent, flags_s, mask, local, aabb)
+    og.L.orc_graph_drop_messages(og.h)
+    og.update_hierarchical_data()
+    fos, ffs = cube_frusta(radius=200.0)
+    cam = np.array([0xFFFFFFFF, 0x0000FFFF, 0xFFFFFFFF, 0xFFFF0000, 0xFFFFFFFF, 0xFFFFFFFF], np.uint32)
+    pf = np.array([0, 0, fb.PASS_SHADOW, 0, fb.PASS_SHADOW, 0], np.uint32)
+    ctx.set_topology(parent, flags_s, mask, aabb)
+    ctx.set_local_matrices(local)
+    pruned_something = 0
+    for entry in ("update_and_cull", "render_prep", "cull"):
+        if entry == "update_and_cull":
+            ctx.update_and_cull(ffs, fb.UPDATE_ALL, cam_mask=cam, pass_flags=pf)
+        elif entry == "render_prep":
+            ctx.render_prep(update_flags=fb.UPDATE_ALL, frusta=ffs, cam_mask=cam, pass_flags=pf)
+        else:
+            ctx.cull(ffs, cam_mask=cam, pass_flags=pf)
+        for f, fo in enumerate(fos):
+            want = np.sort(og.from_graph(fo, int(cam[f]), bool(pf[f] & fb.PASS_SHADOW)))
+            got = np.sort(ctx.get_visible(f))
+            assert np.array_equal(got, want), f"{entry} frustum {f}: {got.size} vs {want.size}"
+    # the pruning really happens: without the static flags more nodes are listed
+    og0 = ob.Graph.build(parent, flags, mask, local, aabb)
+    og0.L.orc_graph_drop_messages(og0.h)
+    og0.update_hierarchical_data()
+    for f, fo in enumerate(fos):
+        pruned_something += og0.from_graph(fo, int(cam[f]), bool(pf[f] & fb.PASS_SHADOW)).size - og.from_graph(fo, int(cam[f]), bool(pf[f] & fb.PASS_SHADOW)).size
+    assert pruned_something > 20
+    # flags arriving later through fyx_set_flags switch the level-by-level cull on as well
+    with fb.Context() as c2:
+        c2.set_topology(parent, flags, mask, aabb)
+        c2.set_local_matrices(local)
+        c2.update_and_cull(ffs, fb.UPDATE_ALL, cam_mask=cam, pass_flags=pf)
+        c2.set_flags(flags_s[static], static.astype(np.uint32))
+        c2.update_and_cull(ffs, fb.UPDATE_INCREMENTAL, cam_mask=cam, pass_flags=pf)
+        for f, fo in enumerate(fos):
+            want = np.sort(og.from_graph(fo, int(cam[f]), bool(pf[f] & fb.PASS_SHADOW)))
+            assert np.array_equal(np.sort(c2.get_visible(f)), want)
+    # a static batch is pushed with the identity as its world matrix (mesh/mod.rs:716)
+    ctx.enable_instances()
+    view, vp, fo, ff = observer((0, 0, 0), (0, 0, -1), zf=400.0, fovy=np.deg2rad(120.0))
+    ctx.update_and_cull([ff], fb.UPDATE_ALL)
+    inst = ctx.pack_instances(0, view, vp)
+    st = set(int(x) for x in static)
+    seen = 0
+    for k, nd in enumerate(inst["node"]):
+        si, w, wvp = og.instance(int(nd), view, vp)
+        assert inst["world"][k].tobytes() == w.tobytes() and inst["wvp"][k].tobytes() == wvp.tobytes()
+        if int(nd) in st:
+            assert np.array_equal(inst["world"][k], np.eye(4, dtype=np.float32).reshape(16))
+            seen += 1
+    assert seen > 0
 
 
 def test_bone_matrix_blocks_of_packed_instances_match_oracle(ctx):

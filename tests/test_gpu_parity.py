@@ -720,19 +720,21 @@ def test_add_link_remove_then_incremental_update_with_only_the_new_matrices(ctx)
     fo, ff = camera_frustum(zfar=800.0, fovy=np.deg2rad(110.0))
     ctx.update_and_cull([ff], fb.UPDATE_ALL)
 
-    # topology B: revive dead pool records as new nodes, re-parent some old nodes, remove some leaves
+    # topology B: revive dead pool records as new nodes, re-parent some old nodes, remove some leaves (a removed node takes
+    # its sub-tree with it in the reference, so nothing may hang under a removed node)
     dead = np.nonzero((flags & fb.NODE_ALIVE) == 0)[0]
     new_nodes = dead[: len(dead) // 2].astype(np.uint32)
     parent2, flags2, local2 = parent.copy(), flags.copy(), local.copy()
-    flags2[new_nodes] = fb.NODE_DEFAULT | fb.NODE_RENDERABLE
-    parent2[new_nodes] = rng.choice(alive, len(new_nodes)).astype(np.uint32)
-    new_m = np.stack([ob.translation(*rng.uniform(-3, 3, 3)) for _ in new_nodes]).astype(np.float32)
-    local2[new_nodes] = new_m
     has_child = np.zeros(n, bool)
     has_child[parent[parent != NONE]] = True
     leaves = alive[(~has_child[alive]) & (alive != 0) & ~np.isin(alive, trs_nodes)]
     removed = leaves[:150]
     flags2[removed] = 0
+    survivors = alive[~np.isin(alive, removed)]
+    flags2[new_nodes] = fb.NODE_DEFAULT | fb.NODE_RENDERABLE
+    parent2[new_nodes] = rng.choice(survivors, len(new_nodes)).astype(np.uint32)
+    new_m = np.stack([ob.translation(*rng.uniform(-3, 3, 3)) for _ in new_nodes]).astype(np.float32)
+    local2[new_nodes] = new_m
     movers = leaves[150:300]
     parent2[movers] = rng.choice(new_nodes, len(movers)).astype(np.uint32)  # old nodes under the new ones
     ctx.set_topology(parent2, flags2, mask, aabb)
