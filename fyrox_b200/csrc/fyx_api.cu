@@ -216,6 +216,7 @@ struct fyx_ctx {
     DevBuf b_counts_packed, b_counts_all;
     uint32_t *h_counts_all = nullptr; // pinned nranks*FYX_MAX_FRUSTA
     bool want_peer = true, want_hostseg = true;
+    unsigned peer_push_ctas = 96;
     bool exchange_built = false, hostseg_ready = false, hostseg_registered = false;
     uint32_t exchange_slots = 0, exch_nf_cap = 0;
     uint64_t exch_total_cap = 0, gather_epoch = 0;

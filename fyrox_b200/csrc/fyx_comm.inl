@@ -277,6 +277,8 @@ extern "C" int32_t fyx_comm_init(fyx_ctx *c, int32_t nranks, int32_t rank, const
     const char *ex = getenv("FYX_EXCHANGE"), *hs = getenv("FYX_HOSTSEG");
     c->want_peer = !(ex && strcmp(ex, "nccl") == 0);
     c->want_hostseg = !(hs && strcmp(hs, "0") == 0);
+    const char *pc = getenv("FYX_PEER_CTAS");
+    c->peer_push_ctas = (pc && atoi(pc) > 0) ? (unsigned)atoi(pc) : 96u;
     int32_t rc;
     if ((rc = dev_ensure(c, c->b_counts_packed, sizeof(uint32_t) * FYX_MAX_FRUSTA))) return rc;
     if ((rc = dev_ensure(c, c->b_counts_all, sizeof(uint32_t) * FYX_MAX_FRUSTA * nranks))) return rc;
@@ -392,15 +394,17 @@ static int32_t allgather_enqueue(fyx_ctx *c, VisSlot &V, cudaStream_t s)
         pp.own_list[f] = V.b_vis[f].as<uint32_t>();
         V.gath_ptr[f] = peer_list(pp, c->rank, (uint32_t)(V.epoch & 1), f);
     }
-    // enough CTAs to keep the NVLink egress busy, few enough to slip in beside the skinning kernel
-    launch_peer_exchange(s, pp, 96);
-    c->launches += 3;
-    CU(cudaGetLastError());
-    // counts of every rank + totals to the host (small): the host segment needs the offsets, the getters the totals
+    launch_peer_counts(s, pp);
+    // the counts of every rank are on this device now: start their (small) copy to the host right away — the host segment
+    // needs the offsets, the getters the totals — while the lists are still travelling
     uint32_t *h = P.h_counts + (size_t)(V.epoch & 1) * 2 * kPeerMaxRanks * FYX_MAX_FRUSTA;
     const PeerCtrl *ctrl = peer_ctrl(pp, c->rank);
     CU(cudaMemcpyAsync(h, ctrl->counts[V.epoch & 1], sizeof(uint32_t) * kPeerMaxRanks * FYX_MAX_FRUSTA, cudaMemcpyDeviceToHost, s));
     CU(cudaEventRecord(V.ev_counts_all, s));
+    // enough CTAs to keep the NVLink egress busy, few enough to slip in beside the skinning kernel
+    launch_peer_push(s, pp, c->peer_push_ctas);
+    c->launches += 3;
+    CU(cudaGetLastError());
     return FYX_OK;
 }
 

@@ -230,7 +230,8 @@ __host__ __device__ inline uint32_t *peer_list(const PeerParams &pp, int r, uint
 {
     return reinterpret_cast<uint32_t *>(pp.base[r] + kPeerCtrlBytes) + ((size_t)slot * pp.nf_cap + f) * pp.total_cap;
 }
-void launch_peer_exchange(cudaStream_t s, const PeerParams &pp, unsigned push_ctas);
+void launch_peer_counts(cudaStream_t s, const PeerParams &pp);                   // publish this rank's counts, wait for everybody's
+void launch_peer_push(cudaStream_t s, const PeerParams &pp, unsigned push_ctas); // store the lists into every rank's buffers, wait for everybody's
 
 // error bits written by kernels into d_err
 constexpr uint32_t E_NOT_AFFINE = 1u;

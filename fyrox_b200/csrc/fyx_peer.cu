@@ -125,9 +125,10 @@ __global__ void __launch_bounds__(32) k_peer_wait(const PeerParams pp)
     }
 }
 
-void launch_peer_exchange(cudaStream_t s, const PeerParams &pp, unsigned push_ctas)
+void launch_peer_counts(cudaStream_t s, const PeerParams &pp) { k_peer_counts<<<1, 256, 0, s>>>(pp); }
+
+void launch_peer_push(cudaStream_t s, const PeerParams &pp, unsigned push_ctas)
 {
-    k_peer_counts<<<1, 256, 0, s>>>(pp);
     k_peer_push<<<push_ctas, 256, 0, s>>>(pp);
     k_peer_wait<<<1, 32, 0, s>>>(pp);
 }
