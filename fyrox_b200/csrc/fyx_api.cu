@@ -119,6 +119,8 @@ struct fyx_ctx {
     NodeArrays a{};
     DevBuf b_parent, b_flags, b_mask, b_gidx, b_L[3], b_G[3], b_la[3], b_wa[3], b_slot_of_node;
     bool have_topology = false, updated_once = false;
+    SubforestPlan sf{};  // deep levels walked by one launch (fyx_internal.h); n_ctas = 0: one launch per level everywhere
+    DevBuf b_sf_rng;
     DevBuf b_statics; // fyx_transform_statics per slot, allocated by the first fyx_set_transform_statics
     bool have_statics = false;
     DevBuf b_trs;     // fyx_trs per slot: the last position/rotation/scale sent for each node (first TRS call allocates)
@@ -465,9 +467,14 @@ int32_t run_update(fyx_ctx *c, uint32_t update_flags, const CullParams *cull)
         launch_snapshot_bones(c->stream, c->a, c->n_late, c->b_late_slot.as<uint32_t>(), c->b_stale_pos.as<float4>());
         c->launches++;
     }
-    for (size_t l = 0; l < nl; ++l) {
+    const size_t nl_wide = c->sf.n_ctas ? std::min<size_t>(nl, c->sf.first_level) : nl;
+    for (size_t l = 0; l < nl_wide; ++l) {
         launch_update_level(c->stream, c->a, c->level_off[l], c->level_off[l + 1], all, cull);
         c->launches += (c->level_off[l + 1] > c->level_off[l]);
+    }
+    if (c->sf.n_ctas) { // the deep levels (small sub-trees: skeletons) in one launch
+        launch_update_subforest(c->stream, c->a, c->sf, all, cull);
+        c->launches++;
     }
     if (c->fold.n) {
         launch_fold_bones(c->stream, c->a, c->fold, cull);
@@ -634,7 +641,7 @@ extern "C" void fyx_destroy(fyx_ctx *c)
     inst_free(c);
     anim_free(c);
     DevBuf *bufs[] = {&c->b_parent, &c->b_flags, &c->b_mask, &c->b_gidx, &c->b_slot_of_node, &c->d_stage, &c->b_statics, &c->b_trs, &c->b_vblk,
-                      &c->b_prune, &c->b_opos, &c->b_onrm, &c->b_bs, &c->b_bs_w, &c->b_surf_of_slot, &c->b_surf_bones, &c->b_palette, &c->b_bone_slot, &c->b_tiles, &c->b_fold_node,
+                      &c->b_prune, &c->b_sf_rng, &c->b_opos, &c->b_onrm, &c->b_bs, &c->b_bs_w, &c->b_surf_of_slot, &c->b_surf_bones, &c->b_palette, &c->b_bone_slot, &c->b_tiles, &c->b_fold_node,
                       &c->b_fold_begin, &c->b_fold_bone, &c->b_fold_stale_idx, &c->b_late_slot, &c->b_stale_pos, &c->b_counts_packed, &c->b_counts_all};
     for (DevBuf *b : bufs) dev_free(*b);
     for (int i = 0; i < 3; ++i) {
@@ -893,6 +900,64 @@ extern "C" int32_t fyx_set_topology(fyx_ctx *c, uint32_t capacity, uint32_t root
         }
     }
 
+    // Sub-forest plan: from the first level on whose sub-trees are all small (<= kSfCap nodes) and numerous relative to the
+    // level's width (skeletons under a wide level of meshes), whole sub-trees are grouped so that no level of a group has
+    // more than kSfCap nodes; a group is one CTA of k_update_subforest.  Not worth it for wide deep levels (each launch is
+    // busy by itself): FYX_SUBFOREST=1 forces it on, =0 off.
+    std::vector<uint2> sf_rng;
+    uint32_t sf_first = 0, sf_levels = 0, sf_ctas = 0;
+    {
+        const char *env = getenv("FYX_SUBFOREST");
+        const int mode = (env && *env) ? atoi(env) : -1;
+        const size_t nlev = level_off.size() ? level_off.size() - 1 : 0;
+        if (mode != 0 && nlev >= 4 && n_slots) {
+            std::vector<uint32_t> size(n_slots, 1u);
+            for (uint32_t s2 = n_slots; s2-- > 0;)
+                if (h_parent[s2] != FYX_NONE) size[h_parent[s2]] += size[s2];
+            size_t pick = 0;
+            for (size_t l = 1; l + 3 <= nlev; ++l) {
+                uint32_t mx = 0;
+                for (uint32_t s2 = level_off[l]; s2 < level_off[l + 1]; ++s2) mx = std::max(mx, size[s2]);
+                const uint64_t cnt = level_off[l + 1] - level_off[l], deep = n_slots - level_off[l];
+                if (cnt && mx <= kSfCap && deep >= 8 * cnt) { pick = l; break; }
+            }
+            const uint64_t deep_nodes = pick ? n_slots - level_off[pick] : 0;
+            const bool small_levels = pick && deep_nodes / (nlev - pick) < 262144u;
+            if (pick && (mode == 1 || small_levels)) {
+                sf_first = (uint32_t)pick;
+                sf_levels = (uint32_t)(nlev - pick);
+                // per level, where each sub-tree's nodes start: the sub-trees of level `pick` in slot order own consecutive ranges
+                const uint32_t n_tiles = level_off[pick + 1] - level_off[pick];
+                std::vector<uint32_t> tile_of(n_slots - level_off[pick]);
+                std::vector<uint32_t> cnt((size_t)n_tiles * sf_levels, 0u);
+                for (uint32_t s2 = level_off[pick]; s2 < n_slots; ++s2) {
+                    const uint32_t rel = s2 - level_off[pick];
+                    tile_of[rel] = (s2 < level_off[pick + 1]) ? rel : tile_of[h_parent[s2] - level_off[pick]];
+                }
+                for (size_t l = pick; l < nlev; ++l)
+                    for (uint32_t s2 = level_off[l]; s2 < level_off[l + 1]; ++s2) cnt[(size_t)tile_of[s2 - level_off[pick]] * sf_levels + (l - pick)]++;
+                std::vector<uint32_t> cursor(sf_levels), acc(sf_levels, 0u);
+                for (uint32_t li = 0; li < sf_levels; ++li) cursor[li] = level_off[pick + li];
+                auto close_group = [&]() {
+                    for (uint32_t li = 0; li < sf_levels; ++li) {
+                        sf_rng.push_back(make_uint2(cursor[li], cursor[li] + acc[li]));
+                        cursor[li] += acc[li];
+                        acc[li] = 0;
+                    }
+                    sf_ctas++;
+                };
+                for (uint32_t t = 0; t < n_tiles; ++t) {
+                    bool fits = true;
+                    for (uint32_t li = 0; li < sf_levels; ++li)
+                        if (acc[li] + cnt[(size_t)t * sf_levels + li] > kSfCap) fits = false;
+                    if (!fits) close_group();
+                    for (uint32_t li = 0; li < sf_levels; ++li) acc[li] += cnt[(size_t)t * sf_levels + li];
+                }
+                close_group();
+            }
+        }
+    }
+
     // Per-node data that is NOT an argument of this call survives it: local matrices, TRS records, transform statics,
     // bundle ids and LOD ranges of every node that was alive before and still is are carried from their old slot to the
     // new one on the device (nodes that were not alive start from the defaults).  old_of_new[s] = the old slot.
@@ -994,6 +1059,15 @@ extern "C" int32_t fyx_set_topology(fyx_ctx *c, uint32_t capacity, uint32_t root
     c->root = root;
     c->n_renderable = n_renderable;
     c->maybe_static_batch = any_static;
+    c->sf = SubforestPlan{};
+    if (sf_ctas) {
+        if ((rc = dev_ensure(c, c->b_sf_rng, sf_rng.size() * sizeof(uint2)))) return rc;
+        CU(cudaMemcpy(c->b_sf_rng.p, sf_rng.data(), sf_rng.size() * sizeof(uint2), cudaMemcpyHostToDevice));
+        c->sf.n_ctas = sf_ctas;
+        c->sf.n_levels = sf_levels;
+        c->sf.first_level = sf_first;
+        c->sf.rng = c->b_sf_rng.as<uint2>();
+    }
     c->slot_of_node.swap(slot_of_node);
     c->node_of_slot.swap(node_of_slot);
     c->level_off.swap(level_off);

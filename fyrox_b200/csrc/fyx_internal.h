@@ -152,6 +152,16 @@ void launch_bone_block_index(cudaStream_t s, uint32_t n, const uint32_t *inst_no
 void launch_bone_blocks(cudaStream_t s, uint32_t n, const uint32_t *inst_node, const uint32_t *slot_of_node, const uint32_t *surf_of_slot, const uint2 *surf_bones,
                         const float *palette, const uint32_t *block_of_inst, float *blocks);
 
+// Sub-forest plan (fyx_set_topology): the deep levels of the hierarchy — small sub-trees such as skeletons — are cut into groups
+// of whole sub-trees; one CTA walks all levels of its group with CTA-wide barriers instead of one kernel launch per level.
+// Slots are sorted by (depth, parent slot), so the nodes of a group form ONE contiguous slot range in every level.
+constexpr uint32_t kSfCap = 384; // nodes per level and CTA (the previous level's matrices stay in shared memory)
+struct SubforestPlan {
+    uint32_t n_ctas = 0, n_levels = 0, first_level = 0; // deep levels = [first_level, first_level + n_levels)
+    const uint2 *rng = nullptr;                        // [cta][level] = slot range (begin, end)
+};
+void launch_update_subforest(cudaStream_t s, const NodeArrays &a, const SubforestPlan &sf, bool update_all, const CullParams *cull);
+
 // ---- launchers (fyx_kernels.cu) ----
 void launch_update_level(cudaStream_t s, const NodeArrays &a, uint32_t lo, uint32_t hi, bool update_all,
                          const CullParams *cull /* nullptr = no fused cull */);

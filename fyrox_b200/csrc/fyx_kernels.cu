@@ -422,6 +422,118 @@ __global__ void __launch_bounds__(kBlock) k_update_level(const NodeArrays a, con
 }
 
 // ------------------------------------------------------------------------------------------------
+// The deep levels of the hierarchy in ONE launch (SubforestPlan, fyx_internal.h): a CTA owns a group of whole
+// sub-trees — e.g. a dozen 64-bone skeletons — and walks their levels itself.  In every level the group's nodes are one
+// contiguous slot range (coalesced like a level kernel); the matrices and flags of the previous level stay in shared
+// memory for the children.  Same arithmetic, flags, change tracking and fused cull as k_update_level; what it removes
+// is a kernel launch per level for levels of a few thousand nodes (C3: six skeleton levels of 10 k - 320 k nodes).
+// ------------------------------------------------------------------------------------------------
+template <int NFT, bool UA>
+__global__ void __launch_bounds__(kBlock) k_update_subforest(const NodeArrays a, const uint2 *__restrict__ rng, const int n_levels,
+                                                             const uint32_t update_all, const CullParams cp)
+{
+    pdl_trigger();
+    __shared__ float4 s_g[2][3][kSfCap];
+    __shared__ uint32_t s_f[2][kSfCap];
+    const uint2 *my = rng + (size_t)blockIdx.x * n_levels;
+    pdl_wait();
+    uint32_t prevA = 0u, prevB = 0u;
+    for (int li = 0; li < n_levels; ++li) {
+        const uint2 r = my[li];
+        const int cur = li & 1, prv = cur ^ 1;
+        for (uint32_t base = r.x; base < r.y; base += kBlock) { // the same trip count for every thread of the CTA
+            const uint32_t slot = base + threadIdx.x;
+            const bool valid = slot < r.y;
+            uint32_t nf = 0u;
+            float2 wx = make_float2(0.f, 0.f), wy = wx, wz = wx;
+            if (valid) {
+                const uint32_t p = a.parent[slot];
+                const uint32_t f = a.flags[slot];
+                Affine L;
+                float2 lx, ly, lz;
+                if (UA) {
+                    L.r0 = ld_stream(a.L[0] + slot);
+                    L.r1 = ld_stream(a.L[1] + slot);
+                    L.r2 = ld_stream(a.L[2] + slot);
+                    lx = ld_stream(a.la[0] + slot);
+                    ly = ld_stream(a.la[1] + slot);
+                    lz = ld_stream(a.la[2] + slot);
+                }
+                const bool in_prev = (li > 0) && (p >= prevA) && (p < prevB); // the parent was handled by this CTA one level up
+                const uint32_t pf = in_prev ? s_f[prv][p - prevA]
+                                            : ((p != FYX_NONE) ? a.flags[p]
+                                                               : (FYX_NODE_GLOBAL_VISIBILITY | FYX_NODE_GLOBAL_ENABLED | ((f & F_ROOT) ? FYX_NODE_REACHABLE : 0u)));
+                const bool dirty = UA || update_all || (f & F_DIRTY_SELF) || (pf & F_DIRTY);
+                nf = f & ~(FYX_NODE_GLOBAL_VISIBILITY | FYX_NODE_GLOBAL_ENABLED | FYX_NODE_REACHABLE | F_DIRTY | F_DIRTY_SELF);
+                if ((pf & FYX_NODE_GLOBAL_VISIBILITY) && (f & FYX_NODE_VISIBILITY)) nf |= FYX_NODE_GLOBAL_VISIBILITY;
+                if ((pf & FYX_NODE_GLOBAL_ENABLED) && (f & FYX_NODE_ENABLED)) nf |= FYX_NODE_GLOBAL_ENABLED;
+                nf |= pf & FYX_NODE_REACHABLE;
+                if (dirty) nf |= F_DIRTY;
+                a.flags[slot] = nf;
+                const uint32_t me = slot - r.x;
+                s_f[cur][me] = nf;
+                Affine Gm;
+                if (dirty) {
+                    if (!UA) {
+                        L.r0 = ld_stream(a.L[0] + slot);
+                        L.r1 = ld_stream(a.L[1] + slot);
+                        L.r2 = ld_stream(a.L[2] + slot);
+                        lx = ld_stream(a.la[0] + slot);
+                        ly = ld_stream(a.la[1] + slot);
+                        lz = ld_stream(a.la[2] + slot);
+                    }
+                    Affine P;
+                    if (in_prev) {
+                        P.r0 = s_g[prv][0][p - prevA];
+                        P.r1 = s_g[prv][1][p - prevA];
+                        P.r2 = s_g[prv][2][p - prevA];
+                    } else if (p != FYX_NONE) {
+                        P.r0 = a.G[0][p];
+                        P.r1 = a.G[1][p];
+                        P.r2 = a.G[2][p];
+                    } else {
+                        P = affine_identity();
+                    }
+                    Gm = affine_mul(P, L);
+                    st_stream(a.G[0] + slot, Gm.r0);
+                    st_stream(a.G[1] + slot, Gm.r1);
+                    st_stream(a.G[2] + slot, Gm.r2);
+                    wx = aabb_transform_row(Gm.r0, lx, ly, lz);
+                    wy = aabb_transform_row(Gm.r1, lx, ly, lz);
+                    wz = aabb_transform_row(Gm.r2, lx, ly, lz);
+                    st_stream(a.wa[0] + slot, wx);
+                    st_stream(a.wa[1] + slot, wy);
+                    st_stream(a.wa[2] + slot, wz);
+                } else {
+                    // clean node: its children may be dirty and need its (unchanged) matrix
+                    Gm.r0 = a.G[0][slot];
+                    Gm.r1 = a.G[1][slot];
+                    Gm.r2 = a.G[2][slot];
+                    if (NFT >= 0) {
+                        wx = ld_stream(a.wa[0] + slot);
+                        wy = ld_stream(a.wa[1] + slot);
+                        wz = ld_stream(a.wa[2] + slot);
+                    }
+                }
+                s_g[cur][0][me] = Gm.r0;
+                s_g[cur][1][me] = Gm.r1;
+                s_g[cur][2][me] = Gm.r2;
+            }
+            if (NFT >= 0) {
+                const bool cand = valid && !(nf & F_SKINNED);
+                const uint32_t mask = cand ? a.mask[slot] : 0u;
+                const uint32_t vis_bits = cull_warp<(NFT > 0 ? NFT : 0), false>(cand, nf, mask, wx, wy, wz, cp, nullptr);
+                const uint32_t gi = vis_bits ? a.gidx[slot] : 0u;
+                compact_emit<(NFT > 0 ? NFT : 0)>(vis_bits, gi, slot, cp);
+            }
+        }
+        __syncthreads(); // this level's rows are complete (and the previous level's are no longer read)
+        prevA = r.x;
+        prevB = r.y;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // Stand-alone cull over all slots (static scene / extra passes: every shadow pass re-runs the cull
 // with its own frustum, renderer/shadow/*.rs).  32 B read per node + 4 B per visible entry.
 // ------------------------------------------------------------------------------------------------
@@ -1243,6 +1355,28 @@ void launch_update_level(cudaStream_t s, const NodeArrays &a, uint32_t lo, uint3
         none.nf = 0;
         if (update_all && (cull_variant(0) & 4)) launch_pdl(k_update_level<-1, 4>, grid_for(hi - lo), kBlock, 0, s, a, lo, hi, 1u, none);
         else launch_pdl(k_update_level<-1, 0>, grid_for(hi - lo), kBlock, 0, s, a, lo, hi, update_all ? 1u : 0u, none);
+    }
+}
+
+template <int NFT> static void launch_subforest_t(cudaStream_t s, const NodeArrays &a, const SubforestPlan &sf, bool ua, const CullParams &cp)
+{
+    if (ua) launch_pdl(k_update_subforest<NFT, true>, sf.n_ctas, kBlock, 0, s, a, sf.rng, (int)sf.n_levels, 1u, cp);
+    else launch_pdl(k_update_subforest<NFT, false>, sf.n_ctas, kBlock, 0, s, a, sf.rng, (int)sf.n_levels, 0u, cp);
+}
+
+void launch_update_subforest(cudaStream_t s, const NodeArrays &a, const SubforestPlan &sf, bool update_all, const CullParams *cull)
+{
+    if (!sf.n_ctas || !sf.n_levels) return;
+    if (!cull) {
+        CullParams none;
+        none.nf = 0;
+        launch_subforest_t<-1>(s, a, sf, update_all, none);
+        return;
+    }
+    switch (cull->nf) {
+    case 1: launch_subforest_t<1>(s, a, sf, update_all, *cull); break;
+    case 6: launch_subforest_t<6>(s, a, sf, update_all, *cull); break;
+    default: launch_subforest_t<0>(s, a, sf, update_all, *cull); break;
     }
 }
 

@@ -34,3 +34,11 @@ def test_cull_variants_match_the_oracle(variant):
 def test_tma_skinning_variants_match_the_oracle(variant):
     """k_skin_tma: vertex blocks staged by cp.async.bulk + mbarrier rings (fyx_kernels.cu)."""
     _run({"FYX_SKIN_VARIANT": variant}, ["test_gpu_parity.py", "test_gpu_fullsize.py"], "skin or render_prep or c3_full")
+
+
+@pytest.mark.timeout(1000)
+@pytest.mark.parametrize("mode", ["0", "1"])
+def test_subforest_kernel_on_and_off_match_the_oracle(mode):
+    """FYX_SUBFOREST: the deep levels of the hierarchy in one launch (k_update_subforest) or one launch per level — forced
+    both ways over the hierarchy / cull / skinning / animation parity tests (the default picks by level size)."""
+    _run({"FYX_SUBFOREST": mode}, ["test_gpu_parity.py", "test_gpu_anim.py", "test_gpu_drawprep.py"], "not cpp_host and not k6 and not k7")
