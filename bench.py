@@ -287,6 +287,26 @@ def run_reference(args):
         line["cpu_multicore"] = time_multicore(ref, max(2, min(args.steps, 5)))
     except Exception as ex:
         line["cpu_multicore"] = {"value": None, "note": f"failed: {ex!r}"}
+    # ONE frame of the FULL workload (the CUDA arm's exact config), so that a same-config number exists next to the
+    # bounded-sample throughput above; skipped when the sample says it would take more than ~90 s
+    full = dict(nodes=w["nodes"], units=w["units"], verts_per_unit=w["verts_per_unit"], frusta=w["frusta"])
+    est_s = (full["nodes"] + full["units"] * full["verts_per_unit"]) / max(value, 1.0)
+    setup_est_s = 0.0035 * full["units"] + 2e-6 * full["nodes"]  # measured: vertex generation + oracle surfaces dominate the set-up
+    if not args.no_full_frame and args.gpus == 1 and full != sample and est_s + setup_est_s < 240.0:
+        try:
+            del ref
+            t0 = time.perf_counter()
+            big = CpuReference(full)
+            setup_s = time.perf_counter() - t0
+            dt, _ = big.step()
+            line["full_workload_frame"] = {"value": big.units_per_frame() / dt, "unit": UNIT, "ms": 1e3 * dt, "frames": 1, "same_config_as_cuda_arm": True,
+                                           "nodes": full["nodes"], "skinned_meshes": full["units"], "frusta": full["frusta"], "setup_s": round(setup_s, 1), "cores": 1, "kind": "port"}
+            del big
+        except Exception as ex:
+            line["full_workload_frame"] = {"value": None, "note": f"failed: {ex!r}"}
+    else:
+        line["full_workload_frame"] = {"value": None, "note": (f"skipped (estimated {est_s:.0f} s per frame + {setup_est_s:.0f} s set-up; only run at --gpus 1)"
+                                                                if full != sample else "the sample IS the full workload")}
     print(json.dumps(line), flush=True)
     return 0
 
@@ -768,6 +788,7 @@ def main():
     ap.add_argument("--upload", default="rot", choices=["rot", "trs", "m16"], help="per-frame upload format of the changed bones")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-device-animation", action="store_true", help="skip the extra mode that samples the bones' animation curves on the device")
+    ap.add_argument("--no-full-frame", action="store_true", help="reference arm: skip the one frame of the full workload that follows the bounded sample")
     ap.add_argument("--no-parity", action="store_true", help="skip the sampled-oracle check that follows the timed regions")
     ap.add_argument("--no-c5", action="store_true", help="skip the strong-scaling C5 measurement that follows the default C4 workload")
     ap.add_argument("--verbose", action="store_true")

@@ -156,7 +156,7 @@ def test_bone_matrix_blocks_of_packed_instances_match_oracle(ctx):
         og.set_local_matrix(int(i), mm)
     og.update_hierarchical_data()
     ctx.enable_instances()
-    view, vp, fo, ff = observer((0, 0, 0), (0, 0, -1), zf=500.0, fovy=np.deg2rad(120.0))
+    view, vp, fo, ff = observer((0, 0, 400), (0, 0, 0), zf=900.0)  # far enough back to see the whole scene
     ctx.render_prep(update_flags=fb.UPDATE_ALL, changed_m16=m, changed_idx=idx, frusta=[ff])
     inst = ctx.pack_instances(0, view, vp)
     ctx.pack_bone_matrices(0)
