@@ -117,6 +117,7 @@ struct fyx_ctx {
     uint32_t n_nodes = 0, n_slots = 0, root = FYX_NONE, n_renderable = 0;
     std::vector<uint32_t> slot_of_node, node_of_slot, level_off;
     NodeArrays a{};
+    DevBuf b_vis;
     DevBuf b_parent, b_flags, b_mask, b_gidx, b_L[3], b_G[3], b_la[3], b_wa[3], b_slot_of_node;
     bool have_topology = false, updated_once = false;
     SubforestPlan sf{};  // deep levels walked by one launch (fyx_internal.h); n_ctas = 0: one launch per level everywhere
@@ -371,6 +372,7 @@ void rebuild_node_arrays(fyx_ctx *c)
     a.flags = c->b_flags.as<uint32_t>();
     a.mask = c->b_mask.as<uint32_t>();
     a.gidx = c->b_gidx.as<uint32_t>();
+    a.vis = c->b_vis.as<uint8_t>();
     for (int i = 0; i < 3; ++i) {
         a.L[i] = c->b_L[i].as<float4>();
         a.G[i] = c->b_G[i].as<float4>();
@@ -474,6 +476,10 @@ int32_t run_update(fyx_ctx *c, uint32_t update_flags, const CullParams *cull)
     }
     if (c->sf.n_ctas) { // the deep levels (small sub-trees: skeletons) in one launch
         launch_update_subforest(c->stream, c->a, c->sf, all, cull);
+        c->launches++;
+    }
+    if (cull && cull_defers_compaction(cull->nf)) { // the level kernels stored visible bits: build the lists now
+        launch_compact_vis(c->stream, c->a, *cull);
         c->launches++;
     }
     if (c->fold.n) {
@@ -640,7 +646,7 @@ extern "C" void fyx_destroy(fyx_ctx *c)
     fyx_comm_destroy_internal(c);
     inst_free(c);
     anim_free(c);
-    DevBuf *bufs[] = {&c->b_parent, &c->b_flags, &c->b_mask, &c->b_gidx, &c->b_slot_of_node, &c->d_stage, &c->b_statics, &c->b_trs, &c->b_vblk,
+    DevBuf *bufs[] = {&c->b_vis, &c->b_parent, &c->b_flags, &c->b_mask, &c->b_gidx, &c->b_slot_of_node, &c->d_stage, &c->b_statics, &c->b_trs, &c->b_vblk,
                       &c->b_prune, &c->b_sf_rng, &c->b_opos, &c->b_onrm, &c->b_bs, &c->b_bs_w, &c->b_surf_of_slot, &c->b_surf_bones, &c->b_palette, &c->b_bone_slot, &c->b_tiles, &c->b_fold_node,
                       &c->b_fold_begin, &c->b_fold_bone, &c->b_fold_stale_idx, &c->b_late_slot, &c->b_stale_pos, &c->b_counts_packed, &c->b_counts_all};
     for (DevBuf *b : bufs) dev_free(*b);
@@ -1026,6 +1032,8 @@ extern "C" int32_t fyx_set_topology(fyx_ctx *c, uint32_t capacity, uint32_t root
     if ((rc = dev_ensure(c, c->b_flags, n * 4))) return rc;
     if ((rc = dev_ensure(c, c->b_mask, n * 4))) return rc;
     if ((rc = dev_ensure(c, c->b_gidx, n * 4))) return rc;
+    if ((rc = dev_ensure(c, c->b_vis, (n + 15) & ~size_t(7)))) return rc;
+    CU(cudaMemset(c->b_vis.p, 0, c->b_vis.bytes));
     if ((rc = dev_ensure(c, c->b_slot_of_node, std::max<size_t>(capacity, 1) * 4))) return rc;
     for (int k = 0; k < 3; ++k) {
         if ((rc = dev_ensure(c, c->b_L[k], n * sizeof(float4)))) return rc;

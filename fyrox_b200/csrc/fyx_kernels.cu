@@ -407,7 +407,7 @@ __global__ void __launch_bounds__(kBlock) k_update_level(const NodeArrays a, con
     uint32_t mask = 0u, gi_early = 0u;
     if (UA && (NFT >= 0) && valid) { // static columns: no reason to wait for anything
         mask = a.mask[slot];
-        gi_early = a.gidx[slot];
+        if (!(VAR & 8)) gi_early = a.gidx[slot];
     }
     if (valid) update_node<(NFT >= 0), UA>(a, slot, update_all, nf, wx, wy, wz);
     else pdl_wait();
@@ -415,6 +415,10 @@ __global__ void __launch_bounds__(kBlock) k_update_level(const NodeArrays a, con
         const bool cand = valid && !(nf & F_SKINNED);
         if (!UA) mask = cand ? a.mask[slot] : 0u;
         const uint32_t vis_bits = cull_warp<(NFT > 0 ? NFT : 0), PRE>(cand, nf, mask, wx, wy, wz, cp, T);
+        if (VAR & 8) { // deferred compaction: one byte per node now, the lists are built by k_compact_vis after the last level
+            if (valid) a.vis[slot] = (uint8_t)vis_bits;
+            return;
+        }
         const uint32_t gi = UA ? gi_early : (vis_bits ? a.gidx[slot] : 0u);
         if (VAR & 2) compact_emit_warp(vis_bits, gi, slot, cp);
         else compact_emit<(NFT > 0 ? NFT : 0)>(vis_bits, gi, slot, cp);
@@ -428,7 +432,7 @@ __global__ void __launch_bounds__(kBlock) k_update_level(const NodeArrays a, con
 // memory for the children.  Same arithmetic, flags, change tracking and fused cull as k_update_level; what it removes
 // is a kernel launch per level for levels of a few thousand nodes (C3: six skeleton levels of 10 k - 320 k nodes).
 // ------------------------------------------------------------------------------------------------
-template <int NFT, bool UA>
+template <int NFT, bool UA, bool DEFER>
 __global__ void __launch_bounds__(kBlock) k_update_subforest(const NodeArrays a, const uint2 *__restrict__ rng, const int n_levels,
                                                              const uint32_t update_all, const CullParams cp)
 {
@@ -523,13 +527,81 @@ __global__ void __launch_bounds__(kBlock) k_update_subforest(const NodeArrays a,
                 const bool cand = valid && !(nf & F_SKINNED);
                 const uint32_t mask = cand ? a.mask[slot] : 0u;
                 const uint32_t vis_bits = cull_warp<(NFT > 0 ? NFT : 0), false>(cand, nf, mask, wx, wy, wz, cp, nullptr);
-                const uint32_t gi = vis_bits ? a.gidx[slot] : 0u;
-                compact_emit<(NFT > 0 ? NFT : 0)>(vis_bits, gi, slot, cp);
+                if (DEFER) {
+                    if (valid) a.vis[slot] = (uint8_t)vis_bits;
+                } else {
+                    const uint32_t gi = vis_bits ? a.gidx[slot] : 0u;
+                    compact_emit<(NFT > 0 ? NFT : 0)>(vis_bits, gi, slot, cp);
+                }
             }
         }
         __syncthreads(); // this level's rows are complete (and the previous level's are no longer read)
         prevA = r.x;
         prevB = r.y;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Deferred compaction.  With the cull fused into the level kernels, the compaction (ballots, shared-memory prefix, one
+// atomic per CTA and frustum, three CTA-wide barriers) sat at the end of a 900-instruction thread and every warp of a CTA
+// waited for the slowest one.  Here the level kernels store ONE byte per node (its visible bits) and this small pass —
+// 1 B read per node, gidx only where something is visible — turns the byte column into the lists: a thread takes 8
+// consecutive slots, a warp 256, one atomicAdd per (warp, frustum with anything visible).  Skinned meshes are emitted by
+// k_fold_bones (their byte is 0).  Order inside a list stays unspecified.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kBlock) k_compact_vis(const NodeArrays a, const CullParams cp)
+{
+    pdl_trigger();
+    pdl_wait();
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint64_t first = ((uint64_t)blockIdx.x * kBlock + threadIdx.x) * 8u;
+    unsigned long long v = 0ull;
+    if (first + 8u <= a.cap) {
+        v = *reinterpret_cast<const unsigned long long *>(a.vis + first); // the column is 256-byte aligned: 8-byte loads are
+    } else if (first < a.cap) {
+        for (uint32_t j = 0; j < 8u && first + j < a.cap; ++j) v |= (unsigned long long)a.vis[first + j] << (8u * j);
+    }
+    uint32_t frusta = 0u; // frusta this thread has entries for
+    {
+        unsigned long long t = v;
+        t |= t >> 32;
+        t |= t >> 16;
+        t |= t >> 8;
+        frusta = (uint32_t)(t & 0xFFu);
+    }
+    uint32_t m = __reduce_or_sync(0xFFFFFFFFu, frusta);
+    if (!m) return;
+    uint32_t gi[8];
+    if (v) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) gi[j] = (first + j < a.cap) ? a.gidx[first + j] : 0u;
+    }
+    while (m) {
+        const int f = __ffs(m) - 1;
+        m &= m - 1u;
+        const unsigned long long sel = (v >> f) & 0x0101010101010101ull; // byte j = node j visible in f
+        const uint32_t cnt = (uint32_t)__popcll(sel);
+        uint32_t incl = cnt; // inclusive warp scan
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+            if (lane >= (uint32_t)d) incl += t;
+        }
+        const uint32_t total = __shfl_sync(0xFFFFFFFFu, incl, 31);
+        uint32_t base = 0u;
+        if (lane == 0) base = atomicAdd(cp.counts + f * kCountStride, total);
+        base = __shfl_sync(0xFFFFFFFFu, base, 0) + incl - cnt;
+        if (cnt) {
+            uint32_t k = 0;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                if ((sel >> (8 * j)) & 1ull) {
+                    cp.out[f][base + k] = gi[j];
+                    if (cp.out_slot[f]) cp.out_slot[f][base + k] = (uint32_t)(first + j);
+                    ++k;
+                }
+            }
+        }
     }
 }
 
@@ -1316,12 +1388,15 @@ static int cull_variant(int nf)
 {
     static int forced = [] {
         const char *e = getenv("FYX_CULL_VARIANT");
-        return (e && *e) ? atoi(e) & 7 : -1;
+        return (e && *e) ? atoi(e) & 15 : -1;
     }();
     if (forced >= 0) return forced;
     (void)nf;
     return 4; // measured (profiles/README.md, round 2): CTA-wide compaction, no pre-reject, FYX_UPDATE_ALL specialisation
 }
+
+// bit 3 of the variant: the level kernels store visible bits, k_compact_vis builds the lists (bit 1 is then meaningless)
+bool cull_defers_compaction(int nf) { return (cull_variant(nf) & 8) != 0; }
 
 #define FYX_DISPATCH_VAR(KERNEL, NF, VAR, ...)                                   \
     switch (VAR) {                                                               \
@@ -1332,7 +1407,11 @@ static int cull_variant(int nf)
     case 4: launch_pdl(KERNEL<NF, 4>, __VA_ARGS__); break;                       \
     case 5: launch_pdl(KERNEL<NF, 5>, __VA_ARGS__); break;                       \
     case 6: launch_pdl(KERNEL<NF, 6>, __VA_ARGS__); break;                       \
-    default: launch_pdl(KERNEL<NF, 7>, __VA_ARGS__); break;                      \
+    case 7: launch_pdl(KERNEL<NF, 7>, __VA_ARGS__); break;                       \
+    case 8: launch_pdl(KERNEL<NF, 8>, __VA_ARGS__); break;                       \
+    case 9: launch_pdl(KERNEL<NF, 9>, __VA_ARGS__); break;                       \
+    case 12: launch_pdl(KERNEL<NF, 12>, __VA_ARGS__); break;                     \
+    default: launch_pdl(KERNEL<NF, 13>, __VA_ARGS__); break;                     \
     }
 
 void launch_update_level(cudaStream_t s, const NodeArrays &a, uint32_t lo, uint32_t hi, bool update_all, const CullParams *cull)
@@ -1341,7 +1420,8 @@ void launch_update_level(cudaStream_t s, const NodeArrays &a, uint32_t lo, uint3
     if (cull) {
         const unsigned g = grid_for(hi - lo);
         const uint32_t ua = update_all ? 1u : 0u;
-        const int var = (cull_variant(cull->nf) & 3) | ((update_all && (cull_variant(cull->nf) & 4)) ? 4 : 0);
+        int var = (cull_variant(cull->nf) & 3) | ((update_all && (cull_variant(cull->nf) & 4)) ? 4 : 0);
+        if (cull_variant(cull->nf) & 8) var = (var & 5) | 8; // deferred compaction: 8, 9, 12, 13
         switch (cull->nf) { // the usual frustum counts get an unrolled cull: camera, CSM cascades, cube faces
         case 1: FYX_DISPATCH_VAR(k_update_level, 1, var, g, kBlock, 0, s, a, lo, hi, ua, *cull); break;
         case 2: FYX_DISPATCH_VAR(k_update_level, 2, var, g, kBlock, 0, s, a, lo, hi, ua, *cull); break;
@@ -1360,8 +1440,11 @@ void launch_update_level(cudaStream_t s, const NodeArrays &a, uint32_t lo, uint3
 
 template <int NFT> static void launch_subforest_t(cudaStream_t s, const NodeArrays &a, const SubforestPlan &sf, bool ua, const CullParams &cp)
 {
-    if (ua) launch_pdl(k_update_subforest<NFT, true>, sf.n_ctas, kBlock, 0, s, a, sf.rng, (int)sf.n_levels, 1u, cp);
-    else launch_pdl(k_update_subforest<NFT, false>, sf.n_ctas, kBlock, 0, s, a, sf.rng, (int)sf.n_levels, 0u, cp);
+    const bool defer = NFT >= 0 && cull_defers_compaction(cp.nf);
+    if (ua && defer) launch_pdl(k_update_subforest<NFT, true, true>, sf.n_ctas, kBlock, 0, s, a, sf.rng, (int)sf.n_levels, 1u, cp);
+    else if (ua) launch_pdl(k_update_subforest<NFT, true, false>, sf.n_ctas, kBlock, 0, s, a, sf.rng, (int)sf.n_levels, 1u, cp);
+    else if (defer) launch_pdl(k_update_subforest<NFT, false, true>, sf.n_ctas, kBlock, 0, s, a, sf.rng, (int)sf.n_levels, 0u, cp);
+    else launch_pdl(k_update_subforest<NFT, false, false>, sf.n_ctas, kBlock, 0, s, a, sf.rng, (int)sf.n_levels, 0u, cp);
 }
 
 void launch_update_subforest(cudaStream_t s, const NodeArrays &a, const SubforestPlan &sf, bool update_all, const CullParams *cull)
@@ -1378,6 +1461,12 @@ void launch_update_subforest(cudaStream_t s, const NodeArrays &a, const Subfores
     case 6: launch_subforest_t<6>(s, a, sf, update_all, *cull); break;
     default: launch_subforest_t<0>(s, a, sf, update_all, *cull); break;
     }
+}
+
+void launch_compact_vis(cudaStream_t s, const NodeArrays &a, const CullParams &cp)
+{
+    if (!a.cap || !cp.nf) return;
+    launch_pdl(k_compact_vis, grid_for(((uint64_t)a.cap + 7) / 8), kBlock, 0, s, a, cp);
 }
 
 void launch_cull_lights(cudaStream_t s, const NodeArrays &a, const CullParams &cp, uint32_t *const *d_out_ptrs, uint32_t *counts)
