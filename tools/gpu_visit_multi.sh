@@ -31,6 +31,9 @@ except Exception as ex:
 PY
 }
 run default "FYX_DUMMY=1" ""
+if [ "$MODE" = "compare" ]; then
+  run nccl_private "FYX_EXCHANGE=nccl FYX_HOSTSEG=0" "--no-c5"
+fi
 if [ "$MODE" = "full" ]; then
   run nccl_private "FYX_EXCHANGE=nccl FYX_HOSTSEG=0" "--no-c5"
   run nccl_seg "FYX_EXCHANGE=nccl" "--no-c5"
