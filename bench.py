@@ -618,6 +618,18 @@ def measure(args, wname, strong, steps, env, full):
             if world > 1:
                 raise
 
+    xstats = None
+    if world > 1:
+        try:  # the exchange of one more device-resident frame, timed on the collective stream (it overlaps the skinning kernel)
+            step_device()
+            ctx.sync()
+            xs = ctx.comm_stats()
+            xstats = {"device_ms": xs["device_ms"], "entries_own": int(xs["entries_own"]), "entries_gathered": int(xs["entries_total"]),
+                      "nvlink_egress_bytes_per_rank": int(xs["egress_bytes"]), "algorithmic_bytes_4_N_Vvis": 4 * int(xs["entries_own"]) * world,
+                      "egress_GBps": xs["egress_bytes"] / max(xs["device_ms"], 1e-6) / 1e6,
+                      "note": "device_ms spans counts -> push -> wait for every peer on the collective stream, beside k_palette / k_skin"}
+        except Exception as ex:
+            xstats = {"error": repr(ex)}
     ms_per_step = total_ms / steps
     e2e_ms_per_step = e2e_ms / steps
     units_all = (w["nodes"] + w["units"] * w["verts_per_unit"]) * mult  # whole job
@@ -655,7 +667,7 @@ def measure(args, wname, strong, steps, env, full):
                e2e_sync_ms=None if e2e_sync_ms is None else e2e_sync_ms / steps, e2e_pipe_ms=e2e_pipe_ms / steps, units_all=units_all,
                sum_vis=sum_vis, own_vis=own_vis, h2d=h2d, d2h=d2h, launches=int(launches), roofline=roofline, clocks=clk, parity=parity,
                inc_ms=inc_ms, dev_anim=dev_anim, frusta=len(frusta), n_local_nodes=n_local_nodes, n_local_verts=n_local_verts,
-               exchange=ctx.comm_mode() if world > 1 else None)
+               exchange={"mode": ctx.comm_mode(), "last_frame": xstats} if world > 1 else None)
     for pi, pm in anim:
         pi.free()
         pm.free()

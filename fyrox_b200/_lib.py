@@ -72,6 +72,11 @@ class fyx_vertex_layout(C.Structure):
     ]
 
 
+class fyx_comm_stats(C.Structure):
+    _fields_ = [("epoch", C.c_uint64), ("entries_own", C.c_uint64), ("entries_total", C.c_uint64), ("egress_bytes", C.c_uint64),
+                ("device_ms", C.c_float), ("mode", C.c_uint32)]
+
+
 class fyx_timings(C.Structure):
     _fields_ = [(n, C.c_float) for n in ("upload_ms", "update_ms", "cull_ms", "palette_ms", "skin_ms", "readback_ms", "total_ms")]
 
@@ -229,6 +234,7 @@ SYMBOLS = {
     "fyx_set_blend_shape_weights": (C.c_int32, [ctx_p, C.c_uint32, C.c_uint32, C.c_void_p]),
     "fyx_allgather_visible": (C.c_int32, [ctx_p]),
     "fyx_comm_mode": (C.c_uint32, [ctx_p]),
+    "fyx_comm_get_stats": (C.c_int32, [ctx_p, C.c_void_p]),
     "fyx_get_visible_gathered": (C.c_int32, [ctx_p, C.c_uint32, C.POINTER(u32p), u32p]),
     "fyx_get_visible_gathered_device": (C.c_int32, [ctx_p, C.c_uint32, C.POINTER(C.c_void_p), u32p]),
 }

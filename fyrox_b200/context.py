@@ -553,6 +553,12 @@ class Context:
         host = "node-wide host segment (each rank copies its own lists)" if m & L.COMM_HOST_SEGMENT else "private copy of the gathered device lists per rank"
         return f"device: {dev}; host: {host}"
 
+    def comm_stats(self) -> dict:
+        """The most recent exchange of this rank: entries, NVLink egress bytes, device time (fyx_comm_get_stats)."""
+        st = L.fyx_comm_stats()
+        self._chk(self._lib.fyx_comm_get_stats(self._h, C.byref(st)))
+        return {n: getattr(st, n) for n, _ in L.fyx_comm_stats._fields_}
+
     def allgather_visible(self):
         self._chk(self._lib.fyx_allgather_visible(self._h))
 

@@ -225,6 +225,9 @@ struct fyx_ctx {
     uint64_t exch_total_cap = 0, gather_epoch = 0;
     PeerState peer;
     HostSeg hostseg;
+    cudaEvent_t ev_x0[2] = {}, ev_x1[2] = {}; // timing of the exchange (per epoch parity)
+    uint64_t x_epoch[2] = {0, 0};
+    int x_slot[2] = {0, 0};
     cudaEvent_t ev_gath_read[2] = {}; // private D2H copies of the gathered device lists (per epoch parity)
     bool gath_read_valid[2] = {false, false};
 };
@@ -611,7 +614,11 @@ extern "C" int32_t fyx_create(const fyx_config *cfg, fyx_ctx **out_ctx)
         CUB(cudaEventCreateWithFlags(&V.ev_gather, cudaEventDisableTiming));
         CUB(cudaEventCreateWithFlags(&V.ev_counts_all, cudaEventDisableTiming));
     }
-    for (int i = 0; i < 2; ++i) CUB(cudaEventCreateWithFlags(&c->ev_gath_read[i], cudaEventDisableTiming));
+    for (int i = 0; i < 2; ++i) {
+        CUB(cudaEventCreateWithFlags(&c->ev_gath_read[i], cudaEventDisableTiming));
+        CUB(cudaEventCreate(&c->ev_x0[i]));
+        CUB(cudaEventCreate(&c->ev_x1[i]));
+    }
     CUB(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
     CUB(cudaStreamCreateWithFlags(&c->d2h_stream, cudaStreamNonBlocking));
     for (int i = 0; i < 2; ++i) {
@@ -682,8 +689,11 @@ extern "C" void fyx_destroy(fyx_ctx *c)
     }
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     if (c->d2h_stream) cudaStreamDestroy(c->d2h_stream);
-    for (int i = 0; i < 2; ++i)
+    for (int i = 0; i < 2; ++i) {
         if (c->ev_gath_read[i]) cudaEventDestroy(c->ev_gath_read[i]);
+        if (c->ev_x0[i]) cudaEventDestroy(c->ev_x0[i]);
+        if (c->ev_x1[i]) cudaEventDestroy(c->ev_x1[i]);
+    }
     if (c->d_err) cudaFree(c->d_err);
     if (c->h_err) cudaFreeHost(c->h_err);
     if (c->h_counts_all) cudaFreeHost(c->h_counts_all);
@@ -1817,6 +1827,7 @@ extern "C" int32_t fyx_render_prep(fyx_ctx *c, const fyx_frame_desc *fr)
         // the host waits only for the cull + the counts (the skinning kernel keeps running), then enqueues the payload
         rc = allgather_finish(c, c->vs[c->cur], c->comm_stream);
         if (rc) return rc;
+        CU(cudaEventRecord(c->ev_x1[c->vs[c->cur].epoch & 1], c->comm_stream));
         CU(cudaEventRecord(c->vs[c->cur].ev_gather, c->comm_stream));
         CU(cudaStreamWaitEvent(s, c->vs[c->cur].ev_gather, 0)); // the frame is complete when the gathered lists are
     }

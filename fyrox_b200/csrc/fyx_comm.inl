@@ -377,6 +377,9 @@ static int32_t allgather_enqueue(fyx_ctx *c, VisSlot &V, cudaStream_t s)
     V.counts_all_known = false;
     V.via_peer = c->peer.ready;
     if (c->hostseg_ready) c->hostseg.begin(V.epoch); // this rank no longer reads the host lists of epoch - 2
+    CU(cudaEventRecord(c->ev_x0[V.epoch & 1], s));
+    c->x_epoch[V.epoch & 1] = V.epoch;
+    c->x_slot[V.epoch & 1] = (int)(&V - c->vs);
     if (c->gath_read_valid[V.epoch & 1]) { // a private D2H copy of the list buffers this epoch reuses must have drained
         CU(cudaStreamWaitEvent(s, c->ev_gath_read[V.epoch & 1], 0));
         c->gath_read_valid[V.epoch & 1] = false;
@@ -471,7 +474,31 @@ extern "C" int32_t fyx_allgather_visible(fyx_ctx *c)
     if (rc) return rc;
     rc = allgather_finish(c, V, c->stream);
     if (rc) return rc;
+    CU(cudaEventRecord(c->ev_x1[V.epoch & 1], c->stream));
     CU(cudaEventRecord(V.ev_gather, c->stream));
+    return FYX_OK;
+}
+
+extern "C" int32_t fyx_comm_get_stats(fyx_ctx *c, fyx_comm_stats *out)
+{
+    if (!c || !out) return FYX_ERR_INVALID_ARGUMENT;
+    memset(out, 0, sizeof *out);
+    if (!c->comm || !c->gather_epoch) return fail(c, FYX_ERR_STATE, "no gathered frame has run yet");
+    CU(cudaSetDevice(c->device));
+    const int p = (int)(c->gather_epoch & 1);
+    VisSlot &V = c->vs[c->x_slot[p]];
+    if (V.epoch != c->x_epoch[p] || !V.gathered) return fail(c, FYX_ERR_STATE, "the last exchange's frame has been overwritten");
+    CU(cudaEventSynchronize(c->ev_x1[p]));
+    CU(cudaEventElapsedTime(&out->device_ms, c->ev_x0[p], c->ev_x1[p]));
+    int32_t rc = resolve_counts(c, V);
+    if (rc) return rc;
+    out->epoch = V.epoch;
+    for (uint32_t f = 0; f < V.nf; ++f) {
+        out->entries_own += V.counts_all[c->rank][f];
+        out->entries_total += V.gath_count[f];
+    }
+    out->egress_bytes = V.via_peer ? 4ull * out->entries_own * (uint64_t)(c->nranks - 1) : 0ull;
+    out->mode = fyx_comm_mode(c);
     return FYX_OK;
 }
 

@@ -483,6 +483,16 @@ int32_t fyx_comm_init(fyx_ctx *ctx, int32_t nranks, int32_t rank, const void *id
 #define FYX_COMM_HOST_SEGMENT 4u
 #define FYX_COMM_UNDECIDED 8u
 uint32_t fyx_comm_mode(const fyx_ctx *ctx);
+/* The most recent COMPLETED exchange of this rank, timed with CUDA events on the collective stream (waits for it). */
+typedef struct fyx_comm_stats {
+    uint64_t epoch;          /* number of the gathered frame */
+    uint64_t entries_own;    /* visible entries this rank contributed (all frusta) */
+    uint64_t entries_total;  /* entries of the gathered lists (all frusta) */
+    uint64_t egress_bytes;   /* bytes this rank stored into OTHER ranks' memory: 4 * entries_own * (nranks - 1) (peer form) */
+    float device_ms;         /* from the first kernel / collective of the exchange to its last one, incl. waiting for peers */
+    uint32_t mode;           /* fyx_comm_mode at that time */
+} fyx_comm_stats;
+int32_t fyx_comm_get_stats(fyx_ctx *ctx, fyx_comm_stats *out);
 /* All-gather the visible lists of the last cull.  Collective: every rank calls it for the same frame. */
 int32_t fyx_allgather_visible(fyx_ctx *ctx);
 /* Gathered list of frustum f: concatenation over ranks (device-resident and, if readback, on the host). */

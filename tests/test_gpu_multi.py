@@ -94,6 +94,11 @@ def _run_modes(ctx, fb, frusta, rank, out, variant):
             out[f"{variant}_{mode}_{f}"] = np.sort(ctx.get_visible_gathered(f))  # complete on every rank that asks
             p, n = ctx.get_visible_gathered_device(f)
             assert n == out[f"{variant}_{mode}_{f}"].size
+        st = ctx.comm_stats()  # the exchange that produced these lists
+        assert st["entries_total"] == sum(out[f"{variant}_{mode}_{f}"].size for f in range(len(frusta)))
+        assert st["device_ms"] > 0.0 and st["entries_own"] <= st["entries_total"]
+        if "peer" in variant:
+            assert st["egress_bytes"] == 4 * st["entries_own"]  # 2 ranks: one peer
 
 
 @pytest.mark.timeout(600)
