@@ -168,12 +168,37 @@ class TransformBuilder:
 
 
 @dataclass
+class BlendShape:
+    """BlendShape (scene/mesh/surface.rs:71-90): weight in 0..100 (default 100) and a name."""
+
+    weight: float = 100.0
+    name: str = ""
+
+
+@dataclass
+class BlendShapesContainer:
+    """BlendShapesContainer (scene/mesh/surface.rs:92-218): the shapes and the volume texture from_lists packs them into —
+    here as its texels: uint16 (n_shapes, width * height, 9) binary16 patterns (position, normal, tangent offsets)."""
+
+    blend_shapes: List[BlendShape] = field(default_factory=list)
+    blend_shape_storage: Optional[np.ndarray] = None
+
+
+class BatchingMode:
+    """BatchingMode (scene/mesh/mod.rs:120-140)."""
+
+    NONE, STATIC, DYNAMIC = "None", "Static", "Dynamic"
+
+
+@dataclass
 class Surface:
-    """Surface (scene/mesh/surface.rs:1249-1271): bone handles + the VertexBuffer bytes."""
+    """Surface (scene/mesh/surface.rs:1249-1271): bone handles + the VertexBuffer bytes (+ SurfaceData::blend_shapes_container)."""
 
     bones: List[Handle] = field(default_factory=list)
     vertex_buffer: Optional[np.ndarray] = None  # uint8, AnimatedVertex records
     surface_id: Optional[int] = None            # fyx surface id once uploaded
+    blend_shapes_container: Optional[BlendShapesContainer] = None
+    _shapes_uploaded: bool = False
 
 
 class Node:
@@ -194,8 +219,25 @@ class Node:
         self.local_bounding_box = np.array([-0.5, -0.5, -0.5, 0.5, 0.5, 0.5], f32) if kind != "mesh" else np.array(
             [np.finfo(f32).max] * 3 + [-np.finfo(f32).max] * 3, f32)
         self.surfaces: List[Surface] = []
+        self.batching_mode = BatchingMode.NONE  # Mesh::batching_mode (scene/mesh/mod.rs:372)
         self._graph: Optional["Graph"] = None
         self._handle = Handle.NONE
+
+    # Mesh::blend_shapes / blend_shapes_mut (scene/mesh/mod.rs:449-456): the weights the renderer divides by 100 (:794-798)
+    def blend_shapes(self) -> List[BlendShape]:
+        for s in self.surfaces:
+            if s.blend_shapes_container is not None:
+                return s.blend_shapes_container.blend_shapes
+        return []
+
+    def blend_shapes_mut(self) -> List[BlendShape]:
+        self._notify("blend_shapes")
+        return self.blend_shapes()
+
+    def set_batching_mode(self, mode: str):
+        """Mesh::set_batching_mode (scene/mesh/mod.rs:612-617); Static => RdcControlFlow::Break when the mesh is rendered."""
+        self.batching_mode = mode
+        self._notify("flags")
 
     # tracked properties
     def local_transform(self) -> Transform:
@@ -268,6 +310,7 @@ class Node:
         f |= L.NODE_FRUSTUM_CULLING if self.frustum_culling else 0
         f |= L.NODE_CAST_SHADOWS if self.cast_shadows else 0
         f |= L.NODE_RENDERABLE if self.kind == "mesh" else 0
+        f |= L.NODE_STATIC_BATCH if (self.kind == "mesh" and self.batching_mode == BatchingMode.STATIC) else 0
         return f
 
 
@@ -353,7 +396,7 @@ class Graph:
         self._free: List[int] = []
         self.root = Handle.NONE
         self._topology_dirty = True
-        self._dirty: Dict[str, set] = {"transform": set(), "flags": set(), "mask": set(), "aabb": set()}
+        self._dirty: Dict[str, set] = {"transform": set(), "flags": set(), "mask": set(), "aabb": set(), "blend_shapes": set()}
         self._cache: Dict[str, np.ndarray] = {}
         self._surfaces_uploaded = 0
         self.root = self.add_node(Node("pivot", "__ROOT__"))  # Graph::new, graph/mod.rs:408-424
@@ -487,6 +530,23 @@ class Graph:
                 ib = np.stack([self._records[b.index].inv_bind_pose_transform if self.is_valid_handle(b) else np.eye(4, dtype=f32).reshape(16) for b in s.bones])
                 s.surface_id = self.ctx.add_skinned_surface(i, bones, ib, s.vertex_buffer, ANIMATED_VERTEX_LAYOUT)
                 self._surfaces_uploaded += 1
+        self._upload_blend_shapes()
+
+    def _upload_blend_shapes(self):
+        """SurfaceData::blend_shapes_container -> fyx_set_blend_shapes once, Mesh::blend_shapes weights whenever they were touched."""
+        for n in self._records:
+            if n is None:
+                continue
+            for s in n.surfaces:
+                c = s.blend_shapes_container
+                if c is None or s.surface_id is None or c.blend_shape_storage is None:
+                    continue
+                w = np.array([b.weight for b in c.blend_shapes], np.float32)
+                if not s._shapes_uploaded:
+                    self.ctx.set_blend_shapes(s.surface_id, c.blend_shape_storage, w)
+                    s._shapes_uploaded = True
+                else:
+                    self.ctx.set_blend_shape_weights(s.surface_id, w)
 
     def update(self, frame_size=None, dt: float = 1.0 / 60.0, switches=None):
         """Graph::update (graph/mod.rs:1459-1504) reduced to its hierarchical part: process_node_messages."""

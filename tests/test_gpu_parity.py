@@ -275,6 +275,34 @@ def test_k7_global_scale_and_from_graph_through_the_host_mirror():
     graph.ctx.close()
 
 
+def test_static_batching_through_the_host_mirror_reads_like_the_reference():
+    """Mesh::set_batching_mode(BatchingMode::Static): once the mesh is rendered, collect_render_data returns
+    RdcControlFlow::Break and the DFS of from_graph skips its children (scene/mesh/mod.rs:701-725, bundle.rs:996-1001);
+    a static mesh outside the frustum lets the DFS go on."""
+    from fyrox_b200.scene import BaseBuilder, BatchingMode, Graph, MeshBuilder, ObserverPosition, RenderDataBundleStorage, TransformBuilder
+
+    graph = Graph()
+    box = [-1, -1, -1, 1, 1, 1]
+    at = lambda x, y, z: TransformBuilder().with_local_position((x, y, z)).build()
+    child_a = MeshBuilder(BaseBuilder().with_local_bounding_box(box).with_local_transform(at(1.0, 0.0, 0.0))).build(graph)
+    parent_a = MeshBuilder(BaseBuilder().with_local_bounding_box(box).with_local_transform(at(0.0, 0.0, -10.0)).with_child(child_a)).build(graph)
+    # the same pair again, but the parent sits behind the camera while its child (local offset) is in front of it
+    child_b = MeshBuilder(BaseBuilder().with_local_bounding_box(box).with_local_transform(at(0.0, 0.0, -70.0))).build(graph)
+    parent_b = MeshBuilder(BaseBuilder().with_local_bounding_box(box).with_local_transform(at(0.0, 0.0, 50.0)).with_child(child_b)).build(graph)
+    graph.update()
+    op = ObserverPosition(np.zeros(3, np.float32), 0.1, 150.0, ob.look_at_rh((0, 0, 0), (0, 0, -1), (0, 1, 0)), ob.perspective(16 / 9, np.deg2rad(60.0), 0.1, 150.0))
+    vis = lambda: set(h.index for h in RenderDataBundleStorage.from_graph(graph, 0xFFFFFFFF, 0.0, op, "GBuffer").visible_handles)
+    assert vis() == {parent_a.index, child_a.index, child_b.index}
+    graph[parent_a].set_batching_mode(BatchingMode.STATIC)
+    graph[parent_b].set_batching_mode(BatchingMode.STATIC)
+    graph.update()
+    assert vis() == {parent_a.index, child_b.index}  # a rendered static batch hides its child; a culled one does not
+    graph[parent_a].set_batching_mode(BatchingMode.NONE)
+    graph.update()
+    assert vis() == {parent_a.index, child_a.index, child_b.index}
+    graph.ctx.close()
+
+
 # ---- palette + skinning -------------------------------------------------------------------------------
 def test_palette_and_skinning_match_oracle(ctx):
     sc = Scene(6000, n_units=24, verts_per_unit=1237)  # 1237: not a multiple of 4 ⇒ padded quads
