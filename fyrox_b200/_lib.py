@@ -227,6 +227,8 @@ SYMBOLS = {
     "fyx_get_instances_device": (C.c_int32, [ctx_p, C.c_uint32, C.POINTER(fyx_instances)]),
     "fyx_comm_get_unique_id": (C.c_int32, [C.c_void_p]),
     "fyx_comm_init": (C.c_int32, [ctx_p, C.c_int32, C.c_int32, C.c_void_p]),
+    "fyx_set_node_surfaces": (C.c_int32, [ctx_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "fyx_get_instance_surfaces": (C.c_int32, [ctx_p, C.c_uint32, C.POINTER(u32p)]),
     "fyx_pack_bone_matrices": (C.c_int32, [ctx_p, C.c_uint32]),
     "fyx_get_bone_matrix_block": (C.c_int32, [ctx_p, C.c_uint32, C.c_uint32, C.c_void_p, C.POINTER(C.c_uint32)]),
     "fyx_get_bone_matrix_blocks_device": (C.c_int32, [ctx_p, C.c_uint32, C.c_void_p]),

@@ -387,6 +387,26 @@ class Context:
         ix = _u32(idx)
         self._chk(self._lib.fyx_set_bundle_ids(self._h, len(ids), _ptr(ix), _ptr(ids)))
 
+    def set_node_surfaces(self, nodes, surfaces):
+        """Mesh::surfaces of the given nodes: surfaces[i] = list of (bundle_id, skin_surface_id or None) for node nodes[i]."""
+        idx = np.ascontiguousarray(nodes, dtype=np.uint32)
+        first = np.zeros(len(idx) + 1, np.uint32)
+        b, sk = [], []
+        for i, lst in enumerate(surfaces):
+            for bid, sid in lst:
+                b.append(bid)
+                sk.append(L.FYX_NONE if sid is None else sid)
+            first[i + 1] = len(b)
+        ba = np.ascontiguousarray(b, dtype=np.uint32)
+        sa = np.ascontiguousarray(sk, dtype=np.uint32)
+        self._chk(self._lib.fyx_set_node_surfaces(self._h, len(idx), _ptr(idx), _ptr(first), ba.ctypes.data_as(C.c_void_p) if ba.size else None,
+                                                  sa.ctypes.data_as(C.c_void_p) if sa.size else None))
+
+    def get_instance_surfaces(self, frustum: int, count: int) -> np.ndarray:
+        p = L.u32p()
+        self._chk(self._lib.fyx_get_instance_surfaces(self._h, frustum, C.byref(p)))
+        return np.ctypeslib.as_array(p, shape=(count,)).copy() if count else np.empty(0, np.uint32)
+
     def enable_instances(self, enable: bool = True):
         self._chk(self._lib.fyx_enable_instances(self._h, 1 if enable else 0))
 
@@ -409,6 +429,7 @@ class Context:
 
         mats = arr(out.matrices, np.float32, n * 32).reshape(n, 2, 16)
         return {
+            "surface": self.get_instance_surfaces(frustum, n),
             "node": arr(out.node, np.uint32, n),
             "sort_index": arr(out.sort_index, np.uint64, n),
             "world": mats[:, 0, :].copy(),

@@ -85,7 +85,10 @@ struct AnimHost {
 
 // N3: packed instances of one frustum (fyx_drawprep.inl)
 struct InstOut {
-    DevBuf b_node, b_sort, b_mats, b_bundles;
+    DevBuf b_node, b_sort, b_mats, b_bundles, b_surf, b_skin;
+    void *h_surf = nullptr;
+    size_t h_surf_cap = 0;
+    uint32_t n_visible = 0;
     DevBuf b_block_of, b_blocks; // bone-matrix blocks of the skinned instances (fyx_pack_bone_matrices)
     uint32_t n_blocks = 0;
     bool blocks_valid = false;
@@ -158,6 +161,11 @@ struct fyx_ctx {
     uint64_t vert_cap = 0;
     uint32_t n_entries = 0, entry_cap = 0;
     DevBuf b_vblk, b_opos, b_onrm, b_ib[3], b_palette, b_bone_slot, b_tiles;
+    // surfaces per node (fyx_set_node_surfaces): host CSR by node, device table by slot (rebuilt when dirty)
+    std::vector<uint2> ms_of_node;       // (first, count) into ms_bundle_h / ms_skin_h; count 0 = default single surface
+    std::vector<uint32_t> ms_bundle_h, ms_skin_h;
+    bool ms_dirty = false, have_ms = false;
+    DevBuf b_ms_range, b_ms_bundle, b_ms_skin;
     DevBuf b_surf_of_slot, b_surf_bones; // per slot: the node's first skinned surface (FYX_NONE = none); per surface: (first palette entry, n_bones)
     DevBuf b_bs, b_bs_w;          // blend-shape offsets (blocked f16) and weights
     uint64_t bs_used = 0;         // shape blocks handed out
@@ -654,7 +662,7 @@ extern "C" void fyx_destroy(fyx_ctx *c)
     inst_free(c);
     anim_free(c);
     DevBuf *bufs[] = {&c->b_vis, &c->b_parent, &c->b_flags, &c->b_mask, &c->b_gidx, &c->b_slot_of_node, &c->d_stage, &c->b_statics, &c->b_trs, &c->b_vblk,
-                      &c->b_prune, &c->b_sf_rng, &c->b_opos, &c->b_onrm, &c->b_bs, &c->b_bs_w, &c->b_surf_of_slot, &c->b_surf_bones, &c->b_palette, &c->b_bone_slot, &c->b_tiles, &c->b_fold_node,
+                      &c->b_ms_range, &c->b_ms_bundle, &c->b_ms_skin, &c->b_prune, &c->b_sf_rng, &c->b_opos, &c->b_onrm, &c->b_bs, &c->b_bs_w, &c->b_surf_of_slot, &c->b_surf_bones, &c->b_palette, &c->b_bone_slot, &c->b_tiles, &c->b_fold_node,
                       &c->b_fold_begin, &c->b_fold_bone, &c->b_fold_stale_idx, &c->b_late_slot, &c->b_stale_pos, &c->b_counts_packed, &c->b_counts_all};
     for (DevBuf *b : bufs) dev_free(*b);
     for (int i = 0; i < 3; ++i) {
@@ -1103,6 +1111,8 @@ extern "C" int32_t fyx_set_topology(fyx_ctx *c, uint32_t capacity, uint32_t root
     }
     if (!same_capacity) c->dfs_rank.clear(); // indexed by node: stays valid while the pool capacity does
     c->rank_on_device = false; // re-derived from dfs_rank in the new slot order
+    c->ms_dirty = c->have_ms;  // the per-slot surface table too (the CSR itself is by node)
+    if (c->ms_of_node.size() < capacity) c->ms_of_node.resize(capacity, make_uint2(0u, 0u));
     c->anim_csr_dirty = true; // animated nodes are addressed by slot
     c->tables_dirty = true; // bone slots depend on the slot order
     rebuild_node_arrays(c);

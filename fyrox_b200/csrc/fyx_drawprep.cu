@@ -32,29 +32,45 @@ __device__ __forceinline__ uint64_t sorting_index(const float *view, const float
     return (ud > center) ? 0ull : center - ud;
 }
 
-// pass 1: sort index per visible entry, bundle histogram, first-pushed instance per bundle
+// surfaces of the visible entry's node: (first, count) — count 0 = the default single surface
+__device__ __forceinline__ uint2 surfaces_of(const InstParams &ip, const uint32_t slot)
+{
+    return ip.ms_range ? ip.ms_range[slot] : make_uint2(0u, 0u);
+}
+__device__ __forceinline__ uint32_t warp_max_u32(const uint32_t v) { return __reduce_max_sync(0xFFFFFFFFu, v); }
+
+// pass 1: sort index per visible entry, bundle histogram over its surfaces (Mesh::collect_render_data pushes one instance per
+// surface, all with the node's sort index, scene/mesh/mod.rs:726-805), first-pushed instance per bundle
 __global__ void __launch_bounds__(kBlock) k_inst_keys(const NodeArrays a, const InstParams ip)
 {
     const uint32_t i = blockIdx.x * kBlock + threadIdx.x;
     const bool valid = i < ip.n;
-    uint32_t b = 0xFFFFFFFFu;
+    uint32_t slot = 0u, nsurf = 0u;
+    uint2 sr = make_uint2(0u, 0u);
     unsigned long long key = ~0ull;
     if (valid) {
-        const uint32_t slot = ip.vis_slot[i];
+        slot = ip.vis_slot[i];
         // Base::global_position() = translation column of the global transform
         const float px = a.G[0][slot].w, py = a.G[1][slot].w, pz = a.G[2][slot].w;
         ip.tmp_sort[i] = sorting_index(ip.view, px, py, pz);
-        b = ip.bundle_of_slot ? ip.bundle_of_slot[slot] : 0u;
         const uint32_t rank = ip.rank_of_slot ? ip.rank_of_slot[slot] : ip.vis_node[i];
         key = ((unsigned long long)rank << 32) | i;
+        sr = surfaces_of(ip, slot);
+        nsurf = sr.y ? sr.y : 1u;
     }
-    // warp-aggregated histogram: one atomic per distinct bundle in the warp
-    const uint32_t peers = __match_any_sync(0xFFFFFFFFu, b);
-    if (valid) {
-        const int lane = threadIdx.x & 31;
-        if ((peers & ((1u << lane) - 1u)) == 0u) atomicAdd(ip.hist + b, (uint32_t)__popc(peers));
-        // the minimum only ever decreases: a plain read is a safe filter in front of the atomic
-        if (key < *reinterpret_cast<volatile unsigned long long *>(ip.first_key + b)) atomicMin(ip.first_key + b, key);
+    const uint32_t rounds = warp_max_u32(nsurf);
+    const int lane = threadIdx.x & 31;
+    for (uint32_t k = 0; k < rounds; ++k) {
+        const bool act = k < nsurf;
+        uint32_t b = 0xFFFFFFFFu;
+        if (act) b = sr.y ? ip.ms_bundle[sr.x + k] : (ip.bundle_of_slot ? ip.bundle_of_slot[slot] : 0u);
+        // warp-aggregated histogram: one atomic per distinct bundle in the warp
+        const uint32_t peers = __match_any_sync(0xFFFFFFFFu, b);
+        if (act) {
+            if ((peers & ((1u << lane) - 1u)) == 0u) atomicAdd(ip.hist + b, (uint32_t)__popc(peers));
+            // the minimum only ever decreases: a plain read is a safe filter in front of the atomic
+            if (key < *reinterpret_cast<volatile unsigned long long *>(ip.first_key + b)) atomicMin(ip.first_key + b, key);
+        }
     }
 }
 
@@ -113,7 +129,10 @@ __global__ void __launch_bounds__(kScanBlock) k_inst_scan(const InstParams ip)
         }
         __syncthreads();
     }
-    if (threadIdx.x == 0) *ip.o_n_bundles = s_carry[1];
+    if (threadIdx.x == 0) {
+        ip.o_n_bundles[0] = s_carry[1];
+        ip.o_n_bundles[2] = s_carry[0]; // instances = sum of the histogram
+    }
 }
 
 // pass 3: scatter into bundle order; matrices are written by 8 lanes per instance (one float4 column each), so a
@@ -123,54 +142,70 @@ __global__ void __launch_bounds__(kBlock) k_inst_scatter(const NodeArrays a, con
     const uint32_t i = blockIdx.x * kBlock + threadIdx.x;
     const int lane = threadIdx.x & 31;
     const bool valid = i < ip.n;
-    uint32_t slot = 0u, b = 0xFFFFFFFFu, pos = 0u;
+    uint32_t slot = 0u, nsurf = 0u, node_flags = 0u;
+    uint2 sr = make_uint2(0u, 0u);
     if (valid) {
         slot = ip.vis_slot[i];
-        b = ip.bundle_of_slot ? ip.bundle_of_slot[slot] : 0u;
+        sr = surfaces_of(ip, slot);
+        nsurf = sr.y ? sr.y : 1u;
+        node_flags = a.flags[slot];
     }
-    const uint32_t peers = __match_any_sync(0xFFFFFFFFu, b);
-    uint32_t base = 0u;
-    const int leader = __ffs(peers) - 1;
-    if (valid && lane == leader) base = ip.offset[b] + atomicAdd(ip.hist + b, (uint32_t)__popc(peers));
-    base = __shfl_sync(0xFFFFFFFFu, base, leader);
-    if (valid) {
-        pos = base + __popc(peers & ((1u << lane) - 1u));
-        ip.o_node[pos] = ip.vis_node[i];
-        ip.o_sort[pos] = ip.tmp_sort[i];
-    }
-    const int j = lane & 7, c = j & 3;
+    const uint32_t rounds = warp_max_u32(nsurf);
+    for (uint32_t k = 0; k < rounds; ++k) {
+        const bool act = k < nsurf;
+        uint32_t b = 0xFFFFFFFFu, pos = 0u, skin = FYX_NONE;
+        if (act) {
+            b = sr.y ? ip.ms_bundle[sr.x + k] : (ip.bundle_of_slot ? ip.bundle_of_slot[slot] : 0u);
+            skin = sr.y ? ip.ms_skin[sr.x + k] : ip.surf_of_slot[slot];
+        }
+        const uint32_t peers = __match_any_sync(0xFFFFFFFFu, b);
+        uint32_t base = 0u;
+        const int leader = __ffs(peers) - 1;
+        if (act && lane == leader) base = ip.offset[b] + atomicAdd(ip.hist + b, (uint32_t)__popc(peers));
+        base = __shfl_sync(0xFFFFFFFFu, base, leader);
+        if (act) {
+            pos = base + __popc(peers & ((1u << lane) - 1u));
+            ip.o_node[pos] = ip.vis_node[i];
+            ip.o_sort[pos] = ip.tmp_sort[i];
+            ip.o_surf[pos] = k;
+            ip.o_skin[pos] = skin;
+        }
+        // the instance's world matrix: identity for a skinned surface (its vertices are placed by the bone palette,
+        // scene/mesh/mod.rs:733-737) and for a static batch (:716), else the node's global transform
+        const bool ident = act && ((skin != FYX_NONE) || (node_flags & FYX_NODE_STATIC_BATCH));
+        const int j = lane & 7, c = j & 3;
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-        const int e = k * 4 + (lane >> 3);
-        const uint32_t pe = __shfl_sync(0xFFFFFFFFu, pos, e);
-        const uint32_t se = __shfl_sync(0xFFFFFFFFu, slot, e);
-        const bool ve = __shfl_sync(0xFFFFFFFFu, (int)valid, e) != 0;
-        if (!ve) continue;
-        // column c of the instance's world matrix: identity for a skinned surface (its vertices are placed by the
-        // bone palette, scene/mesh/mod.rs:733-737), else the node's global transform
-        float w0, w1, w2, w3 = (c == 3) ? 1.0f : 0.0f;
-        if (a.flags[se] & (F_SKINNED | FYX_NODE_STATIC_BATCH)) { // a static batch is pushed with the identity too (mesh/mod.rs:716)
-            w0 = (c == 0) ? 1.0f : 0.0f;
-            w1 = (c == 1) ? 1.0f : 0.0f;
-            w2 = (c == 2) ? 1.0f : 0.0f;
-        } else {
-            const float4 r0 = a.G[0][se], r1 = a.G[1][se], r2 = a.G[2][se];
-            w0 = (c == 0) ? r0.x : (c == 1) ? r0.y : (c == 2) ? r0.z : r0.w;
-            w1 = (c == 0) ? r1.x : (c == 1) ? r1.y : (c == 2) ? r1.z : r1.w;
-            w2 = (c == 0) ? r2.x : (c == 1) ? r2.y : (c == 2) ? r2.z : r2.w;
+        for (int q = 0; q < 8; ++q) {
+            const int e = q * 4 + (lane >> 3);
+            const uint32_t pe = __shfl_sync(0xFFFFFFFFu, pos, e);
+            const uint32_t se = __shfl_sync(0xFFFFFFFFu, slot, e);
+            const bool ve = __shfl_sync(0xFFFFFFFFu, (int)act, e) != 0;
+            const bool ie = __shfl_sync(0xFFFFFFFFu, (int)ident, e) != 0;
+            if (!ve) continue;
+            float w0, w1, w2, w3 = (c == 3) ? 1.0f : 0.0f;
+            if (ie) {
+                w0 = (c == 0) ? 1.0f : 0.0f;
+                w1 = (c == 1) ? 1.0f : 0.0f;
+                w2 = (c == 2) ? 1.0f : 0.0f;
+            } else {
+                const float4 r0 = a.G[0][se], r1 = a.G[1][se], r2 = a.G[2][se];
+                w0 = (c == 0) ? r0.x : (c == 1) ? r0.y : (c == 2) ? r0.z : r0.w;
+                w1 = (c == 0) ? r1.x : (c == 1) ? r1.y : (c == 2) ? r1.z : r1.w;
+                w2 = (c == 0) ? r2.x : (c == 1) ? r2.y : (c == 2) ? r2.z : r2.w;
+            }
+            float4 o;
+            if (j < 4) {
+                o = make_float4(w0, w1, w2, w3);
+            } else {
+                // (view_projection * world)[r, c], nalgebra order (Appendix A1), full 4x4: VP is projective
+                const float *m = ip.vp;
+                o.x = FYX_ADD(FYX_ADD(FYX_ADD(FYX_MUL(m[0], w0), FYX_MUL(m[4], w1)), FYX_MUL(m[8], w2)), FYX_MUL(m[12], w3));
+                o.y = FYX_ADD(FYX_ADD(FYX_ADD(FYX_MUL(m[1], w0), FYX_MUL(m[5], w1)), FYX_MUL(m[9], w2)), FYX_MUL(m[13], w3));
+                o.z = FYX_ADD(FYX_ADD(FYX_ADD(FYX_MUL(m[2], w0), FYX_MUL(m[6], w1)), FYX_MUL(m[10], w2)), FYX_MUL(m[14], w3));
+                o.w = FYX_ADD(FYX_ADD(FYX_ADD(FYX_MUL(m[3], w0), FYX_MUL(m[7], w1)), FYX_MUL(m[11], w2)), FYX_MUL(m[15], w3));
+            }
+            ip.o_mats[(size_t)pe * 8u + j] = o;
         }
-        float4 o;
-        if (j < 4) {
-            o = make_float4(w0, w1, w2, w3);
-        } else {
-            // (view_projection * world)[r, c], nalgebra order (Appendix A1), full 4x4: VP is projective
-            const float *m = ip.vp;
-            o.x = FYX_ADD(FYX_ADD(FYX_ADD(FYX_MUL(m[0], w0), FYX_MUL(m[4], w1)), FYX_MUL(m[8], w2)), FYX_MUL(m[12], w3));
-            o.y = FYX_ADD(FYX_ADD(FYX_ADD(FYX_MUL(m[1], w0), FYX_MUL(m[5], w1)), FYX_MUL(m[9], w2)), FYX_MUL(m[13], w3));
-            o.z = FYX_ADD(FYX_ADD(FYX_ADD(FYX_MUL(m[2], w0), FYX_MUL(m[6], w1)), FYX_MUL(m[10], w2)), FYX_MUL(m[14], w3));
-            o.w = FYX_ADD(FYX_ADD(FYX_ADD(FYX_MUL(m[3], w0), FYX_MUL(m[7], w1)), FYX_MUL(m[11], w2)), FYX_MUL(m[15], w3));
-        }
-        ip.o_mats[(size_t)pe * 8u + j] = o;
     }
 }
 
@@ -208,47 +243,44 @@ void launch_lod_level(cudaStream_t s, const NodeArrays &a, uint32_t lo, uint32_t
 
 // N3, bone matrices of the packed instances — RenderDataBundle::write_uniforms (renderer/bundle.rs:484-496): a skinned instance
 // gets a block of MAX_BONE_MATRICES (255) mat4: its bone_matrices, then all-zero matrices; an unskinned one gets none.
-// pass 1: which instance gets which block (order of the blocks is unspecified)
-__global__ void __launch_bounds__(kBlock) k_bone_block_index(const uint32_t n, const uint32_t *inst_node, const uint32_t *slot_of_node, const uint32_t n_nodes,
-                                                             const uint32_t *surf_of_slot, uint32_t *block_of_inst, uint32_t *counter)
+// pass 1: which instance gets which block (order of the blocks is unspecified); inst_skin = the fyx surface id that skins the instance
+__global__ void __launch_bounds__(kBlock) k_bone_block_index(const uint32_t n, const uint32_t *inst_skin, uint32_t *block_of_inst, uint32_t *counter)
 {
     const uint32_t i = blockIdx.x * kBlock + threadIdx.x;
     if (i >= n) return;
-    const uint32_t node = inst_node[i];
-    const uint32_t slot = node < n_nodes ? slot_of_node[node] : FYX_NONE;
-    const uint32_t sf = slot != FYX_NONE ? surf_of_slot[slot] : FYX_NONE;
-    block_of_inst[i] = (sf != FYX_NONE) ? atomicAdd(counter, 1u) : FYX_NONE;
+    block_of_inst[i] = (inst_skin[i] != FYX_NONE) ? atomicAdd(counter, 1u) : FYX_NONE;
 }
 // pass 2: one CTA per instance copies the surface's palette and pads with zeros (1020 float4 per block)
-__global__ void __launch_bounds__(kBlock) k_bone_blocks(const uint32_t *inst_node, const uint32_t *slot_of_node, const uint32_t *surf_of_slot,
-                                                        const uint2 *surf_bones /* (first palette entry, n_bones) */, const float4 *palette,
-                                                        const uint32_t *block_of_inst, float4 *blocks)
+__global__ void __launch_bounds__(kBlock) k_bone_blocks(const uint32_t *inst_skin, const uint2 *surf_bones /* (first palette entry, n_bones) */,
+                                                        const float4 *palette, const uint32_t *block_of_inst, float4 *blocks)
 {
     const uint32_t i = blockIdx.x;
     const uint32_t blk = block_of_inst[i];
     if (blk == FYX_NONE) return;
-    const uint2 sb = surf_bones[surf_of_slot[slot_of_node[inst_node[i]]]];
+    const uint2 sb = surf_bones[inst_skin[i]];
     float4 *dst = blocks + (size_t)blk * (FYX_MAX_BONES * 4);
     const float4 *src = palette + (size_t)sb.x * 4;
     for (uint32_t e = threadIdx.x; e < FYX_MAX_BONES * 4; e += kBlock) dst[e] = (e < sb.y * 4u) ? src[e] : make_float4(0.f, 0.f, 0.f, 0.f);
 }
 
-void launch_bone_block_index(cudaStream_t s, uint32_t n, const uint32_t *inst_node, const uint32_t *slot_of_node, uint32_t n_nodes, const uint32_t *surf_of_slot,
-                             uint32_t *block_of_inst, uint32_t *counter)
+void launch_bone_block_index(cudaStream_t s, uint32_t n, const uint32_t *inst_skin, uint32_t *block_of_inst, uint32_t *counter)
 {
-    if (n) k_bone_block_index<<<(n + kBlock - 1) / kBlock, kBlock, 0, s>>>(n, inst_node, slot_of_node, n_nodes, surf_of_slot, block_of_inst, counter);
+    if (n) k_bone_block_index<<<(n + kBlock - 1) / kBlock, kBlock, 0, s>>>(n, inst_skin, block_of_inst, counter);
 }
-void launch_bone_blocks(cudaStream_t s, uint32_t n, const uint32_t *inst_node, const uint32_t *slot_of_node, const uint32_t *surf_of_slot, const uint2 *surf_bones,
-                        const float *palette, const uint32_t *block_of_inst, float *blocks)
+void launch_bone_blocks(cudaStream_t s, uint32_t n, const uint32_t *inst_skin, const uint2 *surf_bones, const float *palette, const uint32_t *block_of_inst,
+                        float *blocks)
 {
-    if (n) k_bone_blocks<<<n, kBlock, 0, s>>>(inst_node, slot_of_node, surf_of_slot, surf_bones, reinterpret_cast<const float4 *>(palette), block_of_inst,
-                                             reinterpret_cast<float4 *>(blocks));
+    if (n) k_bone_blocks<<<n, kBlock, 0, s>>>(inst_skin, surf_bones, reinterpret_cast<const float4 *>(palette), block_of_inst, reinterpret_cast<float4 *>(blocks));
 }
 
-void launch_pack_instances(cudaStream_t s, const NodeArrays &a, const InstParams &ip)
+void launch_inst_count(cudaStream_t s, const NodeArrays &a, const InstParams &ip)
 {
     if (ip.n) k_inst_keys<<<(ip.n + kBlock - 1) / kBlock, kBlock, 0, s>>>(a, ip);
     k_inst_scan<<<1, kScanBlock, 0, s>>>(ip);
+}
+
+void launch_inst_scatter(cudaStream_t s, const NodeArrays &a, const InstParams &ip)
+{
     if (ip.n) k_inst_scatter<<<(ip.n + kBlock - 1) / kBlock, kBlock, 0, s>>>(a, ip);
 }
 

@@ -25,6 +25,10 @@ void inst_free(fyx_ctx *c)
         dev_free(o.b_bundles);
         dev_free(o.b_block_of);
         dev_free(o.b_blocks);
+        dev_free(o.b_surf);
+        dev_free(o.b_skin);
+        if (o.h_surf) cudaFreeHost(o.h_surf);
+        o.h_surf = nullptr;
         for (int k = 0; k < 4; ++k) {
             if (o.h[k]) cudaFreeHost(o.h[k]);
             o.h[k] = nullptr;
@@ -82,6 +86,64 @@ extern "C" int32_t fyx_set_bundle_ids(fyx_ctx *c, uint32_t count, const uint32_t
     return FYX_OK;
 }
 
+// Mesh::surfaces of the listed nodes (scene/mesh/mod.rs:726-805: one SurfaceInstanceData per surface)
+extern "C" int32_t fyx_set_node_surfaces(fyx_ctx *c, uint32_t count, const uint32_t *idx, const uint32_t *first, const uint32_t *bundle_ids,
+                                         const uint32_t *skin_surface)
+{
+    if (!c) return FYX_ERR_INVALID_ARGUMENT;
+    if (!c->have_topology) return fail(c, FYX_ERR_STATE, "fyx_set_topology has not been called");
+    if (!count) return FYX_OK;
+    if (!idx || !first) return fail(c, FYX_ERR_INVALID_ARGUMENT, "idx / first are NULL");
+    const uint32_t total = first[count];
+    if (total && !bundle_ids) return fail(c, FYX_ERR_INVALID_ARGUMENT, "bundle_ids is NULL");
+    for (uint32_t i = 0; i < count; ++i) {
+        if (first[i + 1] < first[i]) return fail(c, FYX_ERR_INVALID_ARGUMENT, "first[] must not decrease");
+        if (idx[i] >= c->n_nodes) return fail(c, FYX_ERR_INVALID_ARGUMENT, "node %u out of range", idx[i]);
+    }
+    uint32_t mx = 0;
+    for (uint32_t k = 0; k < total; ++k) {
+        mx = std::max(mx, bundle_ids[k]);
+        if (skin_surface && skin_surface[k] != FYX_NONE && skin_surface[k] >= c->surfaces.size())
+            return fail(c, FYX_ERR_INVALID_ARGUMENT, "skin surface id %u out of range", skin_surface[k]);
+    }
+    if (mx >= (1u << 24)) return fail(c, FYX_ERR_INVALID_ARGUMENT, "bundle id %u too large: ids must be dense (< 2^24)", mx);
+    if (c->ms_of_node.size() < c->n_nodes) c->ms_of_node.resize(c->n_nodes, make_uint2(0u, 0u));
+    for (uint32_t i = 0; i < count; ++i) {
+        const uint32_t n = first[i + 1] - first[i];
+        c->ms_of_node[idx[i]] = make_uint2((uint32_t)c->ms_bundle_h.size(), n); // appended; an older range of the node is abandoned
+        for (uint32_t k = first[i]; k < first[i + 1]; ++k) {
+            c->ms_bundle_h.push_back(bundle_ids[k]);
+            c->ms_skin_h.push_back(skin_surface ? skin_surface[k] : FYX_NONE);
+        }
+    }
+    if (total) c->n_bundle_ids = std::max(c->n_bundle_ids, mx + 1);
+    c->have_ms = true;
+    c->ms_dirty = true;
+    return FYX_OK;
+}
+
+static int32_t ms_flush(fyx_ctx *c)
+{
+    if (!c->have_ms || !c->ms_dirty) return FYX_OK;
+    std::vector<uint2> by_slot(std::max<uint32_t>(c->n_slots, 1), make_uint2(0u, 0u));
+    for (uint32_t sl = 0; sl < c->n_slots; ++sl) {
+        const uint32_t node = c->node_of_slot[sl];
+        if (node < c->ms_of_node.size()) by_slot[sl] = c->ms_of_node[node];
+    }
+    int32_t rc;
+    if ((rc = dev_ensure(c, c->b_ms_range, by_slot.size() * sizeof(uint2)))) return rc;
+    if ((rc = dev_ensure(c, c->b_ms_bundle, std::max<size_t>(c->ms_bundle_h.size(), 1) * 4))) return rc;
+    if ((rc = dev_ensure(c, c->b_ms_skin, std::max<size_t>(c->ms_skin_h.size(), 1) * 4))) return rc;
+    CU(cudaStreamSynchronize(c->stream));
+    CU(cudaMemcpy(c->b_ms_range.p, by_slot.data(), by_slot.size() * sizeof(uint2), cudaMemcpyHostToDevice));
+    if (!c->ms_bundle_h.empty()) {
+        CU(cudaMemcpy(c->b_ms_bundle.p, c->ms_bundle_h.data(), c->ms_bundle_h.size() * 4, cudaMemcpyHostToDevice));
+        CU(cudaMemcpy(c->b_ms_skin.p, c->ms_skin_h.data(), c->ms_skin_h.size() * 4, cudaMemcpyHostToDevice));
+    }
+    c->ms_dirty = false;
+    return FYX_OK;
+}
+
 extern "C" int32_t fyx_enable_instances(fyx_ctx *c, uint32_t enable)
 {
     if (!c) return FYX_ERR_INVALID_ARGUMENT;
@@ -107,14 +169,13 @@ extern "C" int32_t fyx_pack_instances(fyx_ctx *c, uint32_t f, const float *view,
         V.counts_on_host = true;
     }
     const uint32_t n = V.h_counts[f];
-    const uint32_t nb = c->have_bundles ? c->n_bundle_ids : 1u;
+    const uint32_t nb = (c->have_bundles || c->have_ms) ? c->n_bundle_ids : 1u;
     InstOut &o = c->inst[f];
     o.valid = false;
     int32_t rc;
+    if ((rc = commit_surfaces(c))) return rc; // surf_of_slot: which nodes are skinned
+    if ((rc = ms_flush(c))) return rc;
     const size_t n1 = std::max<uint32_t>(n, 1);
-    if ((rc = dev_ensure(c, o.b_node, n1 * 4))) return rc;
-    if ((rc = dev_ensure(c, o.b_sort, n1 * 8))) return rc;
-    if ((rc = dev_ensure(c, o.b_mats, n1 * 128))) return rc;
     if ((rc = dev_ensure(c, o.b_bundles, (size_t)nb * sizeof(fyx_bundle)))) return rc;
     if ((rc = dev_ensure(c, c->b_inst_hist, (size_t)nb * 4))) return rc;
     if ((rc = dev_ensure(c, c->b_inst_first, (size_t)nb * 8))) return rc;
@@ -141,6 +202,10 @@ extern "C" int32_t fyx_pack_instances(fyx_ctx *c, uint32_t f, const float *view,
     ip.vis_slot = V.b_vis_slot[f].as<uint32_t>();
     ip.bundle_of_slot = c->have_bundles ? c->b_bundle.as<uint32_t>() : nullptr;
     ip.rank_of_slot = have_rank ? c->b_rank_slot.as<uint32_t>() : nullptr;
+    ip.ms_range = c->have_ms ? c->b_ms_range.as<uint2>() : nullptr;
+    ip.ms_bundle = c->b_ms_bundle.as<uint32_t>();
+    ip.ms_skin = c->b_ms_skin.as<uint32_t>();
+    ip.surf_of_slot = c->b_surf_of_slot.as<uint32_t>();
     memcpy(ip.view, view, 64);
     memcpy(ip.vp, vp, 64);
     ip.n_bundle_ids = nb;
@@ -148,19 +213,36 @@ extern "C" int32_t fyx_pack_instances(fyx_ctx *c, uint32_t f, const float *view,
     ip.first_key = c->b_inst_first.as<unsigned long long>();
     ip.offset = c->b_inst_offset.as<uint32_t>();
     ip.tmp_sort = c->b_inst_tmp.as<uint64_t>();
-    ip.o_node = o.b_node.as<uint32_t>();
-    ip.o_sort = o.b_sort.as<uint64_t>();
-    ip.o_mats = o.b_mats.as<float4>();
     ip.o_bundles = o.b_bundles.as<fyx_bundle>();
     ip.o_n_bundles = c->b_inst_nb.as<uint32_t>();
-    launch_pack_instances(s, c->a, ip);
-    c->launches += n ? 3 : 1;
+    // phase 1: sort indices, histogram over (visible node, surface), scan -> number of bundles and of instances
+    launch_inst_count(s, c->a, ip);
+    c->launches += n ? 2 : 1;
     CU(cudaGetLastError());
-    CU(cudaMemcpyAsync(c->h_inst_nb, c->b_inst_nb.p, 4, cudaMemcpyDeviceToHost, s));
+    CU(cudaMemcpyAsync(c->h_inst_nb, c->b_inst_nb.p, 12, cudaMemcpyDeviceToHost, s));
     rc = sync_and_check(c);
     if (rc) return rc;
-    o.count = n;
-    o.n_bundles = *c->h_inst_nb;
+    const uint32_t n_inst = c->h_inst_nb[2];
+    const size_t m1 = std::max<uint32_t>(n_inst, 1);
+    if ((rc = dev_ensure(c, o.b_node, m1 * 4))) return rc;
+    if ((rc = dev_ensure(c, o.b_sort, m1 * 8))) return rc;
+    if ((rc = dev_ensure(c, o.b_surf, m1 * 4))) return rc;
+    if ((rc = dev_ensure(c, o.b_skin, m1 * 4))) return rc;
+    if ((rc = dev_ensure(c, o.b_mats, m1 * 128))) return rc;
+    ip.o_node = o.b_node.as<uint32_t>();
+    ip.o_sort = o.b_sort.as<uint64_t>();
+    ip.o_surf = o.b_surf.as<uint32_t>();
+    ip.o_skin = o.b_skin.as<uint32_t>();
+    ip.o_mats = o.b_mats.as<float4>();
+    // phase 2: scatter into bundle order
+    launch_inst_scatter(s, c->a, ip);
+    c->launches += n ? 1 : 0;
+    CU(cudaGetLastError());
+    rc = sync_and_check(c);
+    if (rc) return rc;
+    o.count = n_inst;
+    o.n_visible = n;
+    o.n_bundles = c->h_inst_nb[0];
     o.on_host = false;
     o.valid = true;
     o.blocks_valid = false;
@@ -182,14 +264,13 @@ extern "C" int32_t fyx_pack_bone_matrices(fyx_ctx *c, uint32_t f)
     if ((rc = dev_ensure(c, c->b_inst_nb, 256))) return rc;
     uint32_t *counter = c->b_inst_nb.as<uint32_t>() + 1;
     CU(cudaMemsetAsync(counter, 0, 4, s));
-    launch_bone_block_index(s, o.count, o.b_node.as<uint32_t>(), c->b_slot_of_node.as<uint32_t>(), c->n_nodes, c->b_surf_of_slot.as<uint32_t>(),
-                            o.b_block_of.as<uint32_t>(), counter);
+    launch_bone_block_index(s, o.count, o.b_skin.as<uint32_t>(), o.b_block_of.as<uint32_t>(), counter);
     CU(cudaMemcpyAsync(c->h_inst_nb + 1, counter, 4, cudaMemcpyDeviceToHost, s));
     CU(cudaStreamSynchronize(s));
     o.n_blocks = c->h_inst_nb[1];
     if ((rc = dev_ensure(c, o.b_blocks, std::max<size_t>(o.n_blocks, 1) * FYX_MAX_BONES * 64))) return rc;
-    launch_bone_blocks(s, o.count, o.b_node.as<uint32_t>(), c->b_slot_of_node.as<uint32_t>(), c->b_surf_of_slot.as<uint32_t>(), c->b_surf_bones.as<uint2>(),
-                       c->b_palette.as<float>(), o.b_block_of.as<uint32_t>(), o.b_blocks.as<float>());
+    launch_bone_blocks(s, o.count, o.b_skin.as<uint32_t>(), c->b_surf_bones.as<uint2>(), c->b_palette.as<float>(), o.b_block_of.as<uint32_t>(),
+                       o.b_blocks.as<float>());
     c->launches += o.count ? 2 : 0;
     CU(cudaGetLastError());
     rc = sync_and_check(c);
@@ -261,6 +342,20 @@ extern "C" int32_t fyx_get_instances(fyx_ctx *c, uint32_t f, fyx_instances *out)
     out->sort_index = static_cast<const uint64_t *>(o.h[1]);
     out->matrices = static_cast<const float *>(o.h[2]);
     out->bundles = static_cast<const fyx_bundle *>(o.h[3]);
+    return FYX_OK;
+}
+
+extern "C" int32_t fyx_get_instance_surfaces(fyx_ctx *c, uint32_t f, const uint32_t **out_ordinal)
+{
+    if (!c || !out_ordinal) return FYX_ERR_INVALID_ARGUMENT;
+    if (f >= FYX_MAX_FRUSTA || !c->inst[f].valid) return fail(c, FYX_ERR_STATE, "fyx_pack_instances has not been called for frustum %u", f);
+    InstOut &o = c->inst[f];
+    CU(cudaSetDevice(c->device));
+    int32_t rc = inst_host_ensure(c, &o.h_surf, &o.h_surf_cap, std::max<size_t>((size_t)o.count * 4, 1));
+    if (rc) return rc;
+    if (o.count) CU(cudaMemcpyAsync(o.h_surf, o.b_surf.p, (size_t)o.count * 4, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    *out_ordinal = static_cast<const uint32_t *>(o.h_surf);
     return FYX_OK;
 }
 

@@ -133,6 +133,11 @@ struct InstParams {
     const uint32_t *vis_slot;       // the same entries as slots
     const uint32_t *bundle_of_slot; // nullptr = every node in bundle 0
     const uint32_t *rank_of_slot;   // pre-order DFS rank (fyx_set_dfs_order); nullptr = node index order
+    // surfaces of a node (Mesh::surfaces): ms_range[slot] = (first, count) into ms_bundle / ms_skin; count 0 (or ms_range == nullptr)
+    // = ONE surface in the node's bundle id, skinned iff the node has a skinned surface (surf_of_slot)
+    const uint2 *ms_range;
+    const uint32_t *ms_bundle, *ms_skin;
+    const uint32_t *surf_of_slot;   // the node's first skinned fyx surface, FYX_NONE = none
     float view[16], vp[16];         // column-major
     uint32_t n_bundle_ids;
     // scratch (hist and first_key are cleared by the caller: 0 / ~0)
@@ -143,15 +148,17 @@ struct InstParams {
     // outputs
     uint32_t *o_node;
     uint64_t *o_sort;
+    uint32_t *o_surf;               // ordinal of the instance's surface within its node
+    uint32_t *o_skin;               // fyx surface id whose palette skins the instance, FYX_NONE = unskinned
     float4 *o_mats;                 // 8 float4 per instance: world (4 columns), view_projection * world (4 columns)
     fyx_bundle *o_bundles;
     uint32_t *o_n_bundles;
 };
-void launch_pack_instances(cudaStream_t s, const NodeArrays &a, const InstParams &ip);
-void launch_bone_block_index(cudaStream_t s, uint32_t n, const uint32_t *inst_node, const uint32_t *slot_of_node, uint32_t n_nodes, const uint32_t *surf_of_slot,
-                             uint32_t *block_of_inst, uint32_t *counter);
-void launch_bone_blocks(cudaStream_t s, uint32_t n, const uint32_t *inst_node, const uint32_t *slot_of_node, const uint32_t *surf_of_slot, const uint2 *surf_bones,
-                        const float *palette, const uint32_t *block_of_inst, float *blocks);
+void launch_inst_count(cudaStream_t s, const NodeArrays &a, const InstParams &ip);   // keys + scan: o_n_bundles[0] = bundles, [2] = instances
+void launch_inst_scatter(cudaStream_t s, const NodeArrays &a, const InstParams &ip);
+void launch_bone_block_index(cudaStream_t s, uint32_t n, const uint32_t *inst_skin, uint32_t *block_of_inst, uint32_t *counter);
+void launch_bone_blocks(cudaStream_t s, uint32_t n, const uint32_t *inst_skin, const uint2 *surf_bones, const float *palette, const uint32_t *block_of_inst,
+                        float *blocks);
 
 // Sub-forest plan (fyx_set_topology): the deep levels of the hierarchy — small sub-trees such as skeletons — are cut into groups
 // of whole sub-trees; one CTA walks all levels of its group with CTA-wide barriers instead of one kernel launch per level.

@@ -408,6 +408,15 @@ int32_t fyx_animate(fyx_ctx *ctx, float dt);
  * (renderer/bundle.rs:1248-1278, 483-487), for nodes with ONE surface: the instances of a frustum's visible
  * list grouped by bundle, each with its sort index, world matrix and view_projection * world. */
 
+/* Meshes with several surfaces (Mesh::surfaces): Mesh::collect_render_data pushes ONE SurfaceInstanceData per surface, each
+ * into the bundle of ITS (material, surface data, render path) key and with ITS bones, all with the node's sort index; the
+ * world matrix is the identity for a skinned surface and the node's global transform otherwise (scene/mesh/mod.rs:726-805).
+ * For node idx[i] the surfaces are entries [first[i], first[i+1]) of bundle_ids / skin_surface (first has count + 1 entries):
+ * bundle_ids[k] = the dense bundle id of surface k, skin_surface[k] = the fyx surface id (fyx_add_skinned_surface) whose
+ * palette skins it, FYX_NONE (or skin_surface == NULL) = unskinned.  Nodes never listed keep the default: one surface in the
+ * node's bundle id (fyx_set_bundle_ids), skinned iff the node has a skinned surface.  A count of 0 surfaces restores the default. */
+int32_t fyx_set_node_surfaces(fyx_ctx *ctx, uint32_t count, const uint32_t *idx, const uint32_t *first, const uint32_t *bundle_ids,
+                              const uint32_t *skin_surface);
 /* Per-node bundle id = the host's dense id for the (material, surface data, render path) key that push()
  * hashes (renderer/bundle.rs:1253-1257); every node starts in bundle 0.  idx NULL = nodes 0..count-1. */
 int32_t fyx_set_bundle_ids(fyx_ctx *ctx, uint32_t count, const uint32_t *idx, const uint32_t *bundle_ids);
@@ -425,7 +434,7 @@ typedef struct fyx_bundle {
 } fyx_bundle;
 
 typedef struct fyx_instances {
-    uint32_t count;             /* instances (== the visible count of the frustum) */
+    uint32_t count;             /* instances: one per (visible node, surface) */
     uint32_t n_bundles;         /* non-empty bundles */
     const uint32_t *node;       /* [count]   SurfaceInstanceData::node_handle (index) */
     const uint64_t *sort_index; /* [count]   RenderContext::calculate_sorting_index(global_position) (bundle.rs:118-127) */
@@ -438,6 +447,8 @@ typedef struct fyx_instances {
 /* Pack the visible list of `frustum` (of the most recent cull, made with instances enabled) for an observer
  * with the given view and view-projection matrices (ObserverPosition, renderer/observer.rs). */
 int32_t fyx_pack_instances(fyx_ctx *ctx, uint32_t frustum, const float *view_m16, const float *view_projection_m16);
+/* [count] ordinal of each packed instance's surface within its node (host copy; 0 everywhere without fyx_set_node_surfaces). */
+int32_t fyx_get_instance_surfaces(fyx_ctx *ctx, uint32_t frustum, const uint32_t **out_ordinal);
 /* Result of the last fyx_pack_instances for that frustum: pointers to pinned host copies ... */
 int32_t fyx_get_instances(fyx_ctx *ctx, uint32_t frustum, fyx_instances *out);
 /* ... or to the device-resident arrays (count / n_bundles still come back as host values). */
@@ -447,7 +458,8 @@ int32_t fyx_get_instances_device(fyx_ctx *ctx, uint32_t frustum, fyx_instances *
  * every instance whose node has a skinned surface gets a block of FYX_MAX_BONES (255 = ShaderDefinition::
  * MAX_BONE_MATRICES) column-major mat4 — its SurfaceInstanceData::bone_matrices, then all-zero matrices — and an
  * unskinned instance gets none (bone_matrices_block = None).  Uses the palettes of the last fyx_build_palettes /
- * fyx_render_prep; call after fyx_pack_instances.  Nodes with ONE skinned surface (the first one counts). */
+ * fyx_render_prep; call after fyx_pack_instances.  The surface that skins an instance is the one named by
+ * fyx_set_node_surfaces, else the node's first skinned surface. */
 typedef struct fyx_bone_blocks {
     uint32_t count;                    /* instances == fyx_instances.count */
     uint32_t n_blocks;                 /* skinned instances */

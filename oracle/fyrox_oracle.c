@@ -1239,6 +1239,38 @@ uint64_t orc_node_instance(const orc_graph *g, uint32_t node, const float view[1
     return orc_calculate_sorting_index(view, gp);
 }
 
+/* N3, meshes with several surfaces — Mesh::collect_render_data, scene/mesh/mod.rs:726-805: one SurfaceInstanceData per surface;
+ * `world = if is_skinned { identity } else { global_transform }` per SURFACE (:731-737), the node's sort index for all of them
+ * (:700), a static batch pushes the identity (:716).  Returns the sort index; out_skinned = the surface has bones. */
+uint64_t orc_node_surface_instance(const orc_graph *g, uint32_t node, uint32_t surface, const float view[16], const float vp[16],
+                                   float world[16], float wvp[16], int *out_skinned)
+{
+    const orc_node *n = node_at(g, node);
+    if (out_skinned) *out_skinned = 0;
+    if (!n || surface >= n->n_surfaces) {
+        orc_mat4_identity(world);
+        orc_mat4_mul(vp, world, wvp);
+        return 0;
+    }
+    const int skinned = n->surfaces[surface].n_bones != 0;
+    if (out_skinned) *out_skinned = skinned;
+    if (skinned || n->static_batch) orc_mat4_identity(world);
+    else memcpy(world, n->global_transform, 64);
+    orc_mat4_mul(vp, world, wvp);
+    const float gp[3] = {n->global_transform[12], n->global_transform[13], n->global_transform[14]};
+    return orc_calculate_sorting_index(view, gp);
+}
+
+/* bone_matrices of ONE surface, zero padded to 255 (renderer/bundle.rs:484-496); 0 = the surface is not skinned */
+int orc_surface_bone_block(const orc_graph *g, uint32_t mesh, uint32_t surface, float out[255 * 16])
+{
+    const orc_node *n = node_at(g, mesh);
+    if (!n || surface >= n->n_surfaces || !n->surfaces[surface].n_bones) return 0;
+    memset(out, 0, 255 * 64);
+    orc_mesh_bone_matrices(g, mesh, surface, out);
+    return 1;
+}
+
 /* N3 — the bone-matrix block RenderDataBundle::write_uniforms uploads for one instance (renderer/bundle.rs:484-496):
  * `matrices = [INIT; MAX_BONE_MATRICES]` (all-zero mat4, MAX_BONE_MATRICES = 255, fyrox-material/src/shader/mod.rs:613),
  * `matrices[0..n].copy_from_slice(&instance.bone_matrices)`; an instance with empty bone_matrices gets no block.

@@ -183,6 +183,10 @@ void     orc_mesh_accurate_world_bounding_box(const orc_graph *g, uint32_t mesh,
 /* free-standing skin of one vertex array with a given palette (used by the bench CPU baseline) */
 void orc_skin_vertices(const float *palette_m16, uint32_t n_verts, const void *verts,
                        const orc_vertex_layout *layout, float *out_pos3, float *out_nrm3);
+/* N3: one instance per surface (scene/mesh/mod.rs:726-805) and its bone block */
+uint64_t orc_node_surface_instance(const orc_graph *g, uint32_t node, uint32_t surface, const float view[16], const float vp[16],
+                                   float world[16], float wvp[16], int *out_skinned);
+int orc_surface_bone_block(const orc_graph *g, uint32_t mesh, uint32_t surface, float out[255 * 16]);
 /* N3: the zero-padded 255-mat4 block of one instance (renderer/bundle.rs:484-496); 0 = the node has no skinned surface */
 int orc_instance_bone_block(const orc_graph *g, uint32_t mesh, float out[255 * 16]);
 /* N4: blend-shape stage of the standard shader (standard.shader:167-173), then orc_skin_vertices; weights already / 100 */

@@ -184,6 +184,8 @@ def lib() -> C.CDLL:
         "orc_node_instance": (C.c_uint64, [vp, C.c_uint32, f32p, f32p, f32p, f32p]),
         "orc_mesh_accurate_world_bounding_box": (None, [vp, C.c_uint32, C.POINTER(Aabb)]),
         "orc_skin_vertices": (None, [f32p, C.c_uint32, vp, C.POINTER(VertexLayout), f32p, f32p]),
+        "orc_node_surface_instance": (C.c_uint64, [vp, C.c_uint32, C.c_uint32, f32p, f32p, f32p, f32p, C.POINTER(C.c_int)]),
+        "orc_surface_bone_block": (C.c_int, [vp, C.c_uint32, C.c_uint32, f32p]),
         "orc_instance_bone_block": (C.c_int, [vp, C.c_uint32, f32p]),
         "orc_skin_vertices_blend": (None, [f32p, C.c_uint32, vp, C.POINTER(VertexLayout), C.c_uint32, vp, C.c_uint32, f32p, f32p, f32p]),
     }

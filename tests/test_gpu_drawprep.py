@@ -146,6 +146,94 @@ def test_static_batches_prune_the_dfs_like_rdc_control_flow_break(ctx):
     assert seen > 0
 
 
+def test_meshes_with_several_surfaces_push_one_instance_per_surface(ctx):
+    """Mesh::collect_render_data pushes one SurfaceInstanceData per surface (scene/mesh/mod.rs:726-805): each goes to the
+    bundle of its own key, carries the identity if IT is skinned and the node's global transform otherwise, its own bone
+    matrices, and the node's sort index.  Skinned units get 3 surfaces (skinned, static, skinned with other bones), some
+    static leaves 2; everybody else keeps the default single surface."""
+    import ctypes as C
+
+    sc = Scene(5000, 10, verts_per_unit=64)
+    og, sids = scene_pair(sc, ctx)
+    idx, m = sc.animate(1)
+    for i, mm in zip(idx, m):
+        og.set_local_matrix(int(i), mm)
+    og.update_hierarchical_data()
+    rng = np.random.default_rng(8)
+    bundle = rng.integers(0, 23, sc.capacity).astype(np.uint32)  # default (single-surface) bundle ids
+    ctx.set_bundle_ids(bundle)
+    nodes, surfaces, want_key = [], [], {}
+    for u in range(sc.n_units):
+        mesh = int(sc.unit_mesh_node(u))
+        bones = sc.unit_bone_nodes(u)
+        # oracle: surface 0 exists (all bones); add an unskinned one and one skinned by the first 5 bones
+        og.add_surface(mesh, np.empty(0, np.uint32))
+        og.add_surface(mesh, bones[:5])
+        sid2 = ctx.add_skinned_surface(mesh, bones[:5], sc.unit_inv_bind(u)[:5], None, n_verts=0)
+        lst = [(int(rng.integers(30, 40)), sids[u]), (int(rng.integers(30, 40)), None), (int(rng.integers(30, 40)), sid2)]
+        nodes.append(mesh)
+        surfaces.append(lst)
+        for k, (bid, _) in enumerate(lst):
+            want_key[(mesh, k)] = bid
+    leaves = np.nonzero((sc.flags & fb.NODE_RENDERABLE) != 0)[0]
+    for leaf in leaves[:200:2]:
+        leaf = int(leaf)
+        if leaf in nodes:
+            continue
+        og.add_surface(leaf, np.empty(0, np.uint32))
+        og.add_surface(leaf, np.empty(0, np.uint32))
+        lst = [(int(rng.integers(40, 45)), None), (int(rng.integers(40, 45)), None)]
+        nodes.append(leaf)
+        surfaces.append(lst)
+        for k, (bid, _) in enumerate(lst):
+            want_key[(leaf, k)] = bid
+    ctx.set_node_surfaces(nodes, surfaces)
+    ctx.enable_instances()
+    view, vp, fo, ff = observer((0, 0, 400), (0, 0, 0), zf=900.0)
+    ctx.render_prep(update_flags=fb.UPDATE_ALL, changed_m16=m, changed_idx=idx, frusta=[ff])
+    inst = ctx.pack_instances(0, view, vp)
+    ctx.pack_bone_matrices(0)
+    vis = og.from_graph(fo)
+    multi = {n_: len(l) for n_, l in zip(nodes, surfaces)}
+    assert inst["node"].size == sum(multi.get(int(n_), 1) for n_ in vis)
+    L = ob.lib()
+    seen = set()
+    b = inst["bundles"]
+    owner = np.empty(inst["node"].size, np.uint32)
+    for row in b:
+        owner[int(row["first"]): int(row["first"] + row["count"])] = row["id"]
+    n_multi = n_blocks = 0
+    for k in range(inst["node"].size):
+        nd, sf = int(inst["node"][k]), int(inst["surface"][k])
+        assert (nd, sf) not in seen
+        seen.add((nd, sf))
+        blk = ctx.get_bone_matrix_block(0, k)
+        want = np.empty(255 * 16, np.float32)
+        if nd in multi:
+            w = np.empty(16, np.float32)
+            wvp = np.empty(16, np.float32)
+            sk = C.c_int()
+            # the oracle's surface ordinals of a unit mesh: 0 = the scene's skinned surface, 1, 2 = the two added above
+            si = L.orc_node_surface_instance(og.h, nd, sf, ob.fp(np.ascontiguousarray(view)), ob.fp(np.ascontiguousarray(vp)), ob.fp(w), ob.fp(wvp), C.byref(sk))
+            has = L.orc_surface_bone_block(og.h, nd, sf, ob.fp(want))
+            assert bool(has) == bool(sk.value)
+        else:  # the default: one surface, as Mesh::collect_render_data treats a single-surface mesh
+            assert sf == 0
+            si, w, wvp = og.instance(nd, view, vp)
+            has = L.orc_instance_bone_block(og.h, nd, ob.fp(want))
+        assert int(inst["sort_index"][k]) == si
+        assert inst["world"][k].tobytes() == w.tobytes() and inst["wvp"][k].tobytes() == wvp.tobytes()
+        assert int(owner[k]) == want_key.get((nd, sf), int(bundle[nd]))
+        assert bool(has) == (blk is not None)
+        if has:
+            assert blk.reshape(-1).tobytes() == want.tobytes()
+            n_blocks += 1
+        n_multi += nd in multi
+    assert n_multi > 30 and n_blocks >= 6
+    # every (visible node, surface) pair is there
+    assert seen == {(int(n_), k) for n_ in vis for k in range(multi.get(int(n_), 1))}
+
+
 def test_bone_matrix_blocks_of_packed_instances_match_oracle(ctx):
     """N3: every skinned instance of the packed list carries the 255-mat4 block write_uniforms builds (bone_matrices, then
     zero matrices, renderer/bundle.rs:484-496); unskinned instances carry none."""
