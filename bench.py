@@ -429,9 +429,10 @@ def parity_block(ctx, sc, fb, frusta, upload, world, rank, dist, log):
             gathered = [ctx.get_visible_gathered(f) for f in range(len(frusta))]
             g_ok, c_ok = True, True
             for f, lst in enumerate(gathered):
-                g_ok &= np.unique(lst).size == lst.size
+                sl = sp.SortedList(lst)
+                g_ok &= sl.duplicate_free
                 for p in allp:
-                    g_ok &= bool(np.array_equal(np.isin(p["gid"], lst), p["vis"][:, f]))
+                    g_ok &= bool(np.array_equal(sl.contains(p["gid"]), p["vis"][:, f]))
                 n, sm, x = sp.list_checksum(lst)
                 c_ok &= n == sum(p["sums"][f][0] for p in allp) and sm == sum(p["sums"][f][1] for p in allp) % (1 << 64)
                 xr = 0

@@ -141,6 +141,22 @@ def pick_sample(sc, rng, n_random: int, visible_lists_local=(), per_list: int = 
     return np.unique(np.concatenate(parts)).astype(np.uint32)
 
 
+class SortedList:
+    """One sort of a visible list, then duplicate check and membership of samples by binary search (np.isin / np.unique would
+    sort the list again for every query: the lists hold up to 10^8 entries)."""
+
+    def __init__(self, lst):
+        self.a = np.sort(np.asarray(lst, dtype=np.uint32))
+        self.duplicate_free = bool(self.a.size < 2 or (self.a[1:] != self.a[:-1]).all())
+
+    def contains(self, q) -> np.ndarray:
+        q = np.asarray(q, dtype=np.uint32)
+        if not self.a.size:
+            return np.zeros(q.shape, bool)
+        i = np.searchsorted(self.a, q)
+        return (i < self.a.size) & (self.a[np.minimum(i, self.a.size - 1)] == q)
+
+
 def check_nodes(ctx, truth: SampledTruth, sample: np.ndarray, frusta_o, own_lists_gidx, skinned_bones=None, cam_mask=0xFFFFFFFF):
     """Compare the context with the sampled truth.  own_lists_gidx[f] = this context's visible list of frustum f (global
     indices as emitted).  Returns a dict of counters / booleans and the per-sample expected bits (for N>1 union checks)."""
@@ -159,9 +175,9 @@ def check_nodes(ctx, truth: SampledTruth, sample: np.ndarray, frusta_o, own_list
     v_ok = np.ones(len(sample), bool)
     dup_free = True
     for f in range(len(frusta_o)):
-        lst = np.asarray(own_lists_gidx[f])
-        dup_free = dup_free and (np.unique(lst).size == lst.size)
-        v_ok &= np.isin(gid, lst) == vis[:, f]
+        sl = SortedList(own_lists_gidx[f])
+        dup_free = dup_free and sl.duplicate_free
+        v_ok &= sl.contains(gid) == vis[:, f]
     return {
         "checked_nodes": int(len(sample)),
         "global_matrices_bit_exact": bool(g_ok.all()),
