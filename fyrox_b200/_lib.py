@@ -37,6 +37,7 @@ NODE_ALIVE = 1 << 4
 NODE_RENDERABLE = 1 << 5
 NODE_LIGHT = 1 << 6
 NODE_STATIC_BATCH = 1 << 7
+NODE_REFLECTION_PROBE = 1 << 15
 NODE_GLOBAL_VISIBILITY = 1 << 8
 NODE_GLOBAL_ENABLED = 1 << 9
 NODE_REACHABLE = 1 << 10
@@ -197,6 +198,7 @@ SYMBOLS = {
     "fyx_set_lod_ranges": (C.c_int32, [ctx_p, C.c_uint32, C.c_void_p, C.c_void_p]),
     "fyx_set_observers": (C.c_int32, [ctx_p, C.c_uint32, C.c_void_p]),
     "fyx_cull_lights": (C.c_int32, [ctx_p]),
+    "fyx_select_reflection_probes": (C.c_int32, [ctx_p, C.c_uint32, C.c_void_p]),
     "fyx_get_visible_lights": (C.c_int32, [ctx_p, C.c_uint32, C.POINTER(u32p), u32p]),
     "fyx_build_palettes": (C.c_int32, [ctx_p]),
     "fyx_skin": (C.c_int32, [ctx_p]),

@@ -307,11 +307,19 @@ class Context:
             arr[k].translation[:] = [float(x) for x in t]
             arr[k].z_near, arr[k].z_far = float(zn), float(zf)
         self._chk(self._lib.fyx_set_observers(self._h, len(observers), C.cast(arr, C.c_void_p)))
+        self._n_observers = len(observers)
 
     # ---- N4 (light list) ----
     def cull_lights(self):
         """Light sources seen by every frustum of the most recent cull (renderer/bundle.rs:926-974)."""
         self._chk(self._lib.fyx_cull_lights(self._h))
+
+    def select_reflection_probes(self) -> np.ndarray:
+        """Per observer (set_observers): the reflection probe from_graph would pick (renderer/bundle.rs:918-925), FYX_NONE = none."""
+        n = getattr(self, "_n_observers", 0)
+        out = np.full(max(n, 1), L.FYX_NONE, np.uint32)
+        self._chk(self._lib.fyx_select_reflection_probes(self._h, n, out.ctypes.data_as(C.c_void_p)))
+        return out[:n]
 
     def get_visible_lights(self, frustum: int = 0) -> np.ndarray:
         p = L.u32p()

@@ -398,6 +398,36 @@ extern "C" int32_t fyx_cull_lights(fyx_ctx *c)
     return FYX_OK;
 }
 
+extern "C" int32_t fyx_select_reflection_probes(fyx_ctx *c, uint32_t count, uint32_t *out)
+{
+    if (!c || !out) return FYX_ERR_INVALID_ARGUMENT;
+    if (!c->have_topology) return fail(c, FYX_ERR_STATE, "fyx_set_topology has not been called");
+    if (count != c->observers.size()) return fail(c, FYX_ERR_INVALID_ARGUMENT, "%u results asked for, %zu observers set (fyx_set_observers)", count, c->observers.size());
+    if (!count) return FYX_OK;
+    CU(cudaSetDevice(c->device));
+    LodParams lp{};
+    lp.nf = (int)count;
+    for (uint32_t f = 0; f < count; ++f) {
+        lp.ox[f] = c->observers[f].translation[0];
+        lp.oy[f] = c->observers[f].translation[1];
+        lp.oz[f] = c->observers[f].translation[2];
+    }
+    int32_t rc = dev_ensure(c, c->b_light_counts, sizeof(uint32_t) * kCountStride * FYX_MAX_FRUSTA);
+    if (rc) return rc;
+    uint32_t *best = c->b_light_counts.as<uint32_t>();
+    CU(cudaMemsetAsync(best, 0, sizeof(uint32_t) * FYX_MAX_FRUSTA, c->stream));
+    launch_select_probes(c->stream, c->a, lp, best);
+    c->launches++;
+    CU(cudaGetLastError());
+    uint32_t h[FYX_MAX_FRUSTA];
+    CU(cudaMemcpyAsync(h, best, sizeof(uint32_t) * count, cudaMemcpyDeviceToHost, c->stream));
+    rc = sync_and_check(c);
+    if (rc) return rc;
+    for (uint32_t f = 0; f < count; ++f) out[f] = h[f] ? h[f] - 1u : FYX_NONE;
+    c->lights_valid = false; // the scratch counters were reused
+    return FYX_OK;
+}
+
 extern "C" int32_t fyx_get_visible_lights(fyx_ctx *c, uint32_t f, const uint32_t **out_idx, uint32_t *out_count)
 {
     if (!c || !out_idx || !out_count) return FYX_ERR_INVALID_ARGUMENT;

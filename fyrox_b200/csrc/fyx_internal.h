@@ -185,6 +185,7 @@ struct LodParams {
     float ox[FYX_MAX_FRUSTA], oy[FYX_MAX_FRUSTA], oz[FYX_MAX_FRUSTA], zn[FYX_MAX_FRUSTA], zr[FYX_MAX_FRUSTA];
 };
 void launch_lod_level(cudaStream_t s, const NodeArrays &a, uint32_t lo, uint32_t hi, const float2 *range, uint32_t *lodp, const LodParams &lp);
+void launch_select_probes(cudaStream_t s, const NodeArrays &a, const LodParams &obs, uint32_t *best /* [nf], cleared to 0 by the caller: node index + 1 */);
 void launch_cull_lights(cudaStream_t s, const NodeArrays &a, const CullParams &cp, uint32_t *const *d_out_ptrs, uint32_t *counts);
 void launch_fold_bones(cudaStream_t s, const NodeArrays &a, const FoldArrays &fa, const CullParams *cull);
 void launch_snapshot_bones(cudaStream_t s, const NodeArrays &a, uint32_t n_late, const uint32_t *late_slot, float4 *stale_pos);

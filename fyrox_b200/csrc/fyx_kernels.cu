@@ -1469,6 +1469,28 @@ void launch_compact_vis(cudaStream_t s, const NodeArrays &a, const CullParams &c
     launch_pdl(k_compact_vis, grid_for(((uint64_t)a.cap + 7) / 8), kBlock, 0, s, a, cp);
 }
 
+// Reflection-probe selection of from_graph (renderer/bundle.rs:918-925): the last ReflectionProbe in pool order whose world box
+// contains the observer (AxisAlignedBoundingBox::is_contains_point, inclusive) — atomicMax over (node index + 1) per observer.
+__global__ void __launch_bounds__(kBlock) k_select_probes(const NodeArrays a, const LodParams obs, uint32_t *best)
+{
+    const uint32_t slot = blockIdx.x * kBlock + threadIdx.x;
+    if (slot >= a.cap) return;
+    const uint32_t nf = a.flags[slot];
+    if ((nf & (FYX_NODE_ALIVE | FYX_NODE_REFLECTION_PROBE)) != (FYX_NODE_ALIVE | FYX_NODE_REFLECTION_PROBE)) return;
+    const float2 wx = a.wa[0][slot], wy = a.wa[1][slot], wz = a.wa[2][slot];
+    const uint32_t gi = a.gidx[slot];
+    for (int f = 0; f < obs.nf; ++f) {
+        const float px = obs.ox[f], py = obs.oy[f], pz = obs.oz[f];
+        if (px >= wx.x && px <= wx.y && py >= wy.x && py <= wy.y && pz >= wz.x && pz <= wz.y) atomicMax(best + f, gi + 1u);
+    }
+}
+
+void launch_select_probes(cudaStream_t s, const NodeArrays &a, const LodParams &obs, uint32_t *best)
+{
+    if (!a.cap || !obs.nf) return;
+    k_select_probes<<<grid_for(a.cap), kBlock, 0, s>>>(a, obs, best);
+}
+
 void launch_cull_lights(cudaStream_t s, const NodeArrays &a, const CullParams &cp, uint32_t *const *d_out_ptrs, uint32_t *counts)
 {
     if (!a.cap) return;

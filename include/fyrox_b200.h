@@ -62,7 +62,8 @@ typedef enum fyx_status {
 #define FYX_NODE_STATIC_BATCH    (1u << 7)  /* Mesh with BatchingMode::Static: when it is rendered for a frustum its children are
                                             * not visited for that frustum (RdcControlFlow::Break, scene/mesh/mod.rs:701-725) and its
                                             * instance carries the identity world matrix */
-#define FYX_NODE_INPUT_MASK      0xFFu
+#define FYX_NODE_REFLECTION_PROBE (1u << 15) /* the node is a ReflectionProbe: fyx_select_reflection_probes */
+#define FYX_NODE_INPUT_MASK      0x80FFu
 /* Computed bits, readable through fyx_get_global_flags (Base::global_visibility / is_globally_enabled,
  * scene/base.rs:751-770) */
 #define FYX_NODE_GLOBAL_VISIBILITY (1u << 8)
@@ -234,6 +235,10 @@ int32_t fyx_get_visible_device(fyx_ctx *ctx, uint32_t frustum, const uint32_t **
  * reference).  Lists come back in ascending node index = the reference's pool order.  Lights in sub-trees detached from
  * the root are outside the contract: the reference never updates such sub-trees, this library updates every tree. */
 int32_t fyx_cull_lights(fyx_ctx *ctx);
+/* The reflection-probe part of the same loop (renderer/bundle.rs:918-925): per observer of fyx_set_observers the LAST node in pool
+ * order that carries FYX_NODE_REFLECTION_PROBE and whose world bounding box contains the observer's translation (inclusive) —
+ * `storage.environment_map`; FYX_NONE = none.  out_probe receives one node index per observer. */
+int32_t fyx_select_reflection_probes(fyx_ctx *ctx, uint32_t count, uint32_t *out_probe);
 int32_t fyx_get_visible_lights(fyx_ctx *ctx, uint32_t frustum, const uint32_t **out_idx, uint32_t *out_count);
 
 /* N4 (LOD filter) — the lod_filter of RenderDataBundleStorage::from_graph (renderer/bundle.rs:898-916, 988-1004): a node

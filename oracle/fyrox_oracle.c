@@ -463,6 +463,7 @@ typedef struct orc_node {
     /* Base (scene/base.rs:389-483) */
     float local_matrix[16]; /* Transform::matrix() cache */
     int visibility, enabled, frustum_culling, cast_shadows, is_light;
+    int is_probe;     /* ReflectionProbe node */
     int static_batch; /* BatchingMode::Static: collect_render_data returns RdcControlFlow::Break when the mesh is rendered */
     uint32_t render_mask;
     uint32_t parent;
@@ -666,6 +667,7 @@ orc_graph *orc_graph_build(uint32_t capacity, const uint32_t *parent, const uint
         n->cast_shadows = !!(f & ORC_FLAG_CAST_SHADOWS);
         n->is_light = !!(f & ORC_FLAG_LIGHT);
         n->static_batch = !!(f & ORC_FLAG_STATIC_BATCH);
+        n->is_probe = !!(f & ORC_FLAG_REFLECTION_PROBE);
         if (render_mask) n->render_mask = render_mask[i];
         if (local_m16) memcpy(n->local_matrix, local_m16 + 16 * (size_t)i, 64);
         if (local_aabb6 && n->kind == ORC_KIND_MESH) {
@@ -1196,6 +1198,23 @@ uint32_t orc_mesh_skin(const orc_graph *g, uint32_t mesh, uint32_t surface, floa
 }
 
 int orc_node_is_alive(const orc_graph *g, uint32_t n) { return node_at(g, n) != NULL; }
+
+/* N4 — the reflection-probe part of the node loop of RenderDataBundleStorage::from_graph (renderer/bundle.rs:918-925): for every
+ * alive node in pool order that is a ReflectionProbe whose world bounding box contains the observer's translation (inclusive,
+ * AxisAlignedBoundingBox::is_contains_point, aabb.rs:193-200), `storage.environment_map = Some(probe)` — the LAST one wins.
+ * No visibility / enabled / reachability test there. */
+uint32_t orc_select_reflection_probe(const orc_graph *g, const float observer_translation[3])
+{
+    uint32_t pick = ORC_NONE;
+    for (uint32_t i = 0; i < g->capacity; ++i) {
+        const orc_node *n = node_at(g, i);
+        if (!n || !n->is_probe) continue;
+        orc_aabb w;
+        orc_node_world_bounding_box(g, i, &w);
+        if (orc_aabb_is_contains_point(&w, observer_translation)) pick = i;
+    }
+    return pick;
+}
 
 /* N4 (light list) — the `options.collect_lights` part of RenderDataBundleStorage::from_graph (renderer/bundle.rs:926-974):
  * every alive node, in pool order, that is a BaseLight, whose world bounding box the observer's frustum intersects and

@@ -126,6 +126,7 @@ orc_graph *orc_graph_build(uint32_t capacity, const uint32_t *parent, const uint
 #define ORC_FLAG_ALIVE           (1u << 4)
 #define ORC_FLAG_RENDERABLE      (1u << 5)   /* node kind emits render data (Mesh) */
 #define ORC_FLAG_LIGHT           (1u << 6)   /* node is a BaseLight (point / spot / directional) */
+#define ORC_FLAG_REFLECTION_PROBE (1u << 15) /* node is a ReflectionProbe (renderer/bundle.rs:918-925) */
 #define ORC_FLAG_STATIC_BATCH    (1u << 7)   /* Mesh::batching_mode == BatchingMode::Static (scene/mesh/mod.rs:701-725) */
 
 /* property setters; the three tracked ones push messages like TrackedProperty::deref_mut (base.rs:343-352) */
@@ -175,6 +176,8 @@ void     orc_node_set_lod_group(orc_graph *g, uint32_t node, uint32_t n_levels, 
 void     orc_lod_filter(const orc_graph *g, const float observer_translation[3], float z_near, float z_far, uint8_t *filter);
 size_t   orc_from_graph_lod(const orc_graph *g, const orc_frustum *f, uint32_t render_mask, int shadow_pass,
                             const float observer_translation[3], float z_near, float z_far, uint32_t *out_idx, size_t cap); /* N4: bundle.rs:898-916,988-1004 */
+/* N4: the reflection-probe selection of from_graph (renderer/bundle.rs:918-925): ORC_NONE = no probe contains the observer */
+uint32_t orc_select_reflection_probe(const orc_graph *g, const float observer_translation[3]);
 size_t   orc_collect_lights(const orc_graph *g, const orc_frustum *f, uint32_t *out_idx, size_t cap);   /* N4: renderer/bundle.rs:926-974 */
 uint64_t orc_node_instance(const orc_graph *g, uint32_t node, const float view[16], const float vp[16],
                            float world[16], float wvp[16]);   /* N3: mesh/mod.rs:700,731-737 + bundle.rs:483-487 */

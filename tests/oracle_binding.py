@@ -180,6 +180,7 @@ def lib() -> C.CDLL:
         "orc_node_set_lod_group": (None, [vp, C.c_uint32, C.c_uint32, f32p, f32p, vp, vp]),
         "orc_lod_filter": (None, [vp, f32p, C.c_float, C.c_float, vp]),
         "orc_from_graph_lod": (C.c_size_t, [vp, C.POINTER(Frustum), C.c_uint32, C.c_int, f32p, C.c_float, C.c_float, vp, C.c_size_t]),
+        "orc_select_reflection_probe": (C.c_uint32, [vp, f32p]),
         "orc_collect_lights": (C.c_size_t, [vp, C.POINTER(Frustum), vp, C.c_size_t]),
         "orc_node_instance": (C.c_uint64, [vp, C.c_uint32, f32p, f32p, f32p, f32p]),
         "orc_mesh_accurate_world_bounding_box": (None, [vp, C.c_uint32, C.POINTER(Aabb)]),

@@ -11,7 +11,7 @@ import pytest
 import fyrox_b200 as fb
 import oracle_binding as ob
 from fyrox_b200.scenegen import Scene
-from helpers import bits_equal, cube_frusta, preorder_rank, random_graph, scene_pair
+from helpers import NONE, bits_equal, cube_frusta, preorder_rank, random_graph, scene_pair
 
 pytestmark = pytest.mark.gpu
 
@@ -365,6 +365,42 @@ def test_light_lists_match_oracle(ctx):
     ctx.cull_lights()
     for f, o in enumerate(obs):
         assert np.array_equal(ctx.get_visible_lights(f), og.collect_lights(o[2]))
+
+
+def test_reflection_probe_selection_matches_oracle(ctx):
+    """The reflection-probe part of from_graph's node loop (renderer/bundle.rs:918-925): the LAST probe in pool order whose world
+    box contains the observer wins; no probe -> none; boxes that only touch the observer count (inclusive compares)."""
+    rng = np.random.default_rng(23)
+    parent, flags, mask, local, aabb = random_graph(rng, 3000, p_orphan=0.02)
+    alive = np.nonzero((flags & fb.NODE_ALIVE) != 0)[0]
+    probes = rng.choice(alive[alive != 0], 60, replace=False)
+    flags = flags.copy()
+    flags[probes] |= fb.NODE_REFLECTION_PROBE
+    aabb = aabb.copy()
+    h = rng.uniform(5.0, 40.0, (len(probes), 3)).astype(np.float32)  # big boxes: several contain a given point
+    aabb[probes, :3], aabb[probes, 3:] = -h, h
+    og = ob.Graph.build(parent, flags, mask, local, aabb)
+    og.L.orc_graph_drop_messages(og.h)
+    og.update_hierarchical_data()
+    ctx.set_topology(parent, flags, mask, aabb)
+    ctx.set_local_matrices(local)
+    ctx.update_transforms(fb.UPDATE_ALL)
+    # observers: random points, the centre of a probe's box, a point exactly ON a probe's box face, far away
+    reach = [int(p) for p in probes]
+    boxes = ctx.get_world_aabbs(np.array(reach, np.uint32))
+    obs = [tuple(rng.uniform(-30, 30, 3).astype(np.float32)) for _ in range(4)]
+    obs.append(tuple(((boxes[0, :3] + boxes[0, 3:]) * np.float32(0.5)).astype(np.float32)))
+    obs.append((float(boxes[1, 3]), float(boxes[1, 1] + boxes[1, 4]) * 0.5, float(boxes[1, 2] + boxes[1, 5]) * 0.5))  # on the +x face
+    obs.append((1e6, 1e6, 1e6))
+    ctx.set_observers([(o, 0.1, 100.0) for o in obs])
+    got = ctx.select_reflection_probes()
+    hits = 0
+    for k, o in enumerate(obs):
+        want = og.L.orc_select_reflection_probe(og.h, ob.fp(np.array(o, np.float32)))
+        assert int(got[k]) == int(want), (k, o, got[k], want)
+        hits += want != NONE
+    assert int(got[-1]) == NONE and hits >= 3
+    ctx.set_observers([])
 
 
 def test_lod_filter_matches_oracle(ctx):
