@@ -387,8 +387,10 @@ __device__ __forceinline__ void update_node(const NodeArrays &a, const uint32_t 
 
 // VAR: bit 0 = warp-level pre-reject of whole frusta, bit 1 = warp-wide compaction (else CTA-wide), bit 2 = FYX_UPDATE_ALL
 // specialisation (own columns, render mask and list index loaded up front)
+// bit 4 = compiled for 8 resident CTAs per SM (<= 32 registers: the 40 the kernel wants limit it to 48 of 64 warps, and it is
+// latency-bound)
 template <int NFT, int VAR>
-__global__ void __launch_bounds__(kBlock) k_update_level(const NodeArrays a, const uint32_t lo, const uint32_t hi,
+__global__ void __launch_bounds__(kBlock, (VAR & 16) ? 8 : 1) k_update_level(const NodeArrays a, const uint32_t lo, const uint32_t hi,
                                                          const uint32_t update_all, const CullParams cp)
 {
     pdl_trigger();
@@ -1388,7 +1390,7 @@ static int cull_variant(int nf)
 {
     static int forced = [] {
         const char *e = getenv("FYX_CULL_VARIANT");
-        return (e && *e) ? atoi(e) & 15 : -1;
+        return (e && *e) ? atoi(e) & 31 : -1;
     }();
     if (forced >= 0) return forced;
     (void)nf;
@@ -1411,7 +1413,9 @@ bool cull_defers_compaction(int nf) { return (cull_variant(nf) & 8) != 0; }
     case 8: launch_pdl(KERNEL<NF, 8>, __VA_ARGS__); break;                       \
     case 9: launch_pdl(KERNEL<NF, 9>, __VA_ARGS__); break;                       \
     case 12: launch_pdl(KERNEL<NF, 12>, __VA_ARGS__); break;                     \
-    default: launch_pdl(KERNEL<NF, 13>, __VA_ARGS__); break;                     \
+    case 13: launch_pdl(KERNEL<NF, 13>, __VA_ARGS__); break;                     \
+    case 20: launch_pdl(KERNEL<NF, 20>, __VA_ARGS__); break;                     \
+    default: launch_pdl(KERNEL<NF, 28>, __VA_ARGS__); break;                     \
     }
 
 void launch_update_level(cudaStream_t s, const NodeArrays &a, uint32_t lo, uint32_t hi, bool update_all, const CullParams *cull)
@@ -1422,6 +1426,7 @@ void launch_update_level(cudaStream_t s, const NodeArrays &a, uint32_t lo, uint3
         const uint32_t ua = update_all ? 1u : 0u;
         int var = (cull_variant(cull->nf) & 3) | ((update_all && (cull_variant(cull->nf) & 4)) ? 4 : 0);
         if (cull_variant(cull->nf) & 8) var = (var & 5) | 8; // deferred compaction: 8, 9, 12, 13
+        if ((cull_variant(cull->nf) & 16) && update_all) var = (cull_variant(cull->nf) & 8) ? 28 : 20; // 32-register builds: 20 (= 4 | 16), 28 (= 12 | 16)
         switch (cull->nf) { // the usual frustum counts get an unrolled cull: camera, CSM cascades, cube faces
         case 1: FYX_DISPATCH_VAR(k_update_level, 1, var, g, kBlock, 0, s, a, lo, hi, ua, *cull); break;
         case 2: FYX_DISPATCH_VAR(k_update_level, 2, var, g, kBlock, 0, s, a, lo, hi, ua, *cull); break;

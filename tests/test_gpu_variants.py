@@ -21,9 +21,9 @@ def _run(env, tests, k):
 
 
 @pytest.mark.timeout(1000)
-@pytest.mark.parametrize("variant", ["0", "1", "2", "3", "5", "7", "12", "13"])
+@pytest.mark.parametrize("variant", ["0", "1", "2", "3", "5", "7", "12", "13", "20", "28"])
 def test_cull_variants_match_the_oracle(variant):
-    """bit 0: warp-union pre-reject of whole frusta, bit 1: warp-wide compaction, bit 2: FYX_UPDATE_ALL specialisation, bit 3: deferred compaction (k_compact_vis)
+    """bit 0: warp-union pre-reject of whole frusta, bit 1: warp-wide compaction, bit 2: FYX_UPDATE_ALL specialisation, bit 3: deferred compaction (k_compact_vis), bit 4: 32-register build
     (fyx_kernels.cu; the default is 4)."""
     _run({"FYX_CULL_VARIANT": variant}, ["test_gpu_parity.py", "test_gpu_drawprep.py"],
          "cull or render_prep or pipelined or k7 or lod or light or instances or bundle")
