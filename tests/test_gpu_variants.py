@@ -21,24 +21,25 @@ def _run(env, tests, k):
 
 
 @pytest.mark.timeout(1000)
-@pytest.mark.parametrize("variant", ["0", "1", "2", "3", "5", "7", "12", "13", "20", "28"])
+@pytest.mark.parametrize("variant", ["0", "3", "13", "20"])
 def test_cull_variants_match_the_oracle(variant):
     """bit 0: warp-union pre-reject of whole frusta, bit 1: warp-wide compaction, bit 2: FYX_UPDATE_ALL specialisation, bit 3: deferred compaction (k_compact_vis), bit 4: 32-register build
-    (fyx_kernels.cu; the default is 4)."""
+    (fyx_kernels.cu; the default is 4).  Four variants exercise every bit; the others differ only in combinations."""
     _run({"FYX_CULL_VARIANT": variant}, ["test_gpu_parity.py", "test_gpu_drawprep.py"],
          "cull or render_prep or pipelined or k7 or lod or light or instances or bundle")
 
 
 @pytest.mark.timeout(1000)
-@pytest.mark.parametrize("variant", ["tma2", "tma3"])
+@pytest.mark.parametrize("variant", ["tma2", "tma3"])  # 2-stage / 3-stage rings
 def test_tma_skinning_variants_match_the_oracle(variant):
     """k_skin_tma: vertex blocks staged by cp.async.bulk + mbarrier rings (fyx_kernels.cu)."""
-    _run({"FYX_SKIN_VARIANT": variant}, ["test_gpu_parity.py", "test_gpu_fullsize.py"], "skin or render_prep or c3_full")
+    _run({"FYX_SKIN_VARIANT": variant}, ["test_gpu_parity.py", "test_gpu_fullsize.py"], "skin or render_prep")
 
 
 @pytest.mark.timeout(1000)
 @pytest.mark.parametrize("mode", ["0", "1"])
 def test_subforest_kernel_on_and_off_match_the_oracle(mode):
     """FYX_SUBFOREST: the deep levels of the hierarchy in one launch (k_update_subforest) or one launch per level — forced
-    both ways over the hierarchy / cull / skinning / animation parity tests (the default picks by level size)."""
+    both ways over the hierarchy / cull / skinning / animation parity tests (the default picks by level width: on for most
+    of the small test scenes, so "1" mostly adds the wide ones)."""
     _run({"FYX_SUBFOREST": mode}, ["test_gpu_parity.py", "test_gpu_anim.py", "test_gpu_drawprep.py"], "not cpp_host and not k6 and not k7")
