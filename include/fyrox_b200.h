@@ -311,12 +311,17 @@ typedef struct fyx_frame_desc {
 #define FYX_FRAME_ASYNC (1u << 0)
 /* Multi-GPU (after fyx_comm_init): all-gather the frame's visible lists as soon as the cull is done, on a
  * separate stream, overlapped with the palette / skinning kernels of the same frame; the frame is complete
- * when the gathered lists are (fyx_get_visible_gathered*). */
+ * when the gathered lists are (fyx_get_visible_gathered*).  Collective: every rank issues the frame.
+ * With readback_visible every rank also copies its OWN lists into the node-wide host segment (one PCIe link per rank);
+ * fyx_get_visible_gathered on any rank then returns the whole lists from that segment and fyx_get_visible the rank's
+ * own part of it (fyx_comm_mode tells whether the segment is in use; without it the host copy comes from the rank's
+ * device). */
 #define FYX_FRAME_ALLGATHER (1u << 1)
-/* With FYX_FRAME_ALLGATHER on a pipelined (async + read-back) frame: bring only THIS rank's lists to the host
- * (fyx_get_visible); the gathered lists stay device-resident (fyx_get_visible_gathered_device).  One process of the job
- * — the one that feeds the CPU-side renderer — leaves it off and receives the whole lists through its pinned copy; the
- * others do not multiply that PCIe traffic by the number of GPUs. */
+/* With FYX_FRAME_ALLGATHER on a pipelined (async + read-back) frame and NO host segment (FYX_HOSTSEG=0 or not available):
+ * bring only THIS rank's lists to the host (fyx_get_visible); the gathered lists stay device-resident.  One process of the
+ * job — the one that feeds the CPU-side renderer — leaves it off and receives the whole lists through its pinned copy; the
+ * others do not multiply that PCIe traffic by the number of GPUs.  With the host segment the flag changes nothing: every
+ * rank copies its own lists only. */
 #define FYX_FRAME_READBACK_OWN (1u << 2)
 int32_t fyx_frame_wait(fyx_ctx *ctx);
 int32_t fyx_render_prep(fyx_ctx *ctx, const fyx_frame_desc *frame);
