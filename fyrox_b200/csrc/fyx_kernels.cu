@@ -390,7 +390,7 @@ __device__ __forceinline__ void update_node(const NodeArrays &a, const uint32_t 
 // bit 4 = compiled for 8 resident CTAs per SM (<= 32 registers: the 40 the kernel wants limit it to 48 of 64 warps, and it is
 // latency-bound)
 template <int NFT, int VAR>
-__global__ void __launch_bounds__(kBlock, (VAR & 16) ? 8 : 1) k_update_level(const NodeArrays a, const uint32_t lo, const uint32_t hi,
+__global__ void __launch_bounds__(kBlock, (VAR & 16) ? 8 : 6) k_update_level(const NodeArrays a, const uint32_t lo, const uint32_t hi,
                                                          const uint32_t update_all, const CullParams cp)
 {
     pdl_trigger();
@@ -1394,7 +1394,7 @@ static int cull_variant(int nf)
     }();
     if (forced >= 0) return forced;
     (void)nf;
-    return 4; // measured (profiles/README.md, round 2): CTA-wide compaction, no pre-reject, FYX_UPDATE_ALL specialisation
+    return 20; // measured (profiles/README.md, round 2): CTA-wide compaction, no pre-reject, FYX_UPDATE_ALL specialisation, 32 registers
 }
 
 // bit 3 of the variant: the level kernels store visible bits, k_compact_vis builds the lists (bit 1 is then meaningless)
@@ -1415,6 +1415,7 @@ bool cull_defers_compaction(int nf) { return (cull_variant(nf) & 8) != 0; }
     case 12: launch_pdl(KERNEL<NF, 12>, __VA_ARGS__); break;                     \
     case 13: launch_pdl(KERNEL<NF, 13>, __VA_ARGS__); break;                     \
     case 20: launch_pdl(KERNEL<NF, 20>, __VA_ARGS__); break;                     \
+    case 21: launch_pdl(KERNEL<NF, 21>, __VA_ARGS__); break;                     \
     default: launch_pdl(KERNEL<NF, 28>, __VA_ARGS__); break;                     \
     }
 
@@ -1426,7 +1427,8 @@ void launch_update_level(cudaStream_t s, const NodeArrays &a, uint32_t lo, uint3
         const uint32_t ua = update_all ? 1u : 0u;
         int var = (cull_variant(cull->nf) & 3) | ((update_all && (cull_variant(cull->nf) & 4)) ? 4 : 0);
         if (cull_variant(cull->nf) & 8) var = (var & 5) | 8; // deferred compaction: 8, 9, 12, 13
-        if ((cull_variant(cull->nf) & 16) && update_all) var = (cull_variant(cull->nf) & 8) ? 28 : 20; // 32-register builds: 20 (= 4 | 16), 28 (= 12 | 16)
+        if ((cull_variant(cull->nf) & 16) && update_all) // 32-register builds: 20 (= 4 | 16), 21 (+ pre-reject), 28 (= 12 | 16)
+            var = (cull_variant(cull->nf) & 8) ? 28 : ((cull_variant(cull->nf) & 1) ? 21 : 20);
         switch (cull->nf) { // the usual frustum counts get an unrolled cull: camera, CSM cascades, cube faces
         case 1: FYX_DISPATCH_VAR(k_update_level, 1, var, g, kBlock, 0, s, a, lo, hi, ua, *cull); break;
         case 2: FYX_DISPATCH_VAR(k_update_level, 2, var, g, kBlock, 0, s, a, lo, hi, ua, *cull); break;
@@ -1438,7 +1440,8 @@ void launch_update_level(cudaStream_t s, const NodeArrays &a, uint32_t lo, uint3
     } else {
         CullParams none;
         none.nf = 0;
-        if (update_all && (cull_variant(0) & 4)) launch_pdl(k_update_level<-1, 4>, grid_for(hi - lo), kBlock, 0, s, a, lo, hi, 1u, none);
+        if (update_all && (cull_variant(0) & 16)) launch_pdl(k_update_level<-1, 20>, grid_for(hi - lo), kBlock, 0, s, a, lo, hi, 1u, none);
+        else if (update_all && (cull_variant(0) & 4)) launch_pdl(k_update_level<-1, 4>, grid_for(hi - lo), kBlock, 0, s, a, lo, hi, 1u, none);
         else launch_pdl(k_update_level<-1, 0>, grid_for(hi - lo), kBlock, 0, s, a, lo, hi, update_all ? 1u : 0u, none);
     }
 }

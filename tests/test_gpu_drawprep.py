@@ -371,8 +371,10 @@ def test_reflection_probe_selection_matches_oracle(ctx):
     """The reflection-probe part of from_graph's node loop (renderer/bundle.rs:918-925): the LAST probe in pool order whose world
     box contains the observer wins; no probe -> none; boxes that only touch the observer count (inclusive compares)."""
     rng = np.random.default_rng(23)
-    parent, flags, mask, local, aabb = random_graph(rng, 3000, p_orphan=0.02)
+    parent, flags, mask, local, aabb = random_graph(rng, 3000, p_orphan=0.0)
+    # probes among the nodes whose box the oracle takes from the caller as well (its pivots keep Base's unit box)
     alive = np.nonzero((flags & fb.NODE_ALIVE) != 0)[0]
+    alive = alive[(flags[alive] & fb.NODE_RENDERABLE) != 0]
     probes = rng.choice(alive[alive != 0], 60, replace=False)
     flags = flags.copy()
     flags[probes] |= fb.NODE_REFLECTION_PROBE
