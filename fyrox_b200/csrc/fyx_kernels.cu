@@ -914,6 +914,80 @@ __device__ __forceinline__ void skin_quad(const float4 *s_pal, const uint32_t la
     st_stream(no + 2, make_float4(mz[2], mx[3], my[3], mz[3]));
 }
 
+// two vertices (half of a four-vertex group) per thread: 22 input registers instead of 44 — k_skin2 trades wider loads for
+// more resident warps (k_skin sits at 24 warps per SM with 80 registers and is bound by load latency, not by bandwidth)
+template <int S, int LOG2C>
+__device__ __forceinline__ void skin_pair(const float4 *s_pal, const uint32_t lane, const float2 x2, const float2 y2, const float2 z2, const float2 nx2,
+                                          const float2 ny2, const float2 nz2, const float2 w0, const float2 w1, const float2 w2, const float2 w3,
+                                          const uint2 iq, float2 *po, float2 *no, const PackedConsts kc)
+{
+    constexpr int C = 1 << LOG2C;
+    constexpr int PL = S * C;
+    const float px[2] = {x2.x, x2.y}, py[2] = {y2.x, y2.y}, pz[2] = {z2.x, z2.y};
+    const float nx[2] = {nx2.x, nx2.y}, ny[2] = {ny2.x, ny2.y}, nz[2] = {nz2.x, nz2.y};
+    const float wk2[2][4] = {{w0.x, w1.x, w2.x, w3.x}, {w0.y, w1.y, w2.y, w3.y}};
+    const uint32_t iv[2] = {iq.x, iq.y};
+    float ox[2], oy[2], oz[2], mx[2], my[2], mz[2];
+#pragma unroll
+    for (int v = 0; v < 2; ++v) {
+        const float2 pxx = make_float2(px[v], px[v]), pyy = make_float2(py[v], py[v]), pzz = make_float2(pz[v], pz[v]);
+        const float2 nxx = make_float2(nx[v], nx[v]), nyy = make_float2(ny[v], ny[v]), nzz = make_float2(nz[v], nz[v]);
+        const float2 pnx = make_float2(px[v], nx[v]), pny = make_float2(py[v], ny[v]), pnz = make_float2(pz[v], nz[v]);
+        float2 acc_p = make_float2(0.0f, 0.0f), acc_n = make_float2(0.0f, 0.0f), acc_z = make_float2(0.0f, 0.0f);
+        const float *wk = wk2[v];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const uint32_t bone = (iv[v] >> (8 * k)) & 0xFFu;
+            const float4 *row = s_pal + (((lane - bone) & (uint32_t)(C - 1)) * S + bone);
+            const float4 A = row[0], B = row[PL], Z = row[2 * PL];
+            const float2 ww = make_float2(wk[k], wk[k]);
+            const float2 t = add2(add2(add2(mul2(lo2(A), pxx, kc), mul2(hi2(A), pyy, kc), kc), mul2(lo2(B), pzz, kc), kc), hi2(B), kc);
+            acc_p = add2(acc_p, mul2(t, ww, kc), kc);
+            const float2 r = add2(add2(mul2(lo2(A), nxx, kc), mul2(hi2(A), nyy, kc), kc), mul2(lo2(B), nzz, kc), kc);
+            acc_n = add2(acc_n, mul2(r, ww, kc), kc);
+            float2 z = add2(add2(mul2(pnx, make_float2(Z.x, Z.x), kc), mul2(pny, make_float2(Z.y, Z.y), kc), kc), mul2(pnz, make_float2(Z.z, Z.z), kc), kc);
+            z.x = FYX_ADD(z.x, Z.w);
+            acc_z = add2(acc_z, mul2(z, ww, kc), kc);
+        }
+        ox[v] = acc_p.x; oy[v] = acc_p.y; oz[v] = acc_z.x;
+        mx[v] = acc_n.x; my[v] = acc_n.y; mz[v] = acc_z.y;
+    }
+    st_stream(po + 0, make_float2(ox[0], oy[0]));
+    st_stream(po + 1, make_float2(oz[0], ox[1]));
+    st_stream(po + 2, make_float2(oy[1], oz[1]));
+    st_stream(no + 0, make_float2(mx[0], my[0]));
+    st_stream(no + 1, make_float2(mz[0], mx[1]));
+    st_stream(no + 2, make_float2(my[1], mz[1]));
+}
+
+template <int S, int LOG2C, int MINB>
+__global__ void __launch_bounds__(kBlock, MINB) k_skin2(const SkinArrays sk, const SkinTile *__restrict__ tiles, const uint32_t n_tiles, const float one,
+                                                      const float negzero)
+{
+    extern __shared__ float4 smem[];
+    float4 *const s_pal = smem;
+    PackedConsts kc;
+    kc.one = make_float2(one, one);
+    kc.negzero = make_float2(negzero, negzero);
+    const SkinTile T = tiles[blockIdx.x];
+    pdl_wait(); // the palettes come from k_palette
+    skin_fill_palette<S, LOG2C>(s_pal, sk.palette, T.bone_off, T.n_bones);
+    __syncthreads();
+    const uint32_t lane = threadIdx.x & 31u;
+    for (uint32_t h = threadIdx.x; h < 2u * T.n_quads; h += kBlock) {
+        const size_t quad = (size_t)T.quad_start + (h >> 1);
+        const float2 *row = reinterpret_cast<const float2 *>(sk.vblk + (quad >> 5) * kVblkStride + (quad & 31)) + (h & 1u);
+        const float2 x2 = ld_stream(row + 0 * 64), y2 = ld_stream(row + 1 * 64), z2 = ld_stream(row + 2 * 64);
+        const float2 nx2 = ld_stream(row + 3 * 64), ny2 = ld_stream(row + 4 * 64), nz2 = ld_stream(row + 5 * 64);
+        const float2 w0 = ld_stream(row + 6 * 64), w1 = ld_stream(row + 7 * 64), w2 = ld_stream(row + 8 * 64), w3 = ld_stream(row + 9 * 64);
+        const float2 iqf = ld_stream(row + 10 * 64);
+        const uint2 iq = make_uint2(__float_as_uint(iqf.x), __float_as_uint(iqf.y));
+        const size_t pair = 2 * quad + (h & 1u); // index of the vertex pair: 6 floats = 3 float2 per stream
+        skin_pair<S, LOG2C>(s_pal, lane, x2, y2, z2, nx2, ny2, nz2, w0, w1, w2, w3, iq, reinterpret_cast<float2 *>(sk.opos) + 3 * pair,
+                            reinterpret_cast<float2 *>(sk.onrm) + 3 * pair, kc);
+    }
+}
+
 // N4: blend shapes ahead of the skinning (standard.shader:167-173): for i in 0..blendShapesCount:
 //   inputPosition.xyz += offsets.position * weight;  inputNormal += offsets.normal * weight
 // in shape order, offsets = the f16 texels of BlendShapesContainer::from_lists (scene/mesh/surface.rs:92-218, exact in
@@ -1590,6 +1664,17 @@ template <int S, int LOG2C, int STAGES, int MINB> static void launch_skin_tma_t(
     launch_pdl(k_skin_tma<S, LOG2C, STAGES, MINB>, n_tiles, kBlock, smem, s, sk, tiles, n_tiles, 1.0f, -0.0f);
 }
 
+template <int S, int LOG2C, int MINB> static void launch_skin2_t(cudaStream_t s, const SkinArrays &sk, const SkinTile *tiles, uint32_t n_tiles)
+{
+    constexpr size_t smem_pal = (size_t)3 * S * (1 << LOG2C) * sizeof(float4);
+    static bool init = false;
+    if (!init) {
+        cudaFuncSetAttribute(k_skin2<S, LOG2C, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_pal);
+        init = true;
+    }
+    launch_pdl(k_skin2<S, LOG2C, MINB>, n_tiles, kBlock, smem_pal, s, sk, tiles, n_tiles, 1.0f, -0.0f);
+}
+
 // 0 = LDG straight into registers (default), 2 = TMA bulk ring (2 stages, 4 palette copies, 2 CTAs/SM), 3 = (3 stages, 8 copies, 1 CTA/SM)
 static int skin_variant()
 {
@@ -1598,6 +1683,9 @@ static int skin_variant()
         if (!e || !*e) return 0;
         if (!strcmp(e, "tma2")) return 2;
         if (!strcmp(e, "tma3")) return 3;
+        if (!strcmp(e, "pair4")) return 14; // two vertices per thread, compiled for 4 / 5 / 6 CTAs per SM
+        if (!strcmp(e, "pair5")) return 15;
+        if (!strcmp(e, "pair6")) return 16;
         return 0;
     }();
     return v;
@@ -1607,9 +1695,12 @@ void launch_skin(cudaStream_t s, const SkinArrays &sk, const SkinTile *tiles, ui
 {
     if (!n_tiles) return;
     const int var = skin_variant();
-    if (var && max_bones <= 64 && !blend_shapes) { // the experiment covers the benchmarked palette size
+    if (var && max_bones <= 64 && !blend_shapes) { // the experiments cover the benchmarked palette size
         if (var == 2) launch_skin_tma_t<65, 2, 2, 2>(s, sk, tiles, n_tiles);
-        else launch_skin_tma_t<65, 3, 3, 1>(s, sk, tiles, n_tiles);
+        else if (var == 3) launch_skin_tma_t<65, 3, 3, 1>(s, sk, tiles, n_tiles);
+        else if (var == 14) launch_skin2_t<65, 3, 4>(s, sk, tiles, n_tiles);
+        else if (var == 15) launch_skin2_t<65, 3, 5>(s, sk, tiles, n_tiles);
+        else launch_skin2_t<65, 3, 6>(s, sk, tiles, n_tiles);
         return;
     }
     // 3 CTAs/SM (<= 85 registers): capping at 64 registers for 4 CTAs/SM spills and measured 28 % slower

@@ -30,7 +30,7 @@ def test_cull_variants_match_the_oracle(variant):
 
 
 @pytest.mark.timeout(1000)
-@pytest.mark.parametrize("variant", ["tma2", "tma3"])  # 2-stage / 3-stage rings
+@pytest.mark.parametrize("variant", ["tma2", "tma3", "pair5"])  # TMA rings (2 / 3 stages); two vertices per thread
 def test_tma_skinning_variants_match_the_oracle(variant):
     """k_skin_tma: vertex blocks staged by cp.async.bulk + mbarrier rings (fyx_kernels.cu)."""
     _run({"FYX_SKIN_VARIANT": variant}, ["test_gpu_parity.py", "test_gpu_fullsize.py"], "skin or render_prep")
