@@ -39,6 +39,12 @@ def launches(tag, workload, path):
     # the last frame = everything after the last k_skin but one
     skins = [k for k, (n, _, _) in enumerate(seq) if n.startswith("k_skin")]
     frame = seq[skins[-2] + 1: skins[-1] + 1] if len(skins) >= 2 else seq
+    # prefer the last frame that ran the default FYX_UPDATE_ALL kernels (the run ends with incremental-update frames)
+    for k in range(len(skins) - 1, 0, -1):
+        cand = seq[skins[k - 1] + 1: skins[k] + 1]
+        if any(", 20>" in n for n, _, _ in cand):
+            frame = cand
+            break
     out = os.path.join(OUT, f"{tag}_launches_{workload}.md")
     with open(out, "w") as f:
         f.write(f"# ncu launch list — workload `{workload}` ({tag})\n\n")
