@@ -68,6 +68,7 @@ public:
         if (ftruncate(fd, (off_t)bytes) != 0) return fail("ftruncate");
         if (!map()) return false;
         owner = true;
+        interleave_pages(); // before the first touch
         new (header()) HostSegHeader();
         for (int s = 0; s < 2; ++s)
             for (int r = 0; r < kSegMaxRanks; ++r) {
@@ -121,6 +122,25 @@ public:
     bool wait_complete(uint64_t epoch, double timeout_s = 20.0) { return wait_all(header()->done[epoch & 1], epoch, timeout_s, "done"); }
 
 private:
+    // The segment is written by GPUs on every socket of the node: spread its pages over all NUMA nodes instead of letting
+    // the creator's first touch (cudaHostRegister pins them) put them all next to rank 0.  Best effort (mbind may be denied).
+    void interleave_pages()
+    {
+#ifdef SYS_mbind
+        unsigned long mask[16];
+        int nodes = 0;
+        for (int n = 0; n < 64; ++n) {
+            char path[64];
+            snprintf(path, sizeof path, "/sys/devices/system/node/node%d", n);
+            if (access(path, F_OK) == 0) nodes = n + 1;
+        }
+        if (nodes < 2) return;
+        memset(mask, 0, sizeof mask);
+        for (int n = 0; n < nodes; ++n) mask[n / (8 * sizeof(unsigned long))] |= 1ul << (n % (8 * sizeof(unsigned long)));
+        const int MPOL_INTERLEAVE_ = 3;
+        (void)syscall(SYS_mbind, base, bytes, MPOL_INTERLEAVE_, mask, (unsigned long)(nodes + 1), 0u);
+#endif
+    }
     bool map()
     {
         void *p = mmap(nullptr, bytes, PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
