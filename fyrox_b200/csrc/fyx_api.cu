@@ -153,6 +153,8 @@ struct fyx_ctx {
     cudaEvent_t ev_upload[2] = {}, ev_slot_free[2] = {};
     bool slot_used[2] = {false, false};
     int upload_parity = 0;
+    cudaEvent_t ev_levels_prev = nullptr; // the previous frame's "level kernels + fold + cull are done" event (its ev_cull), if it recorded one
+    uint64_t launches_at_frame_end = ~0ull;
 
     // skinning
     std::vector<Surface> surfaces;
@@ -1766,12 +1768,12 @@ extern "C" int32_t fyx_render_prep(fyx_ctx *c, const fyx_frame_desc *fr)
         }
         const size_t mb = (size_t)fr->n_changed * (as_rot ? 16 : (as_trs ? sizeof(fyx_trs) : 64)), ib = fr->changed_idx ? (size_t)fr->n_changed * 4 : 0;
         const fyx_transform_statics *st = c->have_statics ? c->b_statics.as<fyx_transform_statics>() : nullptr;
-        auto scatter = [&](const void *d_p, const uint32_t *d_i) {
+        auto scatter = [&](cudaStream_t ss, const void *d_p, const uint32_t *d_i) {
             if (as_rot || as_trs)
-                launch_scatter_trs(s, c->a, fr->n_changed, d_i, d_p, as_rot, c->b_trs.as<fyx_trs>(), st, c->b_slot_of_node.as<uint32_t>(),
+                launch_scatter_trs(ss, c->a, fr->n_changed, d_i, d_p, as_rot, c->b_trs.as<fyx_trs>(), st, c->b_slot_of_node.as<uint32_t>(),
                                    c->n_nodes, c->d_err);
             else
-                launch_scatter_locals(s, c->a, fr->n_changed, d_i, static_cast<const float *>(d_p), c->b_slot_of_node.as<uint32_t>(),
+                launch_scatter_locals(ss, c->a, fr->n_changed, d_i, static_cast<const float *>(d_p), c->b_slot_of_node.as<uint32_t>(),
                                       c->n_nodes, c->d_err);
         };
         if (async && is_pinned(payload) && (!fr->changed_idx || is_pinned(fr->changed_idx))) {
@@ -1783,16 +1785,34 @@ extern "C" int32_t fyx_render_prep(fyx_ctx *c, const fyx_frame_desc *fr)
             char *base = c->d_stage_frame[u].as<char>();
             CU(cudaMemcpyAsync(base, payload, mb, cudaMemcpyHostToDevice, c->copy_stream));
             if (ib) CU(cudaMemcpyAsync(base + off, fr->changed_idx, ib, cudaMemcpyHostToDevice, c->copy_stream));
-            CU(cudaEventRecord(c->ev_upload[u], c->copy_stream));
-            CU(cudaStreamWaitEvent(s, c->ev_upload[u], 0));
-            scatter(base, ib ? reinterpret_cast<const uint32_t *>(base + off) : nullptr);
-            CU(cudaEventRecord(c->ev_slot_free[u], s));
+            // The scatter writes local matrices / TRS records / F_DIRTY_SELF of the changed nodes — columns nothing of the PREVIOUS
+            // frame reads once its level kernels and fold are done.  When that point is known (the previous frame recorded its
+            // cull event) and nothing else has been enqueued on the main stream since, the scatter runs on the copy stream, beside
+            // the previous frame's palette / skinning kernels, instead of in front of this frame's level kernels.
+            static const bool side_allowed = [] {
+                const char *e = getenv("FYX_SIDE_SCATTER"); // 0: always scatter on the main stream (A/B measurements)
+                return !(e && *e == '0');
+            }();
+            const bool side = side_allowed && c->ev_levels_prev && c->launches == c->launches_at_frame_end &&
+                              !(fr->struct_size >= sizeof(fyx_frame_desc) && fr->do_animate);
+            if (side) {
+                CU(cudaStreamWaitEvent(c->copy_stream, c->ev_levels_prev, 0));
+                scatter(c->copy_stream, base, ib ? reinterpret_cast<const uint32_t *>(base + off) : nullptr);
+                CU(cudaEventRecord(c->ev_upload[u], c->copy_stream));
+                CU(cudaEventRecord(c->ev_slot_free[u], c->copy_stream));
+                CU(cudaStreamWaitEvent(s, c->ev_upload[u], 0));
+            } else {
+                CU(cudaEventRecord(c->ev_upload[u], c->copy_stream));
+                CU(cudaStreamWaitEvent(s, c->ev_upload[u], 0));
+                scatter(s, base, ib ? reinterpret_cast<const uint32_t *>(base + off) : nullptr);
+                CU(cudaEventRecord(c->ev_slot_free[u], s));
+            }
             c->slot_used[u] = true;
         } else {
             void *d_m = nullptr, *d_i = nullptr;
             rc = stage_to_device(c, payload, mb, fr->changed_idx, ib, true, &d_m, &d_i);
             if (rc) return rc;
-            scatter(d_m, static_cast<const uint32_t *>(d_i));
+            scatter(s, d_m, static_cast<const uint32_t *>(d_i));
         }
         c->launches++;
     }
@@ -1809,7 +1829,11 @@ extern "C" int32_t fyx_render_prep(fyx_ctx *c, const fyx_frame_desc *fr)
         if (unf && (rc = cull_unfused(c, fr->n_frusta))) return rc;
     }
     if (stage_events) CU(cudaEventRecord(c->ev[EV_UPDATE], s));
-    if (fr->n_frusta && (async || (fr->flags & FYX_FRAME_ALLGATHER))) CU(cudaEventRecord(c->vs[c->cur].ev_cull, s)); // consumed by the read-back / collective streams
+    c->ev_levels_prev = nullptr;
+    if (fr->n_frusta && (async || (fr->flags & FYX_FRAME_ALLGATHER))) {
+        CU(cudaEventRecord(c->vs[c->cur].ev_cull, s)); // consumed by the read-back / collective streams and by the next frame's scatter
+        c->ev_levels_prev = c->vs[c->cur].ev_cull;
+    }
     // multi-GPU: the visible lists are complete here; their all-gather runs on the collective stream beside
     // the palette / skinning kernels below (the path's one exchange step)
     const bool gather = (fr->flags & FYX_FRAME_ALLGATHER) && fr->n_frusta;
@@ -1858,6 +1882,7 @@ extern "C" int32_t fyx_render_prep(fyx_ctx *c, const fyx_frame_desc *fr)
         if (rc) return rc;
     } // with FYX_FRAME_ALLGATHER the frame's result is the gathered lists: fyx_get_visible_gathered fetches them
     CU(cudaEventRecord(c->ev[EV_READBACK], s));
+    c->launches_at_frame_end = c->launches;
     if (async) {
         c->timings_pending = true;
         return FYX_OK;
