@@ -82,13 +82,28 @@ struct TransformBuilder {
     Transform build() const { return t; }
 };
 
+// BlendShape / BlendShapesContainer (scene/mesh/surface.rs:71-218): weight in 0..100 and the texels of the volume texture
+// from_lists builds (n_shapes layers x layer_stride records of 9 binary16 values: position, normal, tangent offsets)
+struct BlendShape {
+    float weight = 100.0f;
+    std::string name;
+};
+struct BlendShapesContainer {
+    std::vector<BlendShape> blend_shapes;
+    std::vector<uint16_t> blend_shape_storage;
+    uint32_t layer_stride = 0;
+};
+
 struct Surface {
     std::vector<Handle> bones;
     std::vector<uint8_t> vertex_buffer; // AnimatedVertex records (68 B)
     int64_t surface_id = -1;
+    BlendShapesContainer blend_shapes_container; // SurfaceData::blend_shapes_container
+    bool shapes_uploaded = false;
 };
 
 enum class NodeKind { Pivot, Mesh };
+enum class BatchingMode { None, Static, Dynamic }; // scene/mesh/mod.rs:120-140
 
 class Graph;
 
@@ -102,6 +117,13 @@ class Node {
     AxisAlignedBoundingBox local_bounding_box = AxisAlignedBoundingBox::unit();
     Mat4 inv_bind_pose_transform{{1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1}};
     std::vector<Surface> surfaces;
+
+    // Mesh::batching_mode / set_batching_mode (scene/mesh/mod.rs:372, 612-617): a Static mesh that is rendered returns
+    // RdcControlFlow::Break and the DFS of from_graph does not visit its children (:701-725)
+    BatchingMode batching_mode() const { return batching_mode_; }
+    void set_batching_mode(BatchingMode m);
+    // Mesh::blend_shapes_mut (scene/mesh/mod.rs:453-456): the weights (0..100) of the first surface that has shapes
+    std::vector<BlendShape> &blend_shapes_mut();
 
     const Transform &local_transform() const { return transform_; }
     Transform &local_transform_mut();          // marks TransformChanged (scene/base.rs:343-352)
@@ -121,13 +143,15 @@ class Node {
     friend struct BaseBuilder;
     Transform transform_;
     bool visibility_ = true, enabled_ = true;
+    BatchingMode batching_mode_ = BatchingMode::None;
     Graph *graph_ = nullptr;
     Handle self_;
     uint32_t flags_word() const
     {
         return FYX_NODE_ALIVE | (visibility_ ? FYX_NODE_VISIBILITY : 0u) | (enabled_ ? FYX_NODE_ENABLED : 0u) |
                (frustum_culling ? FYX_NODE_FRUSTUM_CULLING : 0u) | (cast_shadows ? FYX_NODE_CAST_SHADOWS : 0u) |
-               (kind == NodeKind::Mesh ? FYX_NODE_RENDERABLE : 0u);
+               (kind == NodeKind::Mesh ? FYX_NODE_RENDERABLE : 0u) |
+               ((kind == NodeKind::Mesh && batching_mode_ == BatchingMode::Static) ? FYX_NODE_STATIC_BATCH : 0u);
     }
 };
 
@@ -382,7 +406,21 @@ class Graph {
                                               nv ? &animated : nullptr, &sid));
                 s.surface_id = sid;
             }
+            // SurfaceData::blend_shapes_container -> fyx_set_blend_shapes once, Mesh::blend_shapes weights when they were touched
+            for (Surface &s : records_[i].surfaces) {
+                BlendShapesContainer &bc = s.blend_shapes_container;
+                if (s.surface_id < 0 || bc.blend_shapes.empty() || bc.blend_shape_storage.empty()) continue;
+                std::vector<float> w;
+                for (const BlendShape &b : bc.blend_shapes) w.push_back(b.weight);
+                if (!s.shapes_uploaded) {
+                    check(fyx_set_blend_shapes(ctx_, (uint32_t)s.surface_id, (uint32_t)w.size(), bc.blend_shape_storage.data(), bc.layer_stride, w.data()));
+                    s.shapes_uploaded = true;
+                } else if (dirty_shapes_.count(i)) {
+                    check(fyx_set_blend_shape_weights(ctx_, (uint32_t)s.surface_id, (uint32_t)w.size(), w.data()));
+                }
+            }
         }
+        dirty_shapes_.clear();
     }
 
     fyx_ctx *ctx_ = nullptr;
@@ -392,7 +430,7 @@ class Graph {
     std::vector<uint32_t> free_;
     Handle root_;
     bool topology_dirty_ = true;
-    std::set<uint32_t> dirty_transform_, dirty_flags_;
+    std::set<uint32_t> dirty_transform_, dirty_flags_, dirty_shapes_;
 };
 
 inline Transform &Node::local_transform_mut()
@@ -409,6 +447,19 @@ inline void Node::set_enabled(bool v)
 {
     enabled_ = v;
     if (graph_) graph_->dirty_flags_.insert(self_.index);
+}
+inline void Node::set_batching_mode(BatchingMode m)
+{
+    batching_mode_ = m;
+    if (graph_) graph_->dirty_flags_.insert(self_.index);
+}
+inline std::vector<BlendShape> &Node::blend_shapes_mut()
+{
+    if (graph_) graph_->dirty_shapes_.insert(self_.index);
+    for (Surface &s : surfaces)
+        if (!s.blend_shapes_container.blend_shapes.empty()) return s.blend_shapes_container.blend_shapes;
+    static std::vector<BlendShape> none;
+    return none;
 }
 inline Mat4 Node::global_transform() const { return graph_->global_transform(self_); }
 inline Vec3 Node::global_position() const

@@ -63,6 +63,32 @@ int main()
             CHECK(eq(graph[d].global_position(), 2, 1, 1));
             for (Handle h : {a, b, c, d}) CHECK(graph[h].global_visibility() && !graph[h].is_globally_enabled());
         }
+        { // static batching: a rendered BatchingMode::Static mesh returns RdcControlFlow::Break (scene/mesh/mod.rs:701-725)
+            Graph graph;
+            const AxisAlignedBoundingBox box = AxisAlignedBoundingBox::from_min_max({{-1, -1, -1}}, {{1, 1, 1}});
+            auto at = [](float x, float y, float z) { return TransformBuilder().with_local_position({{x, y, z}}).build(); };
+            Handle child_a = BaseBuilder().with_local_bounding_box(box).with_local_transform(at(1, 0, 0)).build_mesh(graph);
+            Handle parent_a = BaseBuilder().with_local_bounding_box(box).with_local_transform(at(0, 0, -10)).with_child(child_a).build_mesh(graph);
+            Handle child_b = BaseBuilder().with_local_bounding_box(box).with_local_transform(at(0, 0, -70)).build_mesh(graph);
+            Handle parent_b = BaseBuilder().with_local_bounding_box(box).with_local_transform(at(0, 0, 50)).with_child(child_b).build_mesh(graph);
+            graph.update();
+            ObserverPosition op;
+            op.view_matrix = look_at_rh_neg_z();
+            op.projection_matrix = perspective(16.0f / 9.0f, 60.0f * 3.14159265358979f / 180.0f, 0.1f, 150.0f);
+            auto vis = [&]() {
+                std::set<uint32_t> v;
+                for (Handle h : RenderDataBundleStorage::from_graph(graph, 0xFFFFFFFFu, 0.0f, op, "GBuffer").visible_handles) v.insert(h.index);
+                return v;
+            };
+            CHECK((vis() == std::set<uint32_t>{parent_a.index, child_a.index, child_b.index}));
+            graph[parent_a].set_batching_mode(BatchingMode::Static);
+            graph[parent_b].set_batching_mode(BatchingMode::Static);
+            graph.update();
+            CHECK((vis() == std::set<uint32_t>{parent_a.index, child_b.index})); // a rendered batch hides its child, a culled one does not
+            graph[parent_a].set_batching_mode(BatchingMode::None);
+            graph.update();
+            CHECK((vis() == std::set<uint32_t>{parent_a.index, child_a.index, child_b.index}));
+        }
         { // test_global_scale, graph/mod.rs:2602-2644 + a cull through from_graph
             Graph graph;
             Handle c = BaseBuilder().with_local_transform(TransformBuilder().with_local_scale({{1, 2, 3}}).build()).build_pivot(graph);
