@@ -271,6 +271,8 @@ int32_t dev_ensure(fyx_ctx *c, DevBuf &b, size_t bytes, bool keep = false)
     nb = (nb + 255) & ~size_t(255);
     void *np = nullptr;
     CU(cudaMalloc(&np, nb));
+    // growable tables are copied as a whole when they grow again: give their not-yet-written tail a defined value
+    if (keep) CU(cudaMemsetAsync(np, 0, nb, c->stream));
     if (b.p) {
         cudaError_t e = cudaSuccess;
         if (keep && b.bytes) e = cudaMemcpyAsync(np, b.p, b.bytes, cudaMemcpyDeviceToDevice, c->stream);

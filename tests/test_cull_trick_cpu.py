@@ -166,3 +166,41 @@ def test_warp_union_pre_reject_never_hides_a_visible_box():
             skipped += int(dead.sum())
             visible_total += int(vis.sum())
     assert skipped > 10000 and visible_total > 10000  # both outcomes are exercised
+
+
+def test_cube_face_frusta_share_planes_and_what_sharing_would_buy():
+    """VERDICT r01 item 4(ii) asked whether plane evaluations can be shared between the frusta of one call.  Facts this test pins
+    for the benchmark's six cube-face frusta (camera.cube_frusta): the 24 side planes are 6 unoriented planes — every side
+    plane is bit-identical to a side plane of one other face and the negation (up to the sign of zero components) of the
+    side planes of two more.  Sharing is exact: for the negated plane the reference's s is -(n·p) + d' (rounding is symmetric
+    under negation), so "all corners behind" is  d' - min_corner(n·p) <= 0  with min_corner built per axis like the max-corner.
+    The kernels do NOT use it — the per-frustum form is already 14 instructions per plane PAIR (packed f32x2) with a warp-vote
+    early exit after the first rejecting pair; a shared form needs 11 instructions per unoriented normal plus 2 per plane
+    (9 * 11 + 36 * 2 = 171 per box against at most 3 * 14 * 6 = 252, typically ~150 with the early exits), and loses the early
+    exit.  See profiles/README.md."""
+    from fyrox_b200 import camera
+    fr = camera.cube_frusta()
+    P = np.array([np.ctypeslib.as_array(f.planes) for f in fr], f32).reshape(36, 4)
+    u32 = lambda v: np.ascontiguousarray(v, f32).view(np.uint32)
+    canon = lambda v: np.where(v == 0, f32(0.0), v)  # +0 for both zeros
+    ident = neg = 0
+    for i in range(36):
+        for j in range(i + 1, 36):
+            if i // 6 == j // 6:
+                continue
+            ident += bool((u32(P[i]) == u32(P[j])).all())
+            neg += bool((u32(canon(P[i][:3])) == u32(canon(-P[j][:3]))).all())
+    assert ident == 12 and neg >= 24, (ident, neg)
+    # exactness of the shared form on the negated plane, random + adversarial cases
+    rng = np.random.default_rng(5)
+    with np.errstate(over="ignore", under="ignore", invalid="ignore"):
+        for mode in ("random", "scaled", "special"):
+            n, d, lo, hi = make_cases(rng, 500_000, mode)
+            want = literal_all_behind(-n, d, lo, hi)
+            # min-corner of +n: operand picked the other way round
+            vx = np.where(n[:, 0] < 0, hi[:, 0], lo[:, 0])
+            vy = np.where(n[:, 1] < 0, hi[:, 1], lo[:, 1])
+            vz = np.where(n[:, 2] < 0, hi[:, 2], lo[:, 2])
+            s_min = (n[:, 0] * vx + n[:, 1] * vy) + n[:, 2] * vz
+            got = (-s_min + d) <= 0
+            assert np.array_equal(got, want), (mode, int((got != want).sum()))
