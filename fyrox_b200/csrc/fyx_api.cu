@@ -2,6 +2,7 @@
 // (slot ordering by hierarchy depth, staging, surface tables) and stream-ordered kernel launches.
 // No CPU fallback exists: every compute entry point launches the sm_100a kernels of fyx_kernels.cu.
 #include <algorithm>
+#include <limits>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -436,6 +437,24 @@ void to_dev_frustum(const fyx_frustum &f, uint32_t cam_mask, uint32_t pass_flags
     d.pass_flags = pass_flags;
     for (int p = 0; p < 6; ++p)
         for (int k = 0; k < 3; ++k) d.vsel[p >> 1][k][p & 1] = (f.planes[p][k] < 0.0f) ? 0x3210u : 0x7654u;
+    // smallest plane value over the frustum's own corners, one rounding per operation in the kernels' order (the volatile
+    // temporaries keep the host compiler from contracting anything)
+    for (int p = 0; p < 6; ++p) {
+        float m = std::numeric_limits<float>::infinity();
+        for (int i = 0; i < 8; ++i) {
+            volatile float a = f.planes[p][0] * f.corners[i][0];
+            volatile float b = f.planes[p][1] * f.corners[i][1];
+            volatile float ab = a + b;
+            volatile float e = f.planes[p][2] * f.corners[i][2];
+            volatile float abe = ab + e;
+            volatile float sv = abe + f.planes[p][3];
+            const float v = sv;
+            if (std::isnan(v) || std::isnan(m)) m = std::nanf("");
+            else if (v < m) m = v;
+        }
+        if (p & 1) d.pm[p >> 1].y = m;
+        else d.pm[p >> 1].x = m;
+    }
 }
 
 int32_t prepare_cull(fyx_ctx *c, uint32_t nf, const fyx_frustum *fr, const uint32_t *cam_mask, const uint32_t *pass_flags)
@@ -450,8 +469,12 @@ int32_t prepare_cull(fyx_ctx *c, uint32_t nf, const fyx_frustum *fr, const uint3
     c->cp.counts = V.d_counts;
     c->cp.one = 1.0f;
     c->cp.negzero = -0.0f;
+    c->cp.shadow_bits = 0u;
+    c->cp.cam_same = 1u;
     for (uint32_t f = 0; f < nf; ++f) {
         to_dev_frustum(fr[f], cam_mask ? cam_mask[f] : 0xFFFFFFFFu, pass_flags ? pass_flags[f] : 0u, c->cp.f[f]);
+        if (c->cp.f[f].pass_flags & FYX_PASS_SHADOW) c->cp.shadow_bits |= 1u << f;
+        if (c->cp.f[f].cam_mask != c->cp.f[0].cam_mask) c->cp.cam_same = 0u;
         // worst case every alive node is visible (fyx_set_flags may turn any of them renderable)
         int32_t rc = dev_ensure(c, V.b_vis[f], sizeof(uint32_t) * std::max<size_t>(c->n_slots, 1));
         if (rc) return rc;

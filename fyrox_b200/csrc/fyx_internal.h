@@ -45,6 +45,8 @@ struct CullParams {
     uint32_t *out_slot[FYX_MAX_FRUSTA]; // the same entries as HBM slots (nullptr unless fyx_enable_instances)
     uint32_t *counts;              // counts[f * kCountStride]
     float one, negzero;            // 1.0f, -0.0f: run-time operands of the unfusable packed FMAs (fyx_math.cuh)
+    uint32_t shadow_bits;          // bit f: frustum f is a shadow pass (FYX_PASS_SHADOW)
+    uint32_t cam_same;             // non-zero: every frustum of the call has the same camera render mask (f[0].cam_mask)
 };
 
 struct SkinArrays {

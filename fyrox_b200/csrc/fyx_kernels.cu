@@ -232,6 +232,113 @@ __device__ __forceinline__ uint32_t cull_warp(const bool cand, const uint32_t nf
 }
 
 // ------------------------------------------------------------------------------------------------
+// The same predicate in warp-convergent form (VAR bit 5), called by all 32 lanes.  The per-lane form above runs the
+// geometric test inside `if (ok && culling)`: every frustum costs a divergence region (BSSY/BSYNC, an activemask per
+// vote) and ~12 instructions of mask / pass / flag tests.  Here
+//   * the cheap tests produce one bit mask of eligible frusta per lane (per call: shadow passes as a bit mask, the
+//     camera masks compared once when they are all equal);
+//   * the plane tests of frustum f run for the WHOLE warp whenever some lane needs them (the other lanes' values are
+//     ignored: same issue slots either way), so every vote uses the full mask and every branch is warp-uniform;
+//   * the corner-in-box fallback runs only for lanes a plane rejected without the margin of `pm` (fyx_math.cuh).
+// Lanes whose box is not tame (never in practice) take the literal per-lane test.  Same booleans as cull_bits.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool corner_in_box(const FrustumDev &f, const float2 x, const float2 y, const float2 z)
+{
+    uint32_t alive = 0xFFu;
+    const float2 box[3] = {x, y, z};
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        const float lo = box[a].x, hi = box[a].y;
+        const float4 v0 = f.ax_val[a][0];
+        uint32_t m = 0u;
+        m |= ((v0.x >= lo) & (v0.x <= hi)) ? f.ax_mask[a][0] : 0u;
+        m |= ((v0.y >= lo) & (v0.y <= hi)) ? f.ax_mask[a][1] : 0u;
+        m |= ((v0.z >= lo) & (v0.z <= hi)) ? f.ax_mask[a][2] : 0u;
+        m |= ((v0.w >= lo) & (v0.w <= hi)) ? f.ax_mask[a][3] : 0u;
+        if (((f.n_ax >> (8 * a)) & 0xFFu) > 4u) {
+            const float4 v1 = f.ax_val[a][1];
+            m |= ((v1.x >= lo) & (v1.x <= hi)) ? f.ax_mask[a][4] : 0u;
+            m |= ((v1.y >= lo) & (v1.y <= hi)) ? f.ax_mask[a][5] : 0u;
+            m |= ((v1.z >= lo) & (v1.z <= hi)) ? f.ax_mask[a][6] : 0u;
+            m |= ((v1.w >= lo) & (v1.w <= hi)) ? f.ax_mask[a][7] : 0u;
+        }
+        alive &= m;
+    }
+    return alive != 0u;
+}
+
+template <int NFT>
+__device__ __forceinline__ uint32_t cull_warp_conv(const bool cand, const uint32_t nf, const uint32_t mask, const float2 wx, const float2 wy,
+                                                   const float2 wz, const CullParams &cp)
+{
+    constexpr uint32_t kFull = 0xFFFFFFFFu;
+    PackedConsts kc;
+    kc.one = make_float2(cp.one, cp.one);
+    kc.negzero = make_float2(cp.negzero, cp.negzero);
+    const int nfr = (NFT > 0) ? NFT : cp.nf;
+    const uint32_t all = (nfr >= 32) ? kFull : ((1u << nfr) - 1u);
+    const bool ok = cand && (nf & kNeedBits) == kNeedBits;
+    // eligible frusta of this lane: render mask ∩ camera mask, shadow passes only for shadow casters
+    uint32_t elig;
+    if (cp.cam_same) {
+        elig = (mask & cp.f[0].cam_mask) ? all : 0u;
+    } else {
+        elig = 0u;
+        if (NFT > 0) {
+#pragma unroll
+            for (int f = 0; f < NFT; ++f) elig |= (mask & cp.f[f].cam_mask) ? (1u << f) : 0u;
+        } else {
+            for (int f = 0; f < nfr; ++f) elig |= (mask & cp.f[f].cam_mask) ? (1u << f) : 0u;
+        }
+    }
+    if (!(nf & FYX_NODE_CAST_SHADOWS)) elig &= ~cp.shadow_bits;
+    if (!ok) elig = 0u;
+    const bool geo = (nf & FYX_NODE_FRUSTUM_CULLING) != 0u;
+    uint32_t want = geo ? elig : 0u; // frusta whose geometric test this lane needs
+    if (!__any_sync(kFull, want != 0u)) return elig;
+    uint32_t bits = geo ? 0u : elig;
+    const bool tame = aabb_is_tame(wx, wy, wz);
+    if (__any_sync(kFull, want != 0u && !tame)) { // literal per-lane path for boxes outside the max-corner form's premise
+        if (want != 0u && !tame) {
+            for (int f = 0; f < nfr; ++f)
+                if (((want >> f) & 1u) && frustum_intersects_aabb(cp.f[f], wx, wy, wz, kc, false)) bits |= 1u << f;
+            want = 0u;
+        }
+    }
+    const uint32_t xl = __float_as_uint(wx.x), xh = __float_as_uint(wx.y), yl = __float_as_uint(wy.x), yh = __float_as_uint(wy.y),
+                   zl = __float_as_uint(wz.x), zh = __float_as_uint(wz.y);
+    auto one = [&](const int f) {
+        const bool act = ((want >> f) & 1u) != 0u;
+        if (!__any_sync(kFull, act)) return;
+        const FrustumDev &F = cp.f[f];
+        bool cloud = act, strong = false;
+#pragma unroll
+        for (int q = 0; q < 3; ++q) {
+            const float2 vx = make_float2(pick(xl, xh, F.vsel[q][0][0]), pick(xl, xh, F.vsel[q][0][1]));
+            const float2 vy = make_float2(pick(yl, yh, F.vsel[q][1][0]), pick(yl, yh, F.vsel[q][1][1]));
+            const float2 vz = make_float2(pick(zl, zh, F.vsel[q][2][0]), pick(zl, zh, F.vsel[q][2][1]));
+            const float2 s = add2(add2(add2(mul2(F.pn[q][0], vx, kc), mul2(F.pn[q][1], vy, kc), kc), mul2(F.pn[q][2], vz, kc), kc), F.pn[q][3], kc);
+            cloud &= !(s.x <= 0.0f) & !(s.y <= 0.0f);
+            strong |= (s.x < F.pm[q].x) | (s.y < F.pm[q].y);
+            if (q < 2 && !__any_sync(kFull, cloud)) break; // every lane that wanted this frustum is rejected already
+        }
+        bool res = cloud;
+        const bool fb = act && !cloud && !strong; // rejected by a plane it (nearly) touches: the reference's corner loop decides
+        if (__any_sync(kFull, fb)) {
+            if (fb) res = corner_in_box(F, wx, wy, wz);
+        }
+        bits |= res ? (1u << f) : 0u;
+    };
+    if (NFT > 0) {
+#pragma unroll
+        for (int f = 0; f < NFT; ++f) one(f);
+    } else {
+        for (int f = 0; f < nfr; ++f) one(f);
+    }
+    return bits;
+}
+
+// ------------------------------------------------------------------------------------------------
 // Compaction of the visible node indices.  Replaces the Vec pushes of RenderDataBundleStorage::push
 // (renderer/bundle.rs:1248-1278).  Order inside a list is unspecified.  Two forms:
 //  * CTA-wide: warp ballot + popc rank, per-warp counts in shared memory, one atomicAdd per (CTA, frustum);
@@ -388,7 +495,7 @@ __device__ __forceinline__ void update_node(const NodeArrays &a, const uint32_t 
 // VAR: bit 0 = warp-level pre-reject of whole frusta, bit 1 = warp-wide compaction (else CTA-wide), bit 2 = FYX_UPDATE_ALL
 // specialisation (own columns, render mask and list index loaded up front)
 // bit 4 = compiled for 8 resident CTAs per SM (<= 32 registers: the 40 the kernel wants limit it to 48 of 64 warps, and it is
-// latency-bound)
+// latency-bound); bit 5 = warp-convergent predicate (cull_warp_conv; replaces bit 0)
 template <int NFT, int VAR>
 __global__ void __launch_bounds__(kBlock, (VAR & 16) ? 8 : 6) k_update_level(const NodeArrays a, const uint32_t lo, const uint32_t hi,
                                                          const uint32_t update_all, const CullParams cp)
@@ -416,7 +523,8 @@ __global__ void __launch_bounds__(kBlock, (VAR & 16) ? 8 : 6) k_update_level(con
     if (NFT >= 0) {
         const bool cand = valid && !(nf & F_SKINNED);
         if (!UA) mask = cand ? a.mask[slot] : 0u;
-        const uint32_t vis_bits = cull_warp<(NFT > 0 ? NFT : 0), PRE>(cand, nf, mask, wx, wy, wz, cp, T);
+        const uint32_t vis_bits = (VAR & 32) ? cull_warp_conv<(NFT > 0 ? NFT : 0)>(cand, nf, mask, wx, wy, wz, cp)
+                                             : cull_warp<(NFT > 0 ? NFT : 0), PRE>(cand, nf, mask, wx, wy, wz, cp, T);
         if (VAR & 8) { // deferred compaction: one byte per node now, the lists are built by k_compact_vis after the last level
             if (valid) a.vis[slot] = (uint8_t)vis_bits;
             return;
@@ -636,7 +744,7 @@ __global__ void __launch_bounds__(kBlock) k_cull(const NodeArrays a, const CullP
         wy = ld_stream(a.wa[1] + slot);
         wz = ld_stream(a.wa[2] + slot);
     }
-    uint32_t vis_bits = cull_warp<NFT, PRE>(valid, nf, mask, wx, wy, wz, cp, T);
+    uint32_t vis_bits = (VAR & 32) ? cull_warp_conv<NFT>(valid, nf, mask, wx, wy, wz, cp) : cull_warp<NFT, PRE>(valid, nf, mask, wx, wy, wz, cp, T);
     uint32_t hidden = 0u;
     if (valid && (lodp || prune)) {
         if (lodp) hidden = lodp[slot]; // frusta whose LOD filter hides the node or one of its ancestors
@@ -1464,7 +1572,7 @@ static int cull_variant(int nf)
 {
     static int forced = [] {
         const char *e = getenv("FYX_CULL_VARIANT");
-        return (e && *e) ? atoi(e) & 31 : -1;
+        return (e && *e) ? atoi(e) & 63 : -1;
     }();
     if (forced >= 0) return forced;
     (void)nf;
@@ -1490,7 +1598,13 @@ bool cull_defers_compaction(int nf) { return (cull_variant(nf) & 8) != 0; }
     case 13: launch_pdl(KERNEL<NF, 13>, __VA_ARGS__); break;                     \
     case 20: launch_pdl(KERNEL<NF, 20>, __VA_ARGS__); break;                     \
     case 21: launch_pdl(KERNEL<NF, 21>, __VA_ARGS__); break;                     \
-    default: launch_pdl(KERNEL<NF, 28>, __VA_ARGS__); break;                     \
+    case 28: launch_pdl(KERNEL<NF, 28>, __VA_ARGS__); break;                     \
+    case 32: launch_pdl(KERNEL<NF, 32>, __VA_ARGS__); break;                     \
+    case 34: launch_pdl(KERNEL<NF, 34>, __VA_ARGS__); break;                     \
+    case 36: launch_pdl(KERNEL<NF, 36>, __VA_ARGS__); break;                     \
+    case 38: launch_pdl(KERNEL<NF, 38>, __VA_ARGS__); break;                     \
+    case 52: launch_pdl(KERNEL<NF, 52>, __VA_ARGS__); break;                     \
+    default: launch_pdl(KERNEL<NF, 54>, __VA_ARGS__); break;                     \
     }
 
 void launch_update_level(cudaStream_t s, const NodeArrays &a, uint32_t lo, uint32_t hi, bool update_all, const CullParams *cull)
@@ -1503,6 +1617,8 @@ void launch_update_level(cudaStream_t s, const NodeArrays &a, uint32_t lo, uint3
         if (cull_variant(cull->nf) & 8) var = (var & 5) | 8; // deferred compaction: 8, 9, 12, 13
         if ((cull_variant(cull->nf) & 16) && update_all) // 32-register builds: 20 (= 4 | 16), 21 (+ pre-reject), 28 (= 12 | 16)
             var = (cull_variant(cull->nf) & 8) ? 28 : ((cull_variant(cull->nf) & 1) ? 21 : 20);
+        if (cull_variant(cull->nf) & 32) // warp-convergent predicate: 32, 34 (+ warp compaction); FYX_UPDATE_ALL: 36, 38, 52, 54
+            var = 32 | (cull_variant(cull->nf) & 2) | (update_all ? ((cull_variant(cull->nf) & 16) ? 20 : (cull_variant(cull->nf) & 4)) : 0);
         switch (cull->nf) { // the usual frustum counts get an unrolled cull: camera, CSM cascades, cube faces
         case 1: FYX_DISPATCH_VAR(k_update_level, 1, var, g, kBlock, 0, s, a, lo, hi, ua, *cull); break;
         case 2: FYX_DISPATCH_VAR(k_update_level, 2, var, g, kBlock, 0, s, a, lo, hi, ua, *cull); break;
@@ -1586,7 +1702,9 @@ template <int NF> static void launch_cull_t(cudaStream_t s, unsigned g, int var,
     case 0: k_cull<NF, 0><<<g, kBlock, 0, s>>>(a, cp, lodp, lo, hi, prune); break;
     case 1: k_cull<NF, 1><<<g, kBlock, 0, s>>>(a, cp, lodp, lo, hi, prune); break;
     case 2: k_cull<NF, 2><<<g, kBlock, 0, s>>>(a, cp, lodp, lo, hi, prune); break;
-    default: k_cull<NF, 3><<<g, kBlock, 0, s>>>(a, cp, lodp, lo, hi, prune); break;
+    case 3: k_cull<NF, 3><<<g, kBlock, 0, s>>>(a, cp, lodp, lo, hi, prune); break;
+    case 32: k_cull<NF, 32><<<g, kBlock, 0, s>>>(a, cp, lodp, lo, hi, prune); break;
+    default: k_cull<NF, 34><<<g, kBlock, 0, s>>>(a, cp, lodp, lo, hi, prune); break;
     }
 }
 
@@ -1594,7 +1712,7 @@ void launch_cull_range(cudaStream_t s, const NodeArrays &a, const CullParams &cp
 {
     if (hi <= lo) return;
     const unsigned g = grid_for(hi - lo);
-    const int var = cull_variant(cp.nf) & 3;
+    const int var = (cull_variant(cp.nf) & 32) ? (32 | (cull_variant(cp.nf) & 2)) : (cull_variant(cp.nf) & 3);
     switch (cp.nf) {
     case 1: launch_cull_t<1>(s, g, var, a, cp, lodp, lo, hi, prune); break;
     case 2: launch_cull_t<2>(s, g, var, a, cp, lodp, lo, hi, prune); break;

@@ -106,6 +106,10 @@ struct FrustumDev {
     float4 ax_val[3][2];
     uint32_t ax_mask[3][8]; // per distinct coordinate: the 8-bit mask of the frustum corners that have it
     float4 corner[8];       // the corners themselves (frustum.rs:70-79 order), for the warp-level pre-reject
+    // pm[q] = for planes (2q, 2q+1): the smallest s = ((nx*cx + ny*cy) + nz*cz) + d over the frustum's OWN eight corners,
+    // evaluated on the host in exactly the kernels' arithmetic (NaN if any of them is NaN).  A box whose max-corner s on a
+    // plane is below it cannot contain a frustum corner (see frustum_intersects_aabb): the fallback is skipped.
+    float2 pm[3];
 };
 
 // Frustum::is_intersects_aabb (fyrox-math/src/frustum.rs:222-245) on (min,max) pairs per axis.
@@ -135,7 +139,7 @@ __device__ __forceinline__ float pick(const uint32_t lo, const uint32_t hi, cons
 __device__ __forceinline__ bool frustum_intersects_aabb(const FrustumDev &f, const float2 x, const float2 y,
                                                         const float2 z, const PackedConsts &kc, const bool tame)
 {
-    bool cloud = true;
+    bool cloud = true, strong = false;
     if (tame) {
         // n*p is monotone in p (rounding is monotone), so max(fl(n*min), fl(n*max)) is fl(n*max) for n >= 0
         // and fl(n*min) for n < 0: pick the operand first (vsel, built on the host) and multiply once.
@@ -150,6 +154,7 @@ __device__ __forceinline__ bool frustum_intersects_aabb(const FrustumDev &f, con
             const float2 vz = make_float2(pick(zl, zh, f.vsel[q][2][0]), pick(zl, zh, f.vsel[q][2][1]));
             const float2 s = add2(add2(add2(mul2(f.pn[q][0], vx, kc), mul2(f.pn[q][1], vy, kc), kc), mul2(f.pn[q][2], vz, kc), kc), f.pn[q][3], kc);
             cloud &= !(s.x <= 0.0f) & !(s.y <= 0.0f);
+            strong |= (s.x < f.pm[q].x) | (s.y < f.pm[q].y);
             // siblings sit in adjacent slots, so a warp's boxes are usually cut off by the same plane: once every
             // lane here is rejected the remaining planes cannot change anything (a lane's own result never depends
             // on the vote: it only ever skips tests whose outcome is already fixed)
@@ -173,6 +178,13 @@ __device__ __forceinline__ bool frustum_intersects_aabb(const FrustumDev &f, con
         }
     }
     if (cloud) return true;
+    // A frustum corner c inside the box (min <= c <= max on every axis) has, on every plane, s(c) <= s(max-corner of the box):
+    // the per-axis products are monotone in the operand and the sums are monotone under round-to-nearest, in the very order
+    // both are evaluated.  So a box whose max-corner s is BELOW the smallest s of the frustum's own corners on some plane
+    // (pm, host-computed with the same operations) holds none of them: the fallback below would say false — skip it.
+    // Only boxes that touch a plane within the rounding slack of the corners (|pm| ~ 1e-6 of the scene's size) go on.
+    // CPU check of the claim: tests/test_cull_trick_cpu.py::test_strong_reject_skips_the_corner_fallback_exactly.
+    if (strong) return false;
     // Fallback: any frustum corner inside the AABB, inclusive compares (aabb.rs:193-200):
     //   exists c: min <= corner_c <= max on all three axes.
     // Evaluated as three 8-bit corner masks (one per axis, built from the DISTINCT corner coordinates of

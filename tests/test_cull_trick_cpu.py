@@ -204,3 +204,66 @@ def test_cube_face_frusta_share_planes_and_what_sharing_would_buy():
             s_min = (n[:, 0] * vx + n[:, 1] * vy) + n[:, 2] * vz
             got = (-s_min + d) <= 0
             assert np.array_equal(got, want), (mode, int((got != want).sum()))
+
+
+def test_strong_reject_skips_the_corner_fallback_exactly():
+    """frustum_intersects_aabb (fyx_math.cuh) skips the corner-in-box fallback of Frustum::is_intersects_aabb (frustum.rs:236-242)
+    when, on some plane, the box's max-corner value s is BELOW pm = the smallest s over the frustum's own eight corners (computed
+    by the host with the same operations).  Claim: then no frustum corner lies inside the box, so the fallback is false.  Checked
+    on real frusta (their corners sit on the planes up to rounding: pm is a few ulps around zero — the touching cases are the
+    point) and on arbitrary plane / corner sets, with boxes snapped onto corners and planes."""
+    from fyrox_b200 import camera
+    rng = np.random.default_rng(31)
+    real = []
+    for f in camera.cube_frusta((1.5, -2.0, 0.25), 300.0):
+        real.append((np.ctypeslib.as_array(f.planes).astype(f32).reshape(6, 4), np.ctypeslib.as_array(f.corners).astype(f32).reshape(8, 3)))
+    skipped = inside_total = weak = 0
+    with np.errstate(over="ignore", under="ignore", invalid="ignore"):
+        for trial in range(40):
+            if trial < 24:
+                P, corners = real[trial % 6]
+                n, d = P[:, :3].copy(), P[:, 3].copy()
+            elif trial < 32:
+                n = rng.normal(size=(6, 3)).astype(f32)
+                d = (rng.normal(size=6) * 30).astype(f32)
+                corners = (rng.normal(size=(8, 3)) * 40).astype(f32)
+            else:
+                n = special_values(rng, 18).reshape(6, 3)
+                d = special_values(rng, 6)
+                corners = special_values(rng, 24).reshape(8, 3)
+            m = 200_000
+            # boxes: around the corners (tiny to large), some bounds exactly ON corner coordinates
+            base = corners[rng.integers(0, 8, m)]
+            ext = (10.0 ** rng.uniform(-7, 2, (m, 1))).astype(f32)
+            a = base + (rng.normal(size=(m, 3)).astype(f32) * ext)
+            b = base + (rng.normal(size=(m, 3)).astype(f32) * ext)
+            snap = rng.random((m, 3)) < 0.25
+            a = np.where(snap, corners[rng.integers(0, 8, m)], a)
+            if trial >= 32:
+                sv = special_values(rng, m * 3).reshape(m, 3)
+                b = np.where(rng.random((m, 3)) < 0.4, sv, b)
+            lo, hi = np.minimum(a, b), np.maximum(a, b)
+            # pm per plane, same arithmetic
+            pm = np.empty(6, f32)
+            for p in range(6):
+                sv_ = ((n[p, 0] * corners[:, 0] + n[p, 1] * corners[:, 1]) + n[p, 2] * corners[:, 2]) + d[p]
+                pm[p] = np.nan if np.isnan(sv_).any() else sv_.min()
+            strong = np.zeros(m, bool)
+            rejected = np.zeros(m, bool)
+            for p in range(6):
+                npl = np.broadcast_to(n[p], (m, 3))
+                vx = np.where(npl[:, 0] < 0, lo[:, 0], hi[:, 0])
+                vy = np.where(npl[:, 1] < 0, lo[:, 1], hi[:, 1])
+                vz = np.where(npl[:, 2] < 0, lo[:, 2], hi[:, 2])
+                s = s_of(npl, np.full(m, d[p], f32), vx, vy, vz)
+                strong |= s < pm[p]
+                rejected |= s <= 0
+            inside = np.zeros(m, bool)
+            for c in range(8):
+                inside |= ((corners[c] >= lo) & (corners[c] <= hi)).all(1)
+            bad = strong & inside
+            assert not bad.any(), (trial, int(bad.sum()), lo[bad][:2], hi[bad][:2])
+            skipped += int((strong & rejected).sum())
+            weak += int((rejected & ~strong).sum())
+            inside_total += int(inside.sum())
+    assert skipped > 100_000 and inside_total > 100_000 and weak > 1000, (skipped, inside_total, weak)
