@@ -24,7 +24,7 @@ def _run(env, tests, k):
 @pytest.mark.parametrize("variant", ["0", "3", "13", "20", "34", "52"])
 def test_cull_variants_match_the_oracle(variant):
     """bit 0: warp-union pre-reject of whole frusta, bit 1: warp-wide compaction, bit 2: FYX_UPDATE_ALL specialisation, bit 3: deferred compaction (k_compact_vis), bit 4: 32-register build, bit 5: warp-convergent predicate
-    (fyx_kernels.cu; the default is 4).  Four variants exercise every bit; the others differ only in combinations."""
+    (fyx_kernels.cu; the default is 20).  Four variants exercise every bit; the others differ only in combinations."""
     _run({"FYX_CULL_VARIANT": variant}, ["test_gpu_parity.py", "test_gpu_drawprep.py"],
          "cull or render_prep or pipelined or k7 or lod or light or instances or bundle")
 
