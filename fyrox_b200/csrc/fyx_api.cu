@@ -150,6 +150,8 @@ struct fyx_ctx {
     // frame pipelining (FYX_FRAME_ASYNC): uploads on their own stream into alternating staging buffers,
     // read-backs on a third stream
     cudaStream_t copy_stream = nullptr, d2h_stream = nullptr;
+    cudaStream_t fold_stream = nullptr; // skinned-mesh fold + cull beside the palette / skinning kernels of asynchronous frames
+    cudaEvent_t ev_levels_done = nullptr, ev_fold_done = nullptr;
     DevBuf d_stage_frame[2];
     cudaEvent_t ev_upload[2] = {}, ev_slot_free[2] = {};
     bool slot_used[2] = {false, false};
@@ -499,7 +501,10 @@ int32_t prepare_cull(fyx_ctx *c, uint32_t nf, const fyx_frustum *fr, const uint3
 }
 
 // Hierarchy + boxes (+ fused cull): one launch per level (parents first), then the skinned-mesh fold.
-int32_t run_update(fyx_ctx *c, uint32_t update_flags, const CullParams *cull)
+// fold_on: stream for the skinned-mesh fold (+ cull of the skinned meshes); nullptr = the main stream, in order.  Another stream
+// is given by asynchronous frames that go on to the palette / skinning kernels: those need the bones' matrices, not the meshes'
+// boxes, so the (latency-bound) fold runs beside them; the caller joins the streams.
+int32_t run_update(fyx_ctx *c, uint32_t update_flags, const CullParams *cull, cudaStream_t fold_on = nullptr)
 {
     const bool all = (update_flags & FYX_UPDATE_ALL) || !c->updated_once;
     const size_t nl = c->level_off.size() ? c->level_off.size() - 1 : 0;
@@ -521,8 +526,13 @@ int32_t run_update(fyx_ctx *c, uint32_t update_flags, const CullParams *cull)
         c->launches++;
     }
     if (c->fold.n) {
-        launch_fold_bones(c->stream, c->a, c->fold, cull);
+        if (fold_on) {
+            CU(cudaEventRecord(c->ev_levels_done, c->stream));
+            CU(cudaStreamWaitEvent(fold_on, c->ev_levels_done, 0));
+        }
+        launch_fold_bones(fold_on ? fold_on : c->stream, c->a, c->fold, cull);
         c->launches++;
+        if (fold_on) CU(cudaEventRecord(c->ev_fold_done, fold_on));
     }
     c->updated_once = true;
     CU(cudaGetLastError());
@@ -656,6 +666,9 @@ extern "C" int32_t fyx_create(const fyx_config *cfg, fyx_ctx **out_ctx)
     }
     CUB(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
     CUB(cudaStreamCreateWithFlags(&c->d2h_stream, cudaStreamNonBlocking));
+    CUB(cudaStreamCreateWithFlags(&c->fold_stream, cudaStreamNonBlocking));
+    CUB(cudaEventCreateWithFlags(&c->ev_levels_done, cudaEventDisableTiming));
+    CUB(cudaEventCreateWithFlags(&c->ev_fold_done, cudaEventDisableTiming));
     for (int i = 0; i < 2; ++i) {
         CUB(cudaEventCreateWithFlags(&c->ev_upload[i], cudaEventDisableTiming));
         CUB(cudaEventCreateWithFlags(&c->ev_slot_free[i], cudaEventDisableTiming));
@@ -701,6 +714,7 @@ extern "C" void fyx_destroy(fyx_ctx *c)
     }
     if (c->copy_stream) cudaStreamSynchronize(c->copy_stream);
     if (c->d2h_stream) cudaStreamSynchronize(c->d2h_stream);
+    if (c->fold_stream) cudaStreamSynchronize(c->fold_stream);
     for (VisSlot &V : c->vs) {
         for (uint32_t f = 0; f < FYX_MAX_FRUSTA; ++f) {
             dev_free(V.b_vis[f]);
@@ -724,6 +738,9 @@ extern "C" void fyx_destroy(fyx_ctx *c)
     }
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     if (c->d2h_stream) cudaStreamDestroy(c->d2h_stream);
+    if (c->fold_stream) cudaStreamDestroy(c->fold_stream);
+    if (c->ev_levels_done) cudaEventDestroy(c->ev_levels_done);
+    if (c->ev_fold_done) cudaEventDestroy(c->ev_fold_done);
     for (int i = 0; i < 2; ++i) {
         if (c->ev_gath_read[i]) cudaEventDestroy(c->ev_gath_read[i]);
         if (c->ev_x0[i]) cudaEventDestroy(c->ev_x0[i]);
@@ -1779,6 +1796,7 @@ extern "C" int32_t fyx_render_prep(fyx_ctx *c, const fyx_frame_desc *fr)
     const bool stage_events = !async;
     c->stage_events_valid = stage_events;
     const bool pipelined = async && fr->readback_visible && fr->n_frusta; // read-back deferred to fyx_frame_wait
+    bool side_fold = false;
     // 1. changed local matrices.  Pinned caller memory is DMA'd in place (the caller keeps it untouched until
     //    the frame is synchronised / waited for).  Async frames upload on the copy stream into alternating
     //    staging buffers, so the H2D of frame i+1 overlaps the kernels of frame i.
@@ -1849,14 +1867,20 @@ extern "C" int32_t fyx_render_prep(fyx_ctx *c, const fyx_frame_desc *fr)
     }
     {
         const bool unf = unfused_cull(c, fr->n_frusta);
-        rc = run_update(c, fr->update_flags, (fr->n_frusta && !unf) ? &c->cp : nullptr);
+        static const bool side_fold_allowed = [] {
+            const char *e = getenv("FYX_SIDE_FOLD"); // 0: the fold always runs in order on the main stream (A/B measurements)
+            return !(e && *e == '0');
+        }();
+        side_fold = side_fold_allowed && async && !unf && c->fold.n && fr->do_skin && c->n_tiles;
+        rc = run_update(c, fr->update_flags, (fr->n_frusta && !unf) ? &c->cp : nullptr, side_fold ? c->fold_stream : nullptr);
         if (rc) return rc;
         if (unf && (rc = cull_unfused(c, fr->n_frusta))) return rc;
     }
     if (stage_events) CU(cudaEventRecord(c->ev[EV_UPDATE], s));
     c->ev_levels_prev = nullptr;
     if (fr->n_frusta && (async || (fr->flags & FYX_FRAME_ALLGATHER))) {
-        CU(cudaEventRecord(c->vs[c->cur].ev_cull, s)); // consumed by the read-back / collective streams and by the next frame's scatter
+        // consumed by the read-back / collective streams and by the next frame's scatter: the lists are complete after the fold
+        CU(cudaEventRecord(c->vs[c->cur].ev_cull, side_fold ? c->fold_stream : s));
         c->ev_levels_prev = c->vs[c->cur].ev_cull;
     }
     // multi-GPU: the visible lists are complete here; their all-gather runs on the collective stream beside
@@ -1882,6 +1906,7 @@ extern "C" int32_t fyx_render_prep(fyx_ctx *c, const fyx_frame_desc *fr)
     }
     if (stage_events) CU(cudaEventRecord(c->ev[EV_SKIN], s));
     CU(cudaGetLastError());
+    if (side_fold) CU(cudaStreamWaitEvent(s, c->ev_fold_done, 0)); // join: whatever follows on the main stream sees the folded boxes and the complete lists
     if (gather) {
         // the host waits only for the cull + the counts (the skinning kernel keeps running), then enqueues the payload
         rc = allgather_finish(c, c->vs[c->cur], c->comm_stream);

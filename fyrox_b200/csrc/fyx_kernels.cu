@@ -802,77 +802,110 @@ __device__ __forceinline__ void fold_max(float &v, uint32_t &k, const float ov, 
     if (ov > v || (ov == v && ok < k)) { v = ov; k = ok; }
 }
 
-// one warp = one skinned mesh (i); lane 0 returns the cull result
-template <int NFT>
-__device__ __forceinline__ void fold_mesh(const NodeArrays &a, const FoldArrays &fa, const uint32_t i, const uint32_t lane,
-                                          const CullParams &cp, uint32_t &vis_bits, uint32_t &gi)
+// one warp = one skinned mesh (i): refreshes the world box (all lanes return it) and reads what the cull needs
+// Every table load that does not depend on another one is issued up front (mesh slot, bone range, the first two rounds of
+// bone slots): three dependent memory round trips per mesh (index -> bone slot -> bone matrix) instead of five.
+__device__ __forceinline__ void fold_mesh(const NodeArrays &a, const FoldArrays &fa, const uint32_t i, const uint32_t lane, uint32_t &nf_out,
+                                          float2 &wx, float2 &wy, float2 &wz)
 {
     const uint32_t slot = fa.node_slot[i];
-    const uint32_t nf = a.flags[slot];
-    float2 wx = a.wa[0][slot], wy = a.wa[1][slot], wz = a.wa[2][slot];
-    if (nf & F_DIRTY) {
-        const uint32_t b0 = fa.bone_begin[i], b1 = fa.bone_begin[i + 1];
-        // candidates start as the transformed box (order key 0 = "already there"); bones get keys 1..
-        float mnx = wx.x, mny = wy.x, mnz = wz.x, mxx = wx.y, mxy = wy.y, mxz = wz.y;
-        uint32_t kmnx = 0, kmny = 0, kmnz = 0, kmxx = 0, kmxy = 0, kmxz = 0;
-        for (uint32_t b = b0 + lane; b < b1; b += 32) {
-            const uint32_t bs = fa.bone_slot[b];
-            if (bs == FYX_NONE) continue; // try_borrow failed ⇒ skipped
-            float px, py, pz; // global_position()
-            const uint32_t si = fa.stale_idx ? fa.stale_idx[b] : FYX_NONE;
-            if (si != FYX_NONE) { // visited after the mesh by the reference's DFS: its value from before this update
-                const float4 o = fa.stale_pos[si];
-                px = o.x; py = o.y; pz = o.z;
-            } else {
-                px = a.G[0][bs].w;
-                py = a.G[1][bs].w;
-                pz = a.G[2][bs].w;
-            }
-            const uint32_t key = b - b0 + 1u;
-            // within a lane keys increase, so the strict compares keep the earliest of equal values
-            if (px < mnx) { mnx = px; kmnx = key; }
-            if (py < mny) { mny = py; kmny = key; }
-            if (pz < mnz) { mnz = pz; kmnz = key; }
-            if (px > mxx) { mxx = px; kmxx = key; }
-            if (py > mxy) { mxy = py; kmxy = key; }
-            if (pz > mxz) { mxz = pz; kmxz = key; }
-        }
+    const uint32_t b0 = fa.bone_begin[i], b1 = fa.bone_begin[i + 1];
+    uint32_t bs_pre[2], si_pre[2];
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            fold_min(mnx, kmnx, __shfl_xor_sync(0xFFFFFFFFu, mnx, o), __shfl_xor_sync(0xFFFFFFFFu, kmnx, o));
-            fold_min(mny, kmny, __shfl_xor_sync(0xFFFFFFFFu, mny, o), __shfl_xor_sync(0xFFFFFFFFu, kmny, o));
-            fold_min(mnz, kmnz, __shfl_xor_sync(0xFFFFFFFFu, mnz, o), __shfl_xor_sync(0xFFFFFFFFu, kmnz, o));
-            fold_max(mxx, kmxx, __shfl_xor_sync(0xFFFFFFFFu, mxx, o), __shfl_xor_sync(0xFFFFFFFFu, kmxx, o));
-            fold_max(mxy, kmxy, __shfl_xor_sync(0xFFFFFFFFu, mxy, o), __shfl_xor_sync(0xFFFFFFFFu, kmxy, o));
-            fold_max(mxz, kmxz, __shfl_xor_sync(0xFFFFFFFFu, mxz, o), __shfl_xor_sync(0xFFFFFFFFu, kmxz, o));
-        }
-        wx = make_float2(mnx, mxx);
-        wy = make_float2(mny, mxy);
-        wz = make_float2(mnz, mxz);
-        if (lane == 0) {
-            a.wa[0][slot] = wx;
-            a.wa[1][slot] = wy;
-            a.wa[2][slot] = wz;
-        }
+    for (int r = 0; r < 2; ++r) {
+        const uint32_t b = b0 + lane + 32u * r;
+        bs_pre[r] = (b < b1) ? fa.bone_slot[b] : FYX_NONE;
+        si_pre[r] = (b < b1 && fa.stale_idx) ? fa.stale_idx[b] : FYX_NONE;
     }
-    if ((NFT >= 0) && lane == 0) {
-        PackedConsts kc;
-        kc.one = make_float2(cp.one, cp.one);
-        kc.negzero = make_float2(cp.negzero, cp.negzero);
-        vis_bits = cull_bits<(NFT > 0 ? NFT : 0)>(nf, a.mask[slot], wx, wy, wz, cp, kc, aabb_is_tame(wx, wy, wz), 0xFFFFFFFFu);
-        if (vis_bits) gi = a.gidx[slot];
+    const uint32_t nf = a.flags[slot];
+    nf_out = nf;
+    wx = a.wa[0][slot];
+    wy = a.wa[1][slot];
+    wz = a.wa[2][slot];
+    if (!(nf & F_DIRTY)) return;
+    // candidates start as the transformed box (order key 0 = "already there"); bones get keys 1..
+    float mnx = wx.x, mny = wy.x, mnz = wz.x, mxx = wx.y, mxy = wy.y, mxz = wz.y;
+    uint32_t kmnx = 0, kmny = 0, kmnz = 0, kmxx = 0, kmxy = 0, kmxz = 0;
+    auto add_bone = [&](const uint32_t b, const uint32_t bs, const uint32_t si) {
+        if (bs == FYX_NONE) return; // try_borrow failed ⇒ skipped
+        float px, py, pz; // global_position()
+        if (si != FYX_NONE) { // visited after the mesh by the reference's DFS: its value from before this update
+            const float4 o = fa.stale_pos[si];
+            px = o.x; py = o.y; pz = o.z;
+        } else {
+            px = a.G[0][bs].w;
+            py = a.G[1][bs].w;
+            pz = a.G[2][bs].w;
+        }
+        const uint32_t key = b - b0 + 1u;
+        // within a lane keys increase, so the strict compares keep the earliest of equal values
+        if (px < mnx) { mnx = px; kmnx = key; }
+        if (py < mny) { mny = py; kmny = key; }
+        if (pz < mnz) { mnz = pz; kmnz = key; }
+        if (px > mxx) { mxx = px; kmxx = key; }
+        if (py > mxy) { mxy = py; kmxy = key; }
+        if (pz > mxz) { mxz = pz; kmxz = key; }
+    };
+#pragma unroll
+    for (int r = 0; r < 2; ++r) add_bone(b0 + lane + 32u * r, bs_pre[r], si_pre[r]);
+    for (uint32_t b = b0 + lane + 64u; b < b1; b += 32)
+        add_bone(b, fa.bone_slot[b], fa.stale_idx ? fa.stale_idx[b] : FYX_NONE);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        fold_min(mnx, kmnx, __shfl_xor_sync(0xFFFFFFFFu, mnx, o), __shfl_xor_sync(0xFFFFFFFFu, kmnx, o));
+        fold_min(mny, kmny, __shfl_xor_sync(0xFFFFFFFFu, mny, o), __shfl_xor_sync(0xFFFFFFFFu, kmny, o));
+        fold_min(mnz, kmnz, __shfl_xor_sync(0xFFFFFFFFu, mnz, o), __shfl_xor_sync(0xFFFFFFFFu, kmnz, o));
+        fold_max(mxx, kmxx, __shfl_xor_sync(0xFFFFFFFFu, mxx, o), __shfl_xor_sync(0xFFFFFFFFu, kmxx, o));
+        fold_max(mxy, kmxy, __shfl_xor_sync(0xFFFFFFFFu, mxy, o), __shfl_xor_sync(0xFFFFFFFFu, kmxy, o));
+        fold_max(mxz, kmxz, __shfl_xor_sync(0xFFFFFFFFu, mxz, o), __shfl_xor_sync(0xFFFFFFFFu, kmxz, o));
+    }
+    wx = make_float2(mnx, mxx);
+    wy = make_float2(mny, mxy);
+    wz = make_float2(mnz, mxz);
+    if (lane == 0) {
+        a.wa[0][slot] = wx;
+        a.wa[1][slot] = wy;
+        a.wa[2][slot] = wz;
     }
 }
 
+// One warp per skinned mesh folds the bones; the cull of the CTA's kBlock/32 meshes is then run by the first lanes of warp 0,
+// one mesh per LANE (the multi-frustum predicate is a long dependent chain: run by lane 0 of every warp it cost eight times the
+// issue slots), and warp 0 emits the entries.
 template <int NFT>
 __global__ void __launch_bounds__(kBlock) k_fold_bones(const NodeArrays a, const FoldArrays fa, const CullParams cp)
 {
     pdl_trigger();
     pdl_wait();
-    const uint32_t i = (blockIdx.x * kBlock + threadIdx.x) >> 5; // mesh = warp
-    uint32_t vis_bits = 0u, gi = 0u;
-    if (i < fa.n) fold_mesh<NFT>(a, fa, i, threadIdx.x & 31u, cp, vis_bits, gi);
-    if (NFT >= 0) compact_emit_warp(vis_bits, gi, vis_bits ? fa.node_slot[i] : 0u, cp); // one mesh per warp: lane 0 holds the bits
+    constexpr int kWarps = kBlock / 32;
+    __shared__ float2 s_box[3][kWarps];
+    __shared__ uint32_t s_nf[kWarps];
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+    const uint32_t i = blockIdx.x * kWarps + warp; // mesh = warp
+    uint32_t nf = 0u;
+    float2 wx = make_float2(0.f, 0.f), wy = wx, wz = wx;
+    if (i < fa.n) fold_mesh(a, fa, i, lane, nf, wx, wy, wz);
+    if (NFT < 0) return;
+    if (lane == 0) {
+        s_box[0][warp] = wx;
+        s_box[1][warp] = wy;
+        s_box[2][warp] = wz;
+        s_nf[warp] = (i < fa.n) ? nf : 0u;
+    }
+    __syncthreads();
+    if (warp != 0) return;
+    uint32_t vis_bits = 0u, gi = 0u, slot = 0u;
+    const uint32_t m = blockIdx.x * kWarps + lane; // lane l of warp 0 culls the mesh of warp l
+    if (lane < kWarps && m < fa.n) {
+        PackedConsts kc;
+        kc.one = make_float2(cp.one, cp.one);
+        kc.negzero = make_float2(cp.negzero, cp.negzero);
+        slot = fa.node_slot[m];
+        const float2 bx = s_box[0][lane], by = s_box[1][lane], bz = s_box[2][lane];
+        vis_bits = cull_bits<(NFT > 0 ? NFT : 0)>(s_nf[lane], a.mask[slot], bx, by, bz, cp, kc, aabb_is_tame(bx, by, bz), 0xFFFFFFFFu);
+        if (vis_bits) gi = a.gidx[slot];
+    }
+    compact_emit_warp(vis_bits, gi, slot, cp);
 }
 
 // positions of the "late" bones (see FoldArrays) as stored before the update starts

@@ -43,3 +43,10 @@ def test_subforest_kernel_on_and_off_match_the_oracle(mode):
     both ways over the hierarchy / cull / skinning / animation parity tests (the default picks by level width: on for most
     of the small test scenes, so "1" mostly adds the wide ones)."""
     _run({"FYX_SUBFOREST": mode}, ["test_gpu_parity.py", "test_gpu_anim.py", "test_gpu_drawprep.py"], "not cpp_host and not k6 and not k7")
+
+
+@pytest.mark.timeout(1000)
+def test_fold_in_stream_order_matches_the_oracle():
+    """FYX_SIDE_FOLD=0: asynchronous frames run the skinned-mesh fold in order on the main stream instead of beside the palette /
+    skinning kernels (the default, exercised by every pipelined test of the normal run)."""
+    _run({"FYX_SIDE_FOLD": "0"}, ["test_gpu_parity.py", "test_gpu_fuzz.py"], "pipelined or render_prep or random_call or skin")
