@@ -5,7 +5,8 @@
  * TEST INFRASTRUCTURE ONLY (see fyrox_oracle.h).  Every function cites the reference file:line it follows
  * (paths under /root/reference).  Pinned against the reference's own unit tests of this code:
  * fyrox-math/src/curve.rs test_curve / test_curve_key, fyrox-math/src/lib.rs test_wrapf
- * (tests/test_oracle_kat.py K11-K13).  Animation::tick, track fetch, pose application have no reference tests:
+ * (tests/test_oracle_kat.py K11-K14), and test_quat_from_euler (K15: quat_mul's order reproduces nalgebra's from_euler_angles
+ * bit for bit).  Animation::tick, track fetch, pose application have no reference tests:
  * "parity unpinned", source-following.  nalgebra (absent from the tree, semver 0.35) supplies Vector::lerp,
  * Quaternion lerp / normalize / mul and the 4-component dot; their op orders are restated from its published
  * source and are this file's definition:

@@ -10,8 +10,8 @@
  * file, sources absent from /root/reference) cannot be compiled here (no
  * cargo/rustc).  This restatement follows the reference source line by line
  * (each function cites file:line under /root/reference) and is PINNED against
- * the reference's own unit-test vectors K1..K13 (see
- * tests/test_oracle_kat.py; K11-K13 pin the animation step's curves / wrapf,
+ * the reference's own unit-test vectors K1..K15 (see
+ * tests/test_oracle_kat.py; K11-K15 pin the animation step's curves / wrapf / quaternion product,
  * fyrox_anim_oracle.c).  The functions the reference does not test
  * (calculate_local_transform, bone palette, LBS, Mesh world AABB,
  * should_be_rendered, from_graph, light collection, instance data,

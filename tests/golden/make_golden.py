@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Emit tests/golden/reference_kats.json: the known-answer vectors of the reference's own unit tests
-for the render-prep path (SURVEY.md §8c K1–K10) and of the animation-sampling step before it (K11–K14), transcribed from the cited test sources.
+for the render-prep path (SURVEY.md §8c K1–K10) and of the animation-sampling step before it (K11–K15), transcribed from the cited test sources.
 
 The reference is Rust (no toolchain here), so the vectors cannot be produced by running it.  When
 /root/reference exists (the build container) this script also checks that each cited file still
@@ -140,6 +140,18 @@ KATS = {
         "max_location": 1.0,
         "after_add_default": [[0.0, 0.0], [0.0, 5.0], [1.0, 10.0]],
         "after_move_key0_to_20": [[0.0, 5.0], [1.0, 10.0], [20.0, 0.0]],
+    },
+    "K15_quat_from_euler": {
+        # A relation, not a literal: the reference asserts that ITS product qz*qy*qx equals nalgebra's closed form, with
+        # UnitQuaternion's PartialEq (all coordinates equal, or all negated).  The oracle restates both sides — quat_mul's
+        # operation order and from_euler_angles (w = cr*cp*cy + sr*sp*sy, i = sr*cp*cy - cr*sp*sy, j = cr*sp*cy + sr*cp*sy,
+        # k = cr*cp*sy - sr*sp*cy with (s, c) = sin_cos(angle * 0.5), nalgebra 0.3x geometry/quaternion_construction.rs, recalled) —
+        # and must reproduce the equality BIT FOR BIT; with these angles the coordinates are 1 and +-4.37e-8 whose last ulps
+        # depend on the order of the sums.
+        "source": "fyrox-math/src/lib.rs:1460-1477",
+        "quote": "UnitQuaternion::from_euler_angles(",
+        "euler": ["pi", "pi", "pi"],
+        "order": "XYZ",
     },
     "K10_handle_numbering": {
         "source": "fyrox-impl/src/scene/graph/mod.rs:408-424",

@@ -506,3 +506,34 @@ def test_lod_filter_prunes_whole_subtrees_and_later_groups_win():
     # a second owner (higher index, so visited later) lists node 2 with a range it falls outside of: the later verdict wins
     og.set_lod_group(6, [(0.5, 1.0, [2])])
     assert og.from_graph_lod(fo, eye, 0.0, 100.0).tolist() == []
+
+
+def test_k15_quat_from_euler_equals_nalgebras_closed_form_bit_for_bit():
+    """fyrox-math/src/lib.rs:1460-1477 asserts quat_from_euler((pi, pi, pi), XYZ) == UnitQuaternion::from_euler_angles(pi, pi, pi)
+    (UnitQuaternion's PartialEq: all coordinates equal, or all negated).  The oracle's product qz * qy * qx (quat_mul's
+    operation order) against nalgebra's closed form restated here in float32, one rounding per operation: the coordinates are
+    1 and +-4.37e-8 and their last ulps differ with the order of the sums — they must agree in every bit."""
+    k = KATS["K15_quat_from_euler"]
+    assert k["euler"] == ["pi", "pi", "pi"] and k["order"] == "XYZ"
+    f32 = np.float32
+    e = np.full(3, np.pi, f32)
+    q = np.zeros(4, f32)
+    L.orc_quat_from_euler_xyz(fp(e), fp(q))
+    libm = C.CDLL("libm.so.6")
+    libm.sinf.restype = libm.cosf.restype = C.c_float
+    libm.sinf.argtypes = libm.cosf.argtypes = [C.c_float]
+    h = f32(np.pi) * f32(0.5)
+    s, c = f32(libm.sinf(float(h))), f32(libm.cosf(float(h)))
+    assert s == 1.0 and c != 0.0  # the case is not degenerate: cos(pi_f32 / 2) is -4.37e-8, not 0
+    sr = sp = sy = s
+    cr = cp = cy = c
+    w = cr * cp * cy + sr * sp * sy
+    i = sr * cp * cy - cr * sp * sy
+    j = cr * sp * cy + sr * cp * sy
+    kk = cr * cp * sy - sr * sp * cy
+    want = np.array([i, j, kk, w], f32)
+    same = (want.view(np.uint32) == q.view(np.uint32)).all()
+    negated = (want.view(np.uint32) == (-q).view(np.uint32)).all()
+    assert same or negated, (q, want)
+    # and the two small coordinates really are different floats (the check can tell summation orders apart)
+    assert abs(q[0]) != abs(q[1])
