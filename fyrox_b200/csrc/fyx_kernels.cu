@@ -444,17 +444,6 @@ __device__ __forceinline__ void update_node(const NodeArrays &a, const uint32_t 
         ly = ld_stream(a.la[1] + slot);
         lz = ld_stream(a.la[2] + slot);
     }
-    // Incremental frames: a node that was not changed itself is most likely clean (static scenery under an unchanged parent) and
-    // will need its stored world box for the cull — ask for it now, next to the parent's flags, instead of after they have said
-    // "clean" (one dependent memory round trip less on the path of 2/3 of a typical frame's nodes; the kernel is latency-bound).
-    // Wasted only on descendants of changed nodes (24 B each).
-    bool have_box = false;
-    if (!UA && WANT_BOX && !(f & F_DIRTY_SELF) && !update_all) {
-        wx = ld_stream(a.wa[0] + slot);
-        wy = ld_stream(a.wa[1] + slot);
-        wz = ld_stream(a.wa[2] + slot);
-        have_box = true;
-    }
     // no parent ⇒ parent values are identity / true (graph/mod.rs:1171-1175,1187-1192,1210-1214)
     const uint32_t pf = (p != FYX_NONE)
                             ? a.flags[p]
@@ -496,7 +485,7 @@ __device__ __forceinline__ void update_node(const NodeArrays &a, const uint32_t 
         st_stream(a.wa[0] + slot, wx);
         st_stream(a.wa[1] + slot, wy);
         st_stream(a.wa[2] + slot, wz);
-    } else if (WANT_BOX && !have_box) {
+    } else if (WANT_BOX) {
         wx = ld_stream(a.wa[0] + slot);
         wy = ld_stream(a.wa[1] + slot);
         wz = ld_stream(a.wa[2] + slot);
@@ -525,7 +514,7 @@ __global__ void __launch_bounds__(kBlock, (VAR & 16) ? 8 : 6) k_update_level(con
     float2 wx = make_float2(0.f, 0.f), wy = wx, wz = wx;
     const bool valid = slot < hi;
     uint32_t mask = 0u, gi_early = 0u;
-    if ((NFT >= 0) && valid) { // static columns: no reason to wait for anything
+    if (UA && (NFT >= 0) && valid) { // static columns: no reason to wait for anything
         mask = a.mask[slot];
         if (!(VAR & 8)) gi_early = a.gidx[slot];
     }
@@ -533,13 +522,14 @@ __global__ void __launch_bounds__(kBlock, (VAR & 16) ? 8 : 6) k_update_level(con
     else pdl_wait();
     if (NFT >= 0) {
         const bool cand = valid && !(nf & F_SKINNED);
+        if (!UA) mask = cand ? a.mask[slot] : 0u;
         const uint32_t vis_bits = (VAR & 32) ? cull_warp_conv<(NFT > 0 ? NFT : 0)>(cand, nf, mask, wx, wy, wz, cp)
                                              : cull_warp<(NFT > 0 ? NFT : 0), PRE>(cand, nf, mask, wx, wy, wz, cp, T);
         if (VAR & 8) { // deferred compaction: one byte per node now, the lists are built by k_compact_vis after the last level
             if (valid) a.vis[slot] = (uint8_t)vis_bits;
             return;
         }
-        const uint32_t gi = gi_early;
+        const uint32_t gi = UA ? gi_early : (vis_bits ? a.gidx[slot] : 0u);
         if (VAR & 2) compact_emit_warp(vis_bits, gi, slot, cp);
         else compact_emit<(NFT > 0 ? NFT : 0)>(vis_bits, gi, slot, cp);
     }
