@@ -1,7 +1,7 @@
 #!/usr/bin/env bash
 # Multi-GPU visit (run with gpurun --gpus N): exchange variants through the parity test, then bench.py under torchrun with the
 # default exchange (peer stores + host segment) and with the round-1 form (NCCL, private host copies) for comparison.
-#   usage: bash tools/gpu_visit_multi.sh <N> <tag> [full|quick]
+#   usage: bash tools/gpu_visit_multi.sh <N> <tag> [full|compare|quick|benchonly]
 set -u
 N=${1:-2}
 TAG=${2:-r02m}
@@ -9,8 +9,10 @@ MODE=${3:-full}
 OUT=gpurun_out
 mkdir -p $OUT
 nvidia-smi -L | head -8
+if [ "$MODE" != "benchonly" ]; then
 echo "[multi] parity test of every exchange variant (2 ranks)"
 timeout 900 python -m pytest tests/test_gpu_multi.py -m gpu -q -x 2>&1 | tail -12 > $OUT/${TAG}_tests.log; tail -12 $OUT/${TAG}_tests.log
+fi
 run() { # name, extra env, extra args
   echo "[multi] bench N=$N $1"
   env $2 timeout 1500 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29517 bench.py --gpus $N --steps 20 --warmup 3 --verbose $3 \
