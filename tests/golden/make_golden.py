@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Emit tests/golden/reference_kats.json: the known-answer vectors of the reference's own unit tests
-for the render-prep path (SURVEY.md §8c K1–K10) and of the animation-sampling step before it (K11–K15), transcribed from the cited test sources.
+for the render-prep path (SURVEY.md §8c K1–K10, K16) and of the animation-sampling step before it (K11–K15), transcribed from the cited test sources.
 
 The reference is Rust (no toolchain here), so the vectors cannot be produced by running it.  When
 /root/reference exists (the build container) this script also checks that each cited file still
@@ -152,6 +152,23 @@ KATS = {
         "quote": "UnitQuaternion::from_euler_angles(",
         "euler": ["pi", "pi", "pi"],
         "order": "XYZ",
+    },
+    "K16_vertex_buffer_attributes": {
+        # the reference's own interleaved test vertex (repr(C): position 3f, tex 2f, tex 2f, normal 3f, tangent 4f, bone weights 4f,
+        # bone indices 4 x u8 = 76 bytes) and what its attribute views read back (test_view_original_equal / test_attribute_view).
+        # Offsets follow from the declared attribute sizes in order (buffer.rs: offset = running sum of size * sizeof(type)).
+        "source": "fyrox-impl/src/scene/mesh/buffer.rs:1687-1828,1882-1901",
+        "quote": "bone_indices: Vector4::new(1, 2, 3, 4),",
+        "stride": 76,
+        "offsets": {"position": 0, "tex_coord": 12, "second_tex_coord": 20, "normal": 28, "tangent": 40, "bone_weights": 56, "bone_indices": 72},
+        "vertices": [
+            {"position": [1.0, 2.0, 3.0], "tex_coord": [0.0, 1.0], "second_tex_coord": [1.0, 0.0], "normal": [0.0, 1.0, 0.0],
+             "tangent": [1.0, 0.0, 0.0, 1.0], "bone_weights": [0.25, 0.25, 0.25, 0.25], "bone_indices": [1, 2, 3, 4]},
+            {"position": [3.0, 2.0, 1.0], "tex_coord": [1.0, 0.0], "second_tex_coord": [1.0, 0.0], "normal": [0.0, 1.0, 0.0],
+             "tangent": [1.0, 0.0, 0.0, 1.0], "bone_weights": [0.25, 0.25, 0.25, 0.25], "bone_indices": [1, 2, 3, 4]},
+            {"position": [1.0, 1.0, 1.0], "tex_coord": [1.0, 1.0], "second_tex_coord": [1.0, 0.0], "normal": [0.0, 1.0, 0.0],
+             "tangent": [1.0, 0.0, 0.0, 1.0], "bone_weights": [0.25, 0.25, 0.25, 0.25], "bone_indices": [1, 2, 3, 4]},
+        ],
     },
     "K10_handle_numbering": {
         "source": "fyrox-impl/src/scene/graph/mod.rs:408-424",

@@ -873,3 +873,45 @@ def test_dfs_order_quirk_is_reproduced_exactly(ctx):
     A, Ao = ctx.get_world_aabbs(meshes), og.world_bounding_boxes(meshes)
     early = np.arange(n_units) % 2 == 1
     assert (A[early] == Ao[early]).all() and not (A[~early] == Ao[~early]).all()
+
+
+def test_k16_reference_vertex_buffer_layout_through_the_c_abi(ctx):
+    """tests/golden K16 (fyrox-impl/src/scene/mesh/buffer.rs:1687-1828): the reference's own 76-byte interleaved test vertex handed to
+    fyx_add_skinned_surface with a fyx_vertex_layout that names its offsets (position 0, normal 28, bone weights 56, u8 bone indices
+    72).  Bones 0..5 translate by (k, 0, 0): every vertex has indices (1, 2, 3, 4) and weights 0.25, so it must come out at
+    position + 2.5 on x (exact in f32) with its normal unchanged — the same check the oracle's reader passes on the CPU
+    (tests/test_oracle_kat.py::test_k16_...)."""
+    import json
+    import os
+
+    k = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_kats.json")))["K16_vertex_buffer_attributes"]
+    off = k["offsets"]
+    nv = len(k["vertices"])
+    rec = np.zeros((nv, k["stride"]), np.uint8)
+    for i, v in enumerate(k["vertices"]):
+        for name in ("position", "tex_coord", "second_tex_coord", "normal", "tangent", "bone_weights"):
+            a = np.asarray(v[name], np.float32)
+            rec[i, off[name]:off[name] + 4 * a.size] = a.view(np.uint8)
+        rec[i, off["bone_indices"]:off["bone_indices"] + 4] = np.asarray(v["bone_indices"], np.uint8)
+    nb = 6
+    n = nb + 2  # root, six bones, the mesh
+    parent = np.array([NONE] + [0] * (n - 1), np.uint32)
+    flags = np.full(n, fb.NODE_DEFAULT, np.uint32)
+    flags[n - 1] |= fb.NODE_RENDERABLE
+    local = np.tile(np.eye(4, dtype=np.float32).reshape(16), (n, 1))
+    for b in range(nb):
+        local[1 + b, 12] = float(b)
+    bones = np.arange(1, nb + 1, dtype=np.uint32)
+    ib = np.tile(np.eye(4, dtype=np.float32).reshape(16), (nb, 1))
+    ctx.set_topology(parent, flags)
+    ctx.set_local_matrices(local)
+    layout = fb._lib.fyx_vertex_layout(k["stride"], off["position"], off["normal"], off["bone_weights"], off["bone_indices"])
+    sid = ctx.add_skinned_surface(n - 1, bones, ib, rec.reshape(-1), layout=layout)
+    ctx.update_transforms(fb.UPDATE_ALL)
+    ctx.build_palettes()
+    ctx.skin()
+    pos, nrm = ctx.get_skinned(sid)
+    for i, v in enumerate(k["vertices"]):
+        want = np.asarray(v["position"], np.float32) + np.array([2.5, 0.0, 0.0], np.float32)
+        assert np.array_equal(pos[i], want), (i, pos[i], want)
+        assert np.array_equal(nrm[i], np.asarray(v["normal"], np.float32)), (i, nrm[i])

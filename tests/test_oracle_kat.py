@@ -537,3 +537,37 @@ def test_k15_quat_from_euler_equals_nalgebras_closed_form_bit_for_bit():
     assert same or negated, (q, want)
     # and the two small coordinates really are different floats (the check can tell summation orders apart)
     assert abs(q[0]) != abs(q[1])
+
+
+def test_k16_vertex_buffer_attributes_are_read_where_the_reference_puts_them():
+    """fyrox-impl/src/scene/mesh/buffer.rs:1687-1828: the reference's interleaved test vertex (76 bytes) and the values its attribute
+    views return.  The oracle's vertex reader (the layout the C ABI's fyx_vertex_layout mirrors) must pick position, normal, bone
+    weights and the u8 bone indices from the same offsets: skinned with a palette whose bone b translates by (b, 0, 0), every vertex
+    comes out at position + 0.25 * (1 + 2 + 3 + 4) on x — exact in f32 for these values — and the normal unchanged."""
+    k = KATS["K16_vertex_buffer_attributes"]
+    off = k["offsets"]
+    n = len(k["vertices"])
+    buf = np.zeros(n * k["stride"], np.uint8)
+    for i, v in enumerate(k["vertices"]):
+        rec = buf[i * k["stride"]:(i + 1) * k["stride"]]
+        for name in ("position", "tex_coord", "second_tex_coord", "normal", "tangent", "bone_weights"):
+            a = np.asarray(v[name], np.float32)
+            rec[off[name]:off[name] + 4 * a.size] = a.view(np.uint8)
+        rec[off["bone_indices"]:off["bone_indices"] + 4] = np.asarray(v["bone_indices"], np.uint8)
+    sizes = {"position": 12, "tex_coord": 8, "second_tex_coord": 8, "normal": 12, "tangent": 16, "bone_weights": 16, "bone_indices": 4}
+    run = 0
+    for name in ("position", "tex_coord", "second_tex_coord", "normal", "tangent", "bone_weights", "bone_indices"):
+        assert off[name] == run  # running sum of the declared attribute sizes, as VertexBuffer::new lays them out
+        run += sizes[name]
+    assert run == k["stride"]
+    layout = ob.VertexLayout(k["stride"], off["position"], off["normal"], off["bone_weights"], off["bone_indices"])
+    pal = np.zeros((6, 16), np.float32)
+    for b in range(6):
+        pal[b] = ob.translation(float(b), 0.0, 0.0)
+    pos = np.zeros((n, 3), np.float32)
+    nrm = np.zeros((n, 3), np.float32)
+    L.orc_skin_vertices(fp(pal), n, buf.ctypes.data_as(C.c_void_p), C.byref(layout), fp(pos), fp(nrm))
+    for i, v in enumerate(k["vertices"]):
+        want = np.asarray(v["position"], np.float32) + np.array([2.5, 0.0, 0.0], np.float32)
+        assert np.array_equal(pos[i], want), (i, pos[i], want)
+        assert np.array_equal(nrm[i], np.asarray(v["normal"], np.float32)), (i, nrm[i])
